@@ -1,0 +1,355 @@
+/* oracle/nuts_oracle.c -- TEST INFRASTRUCTURE ONLY (see nuts_oracle.h).
+ *
+ * Plain-C restatement of the NUTS 3.3.3 per-message byte transform and
+ * fan-out.  It is the checker the CUDA path is compared with, and the "port"
+ * CPU baseline of bench.py; the product never links or loads it.
+ *
+ * Pinned by tests/test_oracle_golden.py against tests/golden/ (minted from the
+ * unmodified reference) and by tests/test_oracle_vs_ref.py against
+ * oracle/_ref/libnutsref.so when that was built.
+ *
+ * c: = /root/reference/nuts333.c, h: = /root/reference/nuts333.h
+ */
+#include "nuts_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+/* h:237-255 -- the 21 two-letter commands, in the reference's order.  The
+ * ANSI strings are generated instead of listed: entries 0-4 are ESC[<d>m with
+ * d = 0,1,4,5,7; entries 5-12 are ESC[3<d>m; entries 13-20 are ESC[4<d>m. */
+static const char orc_codes[21][3] = {
+    "RS","OL","UL","LI","RV",
+    "FK","FR","FG","FY","FB","FM","FT","FW",
+    "BK","BR","BG","BY","BB","BM","BT","BW"
+};
+
+static size_t orc_ansi(int k, uint8_t *out)
+{
+    static const char attr[5] = { '0','1','4','5','7' };
+    size_t o = 0;
+    out[o++] = 0x1b; out[o++] = '[';
+    if (k < 5) out[o++] = (uint8_t)attr[k];
+    else { out[o++] = (uint8_t)(k < 13 ? '3' : '4'); out[o++] = (uint8_t)('0' + (k - 5) % 8); }
+    out[o++] = 'm';
+    return o;
+}
+
+/* The strncmp(str,colcom[i],2) scan of c:1341-1352: both letters must lie
+ * inside the string (strncmp stops at the terminating NUL). */
+static int orc_code_at(const uint8_t *s, size_t n, size_t j)
+{
+    if (j + 1 >= n) return -1;
+    for (int k = 0; k < 21; ++k)
+        if (s[j] == (uint8_t)orc_codes[k][0] && s[j + 1] == (uint8_t)orc_codes[k][1]) return k;
+    return -1;
+}
+
+/* c:1291-1366, USER_TYPE recipient.  The reference's 1000-byte staging buffer
+ * and its flush points (c:1317,1338,1359) only split the stream across write()
+ * calls, so they do not appear here. */
+size_t orc_render(const uint8_t *s, size_t n, int colour, uint8_t *out)
+{
+    size_t i = 0, o = 0;
+    while (i < n) {
+        uint8_t c = s[i];
+        if (c == '\n') {                               /* c:1316-1326 */
+            if (colour) o += orc_ansi(0, out + o);
+            out[o++] = '\n'; out[o++] = '\r';
+            ++i;
+        } else if (c == '/' && i + 1 < n && s[i + 1] == '~') {
+            ++i;                                       /* c:1330: slash dropped */
+        } else if (c == '~' && i > 0 && s[i - 1] == '/') {
+            out[o++] = '~'; ++i;                       /* c:1331-1333 */
+        } else if (c == '~') {                         /* c:1337-1354 */
+            int k = orc_code_at(s, n, i + 1);
+            if (k >= 0) { if (colour) o += orc_ansi(k, out + o); i += 3; }
+            else { out[o++] = '~'; ++i; }
+        } else {
+            out[o++] = c; ++i;                         /* c:1355 */
+        }
+    }
+    if (colour) o += orc_ansi(0, out + o);             /* c:1365 */
+    return o;
+}
+
+static uint8_t orc_lower(uint8_t b) { return (b >= 'A' && b <= 'Z') ? (uint8_t)(b + 32) : b; }
+
+/* memmem on a lower-cased haystack; needle of length 0 matches (strstr). */
+static int orc_has(const uint8_t *h, size_t n, const uint8_t *w, size_t m)
+{
+    if (m == 0) return 1;
+    if (m > n) return 0;
+    for (size_t i = 0; i + m <= n; ++i) {
+        size_t j = 0;
+        while (j < m && orc_lower(h[i + j]) == w[j]) ++j;
+        if (j == m) return 1;
+    }
+    return 0;
+}
+
+/* c:2540-2559: lower-case copy (C locale: only A-Z move, c:2657), then strstr
+ * per list word until the entry that starts with '*'. */
+int orc_contains_swearing(const uint8_t *s, size_t n, const char *const *words)
+{
+    if (!words) return 0;
+    for (size_t w = 0; words[w] && words[w][0] != '*'; ++w)
+        if (orc_has(s, n, (const uint8_t *)words[w], strlen(words[w]))) return 1;
+    return 0;
+}
+
+/* c:2563-2583.  After a hit the code pointer moves on ONE byte and the scan
+ * over the remaining table entries carries on from there (the inner
+ * 'continue' belongs to the for), hence "~FBK" counts 2. */
+int orc_colour_com_count(const uint8_t *s, size_t n)
+{
+    size_t p = 0; int cnt = 0;
+    while (p < n) {
+        if (s[p] != '~') { ++p; continue; }
+        ++p;
+        for (int k = 0; k < 21; ++k)
+            if (p + 1 < n && s[p] == (uint8_t)orc_codes[k][0] && s[p + 1] == (uint8_t)orc_codes[k][1]) {
+                ++cnt; ++p;
+            }
+    }
+    return cnt;
+}
+
+/* c:2588-2610: drops ~XX for known XX, everything else (incl. '/') verbatim. */
+size_t orc_colour_com_strip(const uint8_t *s, size_t n, uint8_t *out)
+{
+    size_t p = 0, o = 0;
+    while (p < n) {
+        if (s[p] == '~' && orc_code_at(s, n, p + 1) >= 0) p += 3;
+        else out[o++] = s[p++];
+    }
+    return o;
+}
+
+static int orc_isspace(uint8_t b)
+{
+    return b == ' ' || (b >= '\t' && b <= '\r');       /* C-locale isspace */
+}
+
+/* c:338-342 / c:357-361: fscanf("%s") then while(!feof): a token is tested only
+ * if the scan that produced it stopped on a whitespace byte, i.e. the token
+ * does not run into end-of-file. */
+size_t orc_ban_tokens(const uint8_t *f, size_t n, uint32_t *tok_off, uint32_t *tok_len, size_t cap)
+{
+    size_t p = 0, cnt = 0;
+    for (;;) {
+        while (p < n && orc_isspace(f[p])) ++p;
+        if (p >= n) break;                              /* EOF while skipping: feof set */
+        size_t b = p;
+        while (p < n && !orc_isspace(f[p])) ++p;
+        if (p >= n) break;                              /* token hit EOF: never tested */
+        if (cnt < cap) { tok_off[cnt] = (uint32_t)b; tok_len[cnt] = (uint32_t)(p - b); }
+        ++cnt;
+    }
+    return cnt;
+}
+
+/* A token is handed to strstr/strcmp as a C string: it ends at an embedded NUL. */
+static size_t orc_cstr_len(const uint8_t *p, size_t n)
+{
+    const uint8_t *z = memchr(p, 0, n);
+    return z ? (size_t)(z - p) : n;
+}
+
+static int orc_ban_scan(const uint8_t *f, size_t n, const uint8_t *q, size_t qn, int substring)
+{
+    size_t p = 0;
+    for (;;) {
+        while (p < n && orc_isspace(f[p])) ++p;
+        if (p >= n) return 0;
+        size_t b = p;
+        while (p < n && !orc_isspace(f[p])) ++p;
+        if (p >= n) return 0;
+        size_t m = orc_cstr_len(f + b, p - b);
+        if (substring) {                                /* c:340 strstr(site,line) */
+            if (m == 0) return 1;
+            for (size_t i = 0; i + m <= qn; ++i)
+                if (memcmp(q + i, f + b, m) == 0) return 1;
+        } else if (m == qn && memcmp(q, f + b, m) == 0) return 1;   /* c:359 */
+    }
+}
+
+int orc_site_banned(const uint8_t *f, size_t n, int present, const uint8_t *site, size_t sn)
+{
+    if (!present) return 0;                             /* c:337 */
+    return orc_ban_scan(f, n, site, orc_cstr_len(site, sn), 1);
+}
+
+int orc_user_banned(const uint8_t *f, size_t n, int present, const uint8_t *name, size_t nn)
+{
+    if (!present) return 0;                             /* c:356 */
+    return orc_ban_scan(f, n, name, orc_cstr_len(name, nn), 0);
+}
+
+/* ---- recipient filter ---------------------------------------------------- */
+
+int orc_delivers(uint8_t kind, int32_t target, int32_t except_user, uint8_t of,
+                 int32_t u, int32_t u_room, uint8_t uf, uint8_t u_level)
+{
+    switch (kind) {
+    case ORC_OP_USER:                                   /* c:1298: NULL user = no-op */
+        return target >= 0 && u == target;
+    case ORC_OP_ROOM:                                   /* c:1410-1415 */
+        if (uf & ORC_UF_LOGIN) return 0;
+        if (u_room < 0) return 0;
+        if (target >= 0 && u_room != target) return 0;
+        if ((uf & ORC_UF_IGNALL) && !(of & ORC_OF_FORCE_LISTEN)) return 0;
+        if ((uf & ORC_UF_IGNSHOUT) && (of & ORC_OF_SHOUT)) return 0;
+        return u != except_user;
+    case ORC_OP_LEVEL:                                  /* c:1379-1383 */
+        if (u == except_user || (uf & ORC_UF_LOGIN) || (uf & ORC_UF_CLONE)) return 0;
+        return (of & ORC_OF_ABOVE) ? (int32_t)u_level >= target : (int32_t)u_level <= target;
+    }
+    return 0;
+}
+
+static int orc_live(int64_t i, const uint8_t *of, const int32_t *gate, const uint8_t *verdict)
+{
+    if (!gate || gate[i] < 0) return 1;
+    int v = verdict[gate[i]] != 0;
+    return (of[i] & ORC_OF_GATE_IF_SET) ? v : !v;
+}
+
+uint64_t orc_fnv1a(const uint8_t *p, size_t n)
+{
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+
+/* ---- batch drivers ------------------------------------------------------- */
+
+void orc_streams_free(orc_streams *s)
+{
+    if (!s) return;
+    free(s->off); free(s->bytes); free(s->n_deliveries);
+    s->off = NULL; s->bytes = NULL; s->n_deliveries = NULL;
+}
+
+int orc_write_batch(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
+                    const uint8_t *kind, const int32_t *target,
+                    const int32_t *except_user, const uint8_t *of,
+                    const int32_t *gate, const uint8_t *verdict,
+                    int32_t n_users, const int32_t *room, const uint8_t *uf,
+                    const uint8_t *ul,
+                    const int32_t *only, int32_t n_only, orc_streams *out)
+{
+    uint8_t *want = NULL;
+    if (only) {
+        want = calloc((size_t)n_users + 1, 1);
+        if (!want) return -1;
+        for (int32_t k = 0; k < n_only; ++k)
+            if (only[k] >= 0 && only[k] < n_users) want[only[k]] = 1;
+    }
+    size_t maxn = 0;
+    for (int64_t i = 0; i < n_ops; ++i) {
+        size_t n = (size_t)(toff[i + 1] - toff[i]);
+        if (n > maxn) maxn = n;
+    }
+    uint8_t *ron = malloc(6 * maxn + 8), *roff = malloc(2 * maxn + 8);
+    out->n_users = n_users;
+    out->off = calloc((size_t)n_users + 1, sizeof(uint64_t));
+    out->n_deliveries = calloc((size_t)n_users + 1, sizeof(uint64_t));
+    uint64_t *cur = calloc((size_t)n_users + 1, sizeof(uint64_t));
+    out->bytes = NULL;
+    if (!ron || !roff || !out->off || !out->n_deliveries || !cur) {
+        free(ron); free(roff); free(cur); free(want); orc_streams_free(out); return -1;
+    }
+    /* two passes in the reference's order: ops outer, user list inner (c:1409) */
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int64_t i = 0; i < n_ops; ++i) {
+            if (!orc_live(i, of, gate, verdict)) continue;
+            const uint8_t *s = text + toff[i];
+            size_t n = (size_t)(toff[i + 1] - toff[i]);
+            size_t lon = 0, loff = 0; int have_on = 0, have_off = 0;
+            int32_t u0 = 0, u1 = n_users;
+            if (kind[i] == ORC_OP_USER) {
+                if (target[i] < 0 || target[i] >= n_users) continue;
+                u0 = target[i]; u1 = u0 + 1;
+            }
+            for (int32_t u = u0; u < u1; ++u) {
+                if (want && !want[u]) continue;
+                if (!orc_delivers(kind[i], target[i], except_user[i], of[i], u, room[u], uf[u], ul[u]))
+                    continue;
+                int c = (uf[u] & ORC_UF_COLOUR) != 0;
+                if (c && !have_on)  { lon  = orc_render(s, n, 1, ron);  have_on = 1; }
+                if (!c && !have_off){ loff = orc_render(s, n, 0, roff); have_off = 1; }
+                size_t len = c ? lon : loff;
+                if (pass == 0) { out->off[u + 1] += len; out->n_deliveries[u] += 1; }
+                else { memcpy(out->bytes + cur[u], c ? ron : roff, len); cur[u] += len; }
+            }
+        }
+        if (pass == 0) {
+            for (int32_t u = 0; u < n_users; ++u) out->off[u + 1] += out->off[u];
+            for (int32_t u = 0; u < n_users; ++u) cur[u] = out->off[u];
+            out->bytes = malloc(out->off[n_users] + 1);
+            if (!out->bytes) { free(ron); free(roff); free(cur); free(want); orc_streams_free(out); return -1; }
+        }
+    }
+    free(ron); free(roff); free(cur); free(want);
+    return 0;
+}
+
+int64_t orc_write_batch_count(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
+                    const uint8_t *kind, const int32_t *target,
+                    const int32_t *except_user, const uint8_t *of,
+                    const int32_t *gate, const uint8_t *verdict,
+                    int32_t n_users, const int32_t *room, const uint8_t *uf,
+                    const uint8_t *ul, uint64_t *out_bytes)
+{
+    /* Faithful cost model: the reference renders the string again for EVERY
+     * recipient (write_user is called per user, c:1427), so does this loop. */
+    size_t maxn = 0;
+    for (int64_t i = 0; i < n_ops; ++i) {
+        size_t n = (size_t)(toff[i + 1] - toff[i]);
+        if (n > maxn) maxn = n;
+    }
+    uint8_t *buf = malloc(6 * maxn + 8);
+    if (!buf) return -1;
+    int64_t deliveries = 0; uint64_t bytes = 0; volatile uint8_t sink = 0;
+    for (int64_t i = 0; i < n_ops; ++i) {
+        if (!orc_live(i, of, gate, verdict)) continue;
+        const uint8_t *s = text + toff[i];
+        size_t n = (size_t)(toff[i + 1] - toff[i]);
+        int32_t u0 = 0, u1 = n_users;
+        if (kind[i] == ORC_OP_USER) {
+            if (target[i] < 0 || target[i] >= n_users) continue;
+            u0 = target[i]; u1 = u0 + 1;
+        }
+        for (int32_t u = u0; u < u1; ++u) {
+            if (!orc_delivers(kind[i], target[i], except_user[i], of[i], u, room[u], uf[u], ul[u]))
+                continue;
+            size_t len = orc_render(s, n, (uf[u] & ORC_UF_COLOUR) != 0, buf);
+            sink ^= buf[len ? len - 1 : 0];
+            bytes += len; ++deliveries;
+        }
+    }
+    free(buf);
+    if (out_bytes) *out_bytes = bytes;
+    return deliveries;
+}
+
+void orc_contains_swearing_batch(int64_t n, const uint8_t *text, const uint64_t *off,
+                                 const char *const *words, uint8_t *verdict)
+{
+    for (int64_t i = 0; i < n; ++i)
+        verdict[i] = (uint8_t)orc_contains_swearing(text + off[i], (size_t)(off[i + 1] - off[i]), words);
+}
+
+void orc_site_banned_batch(const uint8_t *f, size_t fn, int present, int64_t n,
+                           const uint8_t *text, const uint64_t *off, uint8_t *verdict)
+{
+    for (int64_t i = 0; i < n; ++i)
+        verdict[i] = (uint8_t)orc_site_banned(f, fn, present, text + off[i], (size_t)(off[i + 1] - off[i]));
+}
+
+void orc_user_banned_batch(const uint8_t *f, size_t fn, int present, int64_t n,
+                           const uint8_t *text, const uint64_t *off, uint8_t *verdict)
+{
+    for (int64_t i = 0; i < n; ++i)
+        verdict[i] = (uint8_t)orc_user_banned(f, fn, present, text + off[i], (size_t)(off[i + 1] - off[i]));
+}
