@@ -1,0 +1,204 @@
+/* nutsb200.h -- C-ABI of the B200-native NUTS 3.3.3 message path.
+ *
+ * The reference (ToKe79/nuts333) has no plugin/FFI layer: the path is reached by
+ * direct C calls inside one translation unit.  The boundary a replacement must
+ * honour is the function surface the reference declares in nuts333.h:
+ *
+ *     void write_user(UR_OBJECT user, char *str);                        nuts333.c:1291
+ *     void write_room(RM_OBJECT rm, char *str);                          nuts333.c:1390
+ *     void write_room_except(RM_OBJECT rm, char *str, UR_OBJECT user);   nuts333.c:1401
+ *     void write_level(int level, int above, char *str, UR_OBJECT user); nuts333.c:1372
+ *     int  contains_swearing(char *str);                                 nuts333.c:2540
+ *     int  site_banned(char *site);                                      nuts333.c:330
+ *     int  user_banned(char *name);                                      nuts333.c:349
+ *
+ * This header exposes that surface in three tiers, all `extern "C"`, plain
+ * pointers and sizes only:
+ *
+ *   1. queue tier  (nutsb_q_*, nutsb_flush): one call per reference call, user /
+ *      room passed as their index in the reference's lists.  str is copied on
+ *      enqueue (callers overwrite the global text[] right after, c:4094-4098).
+ *      INTEGRATION.md shows the 7 one-line bodies that bind nuts333.c to it.
+ *   2. batch tier, host buffers (nutsb_write_batch, nutsb_*_batch): SoA batches
+ *      in host memory, results in library-owned pinned host memory.
+ *   3. batch tier, device buffers (*_dev): the same on buffers already in HBM.
+ *
+ * Semantics are bit-exact with nuts333.c for USER_TYPE recipients; the clone
+ * relay (c:1416-1426) and netlink framing (c:1299-1307) are not implemented and
+ * users flagged so are rejected with NUTSB_E_UNSUPPORTED.
+ *
+ * Errors: every entry point returns 0 or a negative NUTSB_E_* code and never
+ * aborts the host; on error outputs are left untouched.  One context per host
+ * thread, one context per GPU; not async-signal-safe (the reference enters its
+ * write layer from SIGALRM, c:7721 -- a binding must defer those to the main
+ * loop).  There is NO CPU fallback: without a CUDA device nutsb_create fails.
+ */
+#ifndef NUTSB200_H
+#define NUTSB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NUTSB_VERSION 0x000100
+
+enum {
+    NUTSB_OK            =  0,
+    NUTSB_E_INVAL       = -1,  /* bad argument (NULL, negative count, offsets not monotone) */
+    NUTSB_E_NOMEM       = -2,  /* host or device allocation failed                          */
+    NUTSB_E_CUDA        = -3,  /* CUDA runtime error, see nutsb_last_error()                */
+    NUTSB_E_UNSUPPORTED = -4,  /* clone / remote recipients              */
+    NUTSB_E_RANGE       = -5,  /* string longer than NUTSB_MAX_TEXT, index out of range     */
+    NUTSB_E_STATE       = -6   /* call order (e.g. write batch before nutsb_set_users)      */
+};
+
+/* text[ARR_SIZE*2] is the largest string the reference can pass (nuts333.h:280). */
+#define NUTSB_MAX_TEXT 2000
+/* line[82] in site_banned/user_banned (c:334,353): longer tokens overflow there. */
+#define NUTSB_MAX_BAN_TOKEN 81
+
+/* recipient flags (nuts333.h:67-85 fields actually read on the path) */
+#define NUTSB_UF_COLOUR   0x01u  /* user->colour != 0            */
+#define NUTSB_UF_LOGIN    0x02u  /* user->login  != 0            */
+#define NUTSB_UF_IGNALL   0x04u  /* user->ignall                 */
+#define NUTSB_UF_IGNSHOUT 0x08u  /* user->ignshout               */
+#define NUTSB_UF_CLONE    0x10u  /* type==CLONE_TYPE  (rejected) */
+#define NUTSB_UF_REMOTE   0x20u  /* type==REMOTE_TYPE (rejected) */
+
+/* op kinds: one op == one call of the reference's write surface */
+#define NUTSB_OP_USER  0  /* write_user(target, str)                                   */
+#define NUTSB_OP_ROOM  1  /* write_room_except(target, str, except); target -1 = NULL  */
+#define NUTSB_OP_LEVEL 2  /* write_level(target, above, str, except)                   */
+
+/* op flags: the globals the reference reads inside the call */
+#define NUTSB_OF_FORCE_LISTEN 0x01u  /* force_listen (nuts333.h:293, c:1413)           */
+#define NUTSB_OF_SHOUT        0x02u  /* com_num==SHOUT || com_num==SEMOTE (c:1414)     */
+#define NUTSB_OF_ABOVE        0x04u  /* write_level's `above`                          */
+#define NUTSB_OF_GATE_IF_SET  0x08u  /* with gate>=0: live iff verdict[gate]!=0,
+                                        else live iff verdict[gate]==0 (say(), c:4091) */
+
+typedef struct nutsb_ctx nutsb_ctx;
+
+/* A batch of write calls, in call order.  All arrays have n_ops entries except
+ * text_off (n_ops+1, monotone, text_off[0] may be non-zero).  Strings need no
+ * NUL terminator and must not contain NUL.  gate/verdict may be NULL. */
+typedef struct nutsb_ops {
+    int64_t         n_ops;
+    const uint8_t  *text;
+    const uint64_t *text_off;
+    const uint8_t  *kind;         /* NUTSB_OP_*                                         */
+    const int32_t  *target;       /* user index | room index (-1 all rooms) | level     */
+    const int32_t  *except_user;  /* -1 = none                                          */
+    const uint8_t  *flags;        /* NUTSB_OF_*                                         */
+    const int32_t  *gate;         /* index into verdict, -1 = unconditional; or NULL    */
+    const uint8_t  *verdict;      /* swear verdicts the gates refer to; or NULL         */
+} nutsb_ops;
+
+/* Per-user socket streams: user u receives bytes[off[u] .. off[u+1]) -- exactly
+ * what the reference would have written to user u's socket over the batch, in
+ * call order.  Pointers are owned by the context and stay valid until the next
+ * write batch / flush / destroy on it. */
+typedef struct nutsb_streams {
+    int64_t         n_users;
+    uint64_t        total_bytes;
+    uint64_t        n_deliveries;   /* (op, recipient) pairs rendered                    */
+    const uint64_t *off;            /* n_users + 1                                       */
+    const uint8_t  *bytes;
+    int32_t         on_device;      /* 1: off/bytes are device pointers                  */
+} nutsb_streams;
+
+/* Device-side timings of the last write batch, CUDA events on the context's
+ * stream (ms).  Filled only after nutsb_set_profiling(ctx, 1). */
+typedef struct nutsb_timing {
+    float plan_ms;       /* measure, bucket, prefix, events, offsets                    */
+    float fanout_ms;     /* render + fan-out kernel (the dominant kernel)               */
+    float direct_ms;     /* write_user ops rendered straight into the streams           */
+    float total_ms;      /* first kernel to last kernel, incl. the two size read-backs  */
+    float h2d_ms, d2h_ms;
+    uint64_t fanout_bytes_in, fanout_bytes_out;   /* algorithmic bytes of the fan-out kernel */
+    uint32_t launches;   /* kernels launched by the last batch call                     */
+    uint32_t fanout_launches;
+} nutsb_timing;
+
+int         nutsb_version(void);
+const char *nutsb_strerror(int code);
+const char *nutsb_last_error(const nutsb_ctx *ctx);
+
+int  nutsb_create(nutsb_ctx **out, int device);
+void nutsb_destroy(nutsb_ctx *ctx);
+int  nutsb_set_profiling(nutsb_ctx *ctx, int on);
+int  nutsb_get_timing(const nutsb_ctx *ctx, nutsb_timing *out);
+/* Use the caller's CUDA stream (a cudaStream_t) instead of the context's own. */
+int  nutsb_set_stream(nutsb_ctx *ctx, void *cuda_stream);
+
+/* ---- tables ------------------------------------------------------------- */
+
+/* swear_words[] (nuts333.h:275-277): list ends at the first entry starting
+ * with '*' or at a NULL pointer.  Default = the stock list. */
+int nutsb_set_swear_words(nutsb_ctx *ctx, const char *const *words);
+
+/* Raw FILE BYTES of datafiles/siteban and datafiles/userban; the library
+ * applies the fscanf("%s")/feof tokenizer of c:338-342 (a last token not
+ * followed by whitespace is never tested).  NULL = file missing (verdict 0). */
+int nutsb_set_ban_files(nutsb_ctx *ctx, const void *siteban, size_t siteban_len,
+                        const void *userban, size_t userban_len);
+
+/* Population, index = position in the reference's user list (creation order,
+ * c:2683-2691).  room[u] in [0,n_rooms) or -1 (user->room==NULL). */
+int nutsb_set_users(nutsb_ctx *ctx, int32_t n_users, int32_t n_rooms, const int32_t *room,
+                    const uint8_t *flags, const uint8_t *level);
+
+/* ---- batch tier --------------------------------------------------------- */
+
+/* write_user / write_room[_except] / write_level, batched.  Host variant:
+ * ops in host memory, streams returned in pinned host memory. */
+int nutsb_write_batch(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_streams *out);
+/* Device variant: every pointer in ops is a device pointer; streams stay in HBM. */
+int nutsb_write_batch_dev(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_streams *out);
+
+/* contains_swearing / site_banned / user_banned over n packed strings
+ * (bytes + off[n+1]); verdict[n] gets 0/1.  *_dev: device pointers. */
+int nutsb_contains_swearing_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes,
+                                  const uint64_t *off, uint8_t *verdict);
+int nutsb_contains_swearing_batch_dev(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes,
+                                      const uint64_t *off, uint8_t *verdict);
+int nutsb_site_banned_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes,
+                            const uint64_t *off, uint8_t *verdict);
+int nutsb_site_banned_batch_dev(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes,
+                                const uint64_t *off, uint8_t *verdict);
+int nutsb_user_banned_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes,
+                            const uint64_t *off, uint8_t *verdict);
+int nutsb_user_banned_batch_dev(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes,
+                                const uint64_t *off, uint8_t *verdict);
+
+/* Position-weighted 64-bit digest of every user's stream, computed on the
+ * device from the last write batch: h = fold(h*0x100000001b3 + byte) over the
+ * stream, h0 = 0xcbf29ce484222325.  digest[n_users] is a HOST array. */
+int nutsb_stream_digests(nutsb_ctx *ctx, uint64_t *digest);
+
+/* ---- queue tier: the reference's call surface, one call each ------------ */
+
+int nutsb_q_write_user(nutsb_ctx *ctx, int32_t user, const char *str);            /* c:1291 */
+int nutsb_q_write_room(nutsb_ctx *ctx, int32_t room, const char *str,
+                       int force_listen, int shout);                              /* c:1390 */
+int nutsb_q_write_room_except(nutsb_ctx *ctx, int32_t room, const char *str, int32_t except_user,
+                              int force_listen, int shout);                       /* c:1401 */
+int nutsb_q_write_level(nutsb_ctx *ctx, int level, int above, const char *str,
+                        int32_t except_user);                                     /* c:1372 */
+int64_t nutsb_q_pending(const nutsb_ctx *ctx);
+/* Runs everything queued since the last flush; the host then write()s each
+ * user's stream to its socket. */
+int nutsb_flush(nutsb_ctx *ctx, nutsb_streams *out);
+
+/* Synchronous single-item verdicts (the callers branch on them immediately,
+ * c:4091, c:279, c:1496): one tiny launch each, latency-bound by design. */
+int nutsb_contains_swearing(nutsb_ctx *ctx, const char *str);                     /* c:2540 */
+int nutsb_site_banned(nutsb_ctx *ctx, const char *site);                          /* c:330  */
+int nutsb_user_banned(nutsb_ctx *ctx, const char *name);                          /* c:349  */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NUTSB200_H */

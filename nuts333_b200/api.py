@@ -1,0 +1,338 @@
+"""Host-side mirror of the reference's write surface over the C-ABI (include/nutsb200.h).
+
+`Context` is a thin ctypes binding of libnutsb200.so; `Talker` keeps the reference's
+own names and ambient globals (nuts333.c:1291-1429, 2540, 330, 349; nuts333.h:201,293):
+
+    t = Talker(ctx)
+    t.force_listen = 1                      # h:293
+    t.com_num = SHOUT                       # h:201
+    t.write_room_except(room, text, user)   # c:1401
+    streams = t.flush()                     # per-user socket bytes
+
+Everything here is plumbing: the work happens in the CUDA kernels behind the C-ABI.
+There is no CPU fallback -- constructing a Context without a usable GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+OP_USER, OP_ROOM, OP_LEVEL = 0, 1, 2
+OF_FORCE_LISTEN, OF_SHOUT, OF_ABOVE, OF_GATE_IF_SET = 1, 2, 4, 8
+UF_COLOUR, UF_LOGIN, UF_IGNALL, UF_IGNSHOUT, UF_CLONE, UF_REMOTE = 1, 2, 4, 8, 16, 32
+MAX_TEXT = 2000
+
+# com_num values that matter on the path (enum comvals, nuts333.h:181-183)
+SAY, SHOUT, SEMOTE = 3, 4, 7
+# user levels (nuts333.h: level_name[])
+NEW, USER, WIZ, ARCH, GOD = 0, 1, 2, 3, 4
+
+E_INVAL, E_NOMEM, E_CUDA, E_UNSUPPORTED, E_RANGE, E_STATE = -1, -2, -3, -4, -5, -6
+
+u8p = C.POINTER(C.c_uint8)
+u64p = C.POINTER(C.c_uint64)
+i32p = C.POINTER(C.c_int32)
+
+
+class NutsbError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__(f"nutsb error {code}: {detail}")
+
+
+class _Ops(C.Structure):
+    _fields_ = [("n_ops", C.c_int64), ("text", C.c_void_p), ("text_off", C.c_void_p), ("kind", C.c_void_p),
+                ("target", C.c_void_p), ("except_user", C.c_void_p), ("flags", C.c_void_p),
+                ("gate", C.c_void_p), ("verdict", C.c_void_p)]
+
+
+class _Streams(C.Structure):
+    _fields_ = [("n_users", C.c_int64), ("total_bytes", C.c_uint64), ("n_deliveries", C.c_uint64),
+                ("off", C.c_void_p), ("bytes", C.c_void_p), ("on_device", C.c_int32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("plan_ms", C.c_float), ("fanout_ms", C.c_float), ("direct_ms", C.c_float),
+                ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("fanout_bytes_in", C.c_uint64), ("fanout_bytes_out", C.c_uint64),
+                ("launches", C.c_uint32), ("fanout_launches", C.c_uint32)]
+
+
+EXPORTS = [
+    "nutsb_version", "nutsb_strerror", "nutsb_last_error", "nutsb_create", "nutsb_destroy",
+    "nutsb_set_profiling", "nutsb_get_timing", "nutsb_set_stream", "nutsb_set_swear_words",
+    "nutsb_set_ban_files", "nutsb_set_users", "nutsb_write_batch", "nutsb_write_batch_dev",
+    "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
+    "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
+    "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
+    "nutsb_q_write_level", "nutsb_q_pending", "nutsb_flush", "nutsb_contains_swearing",
+    "nutsb_site_banned", "nutsb_user_banned",
+]
+
+
+def library_path() -> Path:
+    return Path(__file__).resolve().parent / "_lib" / "libnutsb200.so"
+
+
+def bind(lib: C.CDLL) -> C.CDLL:
+    """Declares the C-ABI's signatures on a loaded library."""
+    vp = C.c_void_p
+    lib.nutsb_version.restype = C.c_int
+    lib.nutsb_strerror.restype = C.c_char_p
+    lib.nutsb_strerror.argtypes = [C.c_int]
+    lib.nutsb_last_error.restype = C.c_char_p
+    lib.nutsb_last_error.argtypes = [vp]
+    lib.nutsb_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.nutsb_destroy.argtypes = [vp]
+    lib.nutsb_destroy.restype = None
+    lib.nutsb_set_profiling.argtypes = [vp, C.c_int]
+    lib.nutsb_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    lib.nutsb_set_stream.argtypes = [vp, vp]
+    lib.nutsb_set_swear_words.argtypes = [vp, C.POINTER(C.c_char_p)]
+    lib.nutsb_set_ban_files.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    lib.nutsb_set_users.argtypes = [vp, C.c_int32, C.c_int32, i32p, u8p, u8p]
+    lib.nutsb_write_batch.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_Streams)]
+    lib.nutsb_write_batch_dev.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_Streams)]
+    for name in ("contains_swearing", "site_banned", "user_banned"):
+        getattr(lib, f"nutsb_{name}_batch").argtypes = [vp, C.c_int64, vp, vp, vp]
+        getattr(lib, f"nutsb_{name}_batch_dev").argtypes = [vp, C.c_int64, vp, vp, vp]
+        getattr(lib, f"nutsb_{name}").argtypes = [vp, C.c_char_p]
+    lib.nutsb_stream_digests.argtypes = [vp, u64p]
+    lib.nutsb_q_write_user.argtypes = [vp, C.c_int32, C.c_char_p]
+    lib.nutsb_q_write_room.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int, C.c_int]
+    lib.nutsb_q_write_room_except.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int32, C.c_int, C.c_int]
+    lib.nutsb_q_write_level.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_int32]
+    lib.nutsb_q_pending.restype = C.c_int64
+    lib.nutsb_q_pending.argtypes = [vp]
+    lib.nutsb_flush.argtypes = [vp, C.POINTER(_Streams)]
+    return lib
+
+
+_LIB = None
+
+
+def load_library() -> C.CDLL:
+    """Loads nuts333_b200/_lib/libnutsb200.so (built by nuts333_b200.build).  Fails
+    loudly when it is missing: there is nothing to fall back to."""
+    global _LIB
+    if _LIB is None:
+        p = library_path()
+        if not p.exists():
+            raise FileNotFoundError(f"{p} is missing: run `python -m nuts333_b200.build` (needs nvcc)")
+        _LIB = bind(C.CDLL(str(p)))
+    return _LIB
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _addr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def pack(strings):
+    """list[bytes] -> (u8 array, u64 offsets[n+1])"""
+    off = np.zeros(len(strings) + 1, dtype=np.uint64)
+    if len(strings):
+        off[1:] = np.cumsum([len(s) for s in strings], dtype=np.uint64)
+    data = np.frombuffer(b"".join(strings), dtype=np.uint8)
+    return (data.copy() if data.size else np.zeros(0, np.uint8)), off
+
+
+class Streams:
+    """Per-user socket streams returned by a write batch (host copy)."""
+
+    def __init__(self, off, data, n_deliveries):
+        self.off, self.data, self.n_deliveries = off, data, int(n_deliveries)
+
+    @property
+    def n_users(self):
+        return len(self.off) - 1
+
+    @property
+    def total_bytes(self):
+        return int(self.off[-1]) if len(self.off) else 0
+
+    def user(self, u) -> bytes:
+        return self.data[int(self.off[u]):int(self.off[u + 1])].tobytes()
+
+
+class Context:
+    """One context per GPU (nutsb_create / nutsb_destroy)."""
+
+    def __init__(self, device: int = 0, lib: C.CDLL | None = None):
+        self.lib = lib if lib is not None else load_library()
+        self._h = C.c_void_p()
+        rc = self.lib.nutsb_create(C.byref(self._h), device)
+        if rc != 0:
+            raise NutsbError(rc, "nutsb_create failed (no usable CUDA device?)")
+        self.n_users = 0
+
+    def close(self):
+        if self._h:
+            self.lib.nutsb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise NutsbError(rc, (self.lib.nutsb_last_error(self._h) or b"").decode(errors="replace"))
+        return rc
+
+    # -- tables / population -------------------------------------------------------------
+    def set_swear_words(self, words):
+        """words: the reference's swear_words[] content; the list ends at the first
+        entry starting with '*' (nuts333.h:275-277) or at the end of the sequence."""
+        ws = [w if isinstance(w, bytes) else w.encode() for w in words]
+        arr = (C.c_char_p * (len(ws) + 1))(*ws, None)
+        self._ck(self.lib.nutsb_set_swear_words(self._h, arr))
+
+    def set_ban_files(self, siteban: bytes | None, userban: bytes | None):
+        """Raw bytes of datafiles/siteban and datafiles/userban; None = file missing."""
+        self._ck(self.lib.nutsb_set_ban_files(self._h, siteban, len(siteban or b""), userban, len(userban or b"")))
+
+    def set_users(self, room, flags, level, n_rooms: int):
+        room, flags, level = _np(room, np.int32), _np(flags, np.uint8), _np(level, np.uint8)
+        self._ck(self.lib.nutsb_set_users(self._h, len(room), n_rooms, room.ctypes.data_as(i32p),
+                                          flags.ctypes.data_as(u8p), level.ctypes.data_as(u8p)))
+        self.n_users = len(room)
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.nutsb_set_profiling(self._h, 1 if on else 0))
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self.lib.nutsb_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def timing(self) -> Timing:
+        t = Timing()
+        self._ck(self.lib.nutsb_get_timing(self._h, C.byref(t)))
+        return t
+
+    # -- write batches -------------------------------------------------------------------
+    @staticmethod
+    def _ops_struct(ops, keep):
+        n = len(ops["kind"])
+        arrs = dict(text=_np(ops["text"], np.uint8), off=_np(ops["off"], np.uint64), kind=_np(ops["kind"], np.uint8),
+                    target=_np(ops["target"], np.int32), except_user=_np(ops["except_user"], np.int32),
+                    flags=_np(ops["flags"], np.uint8))
+        gate = ops.get("gate")
+        verdict = ops.get("verdict")
+        if gate is not None and verdict is not None:
+            arrs["gate"], arrs["verdict"] = _np(gate, np.int32), _np(verdict, np.uint8)
+        keep.append(arrs)
+        o = _Ops(n, _addr(arrs["text"]) if arrs["text"].size else None, _addr(arrs["off"]), _addr(arrs["kind"]),
+                 _addr(arrs["target"]), _addr(arrs["except_user"]), _addr(arrs["flags"]),
+                 _addr(arrs.get("gate")), _addr(arrs.get("verdict")))
+        return o
+
+    def write_batch(self, ops) -> Streams:
+        """ops: dict(text u8[], off u64[n+1], kind u8[n], target i32[n], except_user i32[n],
+        flags u8[n][, gate i32[n], verdict u8[]]) in host memory."""
+        keep = []
+        o = self._ops_struct(ops, keep)
+        st = _Streams()
+        self._ck(self.lib.nutsb_write_batch(self._h, C.byref(o), C.byref(st)))
+        return self._host_streams(st)
+
+    def _host_streams(self, st) -> Streams:
+        U = int(st.n_users)
+        off = np.ctypeslib.as_array(C.cast(st.off, u64p), shape=(U + 1,)).copy()
+        total = int(st.total_bytes)
+        data = (np.ctypeslib.as_array(C.cast(st.bytes, u8p), shape=(total,)).copy() if total
+                else np.zeros(0, np.uint8))
+        return Streams(off, data, st.n_deliveries)
+
+    def write_batch_dev(self, n_ops, text, off, kind, target, except_user, flags, gate=0, verdict=0):
+        """All arguments are device addresses (ints).  Returns the raw nutsb_streams
+        (device pointers, owned by the context)."""
+        o = _Ops(n_ops, text, off, kind, target, except_user, flags, gate or None, verdict or None)
+        st = _Streams()
+        self._ck(self.lib.nutsb_write_batch_dev(self._h, C.byref(o), C.byref(st)))
+        return st
+
+    def stream_digests(self):
+        d = np.zeros(max(self.n_users, 1), np.uint64)
+        self._ck(self.lib.nutsb_stream_digests(self._h, d.ctypes.data_as(u64p)))
+        return d[:self.n_users]
+
+    # -- verdict batches -----------------------------------------------------------------
+    def _verdicts(self, name, text, off):
+        text, off = _np(text, np.uint8), _np(off, np.uint64)
+        n = len(off) - 1
+        v = np.zeros(max(n, 1), np.uint8)
+        self._ck(getattr(self.lib, f"nutsb_{name}_batch")(self._h, n, _addr(text) if text.size else None,
+                                                          _addr(off), _addr(v)))
+        return v[:n]
+
+    def contains_swearing_batch(self, text, off):
+        return self._verdicts("contains_swearing", text, off)
+
+    def site_banned_batch(self, text, off):
+        return self._verdicts("site_banned", text, off)
+
+    def user_banned_batch(self, text, off):
+        return self._verdicts("user_banned", text, off)
+
+    def verdicts_dev(self, name, n, text, off, verdict):
+        self._ck(getattr(self.lib, f"nutsb_{name}_batch_dev")(self._h, n, text, off, verdict))
+
+
+class Talker:
+    """The reference's call surface, same names and argument meaning.  Users and rooms
+    are passed as their index in the reference's lists (None = NULL)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.force_listen = 0      # nuts333.h:293
+        self.com_num = -1          # nuts333.h:201
+
+    @staticmethod
+    def _s(s):
+        return s if isinstance(s, bytes) else s.encode("latin-1")
+
+    def _shout(self):
+        return 1 if self.com_num in (SHOUT, SEMOTE) else 0
+
+    def write_user(self, user, s):                                   # c:1291
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_write_user(c._h, -1 if user is None else user, self._s(s)))
+
+    def write_room(self, rm, s):                                     # c:1390
+        self.write_room_except(rm, s, None)
+
+    def write_room_except(self, rm, s, user):                        # c:1401
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_write_room_except(c._h, -1 if rm is None else rm, self._s(s),
+                                              -1 if user is None else user,
+                                              1 if self.force_listen else 0, self._shout()))
+
+    def write_level(self, level, above, s, user):                    # c:1372
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_write_level(c._h, level, 1 if above else 0, self._s(s), -1 if user is None else user))
+
+    def pending(self) -> int:
+        return int(self.ctx.lib.nutsb_q_pending(self.ctx._h))
+
+    def flush(self) -> Streams:
+        """Runs everything queued; the host then write()s each user's stream."""
+        c = self.ctx
+        st = _Streams()
+        c._ck(c.lib.nutsb_flush(c._h, C.byref(st)))
+        return c._host_streams(st)
+
+    def contains_swearing(self, s) -> int:                            # c:2540
+        return self.ctx._ck(self.ctx.lib.nutsb_contains_swearing(self.ctx._h, self._s(s)))
+
+    def site_banned(self, site) -> int:                               # c:330
+        return self.ctx._ck(self.ctx.lib.nutsb_site_banned(self.ctx._h, self._s(site)))
+
+    def user_banned(self, name) -> int:                               # c:349
+        return self.ctx._ck(self.ctx.lib.nutsb_user_banned(self.ctx._h, self._s(name)))

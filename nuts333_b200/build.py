@@ -1,0 +1,55 @@
+"""Builds libnutsb200.so (the C-ABI library of include/nutsb200.h) with nvcc for sm_100a.
+
+In-tree output: nuts333_b200/_lib/libnutsb200.so (git-ignored, travels to the GPU box).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "_lib" / "libnutsb200.so"
+SOURCES = [CSRC / "nutsb_lib.cu"]
+HEADERS = [CSRC / "nutsb_common.cuh", CSRC / "nutsb_kernels.cuh", CSRC / "nutsb_match.cuh",
+           PKG.parent / "include" / "nutsb200.h"]
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared", "-cudart", "static",
+              "--expt-relaxed-constexpr"]
+
+
+def nvcc_path() -> str:
+    cand = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(cand).exists():
+        raise RuntimeError("nvcc not found: libnutsb200.so cannot be built (there is no CPU fallback)")
+    return cand
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any(p.stat().st_mtime > t for p in SOURCES + HEADERS + [Path(__file__)])
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB
+    LIB.parent.mkdir(parents=True, exist_ok=True)
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

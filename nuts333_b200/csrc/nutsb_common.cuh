@@ -1,0 +1,180 @@
+// nutsb_common.cuh -- shared definitions for the sm_100a kernels of the NUTS
+// message path.  Compiled by nvcc for the product; compiled by g++ against
+// tests/cpusim/cpusim.h (-DNUTSB_CPUSIM) for the CPU kernel-logic tests only.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef NUTSB_CPUSIM
+#include "cpusim.h"
+#else
+#include <cuda_runtime.h>
+#define NUTSB_LAUNCH(grid, block, stream, kern, ...) \
+    kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+#include "../../include/nutsb200.h"
+
+typedef uint64_t           u64;
+typedef int64_t            i64;
+typedef uint32_t           u32;
+typedef int32_t            i32;
+typedef uint16_t           u16;
+typedef uint8_t            u8;
+
+#define NUTSB_FULL 0xffffffffu
+
+__device__ __forceinline__ void nutsb_add64(u64 *p, u64 v) { atomicAdd((unsigned long long *)p, (unsigned long long)v); }
+
+// Status bits raised by kernels (ctx->d_status), decoded on the host.
+#define NUTSB_ST_TEXT_TOO_LONG 0x01u
+#define NUTSB_ST_BAD_KIND      0x02u
+#define NUTSB_ST_BAD_INDEX     0x04u
+#define NUTSB_ST_HAS_LEVEL     0x08u   // not an error: batch contains write_level ops
+#define NUTSB_ST_RENDER_MISMATCH 0x10u // internal consistency check failed
+#define NUTSB_ST_BAD_OFFSETS   0x20u
+
+// ---- the colour table, nuts333.h:237-255 ---------------------------------------
+// 26x26 table indexed by the two command letters: value = index+1, 0 = not a
+// command.  Built on the host (nutsb_lib.cu) and staged into shared memory by
+// every kernel that parses '~XX'.
+#define NUTSB_CODETAB_BYTES 676
+
+__device__ __forceinline__ int nutsb_code(const u8 *tab, u8 a, u8 b)
+{
+    u32 ua = (u32)a - 'A', ub = (u32)b - 'A';
+    if (ua < 26u && ub < 26u) return (int)tab[ua * 26u + ub] - 1;
+    return -1;
+}
+// Bytes of colcode[k]: ESC [ d m   (k<5, d in 0 1 4 5 7)  or  ESC [ 3|4 d m.
+__device__ __forceinline__ u32 nutsb_code_len(int k) { return k < 5 ? 4u : 5u; }
+__device__ __forceinline__ u8 nutsb_code_byte(int k, u32 i)
+{
+    if (i == 0) return 0x1b;
+    if (i == 1) return '[';
+    if (k < 5) {
+        if (i == 3) return 'm';
+        // "01457" packed: k=0->'0',1->'1',2->'4',3->'5',4->'7'
+        return (u8)('0' + ((0x75410u >> (4 * k)) & 0xf));
+    }
+    if (i == 2) return (u8)(k < 13 ? '3' : '4');
+    if (i == 3) return (u8)('0' + ((k - 5) & 7));
+    return 'm';
+}
+
+// Recipient filter for the ops that reach a whole class of users (room and
+// level ops); the room match itself is established by bucketing.
+//   ROOM : nuts333.c:1410-1415      LEVEL: nuts333.c:1379-1383
+__device__ __forceinline__ bool nutsb_class_delivers(u32 cflags, u32 clevel, u32 kind, u32 oflags, i32 target)
+{
+    if (cflags & NUTSB_UF_LOGIN) return false;
+    if (kind == NUTSB_OP_ROOM) {
+        if ((cflags & NUTSB_UF_IGNALL) && !(oflags & NUTSB_OF_FORCE_LISTEN)) return false;
+        if ((cflags & NUTSB_UF_IGNSHOUT) && (oflags & NUTSB_OF_SHOUT)) return false;
+        return true;
+    }
+    if (cflags & NUTSB_UF_CLONE) return false;
+    return (oflags & NUTSB_OF_ABOVE) ? ((i32)clevel >= target) : ((i32)clevel <= target);
+}
+
+// Sequential restatement of write_user's byte machine (nuts333.c:1315-1365),
+// one thread, shared -> shared.  s[-1] is never read at i==0; bytes past n are
+// never read.
+__device__ __forceinline__ u32 nutsb_render_seq(const u8 *s, u32 n, int colour, u8 *out, const u8 *tab)
+{
+    u32 i = 0, o = 0;
+    while (i < n) {
+        u8 c = s[i];
+        if (c == '\n') {
+            if (colour) { out[o] = 0x1b; out[o + 1] = '['; out[o + 2] = '0'; out[o + 3] = 'm'; o += 4; }
+            out[o] = '\n'; out[o + 1] = '\r'; o += 2; ++i;
+        } else if (c == '/' && i + 1 < n && s[i + 1] == '~') {
+            ++i;
+        } else if (c == '~') {
+            int k = -1;
+            if (!(i > 0 && s[i - 1] == '/') && i + 2 < n) k = nutsb_code(tab, s[i + 1], s[i + 2]);
+            if (k >= 0) {
+                if (colour) { u32 L = nutsb_code_len(k); for (u32 q = 0; q < L; ++q) out[o + q] = nutsb_code_byte(k, q); o += L; }
+                i += 3;
+            } else { out[o++] = '~'; ++i; }
+        } else { out[o++] = c; ++i; }
+    }
+    if (colour) { out[o] = 0x1b; out[o + 1] = '['; out[o + 2] = '0'; out[o + 3] = 'm'; o += 4; }
+    return o;
+}
+
+// ---- device-wide exclusive scan (three kernels, u64) ----------------------------
+#define NUTSB_SCAN_THREADS 256
+#define NUTSB_SCAN_ITEMS   16
+#define NUTSB_SCAN_TILE    (NUTSB_SCAN_THREADS * NUTSB_SCAN_ITEMS)
+
+// Block-wide exclusive scan of one value per thread (256 threads).  Returns the
+// exclusive prefix; *total gets the block sum.  Contains __syncthreads().
+__device__ __forceinline__ u64 nutsb_block_excl_scan(u64 v, u64 *total)
+{
+    __shared__ u64 s_warp[NUTSB_SCAN_THREADS / 32];
+    __shared__ u64 s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 inc = v;
+    for (int d = 1; d < 32; d <<= 1) {
+        u64 t = __shfl_up_sync(NUTSB_FULL, inc, d);
+        if (lane >= d) inc += t;
+    }
+    __syncthreads();                       // protects s_warp/s_total against the previous call
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u64 w = lane < NUTSB_SCAN_THREADS / 32 ? s_warp[lane] : 0;
+        u64 winc = w;
+        for (int d = 1; d < NUTSB_SCAN_THREADS / 32; d <<= 1) {
+            u64 t = __shfl_up_sync(NUTSB_FULL, winc, d);
+            if (lane >= d) winc += t;
+        }
+        if (lane < NUTSB_SCAN_THREADS / 32) s_warp[lane] = winc - w;
+        if (lane == NUTSB_SCAN_THREADS / 32 - 1) s_total = winc;
+    }
+    __syncthreads();
+    *total = s_total;
+    return s_warp[warp] + inc - v;
+}
+
+template <class In>
+__global__ void __launch_bounds__(NUTSB_SCAN_THREADS)
+k_scan_reduce(In in, i64 n_host, const u32 *n_dev, u64 *block_sums)
+{
+    const i64 n = n_dev ? (i64)*n_dev : n_host;
+    const i64 base = (i64)blockIdx.x * NUTSB_SCAN_TILE + (i64)threadIdx.x * NUTSB_SCAN_ITEMS;
+    u64 s = 0;
+    for (int k = 0; k < NUTSB_SCAN_ITEMS; ++k) { i64 i = base + k; if (i < n) s += in(i); }
+    u64 total;
+    (void)nutsb_block_excl_scan(s, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// One block: exclusive scan of the block sums in place; total -> sums[nb].
+__global__ void __launch_bounds__(NUTSB_SCAN_THREADS)
+k_scan_sums(u64 *sums, i64 nb)
+{
+    u64 carry = 0;
+    for (i64 base = 0; base < nb; base += NUTSB_SCAN_THREADS) {
+        i64 i = base + threadIdx.x;
+        u64 v = i < nb ? sums[i] : 0, total;
+        u64 ex = nutsb_block_excl_scan(v, &total);
+        if (i < nb) sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) sums[nb] = carry;
+}
+
+template <class In, class Out>
+__global__ void __launch_bounds__(NUTSB_SCAN_THREADS)
+k_scan_apply(In in, Out out, i64 n_host, const u32 *n_dev, const u64 *block_sums)
+{
+    const i64 n = n_dev ? (i64)*n_dev : n_host;
+    const i64 base = (i64)blockIdx.x * NUTSB_SCAN_TILE + (i64)threadIdx.x * NUTSB_SCAN_ITEMS;
+    u64 v[NUTSB_SCAN_ITEMS], s = 0;
+    for (int k = 0; k < NUTSB_SCAN_ITEMS; ++k) { i64 i = base + k; v[k] = i < n ? in(i) : 0; s += v[k]; }
+    u64 total;
+    u64 ex = nutsb_block_excl_scan(s, &total) + block_sums[blockIdx.x];
+    for (int k = 0; k < NUTSB_SCAN_ITEMS; ++k) { i64 i = base + k; if (i <= n) out(i, ex); ex += v[k]; }   // out(n) = total
+}

@@ -1,0 +1,766 @@
+// nutsb_kernels.cuh -- hand-written sm_100a kernels of the write path:
+// measure -> bucket by room -> prefix sums -> events -> stream offsets ->
+// render + fan-out.  See DESIGN.md for the data layout and the roofline of each.
+//
+// Reference semantics: nuts333.c:1291-1366 (write_user), :1372-1385
+// (write_level), :1401-1429 (write_room_except).
+#pragma once
+#include "nutsb_common.cuh"
+
+// Device views -------------------------------------------------------------------
+
+struct OpsView {                 // the batch, device pointers (nutsb_ops)
+    i64 n;
+    const u8  *text;
+    const u64 *toff;
+    const u8  *kind;
+    const i32 *target;
+    const i32 *except_user;
+    const u8  *flags;
+    const i32 *gate;             // may be null
+    const u8  *verdict;          // may be null
+};
+
+struct PopView {                 // the population, built by nutsb_set_users
+    i32 n_users, n_rooms, n_rooms_tot;   // n_rooms_tot = n_rooms + 1 (the last is "no room")
+    const i32 *user_room;        // [U]  room' in [0, n_rooms_tot)
+    const i32 *user_cls;         // [U]  global class id
+    const i32 *user_slot;        // [U]  position in (room, class, index) order
+    const i32 *slot_user;        // [U]
+    const i32 *room_slot_off;    // [Rt+1]
+    const i32 *room_cls_off;     // [Rt+1]
+    const u8  *cls_flags;        // [K]
+    const u8  *cls_level;        // [K]
+    const u8  *codetab;          // [676]
+};
+
+#define NUTSB_TILE_OPS   64      // room-list ops per fan-out tile
+#define NUTSB_UCHUNK     128     // recipients per fan-out work item
+#define NUTSB_TEXT_CAP   8192    // staged source bytes per (sub)tile
+#define NUTSB_ON_CAP     16384   // rendered bytes per (sub)tile, colour on  (>= 6*2000+4)
+#define NUTSB_OFF_CAP    8192    // rendered bytes per (sub)tile, colour off (>= 2*2000)
+
+// ---- A. measure ------------------------------------------------------------------
+// One thread per op: rendered length for both colour settings, liveness (gate),
+// validation and the number of room lists the op enters.  The 32 ops of a warp
+// are a contiguous byte range of the packed text: it is staged into shared
+// memory with coalesced 16-byte loads, then each thread scans its own string a
+// 32-bit word at a time and only looks closer at words that hold '~' or '\n'.
+#define NUTSB_MEASURE_THREADS 256
+#define NUTSB_MEASURE_WARP_BYTES 4096
+
+__device__ __forceinline__ bool nutsb_word_has(u32 x, u32 b)
+{
+    u32 y = x ^ (b * 0x01010101u);
+    return ((y - 0x01010101u) & ~y & 0x80808080u) != 0;
+}
+
+__global__ void __launch_bounds__(NUTSB_MEASURE_THREADS)
+k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *status)
+{
+    __shared__ __align__(16) u8 s_stage[NUTSB_MEASURE_THREADS / 32][NUTSB_MEASURE_WARP_BYTES + 32];
+    __shared__ u8 s_tab[NUTSB_CODETAB_BYTES];
+    for (int i = threadIdx.x; i < NUTSB_CODETAB_BYTES; i += blockDim.x) s_tab[i] = pop.codetab[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 wbase = (i64)blockIdx.x * NUTSB_MEASURE_THREADS + warp * 32;
+    if (wbase >= ops.n) return;                    // whole warp leaves together
+    const i64 wend = (wbase + 32 < ops.n) ? wbase + 32 : ops.n;
+    const u64 b0 = ops.toff[wbase], b1 = ops.toff[wend];
+    // 16-byte aligned window around the warp's bytes (any cudaMalloc'd buffer is
+    // readable up to the next 16-byte boundary)
+    const u8 *pa = (const u8 *)((size_t)(ops.text + b0) & ~(size_t)15);
+    const u64 span = (u64)((ops.text + b1) - pa);
+    const bool staged = (b1 >= b0) && span <= NUTSB_MEASURE_WARP_BYTES;
+    u8 *stage = s_stage[warp];
+    if (staged) {
+        const u32 nvec = (u32)((span + 15) >> 4);
+        for (u32 v = lane; v < nvec; v += 32)
+            *(uint4 *)(stage + 16 * v) = __ldg((const uint4 *)pa + v);
+    }
+    __syncwarp();
+
+    const i64 i = wbase + lane;
+    if (i >= ops.n) return;
+    const u64 o0 = ops.toff[i], o1 = ops.toff[i + 1];
+    u32 st = 0;
+    if (o1 < o0) { atomicOr(status, NUTSB_ST_BAD_OFFSETS); len_on[i] = len_off[i] = nrep[i] = 0; return; }
+    const u64 n64 = o1 - o0;
+    if (n64 > NUTSB_MAX_TEXT) { atomicOr(status, NUTSB_ST_TEXT_TOO_LONG); len_on[i] = len_off[i] = nrep[i] = 0; return; }
+    const u32 n = (u32)n64;
+
+    u32 nl = 0, drops = 0, m4 = 0, m5 = 0;
+    if (staged) {
+        const u32 p0 = (u32)((ops.text + o0) - pa), p1 = p0 + n;
+        for (u32 w = p0 >> 2; w < (p1 + 3) >> 2; ++w) {
+            const u32 x = *(const u32 *)(stage + 4 * w);
+            if (!nutsb_word_has(x, '~') && !nutsb_word_has(x, '\n')) continue;
+            for (u32 b = 0; b < 4; ++b) {
+                const u32 j = 4 * w + b;
+                if (j < p0 || j >= p1) continue;
+                const u8 c = (u8)(x >> (8 * b));
+                if (c == '\n') ++nl;
+                else if (c == '~') {
+                    if (j > p0 && stage[j - 1] == '/') ++drops;
+                    else if (j + 2 < p1) {
+                        int k = nutsb_code(s_tab, stage[j + 1], stage[j + 2]);
+                        if (k >= 0) { if (k < 5) ++m4; else ++m5; }
+                    }
+                }
+            }
+        }
+    } else {
+        const u8 *s = ops.text + o0;
+        for (u32 j = 0; j < n; ++j) {
+            const u8 c = s[j];
+            if (c == '\n') ++nl;
+            else if (c == '~') {
+                if (j > 0 && s[j - 1] == '/') ++drops;
+                else if (j + 2 < n) {
+                    int k = nutsb_code(s_tab, s[j + 1], s[j + 2]);
+                    if (k >= 0) { if (k < 5) ++m4; else ++m5; }
+                }
+            }
+        }
+    }
+    const u32 loff = n - drops - 3 * (m4 + m5) + nl;
+    len_off[i] = loff;
+    len_on[i]  = loff + 4 * nl + 4 * m4 + 5 * m5 + 4;
+
+    // liveness + fan-in: how many room lists this op enters
+    bool live = true;
+    if (ops.gate && ops.gate[i] >= 0) {
+        const bool v = ops.verdict[ops.gate[i]] != 0;
+        live = ((ops.flags[i] & NUTSB_OF_GATE_IF_SET) != 0) == v;
+    }
+    const u32 kind = ops.kind[i];
+    const i32 tgt = ops.target[i], exc = ops.except_user[i];
+    u32 rep = 0;
+    if (kind == NUTSB_OP_USER) {
+        if (tgt >= pop.n_users) st |= NUTSB_ST_BAD_INDEX; else if (tgt >= 0) rep = 1;
+    } else if (kind == NUTSB_OP_ROOM) {
+        if (tgt >= pop.n_rooms || tgt < -1) st |= NUTSB_ST_BAD_INDEX;
+        else rep = tgt >= 0 ? 1u : (u32)pop.n_rooms;
+    } else if (kind == NUTSB_OP_LEVEL) {
+        rep = (u32)pop.n_rooms_tot; st |= NUTSB_ST_HAS_LEVEL;
+    } else st |= NUTSB_ST_BAD_KIND;
+    if (exc >= pop.n_users || exc < -1) st |= NUTSB_ST_BAD_INDEX;
+    if (st & ~NUTSB_ST_HAS_LEVEL) rep = 0;
+    nrep[i] = live ? rep : 0;
+    if (st) atomicOr(status, st);
+}
+
+// ---- B. expand ops into (room, op) entries ------------------------------------------
+__global__ void __launch_bounds__(256)
+k_expand(OpsView ops, PopView pop, const u32 *nrep, const u64 *eoff, u32 *e_room, u32 *e_op)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ops.n) return;
+    const u32 rep = nrep[i];
+    if (!rep) return;
+    const u64 base = eoff[i];
+    const u32 kind = ops.kind[i];
+    const i32 tgt = ops.target[i];
+    if (rep == 1 && kind != NUTSB_OP_LEVEL) {
+        u32 r = kind == NUTSB_OP_USER ? (u32)pop.user_room[tgt] : (tgt >= 0 ? (u32)tgt : 0u);
+        e_room[base] = r; e_op[base] = (u32)i;
+    } else {
+        for (u32 j = 0; j < rep; ++j) { e_room[base + j] = j; e_op[base + j] = (u32)i; }
+    }
+}
+
+// ---- stable LSD radix sort of (key,val) pairs, 11-bit digits ------------------------
+#define NUTSB_RS_BITS    11
+#define NUTSB_RS_DIGITS  (1 << NUTSB_RS_BITS)
+#define NUTSB_RS_THREADS 256
+#define NUTSB_RS_ROUNDS  16
+#define NUTSB_RS_CHUNK   (NUTSB_RS_THREADS * NUTSB_RS_ROUNDS)
+
+// hist[digit * nblocks + block]
+__global__ void __launch_bounds__(NUTSB_RS_THREADS)
+k_rs_hist(const u32 *keys, i64 n_host, const u32 *n_dev, int shift, u32 *hist, u32 nblocks)
+{
+    const i64 n = n_dev ? (i64)*n_dev : n_host;
+    __shared__ u32 s_h[NUTSB_RS_DIGITS];
+    for (int d = threadIdx.x; d < NUTSB_RS_DIGITS; d += blockDim.x) s_h[d] = 0;
+    __syncthreads();
+    const i64 base = (i64)blockIdx.x * NUTSB_RS_CHUNK;
+    for (int r = 0; r < NUTSB_RS_ROUNDS; ++r) {
+        const i64 i = base + r * NUTSB_RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & (NUTSB_RS_DIGITS - 1)], 1u);
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < NUTSB_RS_DIGITS; d += blockDim.x)
+        hist[(size_t)d * nblocks + blockIdx.x] = s_h[d];
+}
+
+// offs = exclusive scan of hist (same layout).  vals_in == nullptr means iota.
+__global__ void __launch_bounds__(NUTSB_RS_THREADS)
+k_rs_scatter(const u32 *keys_in, const u32 *vals_in, i64 n_host, const u32 *n_dev, int shift,
+             const u64 *offs, u32 nblocks, u32 *keys_out, u32 *vals_out)
+{
+    const i64 n = n_dev ? (i64)*n_dev : n_host;
+    __shared__ u32 s_run[NUTSB_RS_DIGITS];
+    for (int d = threadIdx.x; d < NUTSB_RS_DIGITS; d += blockDim.x)
+        s_run[d] = (u32)offs[(size_t)d * nblocks + blockIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 base = (i64)blockIdx.x * NUTSB_RS_CHUNK;
+    for (int r = 0; r < NUTSB_RS_ROUNDS; ++r) {
+        const i64 i = base + r * NUTSB_RS_THREADS + threadIdx.x;
+        const bool valid = i < n;
+        const u32 key = valid ? keys_in[i] : 0;
+        const u32 d = valid ? ((key >> shift) & (NUTSB_RS_DIGITS - 1)) : 0xffffffffu;
+        const u32 grp = __match_any_sync(NUTSB_FULL, d);
+        const int leader = __ffs((int)grp) - 1;
+        const u32 rank = (u32)__popc(grp & ((1u << lane) - 1));
+        u32 gbase = 0;
+        // warps take turns so that equal digits keep their input order
+        for (int w = 0; w < NUTSB_RS_THREADS / 32; ++w) {
+            if (warp == w && valid && lane == leader) { gbase = s_run[d]; s_run[d] = gbase + (u32)__popc(grp); }
+            __syncthreads();
+        }
+        gbase = __shfl_sync(NUTSB_FULL, gbase, leader);
+        if (valid) {
+            keys_out[gbase + rank] = key;
+            vals_out[gbase + rank] = vals_in ? vals_in[i] : (u32)i;
+        }
+    }
+}
+
+// seg_off[k] = first index i with keys[i] >= k, for k in [0, nkeys]; keys sorted.
+__global__ void __launch_bounds__(256)
+k_seg_bounds(const u32 *keys, i64 n_host, const u32 *n_dev, u32 nkeys, u32 *seg_off)
+{
+    const i64 n = n_dev ? (i64)*n_dev : n_host;
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    const i64 lo = (i == 0) ? 0 : (i64)keys[i - 1] + 1;
+    const i64 hi = (i == n) ? (i64)nkeys : (i64)keys[i];
+    for (i64 k = lo; k <= hi && k <= (i64)nkeys; ++k) seg_off[k] = (u32)i;
+}
+
+// ---- C. per-entry classification -----------------------------------------------------
+// e_info packs, per room-list entry: bit0 = enters the room slab (room/level op),
+// bits 1-2 = event kind (0 none, 1 direct write_user op, 2 excluded recipient).
+struct EntryArrays {
+    const u32 *e_room, *e_op;    // sorted by room, op order inside
+    u8  *e_info;
+    i32 *e_delta;                // event: signed byte delta on the user's stream
+    u32 *e_slot;                 // event: user slot
+};
+
+__global__ void __launch_bounds__(256)
+k_entry_info(OpsView ops, PopView pop, EntryArrays ea, i64 n_ent, const u32 *len_on, const u32 *len_off)
+{
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ent) return;
+    const u32 op = ea.e_op[e], room = ea.e_room[e];
+    const u32 kind = ops.kind[op];
+    u8 info = 0; i32 delta = 0; u32 slot = 0;
+    if (kind == NUTSB_OP_USER) {
+        const i32 u = ops.target[op];
+        const u32 cf = pop.cls_flags[pop.user_cls[u]];
+        info = 1u << 1;
+        delta = (i32)((cf & NUTSB_UF_COLOUR) ? len_on[op] : len_off[op]);
+        slot = (u32)pop.user_slot[u];
+    } else {
+        info = 1;
+        const i32 x = ops.except_user[op];
+        if (x >= 0 && (u32)pop.user_room[x] == room) {
+            const i32 k = pop.user_cls[x];
+            const u32 cf = pop.cls_flags[k];
+            if (nutsb_class_delivers(cf, pop.cls_level[k], kind, ops.flags[op], ops.target[op])) {
+                info |= 2u << 1;
+                delta = -(i32)((cf & NUTSB_UF_COLOUR) ? len_on[op] : len_off[op]);
+                slot = (u32)pop.user_slot[x];
+            }
+        }
+    }
+    ea.e_info[e] = info; ea.e_delta[e] = delta; ea.e_slot[e] = slot;
+}
+
+// After the packed scan over entries (lo32 = slab ops before, hi32 = events before):
+// scatter the slab list and the event list.
+struct EntryScatter {
+    const u32 *e_room, *e_op; const u8 *e_info; const i32 *e_delta; const u32 *e_slot;
+    const u32 *room_ent_off;     // [Rt+1] entry offset of each room
+    u64 *e_scan;                 // [n_ent+1] packed exclusive scan (written by the scan's Out)
+    u32 *bl_op, *bl_room;        // slab list
+    u32 *ev_slot, *ev_ukey, *ev_op; i32 *ev_delta;
+};
+
+__global__ void __launch_bounds__(256)
+k_entry_scatter(EntryScatter s, i64 n_ent)
+{
+    const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_ent) return;
+    const u8 info = s.e_info[e];
+    const u64 sc = s.e_scan[e];
+    const u32 rankB = (u32)sc, evi = (u32)(sc >> 32);
+    const u32 room = s.e_room[e];
+    if (info & 1) { s.bl_op[rankB] = s.e_op[e]; s.bl_room[rankB] = room; }
+    const u32 ek = info >> 1;
+    if (ek) {
+        const u32 roomB0 = (u32)s.e_scan[s.room_ent_off[room]];     // slab rank of the room's first entry
+        s.ev_slot[evi]  = s.e_slot[e];
+        s.ev_ukey[evi]  = 2u * (rankB - roomB0) + (ek == 2 ? 1u : 0u);
+        s.ev_delta[evi] = s.e_delta[e];
+        s.ev_op[evi]    = s.e_op[e];
+    }
+}
+
+// room_b_off[r] = slab rank of room r's first entry, r in [0, Rt]
+__global__ void __launch_bounds__(256)
+k_room_b_off(const u32 *room_ent_off, const u64 *e_scan, u32 n_rooms_tot, u32 *room_b_off)
+{
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rooms_tot) return;
+    room_b_off[r] = (u32)e_scan[room_ent_off[r]];
+}
+
+// gather the sorted event arrays through the sort permutation
+__global__ void __launch_bounds__(256)
+k_ev_gather(const u32 *perm, const u32 *n_dev, const u32 *ev_ukey, const i32 *ev_delta, const u32 *ev_op,
+            u32 *sv_ukey, i32 *sv_delta, u32 *sv_op)
+{
+    const i64 n_ev = (i64)*n_dev;
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ev) return;
+    const u32 p = perm[i];
+    sv_ukey[i] = ev_ukey[p]; sv_delta[i] = ev_delta[p]; sv_op[i] = ev_op[p];
+}
+
+// ---- class prefix access ---------------------------------------------------------------
+// Bytes of the room slab a class receives before slab rank g.  In alias mode
+// (every class takes every room op: no login/ignall/ignshout users, no level
+// ops) this is the slab prefix itself; otherwise one scan per class column.
+struct ClassPrefix {
+    const u64 *vp_on, *vp_off;   // [nB+1] exclusive prefix of rendered lengths over the slab list
+    const u64 *cp;               // [J][nB+1] or null (alias mode)
+    u64 stride;                  // nB+1
+    const i32 *room_cls_off;
+    const u8  *cls_flags;
+    __device__ __forceinline__ u64 at(i32 k, u32 room, u32 g) const
+    {
+        if (cp) return cp[(u64)(k - room_cls_off[room]) * stride + g];
+        return (cls_flags[k] & NUTSB_UF_COLOUR) ? vp_on[g] : vp_off[g];
+    }
+};
+
+// ---- E. per-user stream length --------------------------------------------------------
+struct UserLenIn {
+    ClassPrefix cpx; PopView pop;
+    const u32 *room_b_off, *ev_off;     // ev_off: [U+1] by slot
+    const u64 *sv_pre;                  // [n_ev+1] exclusive scan of sorted deltas (two's complement)
+    __device__ u64 operator()(i64 u) const
+    {
+        const u32 room = (u32)pop.user_room[u];
+        const i32 k = pop.user_cls[u];
+        const u32 s = (u32)pop.user_slot[u];
+        const u64 cls = cpx.at(k, room, room_b_off[room + 1]) - cpx.at(k, room, room_b_off[room]);
+        return cls + (sv_pre[ev_off[s + 1]] - sv_pre[ev_off[s]]);
+    }
+};
+
+// ---- F. stream position of every (tile, recipient) cell ---------------------------------
+struct Geometry {
+    const u32 *room_b_off;       // [Rt+1]
+    const u32 *room_tile_off;    // [Rt+1] tiles before room r
+    const u64 *room_cell_off;    // [Rt+1] cells before room r; room r has (tiles_r+1)*users_r cells
+    const u32 *room_item_off;    // [Rt+1] fan-out work items before room r
+};
+
+__global__ void __launch_bounds__(256)
+k_fill_pos(PopView pop, Geometry geo, ClassPrefix cpx, const u64 *stream_off,
+           const u32 *ev_off, const u32 *sv_ukey, const u64 *sv_pre, u64 *cell_pos, u32 *cell_evi)
+{
+    const i32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= pop.n_users) return;
+    const i32 u = pop.slot_user[s];
+    const u32 room = (u32)pop.user_room[u];
+    const i32 k = pop.user_cls[u];
+    const u32 users_r = (u32)(pop.room_slot_off[room + 1] - pop.room_slot_off[room]);
+    const u32 ls = (u32)(s - pop.room_slot_off[room]);
+    const u32 b0 = geo.room_b_off[room], nb = geo.room_b_off[room + 1] - b0;
+    const u32 tiles = (nb + NUTSB_TILE_OPS - 1) / NUTSB_TILE_OPS;
+    const u64 base = stream_off[u] - cpx.at(k, room, b0);
+    u32 ptr = ev_off[s];
+    const u32 end = ev_off[s + 1];
+    const u64 pre0 = sv_pre[ptr];
+    u64 cell = geo.room_cell_off[room] + ls;
+    for (u32 t = 0; t < tiles; ++t, cell += users_r) {
+        const u32 a0 = t * NUTSB_TILE_OPS;
+        while (ptr < end && sv_ukey[ptr] < 2 * a0 + 1) ++ptr;
+        cell_pos[cell] = base + cpx.at(k, room, b0 + a0) + (sv_pre[ptr] - pre0);
+        cell_evi[cell] = ptr;
+    }
+    cell_pos[cell] = 0; cell_evi[cell] = end;
+}
+
+// ---- warp copy: shared -> global at arbitrary byte alignment --------------------------
+// Head and tail bytes are stored singly; the body is 16-byte stores whose source
+// is realigned with funnel shifts from two 16-byte shared loads.  src buffers
+// carry >= 32 bytes of readable padding.
+__device__ __forceinline__ void nutsb_warp_copy(u8 *dst, const u8 *src, u32 n, int lane)
+{
+    if (n == 0) return;
+    u32 head = (u32)((16 - ((size_t)dst & 15)) & 15);
+    if (head > n) head = n;
+    if ((u32)lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    const u32 nvec = n >> 4;
+    const u32 sm = (u32)((size_t)src & 15);
+    const uint4 *sa = (const uint4 *)(src - sm);
+    const u32 wsh = sm >> 2, bsh = (sm & 3) * 8;
+    for (u32 v = lane; v < nvec; v += 32) {
+        const uint4 a = sa[v], b = sa[v + 1];
+        u32 w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
+        if (wsh & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; }
+        if (wsh & 2) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; }
+        uint4 o;
+        o.x = __funnelshift_r(w0, w1, bsh); o.y = __funnelshift_r(w1, w2, bsh);
+        o.z = __funnelshift_r(w2, w3, bsh); o.w = __funnelshift_r(w3, w4, bsh);
+        *(uint4 *)(dst + 16 * (size_t)v) = o;
+    }
+    const u32 tail = n & 15;
+    if ((u32)lane < tail) dst[16 * (size_t)nvec + lane] = src[16 * (size_t)nvec + lane];
+}
+
+// ---- H. render + fan-out ----------------------------------------------------------------
+// One work item = (room, tile of <=64 slab ops, chunk of <=128 recipients).
+// The block stages the tile's source strings in shared memory, renders each
+// once per colour setting (one thread per (op, colour): the byte machine is
+// sequential, shared -> shared), then every warp takes recipients in turn and
+// copies that recipient's view of the tile -- normally ONE contiguous run of
+// the rendered slab, cut only where the recipient is the excluded speaker or
+// has a direct write_user op in between -- to its place in the user's stream.
+struct FanoutArgs {
+    OpsView ops; PopView pop; Geometry geo; ClassPrefix cpx;
+    const u32 *bl_op;
+    const u32 *len_on, *len_off;
+    const u64 *cell_pos; const u32 *cell_evi;
+    const u32 *sv_ukey; const i32 *sv_delta;
+    u8 *out;
+    u64 *n_deliveries;           // [0] deliveries, [1] (k_direct), [2] source bytes staged (once per tile)
+    u32 *status;
+    u32 has_level;
+};
+
+#define NUTSB_FAN_THREADS 256
+
+__global__ void __launch_bounds__(NUTSB_FAN_THREADS)
+k_fanout(FanoutArgs A)
+{
+    __shared__ __align__(16) u8 s_text[NUTSB_TEXT_CAP + 32];
+    __shared__ __align__(16) u8 s_on[NUTSB_ON_CAP + 48];
+    __shared__ __align__(16) u8 s_off[NUTSB_OFF_CAP + 48];
+    __shared__ u8  s_tab[NUTSB_CODETAB_BYTES];
+    __shared__ u32 s_op[NUTSB_TILE_OPS];
+    __shared__ u32 s_tlen[NUTSB_TILE_OPS];
+    __shared__ u32 s_toff[NUTSB_TILE_OPS + 1];
+    __shared__ u32 s_oon[NUTSB_TILE_OPS + 1];
+    __shared__ u32 s_ooff[NUTSB_TILE_OPS + 1];
+    __shared__ u8  s_kind[NUTSB_TILE_OPS];
+    __shared__ u8  s_flags[NUTSB_TILE_OPS];
+    __shared__ i32 s_target[NUTSB_TILE_OPS];
+    __shared__ u32 s_sub_b;
+    __shared__ u32 s_room;
+    __shared__ u32 s_deliv;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // -- decode the work item
+    if (tid == 0) {
+        const u32 item = blockIdx.x;
+        u32 lo = 0, hi = (u32)A.pop.n_rooms_tot;        // last r with room_item_off[r] <= item
+        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (A.geo.room_item_off[mid] <= item) lo = mid; else hi = mid; }
+        s_room = lo; s_deliv = 0;
+    }
+    for (int i = tid; i < NUTSB_CODETAB_BYTES; i += NUTSB_FAN_THREADS) s_tab[i] = A.pop.codetab[i];
+    __syncthreads();
+    const u32 room = s_room;
+    const u32 users_r = (u32)(A.pop.room_slot_off[room + 1] - A.pop.room_slot_off[room]);
+    const u32 chunks = (users_r + NUTSB_UCHUNK - 1) / NUTSB_UCHUNK;
+    const u32 local = blockIdx.x - A.geo.room_item_off[room];
+    const u32 t = local / chunks, chunk = local % chunks;
+    const u32 rb0 = A.geo.room_b_off[room];
+    const u32 g0 = rb0 + t * NUTSB_TILE_OPS;
+    const u32 gend = A.geo.room_b_off[room + 1];
+    const u32 nb = (gend - g0 < NUTSB_TILE_OPS) ? gend - g0 : NUTSB_TILE_OPS;
+    const u32 a0 = t * NUTSB_TILE_OPS;                  // room-local slab rank of the tile's first op
+
+    // -- per-op metadata
+    if ((u32)tid < nb) {
+        const u32 op = A.bl_op[g0 + tid];
+        s_op[tid] = op;
+        s_tlen[tid] = (u32)(A.ops.toff[op + 1] - A.ops.toff[op]);
+        s_kind[tid] = A.ops.kind[op]; s_flags[tid] = A.ops.flags[op]; s_target[tid] = A.ops.target[op];
+    }
+    if ((u32)tid <= nb) {
+        s_oon[tid]  = (u32)(A.cpx.vp_on[g0 + tid]  - A.cpx.vp_on[g0]);
+        s_ooff[tid] = (u32)(A.cpx.vp_off[g0 + tid] - A.cpx.vp_off[g0]);
+    }
+    __syncthreads();
+    if (tid == 0) { u32 acc = 0; for (u32 i = 0; i < nb; ++i) { s_toff[i] = acc; acc += s_tlen[i]; } s_toff[nb] = acc; }
+    __syncthreads();
+
+    const u32 slot0 = (u32)A.pop.room_slot_off[room];
+    const u32 ls_begin = chunk * NUTSB_UCHUNK;
+    const u32 ls_end = (ls_begin + NUTSB_UCHUNK < users_r) ? ls_begin + NUTSB_UCHUNK : users_r;
+    const u64 cell_row = A.geo.room_cell_off[room] + (u64)t * users_r;
+    u32 my_deliv = 0;
+
+    u32 a = 0;
+    while (a < nb) {
+        // -- largest sub-tile [a,b) whose source and both renderings fit in shared memory
+        if (tid == 0) {
+            u32 b = a + 1;
+            while (b < nb && s_toff[b + 1] - s_toff[a] <= NUTSB_TEXT_CAP &&
+                   s_oon[b + 1] - s_oon[a] <= NUTSB_ON_CAP && s_ooff[b + 1] - s_ooff[a] <= NUTSB_OFF_CAP) ++b;
+            s_sub_b = b;
+        }
+        __syncthreads();
+        const u32 b = s_sub_b;
+
+        // -- stage the source strings (a warp per string)
+        for (u32 i = a + warp; i < b; i += NUTSB_FAN_THREADS / 32) {
+            const u8 *src = A.ops.text + A.ops.toff[s_op[i]];
+            u8 *dst = s_text + (s_toff[i] - s_toff[a]);
+            const u32 n = s_tlen[i];
+            for (u32 j = lane; j < n; j += 32) dst[j] = __ldg(src + j);
+        }
+        __syncthreads();
+
+        // -- render: thread j -> op a + j/2, colour j&1
+        for (u32 j = tid; j < 2 * (b - a); j += NUTSB_FAN_THREADS) {
+            const u32 i = a + (j >> 1);
+            const int colour = (int)(j & 1);
+            const u8 *src = s_text + (s_toff[i] - s_toff[a]);
+            u8 *dst = colour ? s_on + (s_oon[i] - s_oon[a]) : s_off + (s_ooff[i] - s_ooff[a]);
+            const u32 got = nutsb_render_seq(src, s_tlen[i], colour, dst, s_tab);
+            const u32 want = colour ? s_oon[i + 1] - s_oon[i] : s_ooff[i + 1] - s_ooff[i];
+            if (got != want) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+        }
+        __syncthreads();
+
+        // -- fan out: one warp per recipient at a time
+        for (u32 ls = ls_begin + warp; ls < ls_end; ls += NUTSB_FAN_THREADS / 32) {
+            const i32 u = A.pop.slot_user[slot0 + ls];
+            const i32 k = A.pop.user_cls[u];
+            const u32 cf = A.pop.cls_flags[k], clv = A.pop.cls_level[k];
+            const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
+            const bool full = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
+            const u32 *offc = colour ? s_oon : s_ooff;
+            const u8 *slab = colour ? s_on : s_off;
+            u64 p = A.cell_pos[cell_row + ls];
+            u32 e = A.cell_evi[cell_row + ls];
+            const u32 e1 = A.cell_evi[cell_row + users_r + ls];
+            u32 cur = 0;
+            for (;;) {
+                // next cut: an event of this recipient inside the tile, or the tile end
+                u32 j = nb; u32 ek = 0; i32 dlt = 0;
+                if (e < e1) {
+                    const u32 uk = A.sv_ukey[e];
+                    const u32 jj = (uk >> 1) - a0;
+                    if (jj < nb || (jj == nb && !(uk & 1))) { j = jj < nb ? jj : nb; ek = (uk & 1) ? 2 : 1; dlt = A.sv_delta[e]; }
+                }
+                // emit slab ops [cur, j)
+                if (full) {
+                    const u32 xs = cur > a ? cur : a, ye = j < b ? j : b;
+                    if (xs < ye) {
+                        nutsb_warp_copy(A.out + p + (offc[xs] - offc[cur]), slab + (offc[xs] - offc[a]),
+                                        offc[ye] - offc[xs], lane);
+                        my_deliv += ye - xs;
+                    }
+                    p += offc[j] - offc[cur];
+                } else {
+                    for (u32 i = cur; i < j; ++i) {
+                        if (!nutsb_class_delivers(cf, clv, s_kind[i], s_flags[i], s_target[i])) continue;
+                        const u32 len = offc[i + 1] - offc[i];
+                        if (i >= a && i < b) { nutsb_warp_copy(A.out + p, slab + (offc[i] - offc[a]), len, lane); ++my_deliv; }
+                        p += len;
+                    }
+                }
+                if (!ek) break;
+                if (ek == 2) cur = j + 1;                 // excluded from op j: nothing emitted for it
+                else { p += (u64)(i64)dlt; cur = j; }      // a direct op's bytes go here (k_direct writes them)
+                ++e;
+                if (cur >= nb && !(e < e1)) break;
+            }
+        }
+        __syncthreads();
+        a = b;
+    }
+    if (lane == 0 && my_deliv) atomicAdd(&s_deliv, my_deliv);
+    __syncthreads();
+    if (tid == 0) {
+        if (s_deliv) nutsb_add64(A.n_deliveries, (u64)s_deliv);
+        if (chunk == 0) nutsb_add64(A.n_deliveries + 2, (u64)s_toff[nb]);   // each slab op's source is read once
+    }
+}
+
+// ---- I. direct ops (write_user) -----------------------------------------------------------
+// One warp per op: classify 32 source bytes per step, ballot the emitted lengths,
+// prefix-sum with popc, store the bytes straight into the user's stream.
+struct DirectArgs {
+    OpsView ops; PopView pop; ClassPrefix cpx;
+    const u32 *room_b_off, *ev_off;
+    const u32 *sv_ukey, *sv_op; const u64 *sv_pre;
+    const u64 *stream_off;
+    const u32 *ev_slot_sorted;      // user slot of each sorted event
+    const i32 *sv_delta;
+    u8 *out; i64 n_ev;
+    u64 *n_deliveries;              // [0] deliveries, [1] bytes written by k_direct, [2] source bytes staged by k_fanout
+};
+
+__device__ __forceinline__ void nutsb_warp_render_global(const u8 *s, u32 n, bool colour, u8 *dst,
+                                                         const u8 *tab, int lane)
+{
+    u32 o = 0;
+    for (u32 base = 0; base < n; base += 32) {
+        const u32 j = base + lane;
+        u32 len = 0; u8 c = 0; int k = -1;
+        if (j < n) {
+            c = s[j];
+            const u8 m1 = j >= 1 ? s[j - 1] : 0, m2 = j >= 2 ? s[j - 2] : 0, m3 = j >= 3 ? s[j - 3] : 0;
+            const u8 p1 = j + 1 < n ? s[j + 1] : 0, p2 = j + 2 < n ? s[j + 2] : 0;
+            if (c == '\n') len = colour ? 6 : 2;
+            else if (c == '/' && p1 == '~' && j + 1 < n) len = 0;
+            else if (c == '~') {
+                if (m1 == '/' && j >= 1) len = 1;
+                else {
+                    if (j + 2 < n) k = nutsb_code(tab, p1, p2);
+                    len = k >= 0 ? (colour ? nutsb_code_len(k) : 0u) : 1u;
+                }
+            } else {
+                // consumed as a command letter?  (commands are A-Z pairs, so c is a letter here)
+                const bool lead1 = j >= 1 && m1 == '~' && !(j >= 2 && m2 == '/') && j + 1 < n && nutsb_code(tab, c, p1) >= 0;
+                const bool lead2 = j >= 2 && m2 == '~' && !(j >= 3 && m3 == '/') && nutsb_code(tab, m1, c) >= 0;
+                len = (lead1 || lead2) ? 0 : 1;
+            }
+        }
+        const u32 b0 = __ballot_sync(NUTSB_FULL, len & 1), b1 = __ballot_sync(NUTSB_FULL, len & 2),
+                  b2 = __ballot_sync(NUTSB_FULL, len & 4);
+        const u32 lt = (1u << lane) - 1;
+        const u32 pre = (u32)__popc(b0 & lt) + 2u * (u32)__popc(b1 & lt) + 4u * (u32)__popc(b2 & lt);
+        u8 *d = dst + o + pre;
+        if (len == 1) d[0] = c;
+        else if (len == 2) { d[0] = '\n'; d[1] = '\r'; }
+        else if (len == 6) { d[0] = 0x1b; d[1] = '['; d[2] = '0'; d[3] = 'm'; d[4] = '\n'; d[5] = '\r'; }
+        else if (len) for (u32 q = 0; q < len; ++q) d[q] = nutsb_code_byte(k, q);
+        o += (u32)__popc(b0) + 2u * (u32)__popc(b1) + 4u * (u32)__popc(b2);
+    }
+    if (colour && lane < 4) dst[o + lane] = lane == 0 ? 0x1b : lane == 1 ? '[' : lane == 2 ? '0' : 'm';
+}
+
+#define NUTSB_DIRECT_THREADS 256
+
+__global__ void __launch_bounds__(NUTSB_DIRECT_THREADS)
+k_direct(DirectArgs A)
+{
+    __shared__ u8 s_tab[NUTSB_CODETAB_BYTES];
+    for (int i = threadIdx.x; i < NUTSB_CODETAB_BYTES; i += blockDim.x) s_tab[i] = A.pop.codetab[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const i64 nwarps = (i64)gridDim.x * (NUTSB_DIRECT_THREADS / 32);
+    u32 cnt = 0; u64 nbytes = 0;
+    for (i64 e = (i64)blockIdx.x * (NUTSB_DIRECT_THREADS / 32) + (threadIdx.x >> 5); e < A.n_ev; e += nwarps) {
+        const u32 uk = A.sv_ukey[e];
+        if (uk & 1) continue;                          // an exclusion, not a direct op
+        const u32 s = A.ev_slot_sorted[e];
+        const i32 u = A.pop.slot_user[s];
+        const u32 room = (u32)A.pop.user_room[u];
+        const i32 k = A.pop.user_cls[u];
+        const u32 b0 = A.room_b_off[room];
+        const u64 p = A.stream_off[u] + (A.cpx.at(k, room, b0 + (uk >> 1)) - A.cpx.at(k, room, b0))
+                    + (A.sv_pre[e] - A.sv_pre[A.ev_off[s]]);
+        const u32 op = A.sv_op[e];
+        const u64 t0 = A.ops.toff[op];
+        nutsb_warp_render_global(A.ops.text + t0, (u32)(A.ops.toff[op + 1] - t0),
+                                 (A.pop.cls_flags[k] & NUTSB_UF_COLOUR) != 0, A.out + p, s_tab, lane);
+        ++cnt; nbytes += (u64)A.sv_delta[e];
+    }
+    if (lane == 0 && cnt) { nutsb_add64(A.n_deliveries, (u64)cnt); nutsb_add64(A.n_deliveries + 1, nbytes); }
+}
+
+// ---- stream digests ------------------------------------------------------------------------
+// h = fold(h * P + byte), h0 = FNV offset basis.  A block per user: each thread
+// folds a contiguous slice as an affine map (mult, add), the block composes them
+// in order.
+#define NUTSB_DIGEST_P  0x100000001b3ull
+#define NUTSB_DIGEST_H0 0xcbf29ce484222325ull
+
+__global__ void __launch_bounds__(256)
+k_digest(const u8 *bytes, const u64 *off, i32 n_users, u64 *digest)
+{
+    __shared__ u64 s_m[256], s_a[256];
+    for (i32 u = blockIdx.x; u < n_users; u += gridDim.x) {
+        const u64 b = off[u], n = off[u + 1] - b;
+        const u64 per = (n + 255) / 256;
+        u64 lo = (u64)threadIdx.x * per, hi = lo + per;
+        if (lo > n) lo = n;
+        if (hi > n) hi = n;
+        u64 m = 1, a = 0;                               // x -> x*m + a
+        for (u64 i = lo; i < hi; ++i) { m *= NUTSB_DIGEST_P; a = a * NUTSB_DIGEST_P + bytes[b + i]; }
+        s_m[threadIdx.x] = m; s_a[threadIdx.x] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 h = NUTSB_DIGEST_H0;
+            for (int q = 0; q < 256; ++q) h = h * s_m[q] + s_a[q];
+            digest[u] = h;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- small bookkeeping kernels -----------------------------------------------------------
+// counts[0] = slab ops, counts[1] = events (from the packed entry scan's total)
+__global__ void k_counts(const u64 *e_scan, i64 n_ent, u32 *counts)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) { const u64 t = e_scan[n_ent]; counts[0] = (u32)t; counts[1] = (u32)(t >> 32); }
+}
+
+struct Sizes {                   // read back by the host before the fan-out is launched
+    u64 total_bytes;
+    u64 cells;
+    u32 n_slab, n_events, items, tiles;
+};
+
+// Per room: tiles, (tile, recipient) cells and fan-out work items; exclusive
+// prefixes over rooms.  One block.
+__global__ void __launch_bounds__(NUTSB_SCAN_THREADS)
+k_geometry(PopView pop, const u32 *room_b_off, const u64 *stream_off, const u32 *counts,
+           u32 *room_tile_off, u64 *room_cell_off, u32 *room_item_off, Sizes *sz)
+{
+    u64 c_tiles = 0, c_cells = 0, c_items = 0;
+    const i32 rt = pop.n_rooms_tot;
+    for (i32 base = 0; base < rt; base += NUTSB_SCAN_THREADS) {
+        const i32 r = base + (i32)threadIdx.x;
+        u64 tiles = 0, cells = 0, items = 0;
+        if (r < rt) {
+            const u64 users = (u64)(pop.room_slot_off[r + 1] - pop.room_slot_off[r]);
+            const u64 nb = room_b_off[r + 1] - room_b_off[r];
+            tiles = (nb + NUTSB_TILE_OPS - 1) / NUTSB_TILE_OPS;
+            cells = (tiles + 1) * users;
+            items = tiles * ((users + NUTSB_UCHUNK - 1) / NUTSB_UCHUNK);
+        }
+        u64 t1, t2, t3;
+        const u64 e1 = nutsb_block_excl_scan(tiles, &t1);
+        const u64 e2 = nutsb_block_excl_scan(cells, &t2);
+        const u64 e3 = nutsb_block_excl_scan(items, &t3);
+        if (r < rt) {
+            room_tile_off[r] = (u32)(c_tiles + e1);
+            room_cell_off[r] = c_cells + e2;
+            room_item_off[r] = (u32)(c_items + e3);
+        }
+        c_tiles += t1; c_cells += t2; c_items += t3;
+    }
+    if (threadIdx.x == 0) {
+        room_tile_off[rt] = (u32)c_tiles; room_cell_off[rt] = c_cells; room_item_off[rt] = (u32)c_items;
+        sz->total_bytes = stream_off[pop.n_users];
+        sz->cells = c_cells; sz->n_slab = counts[0]; sz->n_events = counts[1];
+        sz->items = (u32)c_items; sz->tiles = (u32)c_tiles;
+    }
+}

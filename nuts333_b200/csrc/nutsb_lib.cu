@@ -1,0 +1,873 @@
+// nutsb_lib.cu -- host side of libnutsb200.so: context, tables, population,
+// the write pipeline's orchestration and the C-ABI of include/nutsb200.h.
+//
+// There is no CPU implementation of any entry point in this file: every batch
+// call launches the kernels of nutsb_kernels.cuh / nutsb_match.cuh and fails
+// with NUTSB_E_CUDA when no device is usable.
+#include "nutsb_kernels.cuh"
+#include "nutsb_match.cuh"
+
+#define NUTSB_API extern "C" __attribute__((visibility("default")))
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <new>
+#include <numeric>
+#include <string>
+#include <vector>
+
+// ---------------------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------------------
+struct DBuf {                        // growable device buffer
+    void *p = nullptr; size_t cap = 0;
+    template <class T> T *as() const { return (T *)p; }
+};
+struct HBuf {                        // growable pinned host buffer
+    void *p = nullptr; size_t cap = 0;
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct AcHost {
+    std::vector<u32> trans; u8 clsmap[256]; u32 ncls = 1, nstates = 1, root_match = 0;
+};
+struct AcDev { DBuf trans, clsmap; AcView view{}; bool present = false; };
+struct SetDev { DBuf slot_off, slot_len, pool; SetView view{}; bool present = false; };
+
+struct ClassSet {                    // one class granularity (with / without level)
+    std::vector<i32> user_cls, room_cls_off; std::vector<u8> cls_flags, cls_level;
+    DBuf d_user_cls, d_room_cls_off, d_cls_flags, d_cls_level;
+    i32 n_cls = 0, max_per_room = 0;
+};
+
+struct nutsb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr; bool own_stream = true;
+    int sm_count = 148;
+    std::string err;
+    bool profiling = false; nutsb_timing tm{};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
+    // tables
+    DBuf d_codetab;
+    AcDev swear, site; SetDev userban;
+    bool site_file = false, user_file = false;
+
+    // population
+    bool have_users = false, all_simple = true;
+    i32 U = 0, R = 0, Rt = 1;
+    std::vector<i32> user_room, user_slot, slot_user, room_slot_off;
+    DBuf d_user_room, d_user_slot, d_slot_user, d_room_slot_off;
+    ClassSet cls[2];                 // [0] keyed without level, [1] with level
+
+    // per-batch scratch
+    DBuf d_status, d_len_on, d_len_off, d_nrep, d_eoff, d_sums;
+    DBuf d_ek[2], d_ev_[2];          // (room, op) entries, ping-pong
+    DBuf d_hist, d_hoffs;
+    DBuf d_room_ent_off, d_e_info, d_e_delta, d_e_slot, d_e_scan, d_counts, d_room_b_off;
+    DBuf d_bl_op, d_bl_room, d_evk[2], d_evv[2], d_ev_ukey, d_ev_delta, d_ev_op;
+    DBuf d_sv_ukey, d_sv_delta, d_sv_op, d_sv_pre, d_ev_off;
+    DBuf d_vp_on, d_vp_off, d_cp;
+    DBuf d_room_tile_off, d_room_cell_off, d_room_item_off, d_sizes, d_counters;
+    DBuf d_cell_pos, d_cell_evi;
+    DBuf d_off, d_out, d_digest;
+    HBuf h_small, h_off, h_out;
+    u64 last_total = 0; bool have_streams = false;
+
+    // staging for the host-buffer entry points
+    DBuf s_text, s_toff, s_kind, s_target, s_except, s_flags, s_gate, s_verdict, s_v8;
+
+    // queue tier
+    std::vector<u8> q_text; std::vector<u64> q_off{0}; std::vector<u8> q_kind, q_flags;
+    std::vector<i32> q_target, q_except;
+};
+
+static int fail(nutsb_ctx *c, int code, const char *fmt, const char *a = "")
+{
+    if (c) { char b[512]; snprintf(b, sizeof b, fmt, a); c->err = b; }
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(c, e_ == cudaErrorMemoryAllocation ? NUTSB_E_NOMEM : NUTSB_E_CUDA, #call ": %s", cudaGetErrorString(e_)); } while (0)
+#define CKL() CK(cudaGetLastError())
+#define TRY(x) do { int r_ = (x); if (r_ != NUTSB_OK) return r_; } while (0)
+
+static int ensure(nutsb_ctx *c, DBuf &b, size_t bytes)
+{
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes + 256 <= b.cap) return NUTSB_OK;
+    if (b.p) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 512;             // slack: fewer re-allocations, readable padding
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return NUTSB_OK;
+}
+static int ensure_host(nutsb_ctx *c, HBuf &b, size_t bytes)
+{
+    if (bytes + 64 <= b.cap) return NUTSB_OK;
+    if (b.p) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFreeHost(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 4096;
+    CK(cudaHostAlloc(&b.p, want, cudaHostAllocDefault));
+    b.cap = want;
+    return NUTSB_OK;
+}
+static void release(DBuf &b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+static void release(HBuf &b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+
+static int upload(nutsb_ctx *c, DBuf &b, const void *src, size_t bytes)
+{
+    TRY(ensure(c, b, bytes ? bytes : 1));
+    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return NUTSB_OK;
+}
+
+static inline u32 cdiv(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
+static inline u32 bits_for(u64 n) { u32 b = 0; while (b < 32 && (1ull << b) < n) ++b; return b; }
+
+// ---------------------------------------------------------------------------------------
+// scan / sort drivers
+// ---------------------------------------------------------------------------------------
+struct InU32 { const u32 *p; __device__ u64 operator()(i64 i) const { return p[i]; } };
+struct InI32 { const i32 *p; __device__ u64 operator()(i64 i) const { return (u64)(i64)p[i]; } };
+struct OutU64 { u64 *p; __device__ void operator()(i64 i, u64 ex) const { p[i] = ex; } };
+struct InEntryPacked {
+    const u8 *info;
+    __device__ u64 operator()(i64 i) const { const u32 f = info[i]; return (u64)(f & 1u) | ((u64)((f >> 1) != 0) << 32); }
+};
+struct InSlabLen { const u32 *len, *bl_op; __device__ u64 operator()(i64 g) const { return len[bl_op[g]]; } };
+struct InClassLen {                 // bytes class column j receives from slab op g
+    OpsView ops; const u32 *bl_op, *bl_room, *len_on, *len_off;
+    const i32 *room_cls_off; const u8 *cls_flags, *cls_level; i32 j;
+    __device__ u64 operator()(i64 g) const
+    {
+        const u32 room = bl_room[g], op = bl_op[g];
+        const i32 k = room_cls_off[room] + j;
+        if (k >= room_cls_off[room + 1]) return 0;
+        const u32 cf = cls_flags[k];
+        if (!nutsb_class_delivers(cf, cls_level[k], ops.kind[op], ops.flags[op], ops.target[op])) return 0;
+        return (cf & NUTSB_UF_COLOUR) ? len_on[op] : len_off[op];
+    }
+};
+
+// Exclusive scan of in(0..n) into out(0..n) (out(n) = total).  n = *n_dev when given.
+template <class In, class Out>
+static int run_scan(nutsb_ctx *c, In in, Out out, i64 n_upper, const u32 *n_dev)
+{
+    const u32 nb = cdiv((u64)n_upper + 1, NUTSB_SCAN_TILE);
+    TRY(ensure(c, c->d_sums, ((size_t)nb + 1) * sizeof(u64)));
+    u64 *sums = c->d_sums.as<u64>();
+    auto kr = k_scan_reduce<In>;
+    auto ka = k_scan_apply<In, Out>;
+    NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, kr, in, n_upper, n_dev, sums); CKL();
+    NUTSB_LAUNCH(1, NUTSB_SCAN_THREADS, c->stream, k_scan_sums, sums, (i64)nb); CKL();
+    NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, ka, in, out, n_upper, n_dev, sums); CKL();
+    c->tm.launches += 3;
+    return NUTSB_OK;
+}
+
+// Stable LSD radix sort of (key, val) pairs.  On return *keys / *vals point at
+// the sorted arrays (one of the two ping-pong buffers).  vals start as iota.
+static int radix_sort(nutsb_ctx *c, DBuf kb[2], DBuf vb[2], i64 n_upper, const u32 *n_dev, u32 key_bits,
+                      u32 **keys, u32 **vals)
+{
+    const u32 passes = key_bits ? cdiv(key_bits, NUTSB_RS_BITS) : 1;
+    const u32 nblk = cdiv((u64)(n_upper > 0 ? n_upper : 1), NUTSB_RS_CHUNK);
+    const size_t hn = (size_t)NUTSB_RS_DIGITS * nblk;
+    TRY(ensure(c, c->d_hist, hn * sizeof(u32)));
+    TRY(ensure(c, c->d_hoffs, (hn + 1) * sizeof(u64)));
+    for (int q = 0; q < 2; ++q) { TRY(ensure(c, kb[q], (size_t)n_upper * 4 + 16)); TRY(ensure(c, vb[q], (size_t)n_upper * 4 + 16)); }
+    int cur = 0;
+    for (u32 p = 0; p < passes; ++p) {
+        const int shift = (int)(p * NUTSB_RS_BITS);
+        NUTSB_LAUNCH(nblk, NUTSB_RS_THREADS, c->stream, k_rs_hist, kb[cur].as<u32>(), n_upper, n_dev, shift,
+                     c->d_hist.as<u32>(), nblk); CKL();
+        TRY(run_scan(c, InU32{c->d_hist.as<u32>()}, OutU64{c->d_hoffs.as<u64>()}, (i64)hn, nullptr));
+        NUTSB_LAUNCH(nblk, NUTSB_RS_THREADS, c->stream, k_rs_scatter, kb[cur].as<u32>(),
+                     p == 0 ? (const u32 *)nullptr : vb[cur].as<u32>(), n_upper, n_dev, shift,
+                     c->d_hoffs.as<u64>(), nblk, kb[cur ^ 1].as<u32>(), vb[cur ^ 1].as<u32>()); CKL();
+        c->tm.launches += 2;
+        cur ^= 1;
+    }
+    *keys = kb[cur].as<u32>(); *vals = vb[cur].as<u32>();
+    return NUTSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------------------
+static void build_codetab(u8 *tab)
+{
+    // nuts333.h:248-254, in table order (the index selects the ANSI string)
+    static const char *codes = "RSOLULLIRVFKFRFGFYFBFMFTFWBKBRBGBYBBBMBTBW";
+    memset(tab, 0, NUTSB_CODETAB_BYTES);
+    for (int k = 0; k < 21; ++k) tab[(codes[2 * k] - 'A') * 26 + (codes[2 * k + 1] - 'A')] = (u8)(k + 1);
+}
+
+// Aho-Corasick automaton with full transitions, byte classes, match bit in bit 31.
+static void build_ac(const std::vector<std::string> &pats, bool fold_case, AcHost &ac)
+{
+    u8 word_cls[256]; memset(word_cls, 0, sizeof word_cls);
+    ac.ncls = 1; ac.root_match = 0;
+    size_t total = 1;
+    for (auto &p : pats) {
+        if (p.empty()) ac.root_match = 1;
+        total += p.size();
+        for (unsigned char b : p) if (!word_cls[b]) word_cls[b] = (u8)ac.ncls++;
+    }
+    for (int b = 0; b < 256; ++b) {
+        int f = (fold_case && b >= 'A' && b <= 'Z') ? b + 32 : b;
+        ac.clsmap[b] = word_cls[f];
+    }
+    const u32 nc = ac.ncls;
+    std::vector<i32> go(total * nc, -1);
+    std::vector<u8> match(total, 0);
+    u32 ns = 1;
+    for (auto &p : pats) {
+        u32 s = 0;
+        for (unsigned char b : p) {
+            i32 &nx = go[(size_t)s * nc + word_cls[b]];
+            if (nx < 0) nx = (i32)ns++;
+            s = (u32)nx;
+        }
+        if (!p.empty()) match[s] = 1;
+    }
+    std::vector<u32> failv(ns, 0), queue; queue.reserve(ns);
+    for (u32 ccls = 0; ccls < nc; ++ccls) {
+        i32 &nx = go[ccls];
+        if (nx < 0) nx = 0; else { failv[nx] = 0; queue.push_back((u32)nx); }
+    }
+    for (size_t qi = 0; qi < queue.size(); ++qi) {
+        const u32 s = queue[qi];
+        match[s] |= match[failv[s]];
+        for (u32 ccls = 0; ccls < nc; ++ccls) {
+            i32 &nx = go[(size_t)s * nc + ccls];
+            const u32 via = (u32)go[(size_t)failv[s] * nc + ccls];
+            if (nx < 0) nx = (i32)via; else { failv[nx] = via; queue.push_back((u32)nx); }
+        }
+    }
+    ac.nstates = ns;
+    ac.trans.resize((size_t)ns * nc);
+    for (size_t i = 0; i < (size_t)ns * nc; ++i) {
+        const u32 t = (u32)go[i];
+        ac.trans[i] = t | (match[t] ? 0x80000000u : 0u);
+    }
+}
+
+static int upload_ac(nutsb_ctx *c, const AcHost &h, AcDev &d)
+{
+    TRY(upload(c, d.trans, h.trans.data(), h.trans.size() * sizeof(u32)));
+    TRY(upload(c, d.clsmap, h.clsmap, 256));
+    d.view.trans = d.trans.as<u32>(); d.view.clsmap = d.clsmap.as<u8>();
+    d.view.ncls = h.ncls; d.view.nstates = h.nstates; d.view.root_match = h.root_match;
+    d.present = true;
+    CK(cudaStreamSynchronize(c->stream));
+    return NUTSB_OK;
+}
+
+// The fscanf("%s") / feof loop of nuts333.c:338-342 applied to file bytes: a
+// token is tested only when the scan that read it stopped on a whitespace byte.
+// Tokens reach strstr/strcmp as C strings, i.e. cut at an embedded NUL.
+static int ban_tokens(nutsb_ctx *c, const u8 *f, size_t n, std::vector<std::string> &out)
+{
+    auto ws = [](u8 b) { return b == ' ' || (b >= 9 && b <= 13); };
+    size_t p = 0;
+    while (true) {
+        while (p < n && ws(f[p])) ++p;
+        if (p >= n) break;
+        const size_t b = p;
+        while (p < n && !ws(f[p])) ++p;
+        if (p >= n) break;                          // ran into EOF: feof() already true, never tested
+        if (p - b > NUTSB_MAX_BAN_TOKEN) return fail(c, NUTSB_E_RANGE, "ban token longer than 81 bytes%s");
+        size_t m = 0; while (m < p - b && f[b + m]) ++m;
+        out.emplace_back((const char *)f + b, m);
+    }
+    return NUTSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// C-ABI: lifecycle
+// ---------------------------------------------------------------------------------------
+NUTSB_API int nutsb_version(void) { return NUTSB_VERSION; }
+
+NUTSB_API const char *nutsb_strerror(int code)
+{
+    switch (code) {
+    case NUTSB_OK: return "ok";
+    case NUTSB_E_INVAL: return "invalid argument";
+    case NUTSB_E_NOMEM: return "out of memory";
+    case NUTSB_E_CUDA: return "CUDA error";
+    case NUTSB_E_UNSUPPORTED: return "unsupported recipient type (clone/remote)";
+    case NUTSB_E_RANGE: return "value out of range";
+    case NUTSB_E_STATE: return "call order";
+    }
+    return "unknown";
+}
+NUTSB_API const char *nutsb_last_error(const nutsb_ctx *c) { return c ? c->err.c_str() : ""; }
+
+NUTSB_API void nutsb_destroy(nutsb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DBuf *all[] = { &c->d_codetab, &c->swear.trans, &c->swear.clsmap, &c->site.trans, &c->site.clsmap,
+        &c->userban.slot_off, &c->userban.slot_len, &c->userban.pool,
+        &c->d_user_room, &c->d_user_slot, &c->d_slot_user, &c->d_room_slot_off,
+        &c->cls[0].d_user_cls, &c->cls[0].d_room_cls_off, &c->cls[0].d_cls_flags, &c->cls[0].d_cls_level,
+        &c->cls[1].d_user_cls, &c->cls[1].d_room_cls_off, &c->cls[1].d_cls_flags, &c->cls[1].d_cls_level,
+        &c->d_status, &c->d_len_on, &c->d_len_off, &c->d_nrep, &c->d_eoff, &c->d_sums, &c->d_ek[0], &c->d_ek[1],
+        &c->d_ev_[0], &c->d_ev_[1], &c->d_hist, &c->d_hoffs, &c->d_room_ent_off, &c->d_e_info, &c->d_e_delta,
+        &c->d_e_slot, &c->d_e_scan, &c->d_counts, &c->d_room_b_off, &c->d_bl_op, &c->d_bl_room, &c->d_evk[0],
+        &c->d_evk[1], &c->d_evv[0], &c->d_evv[1], &c->d_ev_ukey, &c->d_ev_delta, &c->d_ev_op, &c->d_sv_ukey,
+        &c->d_sv_delta, &c->d_sv_op, &c->d_sv_pre, &c->d_ev_off, &c->d_vp_on, &c->d_vp_off, &c->d_cp,
+        &c->d_room_tile_off, &c->d_room_cell_off, &c->d_room_item_off, &c->d_sizes, &c->d_counters,
+        &c->d_cell_pos, &c->d_cell_evi, &c->d_off, &c->d_out, &c->d_digest,
+        &c->s_text, &c->s_toff, &c->s_kind, &c->s_target, &c->s_except, &c->s_flags, &c->s_gate, &c->s_verdict, &c->s_v8 };
+    for (DBuf *b : all) release(*b);
+    release(c->h_small); release(c->h_off); release(c->h_out);
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int set_swear_impl(nutsb_ctx *c, const char *const *words)
+{
+    std::vector<std::string> pats;
+    for (size_t i = 0; words && words[i] && words[i][0] != '*'; ++i) pats.emplace_back(words[i]);
+    AcHost h; build_ac(pats, true, h);
+    return upload_ac(c, h, c->swear);
+}
+
+NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
+{
+    if (!out) return NUTSB_E_INVAL;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return NUTSB_E_CUDA;
+    nutsb_ctx *c = new (std::nothrow) nutsb_ctx;
+    if (!c) return NUTSB_E_NOMEM;
+    c->device = device;
+    int rc = [&]() -> int {
+        CK(cudaSetDevice(device));
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+        for (auto &e : c->ev) CK(cudaEventCreate(&e));
+        u8 tab[NUTSB_CODETAB_BYTES]; build_codetab(tab);
+        TRY(upload(c, c->d_codetab, tab, sizeof tab));
+        TRY(ensure(c, c->d_status, 64)); TRY(ensure(c, c->d_counts, 64)); TRY(ensure(c, c->d_sizes, sizeof(Sizes)));
+        TRY(ensure(c, c->d_counters, 64));
+        TRY(ensure_host(c, c->h_small, 4096));
+        static const char *stock[] = { "fuck", "shit", "cunt", "*" };      // nuts333.h:275-277
+        TRY(set_swear_impl(c, stock));
+        CK(cudaStreamSynchronize(c->stream));
+        return NUTSB_OK;
+    }();
+    if (rc != NUTSB_OK) { nutsb_destroy(c); return rc; }
+    *out = c;
+    return NUTSB_OK;
+}
+
+NUTSB_API int nutsb_set_profiling(nutsb_ctx *c, int on) { if (!c) return NUTSB_E_INVAL; c->profiling = on != 0; return NUTSB_OK; }
+NUTSB_API int nutsb_get_timing(const nutsb_ctx *c, nutsb_timing *out) { if (!c || !out) return NUTSB_E_INVAL; *out = c->tm; return NUTSB_OK; }
+NUTSB_API int nutsb_set_stream(nutsb_ctx *c, void *s)
+{
+    if (!c) return NUTSB_E_INVAL;
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)s; c->own_stream = false;
+    return NUTSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// C-ABI: tables and population
+// ---------------------------------------------------------------------------------------
+NUTSB_API int nutsb_set_swear_words(nutsb_ctx *c, const char *const *words)
+{
+    if (!c) return NUTSB_E_INVAL;
+    CK(cudaSetDevice(c->device));
+    return set_swear_impl(c, words);
+}
+
+NUTSB_API int nutsb_set_ban_files(nutsb_ctx *c, const void *siteban, size_t sn, const void *userban, size_t un)
+{
+    if (!c) return NUTSB_E_INVAL;
+    CK(cudaSetDevice(c->device));
+    std::vector<std::string> st, ut;
+    if (siteban) TRY(ban_tokens(c, (const u8 *)siteban, sn, st));
+    if (userban) TRY(ban_tokens(c, (const u8 *)userban, un, ut));
+    c->site_file = siteban != nullptr; c->user_file = userban != nullptr;
+    { AcHost h; build_ac(st, false, h); TRY(upload_ac(c, h, c->site)); }
+    // exact-match set
+    u32 nslots = 1; while (nslots < 2 * ut.size() + 1) nslots <<= 1;
+    std::vector<u32> so(nslots, 0xffffffffu), sl(nslots, 0); std::vector<u8> pool;
+    for (auto &t : ut) {
+        u32 h = 0x811c9dc5u; for (unsigned char b : t) { h ^= b; h *= 0x01000193u; }
+        h &= nslots - 1;
+        while (so[h] != 0xffffffffu) h = (h + 1) & (nslots - 1);
+        so[h] = (u32)pool.size(); sl[h] = (u32)t.size();
+        pool.insert(pool.end(), t.begin(), t.end());
+    }
+    pool.push_back(0);
+    TRY(upload(c, c->userban.slot_off, so.data(), so.size() * 4));
+    TRY(upload(c, c->userban.slot_len, sl.data(), sl.size() * 4));
+    TRY(upload(c, c->userban.pool, pool.data(), pool.size()));
+    c->userban.view.slot_off = c->userban.slot_off.as<u32>(); c->userban.view.slot_len = c->userban.slot_len.as<u32>();
+    c->userban.view.pool = c->userban.pool.as<u8>(); c->userban.view.mask = nslots - 1;
+    c->userban.view.count = (u32)ut.size(); c->userban.present = true;
+    CK(cudaStreamSynchronize(c->stream));
+    return NUTSB_OK;
+}
+
+static int build_classes(nutsb_ctx *c, ClassSet &cs, bool with_level, const std::vector<i32> &order,
+                         const u8 *flags, const u8 *level)
+{
+    const i32 U = c->U, Rt = c->Rt;
+    cs.user_cls.assign(U, 0); cs.room_cls_off.assign(Rt + 1, 0); cs.cls_flags.clear(); cs.cls_level.clear();
+    i32 prev_room = -1; u32 prev_key = 0xffffffffu; i32 k = -1;
+    std::vector<i32> per_room(Rt, 0);
+    for (i32 s = 0; s < U; ++s) {
+        const i32 u = order[s], r = c->user_room[u];
+        const u32 key = (u32)(flags[u] & 0x1f) | (with_level ? (u32)level[u] << 8 : 0u);
+        if (r != prev_room || key != prev_key) {
+            ++k; cs.cls_flags.push_back((u8)(flags[u] & 0x1f)); cs.cls_level.push_back(with_level ? level[u] : 0);
+            per_room[r]++; prev_room = r; prev_key = key;
+        }
+        cs.user_cls[u] = k;
+    }
+    cs.n_cls = k + 1; cs.max_per_room = 0;
+    for (i32 r = 0; r < Rt; ++r) { cs.room_cls_off[r + 1] = cs.room_cls_off[r] + per_room[r]; cs.max_per_room = std::max(cs.max_per_room, per_room[r]); }
+    TRY(upload(c, cs.d_user_cls, cs.user_cls.data(), (size_t)U * 4));
+    TRY(upload(c, cs.d_room_cls_off, cs.room_cls_off.data(), (size_t)(Rt + 1) * 4));
+    TRY(upload(c, cs.d_cls_flags, cs.cls_flags.data(), cs.cls_flags.size()));
+    TRY(upload(c, cs.d_cls_level, cs.cls_level.data(), cs.cls_level.size()));
+    return NUTSB_OK;
+}
+
+NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, const int32_t *room,
+                               const uint8_t *flags, const uint8_t *level)
+{
+    if (!c || n_users < 0 || n_rooms < 0 || (n_users && (!room || !flags || !level))) return fail(c, NUTSB_E_INVAL, "nutsb_set_users: bad argument%s");
+    CK(cudaSetDevice(c->device));
+    for (i32 u = 0; u < n_users; ++u) {
+        if (flags[u] & (NUTSB_UF_CLONE | NUTSB_UF_REMOTE)) return fail(c, NUTSB_E_UNSUPPORTED, "clone/remote recipients are not implemented%s");
+        if (room[u] >= n_rooms || room[u] < -1) return fail(c, NUTSB_E_RANGE, "user room out of range%s");
+    }
+    c->have_users = false; c->have_streams = false;
+    c->U = n_users; c->R = n_rooms; c->Rt = n_rooms + 1;
+    c->user_room.resize(n_users);
+    for (i32 u = 0; u < n_users; ++u) c->user_room[u] = room[u] < 0 ? n_rooms : room[u];
+    // slot order: (room, flags, level, index) -- compatible with both class granularities
+    std::vector<i32> order(n_users); std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](i32 a, i32 b) {
+        if (c->user_room[a] != c->user_room[b]) return c->user_room[a] < c->user_room[b];
+        const u32 ka = (u32)(flags[a] & 0x1f), kb = (u32)(flags[b] & 0x1f);
+        if (ka != kb) return ka < kb;
+        return level[a] < level[b];
+    });
+    c->slot_user = order; c->user_slot.assign(n_users, 0); c->room_slot_off.assign(c->Rt + 1, 0);
+    for (i32 s = 0; s < n_users; ++s) { c->user_slot[order[s]] = s; c->room_slot_off[c->user_room[order[s]] + 1]++; }
+    for (i32 r = 0; r < c->Rt; ++r) c->room_slot_off[r + 1] += c->room_slot_off[r];
+    c->all_simple = true;
+    for (i32 u = 0; u < n_users; ++u) if (flags[u] & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT)) c->all_simple = false;
+    TRY(upload(c, c->d_user_room, c->user_room.data(), (size_t)n_users * 4));
+    TRY(upload(c, c->d_user_slot, c->user_slot.data(), (size_t)n_users * 4));
+    TRY(upload(c, c->d_slot_user, c->slot_user.data(), (size_t)n_users * 4));
+    TRY(upload(c, c->d_room_slot_off, c->room_slot_off.data(), (size_t)(c->Rt + 1) * 4));
+    TRY(build_classes(c, c->cls[0], false, order, flags, level));
+    TRY(build_classes(c, c->cls[1], true, order, flags, level));
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_users = true;
+    return NUTSB_OK;
+}
+
+static PopView pop_view(const nutsb_ctx *c, int with_level)
+{
+    const ClassSet &cs = c->cls[with_level ? 1 : 0];
+    PopView p{};
+    p.n_users = c->U; p.n_rooms = c->R; p.n_rooms_tot = c->Rt;
+    p.user_room = c->d_user_room.as<i32>(); p.user_cls = cs.d_user_cls.as<i32>();
+    p.user_slot = c->d_user_slot.as<i32>(); p.slot_user = c->d_slot_user.as<i32>();
+    p.room_slot_off = c->d_room_slot_off.as<i32>(); p.room_cls_off = cs.d_room_cls_off.as<i32>();
+    p.cls_flags = cs.d_cls_flags.as<u8>(); p.cls_level = cs.d_cls_level.as<u8>();
+    p.codetab = c->d_codetab.as<u8>();
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------
+// the write pipeline (device pointers in, streams in HBM out)
+// ---------------------------------------------------------------------------------------
+static int status_to_error(nutsb_ctx *c, u32 st)
+{
+    if (st & NUTSB_ST_BAD_OFFSETS)   return fail(c, NUTSB_E_INVAL, "text_off is not monotone%s");
+    if (st & NUTSB_ST_TEXT_TOO_LONG) return fail(c, NUTSB_E_RANGE, "string longer than NUTSB_MAX_TEXT (2000) bytes%s");
+    if (st & NUTSB_ST_BAD_KIND)      return fail(c, NUTSB_E_INVAL, "unknown op kind%s");
+    if (st & NUTSB_ST_BAD_INDEX)     return fail(c, NUTSB_E_RANGE, "user/room index out of range%s");
+    if (st & NUTSB_ST_RENDER_MISMATCH) return fail(c, NUTSB_E_CUDA, "internal: rendered length mismatch%s");
+    return NUTSB_OK;
+}
+
+static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
+{
+    if (!c->have_users) return fail(c, NUTSB_E_STATE, "nutsb_set_users has not been called%s");
+    const i64 n = o->n_ops;
+    const i32 U = c->U, Rt = c->Rt;
+    cudaStream_t st = c->stream;
+    c->have_streams = false;
+    c->tm.launches = 0; c->tm.fanout_launches = 0;
+    if (c->profiling) CK(cudaEventRecord(c->ev[0], st));
+
+    TRY(ensure(c, c->d_off, ((size_t)U + 1) * 8));
+    u32 *h32 = c->h_small.as<u32>(); u64 *h64 = c->h_small.as<u64>();
+
+    auto finish_empty = [&]() -> int {
+        CK(cudaMemsetAsync(c->d_off.p, 0, ((size_t)U + 1) * 8, st));
+        TRY(ensure(c, c->d_out, 16));
+        if (c->profiling) { for (int q = 1; q < 4; ++q) CK(cudaEventRecord(c->ev[q], st)); }
+        CK(cudaStreamSynchronize(st));
+        c->last_total = 0; c->have_streams = true;
+        c->tm.fanout_bytes_in = c->tm.fanout_bytes_out = 0;
+        out->n_users = U; out->total_bytes = 0; out->n_deliveries = 0;
+        out->off = c->d_off.as<u64>(); out->bytes = c->d_out.as<u8>(); out->on_device = 1;
+        return NUTSB_OK;
+    };
+    if (n == 0) return finish_empty();
+
+    OpsView ops{ n, o->text, o->text_off, o->kind, o->target, o->except_user, o->flags,
+                 o->gate && o->verdict ? o->gate : nullptr, o->gate && o->verdict ? o->verdict : nullptr };
+    PopView pop0 = pop_view(c, 0);
+
+    // -- A. measure + expansion counts
+    TRY(ensure(c, c->d_len_on, (size_t)n * 4)); TRY(ensure(c, c->d_len_off, (size_t)n * 4));
+    TRY(ensure(c, c->d_nrep, (size_t)n * 4)); TRY(ensure(c, c->d_eoff, ((size_t)n + 1) * 8));
+    CK(cudaMemsetAsync(c->d_status.p, 0, 64, st));
+    CK(cudaMemsetAsync(c->d_counters.p, 0, 64, st));
+    u32 *len_on = c->d_len_on.as<u32>(), *len_off = c->d_len_off.as<u32>(), *nrep = c->d_nrep.as<u32>();
+    NUTSB_LAUNCH(cdiv(n, NUTSB_MEASURE_THREADS), NUTSB_MEASURE_THREADS, st, k_measure, ops, pop0, len_on, len_off, nrep,
+                 c->d_status.as<u32>()); CKL();
+    c->tm.launches++;
+    TRY(run_scan(c, InU32{nrep}, OutU64{c->d_eoff.as<u64>()}, n, nullptr));
+
+    // -- read-back #1: number of (room, op) entries, validation status
+    CK(cudaMemcpyAsync(h64, c->d_eoff.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const u64 E = h64[0]; const u32 status = h32[4];
+    TRY(status_to_error(c, status));
+    if (E == 0) return finish_empty();
+    if (E >= 0xfffffff0ull) return fail(c, NUTSB_E_RANGE, "more than 2^32 (room, op) entries in one batch%s");
+    const bool has_level = (status & NUTSB_ST_HAS_LEVEL) != 0;
+    const bool alias = c->all_simple && !has_level;
+    const PopView pop = pop_view(c, has_level ? 1 : 0);
+    const ClassSet &cs = c->cls[has_level ? 1 : 0];
+
+    // -- B. expand + bucket by room
+    for (int q = 0; q < 2; ++q) { TRY(ensure(c, c->d_ek[q], (size_t)E * 4 + 16)); TRY(ensure(c, c->d_ev_[q], (size_t)E * 4 + 16)); }
+    NUTSB_LAUNCH(cdiv(n, 256), 256, st, k_expand, ops, pop, nrep, c->d_eoff.as<u64>(), c->d_ek[0].as<u32>(), c->d_ev_[0].as<u32>()); CKL();
+    c->tm.launches++;
+    // the op index rides as the key's payload: first pass must not use iota
+    u32 *e_room = nullptr, *e_op = nullptr;
+    {
+        const u32 passes = std::max(1u, cdiv(bits_for((u64)Rt), NUTSB_RS_BITS));
+        const u32 nblk = cdiv(E, NUTSB_RS_CHUNK);
+        const size_t hn = (size_t)NUTSB_RS_DIGITS * nblk;
+        TRY(ensure(c, c->d_hist, hn * 4)); TRY(ensure(c, c->d_hoffs, (hn + 1) * 8));
+        int cur = 0;
+        for (u32 p = 0; p < passes; ++p) {
+            const int shift = (int)(p * NUTSB_RS_BITS);
+            NUTSB_LAUNCH(nblk, NUTSB_RS_THREADS, st, k_rs_hist, c->d_ek[cur].as<u32>(), (i64)E, (const u32 *)nullptr, shift, c->d_hist.as<u32>(), nblk); CKL();
+            TRY(run_scan(c, InU32{c->d_hist.as<u32>()}, OutU64{c->d_hoffs.as<u64>()}, (i64)hn, nullptr));
+            NUTSB_LAUNCH(nblk, NUTSB_RS_THREADS, st, k_rs_scatter, c->d_ek[cur].as<u32>(), c->d_ev_[cur].as<u32>(), (i64)E,
+                         (const u32 *)nullptr, shift, c->d_hoffs.as<u64>(), nblk, c->d_ek[cur ^ 1].as<u32>(), c->d_ev_[cur ^ 1].as<u32>()); CKL();
+            c->tm.launches += 2; cur ^= 1;
+        }
+        e_room = c->d_ek[cur].as<u32>(); e_op = c->d_ev_[cur].as<u32>();
+    }
+    TRY(ensure(c, c->d_room_ent_off, ((size_t)Rt + 2) * 4));
+    NUTSB_LAUNCH(cdiv(E + 1, 256), 256, st, k_seg_bounds, e_room, (i64)E, (const u32 *)nullptr, (u32)Rt, c->d_room_ent_off.as<u32>()); CKL();
+
+    // -- C. classify entries, scatter the slab list and the event list
+    TRY(ensure(c, c->d_e_info, E)); TRY(ensure(c, c->d_e_delta, E * 4)); TRY(ensure(c, c->d_e_slot, E * 4));
+    TRY(ensure(c, c->d_e_scan, (E + 1) * 8));
+    EntryArrays ea{ e_room, e_op, c->d_e_info.as<u8>(), c->d_e_delta.as<i32>(), c->d_e_slot.as<u32>() };
+    NUTSB_LAUNCH(cdiv(E, 256), 256, st, k_entry_info, ops, pop, ea, (i64)E, len_on, len_off); CKL();
+    TRY(run_scan(c, InEntryPacked{c->d_e_info.as<u8>()}, OutU64{c->d_e_scan.as<u64>()}, (i64)E, nullptr));
+    u32 *counts = c->d_counts.as<u32>();
+    NUTSB_LAUNCH(1, 32, st, k_counts, c->d_e_scan.as<u64>(), (i64)E, counts); CKL();
+    TRY(ensure(c, c->d_room_b_off, ((size_t)Rt + 2) * 4));
+    NUTSB_LAUNCH(cdiv((u64)Rt + 1, 256), 256, st, k_room_b_off, c->d_room_ent_off.as<u32>(), c->d_e_scan.as<u64>(), (u32)Rt, c->d_room_b_off.as<u32>()); CKL();
+    TRY(ensure(c, c->d_bl_op, E * 4 + 16)); TRY(ensure(c, c->d_bl_room, E * 4 + 16));
+    for (int q = 0; q < 2; ++q) { TRY(ensure(c, c->d_evk[q], E * 4 + 16)); TRY(ensure(c, c->d_evv[q], E * 4 + 16)); }
+    TRY(ensure(c, c->d_ev_ukey, E * 4)); TRY(ensure(c, c->d_ev_delta, E * 4)); TRY(ensure(c, c->d_ev_op, E * 4));
+    EntryScatter es{ e_room, e_op, c->d_e_info.as<u8>(), c->d_e_delta.as<i32>(), c->d_e_slot.as<u32>(),
+                     c->d_room_ent_off.as<u32>(), c->d_e_scan.as<u64>(), c->d_bl_op.as<u32>(), c->d_bl_room.as<u32>(),
+                     c->d_evk[0].as<u32>(), c->d_ev_ukey.as<u32>(), c->d_ev_op.as<u32>(), c->d_ev_delta.as<i32>() };
+    NUTSB_LAUNCH(cdiv(E, 256), 256, st, k_entry_scatter, es, (i64)E); CKL();
+    c->tm.launches += 5;
+
+    // -- slab prefixes (per colour) and, when classes differ in what they take, per class column
+    TRY(ensure(c, c->d_vp_on, (E + 2) * 8)); TRY(ensure(c, c->d_vp_off, (E + 2) * 8));
+    TRY(run_scan(c, InSlabLen{len_on, c->d_bl_op.as<u32>()}, OutU64{c->d_vp_on.as<u64>()}, (i64)E, counts));
+    TRY(run_scan(c, InSlabLen{len_off, c->d_bl_op.as<u32>()}, OutU64{c->d_vp_off.as<u64>()}, (i64)E, counts));
+    ClassPrefix cpx{ c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(), nullptr, (u64)E + 1, pop.room_cls_off, pop.cls_flags };
+    if (!alias) {
+        const i32 J = std::max(1, cs.max_per_room);
+        TRY(ensure(c, c->d_cp, (size_t)J * (E + 1) * 8));
+        for (i32 j = 0; j < J; ++j) {
+            InClassLen in{ ops, c->d_bl_op.as<u32>(), c->d_bl_room.as<u32>(), len_on, len_off, pop.room_cls_off, pop.cls_flags, pop.cls_level, j };
+            TRY(run_scan(c, in, OutU64{c->d_cp.as<u64>() + (size_t)j * (E + 1)}, (i64)E, counts));
+        }
+        cpx.cp = c->d_cp.as<u64>();
+    }
+
+    // -- D. events: sort by recipient slot, prefix of byte deltas
+    u32 *sv_slot = nullptr, *perm = nullptr;
+    TRY(radix_sort(c, c->d_evk, c->d_evv, (i64)E, counts + 1, bits_for((u64)std::max(U, 1)), &sv_slot, &perm));
+    TRY(ensure(c, c->d_sv_ukey, E * 4 + 16)); TRY(ensure(c, c->d_sv_delta, E * 4 + 16)); TRY(ensure(c, c->d_sv_op, E * 4 + 16));
+    TRY(ensure(c, c->d_sv_pre, (E + 2) * 8)); TRY(ensure(c, c->d_ev_off, ((size_t)U + 2) * 4));
+    NUTSB_LAUNCH(cdiv(E, 256), 256, st, k_ev_gather, perm, counts + 1, c->d_ev_ukey.as<u32>(), c->d_ev_delta.as<i32>(),
+                 c->d_ev_op.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_delta.as<i32>(), c->d_sv_op.as<u32>()); CKL();
+    TRY(run_scan(c, InI32{c->d_sv_delta.as<i32>()}, OutU64{c->d_sv_pre.as<u64>()}, (i64)E, counts + 1));
+    NUTSB_LAUNCH(cdiv(E + 1, 256), 256, st, k_seg_bounds, sv_slot, (i64)E, counts + 1, (u32)U, c->d_ev_off.as<u32>()); CKL();
+    c->tm.launches += 2;
+
+    // -- E. stream offsets, geometry
+    UserLenIn uli{ cpx, pop, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_pre.as<u64>() };
+    TRY(run_scan(c, uli, OutU64{c->d_off.as<u64>()}, (i64)U, nullptr));
+    TRY(ensure(c, c->d_room_tile_off, ((size_t)Rt + 2) * 4)); TRY(ensure(c, c->d_room_cell_off, ((size_t)Rt + 2) * 8));
+    TRY(ensure(c, c->d_room_item_off, ((size_t)Rt + 2) * 4));
+    NUTSB_LAUNCH(1, NUTSB_SCAN_THREADS, st, k_geometry, pop, c->d_room_b_off.as<u32>(), c->d_off.as<u64>(), counts,
+                 c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>(), c->d_sizes.as<Sizes>()); CKL();
+    c->tm.launches++;
+
+    // -- read-back #2: sizes
+    Sizes *hs = (Sizes *)(c->h_small.as<u8>() + 256);
+    CK(cudaMemcpyAsync(hs, c->d_sizes.p, sizeof(Sizes), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const Sizes sz = *hs;
+    TRY(ensure(c, c->d_out, sz.total_bytes + 64));
+    TRY(ensure(c, c->d_cell_pos, (sz.cells + 1) * 8)); TRY(ensure(c, c->d_cell_evi, (sz.cells + 1) * 4));
+    Geometry geo{ c->d_room_b_off.as<u32>(), c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>() };
+    if (U > 0) {
+        NUTSB_LAUNCH(cdiv((u64)U, 256), 256, st, k_fill_pos, pop, geo, cpx, c->d_off.as<u64>(), c->d_ev_off.as<u32>(),
+                     c->d_sv_ukey.as<u32>(), c->d_sv_pre.as<u64>(), c->d_cell_pos.as<u64>(), c->d_cell_evi.as<u32>()); CKL();
+        c->tm.launches++;
+    }
+
+    // -- H. render + fan-out
+    if (c->profiling) CK(cudaEventRecord(c->ev[1], st));
+    u64 *counters = c->d_counters.as<u64>();
+    if (sz.items > 0) {
+        FanoutArgs fa{ ops, pop, geo, cpx, c->d_bl_op.as<u32>(), len_on, len_off, c->d_cell_pos.as<u64>(), c->d_cell_evi.as<u32>(),
+                       c->d_sv_ukey.as<u32>(), c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), counters, c->d_status.as<u32>(), has_level ? 1u : 0u };
+        NUTSB_LAUNCH(sz.items, NUTSB_FAN_THREADS, st, k_fanout, fa); CKL();
+        c->tm.launches++; c->tm.fanout_launches = 1;
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev[2], st));
+
+    // -- I. direct ops
+    if (sz.n_events > 0) {
+        DirectArgs da{ ops, pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_op.as<u32>(),
+                       c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), (i64)sz.n_events, counters };
+        const u32 grid = std::min<u32>(cdiv(sz.n_events, NUTSB_DIRECT_THREADS / 32), (u32)c->sm_count * 8u);
+        NUTSB_LAUNCH(grid, NUTSB_DIRECT_THREADS, st, k_direct, da); CKL();
+        c->tm.launches++;
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev[3], st));
+
+    CK(cudaMemcpyAsync(h64 + 8, counters, 24, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    TRY(status_to_error(c, h32[4]));
+    c->last_total = sz.total_bytes; c->have_streams = true;
+    if (c->profiling) {
+        CK(cudaEventElapsedTime(&c->tm.plan_ms, c->ev[0], c->ev[1]));
+        CK(cudaEventElapsedTime(&c->tm.fanout_ms, c->ev[1], c->ev[2]));
+        CK(cudaEventElapsedTime(&c->tm.direct_ms, c->ev[2], c->ev[3]));
+        CK(cudaEventElapsedTime(&c->tm.total_ms, c->ev[0], c->ev[3]));
+    }
+    c->tm.fanout_bytes_out = sz.total_bytes - h64[9];
+    c->tm.fanout_bytes_in = h64[10];
+    out->n_users = U; out->total_bytes = sz.total_bytes; out->n_deliveries = h64[8];
+    out->off = c->d_off.as<u64>(); out->bytes = c->d_out.as<u8>(); out->on_device = 1;
+    return NUTSB_OK;
+}
+
+static int check_ops(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
+{
+    if (!c || !o || !out || o->n_ops < 0) return fail(c, NUTSB_E_INVAL, "null argument or negative n_ops%s");
+    if (o->n_ops && (!o->text_off || !o->kind || !o->target || !o->except_user || !o->flags))
+        return fail(c, NUTSB_E_INVAL, "ops array is NULL%s");
+    return NUTSB_OK;
+}
+
+NUTSB_API int nutsb_write_batch_dev(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
+{
+    TRY(check_ops(c, o, out));
+    CK(cudaSetDevice(c->device));
+    return run_write(c, o, out);
+}
+
+NUTSB_API int nutsb_write_batch(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
+{
+    TRY(check_ops(c, o, out));
+    CK(cudaSetDevice(c->device));
+    const i64 n = o->n_ops;
+    cudaStream_t st = c->stream;
+    if (c->profiling) CK(cudaEventRecord(c->ev[4], st));
+    nutsb_ops d = *o;
+    if (n > 0) {
+        const u64 t0 = o->text_off[0], t1 = o->text_off[n];
+        if (t1 < t0) return fail(c, NUTSB_E_INVAL, "text_off is not monotone%s");
+        if (t1 > t0 && !o->text) return fail(c, NUTSB_E_INVAL, "text is NULL%s");
+        // text is uploaded from t0 on; offsets are used as they are (base pointer shifted back)
+        TRY(ensure(c, c->s_text, (size_t)(t1 - t0) + 64));
+        if (t1 > t0) CK(cudaMemcpyAsync(c->s_text.p, o->text + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, st));
+        TRY(upload(c, c->s_toff, o->text_off, ((size_t)n + 1) * 8));
+        TRY(upload(c, c->s_kind, o->kind, (size_t)n));
+        TRY(upload(c, c->s_target, o->target, (size_t)n * 4));
+        TRY(upload(c, c->s_except, o->except_user, (size_t)n * 4));
+        TRY(upload(c, c->s_flags, o->flags, (size_t)n));
+        d.text = c->s_text.as<u8>() - t0; d.text_off = c->s_toff.as<u64>(); d.kind = c->s_kind.as<u8>();
+        d.target = c->s_target.as<i32>(); d.except_user = c->s_except.as<i32>(); d.flags = c->s_flags.as<u8>();
+        d.gate = nullptr; d.verdict = nullptr;
+        if (o->gate && o->verdict) {
+            i32 mx = -1; for (i64 i = 0; i < n; ++i) mx = std::max(mx, o->gate[i]);
+            TRY(upload(c, c->s_gate, o->gate, (size_t)n * 4));
+            TRY(upload(c, c->s_verdict, o->verdict, (size_t)(mx + 1)));
+            d.gate = c->s_gate.as<i32>(); d.verdict = c->s_verdict.as<u8>();
+        }
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
+    nutsb_streams ds{};
+    TRY(run_write(c, &d, &ds));
+    if (c->profiling) { CK(cudaEventElapsedTime(&c->tm.h2d_ms, c->ev[4], c->ev[5])); CK(cudaEventRecord(c->ev[4], st)); }
+    TRY(ensure_host(c, c->h_off, ((size_t)c->U + 1) * 8));
+    TRY(ensure_host(c, c->h_out, (size_t)ds.total_bytes + 16));
+    CK(cudaMemcpyAsync(c->h_off.p, ds.off, ((size_t)c->U + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (ds.total_bytes) CK(cudaMemcpyAsync(c->h_out.p, ds.bytes, (size_t)ds.total_bytes, cudaMemcpyDeviceToHost, st));
+    if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    if (c->profiling) CK(cudaEventElapsedTime(&c->tm.d2h_ms, c->ev[4], c->ev[5]));
+    *out = ds;
+    out->off = c->h_off.as<u64>(); out->bytes = c->h_out.as<u8>(); out->on_device = 0;
+    return NUTSB_OK;
+}
+
+NUTSB_API int nutsb_stream_digests(nutsb_ctx *c, uint64_t *digest)
+{
+    if (!c || !digest) return NUTSB_E_INVAL;
+    if (!c->have_streams) return fail(c, NUTSB_E_STATE, "no write batch has run%s");
+    CK(cudaSetDevice(c->device));
+    if (c->U == 0) return NUTSB_OK;
+    TRY(ensure(c, c->d_digest, (size_t)c->U * 8));
+    const u32 grid = std::min<u32>((u32)c->U, (u32)c->sm_count * 16u);
+    NUTSB_LAUNCH(grid, 256, c->stream, k_digest, c->d_out.as<u8>(), c->d_off.as<u64>(), c->U, c->d_digest.as<u64>()); CKL();
+    CK(cudaMemcpyAsync(digest, c->d_digest.p, (size_t)c->U * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return NUTSB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// verdict batches
+// ---------------------------------------------------------------------------------------
+static int run_ac(nutsb_ctx *c, const AcDev &ac, i64 n, const u8 *bytes, const u64 *off, u8 *verdict)
+{
+    if (n == 0) return NUTSB_OK;
+    const u32 grid = cdiv(n, NUTSB_AC_THREADS);
+    const bool smem = ac.view.nstates <= 32768u && (u64)ac.view.nstates * ac.view.ncls <= NUTSB_AC_SMEM_ENTRIES;
+    if (smem) { NUTSB_LAUNCH(grid, NUTSB_AC_THREADS, c->stream, k_ac_match<true>, bytes, off, n, ac.view, verdict); }
+    else      { NUTSB_LAUNCH(grid, NUTSB_AC_THREADS, c->stream, k_ac_match<false>, bytes, off, n, ac.view, verdict); }
+    CKL();
+    return NUTSB_OK;
+}
+
+enum { V_SWEAR, V_SITE, V_USER };
+
+static int verdict_dev(nutsb_ctx *c, int which, i64 n, const u8 *bytes, const u64 *off, u8 *verdict)
+{
+    if (!c || n < 0 || (n && (!off || !verdict))) return fail(c, NUTSB_E_INVAL, "bad argument%s");
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return NUTSB_OK;
+    if (which == V_SWEAR) return run_ac(c, c->swear, n, bytes, off, verdict);
+    if (which == V_SITE) {
+        if (!c->site_file || !c->site.present) { CK(cudaMemsetAsync(verdict, 0, (size_t)n, c->stream)); return NUTSB_OK; }   // c:337
+        return run_ac(c, c->site, n, bytes, off, verdict);
+    }
+    if (!c->user_file || !c->userban.present) { CK(cudaMemsetAsync(verdict, 0, (size_t)n, c->stream)); return NUTSB_OK; }       // c:356
+    NUTSB_LAUNCH(cdiv(n, 256), 256, c->stream, k_set_match, bytes, off, n, c->userban.view, verdict); CKL();
+    return NUTSB_OK;
+}
+
+static int verdict_host(nutsb_ctx *c, int which, i64 n, const u8 *bytes, const u64 *off, u8 *verdict)
+{
+    if (!c || n < 0 || (n && (!off || !verdict))) return fail(c, NUTSB_E_INVAL, "bad argument%s");
+    CK(cudaSetDevice(c->device));
+    if (n == 0) return NUTSB_OK;
+    const u64 t0 = off[0], t1 = off[n];
+    if (t1 < t0 || (t1 > t0 && !bytes)) return fail(c, NUTSB_E_INVAL, "bad offsets%s");
+    for (i64 i = 0; i < n; ++i) if (off[i + 1] < off[i]) return fail(c, NUTSB_E_INVAL, "offsets are not monotone%s");
+    TRY(ensure(c, c->s_text, (size_t)(t1 - t0) + 64));
+    if (t1 > t0) CK(cudaMemcpyAsync(c->s_text.p, bytes + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, c->stream));
+    TRY(upload(c, c->s_toff, off, ((size_t)n + 1) * 8));
+    TRY(ensure(c, c->s_v8, (size_t)n));
+    TRY(verdict_dev(c, which, n, c->s_text.as<u8>() - t0, c->s_toff.as<u64>(), c->s_v8.as<u8>()));
+    CK(cudaMemcpyAsync(verdict, c->s_v8.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return NUTSB_OK;
+}
+
+NUTSB_API int nutsb_contains_swearing_batch(nutsb_ctx *c, int64_t n, const uint8_t *b, const uint64_t *o, uint8_t *v) { return verdict_host(c, V_SWEAR, n, b, o, v); }
+NUTSB_API int nutsb_contains_swearing_batch_dev(nutsb_ctx *c, int64_t n, const uint8_t *b, const uint64_t *o, uint8_t *v) { return verdict_dev(c, V_SWEAR, n, b, o, v); }
+NUTSB_API int nutsb_site_banned_batch(nutsb_ctx *c, int64_t n, const uint8_t *b, const uint64_t *o, uint8_t *v) { return verdict_host(c, V_SITE, n, b, o, v); }
+NUTSB_API int nutsb_site_banned_batch_dev(nutsb_ctx *c, int64_t n, const uint8_t *b, const uint64_t *o, uint8_t *v) { return verdict_dev(c, V_SITE, n, b, o, v); }
+NUTSB_API int nutsb_user_banned_batch(nutsb_ctx *c, int64_t n, const uint8_t *b, const uint64_t *o, uint8_t *v) { return verdict_host(c, V_USER, n, b, o, v); }
+NUTSB_API int nutsb_user_banned_batch_dev(nutsb_ctx *c, int64_t n, const uint8_t *b, const uint64_t *o, uint8_t *v) { return verdict_dev(c, V_USER, n, b, o, v); }
+
+static int verdict_one(nutsb_ctx *c, int which, const char *s)
+{
+    if (!c || !s) return NUTSB_E_INVAL;
+    const u64 off[2] = { 0, (u64)strlen(s) };
+    u8 v = 0;
+    const int rc = verdict_host(c, which, 1, (const u8 *)s, off, &v);
+    return rc < 0 ? rc : (int)v;
+}
+NUTSB_API int nutsb_contains_swearing(nutsb_ctx *c, const char *s) { return verdict_one(c, V_SWEAR, s); }
+NUTSB_API int nutsb_site_banned(nutsb_ctx *c, const char *s) { return verdict_one(c, V_SITE, s); }
+NUTSB_API int nutsb_user_banned(nutsb_ctx *c, const char *s) { return verdict_one(c, V_USER, s); }
+
+// ---------------------------------------------------------------------------------------
+// queue tier
+// ---------------------------------------------------------------------------------------
+static int q_push(nutsb_ctx *c, u8 kind, i32 target, const char *str, i32 except_user, u8 flags)
+{
+    if (!c || !str) return NUTSB_E_INVAL;
+    const size_t n = strlen(str);
+    if (n > NUTSB_MAX_TEXT) return fail(c, NUTSB_E_RANGE, "string longer than NUTSB_MAX_TEXT (2000) bytes%s");
+    c->q_text.insert(c->q_text.end(), (const u8 *)str, (const u8 *)str + n);   // copied: callers reuse text[] at once
+    c->q_off.push_back((u64)c->q_text.size());
+    c->q_kind.push_back(kind); c->q_target.push_back(target); c->q_except.push_back(except_user); c->q_flags.push_back(flags);
+    return NUTSB_OK;
+}
+NUTSB_API int nutsb_q_write_user(nutsb_ctx *c, int32_t user, const char *str) { return q_push(c, NUTSB_OP_USER, user, str, -1, 0); }
+NUTSB_API int nutsb_q_write_room_except(nutsb_ctx *c, int32_t room, const char *str, int32_t except_user, int force_listen, int shout)
+{ return q_push(c, NUTSB_OP_ROOM, room, str, except_user, (u8)((force_listen ? NUTSB_OF_FORCE_LISTEN : 0) | (shout ? NUTSB_OF_SHOUT : 0))); }
+NUTSB_API int nutsb_q_write_room(nutsb_ctx *c, int32_t room, const char *str, int force_listen, int shout)
+{ return nutsb_q_write_room_except(c, room, str, -1, force_listen, shout); }
+NUTSB_API int nutsb_q_write_level(nutsb_ctx *c, int level, int above, const char *str, int32_t except_user)
+{ return q_push(c, NUTSB_OP_LEVEL, level, str, except_user, above ? NUTSB_OF_ABOVE : 0); }
+NUTSB_API int64_t nutsb_q_pending(const nutsb_ctx *c) { return c ? (int64_t)c->q_kind.size() : 0; }
+
+NUTSB_API int nutsb_flush(nutsb_ctx *c, nutsb_streams *out)
+{
+    if (!c || !out) return NUTSB_E_INVAL;
+    nutsb_ops o{};
+    o.n_ops = (i64)c->q_kind.size();
+    static const u8 zero = 0;
+    o.text = c->q_text.empty() ? &zero : c->q_text.data(); o.text_off = c->q_off.data();
+    o.kind = c->q_kind.data(); o.target = c->q_target.data(); o.except_user = c->q_except.data(); o.flags = c->q_flags.data();
+    const int rc = nutsb_write_batch(c, &o, out);
+    c->q_text.clear(); c->q_off.assign(1, 0); c->q_kind.clear(); c->q_target.clear(); c->q_except.clear(); c->q_flags.clear();
+    return rc;
+}

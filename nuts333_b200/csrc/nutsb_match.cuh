@@ -1,0 +1,121 @@
+// nutsb_match.cuh -- contains_swearing / site_banned / user_banned kernels.
+//
+//   contains_swearing (nuts333.c:2540-2559): "some list word is a substring of
+//   the lower-cased string"  -> Aho-Corasick automaton over the word list, byte
+//   classes fold A-Z onto a-z (tolower in the C locale, c:2657).
+//   site_banned (c:330-345): "some tested token of datafiles/siteban is a
+//   substring of the site" -> the same automaton, no case folding.
+//   user_banned (c:349-364): "some tested token equals the name" -> hash set.
+//
+// One thread per string.  The 32 strings of a warp are a contiguous byte range:
+// it is staged in shared memory with coalesced 16-byte loads.  The transition
+// table lives in shared memory when it fits (the 64-word swear list: ~22 KB),
+// else it is read through L1/L2 (the 10k-entry site list: ~20 MB, L2-resident).
+#pragma once
+#include "nutsb_common.cuh"
+
+struct AcView {
+    const u32 *trans;        // [nstates][ncls]; bit31 = target state is a match state
+    const u8  *clsmap;       // [256] byte -> class (0 = byte absent from every pattern)
+    u32 ncls, nstates;
+    u32 root_match;          // an empty pattern: every string matches (strstr(s,"") != NULL)
+};
+
+#define NUTSB_AC_THREADS     128
+#define NUTSB_AC_WARP_BYTES  4096
+#define NUTSB_AC_SMEM_ENTRIES 12288      // u16 entries (24 KB)
+
+template <bool SMEM_DFA>
+__global__ void __launch_bounds__(NUTSB_AC_THREADS)
+k_ac_match(const u8 *text, const u64 *off, i64 n, AcView ac, u8 *verdict)
+{
+    __shared__ __align__(16) u8 s_stage[NUTSB_AC_THREADS / 32][NUTSB_AC_WARP_BYTES + 32];
+    __shared__ u8 s_cls[256];
+    __shared__ u16 s_tr[SMEM_DFA ? NUTSB_AC_SMEM_ENTRIES : 1];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = ac.clsmap[i];
+    if (SMEM_DFA) {
+        const u32 cnt = ac.nstates * ac.ncls;
+        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const u32 t = ac.trans[i];
+            s_tr[i] = (u16)((t & 0x7fffu) | ((t >> 31) << 15));
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 wbase = (i64)blockIdx.x * NUTSB_AC_THREADS + warp * 32;
+    if (wbase >= n) return;
+    const i64 wend = (wbase + 32 < n) ? wbase + 32 : n;
+    const u64 b0 = off[wbase], b1 = off[wend];
+    const u8 *pa = (const u8 *)((size_t)(text + b0) & ~(size_t)15);
+    const u64 span = (u64)((text + b1) - pa);
+    const bool staged = (b1 >= b0) && span <= NUTSB_AC_WARP_BYTES;
+    u8 *stage = s_stage[warp];
+    if (staged) {
+        const u32 nvec = (u32)((span + 15) >> 4);
+        for (u32 v = lane; v < nvec; v += 32) *(uint4 *)(stage + 16 * v) = __ldg((const uint4 *)pa + v);
+    }
+    __syncwarp();
+    const i64 i = wbase + lane;
+    if (i >= n) return;
+    const u64 o0 = off[i], o1 = off[i + 1];
+    u32 hit = ac.root_match ? 1u : 0u;
+    if (!hit && o1 > o0) {
+        const u8 *s = staged ? stage + ((text + o0) - pa) : text + o0;
+        const u32 len = (u32)(o1 - o0);
+        u32 st = 0;
+        for (u32 j = 0; j < len; ++j) {
+            const u32 c = s_cls[s[j]];
+            if (SMEM_DFA) {
+                const u32 t = s_tr[st * ac.ncls + c];
+                if (t & 0x8000u) { hit = 1; break; }
+                st = t;
+            } else {
+                const u32 t = __ldg(ac.trans + (size_t)st * ac.ncls + c);
+                if (t >> 31) { hit = 1; break; }
+                st = t;
+            }
+        }
+    }
+    verdict[i] = (u8)hit;
+}
+
+// Exact-match set: open addressing, 32-bit FNV-1a, linear probing.
+struct SetView {
+    const u32 *slot_off;     // [nslots] offset into pool, 0xffffffff = empty
+    const u32 *slot_len;     // [nslots]
+    const u8  *pool;
+    u32 mask;                // nslots - 1 (power of two), 0 when the set is empty
+    u32 count;
+};
+
+__device__ __forceinline__ u32 nutsb_fnv32(const u8 *p, u32 n)
+{
+    u32 h = 0x811c9dc5u;
+    for (u32 i = 0; i < n; ++i) { h ^= p[i]; h *= 0x01000193u; }
+    return h;
+}
+
+__global__ void __launch_bounds__(256)
+k_set_match(const u8 *text, const u64 *off, i64 n, SetView set, u8 *verdict)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 hit = 0;
+    if (set.count) {
+        const u8 *s = text + off[i];
+        const u32 len = (u32)(off[i + 1] - off[i]);
+        u32 h = nutsb_fnv32(s, len) & set.mask;
+        for (;;) {
+            const u32 so = set.slot_off[h];
+            if (so == 0xffffffffu) break;
+            if (set.slot_len[h] == len) {
+                u32 j = 0;
+                while (j < len && set.pool[so + j] == s[j]) ++j;
+                if (j == len) { hit = 1; break; }
+            }
+            h = (h + 1) & set.mask;
+        }
+    }
+    verdict[i] = (u8)hit;
+}
