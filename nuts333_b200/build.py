@@ -50,6 +50,24 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+GEN_LIB = PKG / "_lib" / "libnutsgen.so"
+GEN_SRC = CSRC / "nutsb_gen.c"
+
+
+def build_gen(force: bool = False) -> Path:
+    """The synthetic input generator (host C, shared by the oracle legs and the GPU driver)."""
+    if not force and GEN_LIB.exists() and GEN_LIB.stat().st_mtime >= GEN_SRC.stat().st_mtime:
+        return GEN_LIB
+    GEN_LIB.parent.mkdir(parents=True, exist_ok=True)
+    cc = os.environ.get("CC") or shutil.which("gcc") or "cc"
+    r = subprocess.run([cc, "-O2", "-std=c99", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall",
+                        "-o", str(GEN_LIB), str(GEN_SRC)], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed:\n" + r.stderr)
+    return GEN_LIB
+
+
 if __name__ == "__main__":
     import sys
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_gen(force="--force" in sys.argv))
