@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- rendered messages/s of the NUTS message path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic input per rank:
+BASELINE config 3 (1M say() messages x 10k users in 100 rooms of 100, 64-word swear
+list, ban_swearing on: contains_swearing -> gated write_user / write_room_except ->
+colour render + fan-out) plus config 4's ban verdicts (100k sites + 100k names vs
+10k-entry lists).  Ranks own disjoint rooms (weak scaling, no data-path collective).
+
+value = deliveries/s ("rendered messages/s") with inputs resident in HBM, timed with
+CUDA events on the stream the kernels run on, max over ranks.  e2e = the same through
+the host-buffer C-ABI (nutsb_*_batch with pinned host inputs, per-user streams copied
+back to pinned host memory).  roofline = the render+fan-out kernel's algorithmic bytes
+over its own CUDA-event time vs the measured HBM copy bandwidth.  cpu_baseline = the
+reference's own C routines (oracle/_ref, built from nuts333.c) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "rendered messages/sec (colour+swear+ban)"
+UNIT = "deliveries/s"
+
+# per-rank shard of the workload
+N_MSGS = 1_000_000
+N_USERS = 10_000
+USERS_PER_ROOM = 100
+N_SWEAR = 64
+N_BAN_QUERIES = 100_000
+N_BAN_ENTRIES = 10_000
+SEED = 0x333
+
+
+def workload_name():
+    return ("C3+C4 per rank: %d say() msgs x %d users (%d rooms of %d), %d-word swear list, ban_swearing; "
+            "%d sites + %d names vs %d-entry ban lists" % (N_MSGS, N_USERS, N_USERS // USERS_PER_ROOM, USERS_PER_ROOM,
+                                                           N_SWEAR, N_BAN_QUERIES, N_BAN_QUERIES, N_BAN_ENTRIES))
+
+
+def make_inputs(rank: int, n_msgs: int):
+    """The rank's shard, generated on the host once (same generator for every leg)."""
+    from nuts333_b200 import synth
+    seed = SEED + 0x1000 * rank            # every rank owns different rooms / messages
+    words = synth.swear_words(N_SWEAR)
+    users, n_rooms = synth.users(N_USERS, USERS_PER_ROOM, seed=seed)
+    bt, bo = synth.bodies(n_msgs, words, seed=seed)
+    ops, spk, rm = synth.say_ops(n_msgs, N_USERS, USERS_PER_ROOM, bt, bo, gated=True, seed=seed)
+    st, so = synth.sites(N_BAN_QUERIES, seed=seed)
+    nt, no = synth.names(N_BAN_QUERIES)
+    sfile = synth.ban_file(0, N_BAN_ENTRIES, N_BAN_QUERIES, N_BAN_QUERIES, True, seed=seed)
+    ufile = synth.ban_file(1, N_BAN_ENTRIES, N_BAN_QUERIES, N_BAN_QUERIES, True, seed=seed)
+    return dict(words=words, users=users, n_rooms=n_rooms, bodies=(bt, bo), ops=ops, sites=(st, so), names=(nt, no),
+                sfile=sfile, ufile=ufile)
+
+
+# ---------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc, self.th = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.th = threading.Thread(target=self._read, daemon=True)
+        self.th.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own C routines on host cores
+# ---------------------------------------------------------------------------------------
+def _ref_worker(args):
+    """One process = one single-threaded reference instance (its state is global) on one
+    room-shard of the sample.  Returns (deliveries, bytes, seconds, kind)."""
+    rank, shard, n_shards, n_msgs, n_ban = args
+    import tempfile
+    import oracle_lib as O
+    inp = make_inputs(rank, n_msgs)
+    words, users, ops = inp["words"], inp["users"], inp["ops"]
+    R = O.ref()
+    if R is not None:
+        R._tmp = tempfile.mkdtemp(prefix="nutsref_cwd_")     # per process: the reference reads ./datafiles/
+    kind = "reference" if R is not None else "port"
+    P = O.port()
+    bt, bo = inp["bodies"]
+    # this worker's share: messages whose room % n_shards == shard
+    room_of_op = ops["target"].copy()
+    k1 = ops["kind"] == 1
+    msg_room = room_of_op[k1]
+    mine_msg = (msg_room % n_shards) == shard
+    mine_op = np.repeat(mine_msg, 3)
+    sel = np.nonzero(mine_op)[0]
+    lens = np.diff(ops["off"].astype(np.int64))
+    sub_texts = [ops["text"][int(ops["off"][i]):int(ops["off"][i + 1])].tobytes() for i in sel]
+    text, off = O.pack(sub_texts)
+    msg_idx = np.nonzero(mine_msg)[0]
+    remap = -np.ones(len(mine_msg), np.int64)
+    remap[msg_idx] = np.arange(len(msg_idx))
+    sub = dict(text=text, off=off, kind=ops["kind"][sel], target=ops["target"][sel], except_user=ops["except_user"][sel],
+               flags=ops["flags"][sel], gate=remap[ops["gate"][sel]].astype(np.int32))
+    bsel = [bt[int(bo[i]):int(bo[i + 1])].tobytes() for i in msg_idx]
+    b2, bo2 = O.pack(bsel)
+    st, so = inp["sites"]
+    nt, no = inp["names"]
+    qs = [st[int(so[i]):int(so[i + 1])].tobytes() for i in range(shard, n_ban, n_shards)]
+    qn = [nt[int(no[i]):int(no[i + 1])].tobytes() for i in range(shard, n_ban, n_shards)]
+    qst, qso = O.pack(qs)
+    qnt, qno = O.pack(qn)
+    t0 = time.perf_counter()
+    if R is not None:
+        R.set_swear_words(words[:-1])
+        R.set_ban_file(0, inp["sfile"]); R.set_ban_file(1, inp["ufile"])
+        v = R.contains_swearing_batch(b2, bo2)
+        R.ban_batch(0, qst, qso); R.ban_batch(1, qnt, qno)
+        R.write_batch(sub, inp["n_rooms"], users, verdict=v, sink_mode=1)
+        deliveries = None
+        nbytes = int(R.lib.ref_total_write_bytes())
+        dt = time.perf_counter() - t0
+        deliveries, _ = P.write_batch_count(sub, users, verdict=v)      # counted outside the timed region
+    else:
+        v = P.contains_swearing_batch(b2, bo2, words)
+        P.ban_batch(0, inp["sfile"], qst, qso); P.ban_batch(1, inp["ufile"], qnt, qno)
+        deliveries, nbytes = P.write_batch_count(sub, users, verdict=v)
+        dt = time.perf_counter() - t0
+    return deliveries, nbytes, dt, kind
+
+
+def reference_step(rank: int, n_msgs: int, n_ban: int, procs: int):
+    """Runs the reference's CPU path over a bounded sample with `procs` host processes."""
+    import multiprocessing as mp
+    import oracle_lib as O
+    O.port(); O.ref()                       # build / load the checkers once, before forking
+    args = [(rank, s, procs, n_msgs, n_ban) for s in range(procs)]
+    t0 = time.perf_counter()
+    if procs == 1:
+        res = [_ref_worker(args[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_ref_worker, args)
+    wall = time.perf_counter() - t0
+    d = sum(r[0] for r in res)
+    busy = max(r[2] for r in res)
+    return d, sum(r[1] for r in res), busy, wall, res[0][3]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    procs = max(1, os.cpu_count() or 1)
+    procs = min(procs, 64)
+    n_msgs = min(20_000 * max(1, procs // 4), N_MSGS)
+    n_ban = max(procs, n_msgs * N_BAN_QUERIES // N_MSGS)        # the sample keeps the step's msgs : ban-queries ratio
+    times, deliv = [], 0
+    for i in range(args.warmup + args.steps):
+        d, nbytes, busy, wall, kind = reference_step(0, n_msgs, n_ban, procs)
+        if i >= args.warmup:
+            times.append(busy); deliv += d
+    total = sum(times)
+    value = deliv / total
+    sample = ("%d of %d msgs (all %d users, same generator) + %d of %d ban queries per list, per step; "
+              "%d single-threaded reference processes sharded by room; write(2) hooked to a byte counter"
+              % (n_msgs, N_MSGS, N_USERS, n_ban, N_BAN_QUERIES, procs))
+    line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 * total / max(1, args.steps), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
+                config=dict(workload=workload_name(), note="reference CPU path on a bounded sample of the workload"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=procs, kind=kind, sample=sample),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nuts333_b200 import api, build
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    build.build()
+    dev = torch.device("cuda", local)
+
+    inp = make_inputs(rank, N_MSGS)
+    ops, users = inp["ops"], inp["users"]
+    ctx = api.Context(local)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_profiling(True)
+    ctx.set_swear_words(inp["words"])
+    ctx.set_ban_files(inp["sfile"], inp["ufile"])
+    ctx.set_users(users["room"], users["flags"], users["level"], inp["n_rooms"])
+
+    def to_dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def pad16(a):                      # packed text buffers are read in 16-byte vectors
+        return np.concatenate([a, np.zeros(32, np.uint8)])
+
+    bt, bo = inp["bodies"]
+    st_, so_ = inp["sites"]
+    nt_, no_ = inp["names"]
+    d = dict(bt=to_dev(pad16(bt)), bo=to_dev(bo.view(np.int64)), text=to_dev(pad16(ops["text"])),
+             off=to_dev(ops["off"].view(np.int64)), kind=to_dev(ops["kind"]), target=to_dev(ops["target"]),
+             exc=to_dev(ops["except_user"]), flags=to_dev(ops["flags"]), gate=to_dev(ops["gate"]),
+             st=to_dev(pad16(st_)), so=to_dev(so_.view(np.int64)), nt=to_dev(pad16(nt_)), no=to_dev(no_.view(np.int64)),
+             verdict=torch.zeros(N_MSGS, dtype=torch.uint8, device=dev),
+             vs=torch.zeros(N_BAN_QUERIES, dtype=torch.uint8, device=dev),
+             vu=torch.zeros(N_BAN_QUERIES, dtype=torch.uint8, device=dev))
+    n_ops = len(ops["kind"])
+    input_bytes = sum(int(v.numel() * v.element_size()) for k, v in d.items() if k not in ("verdict", "vs", "vu"))
+    torch.cuda.synchronize()
+
+    state = dict(deliv=0, bytes=0, launches=0, fan_ms=0.0, fan_in=0, fan_out=0, plan_ms=0.0, direct_ms=0.0)
+
+    def step_device():
+        with torch.cuda.stream(stream):
+            ctx.verdicts_dev("contains_swearing", N_MSGS, d["bt"].data_ptr(), d["bo"].data_ptr(), d["verdict"].data_ptr())
+            ctx.verdicts_dev("site_banned", N_BAN_QUERIES, d["st"].data_ptr(), d["so"].data_ptr(), d["vs"].data_ptr())
+            ctx.verdicts_dev("user_banned", N_BAN_QUERIES, d["nt"].data_ptr(), d["no"].data_ptr(), d["vu"].data_ptr())
+            s = ctx.write_batch_dev(n_ops, d["text"].data_ptr(), d["off"].data_ptr(), d["kind"].data_ptr(),
+                                    d["target"].data_ptr(), d["exc"].data_ptr(), d["flags"].data_ptr(),
+                                    d["gate"].data_ptr(), d["verdict"].data_ptr())
+        t = ctx.timing()
+        state["deliv"] += int(s.n_deliveries); state["bytes"] += int(s.total_bytes)
+        state["launches"] += int(t.launches) + 3
+        state["fan_ms"] += float(t.fanout_ms); state["fan_in"] += int(t.fanout_bytes_in); state["fan_out"] += int(t.fanout_bytes_out)
+        state["plan_ms"] += float(t.plan_ms); state["direct_ms"] += float(t.direct_ms)
+        return s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    for k in state:
+        state[k] = 0 if not isinstance(state[k], float) else 0.0
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    dev_state = dict(state)
+
+    # ---- e2e: host buffers through the C-ABI, H2D and D2H inside the timed region
+    hops = dict(ops)
+    e2e_ms, e2e_deliv, h2d, d2h = 0.0, 0, 0, 0
+    e2e_steps = max(1, min(args.steps, 3))
+    for i in range(1 + e2e_steps):              # first pass allocates the pinned result buffers
+        barrier()
+        t0 = time.perf_counter()
+        v = ctx.contains_swearing_batch(bt, bo)
+        vs = ctx.site_banned_batch(st_, so_)
+        vu = ctx.user_banned_batch(nt_, no_)
+        keep = []
+        o = ctx._ops_struct(dict(hops, verdict=v), keep)
+        s = api._Streams()
+        ctx._ck(ctx.lib.nutsb_write_batch(ctx._h, o, s))
+        first = int(np.ctypeslib.as_array(api.C.cast(s.bytes, api.u8p), shape=(16,))[0])     # touch the result
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_ms += dt * 1e3; e2e_deliv += int(s.n_deliveries)
+            h2d = int(bt.nbytes + bo.nbytes + st_.nbytes + so_.nbytes + nt_.nbytes + no_.nbytes + ops["text"].nbytes
+                      + ops["off"].nbytes + 2 * n_ops + 12 * n_ops + v.nbytes)
+            d2h = int(s.total_bytes) + 8 * (N_USERS + 1) + v.nbytes + vs.nbytes + vu.nbytes
+    # ---- reduce over ranks
+    vals = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([dev_state["deliv"], e2e_deliv, dev_state["launches"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max = float(vals[0]), float(vals[1])
+    total_deliv, total_e2e_deliv, total_launch = float(sums[0]), float(sums[1]), int(sums[2])
+
+    if rank == 0:
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        fan_bytes = (dev_state["fan_in"] + dev_state["fan_out"]) / max(1, args.steps)
+        fan_ms = dev_state["fan_ms"] / max(1, args.steps)
+        achieved = fan_bytes / (fan_ms * 1e-3) / 1e9 if fan_ms > 0 else 0.0
+        traffic = None
+        tp = ROOT / "profiles" / "fanout_traffic.json"
+        if tp.exists():
+            try:
+                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = dict(metric=METRIC, value=total_deliv / (ms_max * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms_max / max(1, args.steps), higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="u8", data="synthetic",
+                    config=dict(workload=workload_name(), sharding="rooms per rank, no collective",
+                                l2="inputs (%.0f MB) and outputs (%.1f GB) per step exceed the 126 MB L2; no flush needed"
+                                   % (input_bytes / 1e6, dev_state["bytes"] / max(1, args.steps) / 1e9),
+                                source_msgs_per_s=world * N_MSGS * args.steps / (ms_max * 1e-3),
+                                ban_queries_per_step=2 * N_BAN_QUERIES,
+                                plan_ms=dev_state["plan_ms"] / max(1, args.steps), fanout_ms=fan_ms,
+                                direct_ms=dev_state["direct_ms"] / max(1, args.steps)),
+                    roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                                  traffic=traffic, kernel="k_fanout", peak_source=peak_src,
+                                  algorithmic_bytes_per_launch=fan_bytes),
+                    e2e=dict(value=total_e2e_deliv / (e2e_ms_max * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d,
+                             d2h_bytes_per_step=d2h, steps=e2e_steps),
+                    gpu_launches=total_launch, clocks=clk)
+        if world == 1 and not args.no_cpu_baseline:
+            procs = 1
+            dcpu, nbytes, busy, wall, kind = reference_step(0, 40_000, 4_000, procs)
+            line["cpu_baseline"] = dict(value=dcpu / busy, unit=UNIT, cores=procs, kind=kind,
+                                        sample="40000 of 1000000 msgs (all 10000 users) + 4000 of 100000 ban queries per "
+                                               "list, one single-threaded reference process, write(2) hooked to a byte counter")
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
