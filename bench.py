@@ -319,7 +319,7 @@ def run_ours(args):
     hops = dict(ops)
     e2e_ms, e2e_deliv, h2d, d2h = 0.0, 0, 0, 0
     e2e_steps = max(1, min(args.steps, 3))
-    for i in range(1 + e2e_steps):              # first pass allocates the pinned result buffers
+    for i in range(0 if args.no_e2e else 1 + e2e_steps):   # first pass allocates the pinned result buffers
         barrier()
         t0 = time.perf_counter()
         v = ctx.contains_swearing_batch(bt, bo)
@@ -376,8 +376,9 @@ def run_ours(args):
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                                   traffic=traffic, kernel="k_fanout", peak_source=peak_src,
                                   algorithmic_bytes_per_launch=fan_bytes),
-                    e2e=dict(value=total_e2e_deliv / (e2e_ms_max * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d,
-                             d2h_bytes_per_step=d2h, steps=e2e_steps),
+                    e2e=(None if args.no_e2e else
+                         dict(value=total_e2e_deliv / (e2e_ms_max * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d,
+                              d2h_bytes_per_step=d2h, steps=e2e_steps)),
                     gpu_launches=total_launch, clocks=clk)
         if world == 1 and not args.no_cpu_baseline:
             procs = 1
@@ -400,6 +401,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

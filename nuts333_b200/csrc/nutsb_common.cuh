@@ -11,6 +11,10 @@
 #include <cuda_runtime.h>
 #define NUTSB_LAUNCH(grid, block, stream, kern, ...) \
     kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define NUTSB_LAUNCH_SMEM(grid, block, smem, stream, kern, ...) \
+    kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// dynamic shared memory of the running block, 16-byte aligned
+#define NUTSB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
 #include "../../include/nutsb200.h"

@@ -27,6 +27,8 @@ struct PopView {                 // the population, built by nutsb_set_users
     const i32 *user_cls;         // [U]  global class id
     const i32 *user_slot;        // [U]  position in (room, class, index) order
     const i32 *slot_user;        // [U]
+    const u8  *slot_cf;          // [U]  recipient flags by slot (NUTSB_UF_*)
+    const u8  *slot_lv;          // [U]  level by slot
     const i32 *room_slot_off;    // [Rt+1]
     const i32 *room_cls_off;     // [Rt+1]
     const u8  *cls_flags;        // [K]
@@ -34,11 +36,12 @@ struct PopView {                 // the population, built by nutsb_set_users
     const u8  *codetab;          // [676]
 };
 
-#define NUTSB_TILE_OPS   64      // room-list ops per fan-out tile
+#define NUTSB_TILE_OPS   128     // room-list ops per fan-out tile
 #define NUTSB_UCHUNK     128     // recipients per fan-out work item
-#define NUTSB_TEXT_CAP   8192    // staged source bytes per (sub)tile
+#define NUTSB_TEXT_CAP   12288   // staged source bytes per (sub)tile   (>= 2000+6)
 #define NUTSB_ON_CAP     16384   // rendered bytes per (sub)tile, colour on  (>= 6*2000+4)
-#define NUTSB_OFF_CAP    8192    // rendered bytes per (sub)tile, colour off (>= 2*2000)
+#define NUTSB_OFF_CAP    12288   // rendered bytes per (sub)tile, colour off (>= 2*2000)
+#define NUTSB_EV_CAP     256     // events of a tile's recipients prefetched into shared memory
 
 // ---- A. measure ------------------------------------------------------------------
 // One thread per op: rendered length for both colour settings, liveness (gate),
@@ -90,23 +93,32 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
     if (n64 > NUTSB_MAX_TEXT) { atomicOr(status, NUTSB_ST_TEXT_TOO_LONG); len_on[i] = len_off[i] = nrep[i] = 0; return; }
     const u32 n = (u32)n64;
 
+    // liveness first: a gated-off op is neither measured nor bucketed
+    bool live = true;
+    if (ops.gate && ops.gate[i] >= 0) {
+        const bool v = ops.verdict[ops.gate[i]] != 0;
+        live = ((ops.flags[i] & NUTSB_OF_GATE_IF_SET) != 0) == v;
+    }
+
     u32 nl = 0, drops = 0, m4 = 0, m5 = 0;
-    if (staged) {
+    if (!live) {
+    } else if (staged) {
         const u32 p0 = (u32)((ops.text + o0) - pa), p1 = p0 + n;
         for (u32 w = p0 >> 2; w < (p1 + 3) >> 2; ++w) {
             const u32 x = *(const u32 *)(stage + 4 * w);
-            if (!nutsb_word_has(x, '~') && !nutsb_word_has(x, '\n')) continue;
-            for (u32 b = 0; b < 4; ++b) {
-                const u32 j = 4 * w + b;
-                if (j < p0 || j >= p1) continue;
-                const u8 c = (u8)(x >> (8 * b));
-                if (c == '\n') ++nl;
-                else if (c == '~') {
-                    if (j > p0 && stage[j - 1] == '/') ++drops;
-                    else if (j + 2 < p1) {
-                        int k = nutsb_code(s_tab, stage[j + 1], stage[j + 2]);
-                        if (k >= 0) { if (k < 5) ++m4; else ++m5; }
-                    }
+            // bytes of this word that belong to the string
+            const u32 lo = p0 > 4 * w ? p0 - 4 * w : 0, hi = p1 < 4 * w + 4 ? p1 - 4 * w : 4;
+            const u32 vm = (0xffffffffu << (8 * lo)) & (0xffffffffu >> (8 * (4 - hi)));
+            nl += (u32)__popc(__vcmpeq4(x, 0x0a0a0a0au) & vm) >> 3;
+            u32 mt = __vcmpeq4(x, 0x7e7e7e7eu) & vm;
+            while (mt) {                                   // each '~' of the word, in order
+                const u32 bb = (u32)(__ffs((int)mt) - 1) >> 3;
+                mt &= ~(0xffu << (8 * bb));
+                const u32 j = 4 * w + bb;
+                if (j > p0 && stage[j - 1] == '/') ++drops;
+                else if (j + 2 < p1) {
+                    const int k = nutsb_code(s_tab, stage[j + 1], stage[j + 2]);
+                    if (k >= 0) { if (k < 5) ++m4; else ++m5; }
                 }
             }
         }
@@ -128,12 +140,7 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
     len_off[i] = loff;
     len_on[i]  = loff + 4 * nl + 4 * m4 + 5 * m5 + 4;
 
-    // liveness + fan-in: how many room lists this op enters
-    bool live = true;
-    if (ops.gate && ops.gate[i] >= 0) {
-        const bool v = ops.verdict[ops.gate[i]] != 0;
-        live = ((ops.flags[i] & NUTSB_OF_GATE_IF_SET) != 0) == v;
-    }
+    // fan-in: how many room lists this op enters
     const u32 kind = ops.kind[i];
     const i32 tgt = ops.target[i], exc = ops.except_user[i];
     u32 rep = 0;
@@ -372,70 +379,212 @@ struct Geometry {
     const u32 *room_item_off;    // [Rt+1] fan-out work items before room r
 };
 
+// One thread per cell: where in the recipient's stream the tile's first op
+// starts (class prefix + the recipient's own exclusions / direct ops before the
+// tile), and which of the recipient's events is the first one inside the tile.
 __global__ void __launch_bounds__(256)
 k_fill_pos(PopView pop, Geometry geo, ClassPrefix cpx, const u64 *stream_off,
-           const u32 *ev_off, const u32 *sv_ukey, const u64 *sv_pre, u64 *cell_pos, u32 *cell_evi)
+           const u32 *ev_off, const u32 *sv_ukey, const u64 *sv_pre, u64 n_cells, u64 *cell_pos, u32 *cell_evi)
 {
-    const i32 s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= pop.n_users) return;
-    const i32 u = pop.slot_user[s];
-    const u32 room = (u32)pop.user_room[u];
-    const i32 k = pop.user_cls[u];
+    const u64 cell = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= n_cells) return;
+    u32 lo = 0, hi = (u32)pop.n_rooms_tot;               // last room with room_cell_off[r] <= cell
+    while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (geo.room_cell_off[mid] <= cell) lo = mid; else hi = mid; }
+    const u32 room = lo;
     const u32 users_r = (u32)(pop.room_slot_off[room + 1] - pop.room_slot_off[room]);
-    const u32 ls = (u32)(s - pop.room_slot_off[room]);
+    const u64 local = cell - geo.room_cell_off[room];
+    const u32 t = (u32)(local / users_r), ls = (u32)(local % users_r);
+    const u32 s = (u32)pop.room_slot_off[room] + ls;
     const u32 b0 = geo.room_b_off[room], nb = geo.room_b_off[room + 1] - b0;
     const u32 tiles = (nb + NUTSB_TILE_OPS - 1) / NUTSB_TILE_OPS;
-    const u64 base = stream_off[u] - cpx.at(k, room, b0);
-    u32 ptr = ev_off[s];
-    const u32 end = ev_off[s + 1];
-    const u64 pre0 = sv_pre[ptr];
-    u64 cell = geo.room_cell_off[room] + ls;
-    for (u32 t = 0; t < tiles; ++t, cell += users_r) {
-        const u32 a0 = t * NUTSB_TILE_OPS;
-        while (ptr < end && sv_ukey[ptr] < 2 * a0 + 1) ++ptr;
-        cell_pos[cell] = base + cpx.at(k, room, b0 + a0) + (sv_pre[ptr] - pre0);
-        cell_evi[cell] = ptr;
-    }
-    cell_pos[cell] = 0; cell_evi[cell] = end;
+    const u32 e0 = ev_off[s], e1 = ev_off[s + 1];
+    if (t >= tiles) { cell_pos[cell] = 0; cell_evi[cell] = e1; return; }      // sentinel row
+    const u32 a0 = t * NUTSB_TILE_OPS, thr = 2 * a0 + 1;
+    u32 l = e0, h = e1;                                   // first event with ukey >= thr
+    while (l < h) { const u32 mid = (l + h) >> 1; if (sv_ukey[mid] < thr) l = mid + 1; else h = mid; }
+    const i32 u = pop.slot_user[s];
+    const i32 k = pop.user_cls[u];
+    cell_pos[cell] = stream_off[u] + (cpx.at(k, room, b0 + a0) - cpx.at(k, room, b0)) + (sv_pre[l] - sv_pre[e0]);
+    cell_evi[cell] = l;
 }
 
+// ---- write_user's byte machine, one thread per string ------------------------------------
+// Restates nuts333.c:1315-1365.  The string sits in shared memory; words that
+// hold none of '~' '/' '\n' are copied four bytes at a time, the rest goes
+// through the byte-wise machine.  Emits the colour-on rendering, the colour-off
+// rendering, or both in one pass (the parse is shared).
+__device__ __forceinline__ u32 nutsb_special_mask(u32 w)
+{
+    const u32 y0 = w ^ 0x7e7e7e7eu, y1 = w ^ 0x2f2f2f2fu, y2 = w ^ 0x0a0a0a0au;
+    return (((y0 - 0x01010101u) & ~y0) | ((y1 - 0x01010101u) & ~y1) | ((y2 - 0x01010101u) & ~y2)) & 0x80808080u;
+}
+
+// Bytes of colcode[k] (nuts333.h:237-246), little-endian in one register pair.
+__device__ __forceinline__ u64 nutsb_code_pack(int k)
+{
+    if (k < 5) return 0x1bull | ((u64)'[' << 8) | ((u64)('0' + ((0x75410u >> (4 * k)) & 0xf)) << 16) | ((u64)'m' << 24);
+    return 0x1bull | ((u64)'[' << 8) | ((u64)(k < 13 ? '3' : '4') << 16) | ((u64)('0' + ((k - 5) & 7)) << 24) | ((u64)'m' << 32);
+}
+#define NUTSB_RESET_PACK 0x6d305b1bull     /* ESC [ 0 m */
+
+// One step takes either a whole aligned plain word (4 bytes) or one byte of the
+// machine; what it emits is a (length, packed bytes) pair per colour setting,
+// stored with predicated byte stores -- the step is straight-line code, so the
+// 32 strings of a warp stay converged.  The string must sit in a window that
+// starts at a 4-byte boundary (nutsb_lane_stage / nutsb_warp_stage).
+template <bool ON, bool OFF>
+__device__ __forceinline__ void nutsb_render(const u8 *s, u32 n, u8 *oon, u8 *ooff, const u8 *tab, u32 *len_on, u32 *len_off)
+{
+    u32 i = 0, a = 0, b = 0;
+    while (i < n) {
+        const u8 *p = s + i;
+        const u32 al = (u32)(size_t)p & 3u;
+        const u32 w = *(const u32 *)(p - al);
+        u32 adv = 4, lon = 4, loff = 4, voff = w;
+        u64 von = w;
+        if (al != 0 || i + 4 > n || nutsb_special_mask(w)) {
+            const u32 c = (w >> (8 * al)) & 0xffu;
+            adv = 1; lon = 1; loff = 1; von = c; voff = c;
+            if (c == '\n') {                                                   /* c:1316-1326 */
+                lon = 6; von = NUTSB_RESET_PACK | ((u64)'\n' << 32) | ((u64)'\r' << 40);
+                loff = 2; voff = (u32)'\n' | ((u32)'\r' << 8);
+            } else if (c == '/') {                                             /* c:1330 */
+                if (i + 1 < n && p[1] == '~') { lon = 0; loff = 0; }
+            } else if (c == '~') {                                             /* c:1331-1354 */
+                if (!(i > 0 && p[-1] == '/') && i + 2 < n) {
+                    const int k = nutsb_code(tab, p[1], p[2]);
+                    if (k >= 0) { adv = 3; loff = 0; lon = nutsb_code_len(k); von = nutsb_code_pack(k); }
+                }
+            }
+        }
+        if (ON) {
+            if (lon > 0) oon[a] = (u8)von;
+            if (lon > 1) oon[a + 1] = (u8)(von >> 8);
+            if (lon > 2) oon[a + 2] = (u8)(von >> 16);
+            if (lon > 3) oon[a + 3] = (u8)(von >> 24);
+            if (lon > 4) oon[a + 4] = (u8)(von >> 32);
+            if (lon > 5) oon[a + 5] = (u8)(von >> 40);
+            a += lon;
+        }
+        if (OFF) {
+            if (loff > 0) ooff[b] = (u8)voff;
+            if (loff > 1) ooff[b + 1] = (u8)(voff >> 8);
+            if (loff > 2) ooff[b + 2] = (u8)(voff >> 16);
+            if (loff > 3) ooff[b + 3] = (u8)(voff >> 24);
+            b += loff;
+        }
+        i += adv;
+    }
+    if (ON) { oon[a] = 0x1b; oon[a + 1] = '['; oon[a + 2] = '0'; oon[a + 3] = 'm'; a += 4; }      /* c:1365 */
+    *len_on = a; *len_off = b;
+}
+
+// One lane stages its own string (32-bit loads; lanes of a warp walk 32 different
+// strings, L1 absorbs the overlap).  Same window convention as nutsb_warp_stage.
+__device__ __forceinline__ void nutsb_lane_stage(u8 *dst, const u8 *src, u32 n)
+{
+    const u32 a = (u32)((size_t)src & 3);
+    const u32 *g = (const u32 *)(src - a);
+    const u32 nw = (a + n + 3) >> 2;
+    for (u32 w = 0; w < nw; ++w) ((u32 *)dst)[w] = __ldg(g + w);
+}
+
+// One lane copies its own rendered string from shared memory to an arbitrary
+// byte address: head bytes to a 4-byte boundary, realigned 32-bit stores, tail.
+__device__ __forceinline__ void nutsb_lane_copy(u8 *dst, const u8 *src, u32 n)
+{
+    u32 head = (u32)((4 - ((size_t)dst & 3)) & 3);
+    if (head > n) head = n;
+    for (u32 q = 0; q < head; ++q) dst[q] = src[q];
+    dst += head; src += head; n -= head;
+    const u32 nw = n >> 2;
+    const u32 sm = (u32)((size_t)src & 3);
+    const u32 *sa = (const u32 *)(src - sm);
+    const u32 bsh = 8 * sm;
+    u32 prev = nw ? sa[0] : 0;
+    for (u32 j = 0; j < nw; ++j) {
+        const u32 nxt = sa[j + 1];
+        ((u32 *)dst)[j] = __funnelshift_r(prev, nxt, bsh);
+        prev = nxt;
+    }
+    for (u32 q = 4 * nw; q < n; ++q) dst[q] = src[q];
+}
+
+// Stage one string into shared memory with 32-bit loads: the window starts at
+// the aligned word holding the first byte, so dst must be 4-byte aligned and the
+// string then begins at dst + ((size_t)src & 3).  Reads whole words: up to 3
+// bytes either side of the string (inside the packed text allocation).
+__device__ __forceinline__ void nutsb_warp_stage(u8 *dst, const u8 *src, u32 n, int lane)
+{
+    const u32 a = (u32)((size_t)src & 3);
+    const u32 *g = (const u32 *)(src - a);
+    const u32 nw = (a + n + 3) >> 2;
+    for (u32 w = lane; w < nw; w += 32) ((u32 *)dst)[w] = __ldg(g + w);
+}
+__device__ __forceinline__ u32 nutsb_stage_bytes(const u8 *src, u32 n) { return (((u32)((size_t)src & 3)) + n + 3) & ~3u; }
+
 // ---- warp copy: shared -> global at arbitrary byte alignment --------------------------
-// Head and tail bytes are stored singly; the body is 16-byte stores whose source
-// is realigned with funnel shifts from two 16-byte shared loads.  src buffers
-// carry >= 32 bytes of readable padding.
+// The destination's first partial 16-byte chunk and its last are stored byte by
+// byte (lanes 0-15 the head, lanes 16-31 the tail, one pass); the body is
+// 16-byte stores, fully coalesced, two in flight per lane.  The source is
+// realigned in registers from two 16-byte shared loads; the word part of the
+// shift is a template parameter so no selects are executed.  src buffers carry
+// >= 48 bytes of readable padding.
+template <int WSH>
+__device__ __forceinline__ uint4 nutsb_realign(const uint4 &a, const uint4 &b, u32 bsh)
+{
+    const u32 W[8] = { a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w };
+    uint4 o;
+    o.x = __funnelshift_r(W[WSH], W[WSH + 1], bsh);     o.y = __funnelshift_r(W[WSH + 1], W[WSH + 2], bsh);
+    o.z = __funnelshift_r(W[WSH + 2], W[WSH + 3], bsh); o.w = __funnelshift_r(W[WSH + 3], W[WSH + 4], bsh);
+    return o;
+}
+template <int WSH>
+__device__ __forceinline__ void nutsb_copy_body(u8 *dst, const uint4 *sa, u32 nvec, u32 bsh, int lane)
+{
+    u32 v = (u32)lane;
+    for (; v + 32 < nvec; v += 64) {
+        const uint4 a0 = sa[v], b0 = sa[v + 1], a1 = sa[v + 32], b1 = sa[v + 33];
+        *(uint4 *)(dst + 16 * (size_t)v) = nutsb_realign<WSH>(a0, b0, bsh);
+        *(uint4 *)(dst + 16 * (size_t)(v + 32)) = nutsb_realign<WSH>(a1, b1, bsh);
+    }
+    if (v < nvec) *(uint4 *)(dst + 16 * (size_t)v) = nutsb_realign<WSH>(sa[v], sa[v + 1], bsh);
+}
+
 __device__ __forceinline__ void nutsb_warp_copy(u8 *dst, const u8 *src, u32 n, int lane)
 {
     if (n == 0) return;
     u32 head = (u32)((16 - ((size_t)dst & 15)) & 15);
     if (head > n) head = n;
-    if ((u32)lane < head) dst[lane] = src[lane];
-    dst += head; src += head; n -= head;
-    const u32 nvec = n >> 4;
+    const u32 nvec = (n - head) >> 4, tail = (n - head) & 15, toff = head + 16 * nvec;
+    {   // head (lanes 0-15) and tail (lanes 16-31) bytes in one pass
+        const u32 l2 = (u32)lane & 15;
+        const bool is_tail = lane >= 16;
+        const u32 idx = is_tail ? toff + l2 : l2;
+        if (l2 < (is_tail ? tail : head)) dst[idx] = src[idx];
+    }
+    if (nvec == 0) return;
+    dst += head; src += head;
     const u32 sm = (u32)((size_t)src & 15);
     const uint4 *sa = (const uint4 *)(src - sm);
-    const u32 wsh = sm >> 2, bsh = (sm & 3) * 8;
-    for (u32 v = lane; v < nvec; v += 32) {
-        const uint4 a = sa[v], b = sa[v + 1];
-        u32 w0 = a.x, w1 = a.y, w2 = a.z, w3 = a.w, w4 = b.x, w5 = b.y, w6 = b.z, w7 = b.w;
-        if (wsh & 1) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7; }
-        if (wsh & 2) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; }
-        uint4 o;
-        o.x = __funnelshift_r(w0, w1, bsh); o.y = __funnelshift_r(w1, w2, bsh);
-        o.z = __funnelshift_r(w2, w3, bsh); o.w = __funnelshift_r(w3, w4, bsh);
-        *(uint4 *)(dst + 16 * (size_t)v) = o;
+    const u32 bsh = (sm & 3) * 8;
+    switch (sm >> 2) {
+    case 0:  nutsb_copy_body<0>(dst, sa, nvec, bsh, lane); break;
+    case 1:  nutsb_copy_body<1>(dst, sa, nvec, bsh, lane); break;
+    case 2:  nutsb_copy_body<2>(dst, sa, nvec, bsh, lane); break;
+    default: nutsb_copy_body<3>(dst, sa, nvec, bsh, lane); break;
     }
-    const u32 tail = n & 15;
-    if ((u32)lane < tail) dst[16 * (size_t)nvec + lane] = src[16 * (size_t)nvec + lane];
 }
 
 // ---- H. render + fan-out ----------------------------------------------------------------
 // One work item = (room, tile of <=64 slab ops, chunk of <=128 recipients).
-// The block stages the tile's source strings in shared memory, renders each
-// once per colour setting (one thread per (op, colour): the byte machine is
-// sequential, shared -> shared), then every warp takes recipients in turn and
-// copies that recipient's view of the tile -- normally ONE contiguous run of
-// the rendered slab, cut only where the recipient is the excluded speaker or
-// has a direct write_user op in between -- to its place in the user's stream.
+// The block stages the tile's source strings in shared memory, renders each once
+// (one thread per op, both colour settings in one pass: the byte machine is
+// sequential, shared -> shared), prefetches the chunk's per-recipient cells, then
+// every warp takes recipients in turn and copies that recipient's view of the
+// tile -- normally ONE contiguous run of the rendered slab, cut only where the
+// recipient is the excluded speaker or has a direct write_user op in between --
+// to its place in the user's stream.
 struct FanoutArgs {
     OpsView ops; PopView pop; Geometry geo; ClassPrefix cpx;
     const u32 *bl_op;
@@ -449,22 +598,30 @@ struct FanoutArgs {
 };
 
 #define NUTSB_FAN_THREADS 256
+#define NUTSB_FAN_SMEM (NUTSB_TEXT_CAP + 32 + NUTSB_ON_CAP + 64 + NUTSB_OFF_CAP + 64)
 
 __global__ void __launch_bounds__(NUTSB_FAN_THREADS)
 k_fanout(FanoutArgs A)
 {
-    __shared__ __align__(16) u8 s_text[NUTSB_TEXT_CAP + 32];
-    __shared__ __align__(16) u8 s_on[NUTSB_ON_CAP + 48];
-    __shared__ __align__(16) u8 s_off[NUTSB_OFF_CAP + 48];
+    NUTSB_DYN_SMEM(s_dyn);                       // NUTSB_FAN_SMEM bytes: staged source + the two rendered slabs
+    u8 *const s_text = s_dyn;
+    u8 *const s_on = s_dyn + NUTSB_TEXT_CAP + 32;
+    u8 *const s_off = s_on + NUTSB_ON_CAP + 64;
     __shared__ u8  s_tab[NUTSB_CODETAB_BYTES];
-    __shared__ u32 s_op[NUTSB_TILE_OPS];
+    __shared__ u64 s_src[NUTSB_TILE_OPS];        // byte offset of each string in the packed text
     __shared__ u32 s_tlen[NUTSB_TILE_OPS];
-    __shared__ u32 s_toff[NUTSB_TILE_OPS + 1];
+    __shared__ u32 s_toff[NUTSB_TILE_OPS + 1];   // prefix of staged (word-aligned) sizes
     __shared__ u32 s_oon[NUTSB_TILE_OPS + 1];
     __shared__ u32 s_ooff[NUTSB_TILE_OPS + 1];
     __shared__ u8  s_kind[NUTSB_TILE_OPS];
     __shared__ u8  s_flags[NUTSB_TILE_OPS];
     __shared__ i32 s_target[NUTSB_TILE_OPS];
+    __shared__ u64 s_upos[NUTSB_UCHUNK];         // per recipient of the chunk
+    __shared__ u32 s_uev0[NUTSB_UCHUNK], s_uev1[NUTSB_UCHUNK], s_uevb[NUTSB_UCHUNK];
+    __shared__ u8  s_ucf[NUTSB_UCHUNK], s_ulv[NUTSB_UCHUNK];
+    __shared__ u32 s_evk[NUTSB_EV_CAP];          // the chunk's events inside this tile
+    __shared__ i32 s_evd[NUTSB_EV_CAP];
+    __shared__ u32 s_evn;
     __shared__ u32 s_sub_b;
     __shared__ u32 s_room;
     __shared__ u32 s_deliv;
@@ -476,12 +633,13 @@ k_fanout(FanoutArgs A)
         const u32 item = blockIdx.x;
         u32 lo = 0, hi = (u32)A.pop.n_rooms_tot;        // last r with room_item_off[r] <= item
         while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (A.geo.room_item_off[mid] <= item) lo = mid; else hi = mid; }
-        s_room = lo; s_deliv = 0;
+        s_room = lo; s_deliv = 0; s_evn = 0;
     }
     for (int i = tid; i < NUTSB_CODETAB_BYTES; i += NUTSB_FAN_THREADS) s_tab[i] = A.pop.codetab[i];
     __syncthreads();
     const u32 room = s_room;
-    const u32 users_r = (u32)(A.pop.room_slot_off[room + 1] - A.pop.room_slot_off[room]);
+    const u32 slot0 = (u32)A.pop.room_slot_off[room];
+    const u32 users_r = (u32)A.pop.room_slot_off[room + 1] - slot0;
     const u32 chunks = (users_r + NUTSB_UCHUNK - 1) / NUTSB_UCHUNK;
     const u32 local = blockIdx.x - A.geo.room_item_off[room];
     const u32 t = local / chunks, chunk = local % chunks;
@@ -490,81 +648,110 @@ k_fanout(FanoutArgs A)
     const u32 gend = A.geo.room_b_off[room + 1];
     const u32 nb = (gend - g0 < NUTSB_TILE_OPS) ? gend - g0 : NUTSB_TILE_OPS;
     const u32 a0 = t * NUTSB_TILE_OPS;                  // room-local slab rank of the tile's first op
+    const u32 ls_begin = chunk * NUTSB_UCHUNK;
+    const u32 ls_end = (ls_begin + NUTSB_UCHUNK < users_r) ? ls_begin + NUTSB_UCHUNK : users_r;
+    const u64 cell_row = A.geo.room_cell_off[room] + (u64)t * users_r;
 
-    // -- per-op metadata
+    // -- per-op metadata (threads 0..128) and per-recipient cells + events (threads 128..255)
     if ((u32)tid < nb) {
         const u32 op = A.bl_op[g0 + tid];
-        s_op[tid] = op;
-        s_tlen[tid] = (u32)(A.ops.toff[op + 1] - A.ops.toff[op]);
+        const u64 t0 = A.ops.toff[op];
+        s_src[tid] = t0; s_tlen[tid] = (u32)(A.ops.toff[op + 1] - t0);
         s_kind[tid] = A.ops.kind[op]; s_flags[tid] = A.ops.flags[op]; s_target[tid] = A.ops.target[op];
     }
     if ((u32)tid <= nb) {
         s_oon[tid]  = (u32)(A.cpx.vp_on[g0 + tid]  - A.cpx.vp_on[g0]);
         s_ooff[tid] = (u32)(A.cpx.vp_off[g0 + tid] - A.cpx.vp_off[g0]);
     }
+    if (tid >= NUTSB_FAN_THREADS - NUTSB_UCHUNK) {
+        const u32 q = (u32)tid - (NUTSB_FAN_THREADS - NUTSB_UCHUNK);
+        const u32 ls = ls_begin + q;
+        if (ls < ls_end) {
+            const u32 e0 = A.cell_evi[cell_row + ls], e1 = A.cell_evi[cell_row + users_r + ls];
+            s_upos[q] = A.cell_pos[cell_row + ls];
+            s_uev0[q] = e0; s_uev1[q] = e1;
+            s_ucf[q] = A.pop.slot_cf[slot0 + ls];
+            s_ulv[q] = A.pop.slot_lv[slot0 + ls];
+            u32 base = 0xffffffffu;
+            if (e1 > e0) {
+                const u32 cnt = e1 - e0;
+                const u32 got = atomicAdd(&s_evn, cnt);
+                if (got + cnt <= NUTSB_EV_CAP) {
+                    base = got;
+                    for (u32 j = 0; j < cnt; ++j) { s_evk[base + j] = A.sv_ukey[e0 + j]; s_evd[base + j] = A.sv_delta[e0 + j]; }
+                }
+            }
+            s_uevb[q] = base;
+        }
+    }
     __syncthreads();
-    if (tid == 0) { u32 acc = 0; for (u32 i = 0; i < nb; ++i) { s_toff[i] = acc; acc += s_tlen[i]; } s_toff[nb] = acc; }
+    if (warp == 0) {                                     // prefix of the staged sizes
+        u32 carry = 0;
+        for (u32 base = 0; base < NUTSB_TILE_OPS; base += 32) {
+            const u32 i = base + lane;
+            const u32 v = i < nb ? nutsb_stage_bytes(A.ops.text + s_src[i], s_tlen[i]) : 0;
+            u32 inc = v;
+            for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(NUTSB_FULL, inc, d); if (lane >= d) inc += x; }
+            if (i < nb) s_toff[i] = carry + inc - v;
+            carry += __shfl_sync(NUTSB_FULL, inc, 31);
+        }
+        if (lane == 0) s_toff[nb] = carry;
+    }
     __syncthreads();
 
-    const u32 slot0 = (u32)A.pop.room_slot_off[room];
-    const u32 ls_begin = chunk * NUTSB_UCHUNK;
-    const u32 ls_end = (ls_begin + NUTSB_UCHUNK < users_r) ? ls_begin + NUTSB_UCHUNK : users_r;
-    const u64 cell_row = A.geo.room_cell_off[room] + (u64)t * users_r;
     u32 my_deliv = 0;
-
     u32 a = 0;
     while (a < nb) {
         // -- largest sub-tile [a,b) whose source and both renderings fit in shared memory
         if (tid == 0) {
-            u32 b = a + 1;
-            while (b < nb && s_toff[b + 1] - s_toff[a] <= NUTSB_TEXT_CAP &&
-                   s_oon[b + 1] - s_oon[a] <= NUTSB_ON_CAP && s_ooff[b + 1] - s_ooff[a] <= NUTSB_OFF_CAP) ++b;
+            u32 b = nb;
+            if (s_toff[nb] - s_toff[a] > NUTSB_TEXT_CAP || s_oon[nb] - s_oon[a] > NUTSB_ON_CAP ||
+                s_ooff[nb] - s_ooff[a] > NUTSB_OFF_CAP) {
+                b = a + 1;
+                while (b < nb && s_toff[b + 1] - s_toff[a] <= NUTSB_TEXT_CAP &&
+                       s_oon[b + 1] - s_oon[a] <= NUTSB_ON_CAP && s_ooff[b + 1] - s_ooff[a] <= NUTSB_OFF_CAP) ++b;
+            }
             s_sub_b = b;
         }
         __syncthreads();
         const u32 b = s_sub_b;
 
-        // -- stage the source strings (a warp per string)
-        for (u32 i = a + warp; i < b; i += NUTSB_FAN_THREADS / 32) {
-            const u8 *src = A.ops.text + A.ops.toff[s_op[i]];
-            u8 *dst = s_text + (s_toff[i] - s_toff[a]);
-            const u32 n = s_tlen[i];
-            for (u32 j = lane; j < n; j += 32) dst[j] = __ldg(src + j);
-        }
-        __syncthreads();
-
-        // -- render: thread j -> op a + j/2, colour j&1
-        for (u32 j = tid; j < 2 * (b - a); j += NUTSB_FAN_THREADS) {
-            const u32 i = a + (j >> 1);
-            const int colour = (int)(j & 1);
-            const u8 *src = s_text + (s_toff[i] - s_toff[a]);
-            u8 *dst = colour ? s_on + (s_oon[i] - s_oon[a]) : s_off + (s_ooff[i] - s_ooff[a]);
-            const u32 got = nutsb_render_seq(src, s_tlen[i], colour, dst, s_tab);
-            const u32 want = colour ? s_oon[i + 1] - s_oon[i] : s_ooff[i + 1] - s_ooff[i];
-            if (got != want) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+        // -- stage + render: one thread per op stages its own string (32-bit loads) and
+        //    runs the byte machine once for both colour settings
+        if ((u32)tid < b - a) {
+            const u32 i = a + tid;
+            const u8 *src = A.ops.text + s_src[i];
+            u8 *win = s_text + (s_toff[i] - s_toff[a]);
+            nutsb_lane_stage(win, src, s_tlen[i]);
+            u32 lon, loff;
+            nutsb_render<true, true>(win + ((u32)(size_t)src & 3u), s_tlen[i],
+                                     s_on + (s_oon[i] - s_oon[a]), s_off + (s_ooff[i] - s_ooff[a]), s_tab, &lon, &loff);
+            if (lon != s_oon[i + 1] - s_oon[i] || loff != s_ooff[i + 1] - s_ooff[i]) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
         }
         __syncthreads();
 
         // -- fan out: one warp per recipient at a time
         for (u32 ls = ls_begin + warp; ls < ls_end; ls += NUTSB_FAN_THREADS / 32) {
-            const i32 u = A.pop.slot_user[slot0 + ls];
-            const i32 k = A.pop.user_cls[u];
-            const u32 cf = A.pop.cls_flags[k], clv = A.pop.cls_level[k];
+            const u32 q = ls - ls_begin;
+            const u32 cf = s_ucf[q], clv = s_ulv[q];
             const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
             const bool full = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
             const u32 *offc = colour ? s_oon : s_ooff;
             const u8 *slab = colour ? s_on : s_off;
-            u64 p = A.cell_pos[cell_row + ls];
-            u32 e = A.cell_evi[cell_row + ls];
-            const u32 e1 = A.cell_evi[cell_row + users_r + ls];
+            u64 p = s_upos[q];
+            const u32 e0 = s_uev0[q], e1 = s_uev1[q], evb = s_uevb[q];
+            u32 e = e0;
             u32 cur = 0;
             for (;;) {
                 // next cut: an event of this recipient inside the tile, or the tile end
                 u32 j = nb; u32 ek = 0; i32 dlt = 0;
                 if (e < e1) {
-                    const u32 uk = A.sv_ukey[e];
+                    const u32 uk = evb != 0xffffffffu ? s_evk[evb + (e - e0)] : A.sv_ukey[e];
                     const u32 jj = (uk >> 1) - a0;
-                    if (jj < nb || (jj == nb && !(uk & 1))) { j = jj < nb ? jj : nb; ek = (uk & 1) ? 2 : 1; dlt = A.sv_delta[e]; }
+                    if (jj < nb || (jj == nb && !(uk & 1))) {
+                        j = jj; ek = (uk & 1) ? 2 : 1;
+                        dlt = evb != 0xffffffffu ? s_evd[evb + (e - e0)] : A.sv_delta[e];
+                    }
                 }
                 // emit slab ops [cur, j)
                 if (full) {
@@ -587,7 +774,6 @@ k_fanout(FanoutArgs A)
                 if (ek == 2) cur = j + 1;                 // excluded from op j: nothing emitted for it
                 else { p += (u64)(i64)dlt; cur = j; }      // a direct op's bytes go here (k_direct writes them)
                 ++e;
-                if (cur >= nb && !(e < e1)) break;
             }
         }
         __syncthreads();
@@ -597,13 +783,18 @@ k_fanout(FanoutArgs A)
     __syncthreads();
     if (tid == 0) {
         if (s_deliv) nutsb_add64(A.n_deliveries, (u64)s_deliv);
-        if (chunk == 0) nutsb_add64(A.n_deliveries + 2, (u64)s_toff[nb]);   // each slab op's source is read once
+        if (chunk == 0) {                                  // each slab op's source is read once per tile
+            u32 tb = 0; for (u32 i = 0; i < nb; ++i) tb += s_tlen[i];
+            nutsb_add64(A.n_deliveries + 2, (u64)tb);
+        }
     }
 }
 
 // ---- I. direct ops (write_user) -----------------------------------------------------------
-// One warp per op: classify 32 source bytes per step, ballot the emitted lengths,
-// prefix-sum with popc, store the bytes straight into the user's stream.
+// One thread per event (events are sorted by recipient).  The direct ops among
+// a block's 256 events are staged, rendered in the recipient's colour setting and
+// copied into the recipient's stream at the offset the event prefix gives -- all
+// three by the op's own thread, in sub-batches sized to shared memory.
 struct DirectArgs {
     OpsView ops; PopView pop; ClassPrefix cpx;
     const u32 *room_b_off, *ev_off;
@@ -612,77 +803,86 @@ struct DirectArgs {
     const u32 *ev_slot_sorted;      // user slot of each sorted event
     const i32 *sv_delta;
     u8 *out; i64 n_ev;
-    u64 *n_deliveries;              // [0] deliveries, [1] bytes written by k_direct, [2] source bytes staged by k_fanout
+    u64 *n_deliveries;              // [0] deliveries, [1] bytes written by k_direct, [2] (k_fanout)
+    u32 *status;
 };
 
-__device__ __forceinline__ void nutsb_warp_render_global(const u8 *s, u32 n, bool colour, u8 *dst,
-                                                         const u8 *tab, int lane)
-{
-    u32 o = 0;
-    for (u32 base = 0; base < n; base += 32) {
-        const u32 j = base + lane;
-        u32 len = 0; u8 c = 0; int k = -1;
-        if (j < n) {
-            c = s[j];
-            const u8 m1 = j >= 1 ? s[j - 1] : 0, m2 = j >= 2 ? s[j - 2] : 0, m3 = j >= 3 ? s[j - 3] : 0;
-            const u8 p1 = j + 1 < n ? s[j + 1] : 0, p2 = j + 2 < n ? s[j + 2] : 0;
-            if (c == '\n') len = colour ? 6 : 2;
-            else if (c == '/' && p1 == '~' && j + 1 < n) len = 0;
-            else if (c == '~') {
-                if (m1 == '/' && j >= 1) len = 1;
-                else {
-                    if (j + 2 < n) k = nutsb_code(tab, p1, p2);
-                    len = k >= 0 ? (colour ? nutsb_code_len(k) : 0u) : 1u;
-                }
-            } else {
-                // consumed as a command letter?  (commands are A-Z pairs, so c is a letter here)
-                const bool lead1 = j >= 1 && m1 == '~' && !(j >= 2 && m2 == '/') && j + 1 < n && nutsb_code(tab, c, p1) >= 0;
-                const bool lead2 = j >= 2 && m2 == '~' && !(j >= 3 && m3 == '/') && nutsb_code(tab, m1, c) >= 0;
-                len = (lead1 || lead2) ? 0 : 1;
-            }
-        }
-        const u32 b0 = __ballot_sync(NUTSB_FULL, len & 1), b1 = __ballot_sync(NUTSB_FULL, len & 2),
-                  b2 = __ballot_sync(NUTSB_FULL, len & 4);
-        const u32 lt = (1u << lane) - 1;
-        const u32 pre = (u32)__popc(b0 & lt) + 2u * (u32)__popc(b1 & lt) + 4u * (u32)__popc(b2 & lt);
-        u8 *d = dst + o + pre;
-        if (len == 1) d[0] = c;
-        else if (len == 2) { d[0] = '\n'; d[1] = '\r'; }
-        else if (len == 6) { d[0] = 0x1b; d[1] = '['; d[2] = '0'; d[3] = 'm'; d[4] = '\n'; d[5] = '\r'; }
-        else if (len) for (u32 q = 0; q < len; ++q) d[q] = nutsb_code_byte(k, q);
-        o += (u32)__popc(b0) + 2u * (u32)__popc(b1) + 4u * (u32)__popc(b2);
-    }
-    if (colour && lane < 4) dst[o + lane] = lane == 0 ? 0x1b : lane == 1 ? '[' : lane == 2 ? '0' : 'm';
-}
-
 #define NUTSB_DIRECT_THREADS 256
+#define NUTSB_DIR_TEXT_CAP 16384
+#define NUTSB_DIR_OUT_CAP  24576
 
 __global__ void __launch_bounds__(NUTSB_DIRECT_THREADS)
 k_direct(DirectArgs A)
 {
-    __shared__ u8 s_tab[NUTSB_CODETAB_BYTES];
-    for (int i = threadIdx.x; i < NUTSB_CODETAB_BYTES; i += blockDim.x) s_tab[i] = A.pop.codetab[i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const i64 nwarps = (i64)gridDim.x * (NUTSB_DIRECT_THREADS / 32);
-    u32 cnt = 0; u64 nbytes = 0;
-    for (i64 e = (i64)blockIdx.x * (NUTSB_DIRECT_THREADS / 32) + (threadIdx.x >> 5); e < A.n_ev; e += nwarps) {
+    __shared__ __align__(16) u8 s_text[NUTSB_DIR_TEXT_CAP + 32];
+    __shared__ __align__(16) u8 s_out[NUTSB_DIR_OUT_CAP + 64];
+    __shared__ u8  s_tab[NUTSB_CODETAB_BYTES];
+    __shared__ u32 s_pt[NUTSB_DIRECT_THREADS + 1], s_po[NUTSB_DIRECT_THREADS + 1];
+    __shared__ u32 s_sub_b;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < NUTSB_CODETAB_BYTES; i += NUTSB_DIRECT_THREADS) s_tab[i] = A.pop.codetab[i];
+
+    const i64 e = (i64)blockIdx.x * NUTSB_DIRECT_THREADS + tid;
+    bool isw = false, colour = false;
+    u64 p = 0; const u8 *src = A.ops.text; u32 n = 0;
+    u32 tsz = 0, osz = 0;
+    if (e < A.n_ev) {
         const u32 uk = A.sv_ukey[e];
-        if (uk & 1) continue;                          // an exclusion, not a direct op
-        const u32 s = A.ev_slot_sorted[e];
-        const i32 u = A.pop.slot_user[s];
-        const u32 room = (u32)A.pop.user_room[u];
-        const i32 k = A.pop.user_cls[u];
-        const u32 b0 = A.room_b_off[room];
-        const u64 p = A.stream_off[u] + (A.cpx.at(k, room, b0 + (uk >> 1)) - A.cpx.at(k, room, b0))
-                    + (A.sv_pre[e] - A.sv_pre[A.ev_off[s]]);
-        const u32 op = A.sv_op[e];
-        const u64 t0 = A.ops.toff[op];
-        nutsb_warp_render_global(A.ops.text + t0, (u32)(A.ops.toff[op + 1] - t0),
-                                 (A.pop.cls_flags[k] & NUTSB_UF_COLOUR) != 0, A.out + p, s_tab, lane);
-        ++cnt; nbytes += (u64)A.sv_delta[e];
+        if (!(uk & 1)) {                                   // a direct op (an odd key is an exclusion)
+            const u32 s = A.ev_slot_sorted[e];
+            const i32 u = A.pop.slot_user[s];
+            const u32 room = (u32)A.pop.user_room[u];
+            const i32 k = A.pop.user_cls[u];
+            const u32 b0 = A.room_b_off[room];
+            const u32 op = A.sv_op[e];
+            const u64 t0 = A.ops.toff[op];
+            p = A.stream_off[u] + (A.cpx.at(k, room, b0 + (uk >> 1)) - A.cpx.at(k, room, b0))
+              + (A.sv_pre[e] - A.sv_pre[A.ev_off[s]]);
+            src = A.ops.text + t0;
+            n = (u32)(A.ops.toff[op + 1] - t0);
+            colour = (A.pop.slot_cf[s] & NUTSB_UF_COLOUR) != 0;
+            isw = true;
+            tsz = nutsb_stage_bytes(src, n);
+            osz = (u32)A.sv_delta[e];
+        }
     }
-    if (lane == 0 && cnt) { nutsb_add64(A.n_deliveries, (u64)cnt); nutsb_add64(A.n_deliveries + 1, nbytes); }
+    u64 tot_t, tot_o;
+    const u32 pt = (u32)nutsb_block_excl_scan(tsz, &tot_t);
+    const u32 po = (u32)nutsb_block_excl_scan(osz, &tot_o);
+    s_pt[tid] = pt; s_po[tid] = po;
+    if (tid == 0) { s_pt[NUTSB_DIRECT_THREADS] = (u32)tot_t; s_po[NUTSB_DIRECT_THREADS] = (u32)tot_o; }
+    __syncthreads();
+    u32 a = 0;
+    while (a < NUTSB_DIRECT_THREADS) {
+        if (tid == 0) {
+            u32 b = NUTSB_DIRECT_THREADS;
+            if (s_pt[b] - s_pt[a] > NUTSB_DIR_TEXT_CAP || s_po[b] - s_po[a] > NUTSB_DIR_OUT_CAP) {
+                b = a + 1;
+                while (b < NUTSB_DIRECT_THREADS && s_pt[b + 1] - s_pt[a] <= NUTSB_DIR_TEXT_CAP &&
+                       s_po[b + 1] - s_po[a] <= NUTSB_DIR_OUT_CAP) ++b;
+            }
+            s_sub_b = b;
+        }
+        __syncthreads();
+        const u32 b = s_sub_b;
+        if (isw && (u32)tid >= a && (u32)tid < b) {
+            u8 *win = s_text + (pt - s_pt[a]);
+            u8 *dst = s_out + (po - s_po[a]);
+            nutsb_lane_stage(win, src, n);
+            u32 lon = 0, loff = 0;
+            if (colour) nutsb_render<true, false>(win + ((u32)(size_t)src & 3u), n, dst, dst, s_tab, &lon, &loff);
+            else        nutsb_render<false, true>(win + ((u32)(size_t)src & 3u), n, dst, dst, s_tab, &lon, &loff);
+            if ((colour ? lon : loff) != osz) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+            nutsb_lane_copy(A.out + p, dst, osz);
+        }
+        __syncthreads();
+        a = b;
+    }
+    // deliveries / bytes of this block
+    const u32 wcnt = (u32)__popc(__ballot_sync(NUTSB_FULL, isw));
+    u32 wbytes = isw ? osz : 0;
+    for (int d = 16; d; d >>= 1) wbytes += __shfl_xor_sync(NUTSB_FULL, wbytes, d);
+    if (lane == 0 && wcnt) { nutsb_add64(A.n_deliveries, (u64)wcnt); nutsb_add64(A.n_deliveries + 1, (u64)wbytes); }
 }
 
 // ---- stream digests ------------------------------------------------------------------------

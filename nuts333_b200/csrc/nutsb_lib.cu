@@ -60,7 +60,7 @@ struct nutsb_ctx {
     bool have_users = false, all_simple = true;
     i32 U = 0, R = 0, Rt = 1;
     std::vector<i32> user_room, user_slot, slot_user, room_slot_off;
-    DBuf d_user_room, d_user_slot, d_slot_user, d_room_slot_off;
+    DBuf d_user_room, d_user_slot, d_slot_user, d_room_slot_off, d_slot_cf, d_slot_lv;
     ClassSet cls[2];                 // [0] keyed without level, [1] with level
 
     // per-batch scratch
@@ -314,7 +314,7 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     DBuf *all[] = { &c->d_codetab, &c->swear.trans, &c->swear.clsmap, &c->site.trans, &c->site.clsmap,
         &c->userban.slot_off, &c->userban.slot_len, &c->userban.pool,
-        &c->d_user_room, &c->d_user_slot, &c->d_slot_user, &c->d_room_slot_off,
+        &c->d_user_room, &c->d_user_slot, &c->d_slot_user, &c->d_room_slot_off, &c->d_slot_cf, &c->d_slot_lv,
         &c->cls[0].d_user_cls, &c->cls[0].d_room_cls_off, &c->cls[0].d_cls_flags, &c->cls[0].d_cls_level,
         &c->cls[1].d_user_cls, &c->cls[1].d_room_cls_off, &c->cls[1].d_cls_flags, &c->cls[1].d_cls_level,
         &c->d_status, &c->d_len_on, &c->d_len_off, &c->d_nrep, &c->d_eoff, &c->d_sums, &c->d_ek[0], &c->d_ek[1],
@@ -354,6 +354,7 @@ NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         for (auto &e : c->ev) CK(cudaEventCreate(&e));
+        CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_FAN_SMEM));
         u8 tab[NUTSB_CODETAB_BYTES]; build_codetab(tab);
         TRY(upload(c, c->d_codetab, tab, sizeof tab));
         TRY(ensure(c, c->d_status, 64)); TRY(ensure(c, c->d_counts, 64)); TRY(ensure(c, c->d_sizes, sizeof(Sizes)));
@@ -475,6 +476,13 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     TRY(upload(c, c->d_user_slot, c->user_slot.data(), (size_t)n_users * 4));
     TRY(upload(c, c->d_slot_user, c->slot_user.data(), (size_t)n_users * 4));
     TRY(upload(c, c->d_room_slot_off, c->room_slot_off.data(), (size_t)(c->Rt + 1) * 4));
+    {
+        std::vector<u8> cf(n_users), lv(n_users);
+        for (i32 s = 0; s < n_users; ++s) { cf[s] = (u8)(flags[order[s]] & 0x1f); lv[s] = level[order[s]]; }
+        TRY(upload(c, c->d_slot_cf, cf.data(), (size_t)n_users));
+        TRY(upload(c, c->d_slot_lv, lv.data(), (size_t)n_users));
+        CK(cudaStreamSynchronize(c->stream));          // cf/lv go out of scope
+    }
     TRY(build_classes(c, c->cls[0], false, order, flags, level));
     TRY(build_classes(c, c->cls[1], true, order, flags, level));
     CK(cudaStreamSynchronize(c->stream));
@@ -489,6 +497,7 @@ static PopView pop_view(const nutsb_ctx *c, int with_level)
     p.n_users = c->U; p.n_rooms = c->R; p.n_rooms_tot = c->Rt;
     p.user_room = c->d_user_room.as<i32>(); p.user_cls = cs.d_user_cls.as<i32>();
     p.user_slot = c->d_user_slot.as<i32>(); p.slot_user = c->d_slot_user.as<i32>();
+    p.slot_cf = c->d_slot_cf.as<u8>(); p.slot_lv = c->d_slot_lv.as<u8>();
     p.room_slot_off = c->d_room_slot_off.as<i32>(); p.room_cls_off = cs.d_room_cls_off.as<i32>();
     p.cls_flags = cs.d_cls_flags.as<u8>(); p.cls_level = cs.d_cls_level.as<u8>();
     p.codetab = c->d_codetab.as<u8>();
@@ -649,9 +658,9 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     TRY(ensure(c, c->d_out, sz.total_bytes + 64));
     TRY(ensure(c, c->d_cell_pos, (sz.cells + 1) * 8)); TRY(ensure(c, c->d_cell_evi, (sz.cells + 1) * 4));
     Geometry geo{ c->d_room_b_off.as<u32>(), c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>() };
-    if (U > 0) {
-        NUTSB_LAUNCH(cdiv((u64)U, 256), 256, st, k_fill_pos, pop, geo, cpx, c->d_off.as<u64>(), c->d_ev_off.as<u32>(),
-                     c->d_sv_ukey.as<u32>(), c->d_sv_pre.as<u64>(), c->d_cell_pos.as<u64>(), c->d_cell_evi.as<u32>()); CKL();
+    if (sz.cells > 0) {
+        NUTSB_LAUNCH(cdiv(sz.cells, 256), 256, st, k_fill_pos, pop, geo, cpx, c->d_off.as<u64>(), c->d_ev_off.as<u32>(),
+                     c->d_sv_ukey.as<u32>(), c->d_sv_pre.as<u64>(), (u64)sz.cells, c->d_cell_pos.as<u64>(), c->d_cell_evi.as<u32>()); CKL();
         c->tm.launches++;
     }
 
@@ -661,7 +670,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     if (sz.items > 0) {
         FanoutArgs fa{ ops, pop, geo, cpx, c->d_bl_op.as<u32>(), len_on, len_off, c->d_cell_pos.as<u64>(), c->d_cell_evi.as<u32>(),
                        c->d_sv_ukey.as<u32>(), c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), counters, c->d_status.as<u32>(), has_level ? 1u : 0u };
-        NUTSB_LAUNCH(sz.items, NUTSB_FAN_THREADS, st, k_fanout, fa); CKL();
+        NUTSB_LAUNCH_SMEM(sz.items, NUTSB_FAN_THREADS, NUTSB_FAN_SMEM, st, k_fanout, fa); CKL();
         c->tm.launches++; c->tm.fanout_launches = 1;
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], st));
@@ -669,8 +678,9 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     // -- I. direct ops
     if (sz.n_events > 0) {
         DirectArgs da{ ops, pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_op.as<u32>(),
-                       c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), (i64)sz.n_events, counters };
-        const u32 grid = std::min<u32>(cdiv(sz.n_events, NUTSB_DIRECT_THREADS / 32), (u32)c->sm_count * 8u);
+                       c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), (i64)sz.n_events, counters,
+                       c->d_status.as<u32>() };
+        const u32 grid = cdiv(sz.n_events, NUTSB_DIRECT_THREADS);
         NUTSB_LAUNCH(grid, NUTSB_DIRECT_THREADS, st, k_direct, da); CKL();
         c->tm.launches++;
     }
@@ -775,7 +785,7 @@ NUTSB_API int nutsb_stream_digests(nutsb_ctx *c, uint64_t *digest)
 static int run_ac(nutsb_ctx *c, const AcDev &ac, i64 n, const u8 *bytes, const u64 *off, u8 *verdict)
 {
     if (n == 0) return NUTSB_OK;
-    const u32 grid = cdiv(n, NUTSB_AC_THREADS);
+    const u32 grid = std::min<u32>(cdiv(n, NUTSB_AC_THREADS), (u32)c->sm_count * 16u);
     const bool smem = ac.view.nstates <= 32768u && (u64)ac.view.nstates * ac.view.ncls <= NUTSB_AC_SMEM_ENTRIES;
     if (smem) { NUTSB_LAUNCH(grid, NUTSB_AC_THREADS, c->stream, k_ac_match<true>, bytes, off, n, ac.view, verdict); }
     else      { NUTSB_LAUNCH(grid, NUTSB_AC_THREADS, c->stream, k_ac_match<false>, bytes, off, n, ac.view, verdict); }

@@ -22,14 +22,31 @@ struct AcView {
 };
 
 #define NUTSB_AC_THREADS     128
-#define NUTSB_AC_WARP_BYTES  4096
 #define NUTSB_AC_SMEM_ENTRIES 12288      // u16 entries (24 KB)
 
+// One automaton step per byte: class lookup, then transition.  Bytes are fetched
+// four at a time with one aligned 32-bit load (the four class lookups are
+// independent; only the four transitions form a dependent chain).
+template <bool SMEM_DFA>
+__device__ __forceinline__ bool nutsb_ac_step(u32 &st, u32 c, const u16 *s_tr, const AcView &ac)
+{
+    if (SMEM_DFA) {
+        const u32 t = s_tr[st * ac.ncls + c];
+        st = t & 0x7fffu;
+        return (t & 0x8000u) != 0;
+    } else {
+        const u32 t = __ldg(ac.trans + (size_t)st * ac.ncls + c);
+        st = t & 0x7fffffffu;
+        return (t >> 31) != 0;
+    }
+}
+
+// Persistent blocks: the table is loaded into shared memory once per block, then
+// the block strides over the strings, one thread per string.
 template <bool SMEM_DFA>
 __global__ void __launch_bounds__(NUTSB_AC_THREADS)
 k_ac_match(const u8 *text, const u64 *off, i64 n, AcView ac, u8 *verdict)
 {
-    __shared__ __align__(16) u8 s_stage[NUTSB_AC_THREADS / 32][NUTSB_AC_WARP_BYTES + 32];
     __shared__ u8 s_cls[256];
     __shared__ u16 s_tr[SMEM_DFA ? NUTSB_AC_SMEM_ENTRIES : 1];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = ac.clsmap[i];
@@ -41,43 +58,28 @@ k_ac_match(const u8 *text, const u64 *off, i64 n, AcView ac, u8 *verdict)
         }
     }
     __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const i64 wbase = (i64)blockIdx.x * NUTSB_AC_THREADS + warp * 32;
-    if (wbase >= n) return;
-    const i64 wend = (wbase + 32 < n) ? wbase + 32 : n;
-    const u64 b0 = off[wbase], b1 = off[wend];
-    const u8 *pa = (const u8 *)((size_t)(text + b0) & ~(size_t)15);
-    const u64 span = (u64)((text + b1) - pa);
-    const bool staged = (b1 >= b0) && span <= NUTSB_AC_WARP_BYTES;
-    u8 *stage = s_stage[warp];
-    if (staged) {
-        const u32 nvec = (u32)((span + 15) >> 4);
-        for (u32 v = lane; v < nvec; v += 32) *(uint4 *)(stage + 16 * v) = __ldg((const uint4 *)pa + v);
-    }
-    __syncwarp();
-    const i64 i = wbase + lane;
-    if (i >= n) return;
-    const u64 o0 = off[i], o1 = off[i + 1];
-    u32 hit = ac.root_match ? 1u : 0u;
-    if (!hit && o1 > o0) {
-        const u8 *s = staged ? stage + ((text + o0) - pa) : text + o0;
-        const u32 len = (u32)(o1 - o0);
-        u32 st = 0;
-        for (u32 j = 0; j < len; ++j) {
-            const u32 c = s_cls[s[j]];
-            if (SMEM_DFA) {
-                const u32 t = s_tr[st * ac.ncls + c];
-                if (t & 0x8000u) { hit = 1; break; }
-                st = t;
-            } else {
-                const u32 t = __ldg(ac.trans + (size_t)st * ac.ncls + c);
-                if (t >> 31) { hit = 1; break; }
-                st = t;
+    for (i64 i = (i64)blockIdx.x * NUTSB_AC_THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * NUTSB_AC_THREADS) {
+        const u64 o0 = off[i], o1 = off[i + 1];
+        u32 hit = ac.root_match ? 1u : 0u;
+        if (!hit && o1 > o0) {
+            const u8 *s = text + o0;
+            const u32 len = (u32)(o1 - o0);
+            u32 st = 0, j = 0;
+            while (j < len && !hit) {
+                if ((((size_t)(s + j)) & 3) == 0 && j + 4 <= len) {
+                    const u32 w = __ldg((const u32 *)(s + j));
+                    const u32 c0 = s_cls[w & 0xff], c1 = s_cls[(w >> 8) & 0xff], c2 = s_cls[(w >> 16) & 0xff], c3 = s_cls[w >> 24];
+                    hit = nutsb_ac_step<SMEM_DFA>(st, c0, s_tr, ac) || nutsb_ac_step<SMEM_DFA>(st, c1, s_tr, ac) ||
+                          nutsb_ac_step<SMEM_DFA>(st, c2, s_tr, ac) || nutsb_ac_step<SMEM_DFA>(st, c3, s_tr, ac);
+                    j += 4;
+                } else {
+                    hit = nutsb_ac_step<SMEM_DFA>(st, s_cls[__ldg(s + j)], s_tr, ac);
+                    ++j;
+                }
             }
         }
+        verdict[i] = (u8)hit;
     }
-    verdict[i] = (u8)hit;
 }
 
 // Exact-match set: open addressing, 32-bit FNV-1a, linear probing.

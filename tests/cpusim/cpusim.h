@@ -80,6 +80,8 @@ struct BlockState {
 extern thread_local Idx tl_threadIdx, tl_blockIdx;
 extern thread_local BlockState *tl_block;
 extern Idx g_blockDim, g_gridDim;
+extern unsigned char *g_dyn_smem;      // blocks run one at a time: one buffer serves them all
+void set_dyn_smem(size_t bytes);
 
 template <class Combine>
 static inline uint64_t collective(unsigned mask, uint64_t v, int aux, Combine combine)
@@ -196,6 +198,12 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s)
     return r;
 }
 template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned __vcmpeq4(unsigned a, unsigned b)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) if (((a >> (8 * i)) & 0xff) == ((b >> (8 * i)) & 0xff)) r |= 0xffu << (8 * i);
+    return r;
+}
 
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
@@ -243,11 +251,22 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEve
 
 #define NUTSB_LAUNCH(grid, block, stream, kern, ...) \
     cpusim::launch(dim3(grid), dim3(block), [&] { kern(__VA_ARGS__); })
+#define NUTSB_LAUNCH_SMEM(grid, block, smem, stream, kern, ...) \
+    do { cpusim::set_dyn_smem(smem); cpusim::launch(dim3(grid), dim3(block), [&] { kern(__VA_ARGS__); }); } while (0)
+#define NUTSB_DYN_SMEM(name) unsigned char *name = cpusim::g_dyn_smem
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 
 #ifdef CPUSIM_IMPLEMENTATION
 namespace cpusim {
 thread_local Idx tl_threadIdx, tl_blockIdx;
 thread_local BlockState *tl_block = nullptr;
 Idx g_blockDim, g_gridDim;
+unsigned char *g_dyn_smem = nullptr;
+void set_dyn_smem(size_t bytes)
+{
+    static size_t cap = 0;
+    if (bytes > cap) { free(g_dyn_smem); g_dyn_smem = (unsigned char *)aligned_alloc(64, (bytes + 63) & ~(size_t)63); cap = bytes; }
+}
 }
 #endif

@@ -97,7 +97,8 @@ def test_empty_and_ragged(gpu_ctx, port):
     assert st.user(0) == b"\x1b[0m" + b"\x1b[0m\x1b[0m" and st.user(1) == b"" and st.user(2) == b"\x1b[0m"
     # no users
     gpu_ctx.set_users(np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.uint8), 2)
-    st = gpu_ctx.write_batch(ops := dict(ops, kind=np.array([1, 1, 1, 1], np.uint8), target=np.array([0, 1, -1, 0], np.int32)))
+    st = gpu_ctx.write_batch(dict(ops, kind=np.array([1, 1, 1, 1], np.uint8), target=np.array([0, 1, -1, 0], np.int32),
+                                  except_user=np.full(4, -1, np.int32)))
     assert st.total_bytes == 0 and st.n_users == 0
 
 
