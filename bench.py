@@ -82,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -92,7 +92,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        """Keep the samples taken inside [t0, t1] (the timed region); if the region was
+        shorter than the sampling period, keep the nearest ones taken under the same load."""
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        if not inside:
+            inside = sorted(self.samples, key=lambda s: min(abs(s[0] - t0), abs(s[0] - t1)))[:5]
+        self.samples = inside
 
     def stop(self):
         if not self.proc:
@@ -105,7 +113,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for _, s in self.samples:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 6:
                 continue
@@ -298,19 +306,22 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)
+    clocks.start()                      # nvidia-smi needs ~0.1 s to start: launched before the warm-up
     for _ in range(args.warmup):
         step_device()
     for k in state:
         state[k] = 0 if not isinstance(state[k], float) else 0.0
-    clocks = ClockSampler(local)
     barrier()
-    clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
     e1.record(stream)
     barrier()
+    tw1 = time.perf_counter()
+    clocks.window(tw0, tw1)
     clk = clocks.stop()
     ms = e0.elapsed_time(e1)
     dev_state = dict(state)

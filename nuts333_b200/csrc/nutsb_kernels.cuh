@@ -38,10 +38,11 @@ struct PopView {                 // the population, built by nutsb_set_users
 
 #define NUTSB_TILE_OPS   128     // room-list ops per fan-out tile
 #define NUTSB_UCHUNK     128     // recipients per fan-out work item
-#define NUTSB_TEXT_CAP   12288   // staged source bytes per (sub)tile   (>= 2000+6)
-#define NUTSB_ON_CAP     16384   // rendered bytes per (sub)tile, colour on  (>= 6*2000+4)
-#define NUTSB_OFF_CAP    12288   // rendered bytes per (sub)tile, colour off (>= 2*2000)
+#define NUTSB_TEXT_CAP   11264   // staged source bytes per (sub)tile   (>= 2000+6)
+#define NUTSB_ON_CAP     12288   // rendered bytes per (sub)tile, colour on  (>= 6*2000+4)
+#define NUTSB_OFF_CAP    10240   // rendered bytes per (sub)tile, colour off (>= 2*2000)
 #define NUTSB_EV_CAP     256     // events of a tile's recipients prefetched into shared memory
+#define NUTSB_RUN_CAP    512     // planned copy runs per (sub)tile and recipient chunk
 
 // ---- A. measure ------------------------------------------------------------------
 // One thread per op: rendered length for both colour settings, liveness (gate),
@@ -52,10 +53,10 @@ struct PopView {                 // the population, built by nutsb_set_users
 #define NUTSB_MEASURE_THREADS 256
 #define NUTSB_MEASURE_WARP_BYTES 4096
 
-__device__ __forceinline__ bool nutsb_word_has(u32 x, u32 b)
+// 0x80 in every byte of y that is zero, exact (no borrow between bytes)
+__device__ __forceinline__ u32 nutsb_zero_bytes(u32 y)
 {
-    u32 y = x ^ (b * 0x01010101u);
-    return ((y - 0x01010101u) & ~y & 0x80808080u) != 0;
+    return ~(((y & 0x7f7f7f7fu) + 0x7f7f7f7fu) | y | 0x7f7f7f7fu);
 }
 
 __global__ void __launch_bounds__(NUTSB_MEASURE_THREADS)
@@ -104,16 +105,18 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
     if (!live) {
     } else if (staged) {
         const u32 p0 = (u32)((ops.text + o0) - pa), p1 = p0 + n;
-        for (u32 w = p0 >> 2; w < (p1 + 3) >> 2; ++w) {
+        const u32 w0 = p0 >> 2, w1 = (p1 + 3) >> 2;
+        for (u32 w = w0; w < w1; ++w) {
             const u32 x = *(const u32 *)(stage + 4 * w);
-            // bytes of this word that belong to the string
-            const u32 lo = p0 > 4 * w ? p0 - 4 * w : 0, hi = p1 < 4 * w + 4 ? p1 - 4 * w : 4;
-            const u32 vm = (0xffffffffu << (8 * lo)) & (0xffffffffu >> (8 * (4 - hi)));
-            nl += (u32)__popc(__vcmpeq4(x, 0x0a0a0a0au) & vm) >> 3;
-            u32 mt = __vcmpeq4(x, 0x7e7e7e7eu) & vm;
+            // 0x80 in every byte of the word that belongs to the string
+            u32 vm = 0x80808080u;
+            if (w == w0) vm &= 0xffffffffu << (8 * (p0 & 3));
+            if (w + 1 == w1 && (p1 & 3)) vm &= 0xffffffffu >> (8 * (4 - (p1 & 3)));
+            nl += (u32)__popc(nutsb_zero_bytes(x ^ 0x0a0a0a0au) & vm);
+            u32 mt = nutsb_zero_bytes(x ^ 0x7e7e7e7eu) & vm;
             while (mt) {                                   // each '~' of the word, in order
                 const u32 bb = (u32)(__ffs((int)mt) - 1) >> 3;
-                mt &= ~(0xffu << (8 * bb));
+                mt &= mt - 1;
                 const u32 j = 4 * w + bb;
                 if (j > p0 && stage[j - 1] == '/') ++drops;
                 else if (j + 2 < p1) {
@@ -622,6 +625,10 @@ k_fanout(FanoutArgs A)
     __shared__ u32 s_evk[NUTSB_EV_CAP];          // the chunk's events inside this tile
     __shared__ i32 s_evd[NUTSB_EV_CAP];
     __shared__ u32 s_evn;
+    __shared__ u64 s_rdst[NUTSB_RUN_CAP];        // planned copy runs of the current (sub)tile
+    __shared__ u32 s_rsrc[NUTSB_RUN_CAP], s_rlen[NUTSB_RUN_CAP];
+    __shared__ u8  s_ulegacy[NUTSB_UCHUNK];
+    __shared__ u32 s_nruns, s_next;
     __shared__ u32 s_sub_b;
     __shared__ u32 s_room;
     __shared__ u32 s_deliv;
@@ -711,28 +718,104 @@ k_fanout(FanoutArgs A)
                 while (b < nb && s_toff[b + 1] - s_toff[a] <= NUTSB_TEXT_CAP &&
                        s_oon[b + 1] - s_oon[a] <= NUTSB_ON_CAP && s_ooff[b + 1] - s_ooff[a] <= NUTSB_OFF_CAP) ++b;
             }
-            s_sub_b = b;
+            s_sub_b = b; s_nruns = 0; s_next = 0;
         }
         __syncthreads();
         const u32 b = s_sub_b;
 
-        // -- stage + render: one thread per op stages its own string (32-bit loads) and
-        //    runs the byte machine once for both colour settings
-        if ((u32)tid < b - a) {
-            const u32 i = a + tid;
-            const u8 *src = A.ops.text + s_src[i];
-            u8 *win = s_text + (s_toff[i] - s_toff[a]);
-            nutsb_lane_stage(win, src, s_tlen[i]);
-            u32 lon, loff;
-            nutsb_render<true, true>(win + ((u32)(size_t)src & 3u), s_tlen[i],
-                                     s_on + (s_oon[i] - s_oon[a]), s_off + (s_ooff[i] - s_ooff[a]), s_tab, &lon, &loff);
-            if (lon != s_oon[i + 1] - s_oon[i] || loff != s_ooff[i + 1] - s_ooff[i]) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+        // -- stage + render: two adjacent threads per op.  They stage the string together
+        //    (alternate 32-bit words), then one runs the byte machine for colour-on
+        //    recipients, the other for colour-off.
+        {
+            const u32 i = a + ((u32)tid >> 1);
+            const bool on = (tid & 1) != 0;
+            const bool act = i < b;
+            const u8 *src = A.ops.text;
+            u8 *win = s_text;
+            u32 n = 0;
+            if (act) {
+                src += s_src[i]; n = s_tlen[i]; win += s_toff[i] - s_toff[a];
+                const u32 al = (u32)((size_t)src & 3);
+                const u32 *g = (const u32 *)(src - al);
+                const u32 nw = (al + n + 3) >> 2;
+                for (u32 w = (u32)(tid & 1); w < nw; w += 2) ((u32 *)win)[w] = __ldg(g + w);
+            }
+            __syncwarp();
+            if (act) {
+                u32 lon = 0, loff = 0;
+                const u8 *str = win + ((u32)(size_t)src & 3u);
+                if (on) {
+                    nutsb_render<true, false>(str, n, s_on + (s_oon[i] - s_oon[a]), nullptr, s_tab, &lon, &loff);
+                    if (lon != s_oon[i + 1] - s_oon[i]) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+                } else {
+                    nutsb_render<false, true>(str, n, nullptr, s_off + (s_ooff[i] - s_ooff[a]), s_tab, &lon, &loff);
+                    if (loff != s_ooff[i + 1] - s_ooff[i]) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+                }
+            }
+        }
+
+        // -- plan: one thread per recipient walks the recipient's events inside the tile and
+        //    queues its copy runs (destination, slab offset, length).  Needs only the
+        //    offsets, not the rendered bytes, so it runs before the barrier.
+        if ((u32)tid < ls_end - ls_begin) {
+            const u32 q = (u32)tid;
+            const u32 cf = s_ucf[q];
+            const bool full = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
+            bool legacy = !full;
+            if (full) {
+                const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
+                const u32 *offc = colour ? s_oon : s_ooff;
+                u64 p = s_upos[q];
+                const u32 e0 = s_uev0[q], e1 = s_uev1[q], evb = s_uevb[q];
+                u32 e = e0, cur = 0, deliv = 0;
+                for (;;) {
+                    u32 j = nb, ek = 0; i32 dlt = 0;
+                    if (e < e1) {
+                        const u32 uk = evb != 0xffffffffu ? s_evk[evb + (e - e0)] : A.sv_ukey[e];
+                        const u32 jj = (uk >> 1) - a0;
+                        if (jj < nb || (jj == nb && !(uk & 1))) {
+                            j = jj; ek = (uk & 1) ? 2 : 1;
+                            dlt = evb != 0xffffffffu ? s_evd[evb + (e - e0)] : A.sv_delta[e];
+                        }
+                    }
+                    const u32 xs = cur > a ? cur : a, ye = j < b ? j : b;
+                    if (xs < ye && offc[ye] != offc[xs]) {
+                        const u32 r = atomicAdd(&s_nruns, 1u);
+                        if (r < NUTSB_RUN_CAP) {
+                            s_rdst[r] = p + (offc[xs] - offc[cur]);
+                            s_rsrc[r] = (offc[xs] - offc[a]) | (colour ? 0x80000000u : 0u);
+                            s_rlen[r] = offc[ye] - offc[xs];
+                            deliv += ye - xs;
+                        } else legacy = true;              // queue full: this recipient goes the slow way
+                    } else if (xs < ye) deliv += ye - xs;      // zero-length renderings still count as deliveries
+                    p += offc[j] - offc[cur];
+                    if (!ek) break;
+                    if (ek == 2) cur = j + 1; else { p += (u64)(i64)dlt; cur = j; }
+                    ++e;
+                }
+                if (!legacy && deliv) atomicAdd(&s_deliv, deliv);
+            }
+            s_ulegacy[q] = legacy ? 1 : 0;
         }
         __syncthreads();
 
-        // -- fan out: one warp per recipient at a time
+        // -- copy: warps pull planned runs; a run is one contiguous piece of a recipient's stream
+        {
+            const u32 nruns = s_nruns < NUTSB_RUN_CAP ? s_nruns : NUTSB_RUN_CAP;
+            for (;;) {
+                u32 r = 0;
+                if (lane == 0) r = atomicAdd(&s_next, 1u);
+                r = __shfl_sync(NUTSB_FULL, r, 0);
+                if (r >= nruns) break;
+                const u32 so = s_rsrc[r];
+                nutsb_warp_copy(A.out + s_rdst[r], ((so >> 31) ? s_on : s_off) + (so & 0x7fffffffu), s_rlen[r], lane);
+            }
+        }
+        // -- recipients that are not plain listeners (login / ignall / ignshout, level ops in the
+        //    batch) or did not fit the queue: one warp per recipient, op by op where needed
         for (u32 ls = ls_begin + warp; ls < ls_end; ls += NUTSB_FAN_THREADS / 32) {
             const u32 q = ls - ls_begin;
+            if (!s_ulegacy[q]) continue;
             const u32 cf = s_ucf[q], clv = s_ulv[q];
             const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
             const bool full = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
@@ -743,7 +826,6 @@ k_fanout(FanoutArgs A)
             u32 e = e0;
             u32 cur = 0;
             for (;;) {
-                // next cut: an event of this recipient inside the tile, or the tile end
                 u32 j = nb; u32 ek = 0; i32 dlt = 0;
                 if (e < e1) {
                     const u32 uk = evb != 0xffffffffu ? s_evk[evb + (e - e0)] : A.sv_ukey[e];
@@ -753,7 +835,6 @@ k_fanout(FanoutArgs A)
                         dlt = evb != 0xffffffffu ? s_evd[evb + (e - e0)] : A.sv_delta[e];
                     }
                 }
-                // emit slab ops [cur, j)
                 if (full) {
                     const u32 xs = cur > a ? cur : a, ye = j < b ? j : b;
                     if (xs < ye) {

@@ -7,10 +7,9 @@
 //   substring of the site" -> the same automaton, no case folding.
 //   user_banned (c:349-364): "some tested token equals the name" -> hash set.
 //
-// One thread per string.  The 32 strings of a warp are a contiguous byte range:
-// it is staged in shared memory with coalesced 16-byte loads.  The transition
-// table lives in shared memory when it fits (the 64-word swear list: ~22 KB),
-// else it is read through L1/L2 (the 10k-entry site list: ~20 MB, L2-resident).
+// One thread per string, persistent blocks.  The transition table lives in shared
+// memory when it fits (the 64-word swear list: ~22 KB), else it is read through
+// L1/L2 (the 10k-entry site list: ~20 MB, L2-resident).
 #pragma once
 #include "nutsb_common.cuh"
 
@@ -21,12 +20,10 @@ struct AcView {
     u32 root_match;          // an empty pattern: every string matches (strstr(s,"") != NULL)
 };
 
-#define NUTSB_AC_THREADS     128
+#define NUTSB_AC_THREADS     256
 #define NUTSB_AC_SMEM_ENTRIES 12288      // u16 entries (24 KB)
 
-// One automaton step per byte: class lookup, then transition.  Bytes are fetched
-// four at a time with one aligned 32-bit load (the four class lookups are
-// independent; only the four transitions form a dependent chain).
+// One automaton step per byte: class lookup, then transition.
 template <bool SMEM_DFA>
 __device__ __forceinline__ bool nutsb_ac_step(u32 &st, u32 c, const u16 *s_tr, const AcView &ac)
 {
@@ -42,7 +39,10 @@ __device__ __forceinline__ bool nutsb_ac_step(u32 &st, u32 c, const u16 *s_tr, c
 }
 
 // Persistent blocks: the table is loaded into shared memory once per block, then
-// the block strides over the strings, one thread per string.
+// the block strides over the strings, one thread per string.  Bytes are fetched
+// four at a time with aligned 32-bit loads, the next word requested before the
+// current one is walked (the four class lookups of a word are independent; only
+// the four transitions form a dependent chain).
 template <bool SMEM_DFA>
 __global__ void __launch_bounds__(NUTSB_AC_THREADS)
 k_ac_match(const u8 *text, const u64 *off, i64 n, AcView ac, u8 *verdict)
@@ -60,25 +60,29 @@ k_ac_match(const u8 *text, const u64 *off, i64 n, AcView ac, u8 *verdict)
     __syncthreads();
     for (i64 i = (i64)blockIdx.x * NUTSB_AC_THREADS + threadIdx.x; i < n; i += (i64)gridDim.x * NUTSB_AC_THREADS) {
         const u64 o0 = off[i], o1 = off[i + 1];
-        u32 hit = ac.root_match ? 1u : 0u;
+        bool hit = ac.root_match != 0;
         if (!hit && o1 > o0) {
             const u8 *s = text + o0;
             const u32 len = (u32)(o1 - o0);
             u32 st = 0, j = 0;
-            while (j < len && !hit) {
-                if ((((size_t)(s + j)) & 3) == 0 && j + 4 <= len) {
-                    const u32 w = __ldg((const u32 *)(s + j));
-                    const u32 c0 = s_cls[w & 0xff], c1 = s_cls[(w >> 8) & 0xff], c2 = s_cls[(w >> 16) & 0xff], c3 = s_cls[w >> 24];
-                    hit = nutsb_ac_step<SMEM_DFA>(st, c0, s_tr, ac) || nutsb_ac_step<SMEM_DFA>(st, c1, s_tr, ac) ||
-                          nutsb_ac_step<SMEM_DFA>(st, c2, s_tr, ac) || nutsb_ac_step<SMEM_DFA>(st, c3, s_tr, ac);
-                    j += 4;
-                } else {
-                    hit = nutsb_ac_step<SMEM_DFA>(st, s_cls[__ldg(s + j)], s_tr, ac);
-                    ++j;
-                }
+            while (j < len && (((size_t)(s + j)) & 3) != 0 && !hit) {          // up to the first aligned word
+                hit = nutsb_ac_step<SMEM_DFA>(st, s_cls[__ldg(s + j)], s_tr, ac); ++j;
             }
+            const u32 nwords = hit ? 0 : (len - j) >> 2;
+            const u32 *wp = (const u32 *)(s + j);
+            u32 w = nwords ? __ldg(wp) : 0;
+            u32 k = 0;
+            for (; k < nwords && !hit; ++k) {
+                const u32 wn = (k + 1 < nwords) ? __ldg(wp + k + 1) : 0;
+                const u32 c0 = s_cls[w & 0xff], c1 = s_cls[(w >> 8) & 0xff], c2 = s_cls[(w >> 16) & 0xff], c3 = s_cls[w >> 24];
+                hit = nutsb_ac_step<SMEM_DFA>(st, c0, s_tr, ac) || nutsb_ac_step<SMEM_DFA>(st, c1, s_tr, ac) ||
+                      nutsb_ac_step<SMEM_DFA>(st, c2, s_tr, ac) || nutsb_ac_step<SMEM_DFA>(st, c3, s_tr, ac);
+                w = wn;
+            }
+            j += 4 * nwords;
+            while (j < len && !hit) { hit = nutsb_ac_step<SMEM_DFA>(st, s_cls[__ldg(s + j)], s_tr, ac); ++j; }
         }
-        verdict[i] = (u8)hit;
+        verdict[i] = hit ? 1 : 0;
     }
 }
 
