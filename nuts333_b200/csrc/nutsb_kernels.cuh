@@ -431,55 +431,45 @@ __device__ __forceinline__ u64 nutsb_code_pack(int k)
 #define NUTSB_RESET_PACK 0x6d305b1bull     /* ESC [ 0 m */
 
 // One step takes either a whole aligned plain word (4 bytes) or one byte of the
-// machine; what it emits is a (length, packed bytes) pair per colour setting,
-// stored with predicated byte stores -- the step is straight-line code, so the
-// 32 strings of a warp stay converged.  The string must sit in a window that
-// starts at a 4-byte boundary (nutsb_lane_stage / nutsb_warp_stage).
-template <bool ON, bool OFF>
-__device__ __forceinline__ void nutsb_render(const u8 *s, u32 n, u8 *oon, u8 *ooff, const u8 *tab, u32 *len_on, u32 *len_off)
+// machine; what it emits is a (length, packed bytes) pair chosen by the
+// recipient's colour setting and stored with predicated byte stores -- the step
+// is one code path for both settings, so the strings of a warp stay converged.
+// The string must sit in a window that starts at a 4-byte boundary
+// (nutsb_lane_stage / nutsb_warp_stage).  Returns the rendered length.
+__device__ __forceinline__ u32 nutsb_render1(const u8 *s, u32 n, bool colour, u8 *out, const u8 *tab)
 {
-    u32 i = 0, a = 0, b = 0;
+    u32 i = 0, o = 0;
     while (i < n) {
         const u8 *p = s + i;
         const u32 al = (u32)(size_t)p & 3u;
         const u32 w = *(const u32 *)(p - al);
-        u32 adv = 4, lon = 4, loff = 4, voff = w;
-        u64 von = w;
+        u32 adv = 4, len = 4;
+        u64 val = w;
         if (al != 0 || i + 4 > n || nutsb_special_mask(w)) {
             const u32 c = (w >> (8 * al)) & 0xffu;
-            adv = 1; lon = 1; loff = 1; von = c; voff = c;
+            adv = 1; len = 1; val = c;
             if (c == '\n') {                                                   /* c:1316-1326 */
-                lon = 6; von = NUTSB_RESET_PACK | ((u64)'\n' << 32) | ((u64)'\r' << 40);
-                loff = 2; voff = (u32)'\n' | ((u32)'\r' << 8);
+                len = colour ? 6u : 2u;
+                val = colour ? (NUTSB_RESET_PACK | ((u64)'\n' << 32) | ((u64)'\r' << 40)) : (u64)((u32)'\n' | ((u32)'\r' << 8));
             } else if (c == '/') {                                             /* c:1330 */
-                if (i + 1 < n && p[1] == '~') { lon = 0; loff = 0; }
+                if (i + 1 < n && p[1] == '~') len = 0;
             } else if (c == '~') {                                             /* c:1331-1354 */
                 if (!(i > 0 && p[-1] == '/') && i + 2 < n) {
                     const int k = nutsb_code(tab, p[1], p[2]);
-                    if (k >= 0) { adv = 3; loff = 0; lon = nutsb_code_len(k); von = nutsb_code_pack(k); }
+                    if (k >= 0) { adv = 3; len = colour ? nutsb_code_len(k) : 0u; val = nutsb_code_pack(k); }
                 }
             }
         }
-        if (ON) {
-            if (lon > 0) oon[a] = (u8)von;
-            if (lon > 1) oon[a + 1] = (u8)(von >> 8);
-            if (lon > 2) oon[a + 2] = (u8)(von >> 16);
-            if (lon > 3) oon[a + 3] = (u8)(von >> 24);
-            if (lon > 4) oon[a + 4] = (u8)(von >> 32);
-            if (lon > 5) oon[a + 5] = (u8)(von >> 40);
-            a += lon;
-        }
-        if (OFF) {
-            if (loff > 0) ooff[b] = (u8)voff;
-            if (loff > 1) ooff[b + 1] = (u8)(voff >> 8);
-            if (loff > 2) ooff[b + 2] = (u8)(voff >> 16);
-            if (loff > 3) ooff[b + 3] = (u8)(voff >> 24);
-            b += loff;
-        }
-        i += adv;
+        if (len > 0) out[o] = (u8)val;
+        if (len > 1) out[o + 1] = (u8)(val >> 8);
+        if (len > 2) out[o + 2] = (u8)(val >> 16);
+        if (len > 3) out[o + 3] = (u8)(val >> 24);
+        if (len > 4) out[o + 4] = (u8)(val >> 32);
+        if (len > 5) out[o + 5] = (u8)(val >> 40);
+        o += len; i += adv;
     }
-    if (ON) { oon[a] = 0x1b; oon[a + 1] = '['; oon[a + 2] = '0'; oon[a + 3] = 'm'; a += 4; }      /* c:1365 */
-    *len_on = a; *len_off = b;
+    if (colour) { out[o] = 0x1b; out[o + 1] = '['; out[o + 2] = '0'; out[o + 3] = 'm'; o += 4; }  /* c:1365 */
+    return o;
 }
 
 // One lane stages its own string (32-bit loads; lanes of a warp walk 32 different
@@ -602,6 +592,8 @@ struct FanoutArgs {
 
 #define NUTSB_FAN_THREADS 256
 #define NUTSB_FAN_SMEM (NUTSB_TEXT_CAP + 32 + NUTSB_ON_CAP + 64 + NUTSB_OFF_CAP + 64)
+static_assert(NUTSB_FAN_THREADS == 2 * NUTSB_TILE_OPS && (NUTSB_TILE_OPS & (NUTSB_TILE_OPS - 1)) == 0 &&
+              NUTSB_UCHUNK <= NUTSB_FAN_THREADS / 2, "k_fanout thread mapping");
 
 __global__ void __launch_bounds__(NUTSB_FAN_THREADS)
 k_fanout(FanoutArgs A)
@@ -723,34 +715,30 @@ k_fanout(FanoutArgs A)
         __syncthreads();
         const u32 b = s_sub_b;
 
-        // -- stage + render: two adjacent threads per op.  They stage the string together
-        //    (alternate 32-bit words), then one runs the byte machine for colour-on
-        //    recipients, the other for colour-off.
+        // -- stage: two threads per op (tid and tid+128) copy alternate 32-bit words
         {
-            const u32 i = a + ((u32)tid >> 1);
-            const bool on = (tid & 1) != 0;
-            const bool act = i < b;
-            const u8 *src = A.ops.text;
-            u8 *win = s_text;
-            u32 n = 0;
-            if (act) {
-                src += s_src[i]; n = s_tlen[i]; win += s_toff[i] - s_toff[a];
+            const u32 i = a + ((u32)tid & (NUTSB_TILE_OPS - 1));
+            if (i < b) {
+                const u8 *src = A.ops.text + s_src[i];
                 const u32 al = (u32)((size_t)src & 3);
                 const u32 *g = (const u32 *)(src - al);
-                const u32 nw = (al + n + 3) >> 2;
-                for (u32 w = (u32)(tid & 1); w < nw; w += 2) ((u32 *)win)[w] = __ldg(g + w);
+                const u32 nw = (al + s_tlen[i] + 3) >> 2;
+                u32 *win = (u32 *)(s_text + (s_toff[i] - s_toff[a]));
+                for (u32 w = (u32)tid >> 7; w < nw; w += 2) win[w] = __ldg(g + w);
             }
-            __syncwarp();
-            if (act) {
-                u32 lon = 0, loff = 0;
-                const u8 *str = win + ((u32)(size_t)src & 3u);
-                if (on) {
-                    nutsb_render<true, false>(str, n, s_on + (s_oon[i] - s_oon[a]), nullptr, s_tab, &lon, &loff);
-                    if (lon != s_oon[i + 1] - s_oon[i]) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
-                } else {
-                    nutsb_render<false, true>(str, n, nullptr, s_off + (s_ooff[i] - s_ooff[a]), s_tab, &lon, &loff);
-                    if (loff != s_ooff[i + 1] - s_ooff[i]) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
-                }
+        }
+        __syncthreads();
+        // -- render: threads 0..127 run the byte machine for colour-on recipients, threads
+        //    128..255 for colour-off ones (the setting is uniform per warp)
+        {
+            const u32 i = a + ((u32)tid & (NUTSB_TILE_OPS - 1));
+            const bool on = tid < NUTSB_TILE_OPS;
+            if (i < b) {
+                const u8 *src = A.ops.text + s_src[i];
+                const u8 *str = s_text + (s_toff[i] - s_toff[a]) + ((u32)(size_t)src & 3u);
+                const u32 *offc = on ? s_oon : s_ooff;
+                const u32 got = nutsb_render1(str, s_tlen[i], on, (on ? s_on : s_off) + (offc[i] - offc[a]), s_tab);
+                if (got != offc[i + 1] - offc[i]) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
             }
         }
 
@@ -950,10 +938,8 @@ k_direct(DirectArgs A)
             u8 *win = s_text + (pt - s_pt[a]);
             u8 *dst = s_out + (po - s_po[a]);
             nutsb_lane_stage(win, src, n);
-            u32 lon = 0, loff = 0;
-            if (colour) nutsb_render<true, false>(win + ((u32)(size_t)src & 3u), n, dst, dst, s_tab, &lon, &loff);
-            else        nutsb_render<false, true>(win + ((u32)(size_t)src & 3u), n, dst, dst, s_tab, &lon, &loff);
-            if ((colour ? lon : loff) != osz) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+            if (nutsb_render1(win + ((u32)(size_t)src & 3u), n, colour, dst, s_tab) != osz)
+                atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
             nutsb_lane_copy(A.out + p, dst, osz);
         }
         __syncthreads();
