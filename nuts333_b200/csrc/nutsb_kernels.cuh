@@ -418,8 +418,12 @@ k_fill_pos(PopView pop, Geometry geo, ClassPrefix cpx, const u64 *stream_off,
 // rendering, or both in one pass (the parse is shared).
 __device__ __forceinline__ u32 nutsb_special_mask(u32 w)
 {
+    // 0x80 in every byte of w that is '~', '/' or '\n' -- exact per byte (the cheaper
+    // (y-0x01..)&~y form can flag the byte above a match, e.g. the '.' of "/.")
+    const u32 M = 0x7f7f7f7fu;
     const u32 y0 = w ^ 0x7e7e7e7eu, y1 = w ^ 0x2f2f2f2fu, y2 = w ^ 0x0a0a0a0au;
-    return (((y0 - 0x01010101u) & ~y0) | ((y1 - 0x01010101u) & ~y1) | ((y2 - 0x01010101u) & ~y2)) & 0x80808080u;
+    const u32 t0 = ((y0 & M) + M) | y0, t1 = ((y1 & M) + M) | y1, t2 = ((y2 & M) + M) | y2;
+    return ~((t0 & t1 & t2) | M);
 }
 
 // Bytes of colcode[k] (nuts333.h:237-246), little-endian in one register pair.
@@ -430,12 +434,15 @@ __device__ __forceinline__ u64 nutsb_code_pack(int k)
 }
 #define NUTSB_RESET_PACK 0x6d305b1bull     /* ESC [ 0 m */
 
-// One step takes either a whole aligned plain word (4 bytes) or one byte of the
-// machine; what it emits is a (length, packed bytes) pair chosen by the
-// recipient's colour setting and stored with predicated byte stores -- the step
-// is one code path for both settings, so the strings of a warp stay converged.
-// The string must sit in a window that starts at a 4-byte boundary
-// (nutsb_lane_stage / nutsb_warp_stage).  Returns the rendered length.
+// One step consumes the rest of the current aligned word up to and including its
+// first special byte ('~', '/', '\n'): the plain bytes before it pass through
+// (nuts333.c:1355), the special byte goes through the machine (c:1316-1354).
+// What a step emits is "up to 4 plain bytes, then up to 6 bytes" chosen by the
+// recipient's colour setting, stored with predicated byte stores -- one code
+// path, so the strings of a warp stay converged; only a '~' that is not escaped
+// takes a branch (the table lookup).  The string must sit in a window that
+// starts at a 4-byte boundary (nutsb_lane_stage / nutsb_warp_stage); bytes of
+// the window outside the string are never interpreted.  Returns the rendered length.
 __device__ __forceinline__ u32 nutsb_render1(const u8 *s, u32 n, bool colour, u8 *out, const u8 *tab)
 {
     u32 i = 0, o = 0;
@@ -443,30 +450,44 @@ __device__ __forceinline__ u32 nutsb_render1(const u8 *s, u32 n, bool colour, u8
         const u8 *p = s + i;
         const u32 al = (u32)(size_t)p & 3u;
         const u32 w = *(const u32 *)(p - al);
-        u32 adv = 4, len = 4;
-        u64 val = w;
-        if (al != 0 || i + 4 > n || nutsb_special_mask(w)) {
-            const u32 c = (w >> (8 * al)) & 0xffu;
-            adv = 1; len = 1; val = c;
+        const u32 rem = n - i;
+        const u32 top = al + rem < 4 ? al + rem : 4;             // bytes [al, top) of w belong to the string
+        const u32 range = (0xffffffffu << (8 * al)) & (0xffffffffu >> (8 * (4 - top)));
+        const u32 sm = nutsb_special_mask(w) & range;
+        const u32 q = sm ? ((u32)(__ffs((int)sm) - 1) >> 3) : top;   // first special byte, or end of the word
+        const u32 np = q - al;                                   // plain bytes passed through
+        const u32 pv = w >> (8 * al);
+        u32 adv = np, len = 0;
+        u64 val = 0;
+        if (sm) {
+            const u32 c = (w >> (8 * q)) & 0xffu;
+            const u32 j = i + np;                                // index of the special byte
+            adv = np + 1; len = 1; val = c;
             if (c == '\n') {                                                   /* c:1316-1326 */
                 len = colour ? 6u : 2u;
                 val = colour ? (NUTSB_RESET_PACK | ((u64)'\n' << 32) | ((u64)'\r' << 40)) : (u64)((u32)'\n' | ((u32)'\r' << 8));
             } else if (c == '/') {                                             /* c:1330 */
-                if (i + 1 < n && p[1] == '~') len = 0;
+                if (j + 1 < n && s[j + 1] == '~') len = 0;
             } else if (c == '~') {                                             /* c:1331-1354 */
-                if (!(i > 0 && p[-1] == '/') && i + 2 < n) {
-                    const int k = nutsb_code(tab, p[1], p[2]);
-                    if (k >= 0) { adv = 3; len = colour ? nutsb_code_len(k) : 0u; val = nutsb_code_pack(k); }
+                if (!(j > 0 && s[j - 1] == '/') && j + 2 < n) {
+                    const int k = nutsb_code(tab, s[j + 1], s[j + 2]);
+                    if (k >= 0) { adv = np + 3; len = colour ? nutsb_code_len(k) : 0u; val = nutsb_code_pack(k); }
                 }
             }
         }
-        if (len > 0) out[o] = (u8)val;
-        if (len > 1) out[o + 1] = (u8)(val >> 8);
-        if (len > 2) out[o + 2] = (u8)(val >> 16);
-        if (len > 3) out[o + 3] = (u8)(val >> 24);
-        if (len > 4) out[o + 4] = (u8)(val >> 32);
-        if (len > 5) out[o + 5] = (u8)(val >> 40);
-        o += len; i += adv;
+        u8 *d = out + o;
+        if (np > 0) d[0] = (u8)pv;
+        if (np > 1) d[1] = (u8)(pv >> 8);
+        if (np > 2) d[2] = (u8)(pv >> 16);
+        if (np > 3) d[3] = (u8)(pv >> 24);
+        d += np;
+        if (len > 0) d[0] = (u8)val;
+        if (len > 1) d[1] = (u8)(val >> 8);
+        if (len > 2) d[2] = (u8)(val >> 16);
+        if (len > 3) d[3] = (u8)(val >> 24);
+        if (len > 4) d[4] = (u8)(val >> 32);
+        if (len > 5) d[5] = (u8)(val >> 40);
+        o += np + len; i += adv;
     }
     if (colour) { out[o] = 0x1b; out[o + 1] = '['; out[o + 2] = '0'; out[o + 3] = 'm'; o += 4; }  /* c:1365 */
     return o;
@@ -877,8 +898,8 @@ struct DirectArgs {
 };
 
 #define NUTSB_DIRECT_THREADS 256
-#define NUTSB_DIR_TEXT_CAP 16384
-#define NUTSB_DIR_OUT_CAP  24576
+#define NUTSB_DIR_TEXT_CAP 14336
+#define NUTSB_DIR_OUT_CAP  20480
 
 __global__ void __launch_bounds__(NUTSB_DIRECT_THREADS)
 k_direct(DirectArgs A)
@@ -886,70 +907,76 @@ k_direct(DirectArgs A)
     __shared__ __align__(16) u8 s_text[NUTSB_DIR_TEXT_CAP + 32];
     __shared__ __align__(16) u8 s_out[NUTSB_DIR_OUT_CAP + 64];
     __shared__ u8  s_tab[NUTSB_CODETAB_BYTES];
+    __shared__ u64 s_p[NUTSB_DIRECT_THREADS], s_src[NUTSB_DIRECT_THREADS];
+    __shared__ u32 s_n[NUTSB_DIRECT_THREADS];
     __shared__ u32 s_pt[NUTSB_DIRECT_THREADS + 1], s_po[NUTSB_DIRECT_THREADS + 1];
+    __shared__ u8  s_col[NUTSB_DIRECT_THREADS];
     __shared__ u32 s_sub_b;
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < NUTSB_CODETAB_BYTES; i += NUTSB_DIRECT_THREADS) s_tab[i] = A.pop.codetab[i];
 
+    // -- the direct ops among this block's 256 events, compacted to the front
     const i64 e = (i64)blockIdx.x * NUTSB_DIRECT_THREADS + tid;
     bool isw = false, colour = false;
-    u64 p = 0; const u8 *src = A.ops.text; u32 n = 0;
-    u32 tsz = 0, osz = 0;
+    u64 p = 0, t0 = 0; u32 n = 0, tsz = 0, osz = 0;
     if (e < A.n_ev) {
         const u32 uk = A.sv_ukey[e];
-        if (!(uk & 1)) {                                   // a direct op (an odd key is an exclusion)
+        if (!(uk & 1)) {                                   // an odd key is an exclusion
             const u32 s = A.ev_slot_sorted[e];
             const i32 u = A.pop.slot_user[s];
             const u32 room = (u32)A.pop.user_room[u];
             const i32 k = A.pop.user_cls[u];
             const u32 b0 = A.room_b_off[room];
             const u32 op = A.sv_op[e];
-            const u64 t0 = A.ops.toff[op];
+            t0 = A.ops.toff[op];
             p = A.stream_off[u] + (A.cpx.at(k, room, b0 + (uk >> 1)) - A.cpx.at(k, room, b0))
               + (A.sv_pre[e] - A.sv_pre[A.ev_off[s]]);
-            src = A.ops.text + t0;
             n = (u32)(A.ops.toff[op + 1] - t0);
             colour = (A.pop.slot_cf[s] & NUTSB_UF_COLOUR) != 0;
             isw = true;
-            tsz = nutsb_stage_bytes(src, n);
+            tsz = nutsb_stage_bytes(A.ops.text + t0, n);
             osz = (u32)A.sv_delta[e];
         }
     }
-    u64 tot_t, tot_o;
+    u64 tot_t, tot_o, tot_w;
     const u32 pt = (u32)nutsb_block_excl_scan(tsz, &tot_t);
     const u32 po = (u32)nutsb_block_excl_scan(osz, &tot_o);
-    s_pt[tid] = pt; s_po[tid] = po;
-    if (tid == 0) { s_pt[NUTSB_DIRECT_THREADS] = (u32)tot_t; s_po[NUTSB_DIRECT_THREADS] = (u32)tot_o; }
+    const u32 cp = (u32)nutsb_block_excl_scan(isw ? 1u : 0u, &tot_w);
+    const u32 nw = (u32)tot_w;
+    if (isw) { s_p[cp] = p; s_src[cp] = t0; s_n[cp] = n; s_pt[cp] = pt; s_po[cp] = po; s_col[cp] = colour ? 1 : 0; }
+    if (tid == 0) { s_pt[nw] = (u32)tot_t; s_po[nw] = (u32)tot_o; }
     __syncthreads();
+
+    // -- thread t handles compacted op t: stage, render in the recipient's colour setting,
+    //    copy to the stream; sub-batches [a,b) sized to shared memory
     u32 a = 0;
-    while (a < NUTSB_DIRECT_THREADS) {
+    while (a < nw) {
         if (tid == 0) {
-            u32 b = NUTSB_DIRECT_THREADS;
+            u32 b = nw;
             if (s_pt[b] - s_pt[a] > NUTSB_DIR_TEXT_CAP || s_po[b] - s_po[a] > NUTSB_DIR_OUT_CAP) {
                 b = a + 1;
-                while (b < NUTSB_DIRECT_THREADS && s_pt[b + 1] - s_pt[a] <= NUTSB_DIR_TEXT_CAP &&
-                       s_po[b + 1] - s_po[a] <= NUTSB_DIR_OUT_CAP) ++b;
+                while (b < nw && s_pt[b + 1] - s_pt[a] <= NUTSB_DIR_TEXT_CAP && s_po[b + 1] - s_po[a] <= NUTSB_DIR_OUT_CAP) ++b;
             }
             s_sub_b = b;
         }
         __syncthreads();
         const u32 b = s_sub_b;
-        if (isw && (u32)tid >= a && (u32)tid < b) {
-            u8 *win = s_text + (pt - s_pt[a]);
-            u8 *dst = s_out + (po - s_po[a]);
-            nutsb_lane_stage(win, src, n);
-            if (nutsb_render1(win + ((u32)(size_t)src & 3u), n, colour, dst, s_tab) != osz)
+        const u32 i = (u32)tid;
+        if (i >= a && i < b) {
+            const u8 *src = A.ops.text + s_src[i];
+            u8 *win = s_text + (s_pt[i] - s_pt[a]);
+            u8 *dst = s_out + (s_po[i] - s_po[a]);
+            const u32 want = s_po[i + 1] - s_po[i];
+            nutsb_lane_stage(win, src, s_n[i]);
+            if (nutsb_render1(win + ((u32)(size_t)src & 3u), s_n[i], s_col[i] != 0, dst, s_tab) != want)
                 atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
-            nutsb_lane_copy(A.out + p, dst, osz);
+            nutsb_lane_copy(A.out + s_p[i], dst, want);
         }
         __syncthreads();
         a = b;
     }
-    // deliveries / bytes of this block
-    const u32 wcnt = (u32)__popc(__ballot_sync(NUTSB_FULL, isw));
-    u32 wbytes = isw ? osz : 0;
-    for (int d = 16; d; d >>= 1) wbytes += __shfl_xor_sync(NUTSB_FULL, wbytes, d);
-    if (lane == 0 && wcnt) { nutsb_add64(A.n_deliveries, (u64)wcnt); nutsb_add64(A.n_deliveries + 1, (u64)wbytes); }
+    if (tid == 0 && nw) { nutsb_add64(A.n_deliveries, (u64)nw); nutsb_add64(A.n_deliveries + 1, (u64)tot_o); }
+    (void)lane;
 }
 
 // ---- stream digests ------------------------------------------------------------------------

@@ -30,6 +30,9 @@ KAT_STRINGS = [
     b"~FK~FR~FG~FY~FB~FM~FT~FW~BK~BR~BG~BY~BB~BM~BT~BW~RS~OL~UL~LI~RV", b"\x07\x07beep\x07",
     b"~" * 40, b"/~" * 20, b"\n" * 33, b"/" * 31 + b"~RS", b"x" * 31 + b"~RS", b"x" * 30 + b"~RS", b"x" * 29 + b"~RS",
     b"x" * 62 + b"~O", b"x" * 63 + b"~OL", b"x" * 64 + b"~OL!",
+    # bytes one bit away from the special ones, right after them (SWAR borrow traps)
+    b"a/.b", b"~\x7fRS", b"x\n\x0by", b"/.~RS", b"//.", b"~\x7f", b"abc/.~FRdef\n\x0b~\x7f/./~", b"\x7f\x7e\x2e\x2f\x0b\x0a" * 9,
+    b"http://a/./b/~FRc/~d", b"...///...~~~...\n\n\x0b",
 ]
 # codes straddling the reference's 1000-byte buffer flush points and the string end
 for pos in (990, 993, 994, 995, 996, 997, 998, 999, 1000, 1001, 1010):
