@@ -54,19 +54,18 @@ def workload_name():
 
 
 def make_inputs(rank: int, n_msgs: int):
-    """The rank's shard, generated on the host once (same generator for every leg)."""
-    from nuts333_b200 import synth
-    seed = SEED + 0x1000 * rank            # every rank owns different rooms / messages
+    """The rank's shard (its own rooms, users and messages: nuts333_b200/shard.py), generated
+    on the host once; the same generator feeds every leg."""
+    from nuts333_b200 import shard, synth
+    seed = SEED + 0x1000 * rank
     words = synth.swear_words(N_SWEAR)
-    users, n_rooms = synth.users(N_USERS, USERS_PER_ROOM, seed=seed)
-    bt, bo = synth.bodies(n_msgs, words, seed=seed)
-    ops, spk, rm = synth.say_ops(n_msgs, N_USERS, USERS_PER_ROOM, bt, bo, gated=True, seed=seed)
+    sh = shard.shard_inputs(rank, n_msgs, N_USERS, USERS_PER_ROOM, words, gated=True)
     st, so = synth.sites(N_BAN_QUERIES, seed=seed)
     nt, no = synth.names(N_BAN_QUERIES)
     sfile = synth.ban_file(0, N_BAN_ENTRIES, N_BAN_QUERIES, N_BAN_QUERIES, True, seed=seed)
     ufile = synth.ban_file(1, N_BAN_ENTRIES, N_BAN_QUERIES, N_BAN_QUERIES, True, seed=seed)
-    return dict(words=words, users=users, n_rooms=n_rooms, bodies=(bt, bo), ops=ops, sites=(st, so), names=(nt, no),
-                sfile=sfile, ufile=ufile)
+    return dict(words=words, users=sh["users"], n_rooms=sh["n_rooms"], bodies=sh["bodies"], ops=sh["ops"],
+                sites=(st, so), names=(nt, no), sfile=sfile, ufile=ufile)
 
 
 # ---------------------------------------------------------------------------------------
