@@ -170,15 +170,23 @@ k_scan_sums(u64 *sums, i64 nb)
     if (threadIdx.x == 0) sums[nb] = carry;
 }
 
+// fused != 0: block_sums holds the raw per-block sums (k_scan_sums was skipped) and every
+// block adds up the sums of the blocks before it by itself (cheap while there are few blocks).
 template <class In, class Out>
 __global__ void __launch_bounds__(NUTSB_SCAN_THREADS)
-k_scan_apply(In in, Out out, i64 n_host, const u32 *n_dev, const u64 *block_sums)
+k_scan_apply(In in, Out out, i64 n_host, const u32 *n_dev, const u64 *block_sums, int fused)
 {
     const i64 n = n_dev ? (i64)*n_dev : n_host;
     const i64 base = (i64)blockIdx.x * NUTSB_SCAN_TILE + (i64)threadIdx.x * NUTSB_SCAN_ITEMS;
     u64 v[NUTSB_SCAN_ITEMS], s = 0;
     for (int k = 0; k < NUTSB_SCAN_ITEMS; ++k) { i64 i = base + k; v[k] = i < n ? in(i) : 0; s += v[k]; }
+    u64 before;
+    if (fused) {
+        u64 part = 0;
+        for (u32 j = threadIdx.x; j < blockIdx.x; j += NUTSB_SCAN_THREADS) part += block_sums[j];
+        (void)nutsb_block_excl_scan(part, &before);
+    } else before = block_sums[blockIdx.x];
     u64 total;
-    u64 ex = nutsb_block_excl_scan(s, &total) + block_sums[blockIdx.x];
+    u64 ex = nutsb_block_excl_scan(s, &total) + before;
     for (int k = 0; k < NUTSB_SCAN_ITEMS; ++k) { i64 i = base + k; if (i <= n) out(i, ex); ex += v[k]; }   // out(n) = total
 }

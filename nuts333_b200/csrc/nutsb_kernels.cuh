@@ -45,13 +45,17 @@ struct PopView {                 // the population, built by nutsb_set_users
 #define NUTSB_RUN_CAP    512     // planned copy runs per (sub)tile and recipient chunk
 
 // ---- A. measure ------------------------------------------------------------------
-// One thread per op: rendered length for both colour settings, liveness (gate),
-// validation and the number of room lists the op enters.  The 32 ops of a warp
-// are a contiguous byte range of the packed text: it is staged into shared
-// memory with coalesced 16-byte loads, then each thread scans its own string a
-// 32-bit word at a time and only looks closer at words that hold '~' or '\n'.
+// Rendered length of every op for both colour settings, liveness (gate), validation
+// and the number of room lists the op enters.  A warp owns 32 consecutive ops = one
+// contiguous byte range of the packed text: it is staged into shared memory with
+// coalesced 16-byte loads, then scanned WORD-parallel (lane l takes words l, l+32,
+// ...: balanced whatever the string lengths): exact SWAR masks find the '\n' and
+// '~' bytes, their positions go to a per-warp list, and the list is then resolved
+// 32 entries at a time (owner string by binary search over the 33 offsets, '/~'
+// escape and command lookup in the shared-memory table) into per-string counters.
 #define NUTSB_MEASURE_THREADS 256
 #define NUTSB_MEASURE_WARP_BYTES 4096
+#define NUTSB_MEASURE_LIST 256
 
 // 0x80 in every byte of y that is zero, exact (no borrow between bytes)
 __device__ __forceinline__ u32 nutsb_zero_bytes(u32 y)
@@ -63,6 +67,10 @@ __global__ void __launch_bounds__(NUTSB_MEASURE_THREADS)
 k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *status)
 {
     __shared__ __align__(16) u8 s_stage[NUTSB_MEASURE_THREADS / 32][NUTSB_MEASURE_WARP_BYTES + 32];
+    __shared__ u32 s_list[NUTSB_MEASURE_THREADS / 32][NUTSB_MEASURE_LIST];
+    __shared__ u32 s_p0[NUTSB_MEASURE_THREADS / 32][33];
+    __shared__ u32 s_ca[NUTSB_MEASURE_THREADS / 32][32], s_cb[NUTSB_MEASURE_THREADS / 32][32];
+    __shared__ u32 s_nlist[NUTSB_MEASURE_THREADS / 32];
     __shared__ u8 s_tab[NUTSB_CODETAB_BYTES];
     for (int i = threadIdx.x; i < NUTSB_CODETAB_BYTES; i += blockDim.x) s_tab[i] = pop.codetab[i];
     __syncthreads();
@@ -71,62 +79,83 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
     const i64 wbase = (i64)blockIdx.x * NUTSB_MEASURE_THREADS + warp * 32;
     if (wbase >= ops.n) return;                    // whole warp leaves together
     const i64 wend = (wbase + 32 < ops.n) ? wbase + 32 : ops.n;
+    const u32 nops = (u32)(wend - wbase);
     const u64 b0 = ops.toff[wbase], b1 = ops.toff[wend];
     // 16-byte aligned window around the warp's bytes (any cudaMalloc'd buffer is
     // readable up to the next 16-byte boundary)
     const u8 *pa = (const u8 *)((size_t)(ops.text + b0) & ~(size_t)15);
     const u64 span = (u64)((ops.text + b1) - pa);
-    const bool staged = (b1 >= b0) && span <= NUTSB_MEASURE_WARP_BYTES;
     u8 *stage = s_stage[warp];
-    if (staged) {
-        const u32 nvec = (u32)((span + 15) >> 4);
-        for (u32 v = lane; v < nvec; v += 32)
-            *(uint4 *)(stage + 16 * v) = __ldg((const uint4 *)pa + v);
-    }
-    __syncwarp();
 
+    // -- per-op facts (lane = op)
     const i64 i = wbase + lane;
-    if (i >= ops.n) return;
-    const u64 o0 = ops.toff[i], o1 = ops.toff[i + 1];
-    u32 st = 0;
-    if (o1 < o0) { atomicOr(status, NUTSB_ST_BAD_OFFSETS); len_on[i] = len_off[i] = nrep[i] = 0; return; }
-    const u64 n64 = o1 - o0;
-    if (n64 > NUTSB_MAX_TEXT) { atomicOr(status, NUTSB_ST_TEXT_TOO_LONG); len_on[i] = len_off[i] = nrep[i] = 0; return; }
-    const u32 n = (u32)n64;
-
-    // liveness first: a gated-off op is neither measured nor bucketed
-    bool live = true;
-    if (ops.gate && ops.gate[i] >= 0) {
+    const bool have = i < ops.n;
+    u64 o0 = b1, o1 = b1;
+    if (have) { o0 = ops.toff[i]; o1 = ops.toff[i + 1]; }
+    const bool bad = have && o1 < o0;
+    const bool toolong = have && !bad && o1 - o0 > NUTSB_MAX_TEXT;
+    bool live = have && !bad && !toolong;
+    if (live && ops.gate && ops.gate[i] >= 0) {    // a gated-off op is neither measured nor bucketed
         const bool v = ops.verdict[ops.gate[i]] != 0;
         live = ((ops.flags[i] & NUTSB_OF_GATE_IF_SET) != 0) == v;
     }
-
+    const u32 any_bad = __ballot_sync(NUTSB_FULL, bad);
+    const u32 livemask = __ballot_sync(NUTSB_FULL, live);
+    const bool staged = !any_bad && b1 >= b0 && span <= NUTSB_MEASURE_WARP_BYTES;
+    const u32 n = (have && !bad) ? (u32)(o1 - o0) : 0;
     u32 nl = 0, drops = 0, m4 = 0, m5 = 0;
-    if (!live) {
-    } else if (staged) {
-        const u32 p0 = (u32)((ops.text + o0) - pa), p1 = p0 + n;
-        const u32 w0 = p0 >> 2, w1 = (p1 + 3) >> 2;
-        for (u32 w = w0; w < w1; ++w) {
+
+    if (staged && livemask) {
+        const u32 nvec = (u32)((span + 15) >> 4);
+        for (u32 v = lane; v < nvec; v += 32) *(uint4 *)(stage + 16 * v) = __ldg((const uint4 *)pa + v);
+        s_p0[warp][lane] = (u32)((ops.text + o0) - pa);
+        if (lane == 0) { s_p0[warp][32] = (u32)((ops.text + b1) - pa); s_nlist[warp] = 0; }
+        s_ca[warp][lane] = 0; s_cb[warp][lane] = 0;
+        __syncwarp();
+        // -- word-parallel scan: record the positions of '\n' and '~'
+        const u32 r0 = (u32)((ops.text + b0) - pa), r1 = (u32)span;
+        for (u32 w = (r0 >> 2) + lane; w < (r1 + 3) >> 2; w += 32) {
             const u32 x = *(const u32 *)(stage + 4 * w);
-            // 0x80 in every byte of the word that belongs to the string
-            u32 vm = 0x80808080u;
-            if (w == w0) vm &= 0xffffffffu << (8 * (p0 & 3));
-            if (w + 1 == w1 && (p1 & 3)) vm &= 0xffffffffu >> (8 * (4 - (p1 & 3)));
-            nl += (u32)__popc(nutsb_zero_bytes(x ^ 0x0a0a0a0au) & vm);
-            u32 mt = nutsb_zero_bytes(x ^ 0x7e7e7e7eu) & vm;
-            while (mt) {                                   // each '~' of the word, in order
-                const u32 bb = (u32)(__ffs((int)mt) - 1) >> 3;
-                mt &= mt - 1;
-                const u32 j = 4 * w + bb;
-                if (j > p0 && stage[j - 1] == '/') ++drops;
-                else if (j + 2 < p1) {
-                    const int k = nutsb_code(s_tab, stage[j + 1], stage[j + 2]);
-                    if (k >= 0) { if (k < 5) ++m4; else ++m5; }
-                }
+            u32 vm = 0x80808080u;                     // bytes of the word inside the warp's range
+            if (4 * w < r0) vm &= 0xffffffffu << (8 * (r0 - 4 * w));
+            if (4 * w + 4 > r1) vm &= 0xffffffffu >> (8 * (4 * w + 4 - r1));
+            const u32 mn = nutsb_zero_bytes(x ^ 0x0a0a0a0au) & vm, mt = nutsb_zero_bytes(x ^ 0x7e7e7e7eu) & vm;
+            u32 m = mn | mt;
+            while (m) {
+                const u32 bit = (u32)__ffs((int)m) - 1;
+                m &= m - 1;
+                const u32 slot = atomicAdd(&s_nlist[warp], 1u);
+                if (slot < NUTSB_MEASURE_LIST) s_list[warp][slot] = (4 * w + (bit >> 3)) | ((mn >> bit & 1u) << 31);
             }
         }
-    } else {
+        __syncwarp();
+        const u32 cnt = s_nlist[warp];
+        if (cnt <= NUTSB_MEASURE_LIST) {
+            // -- resolve the list, 32 entries at a time
+            for (u32 e = lane; e < cnt; e += 32) {
+                const u32 ent = s_list[warp][e];
+                const u32 j = ent & 0x7fffffffu;
+                u32 lo = 0, hi = nops;                 // owner: last q with p0[q] <= j
+                while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (s_p0[warp][mid] <= j) lo = mid; else hi = mid; }
+                const u32 q = lo;
+                if (!(livemask >> q & 1u)) continue;
+                const u32 q0 = s_p0[warp][q], q1 = s_p0[warp][q + 1];
+                if (ent >> 31) atomicAdd(&s_ca[warp][q], 1u);                               // '\n'
+                else if (j > q0 && stage[j - 1] == '/') atomicAdd(&s_ca[warp][q], 0x10000u); // "/~": slash dropped
+                else if (j + 2 < q1) {
+                    const int k = nutsb_code(s_tab, stage[j + 1], stage[j + 2]);
+                    if (k >= 0) atomicAdd(&s_cb[warp][q], k < 5 ? 1u : 0x10000u);
+                }
+            }
+            __syncwarp();
+            const u32 ca = s_ca[warp][lane], cb = s_cb[warp][lane];
+            nl = ca & 0xffffu; drops = ca >> 16; m4 = cb & 0xffffu; m5 = cb >> 16;
+        }
+    }
+    if (live && !(staged && s_nlist[warp] <= NUTSB_MEASURE_LIST)) {
+        // strings too long for the staging window, or too many special bytes: byte loop
         const u8 *s = ops.text + o0;
+        nl = drops = m4 = m5 = 0;
         for (u32 j = 0; j < n; ++j) {
             const u8 c = s[j];
             if (c == '\n') ++nl;
@@ -139,6 +168,10 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
             }
         }
     }
+    if (!have) return;
+    if (bad) { atomicOr(status, NUTSB_ST_BAD_OFFSETS); len_on[i] = len_off[i] = nrep[i] = 0; return; }
+    if (toolong) { atomicOr(status, NUTSB_ST_TEXT_TOO_LONG); len_on[i] = len_off[i] = nrep[i] = 0; return; }
+    u32 st = 0;
     const u32 loff = n - drops - 3 * (m4 + m5) + nl;
     len_off[i] = loff;
     len_on[i]  = loff + 4 * nl + 4 * m4 + 5 * m5 + 4;
@@ -189,30 +222,32 @@ k_expand(OpsView ops, PopView pop, const u32 *nrep, const u64 *eoff, u32 *e_room
 
 // hist[digit * nblocks + block]
 __global__ void __launch_bounds__(NUTSB_RS_THREADS)
-k_rs_hist(const u32 *keys, i64 n_host, const u32 *n_dev, int shift, u32 *hist, u32 nblocks)
+k_rs_hist(const u32 *keys, i64 n_host, const u32 *n_dev, int shift, u32 bits, u32 *hist, u32 nblocks)
 {
     const i64 n = n_dev ? (i64)*n_dev : n_host;
+    const u32 digits = 1u << bits;
     __shared__ u32 s_h[NUTSB_RS_DIGITS];
-    for (int d = threadIdx.x; d < NUTSB_RS_DIGITS; d += blockDim.x) s_h[d] = 0;
+    for (u32 d = threadIdx.x; d < digits; d += blockDim.x) s_h[d] = 0;
     __syncthreads();
     const i64 base = (i64)blockIdx.x * NUTSB_RS_CHUNK;
     for (int r = 0; r < NUTSB_RS_ROUNDS; ++r) {
         const i64 i = base + r * NUTSB_RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & (NUTSB_RS_DIGITS - 1)], 1u);
+        if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & (digits - 1)], 1u);
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < NUTSB_RS_DIGITS; d += blockDim.x)
+    for (u32 d = threadIdx.x; d < digits; d += blockDim.x)
         hist[(size_t)d * nblocks + blockIdx.x] = s_h[d];
 }
 
 // offs = exclusive scan of hist (same layout).  vals_in == nullptr means iota.
 __global__ void __launch_bounds__(NUTSB_RS_THREADS)
-k_rs_scatter(const u32 *keys_in, const u32 *vals_in, i64 n_host, const u32 *n_dev, int shift,
+k_rs_scatter(const u32 *keys_in, const u32 *vals_in, i64 n_host, const u32 *n_dev, int shift, u32 bits,
              const u64 *offs, u32 nblocks, u32 *keys_out, u32 *vals_out)
 {
     const i64 n = n_dev ? (i64)*n_dev : n_host;
+    const u32 digits = 1u << bits;
     __shared__ u32 s_run[NUTSB_RS_DIGITS];
-    for (int d = threadIdx.x; d < NUTSB_RS_DIGITS; d += blockDim.x)
+    for (u32 d = threadIdx.x; d < digits; d += blockDim.x)
         s_run[d] = (u32)offs[(size_t)d * nblocks + blockIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -221,7 +256,7 @@ k_rs_scatter(const u32 *keys_in, const u32 *vals_in, i64 n_host, const u32 *n_de
         const i64 i = base + r * NUTSB_RS_THREADS + threadIdx.x;
         const bool valid = i < n;
         const u32 key = valid ? keys_in[i] : 0;
-        const u32 d = valid ? ((key >> shift) & (NUTSB_RS_DIGITS - 1)) : 0xffffffffu;
+        const u32 d = valid ? ((key >> shift) & (digits - 1)) : 0xffffffffu;
         const u32 grp = __match_any_sync(NUTSB_FULL, d);
         const int leader = __ffs((int)grp) - 1;
         const u32 rank = (u32)__popc(grp & ((1u << lane) - 1));
@@ -373,6 +408,13 @@ struct UserLenIn {
         return cls + (sv_pre[ev_off[s + 1]] - sv_pre[ev_off[s]]);
     }
 };
+
+__global__ void __launch_bounds__(128)
+k_user_len(UserLenIn in, i64 n, u64 *len)
+{
+    const i64 u = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n) len[u] = in(u);
+}
 
 // ---- F. stream position of every (tile, recipient) cell ---------------------------------
 struct Geometry {

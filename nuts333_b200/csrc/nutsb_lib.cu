@@ -73,7 +73,7 @@ struct nutsb_ctx {
     DBuf d_vp_on, d_vp_off, d_cp;
     DBuf d_room_tile_off, d_room_cell_off, d_room_item_off, d_sizes, d_counters;
     DBuf d_cell_pos, d_cell_evi;
-    DBuf d_off, d_out, d_digest;
+    DBuf d_off, d_out, d_digest, d_ulen;
     HBuf h_small, h_off, h_out;
     u64 last_total = 0; bool have_streams = false;
 
@@ -131,6 +131,7 @@ static inline u32 bits_for(u64 n) { u32 b = 0; while (b < 32 && (1ull << b) < n)
 // scan / sort drivers
 // ---------------------------------------------------------------------------------------
 struct InU32 { const u32 *p; __device__ u64 operator()(i64 i) const { return p[i]; } };
+struct InU64 { const u64 *p; __device__ u64 operator()(i64 i) const { return p[i]; } };
 struct InI32 { const i32 *p; __device__ u64 operator()(i64 i) const { return (u64)(i64)p[i]; } };
 struct OutU64 { u64 *p; __device__ void operator()(i64 i, u64 ex) const { p[i] = ex; } };
 struct InEntryPacked {
@@ -161,10 +162,11 @@ static int run_scan(nutsb_ctx *c, In in, Out out, i64 n_upper, const u32 *n_dev)
     u64 *sums = c->d_sums.as<u64>();
     auto kr = k_scan_reduce<In>;
     auto ka = k_scan_apply<In, Out>;
+    const int fused = nb <= 1024 ? 1 : 0;
     NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, kr, in, n_upper, n_dev, sums); CKL();
-    NUTSB_LAUNCH(1, NUTSB_SCAN_THREADS, c->stream, k_scan_sums, sums, (i64)nb); CKL();
-    NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, ka, in, out, n_upper, n_dev, sums); CKL();
-    c->tm.launches += 3;
+    if (!fused) { NUTSB_LAUNCH(1, NUTSB_SCAN_THREADS, c->stream, k_scan_sums, sums, (i64)nb); CKL(); }
+    NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, ka, in, out, n_upper, n_dev, sums, fused); CKL();
+    c->tm.launches += fused ? 2 : 3;
     return NUTSB_OK;
 }
 
@@ -174,19 +176,20 @@ static int radix_sort(nutsb_ctx *c, DBuf kb[2], DBuf vb[2], i64 n_upper, const u
                       u32 **keys, u32 **vals)
 {
     const u32 passes = key_bits ? cdiv(key_bits, NUTSB_RS_BITS) : 1;
+    const u32 bits = std::max(1u, cdiv(key_bits, passes));            // digit width: passes balanced, tables small
     const u32 nblk = cdiv((u64)(n_upper > 0 ? n_upper : 1), NUTSB_RS_CHUNK);
-    const size_t hn = (size_t)NUTSB_RS_DIGITS * nblk;
+    const size_t hn = ((size_t)1 << bits) * nblk;
     TRY(ensure(c, c->d_hist, hn * sizeof(u32)));
     TRY(ensure(c, c->d_hoffs, (hn + 1) * sizeof(u64)));
     for (int q = 0; q < 2; ++q) { TRY(ensure(c, kb[q], (size_t)n_upper * 4 + 16)); TRY(ensure(c, vb[q], (size_t)n_upper * 4 + 16)); }
     int cur = 0;
     for (u32 p = 0; p < passes; ++p) {
-        const int shift = (int)(p * NUTSB_RS_BITS);
-        NUTSB_LAUNCH(nblk, NUTSB_RS_THREADS, c->stream, k_rs_hist, kb[cur].as<u32>(), n_upper, n_dev, shift,
+        const int shift = (int)(p * bits);
+        NUTSB_LAUNCH(nblk, NUTSB_RS_THREADS, c->stream, k_rs_hist, kb[cur].as<u32>(), n_upper, n_dev, shift, bits,
                      c->d_hist.as<u32>(), nblk); CKL();
         TRY(run_scan(c, InU32{c->d_hist.as<u32>()}, OutU64{c->d_hoffs.as<u64>()}, (i64)hn, nullptr));
         NUTSB_LAUNCH(nblk, NUTSB_RS_THREADS, c->stream, k_rs_scatter, kb[cur].as<u32>(),
-                     p == 0 ? (const u32 *)nullptr : vb[cur].as<u32>(), n_upper, n_dev, shift,
+                     p == 0 ? (const u32 *)nullptr : vb[cur].as<u32>(), n_upper, n_dev, shift, bits,
                      c->d_hoffs.as<u64>(), nblk, kb[cur ^ 1].as<u32>(), vb[cur ^ 1].as<u32>()); CKL();
         c->tm.launches += 2;
         cur ^= 1;
@@ -323,7 +326,7 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
         &c->d_evk[1], &c->d_evv[0], &c->d_evv[1], &c->d_ev_ukey, &c->d_ev_delta, &c->d_ev_op, &c->d_sv_ukey,
         &c->d_sv_delta, &c->d_sv_op, &c->d_sv_pre, &c->d_ev_off, &c->d_vp_on, &c->d_vp_off, &c->d_cp,
         &c->d_room_tile_off, &c->d_room_cell_off, &c->d_room_item_off, &c->d_sizes, &c->d_counters,
-        &c->d_cell_pos, &c->d_cell_evi, &c->d_off, &c->d_out, &c->d_digest,
+        &c->d_cell_pos, &c->d_cell_evi, &c->d_off, &c->d_out, &c->d_digest, &c->d_ulen,
         &c->s_text, &c->s_toff, &c->s_kind, &c->s_target, &c->s_except, &c->s_flags, &c->s_gate, &c->s_verdict, &c->s_v8 };
     for (DBuf *b : all) release(*b);
     release(c->h_small); release(c->h_off); release(c->h_out);
@@ -578,17 +581,19 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     // the op index rides as the key's payload: first pass must not use iota
     u32 *e_room = nullptr, *e_op = nullptr;
     {
-        const u32 passes = std::max(1u, cdiv(bits_for((u64)Rt), NUTSB_RS_BITS));
+        const u32 kbits = std::max(1u, bits_for((u64)Rt));
+        const u32 passes = cdiv(kbits, NUTSB_RS_BITS);
+        const u32 bits = cdiv(kbits, passes);
         const u32 nblk = cdiv(E, NUTSB_RS_CHUNK);
-        const size_t hn = (size_t)NUTSB_RS_DIGITS * nblk;
+        const size_t hn = ((size_t)1 << bits) * nblk;
         TRY(ensure(c, c->d_hist, hn * 4)); TRY(ensure(c, c->d_hoffs, (hn + 1) * 8));
         int cur = 0;
         for (u32 p = 0; p < passes; ++p) {
-            const int shift = (int)(p * NUTSB_RS_BITS);
-            NUTSB_LAUNCH(nblk, NUTSB_RS_THREADS, st, k_rs_hist, c->d_ek[cur].as<u32>(), (i64)E, (const u32 *)nullptr, shift, c->d_hist.as<u32>(), nblk); CKL();
+            const int shift = (int)(p * bits);
+            NUTSB_LAUNCH(nblk, NUTSB_RS_THREADS, st, k_rs_hist, c->d_ek[cur].as<u32>(), (i64)E, (const u32 *)nullptr, shift, bits, c->d_hist.as<u32>(), nblk); CKL();
             TRY(run_scan(c, InU32{c->d_hist.as<u32>()}, OutU64{c->d_hoffs.as<u64>()}, (i64)hn, nullptr));
             NUTSB_LAUNCH(nblk, NUTSB_RS_THREADS, st, k_rs_scatter, c->d_ek[cur].as<u32>(), c->d_ev_[cur].as<u32>(), (i64)E,
-                         (const u32 *)nullptr, shift, c->d_hoffs.as<u64>(), nblk, c->d_ek[cur ^ 1].as<u32>(), c->d_ev_[cur ^ 1].as<u32>()); CKL();
+                         (const u32 *)nullptr, shift, bits, c->d_hoffs.as<u64>(), nblk, c->d_ek[cur ^ 1].as<u32>(), c->d_ev_[cur ^ 1].as<u32>()); CKL();
             c->tm.launches += 2; cur ^= 1;
         }
         e_room = c->d_ek[cur].as<u32>(); e_op = c->d_ev_[cur].as<u32>();
@@ -643,7 +648,9 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
 
     // -- E. stream offsets, geometry
     UserLenIn uli{ cpx, pop, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_pre.as<u64>() };
-    TRY(run_scan(c, uli, OutU64{c->d_off.as<u64>()}, (i64)U, nullptr));
+    TRY(ensure(c, c->d_ulen, ((size_t)U + 1) * 8));
+    if (U > 0) { NUTSB_LAUNCH(cdiv((u64)U, 128), 128, st, k_user_len, uli, (i64)U, c->d_ulen.as<u64>()); CKL(); c->tm.launches++; }
+    TRY(run_scan(c, InU64{c->d_ulen.as<u64>()}, OutU64{c->d_off.as<u64>()}, (i64)U, nullptr));
     TRY(ensure(c, c->d_room_tile_off, ((size_t)Rt + 2) * 4)); TRY(ensure(c, c->d_room_cell_off, ((size_t)Rt + 2) * 8));
     TRY(ensure(c, c->d_room_item_off, ((size_t)Rt + 2) * 4));
     NUTSB_LAUNCH(1, NUTSB_SCAN_THREADS, st, k_geometry, pop, c->d_room_b_off.as<u32>(), c->d_off.as<u64>(), counts,
