@@ -28,6 +28,30 @@ typedef uint8_t            u8;
 
 #define NUTSB_FULL 0xffffffffu
 
+// ---- TMA bulk copy shared -> global (cp.async.bulk, SASS: UBLKCP) -------------------------
+// 16-byte aligned source, destination and size.  Bulk-group completion: commit, then
+// wait_read before the shared source is overwritten, wait_all before the block exits.
+#ifdef NUTSB_CPUSIM
+static inline void nutsb_bulk_s2g(void *gdst, const void *ssrc, u32 bytes) { memcpy(gdst, ssrc, bytes); }
+static inline void nutsb_bulk_commit() {}
+static inline void nutsb_bulk_wait_read() {}
+static inline void nutsb_bulk_wait_read1() {}
+static inline void nutsb_bulk_wait_all() {}
+static inline void nutsb_fence_async_smem() {}
+#else
+__device__ __forceinline__ void nutsb_bulk_s2g(void *gdst, const void *ssrc, u32 bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((u32)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void nutsb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void nutsb_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void nutsb_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void nutsb_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy writes to shared memory visible to the async proxy (TMA)
+__device__ __forceinline__ void nutsb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
 __device__ __forceinline__ void nutsb_add64(u64 *p, u64 v) { atomicAdd((unsigned long long *)p, (unsigned long long)v); }
 
 // Status bits raised by kernels (ctx->d_status), decoded on the host.

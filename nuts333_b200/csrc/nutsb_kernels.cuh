@@ -36,11 +36,14 @@ struct PopView {                 // the population, built by nutsb_set_users
     const u8  *codetab;          // [676]
 };
 
-#define NUTSB_TILE_OPS   128     // room-list ops per fan-out tile
-#define NUTSB_UCHUNK     128     // recipients per fan-out work item
-#define NUTSB_TEXT_CAP   11264   // staged source bytes per (sub)tile   (>= 2000+6)
-#define NUTSB_ON_CAP     12288   // rendered bytes per (sub)tile, colour on  (>= 6*2000+4)
-#define NUTSB_OFF_CAP    10240   // rendered bytes per (sub)tile, colour off (>= 2*2000)
+#ifndef NUTSB_TILE_OPS
+#define NUTSB_TILE_OPS   128     // room-list ops per fan-out tile (power of two; k_fanout runs 2 threads per op)
+#endif
+#define NUTSB_UCHUNK     (NUTSB_TILE_OPS < 128 ? NUTSB_TILE_OPS : 128)   // recipients per fan-out work item
+#define NUTSB_MAX2(a, b) ((a) > (b) ? (a) : (b))
+#define NUTSB_TEXT_CAP   NUTSB_MAX2(2048 + 64, 88 * NUTSB_TILE_OPS)   // staged source bytes per (sub)tile   (>= 2000+6)
+#define NUTSB_ON_CAP     NUTSB_MAX2(12288, 96 * NUTSB_TILE_OPS)       // rendered bytes per (sub)tile, colour on  (>= 6*2000+4)
+#define NUTSB_OFF_CAP    NUTSB_MAX2(4096, 80 * NUTSB_TILE_OPS)        // rendered bytes per (sub)tile, colour off (>= 2*2000)
 #define NUTSB_EV_CAP     256     // events of a tile's recipients prefetched into shared memory
 #define NUTSB_RUN_CAP    512     // planned copy runs per (sub)tile and recipient chunk
 
@@ -653,8 +656,18 @@ struct FanoutArgs {
     u32 has_level;
 };
 
-#define NUTSB_FAN_THREADS 256
-#define NUTSB_FAN_SMEM (NUTSB_TEXT_CAP + 32 + NUTSB_ON_CAP + 64 + NUTSB_OFF_CAP + 64)
+#define NUTSB_FAN_THREADS (2 * NUTSB_TILE_OPS)
+#ifndef NUTSB_FAN_TMA
+#define NUTSB_FAN_TMA 0          // 1: copy runs with TMA bulk stores from 16 pre-shifted slab pieces (measured slower: DESIGN.md 4.1)
+#endif
+#ifndef NUTSB_FAN_PIECE
+#define NUTSB_FAN_PIECE 2048     // slab bytes per TMA staging round (multiple of 512)
+#endif
+#ifndef NUTSB_FAN_DB
+#define NUTSB_FAN_DB 1           // two staging areas: the next piece is built while the TMA reads this one
+#endif
+#define NUTSB_FAN_STAGE (NUTSB_FAN_TMA ? (NUTSB_FAN_DB ? 2 : 1) * 16 * NUTSB_FAN_PIECE : 0)
+#define NUTSB_FAN_SMEM (NUTSB_TEXT_CAP + 32 + NUTSB_ON_CAP + 64 + NUTSB_OFF_CAP + 64 + NUTSB_FAN_STAGE)
 static_assert(NUTSB_FAN_THREADS == 2 * NUTSB_TILE_OPS && (NUTSB_TILE_OPS & (NUTSB_TILE_OPS - 1)) == 0 &&
               NUTSB_UCHUNK <= NUTSB_FAN_THREADS / 2, "k_fanout thread mapping");
 
@@ -787,7 +800,7 @@ k_fanout(FanoutArgs A)
                 const u32 *g = (const u32 *)(src - al);
                 const u32 nw = (al + s_tlen[i] + 3) >> 2;
                 u32 *win = (u32 *)(s_text + (s_toff[i] - s_toff[a]));
-                for (u32 w = (u32)tid >> 7; w < nw; w += 2) win[w] = __ldg(g + w);
+                for (u32 w = (u32)tid / NUTSB_TILE_OPS; w < nw; w += 2) win[w] = __ldg(g + w);
             }
         }
         __syncthreads();
@@ -850,6 +863,80 @@ k_fanout(FanoutArgs A)
         }
         __syncthreads();
 
+#if NUTSB_FAN_TMA
+        // -- copy with the TMA: a run's destination is byte-aligned, a bulk copy wants 16-byte
+        //    aligned source, destination and size.  So: (1) every run's head and tail (< 16
+        //    bytes each) are stored byte-wise by one thread per run; (2) the slab is taken a
+        //    piece at a time; each piece is written 16 times into a staging area, copy r
+        //    shifted left by r bytes, so whatever (source - destination) mod 16 a run has,
+        //    there is a copy in which its body is 16-byte aligned; (3) one thread per run
+        //    issues the body as one bulk store per piece; the SM moves no body bytes itself.
+        {
+            const u32 nruns = s_nruns < NUTSB_RUN_CAP ? s_nruns : NUTSB_RUN_CAP;
+            u8 *const s_stg0 = s_off + NUTSB_OFF_CAP + 64;
+            u32 round = 0;
+            for (u32 r = (u32)tid; r < nruns; r += NUTSB_FAN_THREADS) {
+                const u32 so = s_rsrc[r], len = s_rlen[r];
+                const u8 *src = ((so >> 31) ? s_on : s_off) + (so & 0x7fffffffu);
+                u8 *dst = A.out + s_rdst[r];
+                u32 head = (u32)((16 - ((size_t)dst & 15)) & 15);
+                if (head > len) head = len;
+                for (u32 q = 0; q < head; ++q) dst[q] = src[q];
+                for (u32 q = head + ((len - head) & ~15u); q < len; ++q) dst[q] = src[q];
+            }
+            bool issued = false;
+            for (int colour = 1; colour >= 0; --colour) {
+                const u8 *slab = colour ? s_on : s_off;
+                const u32 L = colour ? s_oon[b] - s_oon[a] : s_ooff[b] - s_ooff[a];
+                for (u32 P0 = 0; P0 < L; P0 += NUTSB_FAN_PIECE, ++round) {
+                    u8 *const s_stg = s_stg0 + (NUTSB_FAN_DB ? (round & 1) * 16 * NUTSB_FAN_PIECE : 0);
+                    // (2) the 16 shifted copies of this piece: copy r holds slab[P0+r .. P0+r+PIECE)
+                    for (u32 idx = (u32)tid; idx < NUTSB_FAN_PIECE; idx += NUTSB_FAN_THREADS) {
+                        const u32 r = idx / (NUTSB_FAN_PIECE / 16), v = idx % (NUTSB_FAN_PIECE / 16);   // r is uniform per warp
+                        if (P0 + r + 16 * v >= L) continue;
+                        const uint4 *sa = (const uint4 *)(slab + P0) + v;
+                        const uint4 x = sa[0], y = sa[1];
+                        const u32 bsh = (r & 3) * 8;
+                        uint4 o;
+                        switch (r >> 2) {
+                        case 0:  o = nutsb_realign<0>(x, y, bsh); break;
+                        case 1:  o = nutsb_realign<1>(x, y, bsh); break;
+                        case 2:  o = nutsb_realign<2>(x, y, bsh); break;
+                        default: o = nutsb_realign<3>(x, y, bsh); break;
+                        }
+                        ((uint4 *)(s_stg + r * NUTSB_FAN_PIECE))[v] = o;
+                    }
+                    nutsb_fence_async_smem();
+                    __syncthreads();
+                    // (3) bodies: one bulk store per (run, piece)
+                    for (u32 q = (u32)tid; q < nruns; q += NUTSB_FAN_THREADS) {
+                        const u32 so = s_rsrc[q];
+                        if ((int)(so >> 31) != colour) continue;
+                        const u32 S = so & 0x7fffffffu, len = s_rlen[q];
+                        const u64 D = s_rdst[q];
+                        u32 head = (u32)((16 - (((size_t)A.out + D) & 15)) & 15);
+                        if (head > len) head = len;
+                        const u32 nvec = (len - head) >> 4;
+                        if (!nvec) continue;
+                        const u32 Sp = S + head, r = Sp & 15;             // slab bases are 16-byte aligned
+                        const u32 lo = P0 + r, hi = lo + NUTSB_FAN_PIECE;
+                        const u32 x0 = Sp > lo ? Sp : lo, x1 = Sp + 16 * nvec < hi ? Sp + 16 * nvec : hi;
+                        if (x1 > x0) {
+                            nutsb_bulk_s2g(A.out + D + head + (x0 - Sp), s_stg + r * NUTSB_FAN_PIECE + (x0 - lo), x1 - x0);
+                            issued = true;
+                        }
+                    }
+                    nutsb_bulk_commit();
+                    if (NUTSB_FAN_DB) nutsb_bulk_wait_read1();   // the other staging area is free again
+                    else nutsb_bulk_wait_read();                  // the staging area is rewritten by the next round
+                    __syncthreads();
+                }
+            }
+            nutsb_bulk_wait_read();                  // slabs and staging are reused by the next sub-tile
+            if (issued) nutsb_bulk_wait_all();
+            __syncthreads();
+        }
+#else
         // -- copy: warps pull planned runs; a run is one contiguous piece of a recipient's stream
         {
             const u32 nruns = s_nruns < NUTSB_RUN_CAP ? s_nruns : NUTSB_RUN_CAP;
@@ -862,6 +949,7 @@ k_fanout(FanoutArgs A)
                 nutsb_warp_copy(A.out + s_rdst[r], ((so >> 31) ? s_on : s_off) + (so & 0x7fffffffu), s_rlen[r], lane);
             }
         }
+#endif
         // -- recipients that are not plain listeners (login / ignall / ignshout, level ops in the
         //    batch) or did not fit the queue: one warp per recipient, op by op where needed
         for (u32 ls = ls_begin + warp; ls < ls_end; ls += NUTSB_FAN_THREADS / 32) {
