@@ -1028,27 +1028,30 @@ struct DirectArgs {
 };
 
 #define NUTSB_DIRECT_THREADS 256
-#define NUTSB_DIR_TEXT_CAP 14336
-#define NUTSB_DIR_OUT_CAP  20480
+#define NUTSB_DIR_WTEXT 2560        // per-warp staging bytes  (>= 2000 + 12)
+#define NUTSB_DIR_WOUT  3072        // per-warp rendered bytes
 
+// Warps are independent (no block barrier in the loop): a warp takes 32 consecutive
+// events, the direct ops among them are staged, rendered and copied out by their own
+// lanes through the warp's private shared-memory windows, in sub-batches that fit the
+// windows.  A rendering too large for the window (a 2000-byte string of newlines is
+// 12 KB) is written to the stream directly by its lane.
 __global__ void __launch_bounds__(NUTSB_DIRECT_THREADS)
 k_direct(DirectArgs A)
 {
-    __shared__ __align__(16) u8 s_text[NUTSB_DIR_TEXT_CAP + 32];
-    __shared__ __align__(16) u8 s_out[NUTSB_DIR_OUT_CAP + 64];
+    __shared__ __align__(16) u8 s_text[NUTSB_DIRECT_THREADS / 32][NUTSB_DIR_WTEXT + 32];
+    __shared__ __align__(16) u8 s_out[NUTSB_DIRECT_THREADS / 32][NUTSB_DIR_WOUT + 64];
     __shared__ u8  s_tab[NUTSB_CODETAB_BYTES];
-    __shared__ u64 s_p[NUTSB_DIRECT_THREADS], s_src[NUTSB_DIRECT_THREADS];
-    __shared__ u32 s_n[NUTSB_DIRECT_THREADS];
-    __shared__ u32 s_pt[NUTSB_DIRECT_THREADS + 1], s_po[NUTSB_DIRECT_THREADS + 1];
-    __shared__ u8  s_col[NUTSB_DIRECT_THREADS];
-    __shared__ u32 s_sub_b;
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ u32 s_cnt;
+    __shared__ unsigned long long s_bytes;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < NUTSB_CODETAB_BYTES; i += NUTSB_DIRECT_THREADS) s_tab[i] = A.pop.codetab[i];
+    if (tid == 0) { s_cnt = 0; s_bytes = 0; }
+    __syncthreads();
 
-    // -- the direct ops among this block's 256 events, compacted to the front
     const i64 e = (i64)blockIdx.x * NUTSB_DIRECT_THREADS + tid;
     bool isw = false, colour = false;
-    u64 p = 0, t0 = 0; u32 n = 0, tsz = 0, osz = 0;
+    u64 p = 0; const u8 *src = A.ops.text; u32 n = 0, tsz = 0, osz = 0;
     if (e < A.n_ev) {
         const u32 uk = A.sv_ukey[e];
         if (!(uk & 1)) {                                   // an odd key is an exclusion
@@ -1058,55 +1061,56 @@ k_direct(DirectArgs A)
             const i32 k = A.pop.user_cls[u];
             const u32 b0 = A.room_b_off[room];
             const u32 op = A.sv_op[e];
-            t0 = A.ops.toff[op];
+            const u64 t0 = A.ops.toff[op];
             p = A.stream_off[u] + (A.cpx.at(k, room, b0 + (uk >> 1)) - A.cpx.at(k, room, b0))
               + (A.sv_pre[e] - A.sv_pre[A.ev_off[s]]);
+            src = A.ops.text + t0;
             n = (u32)(A.ops.toff[op + 1] - t0);
             colour = (A.pop.slot_cf[s] & NUTSB_UF_COLOUR) != 0;
             isw = true;
-            tsz = nutsb_stage_bytes(A.ops.text + t0, n);
+            tsz = nutsb_stage_bytes(src, n);
             osz = (u32)A.sv_delta[e];
         }
     }
-    u64 tot_t, tot_o, tot_w;
-    const u32 pt = (u32)nutsb_block_excl_scan(tsz, &tot_t);
-    const u32 po = (u32)nutsb_block_excl_scan(osz, &tot_o);
-    const u32 cp = (u32)nutsb_block_excl_scan(isw ? 1u : 0u, &tot_w);
-    const u32 nw = (u32)tot_w;
-    if (isw) { s_p[cp] = p; s_src[cp] = t0; s_n[cp] = n; s_pt[cp] = pt; s_po[cp] = po; s_col[cp] = colour ? 1 : 0; }
-    if (tid == 0) { s_pt[nw] = (u32)tot_t; s_po[nw] = (u32)tot_o; }
-    __syncthreads();
-
-    // -- thread t handles compacted op t: stage, render in the recipient's colour setting,
-    //    copy to the stream; sub-batches [a,b) sized to shared memory
+    // inclusive prefixes over the warp's lanes
+    u32 it = tsz, io = osz;
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 xt = __shfl_up_sync(NUTSB_FULL, it, d), xo = __shfl_up_sync(NUTSB_FULL, io, d);
+        if (lane >= d) { it += xt; io += xo; }
+    }
+    u8 *const wtext = s_text[warp];
+    u8 *const wout = s_out[warp];
     u32 a = 0;
-    while (a < nw) {
-        if (tid == 0) {
-            u32 b = nw;
-            if (s_pt[b] - s_pt[a] > NUTSB_DIR_TEXT_CAP || s_po[b] - s_po[a] > NUTSB_DIR_OUT_CAP) {
-                b = a + 1;
-                while (b < nw && s_pt[b + 1] - s_pt[a] <= NUTSB_DIR_TEXT_CAP && s_po[b + 1] - s_po[a] <= NUTSB_DIR_OUT_CAP) ++b;
+    while (a < 32) {
+        const u32 bt = __shfl_sync(NUTSB_FULL, it - tsz, (int)a), bo = __shfl_sync(NUTSB_FULL, io - osz, (int)a);   // exclusive at lane a
+        const bool fits = (u32)lane >= a && it - bt <= NUTSB_DIR_WTEXT && io - bo <= NUTSB_DIR_WOUT;
+        const u32 nofit = __ballot_sync(NUTSB_FULL, (u32)lane >= a && !fits);
+        u32 b = nofit ? (u32)__ffs((int)nofit) - 1 : 32u;          // [a,b) fits the windows
+        if (b == a) {
+            // lane a's rendering alone exceeds the window: stage it, render straight into the stream
+            if ((u32)lane == a && isw) {
+                nutsb_lane_stage(wtext, src, n);
+                if (nutsb_render1(wtext + ((u32)(size_t)src & 3u), n, colour, A.out + p, s_tab) != osz)
+                    atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
             }
-            s_sub_b = b;
-        }
-        __syncthreads();
-        const u32 b = s_sub_b;
-        const u32 i = (u32)tid;
-        if (i >= a && i < b) {
-            const u8 *src = A.ops.text + s_src[i];
-            u8 *win = s_text + (s_pt[i] - s_pt[a]);
-            u8 *dst = s_out + (s_po[i] - s_po[a]);
-            const u32 want = s_po[i + 1] - s_po[i];
-            nutsb_lane_stage(win, src, s_n[i]);
-            if (nutsb_render1(win + ((u32)(size_t)src & 3u), s_n[i], s_col[i] != 0, dst, s_tab) != want)
+            b = a + 1;
+        } else if (isw && (u32)lane >= a && (u32)lane < b) {
+            u8 *win = wtext + (it - tsz - bt);
+            u8 *dst = wout + (io - osz - bo);
+            nutsb_lane_stage(win, src, n);
+            if (nutsb_render1(win + ((u32)(size_t)src & 3u), n, colour, dst, s_tab) != osz)
                 atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
-            nutsb_lane_copy(A.out + s_p[i], dst, want);
+            nutsb_lane_copy(A.out + p, dst, osz);
         }
-        __syncthreads();
+        __syncwarp();                                       // the windows are reused by the next sub-batch
         a = b;
     }
-    if (tid == 0 && nw) { nutsb_add64(A.n_deliveries, (u64)nw); nutsb_add64(A.n_deliveries + 1, (u64)tot_o); }
-    (void)lane;
+    const u32 wcnt = (u32)__popc(__ballot_sync(NUTSB_FULL, isw));
+    u32 wbytes = isw ? osz : 0;
+    for (int d = 16; d; d >>= 1) wbytes += __shfl_xor_sync(NUTSB_FULL, wbytes, d);
+    if (lane == 0 && wcnt) { atomicAdd(&s_cnt, wcnt); atomicAdd(&s_bytes, (unsigned long long)wbytes); }
+    __syncthreads();
+    if (tid == 0 && s_cnt) { nutsb_add64(A.n_deliveries, (u64)s_cnt); nutsb_add64(A.n_deliveries + 1, (u64)s_bytes); }
 }
 
 // ---- stream digests ------------------------------------------------------------------------
