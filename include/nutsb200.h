@@ -78,6 +78,11 @@ enum {
 #define NUTSB_OF_ABOVE        0x04u  /* write_level's `above`                          */
 #define NUTSB_OF_GATE_IF_SET  0x08u  /* with gate>=0: live iff verdict[gate]!=0,
                                         else live iff verdict[gate]==0 (say(), c:4091) */
+#define NUTSB_OF_PAGER        0x10u  /* render as the pager more() renders a file line
+                                        (nuts333.c:2254-2300): the same byte machine, but
+                                        no terminal reset after the string (c:1365 absent) */
+#define NUTSB_OF_PLAIN        0x20u  /* the recipient's colour setting is ignored and taken
+                                        as off: more(NULL,sock,file) at login (c:2259,2279) */
 
 typedef struct nutsb_ctx nutsb_ctx;
 
@@ -187,6 +192,17 @@ int nutsb_q_write_room_except(nutsb_ctx *ctx, int32_t room, const char *str, int
                               int force_listen, int shout);                       /* c:1401 */
 int nutsb_q_write_level(nutsb_ctx *ctx, int level, int above, const char *str,
                         int32_t except_user);                                     /* c:1372 */
+/* One fgets() chunk of a paged file as more() writes it (c:2254-2300): the byte machine of
+ * write_user without the closing reset; plain != 0 when more() was called with user==NULL. */
+int nutsb_q_page_line(nutsb_ctx *ctx, int32_t sock_user, const char *str, int plain);
+/* The pager more(user, sock, filename) (c:2205-2322) over the file's BYTES (file == NULL:
+ * fopen failed): queues one page -- the fgets(text,1999) chunks from *filepos until 23
+ * screen lines are counted (all of it when user < 0) and, if the file is not finished, the
+ * "Press <return>" prompt -- for sock_user, updates *filepos as the reference updates
+ * user->filepos, and returns more()'s return value (0 no file, 1 more to come, 2 done) in
+ * *retval.  user = -1 stands for user==NULL (login: colour taken as off, no paging). */
+int nutsb_q_more(nutsb_ctx *ctx, int32_t user, int32_t sock_user, const void *file, size_t file_len,
+                 int64_t *filepos, int *retval);
 int64_t nutsb_q_pending(const nutsb_ctx *ctx);
 /* Runs everything queued since the last flush; the host then write()s each
  * user's stream to its socket. */

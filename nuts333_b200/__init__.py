@@ -7,6 +7,6 @@ user_banned) as hand-written sm_100a CUDA kernels behind a C-ABI.
 The CUDA library is built in-tree by `nuts333_b200.build.build()`; there is no CPU path.
 """
 from .api import (Context, Talker, Streams, NutsbError, pack,  # noqa: F401
-                  OP_USER, OP_ROOM, OP_LEVEL, OF_FORCE_LISTEN, OF_SHOUT, OF_ABOVE, OF_GATE_IF_SET,
+                  OP_USER, OP_ROOM, OP_LEVEL, OF_FORCE_LISTEN, OF_SHOUT, OF_ABOVE, OF_GATE_IF_SET, OF_PAGER, OF_PLAIN,
                   UF_COLOUR, UF_LOGIN, UF_IGNALL, UF_IGNSHOUT, SAY, SHOUT, SEMOTE,
                   NEW, USER, WIZ, ARCH, GOD)

@@ -20,7 +20,7 @@ from pathlib import Path
 import numpy as np
 
 OP_USER, OP_ROOM, OP_LEVEL = 0, 1, 2
-OF_FORCE_LISTEN, OF_SHOUT, OF_ABOVE, OF_GATE_IF_SET = 1, 2, 4, 8
+OF_FORCE_LISTEN, OF_SHOUT, OF_ABOVE, OF_GATE_IF_SET, OF_PAGER, OF_PLAIN = 1, 2, 4, 8, 16, 32
 UF_COLOUR, UF_LOGIN, UF_IGNALL, UF_IGNSHOUT, UF_CLONE, UF_REMOTE = 1, 2, 4, 8, 16, 32
 MAX_TEXT = 2000
 
@@ -67,7 +67,7 @@ EXPORTS = [
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
     "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
-    "nutsb_q_write_level", "nutsb_q_pending", "nutsb_flush", "nutsb_contains_swearing",
+    "nutsb_q_write_level", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_contains_swearing",
     "nutsb_site_banned", "nutsb_user_banned",
 ]
 
@@ -104,6 +104,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_q_write_room.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int, C.c_int]
     lib.nutsb_q_write_room_except.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int32, C.c_int, C.c_int]
     lib.nutsb_q_write_level.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.c_int32]
+    lib.nutsb_q_page_line.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int]
+    lib.nutsb_q_more.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_size_t, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
     lib.nutsb_q_pending.restype = C.c_int64
     lib.nutsb_q_pending.argtypes = [vp]
     lib.nutsb_flush.argtypes = [vp, C.POINTER(_Streams)]
@@ -293,6 +295,7 @@ class Talker:
         self.ctx = ctx
         self.force_listen = 0      # nuts333.h:293
         self.com_num = -1          # nuts333.h:201
+        self.filepos = {}          # user->filepos (nuts333.h:75), per user index
 
     @staticmethod
     def _s(s):
@@ -317,6 +320,24 @@ class Talker:
     def write_level(self, level, above, s, user):                    # c:1372
         c = self.ctx
         c._ck(c.lib.nutsb_q_write_level(c._h, level, 1 if above else 0, self._s(s), -1 if user is None else user))
+
+    def more(self, user, sock, filename) -> int:                    # c:2205
+        """The pager: queues one page of `filename` for the user on socket `sock` (a user
+        index; user None = the login-stage call more(NULL,sock,file)).  The file position
+        is kept per user like user->filepos.  Returns more()'s return value (0, 1 or 2)."""
+        c = self.ctx
+        try:
+            with open(filename, "rb") as fh:
+                data = fh.read()
+        except OSError:
+            data = None
+        key = -1 if user is None else user
+        pos = C.c_int64(self.filepos.get(key, 0))
+        rv = C.c_int(0)
+        c._ck(c.lib.nutsb_q_more(c._h, key, sock, data, 0 if data is None else len(data), C.byref(pos), C.byref(rv)))
+        if user is not None:
+            self.filepos[key] = pos.value
+        return rv.value
 
     def pending(self) -> int:
         return int(self.ctx.lib.nutsb_q_pending(self.ctx._h))

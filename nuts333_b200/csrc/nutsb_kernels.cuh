@@ -176,8 +176,10 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
     if (toolong) { atomicOr(status, NUTSB_ST_TEXT_TOO_LONG); len_on[i] = len_off[i] = nrep[i] = 0; return; }
     u32 st = 0;
     const u32 loff = n - drops - 3 * (m4 + m5) + nl;
+    const u32 of = ops.flags[i];
     len_off[i] = loff;
-    len_on[i]  = loff + 4 * nl + 4 * m4 + 5 * m5 + 4;
+    len_on[i]  = (of & NUTSB_OF_PLAIN) ? loff                                   // colour setting ignored
+               : loff + 4 * nl + 4 * m4 + 5 * m5 + ((of & NUTSB_OF_PAGER) ? 0u : 4u);   // pager lines carry no final reset
 
     // fan-in: how many room lists this op enters
     const u32 kind = ops.kind[i];
@@ -488,8 +490,9 @@ __device__ __forceinline__ u64 nutsb_code_pack(int k)
 // takes a branch (the table lookup).  The string must sit in a window that
 // starts at a 4-byte boundary (nutsb_lane_stage / nutsb_warp_stage); bytes of
 // the window outside the string are never interpreted.  Returns the rendered length.
-__device__ __forceinline__ u32 nutsb_render1(const u8 *s, u32 n, bool colour, u8 *out, const u8 *tab)
+__device__ __forceinline__ u32 nutsb_render1(const u8 *s, u32 n, bool colour, u32 oflags, u8 *out, const u8 *tab)
 {
+    if (oflags & NUTSB_OF_PLAIN) colour = false;                 // more(NULL,...): c:2259
     u32 i = 0, o = 0;
     while (i < n) {
         const u8 *p = s + i;
@@ -534,7 +537,9 @@ __device__ __forceinline__ u32 nutsb_render1(const u8 *s, u32 n, bool colour, u8
         if (len > 5) d[5] = (u8)(val >> 40);
         o += np + len; i += adv;
     }
-    if (colour) { out[o] = 0x1b; out[o + 1] = '['; out[o + 2] = '0'; out[o + 3] = 'm'; o += 4; }  /* c:1365 */
+    if (colour && !(oflags & NUTSB_OF_PAGER)) {                  /* c:1365; the pager has no such reset */
+        out[o] = 0x1b; out[o + 1] = '['; out[o + 2] = '0'; out[o + 3] = 'm'; o += 4;
+    }
     return o;
 }
 
@@ -813,7 +818,7 @@ k_fanout(FanoutArgs A)
                 const u8 *src = A.ops.text + s_src[i];
                 const u8 *str = s_text + (s_toff[i] - s_toff[a]) + ((u32)(size_t)src & 3u);
                 const u32 *offc = on ? s_oon : s_ooff;
-                const u32 got = nutsb_render1(str, s_tlen[i], on, (on ? s_on : s_off) + (offc[i] - offc[a]), s_tab);
+                const u32 got = nutsb_render1(str, s_tlen[i], on, s_flags[i], (on ? s_on : s_off) + (offc[i] - offc[a]), s_tab);
                 if (got != offc[i + 1] - offc[i]) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
             }
         }
@@ -1051,7 +1056,7 @@ k_direct(DirectArgs A)
 
     const i64 e = (i64)blockIdx.x * NUTSB_DIRECT_THREADS + tid;
     bool isw = false, colour = false;
-    u64 p = 0; const u8 *src = A.ops.text; u32 n = 0, tsz = 0, osz = 0;
+    u64 p = 0; const u8 *src = A.ops.text; u32 n = 0, tsz = 0, osz = 0, oflags = 0;
     if (e < A.n_ev) {
         const u32 uk = A.sv_ukey[e];
         if (!(uk & 1)) {                                   // an odd key is an exclusion
@@ -1067,6 +1072,7 @@ k_direct(DirectArgs A)
             src = A.ops.text + t0;
             n = (u32)(A.ops.toff[op + 1] - t0);
             colour = (A.pop.slot_cf[s] & NUTSB_UF_COLOUR) != 0;
+            oflags = A.ops.flags[op];
             isw = true;
             tsz = nutsb_stage_bytes(src, n);
             osz = (u32)A.sv_delta[e];
@@ -1090,7 +1096,7 @@ k_direct(DirectArgs A)
             // lane a's rendering alone exceeds the window: stage it, render straight into the stream
             if ((u32)lane == a && isw) {
                 nutsb_lane_stage(wtext, src, n);
-                if (nutsb_render1(wtext + ((u32)(size_t)src & 3u), n, colour, A.out + p, s_tab) != osz)
+                if (nutsb_render1(wtext + ((u32)(size_t)src & 3u), n, colour, oflags, A.out + p, s_tab) != osz)
                     atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
             }
             b = a + 1;
@@ -1098,7 +1104,7 @@ k_direct(DirectArgs A)
             u8 *win = wtext + (it - tsz - bt);
             u8 *dst = wout + (io - osz - bo);
             nutsb_lane_stage(win, src, n);
-            if (nutsb_render1(win + ((u32)(size_t)src & 3u), n, colour, dst, s_tab) != osz)
+            if (nutsb_render1(win + ((u32)(size_t)src & 3u), n, colour, oflags, dst, s_tab) != osz)
                 atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
             nutsb_lane_copy(A.out + p, dst, osz);
         }

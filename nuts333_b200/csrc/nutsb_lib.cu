@@ -874,6 +874,49 @@ NUTSB_API int nutsb_q_write_room(nutsb_ctx *c, int32_t room, const char *str, in
 { return nutsb_q_write_room_except(c, room, str, -1, force_listen, shout); }
 NUTSB_API int nutsb_q_write_level(nutsb_ctx *c, int level, int above, const char *str, int32_t except_user)
 { return q_push(c, NUTSB_OP_LEVEL, level, str, except_user, above ? NUTSB_OF_ABOVE : 0); }
+NUTSB_API int nutsb_q_page_line(nutsb_ctx *c, int32_t sock_user, const char *str, int plain)
+{ return q_push(c, NUTSB_OP_USER, sock_user, str, -1, (u8)(NUTSB_OF_PAGER | (plain ? NUTSB_OF_PLAIN : 0))); }
+
+// more(), nuts333.c:2205-2322, for a local user (the netlink branch, sock == -1, is out of scope).
+NUTSB_API int nutsb_q_more(nutsb_ctx *c, int32_t user, int32_t sock_user, const void *file, size_t n,
+                           int64_t *filepos, int *retval)
+{
+    if (!c || !filepos || !retval) return NUTSB_E_INVAL;
+    if (!file) { if (user >= 0) *filepos = 0; *retval = 0; return NUTSB_OK; }        // c:2214-2217
+    const u8 *f = (const u8 *)file;
+    size_t pos = 0;
+    if (user >= 0 && *filepos > 0) pos = (size_t)*filepos < n ? (size_t)*filepos : n;   // c:2219 fseek
+    bool eof = false;
+    std::string text;
+    // fgets(text, sizeof(text)-1, fp): at most 1998 bytes, stops after '\n'; feof is raised only
+    // when the read runs into the end of the file
+    auto fgets_ = [&]() {
+        size_t got = 0;
+        std::string line;
+        while (got < NUTSB_MAX_TEXT - 2) {
+            if (pos >= n) { eof = true; break; }
+            const u8 b = f[pos++]; line.push_back((char)b); ++got;
+            if (b == '\n') break;
+        }
+        if (got) text = line;                          // NULL return leaves text untouched
+    };
+    int lines = 0; int64_t num_chars = 0;
+    fgets_();
+    while (!eof && (lines < 23 || user < 0)) {         // c:2237
+        const size_t len = strlen(text.c_str());      // the chunk is used as a C string
+        TRY(nutsb_q_page_line(c, sock_user, text.c_str(), user < 0));
+        num_chars += (int64_t)len;
+        lines += (int)(len / 80) + (len < 80);        // c:2303
+        fgets_();
+    }
+    if (user < 0) { *retval = 2; return NUTSB_OK; }    // c:2309
+    if (eof) { *filepos = 0; *retval = 2; return NUTSB_OK; }
+    *filepos += num_chars;                             // c:2316
+    TRY(nutsb_q_write_user(c, user, "           ~BB*** Press <return> to continue, 'e'<return> to exit ***"));
+    *retval = 1;
+    return NUTSB_OK;
+}
+
 NUTSB_API int64_t nutsb_q_pending(const nutsb_ctx *c) { return c ? (int64_t)c->q_kind.size() : 0; }
 
 NUTSB_API int nutsb_flush(nutsb_ctx *c, nutsb_streams *out)

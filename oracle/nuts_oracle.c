@@ -49,7 +49,16 @@ static int orc_code_at(const uint8_t *s, size_t n, size_t j)
  * calls, so they do not appear here. */
 size_t orc_render(const uint8_t *s, size_t n, int colour, uint8_t *out)
 {
+    return orc_render_ex(s, n, colour, 0, out);
+}
+
+/* The same machine as run by write_user (c:1315-1365) and, with ORC_OF_PAGER, by the
+ * pager on one fgets() chunk of a file (c:2254-2300: identical loop, no reset after
+ * the string); ORC_OF_PLAIN = more(NULL,...): colour is `user!=NULL && user->colour`. */
+size_t orc_render_ex(const uint8_t *s, size_t n, int colour, unsigned oflags, uint8_t *out)
+{
     size_t i = 0, o = 0;
+    if (oflags & ORC_OF_PLAIN) colour = 0;
     while (i < n) {
         uint8_t c = s[i];
         if (c == '\n') {                               /* c:1316-1326 */
@@ -68,7 +77,7 @@ size_t orc_render(const uint8_t *s, size_t n, int colour, uint8_t *out)
             out[o++] = c; ++i;                         /* c:1355 */
         }
     }
-    if (colour) o += orc_ansi(0, out + o);             /* c:1365 */
+    if (colour && !(oflags & ORC_OF_PAGER)) o += orc_ansi(0, out + o);   /* c:1365 */
     return o;
 }
 
@@ -276,8 +285,8 @@ int orc_write_batch(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
                 if (!orc_delivers(kind[i], target[i], except_user[i], of[i], u, room[u], uf[u], ul[u]))
                     continue;
                 int c = (uf[u] & ORC_UF_COLOUR) != 0;
-                if (c && !have_on)  { lon  = orc_render(s, n, 1, ron);  have_on = 1; }
-                if (!c && !have_off){ loff = orc_render(s, n, 0, roff); have_off = 1; }
+                if (c && !have_on)  { lon  = orc_render_ex(s, n, 1, of[i], ron);  have_on = 1; }
+                if (!c && !have_off){ loff = orc_render_ex(s, n, 0, of[i], roff); have_off = 1; }
                 size_t len = c ? lon : loff;
                 if (pass == 0) { out->off[u + 1] += len; out->n_deliveries[u] += 1; }
                 else { memcpy(out->bytes + cur[u], c ? ron : roff, len); cur[u] += len; }
@@ -323,7 +332,7 @@ int64_t orc_write_batch_count(int64_t n_ops, const uint8_t *text, const uint64_t
         for (int32_t u = u0; u < u1; ++u) {
             if (!orc_delivers(kind[i], target[i], except_user[i], of[i], u, room[u], uf[u], ul[u]))
                 continue;
-            size_t len = orc_render(s, n, (uf[u] & ORC_UF_COLOUR) != 0, buf);
+            size_t len = orc_render_ex(s, n, (uf[u] & ORC_UF_COLOUR) != 0, of[i], buf);
             sink ^= buf[len ? len - 1 : 0];
             bytes += len; ++deliveries;
         }
@@ -352,4 +361,39 @@ void orc_user_banned_batch(const uint8_t *f, size_t fn, int present, int64_t n,
 {
     for (int64_t i = 0; i < n; ++i)
         verdict[i] = (uint8_t)orc_user_banned(f, fn, present, text + off[i], (size_t)(off[i + 1] - off[i]));
+}
+
+/* more(user, sock, filename), c:2205-2322, local recipient.  file/n = the file's bytes
+ * (present == 0: fopen failed).  Appends what the reference writes to the socket to out
+ * (capacity: 6*n + 256 is always enough), updates *filepos like user->filepos and
+ * returns more()'s return value.  user_null = the login-stage call more(NULL,sock,file). */
+int orc_more(const uint8_t *f, size_t n, int present, int user_null, int colour,
+             int64_t *filepos, uint8_t *out, size_t *out_len)
+{
+    static const char prompt[] = "           ~BB*** Press <return> to continue, 'e'<return> to exit ***";
+    size_t o = 0, pos = 0;
+    *out_len = 0;
+    if (!present) { if (!user_null) *filepos = 0; return 0; }            /* c:2214-2217 */
+    if (!user_null && *filepos > 0) pos = (size_t)*filepos < n ? (size_t)*filepos : n;   /* c:2219 */
+    uint8_t text[2000]; size_t tl = 0;         /* text[ARR_SIZE*2], fgets(text,1999,fp) */
+    int eof = 0, lines = 0; int64_t num_chars = 0;
+#define ORC_FGETS() do { size_t got = 0; uint8_t tmp[2000]; \
+        while (got < 1998) { if (pos >= n) { eof = 1; break; } tmp[got] = f[pos++]; if (tmp[got++] == '\n') break; } \
+        if (got) { memcpy(text, tmp, got); tl = got; } } while (0)
+    ORC_FGETS();
+    while (!eof && (lines < 23 || user_null)) {                          /* c:2237 */
+        size_t len = 0; while (len < tl && text[len]) ++len;             /* while(*str), strlen(text) */
+        o += orc_render_ex(text, len, colour, ORC_OF_PAGER | (user_null ? ORC_OF_PLAIN : 0), out + o);
+        num_chars += (int64_t)len;
+        lines += (int)(len / 80) + (len < 80);                           /* c:2303 */
+        ORC_FGETS();
+    }
+#undef ORC_FGETS
+    *out_len = o;
+    if (user_null) return 2;                                             /* c:2309 */
+    if (eof) { *filepos = 0; return 2; }                                 /* c:2310-2312 */
+    *filepos += num_chars;                                               /* c:2316 */
+    o += orc_render((const uint8_t *)prompt, sizeof prompt - 1, colour, out + o);   /* c:2321 write_user */
+    *out_len = o;
+    return 1;
 }

@@ -40,12 +40,15 @@ extern "C" {
 #define ORC_OF_SHOUT        0x02u /* com_num in {SHOUT,SEMOTE}       c:1414 */
 #define ORC_OF_ABOVE        0x04u /* write_level 'above' argument    c:1381 */
 #define ORC_OF_GATE_IF_SET  0x08u /* op is live iff gate verdict==1 (else ==0) */
+#define ORC_OF_PAGER        0x10u /* pager line: no reset after the string   c:2254-2300 */
+#define ORC_OF_PLAIN        0x20u /* colour taken as off: more(NULL,...)      c:2259      */
 
 /* ---- single-string primitives ------------------------------------------ */
 
 /* c:1291-1366 for a USER_TYPE recipient: returns bytes written to out.
  * out must hold 6*n+4 bytes. */
 size_t orc_render(const uint8_t *s, size_t n, int colour, uint8_t *out);
+size_t orc_render_ex(const uint8_t *s, size_t n, int colour, unsigned oflags, uint8_t *out);
 
 /* c:2540-2559 + c:2654-2658.  words = NULL-or-'*'-terminated list, exactly as
  * swear_words[] (h:275-277). */
@@ -110,6 +113,10 @@ void orc_site_banned_batch(const uint8_t *file, size_t fn, int present, int64_t 
                            const uint8_t *text, const uint64_t *off, uint8_t *verdict);
 void orc_user_banned_batch(const uint8_t *file, size_t fn, int present, int64_t n,
                            const uint8_t *text, const uint64_t *off, uint8_t *verdict);
+
+/* The pager, c:2205-2322 (see nuts_oracle.c). */
+int orc_more(const uint8_t *file, size_t n, int present, int user_null, int colour,
+             int64_t *filepos, uint8_t *out, size_t *out_len);
 
 /* 64-bit FNV-1a, the digest of SURVEY.md section 8(d). */
 uint64_t orc_fnv1a(const uint8_t *p, size_t n);

@@ -192,6 +192,14 @@ int ref_set_ban_file(const char *dir, int which, const void *data, size_t n)
 int ref_site_banned(const char *site) { return site_banned((char *)site); }
 int ref_user_banned(const char *name) { return user_banned((char *)name); }
 
+/* more(), c:2205: the reference's own pager on a file on disk, socket = the user's index */
+int ref_more(int u, int null_user, const char *filename)
+{
+    if (u < 0 || u >= g_nusers) return -1;
+    return more(null_user ? NULL : g_users[u], g_users[u]->socket, (char *)filename);
+}
+long ref_get_filepos(int u) { return (u >= 0 && u < g_nusers) ? (long)g_users[u]->filepos : -1; }
+
 /* ---- stream access ------------------------------------------------------- */
 
 size_t ref_stream_len(int u) { return (u >= 0 && u < g_nsink) ? g_sink[u].n : 0; }

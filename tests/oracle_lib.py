@@ -96,6 +96,9 @@ class Port:
         L.orc_contains_swearing_batch.argtypes = [C.c_int64, u8p, u64p, C.POINTER(C.c_char_p), u8p]
         L.orc_site_banned_batch.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int64, u8p, u64p, u8p]
         L.orc_user_banned_batch.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int64, u8p, u64p, u8p]
+        L.orc_more.restype = C.c_int
+        L.orc_more.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_char_p,
+                               C.POINTER(C.c_size_t)]
         L.orc_fnv1a.restype = C.c_uint64
         L.orc_fnv1a.argtypes = [C.c_char_p, C.c_size_t]
 
@@ -180,6 +183,14 @@ class Port:
         fn(file or b"", len(file or b""), int(file is not None), n, _ptr(text, u8p), _ptr(off, u64p), _ptr(v, u8p))
         return v[:n]
 
+    def more(self, data, user_null: bool, colour: int, filepos: int):
+        """-> (retval, bytes written to the socket, new filepos)"""
+        n = len(data or b"")
+        out = C.create_string_buffer(6 * n + 512)
+        pos, ol = C.c_int64(filepos), C.c_size_t(0)
+        rv = self.lib.orc_more(data or b"", n, int(data is not None), int(user_null), colour, C.byref(pos), out, C.byref(ol))
+        return rv, out.raw[:ol.value], pos.value
+
     def fnv1a(self, b: bytes) -> int:
         return self.lib.orc_fnv1a(b, len(b))
 
@@ -211,6 +222,8 @@ class Ref:
         L.ref_stream_calls.restype = C.c_uint64
         L.ref_total_write_calls.restype = C.c_uint64
         L.ref_total_write_bytes.restype = C.c_uint64
+        L.ref_more.argtypes = [C.c_int, C.c_int, C.c_char_p]
+        L.ref_get_filepos.restype = C.c_long
         L.ref_write_batch.restype = C.c_int64
         L.ref_write_batch.argtypes = [C.c_int64, u8p, u64p, u8p, i32p, i32p, u8p, i32p, u8p]
         L.ref_contains_swearing_batch.argtypes = [C.c_int64, u8p, u64p, u8p]
@@ -282,6 +295,11 @@ class Ref:
 
     def user_banned(self, name: bytes) -> int:
         return self._in_tmp(self.lib.ref_user_banned, name)
+
+    def more(self, u: int, null_user: bool, filename: str):
+        """the reference's pager on a file on disk -> (retval, user->filepos)"""
+        rv = self.lib.ref_more(u, int(null_user), filename.encode())
+        return rv, int(self.lib.ref_get_filepos(u))
 
     def write_batch(self, ops, n_rooms, users, verdict=None, sink_mode=0):
         self.reset(n_rooms, users, sink_mode)
