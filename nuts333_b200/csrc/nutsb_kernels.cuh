@@ -698,10 +698,10 @@ k_fanout(FanoutArgs A)
     __shared__ u32 s_evk[NUTSB_EV_CAP];          // the chunk's events inside this tile
     __shared__ i32 s_evd[NUTSB_EV_CAP];
     __shared__ u32 s_evn;
-    __shared__ u64 s_rdst[NUTSB_RUN_CAP];        // planned copy runs of the current (sub)tile
-    __shared__ u32 s_rsrc[NUTSB_RUN_CAP], s_rlen[NUTSB_RUN_CAP];
+    __shared__ uint4 s_run[NUTSB_RUN_CAP];       // planned copy runs of the current (sub)tile:
+                                                 // x,y = destination byte offset, z = slab offset | colour<<31, w = length
     __shared__ u8  s_ulegacy[NUTSB_UCHUNK];
-    __shared__ u32 s_nruns, s_next;
+    __shared__ u32 s_nruns;
     __shared__ u32 s_sub_b;
     __shared__ u32 s_room;
     __shared__ u32 s_deliv;
@@ -791,7 +791,7 @@ k_fanout(FanoutArgs A)
                 while (b < nb && s_toff[b + 1] - s_toff[a] <= NUTSB_TEXT_CAP &&
                        s_oon[b + 1] - s_oon[a] <= NUTSB_ON_CAP && s_ooff[b + 1] - s_ooff[a] <= NUTSB_OFF_CAP) ++b;
             }
-            s_sub_b = b; s_nruns = 0; s_next = 0;
+            s_sub_b = b; s_nruns = 0;
         }
         __syncthreads();
         const u32 b = s_sub_b;
@@ -851,9 +851,9 @@ k_fanout(FanoutArgs A)
                     if (xs < ye && offc[ye] != offc[xs]) {
                         const u32 r = atomicAdd(&s_nruns, 1u);
                         if (r < NUTSB_RUN_CAP) {
-                            s_rdst[r] = p + (offc[xs] - offc[cur]);
-                            s_rsrc[r] = (offc[xs] - offc[a]) | (colour ? 0x80000000u : 0u);
-                            s_rlen[r] = offc[ye] - offc[xs];
+                            const u64 d = p + (offc[xs] - offc[cur]);
+                            s_run[r] = make_uint4((u32)d, (u32)(d >> 32), (offc[xs] - offc[a]) | (colour ? 0x80000000u : 0u),
+                                                  offc[ye] - offc[xs]);
                             deliv += ye - xs;
                         } else legacy = true;              // queue full: this recipient goes the slow way
                     } else if (xs < ye) deliv += ye - xs;      // zero-length renderings still count as deliveries
@@ -881,9 +881,10 @@ k_fanout(FanoutArgs A)
             u8 *const s_stg0 = s_off + NUTSB_OFF_CAP + 64;
             u32 round = 0;
             for (u32 r = (u32)tid; r < nruns; r += NUTSB_FAN_THREADS) {
-                const u32 so = s_rsrc[r], len = s_rlen[r];
+                const uint4 run = s_run[r];
+                const u32 so = run.z, len = run.w;
                 const u8 *src = ((so >> 31) ? s_on : s_off) + (so & 0x7fffffffu);
-                u8 *dst = A.out + s_rdst[r];
+                u8 *dst = A.out + (((u64)run.y << 32) | run.x);
                 u32 head = (u32)((16 - ((size_t)dst & 15)) & 15);
                 if (head > len) head = len;
                 for (u32 q = 0; q < head; ++q) dst[q] = src[q];
@@ -915,10 +916,11 @@ k_fanout(FanoutArgs A)
                     __syncthreads();
                     // (3) bodies: one bulk store per (run, piece)
                     for (u32 q = (u32)tid; q < nruns; q += NUTSB_FAN_THREADS) {
-                        const u32 so = s_rsrc[q];
+                        const uint4 run = s_run[q];
+                        const u32 so = run.z;
                         if ((int)(so >> 31) != colour) continue;
-                        const u32 S = so & 0x7fffffffu, len = s_rlen[q];
-                        const u64 D = s_rdst[q];
+                        const u32 S = so & 0x7fffffffu, len = run.w;
+                        const u64 D = ((u64)run.y << 32) | run.x;
                         u32 head = (u32)((16 - (((size_t)A.out + D) & 15)) & 15);
                         if (head > len) head = len;
                         const u32 nvec = (len - head) >> 4;
@@ -942,16 +944,14 @@ k_fanout(FanoutArgs A)
             __syncthreads();
         }
 #else
-        // -- copy: warps pull planned runs; a run is one contiguous piece of a recipient's stream
+        // -- copy: a run is one contiguous piece of a recipient's stream; warps take runs in turn
         {
             const u32 nruns = s_nruns < NUTSB_RUN_CAP ? s_nruns : NUTSB_RUN_CAP;
-            for (;;) {
-                u32 r = 0;
-                if (lane == 0) r = atomicAdd(&s_next, 1u);
-                r = __shfl_sync(NUTSB_FULL, r, 0);
-                if (r >= nruns) break;
-                const u32 so = s_rsrc[r];
-                nutsb_warp_copy(A.out + s_rdst[r], ((so >> 31) ? s_on : s_off) + (so & 0x7fffffffu), s_rlen[r], lane);
+            for (u32 r = (u32)warp; r < nruns; r += NUTSB_FAN_THREADS / 32) {
+                const uint4 run = s_run[r];
+                // the colour-off slab follows the colour-on one in the dynamic window
+                const u32 so = (run.z & 0x7fffffffu) + ((run.z >> 31) ? 0u : (u32)(NUTSB_ON_CAP + 64));
+                nutsb_warp_copy(A.out + (((u64)run.y << 32) | run.x), s_on + so, run.w, lane);
             }
         }
 #endif
