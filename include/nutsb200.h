@@ -71,6 +71,7 @@ enum {
 #define NUTSB_OP_USER  0  /* write_user(target, str)                                   */
 #define NUTSB_OP_ROOM  1  /* write_room_except(target, str, except); target -1 = NULL  */
 #define NUTSB_OP_LEVEL 2  /* write_level(target, above, str, except)                   */
+#define NUTSB_OP_NONE  3  /* no call: a branch of a caller that was not taken           */
 
 /* op flags: the globals the reference reads inside the call */
 #define NUTSB_OF_FORCE_LISTEN 0x01u  /* force_listen (nuts333.h:293, c:1413)           */
@@ -177,6 +178,36 @@ int nutsb_user_banned_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes,
                             const uint64_t *off, uint8_t *verdict);
 int nutsb_user_banned_batch_dev(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes,
                                 const uint64_t *off, uint8_t *verdict);
+
+/* ---- the callers' composition: say / shout / emote / semote / echo / bcast ------------- */
+/* What one input line becomes (nuts333.c:4062-4126, 4188-4232, 4289-4305, 4772-4788):
+ * up to three write calls per line -- the refusal ("You are muzzled ...", or noswearing when
+ * ban_swearing is on and the body swears), the speaker's own copy, the line to the room(s).
+ * The caller-level checks (word_count, command_mode) stay with the caller. */
+#define NUTSB_SPEECH_SAY    0   /* say(user,inpstr)     c:4062 */
+#define NUTSB_SPEECH_SHOUT  1   /* shout(user,inpstr)   c:4105 */
+#define NUTSB_SPEECH_EMOTE  2   /* emote(user,inpstr)   c:4188 */
+#define NUTSB_SPEECH_SEMOTE 3   /* semote(user,inpstr)  c:4213 */
+#define NUTSB_SPEECH_ECHO   4   /* echo(user,inpstr)    c:4289 */
+#define NUTSB_SPEECH_BCAST  5   /* bcast(user,inpstr)   c:4772 */
+#define NUTSB_SF_INVIS   0x01u  /* user->vis == 0: others see invisname (nuts333.h:150) */
+#define NUTSB_SF_MUZZLED 0x02u  /* user->muzzled                                        */
+
+/* user->name, user->vis, user->muzzled of every user (names packed, off[n_users+1]). */
+int nutsb_set_user_names(nutsb_ctx *ctx, int32_t n_users, const uint8_t *names, const uint64_t *off,
+                         const uint8_t *speech_flags);
+/* the global ban_swearing (nuts333.h:296, config option c:803-808); default off as in init_globals */
+int nutsb_set_ban_swearing(nutsb_ctx *ctx, int on);
+/* n input lines: verb[n], speaker[n] (user index), bodies packed + off[n+1].  The device
+ * runs contains_swearing on the bodies, composes the calls and renders them; streams as
+ * for nutsb_write_batch.  *_dev: every pointer is a device pointer, streams stay in HBM. */
+int nutsb_speech_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *verb, const int32_t *speaker,
+                       const uint8_t *bodies, const uint64_t *body_off, nutsb_streams *out);
+int nutsb_speech_batch_dev(nutsb_ctx *ctx, int64_t n, const uint8_t *verb, const int32_t *speaker,
+                           const uint8_t *bodies, const uint64_t *body_off, nutsb_streams *out);
+/* queue tier: one call of the reference's say()/shout()/... ; composed on the host, the swear
+ * verdicts of the queued lines are taken in one device batch at nutsb_flush */
+int nutsb_q_speech(nutsb_ctx *ctx, int verb, int32_t user, const char *inpstr);
 
 /* Position-weighted 64-bit digest of every user's stream, computed on the
  * device from the last write batch: h = fold(h*0x100000001b3 + byte) over the

@@ -26,6 +26,9 @@ MAX_TEXT = 2000
 
 # com_num values that matter on the path (enum comvals, nuts333.h:181-183)
 SAY, SHOUT, SEMOTE = 3, 4, 7
+# speech verbs of the composer (nutsb200.h) and per-user speech flags
+SPEECH_SAY, SPEECH_SHOUT, SPEECH_EMOTE, SPEECH_SEMOTE, SPEECH_ECHO, SPEECH_BCAST = range(6)
+SF_INVIS, SF_MUZZLED = 1, 2
 # user levels (nuts333.h: level_name[])
 NEW, USER, WIZ, ARCH, GOD = 0, 1, 2, 3, 4
 
@@ -66,6 +69,7 @@ EXPORTS = [
     "nutsb_set_ban_files", "nutsb_set_users", "nutsb_write_batch", "nutsb_write_batch_dev",
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
+    "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_q_speech",
     "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
     "nutsb_q_write_level", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_contains_swearing",
     "nutsb_site_banned", "nutsb_user_banned",
@@ -99,6 +103,11 @@ def bind(lib: C.CDLL) -> C.CDLL:
         getattr(lib, f"nutsb_{name}_batch").argtypes = [vp, C.c_int64, vp, vp, vp]
         getattr(lib, f"nutsb_{name}_batch_dev").argtypes = [vp, C.c_int64, vp, vp, vp]
         getattr(lib, f"nutsb_{name}").argtypes = [vp, C.c_char_p]
+    lib.nutsb_set_user_names.argtypes = [vp, C.c_int32, vp, vp, vp]
+    lib.nutsb_set_ban_swearing.argtypes = [vp, C.c_int]
+    lib.nutsb_speech_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
+    lib.nutsb_speech_batch_dev.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
+    lib.nutsb_q_speech.argtypes = [vp, C.c_int, C.c_int32, C.c_char_p]
     lib.nutsb_stream_digests.argtypes = [vp, u64p]
     lib.nutsb_q_write_user.argtypes = [vp, C.c_int32, C.c_char_p]
     lib.nutsb_q_write_room.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int, C.c_int]
@@ -206,6 +215,24 @@ class Context:
         self._ck(self.lib.nutsb_set_users(self._h, len(room), n_rooms, room.ctypes.data_as(i32p),
                                           flags.ctypes.data_as(u8p), level.ctypes.data_as(u8p)))
         self.n_users = len(room)
+
+    def set_user_names(self, names, speech_flags):
+        """names: list[bytes] (user->name); speech_flags: SF_INVIS | SF_MUZZLED per user"""
+        data, off = pack([n if isinstance(n, bytes) else n.encode() for n in names])
+        fl = _np(speech_flags, np.uint8)
+        self._ck(self.lib.nutsb_set_user_names(self._h, len(names), _addr(data) if data.size else None, _addr(off), _addr(fl)))
+
+    def set_ban_swearing(self, on: bool):
+        self._ck(self.lib.nutsb_set_ban_swearing(self._h, 1 if on else 0))
+
+    def speech_batch(self, verb, speaker, bodies, body_off) -> "Streams":
+        """say/shout/emote/semote/echo/bcast lines composed and rendered on the device."""
+        verb, speaker = _np(verb, np.uint8), _np(speaker, np.int32)
+        bodies, body_off = _np(bodies, np.uint8), _np(body_off, np.uint64)
+        st = _Streams()
+        self._ck(self.lib.nutsb_speech_batch(self._h, len(verb), _addr(verb), _addr(speaker),
+                                             _addr(bodies) if bodies.size else None, _addr(body_off), C.byref(st)))
+        return self._host_streams(st)
 
     def set_profiling(self, on=True):
         self._ck(self.lib.nutsb_set_profiling(self._h, 1 if on else 0))
@@ -320,6 +347,28 @@ class Talker:
     def write_level(self, level, above, s, user):                    # c:1372
         c = self.ctx
         c._ck(c.lib.nutsb_q_write_level(c._h, level, 1 if above else 0, self._s(s), -1 if user is None else user))
+
+    def _speech(self, verb, user, inpstr):
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_speech(c._h, verb, user, self._s(inpstr)))
+
+    def say(self, user, inpstr):                                     # c:4062
+        self._speech(SPEECH_SAY, user, inpstr)
+
+    def shout(self, user, inpstr):                                   # c:4105
+        self._speech(SPEECH_SHOUT, user, inpstr)
+
+    def emote(self, user, inpstr):                                   # c:4188
+        self._speech(SPEECH_EMOTE, user, inpstr)
+
+    def semote(self, user, inpstr):                                  # c:4213
+        self._speech(SPEECH_SEMOTE, user, inpstr)
+
+    def echo(self, user, inpstr):                                    # c:4289
+        self._speech(SPEECH_ECHO, user, inpstr)
+
+    def bcast(self, user, inpstr):                                   # c:4772
+        self._speech(SPEECH_BCAST, user, inpstr)
 
     def more(self, user, sock, filename) -> int:                    # c:2205
         """The pager: queues one page of `filename` for the user on socket `sock` (a user

@@ -192,8 +192,8 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
         else rep = tgt >= 0 ? 1u : (u32)pop.n_rooms;
     } else if (kind == NUTSB_OP_LEVEL) {
         rep = (u32)pop.n_rooms_tot; st |= NUTSB_ST_HAS_LEVEL;
-    } else st |= NUTSB_ST_BAD_KIND;
-    if (exc >= pop.n_users || exc < -1) st |= NUTSB_ST_BAD_INDEX;
+    } else if (kind != NUTSB_OP_NONE) st |= NUTSB_ST_BAD_KIND;
+    if (kind != NUTSB_OP_NONE && (exc >= pop.n_users || exc < -1)) st |= NUTSB_ST_BAD_INDEX;
     if (st & ~NUTSB_ST_HAS_LEVEL) rep = 0;
     nrep[i] = live ? rep : 0;
     if (st) atomicOr(status, st);

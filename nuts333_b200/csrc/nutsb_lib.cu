@@ -6,6 +6,7 @@
 // with NUTSB_E_CUDA when no device is usable.
 #include "nutsb_kernels.cuh"
 #include "nutsb_match.cuh"
+#include "nutsb_speech.cuh"
 
 #define NUTSB_API extern "C" __attribute__((visibility("default")))
 
@@ -80,9 +81,18 @@ struct nutsb_ctx {
     // staging for the host-buffer entry points
     DBuf s_text, s_toff, s_kind, s_target, s_except, s_flags, s_gate, s_verdict, s_v8;
 
+    // speech: user names / flags, the callers' literals
+    bool have_names = false; bool ban_swearing = false;
+    std::vector<u8> names, sflags; std::vector<u64> name_off;
+    std::vector<std::string> lits;
+    DBuf d_names, d_name_off, d_sflags, d_lit, d_lit_off;
+    DBuf d_sp_len, d_sp_off, d_sp_text, d_sp_kind, d_sp_target, d_sp_except, d_sp_flags, d_sp_gate, d_sp_verdict;
+    DBuf s_verb, s_speaker, s_body, s_boff;
+
     // queue tier
     std::vector<u8> q_text; std::vector<u64> q_off{0}; std::vector<u8> q_kind, q_flags;
-    std::vector<i32> q_target, q_except;
+    std::vector<i32> q_target, q_except, q_gate;
+    std::vector<u8> q_sw_text; std::vector<u64> q_sw_off{0};     // bodies whose swear verdict gates queued ops
 };
 
 static int fail(nutsb_ctx *c, int code, const char *fmt, const char *a = "")
@@ -327,7 +337,10 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
         &c->d_sv_delta, &c->d_sv_op, &c->d_sv_pre, &c->d_ev_off, &c->d_vp_on, &c->d_vp_off, &c->d_cp,
         &c->d_room_tile_off, &c->d_room_cell_off, &c->d_room_item_off, &c->d_sizes, &c->d_counters,
         &c->d_cell_pos, &c->d_cell_evi, &c->d_off, &c->d_out, &c->d_digest, &c->d_ulen,
-        &c->s_text, &c->s_toff, &c->s_kind, &c->s_target, &c->s_except, &c->s_flags, &c->s_gate, &c->s_verdict, &c->s_v8 };
+        &c->s_text, &c->s_toff, &c->s_kind, &c->s_target, &c->s_except, &c->s_flags, &c->s_gate, &c->s_verdict, &c->s_v8,
+        &c->d_names, &c->d_name_off, &c->d_sflags, &c->d_lit, &c->d_lit_off, &c->d_sp_len, &c->d_sp_off, &c->d_sp_text,
+        &c->d_sp_kind, &c->d_sp_target, &c->d_sp_except, &c->d_sp_flags, &c->d_sp_gate, &c->d_sp_verdict,
+        &c->s_verb, &c->s_speaker, &c->s_body, &c->s_boff };
     for (DBuf *b : all) release(*b);
     release(c->h_small); release(c->h_off); release(c->h_out);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -363,6 +376,17 @@ NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
         TRY(ensure(c, c->d_status, 64)); TRY(ensure(c, c->d_counts, 64)); TRY(ensure(c, c->d_sizes, sizeof(Sizes)));
         TRY(ensure(c, c->d_counters, 64));
         TRY(ensure_host(c, c->h_small, 4096));
+        {   // the callers' literals (nutsb_speech.cuh)
+            c->lits.assign(NUTSB_NLIT, std::string());
+#define NUTSB_LIT_X(id, text) c->lits[id] = std::string(text, sizeof(text) - 1);
+            NUTSB_SPEECH_LITERALS(NUTSB_LIT_X)
+#undef NUTSB_LIT_X
+            std::vector<u8> bytes; std::vector<u32> off(NUTSB_NLIT + 1, 0);
+            for (int i = 0; i < NUTSB_NLIT; ++i) { bytes.insert(bytes.end(), c->lits[i].begin(), c->lits[i].end()); off[i + 1] = (u32)bytes.size(); }
+            TRY(upload(c, c->d_lit, bytes.data(), bytes.size()));
+            TRY(upload(c, c->d_lit_off, off.data(), off.size() * 4));
+            CK(cudaStreamSynchronize(c->stream));
+        }
         static const char *stock[] = { "fuck", "shit", "cunt", "*" };      // nuts333.h:275-277
         TRY(set_swear_impl(c, stock));
         CK(cudaStreamSynchronize(c->stream));
@@ -865,6 +889,7 @@ static int q_push(nutsb_ctx *c, u8 kind, i32 target, const char *str, i32 except
     c->q_text.insert(c->q_text.end(), (const u8 *)str, (const u8 *)str + n);   // copied: callers reuse text[] at once
     c->q_off.push_back((u64)c->q_text.size());
     c->q_kind.push_back(kind); c->q_target.push_back(target); c->q_except.push_back(except_user); c->q_flags.push_back(flags);
+    c->q_gate.push_back(-1);
     return NUTSB_OK;
 }
 NUTSB_API int nutsb_q_write_user(nutsb_ctx *c, int32_t user, const char *str) { return q_push(c, NUTSB_OP_USER, user, str, -1, 0); }
@@ -927,7 +952,148 @@ NUTSB_API int nutsb_flush(nutsb_ctx *c, nutsb_streams *out)
     static const u8 zero = 0;
     o.text = c->q_text.empty() ? &zero : c->q_text.data(); o.text_off = c->q_off.data();
     o.kind = c->q_kind.data(); o.target = c->q_target.data(); o.except_user = c->q_except.data(); o.flags = c->q_flags.data();
-    const int rc = nutsb_write_batch(c, &o, out);
+    std::vector<u8> verdict;
+    int rc = NUTSB_OK;
+    const i64 n_sw = (i64)c->q_sw_off.size() - 1;
+    if (n_sw > 0) {        // the swear verdicts the queued say/shout/emote lines branch on: one device batch
+        verdict.assign((size_t)n_sw, 0);
+        rc = nutsb_contains_swearing_batch(c, n_sw, c->q_sw_text.empty() ? &zero : c->q_sw_text.data(), c->q_sw_off.data(), verdict.data());
+        o.gate = c->q_gate.data(); o.verdict = verdict.data();
+    }
+    if (rc == NUTSB_OK) rc = nutsb_write_batch(c, &o, out);
     c->q_text.clear(); c->q_off.assign(1, 0); c->q_kind.clear(); c->q_target.clear(); c->q_except.clear(); c->q_flags.clear();
+    c->q_gate.clear(); c->q_sw_text.clear(); c->q_sw_off.assign(1, 0);
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------
+// the callers' composition
+// ---------------------------------------------------------------------------------------
+NUTSB_API int nutsb_set_user_names(nutsb_ctx *c, int32_t n_users, const uint8_t *names, const uint64_t *off, const uint8_t *sflags)
+{
+    if (!c || n_users < 0 || (n_users && (!off || !sflags))) return fail(c, NUTSB_E_INVAL, "nutsb_set_user_names: bad argument%s");
+    CK(cudaSetDevice(c->device));
+    for (i32 u = 0; u < n_users; ++u) if (off[u + 1] < off[u]) return fail(c, NUTSB_E_INVAL, "name offsets are not monotone%s");
+    const u64 t0 = n_users ? off[0] : 0, t1 = n_users ? off[n_users] : 0;
+    if (t1 > t0 && !names) return fail(c, NUTSB_E_INVAL, "names is NULL%s");
+    c->names.assign(names ? names + t0 : nullptr, names ? names + t1 : nullptr);
+    c->name_off.assign((size_t)n_users + 1, 0);
+    for (i32 u = 0; u <= n_users; ++u) c->name_off[u] = n_users ? off[u] - t0 : 0;
+    c->sflags.assign(sflags, sflags + n_users);
+    TRY(upload(c, c->d_names, c->names.data(), c->names.size()));
+    TRY(upload(c, c->d_name_off, c->name_off.data(), c->name_off.size() * 8));
+    TRY(upload(c, c->d_sflags, c->sflags.data(), c->sflags.size()));
+    CK(cudaStreamSynchronize(c->stream));
+    c->have_names = true;
+    return NUTSB_OK;
+}
+
+NUTSB_API int nutsb_set_ban_swearing(nutsb_ctx *c, int on) { if (!c) return NUTSB_E_INVAL; c->ban_swearing = on != 0; return NUTSB_OK; }
+
+static int speech_ready(nutsb_ctx *c)
+{
+    if (!c->have_users) return fail(c, NUTSB_E_STATE, "nutsb_set_users has not been called%s");
+    if (!c->have_names || (i32)c->sflags.size() != c->U) return fail(c, NUTSB_E_STATE, "nutsb_set_user_names does not match the population%s");
+    return NUTSB_OK;
+}
+
+// queue tier: composed on the host with the same rules the device composer uses
+NUTSB_API int nutsb_q_speech(nutsb_ctx *c, int verb, int32_t user, const char *inpstr)
+{
+    if (!c || !inpstr) return NUTSB_E_INVAL;
+    TRY(speech_ready(c));
+    if (verb < 0 || verb >= NUTSB_SPEECH_VERBS) return fail(c, NUTSB_E_INVAL, "unknown speech verb%s");
+    if (user < 0 || user >= c->U) return fail(c, NUTSB_E_RANGE, "user index out of range%s");
+    const size_t blen = strlen(inpstr);
+    const u8 first = blen ? (u8)inpstr[0] : 0, last = blen ? (u8)inpstr[blen - 1] : 0;
+    const i32 room = c->user_room[user] < c->R ? c->user_room[user] : -1;
+    i32 gate = -1;
+    for (u32 sidx = 0; sidx < 3; ++sidx) {
+        const SpeechSlot sl = nutsb_speech_slot((u32)verb, sidx, user, room, c->sflags[user], c->ban_swearing, first, last);
+        if (sl.kind == NUTSB_OP_NONE) continue;
+        std::string text = c->lits[sl.a];
+        if (sl.name == 2 || (sl.name == 1 && !(c->sflags[user] & NUTSB_SF_INVIS)))
+            text.append((const char *)c->names.data() + c->name_off[user], (size_t)(c->name_off[user + 1] - c->name_off[user]));
+        else if (sl.name == 1) text += c->lits[NUTSB_LIT_INVISNAME];
+        text += c->lits[sl.b];
+        if (sl.body == 1) text.append(inpstr, blen); else if (sl.body == 2 && blen) text.append(inpstr + 1, blen - 1);
+        text += c->lits[sl.c];
+        TRY(q_push(c, sl.kind, sl.target, text.c_str(), sl.except_user, sl.flags));
+        if (sl.gated) {
+            if (gate < 0) {            // the line's body joins the swear batch run at flush
+                gate = (i32)c->q_sw_off.size() - 1;
+                c->q_sw_text.insert(c->q_sw_text.end(), (const u8 *)inpstr, (const u8 *)inpstr + blen);
+                c->q_sw_off.push_back((u64)c->q_sw_text.size());
+            }
+            c->q_gate.back() = gate;
+        }
+    }
+    return NUTSB_OK;
+}
+
+static int run_speech(nutsb_ctx *c, i64 n, const u8 *verb, const i32 *speaker, const u8 *bodies, const u64 *body_off, nutsb_streams *out)
+{
+    TRY(speech_ready(c));
+    cudaStream_t st = c->stream;
+    if (n == 0) { nutsb_ops o{}; return run_write(c, &o, out); }
+    SpeechView v{ n, verb, speaker, bodies, body_off, c->d_names.as<u8>(), c->d_name_off.as<u64>(), c->d_sflags.as<u8>(),
+                  c->d_user_room.as<i32>(), c->d_lit.as<u8>(), c->d_lit_off.as<u32>(), c->U, c->R, c->ban_swearing ? 1u : 0u };
+    const size_t n3 = (size_t)n * 3;
+    TRY(ensure(c, c->d_sp_len, n3 * 4)); TRY(ensure(c, c->d_sp_off, (n3 + 1) * 8));
+    TRY(ensure(c, c->d_sp_kind, n3)); TRY(ensure(c, c->d_sp_flags, n3));
+    TRY(ensure(c, c->d_sp_target, n3 * 4)); TRY(ensure(c, c->d_sp_except, n3 * 4)); TRY(ensure(c, c->d_sp_gate, n3 * 4));
+    TRY(ensure(c, c->d_sp_verdict, (size_t)n));
+    CK(cudaMemsetAsync(c->d_status.p, 0, 64, st));
+    NUTSB_LAUNCH(cdiv(n, 256), 256, st, k_speech_measure, v, c->d_sp_len.as<u32>(), c->d_status.as<u32>()); CKL();
+    TRY(run_scan(c, InU32{c->d_sp_len.as<u32>()}, OutU64{c->d_sp_off.as<u64>()}, (i64)n3, nullptr));
+    u64 *h64 = c->h_small.as<u64>(); u32 *h32 = c->h_small.as<u32>();
+    CK(cudaMemcpyAsync(h64, c->d_sp_off.as<u64>() + n3, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    TRY(status_to_error(c, h32[4]));
+    const u64 text_bytes = h64[0];
+    TRY(ensure(c, c->d_sp_text, text_bytes + 64));
+    NUTSB_LAUNCH(cdiv((u64)n * 32, 256), 256, st, k_speech_compose, v, c->d_sp_off.as<u64>(), c->d_sp_text.as<u8>(),
+                 c->d_sp_kind.as<u8>(), c->d_sp_target.as<i32>(), c->d_sp_except.as<i32>(), c->d_sp_flags.as<u8>(), c->d_sp_gate.as<i32>()); CKL();
+    TRY(verdict_dev(c, V_SWEAR, n, bodies, body_off, c->d_sp_verdict.as<u8>()));
+    nutsb_ops o{ (i64)n3, c->d_sp_text.as<u8>(), c->d_sp_off.as<u64>(), c->d_sp_kind.as<u8>(), c->d_sp_target.as<i32>(),
+                 c->d_sp_except.as<i32>(), c->d_sp_flags.as<u8>(), c->d_sp_gate.as<i32>(), c->d_sp_verdict.as<u8>() };
+    return run_write(c, &o, out);
+}
+
+NUTSB_API int nutsb_speech_batch_dev(nutsb_ctx *c, int64_t n, const uint8_t *verb, const int32_t *speaker,
+                                     const uint8_t *bodies, const uint64_t *body_off, nutsb_streams *out)
+{
+    if (!c || !out || n < 0 || (n && (!verb || !speaker || !body_off))) return fail(c, NUTSB_E_INVAL, "bad argument%s");
+    CK(cudaSetDevice(c->device));
+    return run_speech(c, n, verb, speaker, bodies, body_off, out);
+}
+
+NUTSB_API int nutsb_speech_batch(nutsb_ctx *c, int64_t n, const uint8_t *verb, const int32_t *speaker,
+                                 const uint8_t *bodies, const uint64_t *body_off, nutsb_streams *out)
+{
+    if (!c || !out || n < 0 || (n && (!verb || !speaker || !body_off))) return fail(c, NUTSB_E_INVAL, "bad argument%s");
+    CK(cudaSetDevice(c->device));
+    const u8 *dv = nullptr; const i32 *ds = nullptr; const u8 *db = nullptr; const u64 *dbo = nullptr;
+    if (n > 0) {
+        const u64 t0 = body_off[0], t1 = body_off[n];
+        if (t1 < t0 || (t1 > t0 && !bodies)) return fail(c, NUTSB_E_INVAL, "bad body offsets%s");
+        for (i64 i = 0; i < n; ++i) if (body_off[i + 1] < body_off[i]) return fail(c, NUTSB_E_INVAL, "body offsets are not monotone%s");
+        TRY(ensure(c, c->s_body, (size_t)(t1 - t0) + 64));
+        if (t1 > t0) CK(cudaMemcpyAsync(c->s_body.p, bodies + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, c->stream));
+        TRY(upload(c, c->s_boff, body_off, ((size_t)n + 1) * 8));
+        TRY(upload(c, c->s_verb, verb, (size_t)n));
+        TRY(upload(c, c->s_speaker, speaker, (size_t)n * 4));
+        dv = c->s_verb.as<u8>(); ds = c->s_speaker.as<i32>(); db = c->s_body.as<u8>() - t0; dbo = c->s_boff.as<u64>();
+    }
+    nutsb_streams ds_{};
+    TRY(run_speech(c, n, dv, ds, db, dbo, &ds_));
+    TRY(ensure_host(c, c->h_off, ((size_t)c->U + 1) * 8));
+    TRY(ensure_host(c, c->h_out, (size_t)ds_.total_bytes + 16));
+    CK(cudaMemcpyAsync(c->h_off.p, ds_.off, ((size_t)c->U + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (ds_.total_bytes) CK(cudaMemcpyAsync(c->h_out.p, ds_.bytes, (size_t)ds_.total_bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *out = ds_;
+    out->off = c->h_off.as<u64>(); out->bytes = c->h_out.as<u8>(); out->on_device = 0;
+    return NUTSB_OK;
 }

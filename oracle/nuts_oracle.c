@@ -397,3 +397,106 @@ int orc_more(const uint8_t *f, size_t n, int present, int user_null, int colour,
     *out_len = o;
     return 1;
 }
+
+/* ---- the callers: say / shout / emote / semote / echo / bcast ---------------------------
+ * Restated call by call from nuts333.c; each appends the write calls the reference makes
+ * to an op list (orc_speech_emit).  user_name = user->name, vis/muzzled = the user's
+ * fields, room = the user's room index or -1, ban_swearing = the global. */
+#include <stdio.h>
+typedef struct {
+    uint8_t *text; size_t text_len, text_cap;
+    uint64_t *off; uint8_t *kind; int32_t *target; int32_t *except_user; uint8_t *flags;
+    int64_t n, cap;
+} orc_oplist;
+
+static void orc_emit(orc_oplist *L, uint8_t kind, int32_t target, int32_t exc, uint8_t flags, const char *str, size_t n)
+{
+    if (L->n >= L->cap || L->text_len + n > L->text_cap) { L->n = L->cap + 1; return; }   /* overflow marker */
+    memcpy(L->text + L->text_len, str, n); L->text_len += n;
+    L->kind[L->n] = kind; L->target[L->n] = target; L->except_user[L->n] = exc; L->flags[L->n] = flags;
+    L->off[++L->n] = L->text_len;
+}
+
+static const char orc_noswearing[] = "Swearing is not allowed here.\n";      /* h:151 */
+static const char orc_invisname[] = "A presence";                            /* h:150 */
+
+/* verbs: 0 say c:4062, 1 shout c:4105, 2 emote c:4188, 3 semote c:4213, 4 echo c:4289, 5 bcast c:4772 */
+static void orc_speech_one(orc_oplist *L, int verb, int32_t user, const char *uname, int vis, int muzzled, int32_t room,
+                           int ban_swearing, const char *const *words, const uint8_t *in, size_t n)
+{
+    char text[4200]; int len;
+    const char *name = vis ? uname : orc_invisname;
+    const int sw = ban_swearing && orc_contains_swearing(in, n, words);
+    switch (verb) {
+    case 0: {
+        const char *type = "say";
+        if (muzzled) { const char *m = "You are muzzled, you cannot speak.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
+        if (room < 0) return;                                   /* c:4071: relayed over the netlink */
+        if (n && in[n - 1] == '?') type = "ask"; else if (n && in[n - 1] == '!') type = "exclaim";   /* c:4080 */
+        if (sw) { orc_emit(L, 0, user, -1, 0, orc_noswearing, sizeof orc_noswearing - 1); return; }   /* c:4091 */
+        len = snprintf(text, sizeof text, "You %s: %.*s\n", type, (int)n, (const char *)in);
+        orc_emit(L, 0, user, -1, 0, text, (size_t)len);                              /* c:4095 */
+        len = snprintf(text, sizeof text, "%s %ss: %.*s\n", name, type, (int)n, (const char *)in);
+        orc_emit(L, 1, room, user, 0, text, (size_t)len);                            /* c:4098 */
+        return; }
+    case 1:
+        if (muzzled) { const char *m = "You are muzzled, you cannot shout.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
+        if (sw) { orc_emit(L, 0, user, -1, 0, orc_noswearing, sizeof orc_noswearing - 1); return; }
+        len = snprintf(text, sizeof text, "~OLYou shout:~RS %.*s\n", (int)n, (const char *)in);
+        orc_emit(L, 0, user, -1, 0, text, (size_t)len);
+        len = snprintf(text, sizeof text, "~OL%s shouts:~RS %.*s\n", name, (int)n, (const char *)in);
+        orc_emit(L, 1, -1, user, ORC_OF_SHOUT, text, (size_t)len);                   /* c:4125, com_num==SHOUT */
+        return;
+    case 2:
+        if (muzzled) { const char *m = "You are muzzled, you cannot emote.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
+        if (room < 0) return;                                   /* not reached for users in no room (record(NULL)) */
+        if (sw) { orc_emit(L, 0, user, -1, 0, orc_noswearing, sizeof orc_noswearing - 1); return; }
+        if (n && in[0] == ';') len = snprintf(text, sizeof text, "%s%.*s\n", name, (int)(n - 1), (const char *)in + 1);
+        else len = snprintf(text, sizeof text, "%s %.*s\n", name, (int)n, (const char *)in);
+        orc_emit(L, 1, room, -1, 0, text, (size_t)len);                              /* c:4208 write_room(user->room) */
+        return;
+    case 3:
+        if (muzzled) { const char *m = "You are muzzled, you cannot emote.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
+        if (n && in[0] == '#') len = snprintf(text, sizeof text, "~OL!!~RS %s%.*s\n", name, (int)(n - 1), (const char *)in + 1);
+        else len = snprintf(text, sizeof text, "~OL!!~RS %s %.*s\n", name, (int)n, (const char *)in);
+        orc_emit(L, 1, -1, -1, ORC_OF_SHOUT, text, (size_t)len);                     /* c:4231, com_num==SEMOTE */
+        return;
+    case 4:
+        if (muzzled) { const char *m = "You are muzzled, you cannot echo.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
+        if (room < 0) return;                                   /* as emote */
+        len = snprintf(text, sizeof text, "(%s) ", uname);
+        orc_emit(L, 2, 2 /* WIZ */, -1, ORC_OF_ABOVE, text, (size_t)len);            /* c:4301 write_level(WIZ,1,text,NULL) */
+        len = snprintf(text, sizeof text, "- %.*s\n", (int)n, (const char *)in);
+        orc_emit(L, 1, room, -1, 0, text, (size_t)len);                              /* c:4303 */
+        return;
+    case 5:
+        if (muzzled) { const char *m = "You are muzzled, you cannot broadcast anything.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
+        if (vis) len = snprintf(text, sizeof text, "\07\n~BR*** Broadcast message from %s ***\n%.*s\n\n", uname, (int)n, (const char *)in);
+        else len = snprintf(text, sizeof text, "\07\n~BR*** Broadcast message ***\n%.*s\n\n", (int)n, (const char *)in);
+        orc_emit(L, 1, -1, -1, ORC_OF_FORCE_LISTEN, text, (size_t)len);              /* c:4783-4787 */
+        return;
+    }
+}
+
+/* n input lines -> the ops the reference's callers make, in order.  names = packed user
+ * names with name_off[n_users+1]; sflags bit0 invisible, bit1 muzzled; room[u] or -1.
+ * Arrays sized for cap ops / text_cap bytes.  Returns the number of ops, or -1 on overflow. */
+int64_t orc_speech_ops(int64_t n, const uint8_t *verb, const int32_t *speaker, const uint8_t *bodies, const uint64_t *body_off,
+                       const uint8_t *names, const uint64_t *name_off, const uint8_t *sflags, const int32_t *room,
+                       int ban_swearing, const char *const *words,
+                       uint8_t *text, size_t text_cap, uint64_t *off, uint8_t *kind, int32_t *target, int32_t *except_user,
+                       uint8_t *flags, int64_t cap)
+{
+    orc_oplist L = { text, 0, text_cap, off, kind, target, except_user, flags, 0, cap };
+    off[0] = 0;
+    for (int64_t m = 0; m < n; ++m) {
+        const int32_t u = speaker[m];
+        char uname[64]; size_t nl = (size_t)(name_off[u + 1] - name_off[u]);
+        if (nl > 63) nl = 63;
+        memcpy(uname, names + name_off[u], nl); uname[nl] = 0;
+        orc_speech_one(&L, verb[m], u, uname, !(sflags[u] & 1), (sflags[u] & 2) != 0, room[u], ban_swearing, words,
+                       bodies + body_off[m], (size_t)(body_off[m + 1] - body_off[m]));
+        if (L.n > L.cap) return -1;
+    }
+    return L.n;
+}

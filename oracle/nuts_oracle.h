@@ -114,6 +114,13 @@ void orc_site_banned_batch(const uint8_t *file, size_t fn, int present, int64_t 
 void orc_user_banned_batch(const uint8_t *file, size_t fn, int present, int64_t n,
                            const uint8_t *text, const uint64_t *off, uint8_t *verdict);
 
+/* The callers say/shout/emote/semote/echo/bcast restated (see nuts_oracle.c): input lines -> ops. */
+int64_t orc_speech_ops(int64_t n, const uint8_t *verb, const int32_t *speaker, const uint8_t *bodies, const uint64_t *body_off,
+                       const uint8_t *names, const uint64_t *name_off, const uint8_t *sflags, const int32_t *room,
+                       int ban_swearing, const char *const *words,
+                       uint8_t *text, size_t text_cap, uint64_t *off, uint8_t *kind, int32_t *target, int32_t *except_user,
+                       uint8_t *flags, int64_t cap);
+
 /* The pager, c:2205-2322 (see nuts_oracle.c). */
 int orc_more(const uint8_t *file, size_t n, int present, int user_null, int colour,
              int64_t *filepos, uint8_t *out, size_t *out_len);

@@ -192,6 +192,33 @@ int ref_set_ban_file(const char *dir, int which, const void *data, size_t n)
 int ref_site_banned(const char *site) { return site_banned((char *)site); }
 int ref_user_banned(const char *name) { return user_banned((char *)name); }
 
+/* The reference's own say()/shout()/emote()/semote()/echo()/bcast() (c:4062-4305, c:4772), one
+ * input line each, with the ambient state the main loop / exec_com would have set. */
+void ref_set_user_speech(int u, const char *name, int vis, int muzzled)
+{
+    if (u < 0 || u >= g_nusers) return;
+    strncpy(g_users[u]->name, name, USER_NAME_LEN); g_users[u]->name[USER_NAME_LEN] = 0;
+    g_users[u]->vis = vis; g_users[u]->muzzled = muzzled;
+}
+void ref_set_ban_swearing(int on) { ban_swearing = on; }
+void ref_speech(int verb, int u, const char *inpstr)
+{
+    static char line[ARR_SIZE * 2];
+    if (u < 0 || u >= g_nusers) return;
+    strncpy(line, inpstr, sizeof line - 1); line[sizeof line - 1] = 0;
+    force_listen = 0;                      /* cleared per input line, c:154 */
+    word_count = 2;                        /* the callers' "say what?" checks are the caller's business */
+    switch (verb) {
+    case 0: com_num = SAY;    say(g_users[u], line); break;
+    case 1: com_num = SHOUT;  shout(g_users[u], line); break;
+    case 2: com_num = EMOTE;  emote(g_users[u], line); break;
+    case 3: com_num = SEMOTE; semote(g_users[u], line); break;
+    case 4: com_num = ECHO;   echo(g_users[u], line); break;
+    case 5: com_num = BCAST;  bcast(g_users[u], line); break;
+    }
+    force_listen = 0;
+}
+
 /* more(), c:2205: the reference's own pager on a file on disk, socket = the user's index */
 int ref_more(int u, int null_user, const char *filename)
 {

@@ -96,6 +96,9 @@ class Port:
         L.orc_contains_swearing_batch.argtypes = [C.c_int64, u8p, u64p, C.POINTER(C.c_char_p), u8p]
         L.orc_site_banned_batch.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int64, u8p, u64p, u8p]
         L.orc_user_banned_batch.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int64, u8p, u64p, u8p]
+        L.orc_speech_ops.restype = C.c_int64
+        L.orc_speech_ops.argtypes = [C.c_int64, u8p, i32p, u8p, u64p, u8p, u64p, u8p, i32p, C.c_int, C.POINTER(C.c_char_p),
+                                     u8p, C.c_size_t, u64p, u8p, i32p, i32p, u8p, C.c_int64]
         L.orc_more.restype = C.c_int
         L.orc_more.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_char_p,
                                C.POINTER(C.c_size_t)]
@@ -183,6 +186,22 @@ class Port:
         fn(file or b"", len(file or b""), int(file is not None), n, _ptr(text, u8p), _ptr(off, u64p), _ptr(v, u8p))
         return v[:n]
 
+    def speech_ops(self, verb, speaker, bodies, body_off, names, name_off, sflags, room, ban_swearing, words):
+        """input lines -> ops dict (the callers restated)"""
+        n = len(verb)
+        cap = 3 * n + 1
+        tcap = int(body_off[-1]) * 2 + 256 * n + 64
+        text = np.zeros(tcap, np.uint8); off = np.zeros(cap + 1, np.uint64); kind = np.zeros(cap, np.uint8)
+        target = np.zeros(cap, np.int32); exc = np.zeros(cap, np.int32); flags = np.zeros(cap, np.uint8)
+        q = self.lib.orc_speech_ops(n, _ptr(np.ascontiguousarray(verb, np.uint8), u8p), _ptr(np.ascontiguousarray(speaker, np.int32), i32p),
+                                    _ptr(bodies, u8p), _ptr(body_off, u64p), _ptr(names, u8p), _ptr(name_off, u64p),
+                                    _ptr(np.ascontiguousarray(sflags, np.uint8), u8p), _ptr(np.ascontiguousarray(room, np.int32), i32p),
+                                    int(ban_swearing), self._words(words), _ptr(text, u8p), tcap, _ptr(off, u64p), _ptr(kind, u8p),
+                                    _ptr(target, i32p), _ptr(exc, i32p), _ptr(flags, u8p), cap)
+        assert q >= 0
+        return dict(text=text[:int(off[q])].copy(), off=off[:q + 1].copy(), kind=kind[:q].copy(), target=target[:q].copy(),
+                    except_user=exc[:q].copy(), flags=flags[:q].copy())
+
     def more(self, data, user_null: bool, colour: int, filepos: int):
         """-> (retval, bytes written to the socket, new filepos)"""
         n = len(data or b"")
@@ -222,6 +241,8 @@ class Ref:
         L.ref_stream_calls.restype = C.c_uint64
         L.ref_total_write_calls.restype = C.c_uint64
         L.ref_total_write_bytes.restype = C.c_uint64
+        L.ref_set_user_speech.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int]
+        L.ref_speech.argtypes = [C.c_int, C.c_int, C.c_char_p]
         L.ref_more.argtypes = [C.c_int, C.c_int, C.c_char_p]
         L.ref_get_filepos.restype = C.c_long
         L.ref_write_batch.restype = C.c_int64
