@@ -209,6 +209,14 @@ int nutsb_speech_batch_dev(nutsb_ctx *ctx, int64_t n, const uint8_t *verb, const
  * verdicts of the queued lines are taken in one device batch at nutsb_flush */
 int nutsb_q_speech(nutsb_ctx *ctx, int verb, int32_t user, const char *inpstr);
 
+/* ---- colour_com_count / colour_com_strip (nuts333.c:2563-2610), host buffers ------------- */
+/* count[i] = colour_com_count(string i), including its double count ("~FBK" is 2). */
+int nutsb_colour_com_count_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes, const uint64_t *off, int32_t *count);
+/* string i with every "~XX" (XX a colour command) removed, as colour_com_strip returns it:
+ * (*out_bytes)[(*out_off)[i] .. (*out_off)[i+1]); buffers owned by the context. */
+int nutsb_colour_com_strip_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes, const uint64_t *off,
+                                 const uint8_t **out_bytes, const uint64_t **out_off);
+
 /* Position-weighted 64-bit digest of every user's stream, computed on the
  * device from the last write batch: h = fold(h*0x100000001b3 + byte) over the
  * stream, h0 = 0xcbf29ce484222325.  digest[n_users] is a HOST array. */

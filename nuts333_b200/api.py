@@ -70,7 +70,7 @@ EXPORTS = [
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
     "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_q_speech",
-    "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
+    "nutsb_colour_com_count_batch", "nutsb_colour_com_strip_batch", "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
     "nutsb_q_write_level", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_contains_swearing",
     "nutsb_site_banned", "nutsb_user_banned",
 ]
@@ -108,6 +108,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_speech_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
     lib.nutsb_speech_batch_dev.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
     lib.nutsb_q_speech.argtypes = [vp, C.c_int, C.c_int32, C.c_char_p]
+    lib.nutsb_colour_com_count_batch.argtypes = [vp, C.c_int64, vp, vp, vp]
+    lib.nutsb_colour_com_strip_batch.argtypes = [vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp)]
     lib.nutsb_stream_digests.argtypes = [vp, u64p]
     lib.nutsb_q_write_user.argtypes = [vp, C.c_int32, C.c_char_p]
     lib.nutsb_q_write_room.argtypes = [vp, C.c_int32, C.c_char_p, C.c_int, C.c_int]
@@ -309,6 +311,25 @@ class Context:
 
     def user_banned_batch(self, text, off):
         return self._verdicts("user_banned", text, off)
+
+    def colour_com_count_batch(self, text, off):                      # c:2563
+        text, off = _np(text, np.uint8), _np(off, np.uint64)
+        n = len(off) - 1
+        cnt = np.zeros(max(n, 1), np.int32)
+        self._ck(self.lib.nutsb_colour_com_count_batch(self._h, n, _addr(text) if text.size else None, _addr(off), _addr(cnt)))
+        return cnt[:n]
+
+    def colour_com_strip_batch(self, text, off):                      # c:2588
+        """-> (bytes u8[], off u64[n+1]) of the stripped strings"""
+        text, off = _np(text, np.uint8), _np(off, np.uint64)
+        n = len(off) - 1
+        ob, oo = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.nutsb_colour_com_strip_batch(self._h, n, _addr(text) if text.size else None, _addr(off),
+                                                       C.byref(ob), C.byref(oo)))
+        o = np.ctypeslib.as_array(C.cast(oo, u64p), shape=(n + 1,)).copy()
+        total = int(o[n])
+        d = np.ctypeslib.as_array(C.cast(ob, u8p), shape=(total,)).copy() if total else np.zeros(0, np.uint8)
+        return d, o
 
     def verdicts_dev(self, name, n, text, off, verdict):
         self._ck(getattr(self.lib, f"nutsb_{name}_batch_dev")(self._h, n, text, off, verdict))

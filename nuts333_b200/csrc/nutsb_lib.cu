@@ -866,6 +866,45 @@ NUTSB_API int nutsb_site_banned_batch_dev(nutsb_ctx *c, int64_t n, const uint8_t
 NUTSB_API int nutsb_user_banned_batch(nutsb_ctx *c, int64_t n, const uint8_t *b, const uint64_t *o, uint8_t *v) { return verdict_host(c, V_USER, n, b, o, v); }
 NUTSB_API int nutsb_user_banned_batch_dev(nutsb_ctx *c, int64_t n, const uint8_t *b, const uint64_t *o, uint8_t *v) { return verdict_dev(c, V_USER, n, b, o, v); }
 
+// colour_com_count / colour_com_strip over host strings
+static int colour_com(nutsb_ctx *c, i64 n, const u8 *bytes, const u64 *off, i32 *count, const u8 **out_bytes, const u64 **out_off)
+{
+    if (!c || n < 0 || (n && !off) || (!count && (!out_bytes || !out_off))) return fail(c, NUTSB_E_INVAL, "bad argument%s");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    TRY(ensure_host(c, c->h_off, ((size_t)n + 1) * 8));
+    if (n == 0) { if (out_off) { c->h_off.as<u64>()[0] = 0; *out_off = c->h_off.as<u64>(); *out_bytes = c->h_out.as<u8>(); } return NUTSB_OK; }
+    const u64 t0 = off[0], t1 = off[n];
+    if (t1 < t0 || (t1 > t0 && !bytes)) return fail(c, NUTSB_E_INVAL, "bad offsets%s");
+    for (i64 i = 0; i < n; ++i) if (off[i + 1] < off[i]) return fail(c, NUTSB_E_INVAL, "offsets are not monotone%s");
+    TRY(ensure(c, c->s_text, (size_t)(t1 - t0) + 64));
+    if (t1 > t0) CK(cudaMemcpyAsync(c->s_text.p, bytes + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, st));
+    TRY(upload(c, c->s_toff, off, ((size_t)n + 1) * 8));
+    TRY(ensure(c, c->s_gate, (size_t)n * 4)); TRY(ensure(c, c->d_sp_len, (size_t)n * 4));
+    const u8 *dtext = c->s_text.as<u8>() - t0;
+    NUTSB_LAUNCH(cdiv(n, 256), 256, st, k_colour_com_count, dtext, c->s_toff.as<u64>(), n, c->d_codetab.as<u8>(),
+                 c->s_gate.as<i32>(), c->d_sp_len.as<u32>()); CKL();
+    if (count) CK(cudaMemcpyAsync(count, c->s_gate.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (out_bytes) {
+        TRY(ensure(c, c->d_sp_off, ((size_t)n + 1) * 8));
+        TRY(run_scan(c, InU32{c->d_sp_len.as<u32>()}, OutU64{c->d_sp_off.as<u64>()}, n, nullptr));
+        TRY(ensure(c, c->d_sp_text, (size_t)(t1 - t0) + 64));            // a stripped string is never longer
+        NUTSB_LAUNCH(cdiv(n, 256), 256, st, k_colour_com_strip, dtext, c->s_toff.as<u64>(), n, c->d_codetab.as<u8>(),
+                     c->d_sp_off.as<u64>(), c->d_sp_text.as<u8>()); CKL();
+        TRY(ensure_host(c, c->h_out, (size_t)(t1 - t0) + 16));
+        CK(cudaMemcpyAsync(c->h_off.p, c->d_sp_off.p, ((size_t)n + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_out.p, c->d_sp_text.p, (size_t)(t1 - t0), cudaMemcpyDeviceToHost, st));
+        *out_bytes = c->h_out.as<u8>(); *out_off = c->h_off.as<u64>();
+    }
+    CK(cudaStreamSynchronize(st));
+    c->have_streams = false;        // the pinned result buffers were reused
+    return NUTSB_OK;
+}
+NUTSB_API int nutsb_colour_com_count_batch(nutsb_ctx *c, int64_t n, const uint8_t *b, const uint64_t *o, int32_t *count)
+{ if (!count) return NUTSB_E_INVAL; return colour_com(c, n, b, o, count, nullptr, nullptr); }
+NUTSB_API int nutsb_colour_com_strip_batch(nutsb_ctx *c, int64_t n, const uint8_t *b, const uint64_t *o, const uint8_t **ob, const uint64_t **oo)
+{ if (!ob || !oo) return NUTSB_E_INVAL; return colour_com(c, n, b, o, nullptr, ob, oo); }
+
 static int verdict_one(nutsb_ctx *c, int which, const char *s)
 {
     if (!c || !s) return NUTSB_E_INVAL;

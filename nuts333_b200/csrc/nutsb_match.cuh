@@ -125,3 +125,56 @@ k_set_match(const u8 *text, const u64 *off, i64 n, SetView set, u8 *verdict)
     }
     verdict[i] = (u8)hit;
 }
+
+// ---- colour_com_count / colour_com_strip (nuts333.c:2563-2610) -----------------------------
+// Small text utilities of the reference: `.who` pads its columns by the number of colour
+// commands in a line (c:4846), peers older than 3.2 get lines with the commands removed
+// (c:1301).  One thread per string; the strings are short.
+//   count: after a hit the scan pointer moves on ONE byte and the loop over the remaining
+//          table entries goes on from there (the `continue` belongs to the for, c:2575), so
+//          "~FBK" counts 2.  strip: "~XX" removed for known XX, everything else kept; no '/~'
+//          escape, no CR.
+__global__ void __launch_bounds__(256)
+k_colour_com_count(const u8 *text, const u64 *off, i64 n, const u8 *codetab, i32 *count, u32 *strip_len)
+{
+    __shared__ u8 s_tab[NUTSB_CODETAB_BYTES];
+    for (int i = threadIdx.x; i < NUTSB_CODETAB_BYTES; i += blockDim.x) s_tab[i] = codetab[i];
+    __syncthreads();
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u8 *s = text + off[i];
+    const u32 len = (u32)(off[i + 1] - off[i]);
+    i32 cnt = 0; u32 kept = 0;
+    // strip length: the plain left-to-right rule
+    for (u32 p = 0; p < len;) {
+        if (s[p] == '~' && p + 2 < len && nutsb_code(s_tab, s[p + 1], s[p + 2]) >= 0) p += 3; else { ++kept; ++p; }
+    }
+    // count: the table is walked in its own order k = 0..20 with a moving pointer
+    for (u32 p = 0; p < len;) {
+        if (s[p] != '~') { ++p; continue; }
+        ++p;
+        int k = 0;
+        while (k < 21 && p + 1 < len) {
+            const int hit = nutsb_code(s_tab, s[p], s[p + 1]);     // index of the pair in the table, or -1
+            if (hit >= k) { ++cnt; ++p; k = hit + 1; } else break;   // only entries not yet passed can still match
+        }
+    }
+    if (count) count[i] = cnt;
+    if (strip_len) strip_len[i] = kept;
+}
+
+__global__ void __launch_bounds__(256)
+k_colour_com_strip(const u8 *text, const u64 *off, i64 n, const u8 *codetab, const u64 *out_off, u8 *out)
+{
+    __shared__ u8 s_tab[NUTSB_CODETAB_BYTES];
+    for (int i = threadIdx.x; i < NUTSB_CODETAB_BYTES; i += blockDim.x) s_tab[i] = codetab[i];
+    __syncthreads();
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u8 *s = text + off[i];
+    const u32 len = (u32)(off[i + 1] - off[i]);
+    u8 *d = out + out_off[i];
+    for (u32 p = 0; p < len;) {
+        if (s[p] == '~' && p + 2 < len && nutsb_code(s_tab, s[p + 1], s[p + 2]) >= 0) p += 3; else *d++ = s[p++];
+    }
+}
