@@ -74,21 +74,8 @@ __device__ __forceinline__ int nutsb_code(const u8 *tab, u8 a, u8 b)
     if (ua < 26u && ub < 26u) return (int)tab[ua * 26u + ub] - 1;
     return -1;
 }
-// Bytes of colcode[k]: ESC [ d m   (k<5, d in 0 1 4 5 7)  or  ESC [ 3|4 d m.
+// Length of colcode[k]: ESC [ d m (k<5) or ESC [ 3|4 d m.
 __device__ __forceinline__ u32 nutsb_code_len(int k) { return k < 5 ? 4u : 5u; }
-__device__ __forceinline__ u8 nutsb_code_byte(int k, u32 i)
-{
-    if (i == 0) return 0x1b;
-    if (i == 1) return '[';
-    if (k < 5) {
-        if (i == 3) return 'm';
-        // "01457" packed: k=0->'0',1->'1',2->'4',3->'5',4->'7'
-        return (u8)('0' + ((0x75410u >> (4 * k)) & 0xf));
-    }
-    if (i == 2) return (u8)(k < 13 ? '3' : '4');
-    if (i == 3) return (u8)('0' + ((k - 5) & 7));
-    return 'm';
-}
 
 // Recipient filter for the ops that reach a whole class of users (room and
 // level ops); the room match itself is established by bucketing.
@@ -103,32 +90,6 @@ __device__ __forceinline__ bool nutsb_class_delivers(u32 cflags, u32 clevel, u32
     }
     if (cflags & NUTSB_UF_CLONE) return false;
     return (oflags & NUTSB_OF_ABOVE) ? ((i32)clevel >= target) : ((i32)clevel <= target);
-}
-
-// Sequential restatement of write_user's byte machine (nuts333.c:1315-1365),
-// one thread, shared -> shared.  s[-1] is never read at i==0; bytes past n are
-// never read.
-__device__ __forceinline__ u32 nutsb_render_seq(const u8 *s, u32 n, int colour, u8 *out, const u8 *tab)
-{
-    u32 i = 0, o = 0;
-    while (i < n) {
-        u8 c = s[i];
-        if (c == '\n') {
-            if (colour) { out[o] = 0x1b; out[o + 1] = '['; out[o + 2] = '0'; out[o + 3] = 'm'; o += 4; }
-            out[o] = '\n'; out[o + 1] = '\r'; o += 2; ++i;
-        } else if (c == '/' && i + 1 < n && s[i + 1] == '~') {
-            ++i;
-        } else if (c == '~') {
-            int k = -1;
-            if (!(i > 0 && s[i - 1] == '/') && i + 2 < n) k = nutsb_code(tab, s[i + 1], s[i + 2]);
-            if (k >= 0) {
-                if (colour) { u32 L = nutsb_code_len(k); for (u32 q = 0; q < L; ++q) out[o + q] = nutsb_code_byte(k, q); o += L; }
-                i += 3;
-            } else { out[o++] = '~'; ++i; }
-        } else { out[o++] = c; ++i; }
-    }
-    if (colour) { out[o] = 0x1b; out[o + 1] = '['; out[o + 2] = '0'; out[o + 3] = 'm'; o += 4; }
-    return o;
 }
 
 // ---- device-wide exclusive scan (three kernels, u64) ----------------------------

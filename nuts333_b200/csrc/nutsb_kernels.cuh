@@ -544,7 +544,7 @@ __device__ __forceinline__ u32 nutsb_render1(const u8 *s, u32 n, bool colour, u3
 }
 
 // One lane stages its own string (32-bit loads; lanes of a warp walk 32 different
-// strings, L1 absorbs the overlap).  Same window convention as nutsb_warp_stage.
+// strings, L1 absorbs the overlap).
 __device__ __forceinline__ void nutsb_lane_stage(u8 *dst, const u8 *src, u32 n)
 {
     const u32 a = (u32)((size_t)src & 3);
@@ -574,17 +574,10 @@ __device__ __forceinline__ void nutsb_lane_copy(u8 *dst, const u8 *src, u32 n)
     for (u32 q = 4 * nw; q < n; ++q) dst[q] = src[q];
 }
 
-// Stage one string into shared memory with 32-bit loads: the window starts at
-// the aligned word holding the first byte, so dst must be 4-byte aligned and the
-// string then begins at dst + ((size_t)src & 3).  Reads whole words: up to 3
-// bytes either side of the string (inside the packed text allocation).
-__device__ __forceinline__ void nutsb_warp_stage(u8 *dst, const u8 *src, u32 n, int lane)
-{
-    const u32 a = (u32)((size_t)src & 3);
-    const u32 *g = (const u32 *)(src - a);
-    const u32 nw = (a + n + 3) >> 2;
-    for (u32 w = lane; w < nw; w += 32) ((u32 *)dst)[w] = __ldg(g + w);
-}
+// Staging convention: a string is copied into shared memory with 32-bit loads as the window
+// of aligned words that holds it, so the window starts 4-byte aligned and the string begins
+// at window + ((size_t)src & 3).  Whole words are read: up to 3 bytes either side of the
+// string (inside the packed text allocation).  Size of that window:
 __device__ __forceinline__ u32 nutsb_stage_bytes(const u8 *src, u32 n) { return (((u32)((size_t)src & 3)) + n + 3) & ~3u; }
 
 // ---- warp copy: shared -> global at arbitrary byte alignment --------------------------
@@ -594,6 +587,9 @@ __device__ __forceinline__ u32 nutsb_stage_bytes(const u8 *src, u32 n) { return 
 // realigned in registers from two 16-byte shared loads; the word part of the
 // shift is a template parameter so no selects are executed.  src buffers carry
 // >= 48 bytes of readable padding.
+#ifndef NUTSB_COPY_UNROLL4
+#define NUTSB_COPY_UNROLL4 0
+#endif
 template <int WSH>
 __device__ __forceinline__ uint4 nutsb_realign(const uint4 &a, const uint4 &b, u32 bsh)
 {
@@ -607,6 +603,16 @@ template <int WSH>
 __device__ __forceinline__ void nutsb_copy_body(u8 *dst, const uint4 *sa, u32 nvec, u32 bsh, int lane)
 {
     u32 v = (u32)lane;
+#if NUTSB_COPY_UNROLL4
+    for (; v + 96 < nvec; v += 128) {                   // four coalesced 512-byte stores in flight per lane
+        const uint4 a0 = sa[v], b0 = sa[v + 1], a1 = sa[v + 32], b1 = sa[v + 33];
+        const uint4 a2 = sa[v + 64], b2 = sa[v + 65], a3 = sa[v + 96], b3 = sa[v + 97];
+        *(uint4 *)(dst + 16 * (size_t)v) = nutsb_realign<WSH>(a0, b0, bsh);
+        *(uint4 *)(dst + 16 * (size_t)(v + 32)) = nutsb_realign<WSH>(a1, b1, bsh);
+        *(uint4 *)(dst + 16 * (size_t)(v + 64)) = nutsb_realign<WSH>(a2, b2, bsh);
+        *(uint4 *)(dst + 16 * (size_t)(v + 96)) = nutsb_realign<WSH>(a3, b3, bsh);
+    }
+#endif
     for (; v + 32 < nvec; v += 64) {
         const uint4 a0 = sa[v], b0 = sa[v + 1], a1 = sa[v + 32], b1 = sa[v + 33];
         *(uint4 *)(dst + 16 * (size_t)v) = nutsb_realign<WSH>(a0, b0, bsh);
