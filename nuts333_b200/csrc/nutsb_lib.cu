@@ -738,6 +738,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
 static int check_ops(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
 {
     if (!c || !o || !out || o->n_ops < 0) return fail(c, NUTSB_E_INVAL, "null argument or negative n_ops%s");
+    if (o->n_ops >= 0xfffffff0ll) return fail(c, NUTSB_E_RANGE, "more than 2^32 ops in one batch%s");
     if (o->n_ops && (!o->text_off || !o->kind || !o->target || !o->except_user || !o->flags))
         return fail(c, NUTSB_E_INVAL, "ops array is NULL%s");
     return NUTSB_OK;

@@ -165,6 +165,42 @@ def test_random_batches_vs_oracle(gpu_ctx, port, seed, U, NR, N, maxlen):
         assert int(dg[u]) == h
 
 
+def test_fuzz_many_shapes_vs_oracle(gpu_ctx, port):
+    """40 random (population, batch) shapes: rooms of 1..600 users, empty rooms, tiles that are
+    exactly full / one over, strings that force sub-tiles, all flags, pager and plain ops."""
+    for seed in range(100, 140):
+        rng = random.Random(seed)
+        U = rng.choice([1, 2, 31, 32, 33, 127, 128, 129, 257, 600])
+        NR = rng.choice([1, 1, 2, 5, 40])
+        N = rng.choice([1, 127, 128, 129, 256, 257, 700, 2000])
+        simple = rng.random() < 0.5
+        room = np.array([rng.randint(0 if simple else -1, NR - 1) for _ in range(U)], np.int32)
+        flags = np.array([rng.choice([0, 1] if simple else [0, 1, 1, 0, 2, 4, 8, 5, 9]) for _ in range(U)], np.uint8)
+        level = np.array([rng.randint(0, 4) for _ in range(U)], np.uint8)
+        big = rng.random() < 0.3
+        texts, kind, target, exc, fl = [], [], [], [], []
+        for i in range(N):
+            k = rng.choice([0, 1, 1, 1, 1] if simple else [0, 1, 1, 1, 1, 2])
+            n = rng.randint(0, 400 if big else 40)
+            texts.append(b"".join(rng.choice(ALPHA + [b"~FR", b"~RS", b"~OL", b"word ", b"/~", b"\n"]) for _ in range(n))[:2000])
+            kind.append(k)
+            f = rng.choice([0, 0, 0, api.OF_PAGER, api.OF_PLAIN])
+            if k == 0:
+                target.append(rng.randint(-1, U - 1)); exc.append(-1); fl.append(f)
+            elif k == 1:
+                target.append(rng.randint(-1, NR - 1)); exc.append(rng.randint(-1, U - 1)); fl.append(f | rng.choice([0, 0, 1, 2]))
+            else:
+                target.append(rng.randint(0, 4)); exc.append(rng.randint(-1, U - 1)); fl.append(f | rng.choice([0, 4]))
+        text, off = O.pack(texts)
+        ops = dict(text=text, off=off, kind=np.array(kind, np.uint8), target=np.array(target, np.int32),
+                   except_user=np.array(exc, np.int32), flags=np.array(fl, np.uint8))
+        users = dict(room=room, flags=flags, level=level)
+        gpu_ctx.set_users(room, flags, level, NR)
+        st = gpu_ctx.write_batch(ops)
+        o, d, nd = port.write_batch(ops, users)
+        assert (st.off == o).all() and (st.data == d).all() and st.n_deliveries == int(nd.sum()), seed
+
+
 def test_simple_population_fast_path_vs_oracle(gpu_ctx, port):
     """colour-only population (no login/ignall/ignshout, no level ops): the path the
     benchmark takes, at a size the oracle finishes in seconds (config 2, scaled)."""
