@@ -283,7 +283,7 @@ def run_ours(args):
     input_bytes = sum(int(v.numel() * v.element_size()) for k, v in d.items() if k not in ("verdict", "vs", "vu"))
     torch.cuda.synchronize()
 
-    state = dict(deliv=0, bytes=0, launches=0, fan_ms=0.0, fan_in=0, fan_out=0, plan_ms=0.0, direct_ms=0.0)
+    state = dict(deliv=0, bytes=0, launches=0, fan_ms=0.0, fan_in=0, fan_out=0, plan_ms=0.0, direct_ms=0.0, phase=None)
 
     def step_device():
         with torch.cuda.stream(stream):
@@ -298,6 +298,7 @@ def run_ours(args):
         state["launches"] += int(t.launches) + 3
         state["fan_ms"] += float(t.fanout_ms); state["fan_in"] += int(t.fanout_bytes_in); state["fan_out"] += int(t.fanout_bytes_out)
         state["plan_ms"] += float(t.plan_ms); state["direct_ms"] += float(t.direct_ms)
+        state["phase"] = [int(x) for x in t.phase_cycles]
         return s
 
     def barrier():
@@ -310,7 +311,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_device()
     for k in state:
-        state[k] = 0 if not isinstance(state[k], float) else 0.0
+        state[k] = None if k == "phase" else (0 if not isinstance(state[k], float) else 0.0)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
@@ -390,6 +391,8 @@ def run_ours(args):
                          dict(value=total_e2e_deliv / (e2e_ms_max * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d,
                               d2h_bytes_per_step=d2h, steps=e2e_steps)),
                     gpu_launches=total_launch, clocks=clk)
+        if dev_state.get("phase") and any(dev_state["phase"]):
+            line["config"]["fanout_phase_cycles"] = dev_state["phase"]      # only with -DNUTSB_FAN_PROFILE=1
         if world == 1 and not args.no_cpu_baseline:
             procs = 1
             dcpu, nbytes, busy, wall, kind = reference_step(0, 40_000, 4_000, procs)

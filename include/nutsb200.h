@@ -126,6 +126,7 @@ typedef struct nutsb_timing {
     uint64_t fanout_bytes_in, fanout_bytes_out;   /* algorithmic bytes of the fan-out kernel */
     uint32_t launches;   /* kernels launched by the last batch call                     */
     uint32_t fanout_launches;
+    uint64_t phase_cycles[6];   /* development aid: zero unless built with -DNUTSB_FAN_PROFILE=1 */
 } nutsb_timing;
 
 int         nutsb_version(void);

@@ -60,7 +60,7 @@ class Timing(C.Structure):
     _fields_ = [("plan_ms", C.c_float), ("fanout_ms", C.c_float), ("direct_ms", C.c_float),
                 ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("fanout_bytes_in", C.c_uint64), ("fanout_bytes_out", C.c_uint64),
-                ("launches", C.c_uint32), ("fanout_launches", C.c_uint32)]
+                ("launches", C.c_uint32), ("fanout_launches", C.c_uint32), ("phase_cycles", C.c_uint64 * 6)]
 
 
 EXPORTS = [

@@ -668,6 +668,16 @@ struct FanoutArgs {
 };
 
 #define NUTSB_FAN_THREADS (2 * NUTSB_TILE_OPS)
+// -DNUTSB_FAN_PROFILE=1: thread 0 of every block adds the cycles it spent in each phase to
+// counters[3..7] (setup, stage, render+plan, copy, barrier at the end of copy) -- a development aid
+#ifndef NUTSB_FAN_PROFILE
+#define NUTSB_FAN_PROFILE 0
+#endif
+#if NUTSB_FAN_PROFILE && !defined(NUTSB_CPUSIM)
+#define NUTSB_PHASE(slot) do { if (tid == 0) { const long long t_ = clock64(); nutsb_add64(A.n_deliveries + (slot), (u64)(t_ - t_prev)); t_prev = t_; } } while (0)
+#else
+#define NUTSB_PHASE(slot) do { } while (0)
+#endif
 #ifndef NUTSB_FAN_TMA
 #define NUTSB_FAN_TMA 0          // 1: copy runs with TMA bulk stores from 16 pre-shifted slab pieces (measured slower: DESIGN.md 4.1)
 #endif
@@ -713,6 +723,9 @@ k_fanout(FanoutArgs A)
     __shared__ u32 s_deliv;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if NUTSB_FAN_PROFILE && !defined(NUTSB_CPUSIM)
+    long long t_prev = clock64();
+#endif
 
     // -- decode the work item
     if (tid == 0) {
@@ -785,6 +798,7 @@ k_fanout(FanoutArgs A)
     }
     __syncthreads();
 
+    NUTSB_PHASE(3);
     u32 my_deliv = 0;
     u32 a = 0;
     while (a < nb) {
@@ -815,6 +829,7 @@ k_fanout(FanoutArgs A)
             }
         }
         __syncthreads();
+        NUTSB_PHASE(4);
         // -- render: threads 0..127 run the byte machine for colour-on recipients, threads
         //    128..255 for colour-off ones (the setting is uniform per warp)
         {
@@ -872,7 +887,9 @@ k_fanout(FanoutArgs A)
             }
             s_ulegacy[q] = legacy ? 1 : 0;
         }
+        NUTSB_PHASE(5);                 // thread 0's own render + plan
         __syncthreads();
+        NUTSB_PHASE(6);                 // waiting for the slowest renderer
 
 #if NUTSB_FAN_TMA
         // -- copy with the TMA: a run's destination is byte-aligned, a bulk copy wants 16-byte
@@ -1007,7 +1024,9 @@ k_fanout(FanoutArgs A)
                 ++e;
             }
         }
+        NUTSB_PHASE(7);                 // warp 0's share of the copy
         __syncthreads();
+        NUTSB_PHASE(8);                 // waiting for the slowest copier
         a = b;
     }
     if (lane == 0 && my_deliv) atomicAdd(&s_deliv, my_deliv);

@@ -374,7 +374,7 @@ NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
         u8 tab[NUTSB_CODETAB_BYTES]; build_codetab(tab);
         TRY(upload(c, c->d_codetab, tab, sizeof tab));
         TRY(ensure(c, c->d_status, 64)); TRY(ensure(c, c->d_counts, 64)); TRY(ensure(c, c->d_sizes, sizeof(Sizes)));
-        TRY(ensure(c, c->d_counters, 64));
+        TRY(ensure(c, c->d_counters, 128));
         TRY(ensure_host(c, c->h_small, 4096));
         {   // the callers' literals (nutsb_speech.cuh)
             c->lits.assign(NUTSB_NLIT, std::string());
@@ -578,7 +578,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     TRY(ensure(c, c->d_len_on, (size_t)n * 4)); TRY(ensure(c, c->d_len_off, (size_t)n * 4));
     TRY(ensure(c, c->d_nrep, (size_t)n * 4)); TRY(ensure(c, c->d_eoff, ((size_t)n + 1) * 8));
     CK(cudaMemsetAsync(c->d_status.p, 0, 64, st));
-    CK(cudaMemsetAsync(c->d_counters.p, 0, 64, st));
+    CK(cudaMemsetAsync(c->d_counters.p, 0, 128, st));
     u32 *len_on = c->d_len_on.as<u32>(), *len_off = c->d_len_off.as<u32>(), *nrep = c->d_nrep.as<u32>();
     NUTSB_LAUNCH(cdiv(n, NUTSB_MEASURE_THREADS), NUTSB_MEASURE_THREADS, st, k_measure, ops, pop0, len_on, len_off, nrep,
                  c->d_status.as<u32>()); CKL();
@@ -717,7 +717,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[3], st));
 
-    CK(cudaMemcpyAsync(h64 + 8, counters, 24, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h64 + 8, counters, 72, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     TRY(status_to_error(c, h32[4]));
@@ -730,6 +730,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     }
     c->tm.fanout_bytes_out = sz.total_bytes - h64[9];
     c->tm.fanout_bytes_in = h64[10];
+    for (int q = 0; q < 6; ++q) c->tm.phase_cycles[q] = h64[11 + q];
     out->n_users = U; out->total_bytes = sz.total_bytes; out->n_deliveries = h64[8];
     out->off = c->d_off.as<u64>(); out->bytes = c->d_out.as<u8>(); out->on_device = 1;
     return NUTSB_OK;

@@ -4,9 +4,6 @@ mkdir -p gpurun_out; : > gpurun_out/matrix.txt
 IFS='|' read -ra VS <<< "${VARIANTS:--DNUTSB_TILE_OPS=128}"
 for v in "${VS[@]}"; do
   NUTSB_NVCC_EXTRA="$v" python nuts333_b200/build.py --force > /dev/null 2>gpurun_out/build.err || { echo "$v BUILD FAILED" >> gpurun_out/matrix.txt; continue; }
-  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>gpurun_out/m.err | python -c "
-import sys,json
-d=json.loads(sys.stdin.read()); c=d['config']
-print('$v', 'ms/step', round(d['ms_per_step'],3), 'fanout', round(c['fanout_ms'],3), 'direct', round(c['direct_ms'],3), 'plan', round(c['plan_ms'],3), 'frac', round(d['roofline']['frac'],3))" >> gpurun_out/matrix.txt 2>&1
+  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>gpurun_out/m.err | python scripts/bench_line.py "$v" >> gpurun_out/matrix.txt 2>&1
 done
 cat gpurun_out/matrix.txt
