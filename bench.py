@@ -283,7 +283,7 @@ def run_ours(args):
     input_bytes = sum(int(v.numel() * v.element_size()) for k, v in d.items() if k not in ("verdict", "vs", "vu"))
     torch.cuda.synchronize()
 
-    state = dict(deliv=0, bytes=0, launches=0, fan_ms=0.0, fan_in=0, fan_out=0, plan_ms=0.0, direct_ms=0.0, phase=None)
+    state = dict(deliv=0, bytes=0, launches=0, fan_ms=0.0, fan_in=0, fan_out=0, plan_ms=0.0, direct_ms=0.0, render_ms=0.0)
 
     def step_device():
         with torch.cuda.stream(stream):
@@ -297,8 +297,7 @@ def run_ours(args):
         state["deliv"] += int(s.n_deliveries); state["bytes"] += int(s.total_bytes)
         state["launches"] += int(t.launches) + 3
         state["fan_ms"] += float(t.fanout_ms); state["fan_in"] += int(t.fanout_bytes_in); state["fan_out"] += int(t.fanout_bytes_out)
-        state["plan_ms"] += float(t.plan_ms); state["direct_ms"] += float(t.direct_ms)
-        state["phase"] = [int(x) for x in t.phase_cycles]
+        state["plan_ms"] += float(t.plan_ms); state["direct_ms"] += float(t.direct_ms); state["render_ms"] += float(t.render_ms)
         return s
 
     def barrier():
@@ -311,7 +310,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_device()
     for k in state:
-        state[k] = None if k == "phase" else (0 if not isinstance(state[k], float) else 0.0)
+        state[k] = 0 if not isinstance(state[k], float) else 0.0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
@@ -382,7 +381,8 @@ def run_ours(args):
                                    % (input_bytes / 1e6, dev_state["bytes"] / max(1, args.steps) / 1e9),
                                 source_msgs_per_s=world * N_MSGS * args.steps / (ms_max * 1e-3),
                                 ban_queries_per_step=2 * N_BAN_QUERIES,
-                                plan_ms=dev_state["plan_ms"] / max(1, args.steps), fanout_ms=fan_ms,
+                                plan_ms=dev_state["plan_ms"] / max(1, args.steps),
+                                render_ms=dev_state["render_ms"] / max(1, args.steps), fanout_ms=fan_ms,
                                 direct_ms=dev_state["direct_ms"] / max(1, args.steps)),
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                                   traffic=traffic, kernel="k_fanout", peak_source=peak_src,
@@ -391,8 +391,6 @@ def run_ours(args):
                          dict(value=total_e2e_deliv / (e2e_ms_max * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d,
                               d2h_bytes_per_step=d2h, steps=e2e_steps)),
                     gpu_launches=total_launch, clocks=clk)
-        if dev_state.get("phase") and any(dev_state["phase"]):
-            line["config"]["fanout_phase_cycles"] = dev_state["phase"]      # only with -DNUTSB_FAN_PROFILE=1
         if world == 1 and not args.no_cpu_baseline:
             procs = 1
             dcpu, nbytes, busy, wall, kind = reference_step(0, 40_000, 4_000, procs)

@@ -118,15 +118,17 @@ typedef struct nutsb_streams {
 /* Device-side timings of the last write batch, CUDA events on the context's
  * stream (ms).  Filled only after nutsb_set_profiling(ctx, 1). */
 typedef struct nutsb_timing {
-    float plan_ms;       /* measure, bucket, prefix, events, offsets                    */
-    float fanout_ms;     /* render + fan-out kernel (the dominant kernel)               */
+    float plan_ms;       /* measure, bucket, prefix, events, offsets, copy plan         */
+    float render_ms;     /* k_render: every room/level op rendered once per colour      */
+    float fanout_ms;     /* k_fanout: rendered bytes -> recipients' streams (dominant)  */
     float direct_ms;     /* write_user ops rendered straight into the streams           */
     float total_ms;      /* first kernel to last kernel, incl. the two size read-backs  */
     float h2d_ms, d2h_ms;
-    uint64_t fanout_bytes_in, fanout_bytes_out;   /* algorithmic bytes of the fan-out kernel */
+    uint64_t fanout_bytes_in, fanout_bytes_out;   /* algorithmic bytes of the fan-out kernel:
+                                                     rendered slab read once, deliveries written once */
+    uint64_t render_bytes_in, slab_bytes;         /* k_render: source bytes read, rendered bytes written */
     uint32_t launches;   /* kernels launched by the last batch call                     */
     uint32_t fanout_launches;
-    uint64_t phase_cycles[6];   /* development aid: zero unless built with -DNUTSB_FAN_PROFILE=1 */
 } nutsb_timing;
 
 int         nutsb_version(void);

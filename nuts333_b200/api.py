@@ -57,10 +57,11 @@ class _Streams(C.Structure):
 
 
 class Timing(C.Structure):
-    _fields_ = [("plan_ms", C.c_float), ("fanout_ms", C.c_float), ("direct_ms", C.c_float),
+    _fields_ = [("plan_ms", C.c_float), ("render_ms", C.c_float), ("fanout_ms", C.c_float), ("direct_ms", C.c_float),
                 ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("fanout_bytes_in", C.c_uint64), ("fanout_bytes_out", C.c_uint64),
-                ("launches", C.c_uint32), ("fanout_launches", C.c_uint32), ("phase_cycles", C.c_uint64 * 6)]
+                ("render_bytes_in", C.c_uint64), ("slab_bytes", C.c_uint64),
+                ("launches", C.c_uint32), ("fanout_launches", C.c_uint32)]
 
 
 EXPORTS = [

@@ -37,15 +37,16 @@ struct PopView {                 // the population, built by nutsb_set_users
 };
 
 #ifndef NUTSB_TILE_OPS
-#define NUTSB_TILE_OPS   128     // room-list ops per fan-out tile (power of two; k_fanout runs 2 threads per op)
+#define NUTSB_TILE_OPS   128     // slab ops per fan-out tile
 #endif
-#define NUTSB_UCHUNK     (NUTSB_TILE_OPS < 128 ? NUTSB_TILE_OPS : 128)   // recipients per fan-out work item
-#define NUTSB_MAX2(a, b) ((a) > (b) ? (a) : (b))
-#define NUTSB_TEXT_CAP   NUTSB_MAX2(2048 + 64, 88 * NUTSB_TILE_OPS)   // staged source bytes per (sub)tile   (>= 2000+6)
-#define NUTSB_ON_CAP     NUTSB_MAX2(12288, 96 * NUTSB_TILE_OPS)       // rendered bytes per (sub)tile, colour on  (>= 6*2000+4)
-#define NUTSB_OFF_CAP    NUTSB_MAX2(4096, 80 * NUTSB_TILE_OPS)        // rendered bytes per (sub)tile, colour off (>= 2*2000)
-#define NUTSB_EV_CAP     256     // events of a tile's recipients prefetched into shared memory
-#define NUTSB_RUN_CAP    512     // planned copy runs per (sub)tile and recipient chunk
+#define NUTSB_UCHUNK     128     // recipients per fan-out work item
+#ifndef NUTSB_FAN_ON_CAP
+#define NUTSB_FAN_ON_CAP  (96 * NUTSB_TILE_OPS)   // shared-memory window for a tile's colour-on rendering
+#endif
+#ifndef NUTSB_FAN_OFF_CAP
+#define NUTSB_FAN_OFF_CAP (80 * NUTSB_TILE_OPS)   // ... and its colour-off rendering (larger tiles are copied slab -> stream directly)
+#endif
+#define NUTSB_FAN_RUN_CAP 256    // runs staged per round
 
 // ---- A. measure ------------------------------------------------------------------
 // Rendered length of every op for both colour settings, liveness (gate), validation
@@ -338,6 +339,8 @@ struct EntryScatter {
     const u32 *room_ent_off;     // [Rt+1] entry offset of each room
     u64 *e_scan;                 // [n_ent+1] packed exclusive scan (written by the scan's Out)
     u32 *bl_op, *bl_room;        // slab list
+    u32 *bl_meta;                // kind | flags << 8 | clamped target << 16 of each slab op (k_plan's filter walk)
+    OpsView ops;
     u32 *ev_slot, *ev_ukey, *ev_op; i32 *ev_delta;
 };
 
@@ -350,7 +353,12 @@ k_entry_scatter(EntryScatter s, i64 n_ent)
     const u64 sc = s.e_scan[e];
     const u32 rankB = (u32)sc, evi = (u32)(sc >> 32);
     const u32 room = s.e_room[e];
-    if (info & 1) { s.bl_op[rankB] = s.e_op[e]; s.bl_room[rankB] = room; }
+    if (info & 1) {
+        const u32 op = s.e_op[e];
+        i32 tg = s.ops.target[op]; tg = tg < -32768 ? -32768 : (tg > 32767 ? 32767 : tg);   // only compared with a level (u8)
+        s.bl_op[rankB] = op; s.bl_room[rankB] = room;
+        s.bl_meta[rankB] = (u32)s.ops.kind[op] | ((u32)s.ops.flags[op] << 8) | ((u32)(tg & 0xffff) << 16);
+    }
     const u32 ek = info >> 1;
     if (ek) {
         const u32 roomB0 = (u32)s.e_scan[s.room_ent_off[room]];     // slab rank of the room's first entry
@@ -421,41 +429,145 @@ k_user_len(UserLenIn in, i64 n, u64 *len)
     if (u < n) len[u] = in(u);
 }
 
-// ---- F. stream position of every (tile, recipient) cell ---------------------------------
+// ---- F. copy plan ---------------------------------------------------------------------------
+// A room's slab ops are cut into tiles of NUTSB_TILE_OPS; a cell is one (tile,
+// recipient) pair.  Every recipient's view of a tile is a short list of RUNS:
+// contiguous pieces of the rendered slab (k_render), cut only where the
+// recipient is the excluded speaker (c:1415), where a direct write_user op's
+// bytes interleave, or -- for recipients behind a filter (login / ignall /
+// ignshout, write_level) -- where an op is not delivered to the recipient's
+// class.  The plan is made in two passes over the cells (count, exclusive scan,
+// fill) and leaves a flat run list in (room, tile, recipient) order plus one
+// descriptor per fan-out work item, so that the kernel that moves the bytes
+// (k_fanout) has nothing to decide.
 struct Geometry {
-    const u32 *room_b_off;       // [Rt+1]
+    const u32 *room_b_off;       // [Rt+1] slab rank of room r's first op
     const u32 *room_tile_off;    // [Rt+1] tiles before room r
-    const u64 *room_cell_off;    // [Rt+1] cells before room r; room r has (tiles_r+1)*users_r cells
+    const u64 *room_cell_off;    // [Rt+1] cells before room r; room r has tiles_r * users_r cells
     const u32 *room_item_off;    // [Rt+1] fan-out work items before room r
 };
 
-// One thread per cell: where in the recipient's stream the tile's first op
-// starts (class prefix + the recipient's own exclusions / direct ops before the
-// tile), and which of the recipient's events is the first one inside the tile.
-__global__ void __launch_bounds__(256)
-k_fill_pos(PopView pop, Geometry geo, ClassPrefix cpx, const u64 *stream_off,
-           const u32 *ev_off, const u32 *sv_ukey, const u64 *sv_pre, u64 n_cells, u64 *cell_pos, u32 *cell_evi)
+struct ItemDesc {                // one fan-out work item = (room, tile, chunk of <= NUTSB_UCHUNK recipients)
+    u64 on_src, off_src;         // the tile's two renderings: byte offsets into the slab buffer
+    u32 on_len, off_len;
+    u32 run_begin, run_cnt;      // the item's runs in the run list
+};
+
+// A run, 16 bytes: x,y = destination byte offset in the stream buffer, z = source
+// byte offset in the slab buffer (low 32 bits), w = length (24 bits) | source bits 32..39 << 24.
+__device__ __forceinline__ uint4 nutsb_run_pack(u64 dst, u64 src, u32 len)
 {
+    return make_uint4((u32)dst, (u32)(dst >> 32), (u32)src, (len & 0xffffffu) | ((u32)(src >> 32) << 24));
+}
+#define NUTSB_RUN_MAX_LEN 0xffffffu
+
+struct PlanArgs {
+    PopView pop; Geometry geo; ClassPrefix cpx;
+    const u64 *stream_off;
+    const u32 *ev_off, *sv_ukey; const i32 *sv_delta; const u64 *sv_pre;
+    const u32 *bl_meta;          // per slab op: kind | flags << 8 | clamped target << 16
+    u64 n_cells, off_base;       // off_base: where the colour-off renderings start in the slab buffer
+    u32 has_level;
+    u32 *cell_nruns;             // count pass: out
+    const u64 *run_off;          // fill pass: exclusive scan of cell_nruns, [n_cells+1]
+    uint4 *runs; ItemDesc *items;
+    u64 *counters;               // [0] deliveries
+    u32 *status;
+};
+
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+k_plan(PlanArgs A)
+{
+    __shared__ u32 s_deliv;
+    if (FILL) { if (threadIdx.x == 0) s_deliv = 0; __syncthreads(); }
     const u64 cell = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= n_cells) return;
-    u32 lo = 0, hi = (u32)pop.n_rooms_tot;               // last room with room_cell_off[r] <= cell
-    while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (geo.room_cell_off[mid] <= cell) lo = mid; else hi = mid; }
-    const u32 room = lo;
-    const u32 users_r = (u32)(pop.room_slot_off[room + 1] - pop.room_slot_off[room]);
-    const u64 local = cell - geo.room_cell_off[room];
-    const u32 t = (u32)(local / users_r), ls = (u32)(local % users_r);
-    const u32 s = (u32)pop.room_slot_off[room] + ls;
-    const u32 b0 = geo.room_b_off[room], nb = geo.room_b_off[room + 1] - b0;
-    const u32 tiles = (nb + NUTSB_TILE_OPS - 1) / NUTSB_TILE_OPS;
-    const u32 e0 = ev_off[s], e1 = ev_off[s + 1];
-    if (t >= tiles) { cell_pos[cell] = 0; cell_evi[cell] = e1; return; }      // sentinel row
-    const u32 a0 = t * NUTSB_TILE_OPS, thr = 2 * a0 + 1;
-    u32 l = e0, h = e1;                                   // first event with ukey >= thr
-    while (l < h) { const u32 mid = (l + h) >> 1; if (sv_ukey[mid] < thr) l = mid + 1; else h = mid; }
-    const i32 u = pop.slot_user[s];
-    const i32 k = pop.user_cls[u];
-    cell_pos[cell] = stream_off[u] + (cpx.at(k, room, b0 + a0) - cpx.at(k, room, b0)) + (sv_pre[l] - sv_pre[e0]);
-    cell_evi[cell] = l;
+    u32 deliv = 0;
+    if (cell < A.n_cells) {
+        u32 lo = 0, hi = (u32)A.pop.n_rooms_tot;            // last room with room_cell_off[r] <= cell
+        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (A.geo.room_cell_off[mid] <= cell) lo = mid; else hi = mid; }
+        const u32 room = lo;
+        const u32 slot0 = (u32)A.pop.room_slot_off[room];
+        const u32 users_r = (u32)A.pop.room_slot_off[room + 1] - slot0;
+        const u64 local = cell - A.geo.room_cell_off[room];
+        const u32 t = (u32)(local / users_r), ls = (u32)(local % users_r);
+        const u32 s = slot0 + ls;
+        const u32 b0 = A.geo.room_b_off[room], nb_room = A.geo.room_b_off[room + 1] - b0;
+        const u32 a0 = t * NUTSB_TILE_OPS;                   // room-local slab rank of the tile's first op
+        const u32 nb = nb_room - a0 < NUTSB_TILE_OPS ? nb_room - a0 : NUTSB_TILE_OPS;
+        const u32 g0 = b0 + a0;
+        const u32 e0 = A.ev_off[s], e1 = A.ev_off[s + 1];
+        // the recipient's events inside the tile: keys in [2*a0+1, 2*(a0+nb)]
+        u32 l = e0, h = e1;
+        { const u32 thr = 2 * a0 + 1; while (l < h) { const u32 mid = (l + h) >> 1; if (A.sv_ukey[mid] < thr) l = mid + 1; else h = mid; } }
+        u32 l_end = l; h = e1;
+        { const u32 thr = 2 * (a0 + nb) + 1; while (l_end < h) { const u32 mid = (l_end + h) >> 1; if (A.sv_ukey[mid] < thr) l_end = mid + 1; else h = mid; } }
+        const i32 u = A.pop.slot_user[s];
+        const i32 k = A.pop.user_cls[u];
+        const u32 cf = A.pop.slot_cf[s], clv = A.pop.slot_lv[s];
+        const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
+        const bool full = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
+        const u64 *vp = (colour ? A.cpx.vp_on : A.cpx.vp_off) + g0;      // tile-local prefix of rendered lengths
+        const u64 sb = colour ? 0 : A.off_base;
+        // stream position of the tile's first op: class prefix + the recipient's own events before the tile
+        u64 p = 0;
+        if (FILL) p = A.stream_off[u] + (A.cpx.at(k, room, g0) - A.cpx.at(k, room, b0)) + (A.sv_pre[l] - A.sv_pre[e0]);
+        u64 r_out = FILL ? A.run_off[cell] : 0;
+        u32 nruns = 0;
+        u32 cur = 0;
+        for (u32 e = l; ; ++e) {
+            u32 j = nb; bool excl = false; i32 dlt = 0;
+            if (e < l_end) { const u32 uk = A.sv_ukey[e]; j = (uk >> 1) - a0; excl = (uk & 1) != 0; if (FILL && !excl) dlt = A.sv_delta[e]; }
+            if (full) {
+                if (cur < j) {
+                    const u64 v0 = vp[cur], v1 = vp[j];
+                    deliv += j - cur;                                  // zero-length renderings are deliveries too
+                    if (v1 > v0) {
+                        if (FILL) { A.runs[r_out + nruns] = nutsb_run_pack(p, sb + v0, (u32)(v1 - v0)); p += v1 - v0; }
+                        ++nruns;
+                    }
+                }
+            } else {
+                // behind a filter: op by op, maximal stretches of delivered ops make a run
+                u64 run_dst = 0, run_src = 0; u32 run_len = 0;
+                for (u32 i = cur; i < j; ++i) {
+                    const u32 m = A.bl_meta[g0 + i];
+                    const bool del = nutsb_class_delivers(cf, clv, m & 0xffu, (m >> 8) & 0xffu, (i32)(int16_t)(m >> 16));
+                    if (del) {
+                        const u64 v0 = vp[i]; const u32 len = (u32)(vp[i + 1] - v0);
+                        ++deliv;
+                        if (!run_len) { run_dst = p; run_src = sb + v0; }
+                        run_len += len; p += len;
+                    }
+                    if ((!del || i + 1 == j) && run_len) {
+                        if (FILL) A.runs[r_out + nruns] = nutsb_run_pack(run_dst, run_src, run_len);
+                        ++nruns; run_len = 0;
+                    }
+                }
+            }
+            if (e >= l_end) break;
+            if (excl) cur = j + 1;                            // excluded from op j: nothing emitted for it
+            else { p += (u64)(i64)dlt; cur = j; }             // a direct op's bytes go here (k_direct writes them)
+        }
+        if (!FILL) A.cell_nruns[cell] = nruns;
+        else if (ls % NUTSB_UCHUNK == 0) {
+            const u32 chunks = (users_r + NUTSB_UCHUNK - 1) / NUTSB_UCHUNK;
+            const u32 ls_end = ls + NUTSB_UCHUNK < users_r ? ls + NUTSB_UCHUNK : users_r;
+            const u64 r_end = A.run_off[cell + (ls_end - ls)];
+            ItemDesc d;
+            d.on_src = A.cpx.vp_on[g0]; d.on_len = (u32)(A.cpx.vp_on[g0 + nb] - d.on_src);
+            const u64 o0 = A.cpx.vp_off[g0];
+            d.off_src = A.off_base + o0; d.off_len = (u32)(A.cpx.vp_off[g0 + nb] - o0);
+            d.run_begin = (u32)r_out; d.run_cnt = (u32)(r_end - r_out);
+            A.items[A.geo.room_item_off[room] + t * chunks + ls / NUTSB_UCHUNK] = d;
+        }
+    }
+    if (FILL) {
+        for (int d = 16; d; d >>= 1) deliv += __shfl_xor_sync(NUTSB_FULL, deliv, d);
+        if ((threadIdx.x & 31) == 0 && deliv) atomicAdd(&s_deliv, deliv);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_deliv) nutsb_add64(A.counters, (u64)s_deliv);
+    }
 }
 
 // ---- write_user's byte machine, one thread per string ------------------------------------
@@ -587,9 +699,6 @@ __device__ __forceinline__ u32 nutsb_stage_bytes(const u8 *src, u32 n) { return 
 // realigned in registers from two 16-byte shared loads; the word part of the
 // shift is a template parameter so no selects are executed.  src buffers carry
 // >= 48 bytes of readable padding.
-#ifndef NUTSB_COPY_UNROLL4
-#define NUTSB_COPY_UNROLL4 0
-#endif
 template <int WSH>
 __device__ __forceinline__ uint4 nutsb_realign(const uint4 &a, const uint4 &b, u32 bsh)
 {
@@ -599,39 +708,32 @@ __device__ __forceinline__ uint4 nutsb_realign(const uint4 &a, const uint4 &b, u
     o.z = __funnelshift_r(W[WSH + 2], W[WSH + 3], bsh); o.w = __funnelshift_r(W[WSH + 3], W[WSH + 4], bsh);
     return o;
 }
-template <int WSH>
-__device__ __forceinline__ void nutsb_copy_body(u8 *dst, const uint4 *sa, u32 nvec, u32 bsh, int lane)
+template <int WSH, int WIDTH>
+__device__ __forceinline__ void nutsb_copy_body(u8 *dst, const uint4 *sa, u32 nvec, u32 bsh, int idx)
 {
-    u32 v = (u32)lane;
-#if NUTSB_COPY_UNROLL4
-    for (; v + 96 < nvec; v += 128) {                   // four coalesced 512-byte stores in flight per lane
-        const uint4 a0 = sa[v], b0 = sa[v + 1], a1 = sa[v + 32], b1 = sa[v + 33];
-        const uint4 a2 = sa[v + 64], b2 = sa[v + 65], a3 = sa[v + 96], b3 = sa[v + 97];
+    u32 v = (u32)idx;
+    for (; v + WIDTH < nvec; v += 2 * WIDTH) {          // two coalesced stores in flight per lane
+        const uint4 a0 = sa[v], b0 = sa[v + 1], a1 = sa[v + WIDTH], b1 = sa[v + WIDTH + 1];
         *(uint4 *)(dst + 16 * (size_t)v) = nutsb_realign<WSH>(a0, b0, bsh);
-        *(uint4 *)(dst + 16 * (size_t)(v + 32)) = nutsb_realign<WSH>(a1, b1, bsh);
-        *(uint4 *)(dst + 16 * (size_t)(v + 64)) = nutsb_realign<WSH>(a2, b2, bsh);
-        *(uint4 *)(dst + 16 * (size_t)(v + 96)) = nutsb_realign<WSH>(a3, b3, bsh);
-    }
-#endif
-    for (; v + 32 < nvec; v += 64) {
-        const uint4 a0 = sa[v], b0 = sa[v + 1], a1 = sa[v + 32], b1 = sa[v + 33];
-        *(uint4 *)(dst + 16 * (size_t)v) = nutsb_realign<WSH>(a0, b0, bsh);
-        *(uint4 *)(dst + 16 * (size_t)(v + 32)) = nutsb_realign<WSH>(a1, b1, bsh);
+        *(uint4 *)(dst + 16 * (size_t)(v + WIDTH)) = nutsb_realign<WSH>(a1, b1, bsh);
     }
     if (v < nvec) *(uint4 *)(dst + 16 * (size_t)v) = nutsb_realign<WSH>(sa[v], sa[v + 1], bsh);
 }
 
-__device__ __forceinline__ void nutsb_warp_copy(u8 *dst, const u8 *src, u32 n, int lane)
+// WIDTH threads (a warp, or several warps of one block) copy one run; idx = the thread's
+// index in the group.
+template <int WIDTH>
+__device__ __forceinline__ void nutsb_group_copy(u8 *dst, const u8 *src, u32 n, int idx)
 {
     if (n == 0) return;
     u32 head = (u32)((16 - ((size_t)dst & 15)) & 15);
     if (head > n) head = n;
     const u32 nvec = (n - head) >> 4, tail = (n - head) & 15, toff = head + 16 * nvec;
-    {   // head (lanes 0-15) and tail (lanes 16-31) bytes in one pass
-        const u32 l2 = (u32)lane & 15;
-        const bool is_tail = lane >= 16;
-        const u32 idx = is_tail ? toff + l2 : l2;
-        if (l2 < (is_tail ? tail : head)) dst[idx] = src[idx];
+    if (idx < 32) {   // head (threads 0-15) and tail (threads 16-31) bytes in one pass
+        const u32 l2 = (u32)idx & 15;
+        const bool is_tail = idx >= 16;
+        const u32 at = is_tail ? toff + l2 : l2;
+        if (l2 < (is_tail ? tail : head)) dst[at] = src[at];
     }
     if (nvec == 0) return;
     dst += head; src += head;
@@ -639,403 +741,262 @@ __device__ __forceinline__ void nutsb_warp_copy(u8 *dst, const u8 *src, u32 n, i
     const uint4 *sa = (const uint4 *)(src - sm);
     const u32 bsh = (sm & 3) * 8;
     switch (sm >> 2) {
-    case 0:  nutsb_copy_body<0>(dst, sa, nvec, bsh, lane); break;
-    case 1:  nutsb_copy_body<1>(dst, sa, nvec, bsh, lane); break;
-    case 2:  nutsb_copy_body<2>(dst, sa, nvec, bsh, lane); break;
-    default: nutsb_copy_body<3>(dst, sa, nvec, bsh, lane); break;
+    case 0:  nutsb_copy_body<0, WIDTH>(dst, sa, nvec, bsh, idx); break;
+    case 1:  nutsb_copy_body<1, WIDTH>(dst, sa, nvec, bsh, idx); break;
+    case 2:  nutsb_copy_body<2, WIDTH>(dst, sa, nvec, bsh, idx); break;
+    default: nutsb_copy_body<3, WIDTH>(dst, sa, nvec, bsh, idx); break;
     }
 }
+__device__ __forceinline__ void nutsb_warp_copy(u8 *dst, const u8 *src, u32 n, int lane) { nutsb_group_copy<32>(dst, src, n, lane); }
 
-// ---- H. render + fan-out ----------------------------------------------------------------
-// One work item = (room, tile of <=64 slab ops, chunk of <=128 recipients).
-// The block stages the tile's source strings in shared memory, renders each once
-// (one thread per op, both colour settings in one pass: the byte machine is
-// sequential, shared -> shared), prefetches the chunk's per-recipient cells, then
-// every warp takes recipients in turn and copies that recipient's view of the
-// tile -- normally ONE contiguous run of the rendered slab, cut only where the
-// recipient is the excluded speaker or has a direct write_user op in between --
-// to its place in the user's stream.
-struct FanoutArgs {
-    OpsView ops; PopView pop; Geometry geo; ClassPrefix cpx;
-    const u32 *bl_op;
-    const u32 *len_on, *len_off;
-    const u64 *cell_pos; const u32 *cell_evi;
-    const u32 *sv_ukey; const i32 *sv_delta;
-    u8 *out;
-    u64 *n_deliveries;           // [0] deliveries, [1] (k_direct), [2] source bytes staged (once per tile)
+// ---- G. render the slab ---------------------------------------------------------------------
+// Every slab op is rendered ONCE per colour setting (the reference renders it once
+// per recipient, c:1427 -> c:1315) into the slab buffer: the colour-on rendering of
+// slab rank g at slab + vp_on[g], the colour-off one at slab + off_base + vp_off[g].
+//
+// write_user's byte machine (c:1315-1365) is position-local: what
+// byte i emits depends on bytes i-3..i+2 only.  So a warp takes NUTSB_REN_OPS
+// consecutive slab ops as ONE flat array of aligned 32-bit words and renders 32
+// words per round, lane = word, whatever the string lengths: every lane classifies
+// its four bytes, a warp scan of the emitted lengths places them, and the bytes go
+// into the warp's private shared-memory windows, flushed to the slab with 16-byte
+// stores whenever a window could overflow in the next round.  No text staging: a
+// lane reads its word and the two neighbouring words straight from the packed text
+// (consecutive lanes read consecutive words of the same string).
+#define NUTSB_REN_THREADS 256
+#define NUTSB_REN_OPS     16                       // slab ops per warp (<= 32)
+#define NUTSB_REN_ON_WIN  3072                     // per-warp window, colour on  (a round emits <= 32*28 bytes)
+#define NUTSB_REN_OFF_WIN 1536                     // per-warp window, colour off (a round emits <= 32*8 bytes)
+#define NUTSB_REN_ON_ROUND  (32 * 28)
+#define NUTSB_REN_OFF_ROUND (32 * 8)
+
+struct RenderArgs {
+    OpsView ops; const u8 *codetab;
+    const u32 *bl_op; const u64 *vp_on, *vp_off;
+    const u32 *n_slab;
+    u8 *slab; u64 off_base;
+    u64 *counters;               // [2] source bytes read
     u32 *status;
-    u32 has_level;
 };
 
-#define NUTSB_FAN_THREADS (2 * NUTSB_TILE_OPS)
-// -DNUTSB_FAN_PROFILE=1: thread 0 of every block adds the cycles it spent in each phase to
-// counters[3..7] (setup, stage, render+plan, copy, barrier at the end of copy) -- a development aid
-#ifndef NUTSB_FAN_PROFILE
-#define NUTSB_FAN_PROFILE 0
-#endif
-#if NUTSB_FAN_PROFILE && !defined(NUTSB_CPUSIM)
-#define NUTSB_PHASE(slot) do { if (tid == 0) { const long long t_ = clock64(); nutsb_add64(A.n_deliveries + (slot), (u64)(t_ - t_prev)); t_prev = t_; } } while (0)
-#else
-#define NUTSB_PHASE(slot) do { } while (0)
-#endif
-#ifndef NUTSB_FAN_TMA
-#define NUTSB_FAN_TMA 0          // 1: copy runs with TMA bulk stores from 16 pre-shifted slab pieces (measured slower: DESIGN.md 4.1)
-#endif
-#ifndef NUTSB_FAN_PIECE
-#define NUTSB_FAN_PIECE 2048     // slab bytes per TMA staging round (multiple of 512)
-#endif
-#ifndef NUTSB_FAN_DB
-#define NUTSB_FAN_DB 1           // two staging areas: the next piece is built while the TMA reads this one
-#endif
-#define NUTSB_FAN_STAGE (NUTSB_FAN_TMA ? (NUTSB_FAN_DB ? 2 : 1) * 16 * NUTSB_FAN_PIECE : 0)
-#define NUTSB_FAN_SMEM (NUTSB_TEXT_CAP + 32 + NUTSB_ON_CAP + 64 + NUTSB_OFF_CAP + 64 + NUTSB_FAN_STAGE)
-static_assert(NUTSB_FAN_THREADS == 2 * NUTSB_TILE_OPS && (NUTSB_TILE_OPS & (NUTSB_TILE_OPS - 1)) == 0 &&
-              NUTSB_UCHUNK <= NUTSB_FAN_THREADS / 2, "k_fanout thread mapping");
+// 0xff in byte k of the result iff lo <= wb + k < hi (window byte coordinates)
+__device__ __forceinline__ u32 nutsb_keep_mask(i32 wb, i32 lo, i32 hi)
+{
+    i32 dl = lo - wb; dl = dl < 0 ? 0 : dl;
+    i32 dh = wb + 4 - hi; dh = dh < 0 ? 0 : dh;
+    const u32 a = dl >= 4 ? 0u : 0xffffffffu << (8 * dl);
+    const u32 b = dh >= 4 ? 0u : 0xffffffffu >> (8 * dh);
+    return a & b;
+}
 
-__global__ void __launch_bounds__(NUTSB_FAN_THREADS)
+// Context of one lane: pv | x | nx = window words wi-1, wi, wi+1 with every byte outside
+// the string zeroed.  NUTSB_CTX(j), j in [-3, 5], is the byte j positions from x's byte 0.
+#define NUTSB_CTX(j) ((j) < 0 ? (pv >> (8 * (((j) + 4) & 3))) & 0xffu : (j) < 4 ? (x >> (8 * ((j) & 3))) & 0xffu : (nx >> (8 * (((j) - 4) & 3))) & 0xffu)
+
+// What position k of the lane's word emits (SURVEY.md A.1's table).  on_len/off_len in
+// bytes; von = the colour-on bytes, little-endian; the colour-off bytes are "\n\r"
+// (off_len 2) or the byte itself (off_len 1).
+#define NUTSB_CLASSIFY(k, valid, colour, on_len, off_len, von)                                               \
+    do {                                                                                                     \
+        const u32 c_ = NUTSB_CTX(k);                                                                         \
+        on_len = 0; off_len = 0; von = c_;                                                                   \
+        if (valid) {                                                                                         \
+            on_len = 1; off_len = 1;                                                                         \
+            if (c_ == '\n') {                                                   /* c:1316-1326 */            \
+                off_len = 2;                                                                                 \
+                if (colour) { on_len = 6; von = NUTSB_RESET_PACK | ((u64)'\n' << 32) | ((u64)'\r' << 40); }   \
+                else { on_len = 2; von = (u64)((u32)'\n' | ((u32)'\r' << 8)); }                               \
+            } else if (c_ == '/') {                                             /* c:1330 */                 \
+                if (NUTSB_CTX((k) + 1) == '~') { on_len = 0; off_len = 0; }                                  \
+            } else if (c_ == '~') {                                             /* c:1331-1354 */            \
+                if (NUTSB_CTX((k) - 1) != '/') {                                                             \
+                    const int kk_ = nutsb_code(tab, (u8)NUTSB_CTX((k) + 1), (u8)NUTSB_CTX((k) + 2));         \
+                    if (kk_ >= 0) { off_len = 0; on_len = colour ? nutsb_code_len(kk_) : 0u; von = nutsb_code_pack(kk_); } \
+                }                                                                                            \
+            } else if (c_ - 'A' < 26u) {                                        /* a command's two letters */ \
+                const bool m1_ = NUTSB_CTX((k) - 1) == '~' && NUTSB_CTX((k) - 2) != '/' &&                   \
+                                 nutsb_code(tab, (u8)c_, (u8)NUTSB_CTX((k) + 1)) >= 0;                       \
+                const bool m2_ = NUTSB_CTX((k) - 2) == '~' && NUTSB_CTX((k) - 3) != '/' &&                   \
+                                 nutsb_code(tab, (u8)NUTSB_CTX((k) - 1), (u8)c_) >= 0;                       \
+                if (m1_ || m2_) { on_len = 0; off_len = 0; }                                                 \
+            }                                                                                                \
+        }                                                                                                    \
+    } while (0)
+
+#define NUTSB_EMIT_ON(d, len, v)                                                                             \
+    do {                                                                                                     \
+        if (len > 0) (d)[0] = (u8)(v);                                                                       \
+        if (len > 1) (d)[1] = (u8)((v) >> 8);                                                                \
+        if (len > 2) (d)[2] = (u8)((v) >> 16);                                                               \
+        if (len > 3) (d)[3] = (u8)((v) >> 24);                                                               \
+        if (len > 4) (d)[4] = (u8)((v) >> 32);                                                               \
+        if (len > 5) (d)[5] = (u8)((v) >> 40);                                                               \
+        (d) += len;                                                                                          \
+    } while (0)
+#define NUTSB_EMIT_OFF(d, len, c)                                                                            \
+    do {                                                                                                     \
+        if (len > 0) (d)[0] = len == 2 ? (u8)'\n' : (u8)(c);                                                 \
+        if (len > 1) (d)[1] = (u8)'\r';                                                                      \
+        (d) += len;                                                                                          \
+    } while (0)
+
+__global__ void __launch_bounds__(NUTSB_REN_THREADS)
+k_render(RenderArgs A)
+{
+    __shared__ __align__(16) u8 s_on[NUTSB_REN_THREADS / 32][NUTSB_REN_ON_WIN + 64];
+    __shared__ __align__(16) u8 s_off[NUTSB_REN_THREADS / 32][NUTSB_REN_OFF_WIN + 64];
+    __shared__ u8 s_tab[NUTSB_CODETAB_BYTES];
+    for (int i = threadIdx.x; i < NUTSB_CODETAB_BYTES; i += NUTSB_REN_THREADS) s_tab[i] = A.codetab[i];
+    __syncthreads();
+    const u8 *const tab = s_tab;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 n_slab = *A.n_slab;
+    const u32 gbase = (blockIdx.x * (NUTSB_REN_THREADS / 32) + (u32)warp) * NUTSB_REN_OPS;
+    if (gbase >= n_slab) return;                               // whole warp leaves together
+    const u32 cnt = n_slab - gbase < NUTSB_REN_OPS ? n_slab - gbase : NUTSB_REN_OPS;
+
+    // -- lane q < cnt holds op q: window = the aligned words that hold the string
+    u32 al = 0, n = 0, fl = 0, nw = 0; u64 gw = 0;
+    if ((u32)lane < cnt) {
+        const u32 op = A.bl_op[gbase + lane];
+        const u64 t0 = A.ops.toff[op];
+        n = (u32)(A.ops.toff[op + 1] - t0);
+        const u8 *src = A.ops.text + t0;
+        al = (u32)((size_t)src & 3);
+        gw = (u64)(size_t)(src - al);
+        nw = (al + n + 3) >> 2; if (!nw) nw = 1;                // an empty string still ends in a reset (c:1365)
+        fl = A.ops.flags[op];
+    }
+    u32 inc = nw;
+    for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(NUTSB_FULL, inc, d); if (lane >= d) inc += t; }
+    const u32 P = inc - nw;                                    // first flat word of op q
+    const u32 W = __shfl_sync(NUTSB_FULL, inc, 31);
+    const u64 on0 = A.vp_on[gbase], off0 = A.vp_off[gbase];
+    u8 *g_on = A.slab + on0, *g_off = A.slab + A.off_base + off0;
+    u8 *const w_on = s_on[warp], *const w_off = s_off[warp];
+    u32 fill_on = 0, fill_off = 0, qcount = 0;
+
+    for (u32 F = 0; F < W; F += 32) {
+        // -- which op does flat word F + lane belong to
+        const bool starts = (u32)lane < cnt && P >= F && P < F + 32;
+        const u32 heads = __reduce_or_sync(NUTSB_FULL, starts ? 1u << (P - F) : 0u);
+        u32 q = qcount + (u32)__popc(heads & (0xffffffffu >> (31 - lane))) - 1;
+        qcount += (u32)__popc(heads);
+        if (q >= cnt) q = cnt - 1;
+        const u32 Pq = __shfl_sync(NUTSB_FULL, P, (int)q), alq = __shfl_sync(NUTSB_FULL, al, (int)q);
+        const u32 nq = __shfl_sync(NUTSB_FULL, n, (int)q), flq = __shfl_sync(NUTSB_FULL, fl, (int)q);
+        const u32 nwq = __shfl_sync(NUTSB_FULL, nw, (int)q);
+        const u32 *gwq = (const u32 *)(size_t)__shfl_sync(NUTSB_FULL, gw, (int)q);
+        const bool act = F + lane < W;
+        const u32 wi = F + lane - Pq;
+        u32 x = 0, pv = 0, nx = 0;
+        const i32 lo = (i32)alq, hi = (i32)(alq + nq);
+        if (act) {
+            x = __ldg(gwq + wi) & nutsb_keep_mask((i32)(4 * wi), lo, hi);
+            if (wi > 0) pv = __ldg(gwq + wi - 1) & nutsb_keep_mask((i32)(4 * wi) - 4, lo, hi);
+            if (wi + 1 < nwq) nx = __ldg(gwq + wi + 1) & nutsb_keep_mask((i32)(4 * wi) + 4, lo, hi);
+        }
+        const bool colour = !(flq & NUTSB_OF_PLAIN);                        // more(NULL,...): c:2259
+        const bool tail = act && wi == nwq - 1 && colour && !(flq & NUTSB_OF_PAGER);   // c:1365; the pager has no such reset
+        const u32 vm = act ? nutsb_keep_mask((i32)(4 * wi), lo, hi) : 0u;
+        u32 on0_, on1_, on2_, on3_, of0_, of1_, of2_, of3_; u64 v0_, v1_, v2_, v3_;
+        NUTSB_CLASSIFY(0, (vm & 0xffu) != 0, colour, on0_, of0_, v0_);
+        NUTSB_CLASSIFY(1, (vm & 0xff00u) != 0, colour, on1_, of1_, v1_);
+        NUTSB_CLASSIFY(2, (vm & 0xff0000u) != 0, colour, on2_, of2_, v2_);
+        NUTSB_CLASSIFY(3, (vm & 0xff000000u) != 0, colour, on3_, of3_, v3_);
+        const u32 t_on = on0_ + on1_ + on2_ + on3_ + (tail ? 4u : 0u), t_off = of0_ + of1_ + of2_ + of3_;
+        u32 sc = t_on | (t_off << 16);
+        for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(NUTSB_FULL, sc, d); if (lane >= d) sc += t; }
+        const u32 tot = __shfl_sync(NUTSB_FULL, sc, 31);
+        {
+            u8 *d = w_on + fill_on + (sc & 0xffffu) - t_on;
+            NUTSB_EMIT_ON(d, on0_, v0_); NUTSB_EMIT_ON(d, on1_, v1_); NUTSB_EMIT_ON(d, on2_, v2_); NUTSB_EMIT_ON(d, on3_, v3_);
+            if (tail) { d[0] = 0x1b; d[1] = '['; d[2] = '0'; d[3] = 'm'; }
+            u8 *e = w_off + fill_off + (sc >> 16) - t_off;
+            NUTSB_EMIT_OFF(e, of0_, v0_); NUTSB_EMIT_OFF(e, of1_, v1_); NUTSB_EMIT_OFF(e, of2_, v2_); NUTSB_EMIT_OFF(e, of3_, v3_);
+        }
+        fill_on += tot & 0xffffu; fill_off += tot >> 16;
+        const bool last = F + 32 >= W;
+        if (last || fill_on + NUTSB_REN_ON_ROUND > NUTSB_REN_ON_WIN) {
+            __syncwarp();
+            nutsb_warp_copy(g_on, w_on, fill_on, lane);
+            g_on += fill_on; fill_on = 0;
+            __syncwarp();
+        }
+        if (last || fill_off + NUTSB_REN_OFF_ROUND > NUTSB_REN_OFF_WIN) {
+            __syncwarp();
+            nutsb_warp_copy(g_off, w_off, fill_off, lane);
+            g_off += fill_off; fill_off = 0;
+            __syncwarp();
+        }
+    }
+    // -- consistency with k_measure's lengths; bytes read
+    if (lane == 0) {
+        if ((u64)(g_on - A.slab) != A.vp_on[gbase + cnt] || (u64)(g_off - A.slab) != A.off_base + A.vp_off[gbase + cnt])
+            atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+    }
+    u32 nsum = n;
+    for (int d = 16; d; d >>= 1) nsum += __shfl_xor_sync(NUTSB_FULL, nsum, d);
+    if (lane == 0) nutsb_add64(A.counters + 2, (u64)nsum);
+}
+
+// ---- H. fan-out -------------------------------------------------------------------------------
+// The kernel that moves the bytes, and nothing else: one block per work item
+// (room, tile, chunk of recipients).  It loads the tile's two renderings from the
+// slab buffer into shared memory (contiguous, 16-byte loads), loads the item's runs,
+// and its warps copy run after run to the recipients' streams with nutsb_warp_copy
+// (coalesced 16-byte stores at whatever byte alignment the stream position has).
+// A tile whose renderings exceed the shared-memory windows (strings of many hundred
+// bytes) is copied slab -> stream directly, same routine, global source.
+#ifndef NUTSB_FAN_THREADS
+#define NUTSB_FAN_THREADS 256
+#endif
+#ifndef NUTSB_FAN_MINBLOCKS
+#define NUTSB_FAN_MINBLOCKS 5
+#endif
+#ifndef NUTSB_FAN_GROUP
+#define NUTSB_FAN_GROUP 1                          // warps that copy one run together
+#endif
+#define NUTSB_FAN_SMEM (NUTSB_FAN_ON_CAP + 80 + NUTSB_FAN_OFF_CAP + 80 + 16 * NUTSB_FAN_RUN_CAP)
+
+struct FanoutArgs {
+    const ItemDesc *items; const uint4 *runs;
+    const u8 *slab; u64 off_base;
+    u8 *out;
+};
+
+__global__ void __launch_bounds__(NUTSB_FAN_THREADS, NUTSB_FAN_MINBLOCKS)
 k_fanout(FanoutArgs A)
 {
-    NUTSB_DYN_SMEM(s_dyn);                       // NUTSB_FAN_SMEM bytes: staged source + the two rendered slabs
-    u8 *const s_text = s_dyn;
-    u8 *const s_on = s_dyn + NUTSB_TEXT_CAP + 32;
-    u8 *const s_off = s_on + NUTSB_ON_CAP + 64;
-    __shared__ u8  s_tab[NUTSB_CODETAB_BYTES];
-    __shared__ u64 s_src[NUTSB_TILE_OPS];        // byte offset of each string in the packed text
-    __shared__ u32 s_tlen[NUTSB_TILE_OPS];
-    __shared__ u32 s_toff[NUTSB_TILE_OPS + 1];   // prefix of staged (word-aligned) sizes
-    __shared__ u32 s_oon[NUTSB_TILE_OPS + 1];
-    __shared__ u32 s_ooff[NUTSB_TILE_OPS + 1];
-    __shared__ u8  s_kind[NUTSB_TILE_OPS];
-    __shared__ u8  s_flags[NUTSB_TILE_OPS];
-    __shared__ i32 s_target[NUTSB_TILE_OPS];
-    __shared__ u64 s_upos[NUTSB_UCHUNK];         // per recipient of the chunk
-    __shared__ u32 s_uev0[NUTSB_UCHUNK], s_uev1[NUTSB_UCHUNK], s_uevb[NUTSB_UCHUNK];
-    __shared__ u8  s_ucf[NUTSB_UCHUNK], s_ulv[NUTSB_UCHUNK];
-    __shared__ u32 s_evk[NUTSB_EV_CAP];          // the chunk's events inside this tile
-    __shared__ i32 s_evd[NUTSB_EV_CAP];
-    __shared__ u32 s_evn;
-    __shared__ uint4 s_run[NUTSB_RUN_CAP];       // planned copy runs of the current (sub)tile:
-                                                 // x,y = destination byte offset, z = slab offset | colour<<31, w = length
-    __shared__ u8  s_ulegacy[NUTSB_UCHUNK];
-    __shared__ u32 s_nruns;
-    __shared__ u32 s_sub_b;
-    __shared__ u32 s_room;
-    __shared__ u32 s_deliv;
-
+    NUTSB_DYN_SMEM(s_dyn);
+    u8 *const s_on = s_dyn;
+    u8 *const s_off = s_dyn + NUTSB_FAN_ON_CAP + 80;
+    uint4 *const s_run = (uint4 *)(s_dyn + NUTSB_FAN_ON_CAP + 80 + NUTSB_FAN_OFF_CAP + 80);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#if NUTSB_FAN_PROFILE && !defined(NUTSB_CPUSIM)
-    long long t_prev = clock64();
-#endif
-
-    // -- decode the work item
-    if (tid == 0) {
-        const u32 item = blockIdx.x;
-        u32 lo = 0, hi = (u32)A.pop.n_rooms_tot;        // last r with room_item_off[r] <= item
-        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (A.geo.room_item_off[mid] <= item) lo = mid; else hi = mid; }
-        s_room = lo; s_deliv = 0; s_evn = 0;
+    const ItemDesc d = A.items[blockIdx.x];
+    const bool staged = d.on_len <= NUTSB_FAN_ON_CAP && d.off_len <= NUTSB_FAN_OFF_CAP;
+    const u32 a_on = (u32)(d.on_src & 15), a_off = (u32)(d.off_src & 15);
+    if (staged) {
+        const uint4 *g = (const uint4 *)(A.slab + (d.on_src - a_on));
+        for (u32 v = (u32)tid, nv = (a_on + d.on_len + 15) >> 4; v < nv; v += NUTSB_FAN_THREADS) ((uint4 *)s_on)[v] = __ldg(g + v);
+        g = (const uint4 *)(A.slab + (d.off_src - a_off));
+        for (u32 v = (u32)tid, nv = (a_off + d.off_len + 15) >> 4; v < nv; v += NUTSB_FAN_THREADS) ((uint4 *)s_off)[v] = __ldg(g + v);
     }
-    for (int i = tid; i < NUTSB_CODETAB_BYTES; i += NUTSB_FAN_THREADS) s_tab[i] = A.pop.codetab[i];
-    __syncthreads();
-    const u32 room = s_room;
-    const u32 slot0 = (u32)A.pop.room_slot_off[room];
-    const u32 users_r = (u32)A.pop.room_slot_off[room + 1] - slot0;
-    const u32 chunks = (users_r + NUTSB_UCHUNK - 1) / NUTSB_UCHUNK;
-    const u32 local = blockIdx.x - A.geo.room_item_off[room];
-    const u32 t = local / chunks, chunk = local % chunks;
-    const u32 rb0 = A.geo.room_b_off[room];
-    const u32 g0 = rb0 + t * NUTSB_TILE_OPS;
-    const u32 gend = A.geo.room_b_off[room + 1];
-    const u32 nb = (gend - g0 < NUTSB_TILE_OPS) ? gend - g0 : NUTSB_TILE_OPS;
-    const u32 a0 = t * NUTSB_TILE_OPS;                  // room-local slab rank of the tile's first op
-    const u32 ls_begin = chunk * NUTSB_UCHUNK;
-    const u32 ls_end = (ls_begin + NUTSB_UCHUNK < users_r) ? ls_begin + NUTSB_UCHUNK : users_r;
-    const u64 cell_row = A.geo.room_cell_off[room] + (u64)t * users_r;
-
-    // -- per-op metadata (threads 0..128) and per-recipient cells + events (threads 128..255)
-    if ((u32)tid < nb) {
-        const u32 op = A.bl_op[g0 + tid];
-        const u64 t0 = A.ops.toff[op];
-        s_src[tid] = t0; s_tlen[tid] = (u32)(A.ops.toff[op + 1] - t0);
-        s_kind[tid] = A.ops.kind[op]; s_flags[tid] = A.ops.flags[op]; s_target[tid] = A.ops.target[op];
-    }
-    if ((u32)tid <= nb) {
-        s_oon[tid]  = (u32)(A.cpx.vp_on[g0 + tid]  - A.cpx.vp_on[g0]);
-        s_ooff[tid] = (u32)(A.cpx.vp_off[g0 + tid] - A.cpx.vp_off[g0]);
-    }
-    if (tid >= NUTSB_FAN_THREADS - NUTSB_UCHUNK) {
-        const u32 q = (u32)tid - (NUTSB_FAN_THREADS - NUTSB_UCHUNK);
-        const u32 ls = ls_begin + q;
-        if (ls < ls_end) {
-            const u32 e0 = A.cell_evi[cell_row + ls], e1 = A.cell_evi[cell_row + users_r + ls];
-            s_upos[q] = A.cell_pos[cell_row + ls];
-            s_uev0[q] = e0; s_uev1[q] = e1;
-            s_ucf[q] = A.pop.slot_cf[slot0 + ls];
-            s_ulv[q] = A.pop.slot_lv[slot0 + ls];
-            u32 base = 0xffffffffu;
-            if (e1 > e0) {
-                const u32 cnt = e1 - e0;
-                const u32 got = atomicAdd(&s_evn, cnt);
-                if (got + cnt <= NUTSB_EV_CAP) {
-                    base = got;
-                    for (u32 j = 0; j < cnt; ++j) { s_evk[base + j] = A.sv_ukey[e0 + j]; s_evd[base + j] = A.sv_delta[e0 + j]; }
-                }
-            }
-            s_uevb[q] = base;
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {                                     // prefix of the staged sizes
-        u32 carry = 0;
-        for (u32 base = 0; base < NUTSB_TILE_OPS; base += 32) {
-            const u32 i = base + lane;
-            const u32 v = i < nb ? nutsb_stage_bytes(A.ops.text + s_src[i], s_tlen[i]) : 0;
-            u32 inc = v;
-            for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(NUTSB_FULL, inc, d); if (lane >= d) inc += x; }
-            if (i < nb) s_toff[i] = carry + inc - v;
-            carry += __shfl_sync(NUTSB_FULL, inc, 31);
-        }
-        if (lane == 0) s_toff[nb] = carry;
-    }
-    __syncthreads();
-
-    NUTSB_PHASE(3);
-    u32 my_deliv = 0;
-    u32 a = 0;
-    while (a < nb) {
-        // -- largest sub-tile [a,b) whose source and both renderings fit in shared memory
-        if (tid == 0) {
-            u32 b = nb;
-            if (s_toff[nb] - s_toff[a] > NUTSB_TEXT_CAP || s_oon[nb] - s_oon[a] > NUTSB_ON_CAP ||
-                s_ooff[nb] - s_ooff[a] > NUTSB_OFF_CAP) {
-                b = a + 1;
-                while (b < nb && s_toff[b + 1] - s_toff[a] <= NUTSB_TEXT_CAP &&
-                       s_oon[b + 1] - s_oon[a] <= NUTSB_ON_CAP && s_ooff[b + 1] - s_ooff[a] <= NUTSB_OFF_CAP) ++b;
-            }
-            s_sub_b = b; s_nruns = 0;
-        }
+    for (u32 r0 = 0; r0 < d.run_cnt; r0 += NUTSB_FAN_RUN_CAP) {
+        const u32 nr = d.run_cnt - r0 < NUTSB_FAN_RUN_CAP ? d.run_cnt - r0 : NUTSB_FAN_RUN_CAP;
+        if (r0) __syncthreads();                               // the previous batch has been consumed
+        for (u32 r = (u32)tid; r < nr; r += NUTSB_FAN_THREADS) s_run[r] = __ldg(A.runs + d.run_begin + r0 + r);
         __syncthreads();
-        const u32 b = s_sub_b;
-
-        // -- stage: two threads per op (tid and tid+128) copy alternate 32-bit words
-        {
-            const u32 i = a + ((u32)tid & (NUTSB_TILE_OPS - 1));
-            if (i < b) {
-                const u8 *src = A.ops.text + s_src[i];
-                const u32 al = (u32)((size_t)src & 3);
-                const u32 *g = (const u32 *)(src - al);
-                const u32 nw = (al + s_tlen[i] + 3) >> 2;
-                u32 *win = (u32 *)(s_text + (s_toff[i] - s_toff[a]));
-                for (u32 w = (u32)tid / NUTSB_TILE_OPS; w < nw; w += 2) win[w] = __ldg(g + w);
-            }
-        }
-        __syncthreads();
-        NUTSB_PHASE(4);
-        // -- render: threads 0..127 run the byte machine for colour-on recipients, threads
-        //    128..255 for colour-off ones (the setting is uniform per warp)
-        {
-            const u32 i = a + ((u32)tid & (NUTSB_TILE_OPS - 1));
-            const bool on = tid < NUTSB_TILE_OPS;
-            if (i < b) {
-                const u8 *src = A.ops.text + s_src[i];
-                const u8 *str = s_text + (s_toff[i] - s_toff[a]) + ((u32)(size_t)src & 3u);
-                const u32 *offc = on ? s_oon : s_ooff;
-                const u32 got = nutsb_render1(str, s_tlen[i], on, s_flags[i], (on ? s_on : s_off) + (offc[i] - offc[a]), s_tab);
-                if (got != offc[i + 1] - offc[i]) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
-            }
-        }
-
-        // -- plan: one thread per recipient walks the recipient's events inside the tile and
-        //    queues its copy runs (destination, slab offset, length).  Needs only the
-        //    offsets, not the rendered bytes, so it runs before the barrier.
-        if ((u32)tid < ls_end - ls_begin) {
-            const u32 q = (u32)tid;
-            const u32 cf = s_ucf[q];
-            const bool full = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
-            bool legacy = !full;
-            if (full) {
-                const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
-                const u32 *offc = colour ? s_oon : s_ooff;
-                u64 p = s_upos[q];
-                const u32 e0 = s_uev0[q], e1 = s_uev1[q], evb = s_uevb[q];
-                u32 e = e0, cur = 0, deliv = 0;
-                for (;;) {
-                    u32 j = nb, ek = 0; i32 dlt = 0;
-                    if (e < e1) {
-                        const u32 uk = evb != 0xffffffffu ? s_evk[evb + (e - e0)] : A.sv_ukey[e];
-                        const u32 jj = (uk >> 1) - a0;
-                        if (jj < nb || (jj == nb && !(uk & 1))) {
-                            j = jj; ek = (uk & 1) ? 2 : 1;
-                            dlt = evb != 0xffffffffu ? s_evd[evb + (e - e0)] : A.sv_delta[e];
-                        }
-                    }
-                    const u32 xs = cur > a ? cur : a, ye = j < b ? j : b;
-                    if (xs < ye && offc[ye] != offc[xs]) {
-                        const u32 r = atomicAdd(&s_nruns, 1u);
-                        if (r < NUTSB_RUN_CAP) {
-                            const u64 d = p + (offc[xs] - offc[cur]);
-                            s_run[r] = make_uint4((u32)d, (u32)(d >> 32), (offc[xs] - offc[a]) | (colour ? 0x80000000u : 0u),
-                                                  offc[ye] - offc[xs]);
-                            deliv += ye - xs;
-                        } else legacy = true;              // queue full: this recipient goes the slow way
-                    } else if (xs < ye) deliv += ye - xs;      // zero-length renderings still count as deliveries
-                    p += offc[j] - offc[cur];
-                    if (!ek) break;
-                    if (ek == 2) cur = j + 1; else { p += (u64)(i64)dlt; cur = j; }
-                    ++e;
-                }
-                if (!legacy && deliv) atomicAdd(&s_deliv, deliv);
-            }
-            s_ulegacy[q] = legacy ? 1 : 0;
-        }
-        NUTSB_PHASE(5);                 // thread 0's own render + plan
-        __syncthreads();
-        NUTSB_PHASE(6);                 // waiting for the slowest renderer
-
-#if NUTSB_FAN_TMA
-        // -- copy with the TMA: a run's destination is byte-aligned, a bulk copy wants 16-byte
-        //    aligned source, destination and size.  So: (1) every run's head and tail (< 16
-        //    bytes each) are stored byte-wise by one thread per run; (2) the slab is taken a
-        //    piece at a time; each piece is written 16 times into a staging area, copy r
-        //    shifted left by r bytes, so whatever (source - destination) mod 16 a run has,
-        //    there is a copy in which its body is 16-byte aligned; (3) one thread per run
-        //    issues the body as one bulk store per piece; the SM moves no body bytes itself.
-        {
-            const u32 nruns = s_nruns < NUTSB_RUN_CAP ? s_nruns : NUTSB_RUN_CAP;
-            u8 *const s_stg0 = s_off + NUTSB_OFF_CAP + 64;
-            u32 round = 0;
-            for (u32 r = (u32)tid; r < nruns; r += NUTSB_FAN_THREADS) {
-                const uint4 run = s_run[r];
-                const u32 so = run.z, len = run.w;
-                const u8 *src = ((so >> 31) ? s_on : s_off) + (so & 0x7fffffffu);
-                u8 *dst = A.out + (((u64)run.y << 32) | run.x);
-                u32 head = (u32)((16 - ((size_t)dst & 15)) & 15);
-                if (head > len) head = len;
-                for (u32 q = 0; q < head; ++q) dst[q] = src[q];
-                for (u32 q = head + ((len - head) & ~15u); q < len; ++q) dst[q] = src[q];
-            }
-            bool issued = false;
-            for (int colour = 1; colour >= 0; --colour) {
-                const u8 *slab = colour ? s_on : s_off;
-                const u32 L = colour ? s_oon[b] - s_oon[a] : s_ooff[b] - s_ooff[a];
-                for (u32 P0 = 0; P0 < L; P0 += NUTSB_FAN_PIECE, ++round) {
-                    u8 *const s_stg = s_stg0 + (NUTSB_FAN_DB ? (round & 1) * 16 * NUTSB_FAN_PIECE : 0);
-                    // (2) the 16 shifted copies of this piece: copy r holds slab[P0+r .. P0+r+PIECE)
-                    for (u32 idx = (u32)tid; idx < NUTSB_FAN_PIECE; idx += NUTSB_FAN_THREADS) {
-                        const u32 r = idx / (NUTSB_FAN_PIECE / 16), v = idx % (NUTSB_FAN_PIECE / 16);   // r is uniform per warp
-                        if (P0 + r + 16 * v >= L) continue;
-                        const uint4 *sa = (const uint4 *)(slab + P0) + v;
-                        const uint4 x = sa[0], y = sa[1];
-                        const u32 bsh = (r & 3) * 8;
-                        uint4 o;
-                        switch (r >> 2) {
-                        case 0:  o = nutsb_realign<0>(x, y, bsh); break;
-                        case 1:  o = nutsb_realign<1>(x, y, bsh); break;
-                        case 2:  o = nutsb_realign<2>(x, y, bsh); break;
-                        default: o = nutsb_realign<3>(x, y, bsh); break;
-                        }
-                        ((uint4 *)(s_stg + r * NUTSB_FAN_PIECE))[v] = o;
-                    }
-                    nutsb_fence_async_smem();
-                    __syncthreads();
-                    // (3) bodies: one bulk store per (run, piece)
-                    for (u32 q = (u32)tid; q < nruns; q += NUTSB_FAN_THREADS) {
-                        const uint4 run = s_run[q];
-                        const u32 so = run.z;
-                        if ((int)(so >> 31) != colour) continue;
-                        const u32 S = so & 0x7fffffffu, len = run.w;
-                        const u64 D = ((u64)run.y << 32) | run.x;
-                        u32 head = (u32)((16 - (((size_t)A.out + D) & 15)) & 15);
-                        if (head > len) head = len;
-                        const u32 nvec = (len - head) >> 4;
-                        if (!nvec) continue;
-                        const u32 Sp = S + head, r = Sp & 15;             // slab bases are 16-byte aligned
-                        const u32 lo = P0 + r, hi = lo + NUTSB_FAN_PIECE;
-                        const u32 x0 = Sp > lo ? Sp : lo, x1 = Sp + 16 * nvec < hi ? Sp + 16 * nvec : hi;
-                        if (x1 > x0) {
-                            nutsb_bulk_s2g(A.out + D + head + (x0 - Sp), s_stg + r * NUTSB_FAN_PIECE + (x0 - lo), x1 - x0);
-                            issued = true;
-                        }
-                    }
-                    nutsb_bulk_commit();
-                    if (NUTSB_FAN_DB) nutsb_bulk_wait_read1();   // the other staging area is free again
-                    else nutsb_bulk_wait_read();                  // the staging area is rewritten by the next round
-                    __syncthreads();
-                }
-            }
-            nutsb_bulk_wait_read();                  // slabs and staging are reused by the next sub-tile
-            if (issued) nutsb_bulk_wait_all();
-            __syncthreads();
-        }
-#else
-        // -- copy: a run is one contiguous piece of a recipient's stream; warps take runs in turn
-        {
-            const u32 nruns = s_nruns < NUTSB_RUN_CAP ? s_nruns : NUTSB_RUN_CAP;
-            for (u32 r = (u32)warp; r < nruns; r += NUTSB_FAN_THREADS / 32) {
-                const uint4 run = s_run[r];
-                // the colour-off slab follows the colour-on one in the dynamic window
-                const u32 so = (run.z & 0x7fffffffu) + ((run.z >> 31) ? 0u : (u32)(NUTSB_ON_CAP + 64));
-                nutsb_warp_copy(A.out + (((u64)run.y << 32) | run.x), s_on + so, run.w, lane);
-            }
-        }
-#endif
-        // -- recipients that are not plain listeners (login / ignall / ignshout, level ops in the
-        //    batch) or did not fit the queue: one warp per recipient, op by op where needed
-        for (u32 ls = ls_begin + warp; ls < ls_end; ls += NUTSB_FAN_THREADS / 32) {
-            const u32 q = ls - ls_begin;
-            if (!s_ulegacy[q]) continue;
-            const u32 cf = s_ucf[q], clv = s_ulv[q];
-            const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
-            const bool full = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
-            const u32 *offc = colour ? s_oon : s_ooff;
-            const u8 *slab = colour ? s_on : s_off;
-            u64 p = s_upos[q];
-            const u32 e0 = s_uev0[q], e1 = s_uev1[q], evb = s_uevb[q];
-            u32 e = e0;
-            u32 cur = 0;
-            for (;;) {
-                u32 j = nb; u32 ek = 0; i32 dlt = 0;
-                if (e < e1) {
-                    const u32 uk = evb != 0xffffffffu ? s_evk[evb + (e - e0)] : A.sv_ukey[e];
-                    const u32 jj = (uk >> 1) - a0;
-                    if (jj < nb || (jj == nb && !(uk & 1))) {
-                        j = jj; ek = (uk & 1) ? 2 : 1;
-                        dlt = evb != 0xffffffffu ? s_evd[evb + (e - e0)] : A.sv_delta[e];
-                    }
-                }
-                if (full) {
-                    const u32 xs = cur > a ? cur : a, ye = j < b ? j : b;
-                    if (xs < ye) {
-                        nutsb_warp_copy(A.out + p + (offc[xs] - offc[cur]), slab + (offc[xs] - offc[a]),
-                                        offc[ye] - offc[xs], lane);
-                        my_deliv += ye - xs;
-                    }
-                    p += offc[j] - offc[cur];
-                } else {
-                    for (u32 i = cur; i < j; ++i) {
-                        if (!nutsb_class_delivers(cf, clv, s_kind[i], s_flags[i], s_target[i])) continue;
-                        const u32 len = offc[i + 1] - offc[i];
-                        if (i >= a && i < b) { nutsb_warp_copy(A.out + p, slab + (offc[i] - offc[a]), len, lane); ++my_deliv; }
-                        p += len;
-                    }
-                }
-                if (!ek) break;
-                if (ek == 2) cur = j + 1;                 // excluded from op j: nothing emitted for it
-                else { p += (u64)(i64)dlt; cur = j; }      // a direct op's bytes go here (k_direct writes them)
-                ++e;
-            }
-        }
-        NUTSB_PHASE(7);                 // warp 0's share of the copy
-        __syncthreads();
-        NUTSB_PHASE(8);                 // waiting for the slowest copier
-        a = b;
-    }
-    if (lane == 0 && my_deliv) atomicAdd(&s_deliv, my_deliv);
-    __syncthreads();
-    if (tid == 0) {
-        if (s_deliv) nutsb_add64(A.n_deliveries, (u64)s_deliv);
-        if (chunk == 0) {                                  // each slab op's source is read once per tile
-            u32 tb = 0; for (u32 i = 0; i < nb; ++i) tb += s_tlen[i];
-            nutsb_add64(A.n_deliveries + 2, (u64)tb);
+        for (u32 r = (u32)warp / NUTSB_FAN_GROUP; r < nr; r += NUTSB_FAN_THREADS / 32 / NUTSB_FAN_GROUP) {
+            const uint4 run = s_run[r];
+            const u64 so = (u64)run.z | ((u64)(run.w >> 24) << 32);
+            const u32 len = run.w & 0xffffffu;
+            u8 *dst = A.out + (((u64)run.y << 32) | run.x);
+            const u8 *src;
+            if (!staged) src = A.slab + so;
+            else if (so >= A.off_base) src = s_off + a_off + (u32)(so - d.off_src);
+            else src = s_on + a_on + (u32)(so - d.on_src);
+            nutsb_group_copy<32 * NUTSB_FAN_GROUP>(dst, src, len, tid % (32 * NUTSB_FAN_GROUP));
         }
     }
 }
@@ -1184,13 +1145,14 @@ __global__ void k_counts(const u64 *e_scan, i64 n_ent, u32 *counts)
 struct Sizes {                   // read back by the host before the fan-out is launched
     u64 total_bytes;
     u64 cells;
+    u64 slab_on, slab_off;       // bytes of the slab's two renderings
     u32 n_slab, n_events, items, tiles;
 };
 
 // Per room: tiles, (tile, recipient) cells and fan-out work items; exclusive
 // prefixes over rooms.  One block.
 __global__ void __launch_bounds__(NUTSB_SCAN_THREADS)
-k_geometry(PopView pop, const u32 *room_b_off, const u64 *stream_off, const u32 *counts,
+k_geometry(PopView pop, const u32 *room_b_off, const u64 *stream_off, const u32 *counts, const u64 *vp_on, const u64 *vp_off,
            u32 *room_tile_off, u64 *room_cell_off, u32 *room_item_off, Sizes *sz)
 {
     u64 c_tiles = 0, c_cells = 0, c_items = 0;
@@ -1202,7 +1164,7 @@ k_geometry(PopView pop, const u32 *room_b_off, const u64 *stream_off, const u32 
             const u64 users = (u64)(pop.room_slot_off[r + 1] - pop.room_slot_off[r]);
             const u64 nb = room_b_off[r + 1] - room_b_off[r];
             tiles = (nb + NUTSB_TILE_OPS - 1) / NUTSB_TILE_OPS;
-            cells = (tiles + 1) * users;
+            cells = tiles * users;
             items = tiles * ((users + NUTSB_UCHUNK - 1) / NUTSB_UCHUNK);
         }
         u64 t1, t2, t3;
@@ -1221,5 +1183,6 @@ k_geometry(PopView pop, const u32 *room_b_off, const u64 *stream_off, const u32 
         sz->total_bytes = stream_off[pop.n_users];
         sz->cells = c_cells; sz->n_slab = counts[0]; sz->n_events = counts[1];
         sz->items = (u32)c_items; sz->tiles = (u32)c_tiles;
+        sz->slab_on = vp_on[counts[0]]; sz->slab_off = vp_off[counts[0]];
     }
 }

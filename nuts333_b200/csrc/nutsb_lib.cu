@@ -50,7 +50,7 @@ struct nutsb_ctx {
     int sm_count = 148;
     std::string err;
     bool profiling = false; nutsb_timing tm{};
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     // tables
     DBuf d_codetab;
@@ -73,7 +73,7 @@ struct nutsb_ctx {
     DBuf d_sv_ukey, d_sv_delta, d_sv_op, d_sv_pre, d_ev_off;
     DBuf d_vp_on, d_vp_off, d_cp;
     DBuf d_room_tile_off, d_room_cell_off, d_room_item_off, d_sizes, d_counters;
-    DBuf d_cell_pos, d_cell_evi;
+    DBuf d_cell_nruns, d_run_off, d_runs, d_items, d_slab, d_bl_meta;
     DBuf d_off, d_out, d_digest, d_ulen;
     HBuf h_small, h_off, h_out;
     u64 last_total = 0; bool have_streams = false;
@@ -336,7 +336,7 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
         &c->d_evk[1], &c->d_evv[0], &c->d_evv[1], &c->d_ev_ukey, &c->d_ev_delta, &c->d_ev_op, &c->d_sv_ukey,
         &c->d_sv_delta, &c->d_sv_op, &c->d_sv_pre, &c->d_ev_off, &c->d_vp_on, &c->d_vp_off, &c->d_cp,
         &c->d_room_tile_off, &c->d_room_cell_off, &c->d_room_item_off, &c->d_sizes, &c->d_counters,
-        &c->d_cell_pos, &c->d_cell_evi, &c->d_off, &c->d_out, &c->d_digest, &c->d_ulen,
+        &c->d_cell_nruns, &c->d_run_off, &c->d_runs, &c->d_items, &c->d_slab, &c->d_bl_meta, &c->d_off, &c->d_out, &c->d_digest, &c->d_ulen,
         &c->s_text, &c->s_toff, &c->s_kind, &c->s_target, &c->s_except, &c->s_flags, &c->s_gate, &c->s_verdict, &c->s_v8,
         &c->d_names, &c->d_name_off, &c->d_sflags, &c->d_lit, &c->d_lit_off, &c->d_sp_len, &c->d_sp_off, &c->d_sp_text,
         &c->d_sp_kind, &c->d_sp_target, &c->d_sp_except, &c->d_sp_flags, &c->d_sp_gate, &c->d_sp_verdict,
@@ -563,7 +563,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
         if (c->profiling) { for (int q = 1; q < 4; ++q) CK(cudaEventRecord(c->ev[q], st)); }
         CK(cudaStreamSynchronize(st));
         c->last_total = 0; c->have_streams = true;
-        c->tm.fanout_bytes_in = c->tm.fanout_bytes_out = 0;
+        c->tm.fanout_bytes_in = c->tm.fanout_bytes_out = 0; c->tm.slab_bytes = c->tm.render_bytes_in = 0;
         out->n_users = U; out->total_bytes = 0; out->n_deliveries = 0;
         out->off = c->d_off.as<u64>(); out->bytes = c->d_out.as<u8>(); out->on_device = 1;
         return NUTSB_OK;
@@ -635,12 +635,12 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     NUTSB_LAUNCH(1, 32, st, k_counts, c->d_e_scan.as<u64>(), (i64)E, counts); CKL();
     TRY(ensure(c, c->d_room_b_off, ((size_t)Rt + 2) * 4));
     NUTSB_LAUNCH(cdiv((u64)Rt + 1, 256), 256, st, k_room_b_off, c->d_room_ent_off.as<u32>(), c->d_e_scan.as<u64>(), (u32)Rt, c->d_room_b_off.as<u32>()); CKL();
-    TRY(ensure(c, c->d_bl_op, E * 4 + 16)); TRY(ensure(c, c->d_bl_room, E * 4 + 16));
+    TRY(ensure(c, c->d_bl_op, E * 4 + 16)); TRY(ensure(c, c->d_bl_room, E * 4 + 16)); TRY(ensure(c, c->d_bl_meta, E * 4 + 16));
     for (int q = 0; q < 2; ++q) { TRY(ensure(c, c->d_evk[q], E * 4 + 16)); TRY(ensure(c, c->d_evv[q], E * 4 + 16)); }
     TRY(ensure(c, c->d_ev_ukey, E * 4)); TRY(ensure(c, c->d_ev_delta, E * 4)); TRY(ensure(c, c->d_ev_op, E * 4));
     EntryScatter es{ e_room, e_op, c->d_e_info.as<u8>(), c->d_e_delta.as<i32>(), c->d_e_slot.as<u32>(),
                      c->d_room_ent_off.as<u32>(), c->d_e_scan.as<u64>(), c->d_bl_op.as<u32>(), c->d_bl_room.as<u32>(),
-                     c->d_evk[0].as<u32>(), c->d_ev_ukey.as<u32>(), c->d_ev_op.as<u32>(), c->d_ev_delta.as<i32>() };
+                     c->d_bl_meta.as<u32>(), ops, c->d_evk[0].as<u32>(), c->d_ev_ukey.as<u32>(), c->d_ev_op.as<u32>(), c->d_ev_delta.as<i32>() };
     NUTSB_LAUNCH(cdiv(E, 256), 256, st, k_entry_scatter, es, (i64)E); CKL();
     c->tm.launches += 5;
 
@@ -678,6 +678,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     TRY(ensure(c, c->d_room_tile_off, ((size_t)Rt + 2) * 4)); TRY(ensure(c, c->d_room_cell_off, ((size_t)Rt + 2) * 8));
     TRY(ensure(c, c->d_room_item_off, ((size_t)Rt + 2) * 4));
     NUTSB_LAUNCH(1, NUTSB_SCAN_THREADS, st, k_geometry, pop, c->d_room_b_off.as<u32>(), c->d_off.as<u64>(), counts,
+                 c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(),
                  c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>(), c->d_sizes.as<Sizes>()); CKL();
     c->tm.launches++;
 
@@ -687,20 +688,50 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     CK(cudaStreamSynchronize(st));
     const Sizes sz = *hs;
     TRY(ensure(c, c->d_out, sz.total_bytes + 64));
-    TRY(ensure(c, c->d_cell_pos, (sz.cells + 1) * 8)); TRY(ensure(c, c->d_cell_evi, (sz.cells + 1) * 4));
     Geometry geo{ c->d_room_b_off.as<u32>(), c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>() };
-    if (sz.cells > 0) {
-        NUTSB_LAUNCH(cdiv(sz.cells, 256), 256, st, k_fill_pos, pop, geo, cpx, c->d_off.as<u64>(), c->d_ev_off.as<u32>(),
-                     c->d_sv_ukey.as<u32>(), c->d_sv_pre.as<u64>(), (u64)sz.cells, c->d_cell_pos.as<u64>(), c->d_cell_evi.as<u32>()); CKL();
-        c->tm.launches++;
+    u64 *counters = c->d_counters.as<u64>();
+    const u64 off_base = (sz.slab_on + 15) & ~(u64)15;          // the colour-off renderings follow the colour-on ones
+    c->tm.fanout_launches = 0;
+    c->tm.slab_bytes = sz.slab_on + sz.slab_off;
+
+    // -- F. copy plan: runs per cell (count, scan, fill) and the work-item descriptors
+    if (sz.cells > 0 && sz.items > 0) {
+        if (off_base + sz.slab_off >= (1ull << 40)) return fail(c, NUTSB_E_RANGE, "more than 2^40 bytes of rendered slab in one batch%s");
+        TRY(ensure(c, c->d_cell_nruns, (sz.cells + 1) * 4)); TRY(ensure(c, c->d_run_off, (sz.cells + 2) * 8));
+        TRY(ensure(c, c->d_items, (size_t)sz.items * sizeof(ItemDesc)));
+        PlanArgs pa{ pop, geo, cpx, c->d_off.as<u64>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_delta.as<i32>(),
+                     c->d_sv_pre.as<u64>(), c->d_bl_meta.as<u32>(), (u64)sz.cells, off_base, has_level ? 1u : 0u,
+                     c->d_cell_nruns.as<u32>(), c->d_run_off.as<u64>(), nullptr, c->d_items.as<ItemDesc>(), counters, c->d_status.as<u32>() };
+        NUTSB_LAUNCH(cdiv(sz.cells, 256), 256, st, k_plan<false>, pa); CKL();
+        TRY(run_scan(c, InU32{c->d_cell_nruns.as<u32>()}, OutU64{c->d_run_off.as<u64>()}, (i64)sz.cells, nullptr));
+        // plain listeners: at most one run per cell plus one per event; behind a filter the count is read back
+        u64 n_runs = sz.cells + sz.n_events;
+        if (!alias) {
+            CK(cudaMemcpyAsync(h64 + 2, c->d_run_off.as<u64>() + sz.cells, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            n_runs = h64[2];
+        }
+        if (n_runs >= 0xfffffff0ull) return fail(c, NUTSB_E_RANGE, "more than 2^32 copy runs in one batch%s");
+        TRY(ensure(c, c->d_runs, (n_runs + 1) * sizeof(uint4)));
+        pa.runs = c->d_runs.as<uint4>();
+        NUTSB_LAUNCH(cdiv(sz.cells, 256), 256, st, k_plan<true>, pa); CKL();
+        c->tm.launches += 2;
     }
 
-    // -- H. render + fan-out
+    // -- G. render the slab, once per colour setting
     if (c->profiling) CK(cudaEventRecord(c->ev[1], st));
-    u64 *counters = c->d_counters.as<u64>();
-    if (sz.items > 0) {
-        FanoutArgs fa{ ops, pop, geo, cpx, c->d_bl_op.as<u32>(), len_on, len_off, c->d_cell_pos.as<u64>(), c->d_cell_evi.as<u32>(),
-                       c->d_sv_ukey.as<u32>(), c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), counters, c->d_status.as<u32>(), has_level ? 1u : 0u };
+    TRY(ensure(c, c->d_slab, off_base + sz.slab_off + 256));
+    if (sz.n_slab > 0) {
+        RenderArgs ra{ ops, c->d_codetab.as<u8>(), c->d_bl_op.as<u32>(), c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(), counts,
+                       c->d_slab.as<u8>(), off_base, counters, c->d_status.as<u32>() };
+        NUTSB_LAUNCH(cdiv(sz.n_slab, NUTSB_REN_OPS * (NUTSB_REN_THREADS / 32)), NUTSB_REN_THREADS, st, k_render, ra); CKL();
+        c->tm.launches++;
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
+
+    // -- H. fan-out
+    if (sz.cells > 0 && sz.items > 0) {
+        FanoutArgs fa{ c->d_items.as<ItemDesc>(), c->d_runs.as<uint4>(), c->d_slab.as<u8>(), off_base, c->d_out.as<u8>() };
         NUTSB_LAUNCH_SMEM(sz.items, NUTSB_FAN_THREADS, NUTSB_FAN_SMEM, st, k_fanout, fa); CKL();
         c->tm.launches++; c->tm.fanout_launches = 1;
     }
@@ -717,20 +748,21 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[3], st));
 
-    CK(cudaMemcpyAsync(h64 + 8, counters, 72, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h64 + 8, counters, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     TRY(status_to_error(c, h32[4]));
     c->last_total = sz.total_bytes; c->have_streams = true;
     if (c->profiling) {
         CK(cudaEventElapsedTime(&c->tm.plan_ms, c->ev[0], c->ev[1]));
-        CK(cudaEventElapsedTime(&c->tm.fanout_ms, c->ev[1], c->ev[2]));
+        CK(cudaEventElapsedTime(&c->tm.render_ms, c->ev[1], c->ev[5]));
+        CK(cudaEventElapsedTime(&c->tm.fanout_ms, c->ev[5], c->ev[2]));
         CK(cudaEventElapsedTime(&c->tm.direct_ms, c->ev[2], c->ev[3]));
         CK(cudaEventElapsedTime(&c->tm.total_ms, c->ev[0], c->ev[3]));
     }
     c->tm.fanout_bytes_out = sz.total_bytes - h64[9];
-    c->tm.fanout_bytes_in = h64[10];
-    for (int q = 0; q < 6; ++q) c->tm.phase_cycles[q] = h64[11 + q];
+    c->tm.fanout_bytes_in = c->tm.slab_bytes;          // each rendering of a tile is read once per work item
+    c->tm.render_bytes_in = h64[10];
     out->n_users = U; out->total_bytes = sz.total_bytes; out->n_deliveries = h64[8];
     out->off = c->d_off.as<u64>(); out->bytes = c->d_out.as<u8>(); out->on_device = 1;
     return NUTSB_OK;

@@ -31,6 +31,7 @@
 #define __forceinline__ inline
 #define __shared__ static
 #define __launch_bounds__(...)
+#define __restrict__
 #define __align__(n) __attribute__((aligned(n)))
 #define __constant__ static
 
@@ -147,6 +148,11 @@ static inline unsigned __ballot_sync(unsigned mask, int pred)
 {
     return (unsigned)cpusim::collective(mask, pred ? 1 : 0, 0, [](const cpusim::Slot *in, unsigned m, int) {
         uint64_t r = 0; for (int k = 0; k < 32; ++k) if ((m >> k & 1) && in[k].v) r |= 1ull << k; return r; });
+}
+static inline unsigned __reduce_or_sync(unsigned mask, unsigned v)
+{
+    return (unsigned)cpusim::collective(mask, v, 0, [](const cpusim::Slot *in, unsigned m, int) {
+        uint64_t r = 0; for (int k = 0; k < 32; ++k) if (m >> k & 1) r |= in[k].v; return r; });
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
 static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
