@@ -42,6 +42,7 @@ N_MSGS = 1_000_000
 N_USERS = 10_000
 USERS_PER_ROOM = 100
 N_SWEAR = 64
+KERNEL_TIMING_STEPS = 3
 N_BAN_QUERIES = 100_000
 N_BAN_ENTRIES = 10_000
 SEED = 0x333
@@ -283,7 +284,7 @@ def run_ours(args):
     input_bytes = sum(int(v.numel() * v.element_size()) for k, v in d.items() if k not in ("verdict", "vs", "vu"))
     torch.cuda.synchronize()
 
-    state = dict(deliv=0, bytes=0, launches=0, fan_ms=0.0, fan_in=0, fan_out=0, plan_ms=0.0, direct_ms=0.0, render_ms=0.0)
+    state = dict(deliv=0, bytes=0, launches=0, fan_ms=0.0, fan_in=0, fan_out=0, plan_ms=0.0, direct_ms=0.0, render_ms=0.0, ksteps=0)
 
     def step_device():
         with torch.cuda.stream(stream):
@@ -298,6 +299,7 @@ def run_ours(args):
         state["launches"] += int(t.launches) + 3
         state["fan_ms"] += float(t.fanout_ms); state["fan_in"] += int(t.fanout_bytes_in); state["fan_out"] += int(t.fanout_bytes_out)
         state["plan_ms"] += float(t.plan_ms); state["direct_ms"] += float(t.direct_ms); state["render_ms"] += float(t.render_ms)
+        state["ksteps"] += 1
         return s
 
     def barrier():
@@ -324,6 +326,17 @@ def run_ours(args):
     clk = clocks.stop()
     ms = e0.elapsed_time(e1)
     dev_state = dict(state)
+    # ---- per-kernel durations: the same step with every kernel on one stream (no k_render / k_direct beside
+    #      the plan / the fan-out), so that each kernel is timed alone with CUDA events on its own stream
+    ctx.set_overlap(False)
+    step_device()                       # warm-up of the serial schedule
+    for k in state:
+        state[k] = 0 if not isinstance(state[k], float) else 0.0
+    for _ in range(KERNEL_TIMING_STEPS):
+        step_device()
+    torch.cuda.synchronize()
+    kstate = dict(state)
+    ctx.set_overlap(os.environ.get('NUTSB_OVERLAP', '1') != '0')
 
     # ---- e2e: host buffers through the C-ABI, H2D and D2H inside the timed region
     hops = dict(ops)
@@ -363,8 +376,9 @@ def run_ours(args):
             peaks = json.loads(pk.read_text())
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-        fan_bytes = (dev_state["fan_in"] + dev_state["fan_out"]) / max(1, args.steps)
-        fan_ms = dev_state["fan_ms"] / max(1, args.steps)
+        ks = max(1, kstate["ksteps"])
+        fan_bytes = (kstate["fan_in"] + kstate["fan_out"]) / ks
+        fan_ms = kstate["fan_ms"] / ks
         achieved = fan_bytes / (fan_ms * 1e-3) / 1e9 if fan_ms > 0 else 0.0
         traffic = None
         tp = ROOT / "profiles" / "fanout_traffic.json"
@@ -381,9 +395,12 @@ def run_ours(args):
                                    % (input_bytes / 1e6, dev_state["bytes"] / max(1, args.steps) / 1e9),
                                 source_msgs_per_s=world * N_MSGS * args.steps / (ms_max * 1e-3),
                                 ban_queries_per_step=2 * N_BAN_QUERIES,
-                                plan_ms=dev_state["plan_ms"] / max(1, args.steps),
-                                render_ms=dev_state["render_ms"] / max(1, args.steps), fanout_ms=fan_ms,
-                                direct_ms=dev_state["direct_ms"] / max(1, args.steps)),
+                                kernel_ms_alone=dict(plan=kstate["plan_ms"] / ks, render=kstate["render_ms"] / ks, fanout=fan_ms,
+                                                     direct=kstate["direct_ms"] / ks, steps=ks,
+                                                     how="extra steps after the timed region with nutsb_set_overlap(0): "
+                                                         "every kernel on one stream, CUDA events around each"),
+                                plan_ms=kstate["plan_ms"] / ks, render_ms=kstate["render_ms"] / ks, fanout_ms=fan_ms,
+                                direct_ms=kstate["direct_ms"] / ks),
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                                   traffic=traffic, kernel="k_fanout", peak_source=peak_src,
                                   algorithmic_bytes_per_launch=fan_bytes),

@@ -139,6 +139,9 @@ int  nutsb_create(nutsb_ctx **out, int device);
 void nutsb_destroy(nutsb_ctx *ctx);
 int  nutsb_set_profiling(nutsb_ctx *ctx, int on);
 int  nutsb_get_timing(const nutsb_ctx *ctx, nutsb_timing *out);
+/* 1 (default): k_render and k_direct run on a second stream beside the planning kernels and the
+ * fan-out.  0: every kernel on one stream, so that each kernel's own duration can be timed alone. */
+int  nutsb_set_overlap(nutsb_ctx *ctx, int on);
 /* Use the caller's CUDA stream (a cudaStream_t) instead of the context's own. */
 int  nutsb_set_stream(nutsb_ctx *ctx, void *cuda_stream);
 

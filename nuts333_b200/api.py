@@ -66,7 +66,7 @@ class Timing(C.Structure):
 
 EXPORTS = [
     "nutsb_version", "nutsb_strerror", "nutsb_last_error", "nutsb_create", "nutsb_destroy",
-    "nutsb_set_profiling", "nutsb_get_timing", "nutsb_set_stream", "nutsb_set_swear_words",
+    "nutsb_set_profiling", "nutsb_get_timing", "nutsb_set_overlap", "nutsb_set_stream", "nutsb_set_swear_words",
     "nutsb_set_ban_files", "nutsb_set_users", "nutsb_write_batch", "nutsb_write_batch_dev",
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
@@ -95,6 +95,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_set_profiling.argtypes = [vp, C.c_int]
     lib.nutsb_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.nutsb_set_stream.argtypes = [vp, vp]
+    lib.nutsb_set_overlap.argtypes = [vp, C.c_int]
     lib.nutsb_set_swear_words.argtypes = [vp, C.POINTER(C.c_char_p)]
     lib.nutsb_set_ban_files.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
     lib.nutsb_set_users.argtypes = [vp, C.c_int32, C.c_int32, i32p, u8p, u8p]
@@ -239,6 +240,9 @@ class Context:
 
     def set_profiling(self, on=True):
         self._ck(self.lib.nutsb_set_profiling(self._h, 1 if on else 0))
+
+    def set_overlap(self, on: bool = True):
+        self._ck(self.lib.nutsb_set_overlap(self._h, 1 if on else 0))
 
     def set_stream(self, cuda_stream: int):
         self._ck(self.lib.nutsb_set_stream(self._h, C.c_void_p(cuda_stream)))

@@ -52,6 +52,20 @@ __device__ __forceinline__ void nutsb_bulk_wait_all() { asm volatile("cp.async.b
 __device__ __forceinline__ void nutsb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #endif
 
+// ---- cp.async (LDGSTS): 16 bytes global -> shared without a register round trip ----------------
+#ifdef NUTSB_CPUSIM
+static inline void nutsb_cp_async16(void *sdst, const void *gsrc) { memcpy(sdst, gsrc, 16); }
+static inline void nutsb_cp_async_commit() {}
+template <int N> static inline void nutsb_cp_async_wait() {}
+#else
+__device__ __forceinline__ void nutsb_cp_async16(void *sdst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((u32)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void nutsb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void nutsb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+#endif
+
 __device__ __forceinline__ void nutsb_add64(u64 *p, u64 v) { atomicAdd((unsigned long long *)p, (unsigned long long)v); }
 
 // Status bits raised by kernels (ctx->d_status), decoded on the host.

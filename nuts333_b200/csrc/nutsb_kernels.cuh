@@ -46,6 +46,7 @@ struct PopView {                 // the population, built by nutsb_set_users
 #ifndef NUTSB_FAN_OFF_CAP
 #define NUTSB_FAN_OFF_CAP (80 * NUTSB_TILE_OPS)   // ... and its colour-off rendering (larger tiles are copied slab -> stream directly)
 #endif
+
 #define NUTSB_FAN_RUN_CAP 256    // runs staged per round
 
 // ---- A. measure ------------------------------------------------------------------
@@ -58,6 +59,7 @@ struct PopView {                 // the population, built by nutsb_set_users
 // 32 entries at a time (owner string by binary search over the 33 offsets, '/~'
 // escape and command lookup in the shared-memory table) into per-string counters.
 #define NUTSB_MEASURE_THREADS 256
+#define NUTSB_SLAB_TOT_WAYS 32
 #define NUTSB_MEASURE_WARP_BYTES 4096
 #define NUTSB_MEASURE_LIST 256
 
@@ -68,7 +70,7 @@ __device__ __forceinline__ u32 nutsb_zero_bytes(u32 y)
 }
 
 __global__ void __launch_bounds__(NUTSB_MEASURE_THREADS)
-k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *status)
+k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *status, u64 *slab_tot)
 {
     __shared__ __align__(16) u8 s_stage[NUTSB_MEASURE_THREADS / 32][NUTSB_MEASURE_WARP_BYTES + 32];
     __shared__ u32 s_list[NUTSB_MEASURE_THREADS / 32][NUTSB_MEASURE_LIST];
@@ -172,32 +174,44 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
             }
         }
     }
-    if (!have) return;
-    if (bad) { atomicOr(status, NUTSB_ST_BAD_OFFSETS); len_on[i] = len_off[i] = nrep[i] = 0; return; }
-    if (toolong) { atomicOr(status, NUTSB_ST_TEXT_TOO_LONG); len_on[i] = len_off[i] = nrep[i] = 0; return; }
-    u32 st = 0;
-    const u32 loff = n - drops - 3 * (m4 + m5) + nl;
-    const u32 of = ops.flags[i];
-    len_off[i] = loff;
-    len_on[i]  = (of & NUTSB_OF_PLAIN) ? loff                                   // colour setting ignored
-               : loff + 4 * nl + 4 * m4 + 5 * m5 + ((of & NUTSB_OF_PAGER) ? 0u : 4u);   // pager lines carry no final reset
+    // (no early return: the warp reduces the slab totals together at the end)
+    u32 st = 0, lon = 0, loff = 0, rep = 0;
+    u32 kind = NUTSB_OP_NONE;
+    if (have && bad) { atomicOr(status, NUTSB_ST_BAD_OFFSETS); len_on[i] = len_off[i] = nrep[i] = 0; }
+    else if (have && toolong) { atomicOr(status, NUTSB_ST_TEXT_TOO_LONG); len_on[i] = len_off[i] = nrep[i] = 0; }
+    else if (have) {
+        loff = n - drops - 3 * (m4 + m5) + nl;
+        const u32 of = ops.flags[i];
+        lon = (of & NUTSB_OF_PLAIN) ? loff                                    // colour setting ignored
+            : loff + 4 * nl + 4 * m4 + 5 * m5 + ((of & NUTSB_OF_PAGER) ? 0u : 4u);   // pager lines carry no final reset
+        len_off[i] = loff; len_on[i] = lon;
 
-    // fan-in: how many room lists this op enters
-    const u32 kind = ops.kind[i];
-    const i32 tgt = ops.target[i], exc = ops.except_user[i];
-    u32 rep = 0;
-    if (kind == NUTSB_OP_USER) {
-        if (tgt >= pop.n_users) st |= NUTSB_ST_BAD_INDEX; else if (tgt >= 0) rep = 1;
-    } else if (kind == NUTSB_OP_ROOM) {
-        if (tgt >= pop.n_rooms || tgt < -1) st |= NUTSB_ST_BAD_INDEX;
-        else rep = tgt >= 0 ? 1u : (u32)pop.n_rooms;
-    } else if (kind == NUTSB_OP_LEVEL) {
-        rep = (u32)pop.n_rooms_tot; st |= NUTSB_ST_HAS_LEVEL;
-    } else if (kind != NUTSB_OP_NONE) st |= NUTSB_ST_BAD_KIND;
-    if (kind != NUTSB_OP_NONE && (exc >= pop.n_users || exc < -1)) st |= NUTSB_ST_BAD_INDEX;
-    if (st & ~NUTSB_ST_HAS_LEVEL) rep = 0;
-    nrep[i] = live ? rep : 0;
-    if (st) atomicOr(status, st);
+        // fan-in: how many room lists this op enters
+        kind = ops.kind[i];
+        const i32 tgt = ops.target[i], exc = ops.except_user[i];
+        if (kind == NUTSB_OP_USER) {
+            if (tgt >= pop.n_users) st |= NUTSB_ST_BAD_INDEX; else if (tgt >= 0) rep = 1;
+        } else if (kind == NUTSB_OP_ROOM) {
+            if (tgt >= pop.n_rooms || tgt < -1) st |= NUTSB_ST_BAD_INDEX;
+            else rep = tgt >= 0 ? 1u : (u32)pop.n_rooms;
+        } else if (kind == NUTSB_OP_LEVEL) {
+            rep = (u32)pop.n_rooms_tot; st |= NUTSB_ST_HAS_LEVEL;
+        } else if (kind != NUTSB_OP_NONE) st |= NUTSB_ST_BAD_KIND;
+        if (kind != NUTSB_OP_NONE && (exc >= pop.n_users || exc < -1)) st |= NUTSB_ST_BAD_INDEX;
+        if (st & ~NUTSB_ST_HAS_LEVEL) rep = 0;
+        if (!live) rep = 0;
+        nrep[i] = rep;
+        if (st) atomicOr(status, st);
+    }
+    // bytes of the slab's two renderings: every (room, op) entry of a room / level op is rendered once per
+    // setting.  Known here already, so the slab buffer can be sized at the first read-back.
+    const bool slab = rep && kind != NUTSB_OP_USER;
+    u64 s_on = slab ? (u64)lon * rep : 0, s_off = slab ? (u64)loff * rep : 0;
+    for (int d = 16; d; d >>= 1) { s_on += __shfl_xor_sync(NUTSB_FULL, s_on, d); s_off += __shfl_xor_sync(NUTSB_FULL, s_off, d); }
+    if (lane == 0 && (s_on | s_off)) {                         // NUTSB_SLAB_TOT_WAYS pairs: same-address atomics serialise
+        u64 *t = slab_tot + 2 * (blockIdx.x % NUTSB_SLAB_TOT_WAYS);
+        nutsb_add64(t, s_on); nutsb_add64(t + 1, s_off);
+    }
 }
 
 // ---- B. expand ops into (room, op) entries ------------------------------------------
@@ -294,7 +308,13 @@ k_seg_bounds(const u32 *keys, i64 n_host, const u32 *n_dev, u32 nkeys, u32 *seg_
 
 // ---- C. per-entry classification -----------------------------------------------------
 // e_info packs, per room-list entry: bit0 = enters the room slab (room/level op),
-// bits 1-2 = event kind (0 none, 1 direct write_user op, 2 excluded recipient).
+// bits 1-2 = event kind (0 none, 1 direct write_user op, 2 excluded recipient, 3 both in one:
+// a write_user to u directly followed, in the same room list, by a room op that excludes u --
+// say(), shout(), tell() ... all write "You ..." to the speaker and the line to everybody else).
+// Event keys: 4 * (slab rank the event sits before) + 0 direct | 1 direct-and-skip | 2 skip.
+#define NUTSB_EV_DIRECT  0u
+#define NUTSB_EV_REPLACE 1u
+#define NUTSB_EV_SKIP    2u
 struct EntryArrays {
     const u32 *e_room, *e_op;    // sorted by room, op order inside
     u8  *e_info;
@@ -312,10 +332,20 @@ k_entry_info(OpsView ops, PopView pop, EntryArrays ea, i64 n_ent, const u32 *len
     u8 info = 0; i32 delta = 0; u32 slot = 0;
     if (kind == NUTSB_OP_USER) {
         const i32 u = ops.target[op];
-        const u32 cf = pop.cls_flags[pop.user_cls[u]];
+        const i32 k = pop.user_cls[u];
+        const u32 cf = pop.cls_flags[k];
         info = 1u << 1;
         delta = (i32)((cf & NUTSB_UF_COLOUR) ? len_on[op] : len_off[op]);
         slot = (u32)pop.user_slot[u];
+        if (e + 1 < n_ent && ea.e_room[e + 1] == room) {     // followed by a room op that excludes u: one event
+            const u32 op2 = ea.e_op[e + 1];
+            const u32 kind2 = ops.kind[op2];
+            if (kind2 != NUTSB_OP_USER && ops.except_user[op2] == u &&
+                nutsb_class_delivers(cf, pop.cls_level[k], kind2, ops.flags[op2], ops.target[op2])) {
+                info = 3u << 1;
+                delta -= (i32)((cf & NUTSB_UF_COLOUR) ? len_on[op2] : len_off[op2]);
+            }
+        }
     } else {
         info = 1;
         const i32 x = ops.except_user[op];
@@ -323,9 +353,16 @@ k_entry_info(OpsView ops, PopView pop, EntryArrays ea, i64 n_ent, const u32 *len
             const i32 k = pop.user_cls[x];
             const u32 cf = pop.cls_flags[k];
             if (nutsb_class_delivers(cf, pop.cls_level[k], kind, ops.flags[op], ops.target[op])) {
-                info |= 2u << 1;
-                delta = -(i32)((cf & NUTSB_UF_COLOUR) ? len_on[op] : len_off[op]);
-                slot = (u32)pop.user_slot[x];
+                bool merged = false;                           // the write_user just before carries the exclusion
+                if (e > 0 && ea.e_room[e - 1] == room) {
+                    const u32 op0 = ea.e_op[e - 1];
+                    merged = ops.kind[op0] == NUTSB_OP_USER && ops.target[op0] == x;
+                }
+                if (!merged) {
+                    info |= 2u << 1;
+                    delta = -(i32)((cf & NUTSB_UF_COLOUR) ? len_on[op] : len_off[op]);
+                    slot = (u32)pop.user_slot[x];
+                }
             }
         }
     }
@@ -363,7 +400,7 @@ k_entry_scatter(EntryScatter s, i64 n_ent)
     if (ek) {
         const u32 roomB0 = (u32)s.e_scan[s.room_ent_off[room]];     // slab rank of the room's first entry
         s.ev_slot[evi]  = s.e_slot[e];
-        s.ev_ukey[evi]  = 2u * (rankB - roomB0) + (ek == 2 ? 1u : 0u);
+        s.ev_ukey[evi]  = 4u * (rankB - roomB0) + (ek == 1 ? NUTSB_EV_DIRECT : ek == 3 ? NUTSB_EV_REPLACE : NUTSB_EV_SKIP);
         s.ev_delta[evi] = s.e_delta[e];
         s.ev_op[evi]    = s.e_op[e];
     }
@@ -457,6 +494,9 @@ struct ItemDesc {                // one fan-out work item = (room, tile, chunk o
 // byte offset in the slab buffer (low 32 bits), w = length (24 bits) | source bits 32..39 << 24.
 __device__ __forceinline__ uint4 nutsb_run_pack(u64 dst, u64 src, u32 len)
 {
+#ifdef NUTSB_EXPERIMENT_ALIGN     // timing experiment only (wrong bytes): every run starts and ends on a sector boundary
+    dst &= ~(u64)(NUTSB_EXPERIMENT_ALIGN - 1); len = (len + NUTSB_EXPERIMENT_ALIGN - 1) & ~(u32)(NUTSB_EXPERIMENT_ALIGN - 1);
+#endif
     return make_uint4((u32)dst, (u32)(dst >> 32), (u32)src, (len & 0xffffffu) | ((u32)(src >> 32) << 24));
 }
 #define NUTSB_RUN_MAX_LEN 0xffffffu
@@ -497,11 +537,12 @@ k_plan(PlanArgs A)
         const u32 nb = nb_room - a0 < NUTSB_TILE_OPS ? nb_room - a0 : NUTSB_TILE_OPS;
         const u32 g0 = b0 + a0;
         const u32 e0 = A.ev_off[s], e1 = A.ev_off[s + 1];
-        // the recipient's events inside the tile: keys in [2*a0+1, 2*(a0+nb)]
+        // the recipient's events inside the tile: keys in [4*a0+1, 4*(a0+nb)] (a direct op before the tile's first
+        // slab op belongs to the tile before)
         u32 l = e0, h = e1;
-        { const u32 thr = 2 * a0 + 1; while (l < h) { const u32 mid = (l + h) >> 1; if (A.sv_ukey[mid] < thr) l = mid + 1; else h = mid; } }
+        { const u32 thr = 4 * a0 + 1; while (l < h) { const u32 mid = (l + h) >> 1; if (A.sv_ukey[mid] < thr) l = mid + 1; else h = mid; } }
         u32 l_end = l; h = e1;
-        { const u32 thr = 2 * (a0 + nb) + 1; while (l_end < h) { const u32 mid = (l_end + h) >> 1; if (A.sv_ukey[mid] < thr) l_end = mid + 1; else h = mid; } }
+        { const u32 thr = 4 * (a0 + nb) + 1; while (l_end < h) { const u32 mid = (l_end + h) >> 1; if (A.sv_ukey[mid] < thr) l_end = mid + 1; else h = mid; } }
         const i32 u = A.pop.slot_user[s];
         const i32 k = A.pop.user_cls[u];
         const u32 cf = A.pop.slot_cf[s], clv = A.pop.slot_lv[s];
@@ -510,21 +551,38 @@ k_plan(PlanArgs A)
         const u64 *vp = (colour ? A.cpx.vp_on : A.cpx.vp_off) + g0;      // tile-local prefix of rendered lengths
         const u64 sb = colour ? 0 : A.off_base;
         // stream position of the tile's first op: class prefix + the recipient's own events before the tile
-        u64 p = 0;
-        if (FILL) p = A.stream_off[u] + (A.cpx.at(k, room, g0) - A.cpx.at(k, room, b0)) + (A.sv_pre[l] - A.sv_pre[e0]);
+        const u64 so_u = A.stream_off[u], cp_b0 = A.cpx.at(k, room, b0);
+        u64 p = so_u + (A.cpx.at(k, room, g0) - cp_b0) + (A.sv_pre[l] - A.sv_pre[e0]);
+        // Plain listeners: a run covers only whole 32-byte sectors of the stream.  The pieces of a sector
+        // that holds a discontinuity (an event of this recipient) are written together by k_direct's seam
+        // pass: two partial writes of one sector far apart in time cost a read-modify-write in DRAM.
+        // a_start = where the contiguous stretch of slab bytes this run belongs to begins in the stream.
+        u64 a_start = so_u; bool first_seg = true;
+        if (full && l > e0) {                                 // ... after the last event before the tile
+            const u32 uk = A.sv_ukey[l - 1];
+            a_start = so_u + (A.cpx.at(k, room, b0 + (uk >> 2) + ((uk & 3u) != NUTSB_EV_DIRECT)) - cp_b0) + (A.sv_pre[l] - A.sv_pre[e0]);
+            first_seg = false;
+        }
+        const bool last_tile = a0 + nb == nb_room;
         u64 r_out = FILL ? A.run_off[cell] : 0;
         u32 nruns = 0;
         u32 cur = 0;
         for (u32 e = l; ; ++e) {
-            u32 j = nb; bool excl = false; i32 dlt = 0;
-            if (e < l_end) { const u32 uk = A.sv_ukey[e]; j = (uk >> 1) - a0; excl = (uk & 1) != 0; if (FILL && !excl) dlt = A.sv_delta[e]; }
+            u32 j = nb, ek = NUTSB_EV_SKIP; i32 dlt = 0;
+            if (e < l_end) { const u32 uk = A.sv_ukey[e]; j = (uk >> 2) - a0; ek = uk & 3u; if (ek != NUTSB_EV_SKIP) dlt = A.sv_delta[e]; }
             if (full) {
                 if (cur < j) {
                     const u64 v0 = vp[cur], v1 = vp[j];
                     deliv += j - cur;                                  // zero-length renderings are deliveries too
                     if (v1 > v0) {
-                        if (FILL) { A.runs[r_out + nruns] = nutsb_run_pack(p, sb + v0, (u32)(v1 - v0)); p += v1 - v0; }
-                        ++nruns;
+                        const u64 x0 = p, x1 = p + (v1 - v0), f0 = x0 & ~(u64)31;
+                        const u64 xs = a_start <= f0 ? f0 : (first_seg ? x0 : (x0 + 31) & ~(u64)31);
+                        const u64 xe = (e >= l_end && last_tile) ? x1 : x1 & ~(u64)31;      // the stream's end is kept exact
+                        if (xs < xe) {
+                            if (FILL) A.runs[r_out + nruns] = nutsb_run_pack(xs, sb + v0 + xs - x0, (u32)(xe - xs));
+                            ++nruns;
+                        }
+                        p = x1;
                     }
                 }
             } else {
@@ -546,18 +604,24 @@ k_plan(PlanArgs A)
                 }
             }
             if (e >= l_end) break;
-            if (excl) cur = j + 1;                            // excluded from op j: nothing emitted for it
-            else { p += (u64)(i64)dlt; cur = j; }             // a direct op's bytes go here (k_direct writes them)
+            // a direct op's bytes go here (k_direct writes them); excluded from op j: nothing emitted for it
+            if (ek == NUTSB_EV_DIRECT) { p += (u64)(i64)dlt; cur = j; }
+            else {
+                if (ek == NUTSB_EV_REPLACE) p += (u64)(i64)dlt + (A.cpx.at(k, room, g0 + j + 1) - A.cpx.at(k, room, g0 + j));
+                cur = j + 1;
+            }
+            a_start = p; first_seg = false;
         }
         if (!FILL) A.cell_nruns[cell] = nruns;
         else if (ls % NUTSB_UCHUNK == 0) {
             const u32 chunks = (users_r + NUTSB_UCHUNK - 1) / NUTSB_UCHUNK;
             const u32 ls_end = ls + NUTSB_UCHUNK < users_r ? ls + NUTSB_UCHUNK : users_r;
             const u64 r_end = A.run_off[cell + (ls_end - ls)];
-            ItemDesc d;
-            d.on_src = A.cpx.vp_on[g0]; d.on_len = (u32)(A.cpx.vp_on[g0 + nb] - d.on_src);
-            const u64 o0 = A.cpx.vp_off[g0];
-            d.off_src = A.off_base + o0; d.off_len = (u32)(A.cpx.vp_off[g0 + nb] - o0);
+            ItemDesc d;                                       // a run may reach up to 31 bytes back into the previous tile
+            const u64 n0 = A.cpx.vp_on[g0], o0 = A.cpx.vp_off[g0];
+            const u32 xn = n0 < 32 ? (u32)n0 : 32u, xo = o0 < 32 ? (u32)o0 : 32u;
+            d.on_src = n0 - xn; d.on_len = (u32)(A.cpx.vp_on[g0 + nb] - n0) + xn;
+            d.off_src = A.off_base + o0 - xo; d.off_len = (u32)(A.cpx.vp_off[g0 + nb] - o0) + xo;
             d.run_begin = (u32)r_out; d.run_cnt = (u32)(r_end - r_out);
             A.items[A.geo.room_item_off[room] + t * chunks + ls / NUTSB_UCHUNK] = d;
         }
@@ -570,127 +634,12 @@ k_plan(PlanArgs A)
     }
 }
 
-// ---- write_user's byte machine, one thread per string ------------------------------------
-// Restates nuts333.c:1315-1365.  The string sits in shared memory; words that
-// hold none of '~' '/' '\n' are copied four bytes at a time, the rest goes
-// through the byte-wise machine.  Emits the colour-on rendering, the colour-off
-// rendering, or both in one pass (the parse is shared).
-__device__ __forceinline__ u32 nutsb_special_mask(u32 w)
-{
-    // 0x80 in every byte of w that is '~', '/' or '\n' -- exact per byte (the cheaper
-    // (y-0x01..)&~y form can flag the byte above a match, e.g. the '.' of "/.")
-    const u32 M = 0x7f7f7f7fu;
-    const u32 y0 = w ^ 0x7e7e7e7eu, y1 = w ^ 0x2f2f2f2fu, y2 = w ^ 0x0a0a0a0au;
-    const u32 t0 = ((y0 & M) + M) | y0, t1 = ((y1 & M) + M) | y1, t2 = ((y2 & M) + M) | y2;
-    return ~((t0 & t1 & t2) | M);
-}
-
 // Bytes of colcode[k] (nuts333.h:237-246), little-endian in one register pair.
 __device__ __forceinline__ u64 nutsb_code_pack(int k)
 {
     if (k < 5) return 0x1bull | ((u64)'[' << 8) | ((u64)('0' + ((0x75410u >> (4 * k)) & 0xf)) << 16) | ((u64)'m' << 24);
     return 0x1bull | ((u64)'[' << 8) | ((u64)(k < 13 ? '3' : '4') << 16) | ((u64)('0' + ((k - 5) & 7)) << 24) | ((u64)'m' << 32);
 }
-#define NUTSB_RESET_PACK 0x6d305b1bull     /* ESC [ 0 m */
-
-// One step consumes the rest of the current aligned word up to and including its
-// first special byte ('~', '/', '\n'): the plain bytes before it pass through
-// (nuts333.c:1355), the special byte goes through the machine (c:1316-1354).
-// What a step emits is "up to 4 plain bytes, then up to 6 bytes" chosen by the
-// recipient's colour setting, stored with predicated byte stores -- one code
-// path, so the strings of a warp stay converged; only a '~' that is not escaped
-// takes a branch (the table lookup).  The string must sit in a window that
-// starts at a 4-byte boundary (nutsb_lane_stage / nutsb_warp_stage); bytes of
-// the window outside the string are never interpreted.  Returns the rendered length.
-__device__ __forceinline__ u32 nutsb_render1(const u8 *s, u32 n, bool colour, u32 oflags, u8 *out, const u8 *tab)
-{
-    if (oflags & NUTSB_OF_PLAIN) colour = false;                 // more(NULL,...): c:2259
-    u32 i = 0, o = 0;
-    while (i < n) {
-        const u8 *p = s + i;
-        const u32 al = (u32)(size_t)p & 3u;
-        const u32 w = *(const u32 *)(p - al);
-        const u32 rem = n - i;
-        const u32 top = al + rem < 4 ? al + rem : 4;             // bytes [al, top) of w belong to the string
-        const u32 range = (0xffffffffu << (8 * al)) & (0xffffffffu >> (8 * (4 - top)));
-        const u32 sm = nutsb_special_mask(w) & range;
-        const u32 q = sm ? ((u32)(__ffs((int)sm) - 1) >> 3) : top;   // first special byte, or end of the word
-        const u32 np = q - al;                                   // plain bytes passed through
-        const u32 pv = w >> (8 * al);
-        u32 adv = np, len = 0;
-        u64 val = 0;
-        if (sm) {
-            const u32 c = (w >> (8 * q)) & 0xffu;
-            const u32 j = i + np;                                // index of the special byte
-            adv = np + 1; len = 1; val = c;
-            if (c == '\n') {                                                   /* c:1316-1326 */
-                len = colour ? 6u : 2u;
-                val = colour ? (NUTSB_RESET_PACK | ((u64)'\n' << 32) | ((u64)'\r' << 40)) : (u64)((u32)'\n' | ((u32)'\r' << 8));
-            } else if (c == '/') {                                             /* c:1330 */
-                if (j + 1 < n && s[j + 1] == '~') len = 0;
-            } else if (c == '~') {                                             /* c:1331-1354 */
-                if (!(j > 0 && s[j - 1] == '/') && j + 2 < n) {
-                    const int k = nutsb_code(tab, s[j + 1], s[j + 2]);
-                    if (k >= 0) { adv = np + 3; len = colour ? nutsb_code_len(k) : 0u; val = nutsb_code_pack(k); }
-                }
-            }
-        }
-        u8 *d = out + o;
-        if (np > 0) d[0] = (u8)pv;
-        if (np > 1) d[1] = (u8)(pv >> 8);
-        if (np > 2) d[2] = (u8)(pv >> 16);
-        if (np > 3) d[3] = (u8)(pv >> 24);
-        d += np;
-        if (len > 0) d[0] = (u8)val;
-        if (len > 1) d[1] = (u8)(val >> 8);
-        if (len > 2) d[2] = (u8)(val >> 16);
-        if (len > 3) d[3] = (u8)(val >> 24);
-        if (len > 4) d[4] = (u8)(val >> 32);
-        if (len > 5) d[5] = (u8)(val >> 40);
-        o += np + len; i += adv;
-    }
-    if (colour && !(oflags & NUTSB_OF_PAGER)) {                  /* c:1365; the pager has no such reset */
-        out[o] = 0x1b; out[o + 1] = '['; out[o + 2] = '0'; out[o + 3] = 'm'; o += 4;
-    }
-    return o;
-}
-
-// One lane stages its own string (32-bit loads; lanes of a warp walk 32 different
-// strings, L1 absorbs the overlap).
-__device__ __forceinline__ void nutsb_lane_stage(u8 *dst, const u8 *src, u32 n)
-{
-    const u32 a = (u32)((size_t)src & 3);
-    const u32 *g = (const u32 *)(src - a);
-    const u32 nw = (a + n + 3) >> 2;
-    for (u32 w = 0; w < nw; ++w) ((u32 *)dst)[w] = __ldg(g + w);
-}
-
-// One lane copies its own rendered string from shared memory to an arbitrary
-// byte address: head bytes to a 4-byte boundary, realigned 32-bit stores, tail.
-__device__ __forceinline__ void nutsb_lane_copy(u8 *dst, const u8 *src, u32 n)
-{
-    u32 head = (u32)((4 - ((size_t)dst & 3)) & 3);
-    if (head > n) head = n;
-    for (u32 q = 0; q < head; ++q) dst[q] = src[q];
-    dst += head; src += head; n -= head;
-    const u32 nw = n >> 2;
-    const u32 sm = (u32)((size_t)src & 3);
-    const u32 *sa = (const u32 *)(src - sm);
-    const u32 bsh = 8 * sm;
-    u32 prev = nw ? sa[0] : 0;
-    for (u32 j = 0; j < nw; ++j) {
-        const u32 nxt = sa[j + 1];
-        ((u32 *)dst)[j] = __funnelshift_r(prev, nxt, bsh);
-        prev = nxt;
-    }
-    for (u32 q = 4 * nw; q < n; ++q) dst[q] = src[q];
-}
-
-// Staging convention: a string is copied into shared memory with 32-bit loads as the window
-// of aligned words that holds it, so the window starts 4-byte aligned and the string begins
-// at window + ((size_t)src & 3).  Whole words are read: up to 3 bytes either side of the
-// string (inside the packed text allocation).  Size of that window:
-__device__ __forceinline__ u32 nutsb_stage_bytes(const u8 *src, u32 n) { return (((u32)((size_t)src & 3)) + n + 3) & ~3u; }
 
 // ---- warp copy: shared -> global at arbitrary byte alignment --------------------------
 // The destination's first partial 16-byte chunk and its last are stored byte by
@@ -749,35 +698,25 @@ __device__ __forceinline__ void nutsb_group_copy(u8 *dst, const u8 *src, u32 n, 
 }
 __device__ __forceinline__ void nutsb_warp_copy(u8 *dst, const u8 *src, u32 n, int lane) { nutsb_group_copy<32>(dst, src, n, lane); }
 
-// ---- G. render the slab ---------------------------------------------------------------------
-// Every slab op is rendered ONCE per colour setting (the reference renders it once
-// per recipient, c:1427 -> c:1315) into the slab buffer: the colour-on rendering of
-// slab rank g at slab + vp_on[g], the colour-off one at slab + off_base + vp_off[g].
-//
+// ---- G. render ------------------------------------------------------------------------------
 // write_user's byte machine (c:1315-1365) is position-local: what
-// byte i emits depends on bytes i-3..i+2 only.  So a warp takes NUTSB_REN_OPS
-// consecutive slab ops as ONE flat array of aligned 32-bit words and renders 32
-// words per round, lane = word, whatever the string lengths: every lane classifies
-// its four bytes, a warp scan of the emitted lengths places them, and the bytes go
-// into the warp's private shared-memory windows, flushed to the slab with 16-byte
-// stores whenever a window could overflow in the next round.  No text staging: a
-// lane reads its word and the two neighbouring words straight from the packed text
-// (consecutive lanes read consecutive words of the same string).
-#define NUTSB_REN_THREADS 256
-#define NUTSB_REN_OPS     16                       // slab ops per warp (<= 32)
-#define NUTSB_REN_ON_WIN  3072                     // per-warp window, colour on  (a round emits <= 32*28 bytes)
-#define NUTSB_REN_OFF_WIN 1536                     // per-warp window, colour off (a round emits <= 32*8 bytes)
+// byte i emits depends on bytes i-3..i+2 only.  So a warp takes up to 32 strings as
+// ONE flat array of aligned 32-bit words and renders 32 words per round, lane =
+// word, whatever the string lengths: every lane finds the '~' '/' '\n' bytes of its
+// word with SWAR masks, resolves the (rare) '~XX' commands against the table, a warp
+// scan of the emitted lengths places the bytes, and they go into the warp's private
+// shared-memory windows, flushed through a sink whenever a window could overflow in
+// the next round.  No text staging: a lane reads its word straight from the packed
+// text (consecutive lanes read consecutive words of the same string) and gets the
+// neighbouring words from the neighbouring lanes.
+//
+// BOTH = true : both renderings (colour on -> w_on, colour off -> w_off)   [k_render]
+// BOTH = false: one rendering, in the colour setting of bit NUTSB_FL_COLOUR of fl  [k_direct]
+#define NUTSB_REN_ON_WIN    3072                   // per-warp window, colour on  (a round emits <= 32*28 bytes)
+#define NUTSB_REN_OFF_WIN   1536                   // per-warp window, colour off (a round emits <= 32*8 bytes)
 #define NUTSB_REN_ON_ROUND  (32 * 28)
 #define NUTSB_REN_OFF_ROUND (32 * 8)
-
-struct RenderArgs {
-    OpsView ops; const u8 *codetab;
-    const u32 *bl_op; const u64 *vp_on, *vp_off;
-    const u32 *n_slab;
-    u8 *slab; u64 off_base;
-    u64 *counters;               // [2] source bytes read
-    u32 *status;
-};
+#define NUTSB_FL_COLOUR     0x100u                 // internal: the rendering wanted is the colour-on one
 
 // 0xff in byte k of the result iff lo <= wb + k < hi (window byte coordinates)
 __device__ __forceinline__ u32 nutsb_keep_mask(i32 wb, i32 lo, i32 hi)
@@ -789,56 +728,154 @@ __device__ __forceinline__ u32 nutsb_keep_mask(i32 wb, i32 lo, i32 hi)
     return a & b;
 }
 
-// Context of one lane: pv | x | nx = window words wi-1, wi, wi+1 with every byte outside
-// the string zeroed.  NUTSB_CTX(j), j in [-3, 5], is the byte j positions from x's byte 0.
-#define NUTSB_CTX(j) ((j) < 0 ? (pv >> (8 * (((j) + 4) & 3))) & 0xffu : (j) < 4 ? (x >> (8 * ((j) & 3))) & 0xffu : (nx >> (8 * (((j) - 4) & 3))) & 0xffu)
+// Lane q < cnt describes string q: window = the aligned words that hold it (gw = address of
+// the first, meta = NUTSB_FLAT_META(al, n, fl): al = offset of the string in it, n = length,
+// fl = op flags | NUTSB_FL_COLOUR; nw = words, at least 1).  sink.on(window, bytes) /
+// sink.off(window, bytes) take the rendered bytes in order; every string's rendering is
+// contiguous in that byte sequence.
+#define NUTSB_FLAT_META(al, n, fl) ((u32)(al) | ((u32)(n) << 2) | ((u32)(fl) << 14))     /* n <= NUTSB_MAX_TEXT < 4096 */
 
-// What position k of the lane's word emits (SURVEY.md A.1's table).  on_len/off_len in
-// bytes; von = the colour-on bytes, little-endian; the colour-off bytes are "\n\r"
-// (off_len 2) or the byte itself (off_len 1).
-#define NUTSB_CLASSIFY(k, valid, colour, on_len, off_len, von)                                               \
-    do {                                                                                                     \
-        const u32 c_ = NUTSB_CTX(k);                                                                         \
-        on_len = 0; off_len = 0; von = c_;                                                                   \
-        if (valid) {                                                                                         \
-            on_len = 1; off_len = 1;                                                                         \
-            if (c_ == '\n') {                                                   /* c:1316-1326 */            \
-                off_len = 2;                                                                                 \
-                if (colour) { on_len = 6; von = NUTSB_RESET_PACK | ((u64)'\n' << 32) | ((u64)'\r' << 40); }   \
-                else { on_len = 2; von = (u64)((u32)'\n' | ((u32)'\r' << 8)); }                               \
-            } else if (c_ == '/') {                                             /* c:1330 */                 \
-                if (NUTSB_CTX((k) + 1) == '~') { on_len = 0; off_len = 0; }                                  \
-            } else if (c_ == '~') {                                             /* c:1331-1354 */            \
-                if (NUTSB_CTX((k) - 1) != '/') {                                                             \
-                    const int kk_ = nutsb_code(tab, (u8)NUTSB_CTX((k) + 1), (u8)NUTSB_CTX((k) + 2));         \
-                    if (kk_ >= 0) { off_len = 0; on_len = colour ? nutsb_code_len(kk_) : 0u; von = nutsb_code_pack(kk_); } \
-                }                                                                                            \
-            } else if (c_ - 'A' < 26u) {                                        /* a command's two letters */ \
-                const bool m1_ = NUTSB_CTX((k) - 1) == '~' && NUTSB_CTX((k) - 2) != '/' &&                   \
-                                 nutsb_code(tab, (u8)c_, (u8)NUTSB_CTX((k) + 1)) >= 0;                       \
-                const bool m2_ = NUTSB_CTX((k) - 2) == '~' && NUTSB_CTX((k) - 3) != '/' &&                   \
-                                 nutsb_code(tab, (u8)NUTSB_CTX((k) - 1), (u8)c_) >= 0;                       \
-                if (m1_ || m2_) { on_len = 0; off_len = 0; }                                                 \
-            }                                                                                                \
-        }                                                                                                    \
-    } while (0)
+template <bool BOTH, class Sink>
+__device__ __forceinline__ void nutsb_flat_render(u32 cnt, u32 meta, u64 gw, u32 nw,
+                                                  u8 *w_on, u8 *w_off, const u8 *tab, int lane, Sink &sink)
+{
+    u32 inc = nw;
+    for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(NUTSB_FULL, inc, d); if (lane >= d) inc += t; }
+    const u32 P = inc - nw;                                    // first flat word of string q
+    const u32 W = __shfl_sync(NUTSB_FULL, inc, 31);
+    u32 fill_on = 0, fill_off = 0, qcount = 0;
+    u32 carry_x = 0, carry_m = 0;                              // lane 31's word and command mask of the previous round
 
-#define NUTSB_EMIT_ON(d, len, v)                                                                             \
-    do {                                                                                                     \
-        if (len > 0) (d)[0] = (u8)(v);                                                                       \
-        if (len > 1) (d)[1] = (u8)((v) >> 8);                                                                \
-        if (len > 2) (d)[2] = (u8)((v) >> 16);                                                               \
-        if (len > 3) (d)[3] = (u8)((v) >> 24);                                                               \
-        if (len > 4) (d)[4] = (u8)((v) >> 32);                                                               \
-        if (len > 5) (d)[5] = (u8)((v) >> 40);                                                               \
-        (d) += len;                                                                                          \
-    } while (0)
-#define NUTSB_EMIT_OFF(d, len, c)                                                                            \
-    do {                                                                                                     \
-        if (len > 0) (d)[0] = len == 2 ? (u8)'\n' : (u8)(c);                                                 \
-        if (len > 1) (d)[1] = (u8)'\r';                                                                      \
-        (d) += len;                                                                                          \
-    } while (0)
+    for (u32 F = 0; F < W; F += 32) {
+        // -- which string does flat word F + lane belong to
+        const bool starts = (u32)lane < cnt && P >= F && P < F + 32;
+        const u32 heads = __reduce_or_sync(NUTSB_FULL, starts ? 1u << (P - F) : 0u);
+        u32 q = qcount + (u32)__popc(heads & (0xffffffffu >> (31 - lane))) - 1;
+        qcount += (u32)__popc(heads);
+        if (q >= cnt) q = cnt - 1;
+        const u32 Pq = __shfl_sync(NUTSB_FULL, P, (int)q), mq = __shfl_sync(NUTSB_FULL, meta, (int)q);
+        const u32 *gwq = (const u32 *)(size_t)__shfl_sync(NUTSB_FULL, gw, (int)q);
+        const u32 alq = mq & 3u, nq = (mq >> 2) & 0xfffu, flq = mq >> 14;
+        const u32 endq = alq + nq;                             // window byte after the string's last
+        u32 nwq = (endq + 3) >> 2; if (!nwq) nwq = 1;
+        const bool act = F + lane < W;
+        const u32 wi = F + lane - Pq;
+        // -- the lane's word and its neighbours, bytes outside the string zeroed (a string holds no NUL)
+        const i32 left = (i32)endq - (i32)(4 * wi);            // bytes of this word before the string's end
+        u32 km = left < 4 ? (left > 0 ? (1u << (8 * left)) - 1u : 0u) : 0xffffffffu;
+        if (wi == 0) km &= 0xffffffffu << (8 * alq);
+        if (!act) km = 0;
+        const u32 x = act ? __ldg(gwq + wi) & km : 0u;
+        u32 pv = __shfl_up_sync(NUTSB_FULL, x, 1), nx = __shfl_down_sync(NUTSB_FULL, x, 1);
+        if (lane == 0) pv = carry_x;
+        if (lane == 31) nx = (act && wi + 1 < nwq) ? __ldg(gwq + wi + 1) & (left < 8 ? (1u << (8 * (left - 4))) - 1u : 0xffffffffu) : 0u;
+        if (wi == 0) pv = 0;
+        if (wi + 1 >= nwq) nx = 0;
+        const bool colour = (flq & NUTSB_FL_COLOUR) && !(flq & NUTSB_OF_PLAIN);     // more(NULL,...): c:2259
+        const bool tail = act && wi == nwq - 1 && colour && !(flq & NUTSB_OF_PAGER);   // c:1365; the pager has no such reset
+
+        // -- special bytes of the word: 0x80 per byte
+        const u32 tl = nutsb_zero_bytes(x ^ 0x7e7e7e7eu), sl = nutsb_zero_bytes(x ^ 0x2f2f2f2fu), nl = nutsb_zero_bytes(x ^ 0x0a0a0a0au);
+        const u32 t_next = (tl >> 8) | ((nx & 0xffu) == '~' ? 0x80000000u : 0u);      // byte k+1 is '~'
+        const u32 s_prev = (sl << 8) | ((pv >> 24) == '/' ? 0x80u : 0u);             // byte k-1 is '/'
+        const u32 slash_drop = sl & t_next;                                          // c:1330
+        u32 ta = tl & ~s_prev;                                                       // '~' not after '/': c:1331-1333
+        u32 mm = 0, m5 = 0, codes = 0;                    // matched commands: mask, mask of the 5-byte codes, index per byte
+        if (ta) {
+            const u64 xn = (u64)x | ((u64)nx << 32);
+            do {
+                const u32 bit = (u32)__ffs((int)ta) - 1;                            // 7, 15, 23 or 31
+                ta &= ta - 1;
+                const int kk = nutsb_code(tab, (u8)(xn >> (bit + 1)), (u8)(xn >> (bit + 9)));   // c:1337-1352
+                if (kk >= 0) { mm |= 1u << bit; codes |= (u32)kk << (bit - 7); if (kk >= 5) m5 |= 1u << bit; }
+            } while (ta);
+        }
+        u32 mp = __shfl_up_sync(NUTSB_FULL, mm, 1);
+        if (lane == 0) mp = carry_m;
+        if (wi == 0) mp = 0;
+        const u32 consumed = (mm << 8) | (mm << 16) | (mp >> 24) | ((mp >> 16) & 0x8080u);   // a command's two letters
+        const u32 plain = (km & 0x80808080u) & ~(slash_drop | consumed | mm | nl);
+        // -- bytes emitted per position, one count per byte of the register (SURVEY.md A.1's table)
+        const u32 l_off = (plain >> 7) + 2 * (nl >> 7);
+        const u32 l_on = colour ? (plain >> 7) + 6 * (nl >> 7) + 4 * (mm >> 7) + (m5 >> 7) : l_off;
+        const u32 t_off = (l_off * 0x01010101u) >> 24;
+        const u32 t_on = ((l_on * 0x01010101u) >> 24) + (tail ? 4u : 0u);
+        u32 sc = BOTH ? (t_on | (t_off << 16)) : t_on;
+        for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(NUTSB_FULL, sc, d); if (lane >= d) sc += t; }
+        const u32 tot = __shfl_sync(NUTSB_FULL, sc, 31);
+        carry_x = __shfl_sync(NUTSB_FULL, x, 31); carry_m = __shfl_sync(NUTSB_FULL, mm, 31);
+
+        // -- emit: the plain bytes at their offsets, then the few '\n' and commands
+        {
+            u8 *const d = w_on + fill_on + (BOTH ? (sc & 0xffffu) : sc) - t_on;
+            u8 *const e = w_off + fill_off + (sc >> 16) - t_off;
+            const u32 p_on = l_on * 0x01010100u, p_off = l_off * 0x01010100u;     // exclusive prefix per position
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (plain & (0x80u << (8 * k))) {
+                    const u8 c = (u8)(x >> (8 * k));
+                    d[(p_on >> (8 * k)) & 0xffu] = c;
+                    if (BOTH) e[(p_off >> (8 * k)) & 0xffu] = c;
+                }
+            }
+            u32 sp = colour ? (nl | mm) : nl;
+            while (sp) {
+                const u32 bit = (u32)__ffs((int)sp) - 1, k8 = bit - 7;
+                sp &= sp - 1;
+                const bool is_nl = (nl >> bit) & 1u;
+                u8 *dd = d + ((p_on >> k8) & 0xffu);
+                if (is_nl) {                                                     /* c:1316-1326 */
+                    if (colour) { dd[0] = 0x1b; dd[1] = '['; dd[2] = '0'; dd[3] = 'm'; dd += 4; }
+                    dd[0] = '\n'; dd[1] = '\r';
+                    if (BOTH) { u8 *ee = e + ((p_off >> k8) & 0xffu); ee[0] = '\n'; ee[1] = '\r'; }
+                } else {                                                         /* colcode[kk], h:237-246 */
+                    const int kk = (int)((codes >> k8) & 0x1fu);
+                    const u64 v = nutsb_code_pack(kk);
+                    dd[0] = 0x1b; dd[1] = '['; dd[2] = (u8)(v >> 16); dd[3] = (u8)(v >> 24);
+                    if (kk >= 5) dd[4] = 'm';
+                }
+            }
+            if (tail) { u8 *dd = d + t_on - 4; dd[0] = 0x1b; dd[1] = '['; dd[2] = '0'; dd[3] = 'm'; }
+        }
+        fill_on += BOTH ? (tot & 0xffffu) : tot; if (BOTH) fill_off += tot >> 16;
+        const bool last = F + 32 >= W;
+        if (last || fill_on + NUTSB_REN_ON_ROUND > NUTSB_REN_ON_WIN) {
+            __syncwarp();
+            sink.on(w_on, fill_on, lane);
+            fill_on = 0;
+            __syncwarp();
+        }
+        if (BOTH && (last || fill_off + NUTSB_REN_OFF_ROUND > NUTSB_REN_OFF_WIN)) {
+            __syncwarp();
+            sink.off(w_off, fill_off, lane);
+            fill_off = 0;
+            __syncwarp();
+        }
+    }
+}
+
+// Every slab op is rendered ONCE per colour setting (the reference renders it once
+// per recipient, c:1427 -> c:1315) into the slab buffer: the colour-on rendering of
+// slab rank g at slab + vp_on[g], the colour-off one at slab + off_base + vp_off[g].
+// A warp takes NUTSB_REN_OPS consecutive slab ops: its output is one contiguous
+// piece of each rendering, written with 16-byte stores.
+#define NUTSB_REN_THREADS 256
+#define NUTSB_REN_OPS     32                       // slab ops per warp (<= 32)
+
+struct RenderArgs {
+    OpsView ops; const u8 *codetab;
+    const u32 *bl_op; const u64 *vp_on, *vp_off;
+    const u32 *n_slab;
+    u8 *slab; u64 off_base;
+    u64 *counters;               // [2] source bytes read
+    u32 *status;
+};
+
+struct SlabSink {
+    u8 *g_on, *g_off;
+    __device__ __forceinline__ void on(const u8 *w, u32 nbytes, int lane) { nutsb_warp_copy(g_on, w, nbytes, lane); g_on += nbytes; }
+    __device__ __forceinline__ void off(const u8 *w, u32 nbytes, int lane) { nutsb_warp_copy(g_off, w, nbytes, lane); g_off += nbytes; }
+};
 
 __global__ void __launch_bounds__(NUTSB_REN_THREADS)
 k_render(RenderArgs A)
@@ -848,96 +885,34 @@ k_render(RenderArgs A)
     __shared__ u8 s_tab[NUTSB_CODETAB_BYTES];
     for (int i = threadIdx.x; i < NUTSB_CODETAB_BYTES; i += NUTSB_REN_THREADS) s_tab[i] = A.codetab[i];
     __syncthreads();
-    const u8 *const tab = s_tab;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 n_slab = *A.n_slab;
-    const u32 gbase = (blockIdx.x * (NUTSB_REN_THREADS / 32) + (u32)warp) * NUTSB_REN_OPS;
-    if (gbase >= n_slab) return;                               // whole warp leaves together
-    const u32 cnt = n_slab - gbase < NUTSB_REN_OPS ? n_slab - gbase : NUTSB_REN_OPS;
-
-    // -- lane q < cnt holds op q: window = the aligned words that hold the string
-    u32 al = 0, n = 0, fl = 0, nw = 0; u64 gw = 0;
-    if ((u32)lane < cnt) {
-        const u32 op = A.bl_op[gbase + lane];
-        const u64 t0 = A.ops.toff[op];
-        n = (u32)(A.ops.toff[op + 1] - t0);
-        const u8 *src = A.ops.text + t0;
-        al = (u32)((size_t)src & 3);
-        gw = (u64)(size_t)(src - al);
-        nw = (al + n + 3) >> 2; if (!nw) nw = 1;                // an empty string still ends in a reset (c:1365)
-        fl = A.ops.flags[op];
-    }
-    u32 inc = nw;
-    for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(NUTSB_FULL, inc, d); if (lane >= d) inc += t; }
-    const u32 P = inc - nw;                                    // first flat word of op q
-    const u32 W = __shfl_sync(NUTSB_FULL, inc, 31);
-    const u64 on0 = A.vp_on[gbase], off0 = A.vp_off[gbase];
-    u8 *g_on = A.slab + on0, *g_off = A.slab + A.off_base + off0;
-    u8 *const w_on = s_on[warp], *const w_off = s_off[warp];
-    u32 fill_on = 0, fill_off = 0, qcount = 0;
-
-    for (u32 F = 0; F < W; F += 32) {
-        // -- which op does flat word F + lane belong to
-        const bool starts = (u32)lane < cnt && P >= F && P < F + 32;
-        const u32 heads = __reduce_or_sync(NUTSB_FULL, starts ? 1u << (P - F) : 0u);
-        u32 q = qcount + (u32)__popc(heads & (0xffffffffu >> (31 - lane))) - 1;
-        qcount += (u32)__popc(heads);
-        if (q >= cnt) q = cnt - 1;
-        const u32 Pq = __shfl_sync(NUTSB_FULL, P, (int)q), alq = __shfl_sync(NUTSB_FULL, al, (int)q);
-        const u32 nq = __shfl_sync(NUTSB_FULL, n, (int)q), flq = __shfl_sync(NUTSB_FULL, fl, (int)q);
-        const u32 nwq = __shfl_sync(NUTSB_FULL, nw, (int)q);
-        const u32 *gwq = (const u32 *)(size_t)__shfl_sync(NUTSB_FULL, gw, (int)q);
-        const bool act = F + lane < W;
-        const u32 wi = F + lane - Pq;
-        u32 x = 0, pv = 0, nx = 0;
-        const i32 lo = (i32)alq, hi = (i32)(alq + nq);
-        if (act) {
-            x = __ldg(gwq + wi) & nutsb_keep_mask((i32)(4 * wi), lo, hi);
-            if (wi > 0) pv = __ldg(gwq + wi - 1) & nutsb_keep_mask((i32)(4 * wi) - 4, lo, hi);
-            if (wi + 1 < nwq) nx = __ldg(gwq + wi + 1) & nutsb_keep_mask((i32)(4 * wi) + 4, lo, hi);
+    // a warp takes units of NUTSB_REN_OPS slab ops, grid-strided (the grid may be smaller than the work:
+    // beside the planning kernels k_render runs with a few blocks per SM)
+    const u32 wstride = gridDim.x * (NUTSB_REN_THREADS / 32) * NUTSB_REN_OPS;
+    u64 nsum = 0;
+    for (u32 gbase = (blockIdx.x * (NUTSB_REN_THREADS / 32) + (u32)warp) * NUTSB_REN_OPS; gbase < n_slab; gbase += wstride) {
+        const u32 cnt = n_slab - gbase < NUTSB_REN_OPS ? n_slab - gbase : NUTSB_REN_OPS;
+        u32 meta = 0, n = 0, nw = 0; u64 gw = 0;
+        if ((u32)lane < cnt) {
+            const u32 op = A.bl_op[gbase + lane];
+            const u64 t0 = A.ops.toff[op];
+            n = (u32)(A.ops.toff[op + 1] - t0);
+            const u8 *src = A.ops.text + t0;
+            const u32 al = (u32)((size_t)src & 3);
+            gw = (u64)(size_t)(src - al);
+            nw = (al + n + 3) >> 2; if (!nw) nw = 1;            // an empty string still ends in a reset (c:1365)
+            meta = NUTSB_FLAT_META(al, n, A.ops.flags[op] | NUTSB_FL_COLOUR);
         }
-        const bool colour = !(flq & NUTSB_OF_PLAIN);                        // more(NULL,...): c:2259
-        const bool tail = act && wi == nwq - 1 && colour && !(flq & NUTSB_OF_PAGER);   // c:1365; the pager has no such reset
-        const u32 vm = act ? nutsb_keep_mask((i32)(4 * wi), lo, hi) : 0u;
-        u32 on0_, on1_, on2_, on3_, of0_, of1_, of2_, of3_; u64 v0_, v1_, v2_, v3_;
-        NUTSB_CLASSIFY(0, (vm & 0xffu) != 0, colour, on0_, of0_, v0_);
-        NUTSB_CLASSIFY(1, (vm & 0xff00u) != 0, colour, on1_, of1_, v1_);
-        NUTSB_CLASSIFY(2, (vm & 0xff0000u) != 0, colour, on2_, of2_, v2_);
-        NUTSB_CLASSIFY(3, (vm & 0xff000000u) != 0, colour, on3_, of3_, v3_);
-        const u32 t_on = on0_ + on1_ + on2_ + on3_ + (tail ? 4u : 0u), t_off = of0_ + of1_ + of2_ + of3_;
-        u32 sc = t_on | (t_off << 16);
-        for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(NUTSB_FULL, sc, d); if (lane >= d) sc += t; }
-        const u32 tot = __shfl_sync(NUTSB_FULL, sc, 31);
-        {
-            u8 *d = w_on + fill_on + (sc & 0xffffu) - t_on;
-            NUTSB_EMIT_ON(d, on0_, v0_); NUTSB_EMIT_ON(d, on1_, v1_); NUTSB_EMIT_ON(d, on2_, v2_); NUTSB_EMIT_ON(d, on3_, v3_);
-            if (tail) { d[0] = 0x1b; d[1] = '['; d[2] = '0'; d[3] = 'm'; }
-            u8 *e = w_off + fill_off + (sc >> 16) - t_off;
-            NUTSB_EMIT_OFF(e, of0_, v0_); NUTSB_EMIT_OFF(e, of1_, v1_); NUTSB_EMIT_OFF(e, of2_, v2_); NUTSB_EMIT_OFF(e, of3_, v3_);
-        }
-        fill_on += tot & 0xffffu; fill_off += tot >> 16;
-        const bool last = F + 32 >= W;
-        if (last || fill_on + NUTSB_REN_ON_ROUND > NUTSB_REN_ON_WIN) {
-            __syncwarp();
-            nutsb_warp_copy(g_on, w_on, fill_on, lane);
-            g_on += fill_on; fill_on = 0;
-            __syncwarp();
-        }
-        if (last || fill_off + NUTSB_REN_OFF_ROUND > NUTSB_REN_OFF_WIN) {
-            __syncwarp();
-            nutsb_warp_copy(g_off, w_off, fill_off, lane);
-            g_off += fill_off; fill_off = 0;
-            __syncwarp();
-        }
-    }
-    // -- consistency with k_measure's lengths; bytes read
-    if (lane == 0) {
-        if ((u64)(g_on - A.slab) != A.vp_on[gbase + cnt] || (u64)(g_off - A.slab) != A.off_base + A.vp_off[gbase + cnt])
+        SlabSink sink{ A.slab + A.vp_on[gbase], A.slab + A.off_base + A.vp_off[gbase] };
+        nutsb_flat_render<true>(cnt, meta, gw, nw, s_on[warp], s_off[warp], s_tab, lane, sink);
+        // consistency with k_measure's lengths
+        if (lane == 0 && ((u64)(sink.g_on - A.slab) != A.vp_on[gbase + cnt] || (u64)(sink.g_off - A.slab) != A.off_base + A.vp_off[gbase + cnt]))
             atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+        nsum += n;
     }
-    u32 nsum = n;
     for (int d = 16; d; d >>= 1) nsum += __shfl_xor_sync(NUTSB_FULL, nsum, d);
-    if (lane == 0) nutsb_add64(A.counters + 2, (u64)nsum);
+    if (lane == 0 && nsum) nutsb_add64(A.counters + 2, nsum);
 }
 
 // ---- H. fan-out -------------------------------------------------------------------------------
@@ -1002,10 +977,10 @@ k_fanout(FanoutArgs A)
 }
 
 // ---- I. direct ops (write_user) -----------------------------------------------------------
-// One thread per event (events are sorted by recipient).  The direct ops among
-// a block's 256 events are staged, rendered in the recipient's colour setting and
-// copied into the recipient's stream at the offset the event prefix gives -- all
-// three by the op's own thread, in sub-batches sized to shared memory.
+// Events are sorted by recipient.  A warp takes 32 consecutive events; the direct ops among
+// them (even keys) are rendered with the flat renderer in their recipient's colour setting
+// and each rendering is copied into the recipient's stream at the offset the event prefix
+// gives.
 struct DirectArgs {
     OpsView ops; PopView pop; ClassPrefix cpx;
     const u32 *room_b_off, *ev_off;
@@ -1014,95 +989,155 @@ struct DirectArgs {
     const u32 *ev_slot_sorted;      // user slot of each sorted event
     const i32 *sv_delta;
     u8 *out; i64 n_ev;
-    u64 *n_deliveries;              // [0] deliveries, [1] bytes written by k_direct, [2] (k_fanout)
+    u64 *n_deliveries;              // [0] deliveries, [1] bytes written by k_direct, [2] (k_render)
     u32 *status;
+    const u8 *slab; u64 off_base;   // the rendered slab (k_render): source of the seam bytes
+    u32 has_level;
 };
 
 #define NUTSB_DIRECT_THREADS 256
-#define NUTSB_DIR_WTEXT 2560        // per-warp staging bytes  (>= 2000 + 12)
-#define NUTSB_DIR_WOUT  3072        // per-warp rendered bytes
 
-// Warps are independent (no block barrier in the loop): a warp takes 32 consecutive
-// events, the direct ops among them are staged, rendered and copied out by their own
-// lanes through the warp's private shared-memory windows, in sub-batches that fit the
-// windows.  A rendering too large for the window (a 2000-byte string of newlines is
-// 12 KB) is written to the stream directly by its lane.
+struct DirectSink {                 // string q's rendering is bytes [O, O + osz) of the warp's output; it goes to out + p
+    u8 *out; u64 p; u32 O, osz;     // lane q holds string q
+    u32 cnt, done, qf;
+    __device__ __forceinline__ void on(const u8 *w, u32 nbytes, int lane)
+    {
+        const u32 end = done + nbytes;
+        while (qf < cnt) {
+            const u32 Oq = __shfl_sync(NUTSB_FULL, O, (int)qf), zq = __shfl_sync(NUTSB_FULL, osz, (int)qf);
+            const u64 pq = __shfl_sync(NUTSB_FULL, p, (int)qf);
+            if (Oq >= end && zq) break;
+            const u32 x0 = Oq > done ? Oq : done, x1 = Oq + zq < end ? Oq + zq : end;
+            if (x1 > x0) {
+                u8 *dst = out + pq + (x0 - Oq);
+                const u8 *src = w + (x0 - done);
+                const u32 len = x1 - x0;
+                if (len < 192) { for (u32 i = (u32)lane; i < len; i += 32) dst[i] = src[i]; }
+                else nutsb_warp_copy(dst, src, len, lane);
+            }
+            if (Oq + zq <= end) ++qf; else break;
+        }
+        done = end;
+    }
+    __device__ __forceinline__ void off(const u8 *, u32, int) {}
+};
+
 __global__ void __launch_bounds__(NUTSB_DIRECT_THREADS)
 k_direct(DirectArgs A)
 {
-    __shared__ __align__(16) u8 s_text[NUTSB_DIRECT_THREADS / 32][NUTSB_DIR_WTEXT + 32];
-    __shared__ __align__(16) u8 s_out[NUTSB_DIRECT_THREADS / 32][NUTSB_DIR_WOUT + 64];
-    __shared__ u8  s_tab[NUTSB_CODETAB_BYTES];
-    __shared__ u32 s_cnt;
-    __shared__ unsigned long long s_bytes;
+    __shared__ __align__(16) u8 s_on[NUTSB_DIRECT_THREADS / 32][NUTSB_REN_ON_WIN + 64];
+    __shared__ u64 s_gw[NUTSB_DIRECT_THREADS / 32][32], s_p[NUTSB_DIRECT_THREADS / 32][32];
+    __shared__ u32 s_par[NUTSB_DIRECT_THREADS / 32][32][2];
+    __shared__ u8 s_tab[NUTSB_CODETAB_BYTES];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < NUTSB_CODETAB_BYTES; i += NUTSB_DIRECT_THREADS) s_tab[i] = A.pop.codetab[i];
-    if (tid == 0) { s_cnt = 0; s_bytes = 0; }
     __syncthreads();
 
-    const i64 e = (i64)blockIdx.x * NUTSB_DIRECT_THREADS + tid;
-    bool isw = false, colour = false;
-    u64 p = 0; const u8 *src = A.ops.text; u32 n = 0, tsz = 0, osz = 0, oflags = 0;
-    if (e < A.n_ev) {
-        const u32 uk = A.sv_ukey[e];
-        if (!(uk & 1)) {                                   // an odd key is an exclusion
+    u64 c_cnt = 0, c_bytes = 0;
+    for (i64 ebase = ((i64)blockIdx.x * (NUTSB_DIRECT_THREADS / 32) + warp) * 32; ebase < A.n_ev;
+         ebase += (i64)gridDim.x * NUTSB_DIRECT_THREADS) {
+        const i64 e = ebase + lane;
+        bool isw = false, seam = false, first_ev = false, last_ev = false;
+        u64 p = 0, q = 0, gw = 0; u32 n = 0, al = 0, osz = 0, fl = 0;
+        u64 a_start = 0, b_end = 0; const u8 *sa = nullptr, *sb = nullptr;
+        if (e < A.n_ev) {
+            const u32 uk = A.sv_ukey[e];
             const u32 s = A.ev_slot_sorted[e];
             const i32 u = A.pop.slot_user[s];
             const u32 room = (u32)A.pop.user_room[u];
             const i32 k = A.pop.user_cls[u];
             const u32 b0 = A.room_b_off[room];
-            const u32 op = A.sv_op[e];
-            const u64 t0 = A.ops.toff[op];
-            p = A.stream_off[u] + (A.cpx.at(k, room, b0 + (uk >> 1)) - A.cpx.at(k, room, b0))
-              + (A.sv_pre[e] - A.sv_pre[A.ev_off[s]]);
-            src = A.ops.text + t0;
-            n = (u32)(A.ops.toff[op + 1] - t0);
-            colour = (A.pop.slot_cf[s] & NUTSB_UF_COLOUR) != 0;
-            oflags = A.ops.flags[op];
-            isw = true;
-            tsz = nutsb_stage_bytes(src, n);
-            osz = (u32)A.sv_delta[e];
-        }
-    }
-    // inclusive prefixes over the warp's lanes
-    u32 it = tsz, io = osz;
-    for (int d = 1; d < 32; d <<= 1) {
-        const u32 xt = __shfl_up_sync(NUTSB_FULL, it, d), xo = __shfl_up_sync(NUTSB_FULL, io, d);
-        if (lane >= d) { it += xt; io += xo; }
-    }
-    u8 *const wtext = s_text[warp];
-    u8 *const wout = s_out[warp];
-    u32 a = 0;
-    while (a < 32) {
-        const u32 bt = __shfl_sync(NUTSB_FULL, it - tsz, (int)a), bo = __shfl_sync(NUTSB_FULL, io - osz, (int)a);   // exclusive at lane a
-        const bool fits = (u32)lane >= a && it - bt <= NUTSB_DIR_WTEXT && io - bo <= NUTSB_DIR_WOUT;
-        const u32 nofit = __ballot_sync(NUTSB_FULL, (u32)lane >= a && !fits);
-        u32 b = nofit ? (u32)__ffs((int)nofit) - 1 : 32u;          // [a,b) fits the windows
-        if (b == a) {
-            // lane a's rendering alone exceeds the window: stage it, render straight into the stream
-            if ((u32)lane == a && isw) {
-                nutsb_lane_stage(wtext, src, n);
-                if (nutsb_render1(wtext + ((u32)(size_t)src & 3u), n, colour, oflags, A.out + p, s_tab) != osz)
-                    atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+            const u32 cf = A.pop.slot_cf[s];
+            const u32 e0 = A.ev_off[s], e1 = A.ev_off[s + 1];
+            const u64 so_u = A.stream_off[u], cp_b0 = A.cpx.at(k, room, b0), pre0 = A.sv_pre[e0];
+            const u32 j = uk >> 2, ek = uk & 3u, skip = ek != NUTSB_EV_DIRECT;
+            const u64 base = so_u - cp_b0 - pre0;
+            p = base + A.cpx.at(k, room, b0 + j) + A.sv_pre[e];
+            q = base + A.cpx.at(k, room, b0 + j + skip) + A.sv_pre[e + 1];     // where the stream goes on after the event
+            if (ek != NUTSB_EV_SKIP) {                         // a direct op: its rendering fills [p, q)
+                const u32 op = A.sv_op[e];
+                const u64 t0 = A.ops.toff[op];
+                const u8 *src = A.ops.text + t0;
+                n = (u32)(A.ops.toff[op + 1] - t0);
+                al = (u32)((size_t)src & 3);
+                gw = (u64)(size_t)(src - al);
+                fl = A.ops.flags[op] | ((cf & NUTSB_UF_COLOUR) ? NUTSB_FL_COLOUR : 0u);
+                osz = (u32)(q - p);
+                isw = true;
             }
-            b = a + 1;
-        } else if (isw && (u32)lane >= a && (u32)lane < b) {
-            u8 *win = wtext + (it - tsz - bt);
-            u8 *dst = wout + (io - osz - bo);
-            nutsb_lane_stage(win, src, n);
-            if (nutsb_render1(win + ((u32)(size_t)src & 3u), n, colour, oflags, dst, s_tab) != osz)
-                atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
-            nutsb_lane_copy(A.out + p, dst, osz);
+            // -- seam: the event is a discontinuity in a plain listener's stream.  k_fanout's runs cover whole
+            //    32-byte sectors only; the slab bytes that share a sector with the discontinuity -- the end of the
+            //    stretch before it and the start of the stretch after it -- are written here, together.
+            seam = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
+            if (seam) {
+                const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
+                const u64 *vp = colour ? A.cpx.vp_on : A.cpx.vp_off;
+                const u8 *R = A.slab + (colour ? 0 : A.off_base);
+                first_ev = (u32)e == e0; last_ev = (u32)e + 1 == e1;
+                a_start = so_u; b_end = A.stream_off[u + 1];
+                if (!first_ev && lane == 0) {                  // the other lanes take it from their neighbour
+                    const u32 ukp = A.sv_ukey[e - 1];
+                    a_start = base + A.cpx.at(k, room, b0 + (ukp >> 2) + ((ukp & 3u) != NUTSB_EV_DIRECT)) + A.sv_pre[e];
+                }
+                if (!last_ev && (lane == 31 || e + 1 >= A.n_ev))
+                    b_end = base + A.cpx.at(k, room, b0 + (A.sv_ukey[e + 1] >> 2)) + A.sv_pre[e + 1];
+                sa = R + vp[b0 + j];                           // the stretch before ends where slab op j begins
+                sb = R + vp[b0 + j + skip];                    // after an exclusion the stream goes on with op j+1
+            }
         }
-        __syncwarp();                                       // the windows are reused by the next sub-batch
-        a = b;
+        {
+            // the neighbouring events of the same recipient sit in the neighbouring lanes
+            const u64 q_prev = __shfl_up_sync(NUTSB_FULL, q, 1), p_next = __shfl_down_sync(NUTSB_FULL, p, 1);
+            if (seam && !first_ev && lane > 0) a_start = q_prev;
+            if (seam && !last_ev && lane < 31 && e + 1 < A.n_ev) b_end = p_next;
+            u64 t0 = p & ~(u64)31; if (t0 < a_start) t0 = a_start;
+            u64 h1 = (q + 31) & ~(u64)31; if (h1 > b_end) h1 = b_end;
+            const u32 tlen = seam ? (u32)(p - t0) : 0u, hlen = seam && h1 > q ? (u32)(h1 - q) : 0u;
+            // every piece (< 32 bytes) is copied by the whole warp at once: one store request per piece
+            u32 m = __ballot_sync(NUTSB_FULL, tlen != 0);
+            while (m) {
+                const int i = __ffs((int)m) - 1; m &= m - 1;
+                const u32 len = __shfl_sync(NUTSB_FULL, tlen, i);
+                const u64 dpos = __shfl_sync(NUTSB_FULL, t0, i);
+                const u8 *src = (const u8 *)(size_t)__shfl_sync(NUTSB_FULL, (u64)(size_t)sa, i) - len;
+                if ((u32)lane < len) A.out[dpos + lane] = src[lane];
+            }
+            m = __ballot_sync(NUTSB_FULL, hlen != 0);
+            while (m) {
+                const int i = __ffs((int)m) - 1; m &= m - 1;
+                const u32 len = __shfl_sync(NUTSB_FULL, hlen, i);
+                const u64 dpos = __shfl_sync(NUTSB_FULL, q, i);
+                const u8 *src = (const u8 *)(size_t)__shfl_sync(NUTSB_FULL, (u64)(size_t)sb, i);
+                if ((u32)lane < len) A.out[dpos + lane] = src[lane];
+            }
+        }
+        // -- compact the warp's direct ops to lanes 0..cnt-1
+        const u32 wmask = __ballot_sync(NUTSB_FULL, isw);
+        const u32 cnt = (u32)__popc(wmask);
+        if (!cnt) continue;                                    // whole warp
+        if (isw) {
+            const u32 r = (u32)__popc(wmask & ((1u << lane) - 1));
+            s_gw[warp][r] = gw; s_p[warp][r] = p;
+            s_par[warp][r][0] = NUTSB_FLAT_META(al, n, fl); s_par[warp][r][1] = osz;
+        }
+        __syncwarp();
+        u32 nw = 0, meta = 0;
+        osz = 0; gw = 0; p = 0;
+        if ((u32)lane < cnt) {
+            gw = s_gw[warp][lane]; p = s_p[warp][lane];
+            meta = s_par[warp][lane][0]; osz = s_par[warp][lane][1];
+            nw = ((meta & 3u) + ((meta >> 2) & 0xfffu) + 3) >> 2; if (!nw) nw = 1;
+        }
+        __syncwarp();
+        u32 inc = osz;
+        for (int d = 1; d < 32; d <<= 1) { const u32 t = __shfl_up_sync(NUTSB_FULL, inc, d); if (lane >= d) inc += t; }
+        const u32 total = __shfl_sync(NUTSB_FULL, inc, 31);
+        DirectSink sink{ A.out, p, inc - osz, osz, cnt, 0u, 0u };
+        nutsb_flat_render<false>(cnt, meta, gw, nw, s_on[warp], (u8 *)nullptr, s_tab, lane, sink);
+        if (lane == 0 && sink.done != total) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
+        c_cnt += cnt; c_bytes += total;
     }
-    const u32 wcnt = (u32)__popc(__ballot_sync(NUTSB_FULL, isw));
-    u32 wbytes = isw ? osz : 0;
-    for (int d = 16; d; d >>= 1) wbytes += __shfl_xor_sync(NUTSB_FULL, wbytes, d);
-    if (lane == 0 && wcnt) { atomicAdd(&s_cnt, wcnt); atomicAdd(&s_bytes, (unsigned long long)wbytes); }
-    __syncthreads();
-    if (tid == 0 && s_cnt) { nutsb_add64(A.n_deliveries, (u64)s_cnt); nutsb_add64(A.n_deliveries + 1, (u64)s_bytes); }
+    if (lane == 0 && c_cnt) { nutsb_add64(A.n_deliveries, c_cnt); nutsb_add64(A.n_deliveries + 1, c_bytes); }
 }
 
 // ---- stream digests ------------------------------------------------------------------------

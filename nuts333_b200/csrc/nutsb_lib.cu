@@ -47,10 +47,13 @@ struct ClassSet {                    // one class granularity (with / without le
 struct nutsb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr; bool own_stream = true;
+    cudaStream_t side = nullptr; bool overlap = true;     // k_render / k_direct run beside the plan / the fan-out ...
+    int side_render = 8, side_direct = 8;                 // ... with this many blocks per SM
+    cudaEvent_t dep[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
     std::string err;
     bool profiling = false; nutsb_timing tm{};
-    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[12] = {};
 
     // tables
     DBuf d_codetab;
@@ -149,6 +152,11 @@ struct InEntryPacked {
     __device__ u64 operator()(i64 i) const { const u32 f = info[i]; return (u64)(f & 1u) | ((u64)((f >> 1) != 0) << 32); }
 };
 struct InSlabLen { const u32 *len, *bl_op; __device__ u64 operator()(i64 g) const { return len[bl_op[g]]; } };
+struct InSlabLen2 {                 // both settings in one scan: low word colour on, high word colour off
+    const u32 *len_on, *len_off, *bl_op;
+    __device__ u64 operator()(i64 g) const { const u32 op = bl_op[g]; return (u64)len_on[op] | ((u64)len_off[op] << 32); }
+};
+struct OutSplit { u64 *a, *b; __device__ void operator()(i64 i, u64 ex) const { a[i] = (u32)ex; b[i] = ex >> 32; } };
 struct InClassLen {                 // bytes class column j receives from slab op g
     OpsView ops; const u32 *bl_op, *bl_room, *len_on, *len_off;
     const i32 *room_cls_off; const u8 *cls_flags, *cls_level; i32 j;
@@ -344,6 +352,8 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
     for (DBuf *b : all) release(*b);
     release(c->h_small); release(c->h_off); release(c->h_out);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    for (auto &e : c->dep) if (e) cudaEventDestroy(e);
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -369,12 +379,17 @@ NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
         CK(cudaSetDevice(device));
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+        CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        if (const char *e = getenv("NUTSB_SIDE_RENDER")) c->side_render = std::max(1, atoi(e));     // tuning aids
+        if (const char *e = getenv("NUTSB_SIDE_DIRECT")) c->side_direct = std::max(1, atoi(e));
+        if (const char *e = getenv("NUTSB_OVERLAP")) c->overlap = atoi(e) != 0;
         for (auto &e : c->ev) CK(cudaEventCreate(&e));
+        for (auto &e : c->dep) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_FAN_SMEM));
         u8 tab[NUTSB_CODETAB_BYTES]; build_codetab(tab);
         TRY(upload(c, c->d_codetab, tab, sizeof tab));
         TRY(ensure(c, c->d_status, 64)); TRY(ensure(c, c->d_counts, 64)); TRY(ensure(c, c->d_sizes, sizeof(Sizes)));
-        TRY(ensure(c, c->d_counters, 128));
+        TRY(ensure(c, c->d_counters, 1024));
         TRY(ensure_host(c, c->h_small, 4096));
         {   // the callers' literals (nutsb_speech.cuh)
             c->lits.assign(NUTSB_NLIT, std::string());
@@ -398,6 +413,7 @@ NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
 }
 
 NUTSB_API int nutsb_set_profiling(nutsb_ctx *c, int on) { if (!c) return NUTSB_E_INVAL; c->profiling = on != 0; return NUTSB_OK; }
+NUTSB_API int nutsb_set_overlap(nutsb_ctx *c, int on) { if (!c) return NUTSB_E_INVAL; c->overlap = on != 0; return NUTSB_OK; }
 NUTSB_API int nutsb_get_timing(const nutsb_ctx *c, nutsb_timing *out) { if (!c || !out) return NUTSB_E_INVAL; *out = c->tm; return NUTSB_OK; }
 NUTSB_API int nutsb_set_stream(nutsb_ctx *c, void *s)
 {
@@ -552,6 +568,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     cudaStream_t st = c->stream;
     c->have_streams = false;
     c->tm.launches = 0; c->tm.fanout_launches = 0;
+    if (c->side) CK(cudaStreamSynchronize(c->side));           // idle unless an earlier batch failed half-way
     if (c->profiling) CK(cudaEventRecord(c->ev[0], st));
 
     TRY(ensure(c, c->d_off, ((size_t)U + 1) * 8));
@@ -578,18 +595,22 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     TRY(ensure(c, c->d_len_on, (size_t)n * 4)); TRY(ensure(c, c->d_len_off, (size_t)n * 4));
     TRY(ensure(c, c->d_nrep, (size_t)n * 4)); TRY(ensure(c, c->d_eoff, ((size_t)n + 1) * 8));
     CK(cudaMemsetAsync(c->d_status.p, 0, 64, st));
-    CK(cudaMemsetAsync(c->d_counters.p, 0, 128, st));
+    CK(cudaMemsetAsync(c->d_counters.p, 0, 1024, st));
     u32 *len_on = c->d_len_on.as<u32>(), *len_off = c->d_len_off.as<u32>(), *nrep = c->d_nrep.as<u32>();
     NUTSB_LAUNCH(cdiv(n, NUTSB_MEASURE_THREADS), NUTSB_MEASURE_THREADS, st, k_measure, ops, pop0, len_on, len_off, nrep,
-                 c->d_status.as<u32>()); CKL();
+                 c->d_status.as<u32>(), c->d_counters.as<u64>() + 8); CKL();
     c->tm.launches++;
     TRY(run_scan(c, InU32{nrep}, OutU64{c->d_eoff.as<u64>()}, n, nullptr));
 
     // -- read-back #1: number of (room, op) entries, validation status
     CK(cudaMemcpyAsync(h64, c->d_eoff.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h64 + 64, c->d_counters.as<u64>() + 8, 16 * NUTSB_SLAB_TOT_WAYS, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const u64 E = h64[0]; const u32 status = h32[4];
+    u64 slab_on = 0, slab_off = 0;
+    for (int w = 0; w < NUTSB_SLAB_TOT_WAYS; ++w) { slab_on += h64[64 + 2 * w]; slab_off += h64[65 + 2 * w]; }
+    const u64 off_base = (slab_on + 15) & ~(u64)15;            // the colour-off renderings follow the colour-on ones
     TRY(status_to_error(c, status));
     if (E == 0) return finish_empty();
     if (E >= 0xfffffff0ull) return fail(c, NUTSB_E_RANGE, "more than 2^32 (room, op) entries in one batch%s");
@@ -646,8 +667,12 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
 
     // -- slab prefixes (per colour) and, when classes differ in what they take, per class column
     TRY(ensure(c, c->d_vp_on, (E + 2) * 8)); TRY(ensure(c, c->d_vp_off, (E + 2) * 8));
-    TRY(run_scan(c, InSlabLen{len_on, c->d_bl_op.as<u32>()}, OutU64{c->d_vp_on.as<u64>()}, (i64)E, counts));
-    TRY(run_scan(c, InSlabLen{len_off, c->d_bl_op.as<u32>()}, OutU64{c->d_vp_off.as<u64>()}, (i64)E, counts));
+    if (slab_on < 0xffffffffull) {                             // (slab_off <= slab_on) both prefixes fit 32 bits: one scan
+        TRY(run_scan(c, InSlabLen2{len_on, len_off, c->d_bl_op.as<u32>()}, OutSplit{c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>()}, (i64)E, counts));
+    } else {
+        TRY(run_scan(c, InSlabLen{len_on, c->d_bl_op.as<u32>()}, OutU64{c->d_vp_on.as<u64>()}, (i64)E, counts));
+        TRY(run_scan(c, InSlabLen{len_off, c->d_bl_op.as<u32>()}, OutU64{c->d_vp_off.as<u64>()}, (i64)E, counts));
+    }
     ClassPrefix cpx{ c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(), nullptr, (u64)E + 1, pop.room_cls_off, pop.cls_flags };
     if (!alias) {
         const i32 J = std::max(1, cs.max_per_room);
@@ -658,6 +683,28 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
         }
         cpx.cp = c->d_cp.as<u64>();
     }
+
+    // -- G. render the slab, once per colour setting: needs only the slab list and its prefixes, so it
+    //    runs on the side stream while this one goes on planning
+    const bool par = c->overlap && c->side != nullptr;
+    cudaStream_t sd = par ? c->side : st;
+    u64 *counters = c->d_counters.as<u64>();
+    if (off_base + slab_off >= (1ull << 40)) return fail(c, NUTSB_E_RANGE, "more than 2^40 bytes of rendered slab in one batch%s");
+    TRY(ensure(c, c->d_slab, off_base + slab_off + 256));
+    c->tm.slab_bytes = slab_on + slab_off;
+    if (par) { CK(cudaEventRecord(c->dep[0], st)); CK(cudaStreamWaitEvent(sd, c->dep[0], 0)); }
+    if (c->profiling) CK(cudaEventRecord(c->ev[1], sd));
+    {
+        RenderArgs ra{ ops, c->d_codetab.as<u8>(), c->d_bl_op.as<u32>(), c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(), counts,
+                       c->d_slab.as<u8>(), off_base, counters, c->d_status.as<u32>() };
+        // grid from the host's bound on the slab ops (E entries); warps past the device's count leave at once
+        u32 grid = cdiv(E, NUTSB_REN_OPS * (NUTSB_REN_THREADS / 32));
+        if (par) grid = std::min(grid, (u32)(c->sm_count * c->side_render));
+        NUTSB_LAUNCH(grid, NUTSB_REN_THREADS, sd, k_render, ra); CKL();
+        c->tm.launches++;
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev[8], sd));
+    if (par) CK(cudaEventRecord(c->dep[1], sd));
 
     // -- D. events: sort by recipient slot, prefix of byte deltas
     u32 *sv_slot = nullptr, *perm = nullptr;
@@ -687,16 +734,30 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     CK(cudaMemcpyAsync(hs, c->d_sizes.p, sizeof(Sizes), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const Sizes sz = *hs;
+    if (sz.slab_on != slab_on || sz.slab_off != slab_off) return fail(c, NUTSB_E_CUDA, "internal: slab size mismatch%s");
     TRY(ensure(c, c->d_out, sz.total_bytes + 64));
     Geometry geo{ c->d_room_b_off.as<u32>(), c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>() };
-    u64 *counters = c->d_counters.as<u64>();
-    const u64 off_base = (sz.slab_on + 15) & ~(u64)15;          // the colour-off renderings follow the colour-on ones
     c->tm.fanout_launches = 0;
-    c->tm.slab_bytes = sz.slab_on + sz.slab_off;
+
+    // -- I. direct ops: independent of the copy plan and of the fan-out (disjoint bytes of the streams), so
+    //    they go to the side stream as well
+    if (c->profiling) CK(cudaEventRecord(c->ev[9], sd));
+    if (sz.n_events > 0) {
+        if (par) { CK(cudaEventRecord(c->dep[2], st)); CK(cudaStreamWaitEvent(sd, c->dep[2], 0)); }
+        DirectArgs da{ ops, pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_op.as<u32>(),
+                       c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), (i64)sz.n_events, counters,
+                       c->d_status.as<u32>(), c->d_slab.as<u8>(), off_base, has_level ? 1u : 0u };
+        u32 grid = cdiv(sz.n_events, NUTSB_DIRECT_THREADS);
+        if (par) grid = std::min(grid, (u32)(c->sm_count * c->side_direct));
+        NUTSB_LAUNCH(grid, NUTSB_DIRECT_THREADS, sd, k_direct, da); CKL();
+        c->tm.launches++;
+    }
+    if (c->profiling) CK(cudaEventRecord(c->ev[3], sd));
+    if (par) CK(cudaEventRecord(c->dep[3], sd));
 
     // -- F. copy plan: runs per cell (count, scan, fill) and the work-item descriptors
-    if (sz.cells > 0 && sz.items > 0) {
-        if (off_base + sz.slab_off >= (1ull << 40)) return fail(c, NUTSB_E_RANGE, "more than 2^40 bytes of rendered slab in one batch%s");
+    const bool fan = sz.cells > 0 && sz.items > 0;
+    if (fan) {
         TRY(ensure(c, c->d_cell_nruns, (sz.cells + 1) * 4)); TRY(ensure(c, c->d_run_off, (sz.cells + 2) * 8));
         TRY(ensure(c, c->d_items, (size_t)sz.items * sizeof(ItemDesc)));
         PlanArgs pa{ pop, geo, cpx, c->d_off.as<u64>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_delta.as<i32>(),
@@ -718,35 +779,17 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
         c->tm.launches += 2;
     }
 
-    // -- G. render the slab, once per colour setting
-    if (c->profiling) CK(cudaEventRecord(c->ev[1], st));
-    TRY(ensure(c, c->d_slab, off_base + sz.slab_off + 256));
-    if (sz.n_slab > 0) {
-        RenderArgs ra{ ops, c->d_codetab.as<u8>(), c->d_bl_op.as<u32>(), c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(), counts,
-                       c->d_slab.as<u8>(), off_base, counters, c->d_status.as<u32>() };
-        NUTSB_LAUNCH(cdiv(sz.n_slab, NUTSB_REN_OPS * (NUTSB_REN_THREADS / 32)), NUTSB_REN_THREADS, st, k_render, ra); CKL();
-        c->tm.launches++;
-    }
-    if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
-
-    // -- H. fan-out
-    if (sz.cells > 0 && sz.items > 0) {
+    // -- H. fan-out: after the slab is rendered
+    if (par) CK(cudaStreamWaitEvent(st, c->dep[1], 0));
+    if (c->profiling) CK(cudaEventRecord(c->ev[10], st));
+    if (fan) {
         FanoutArgs fa{ c->d_items.as<ItemDesc>(), c->d_runs.as<uint4>(), c->d_slab.as<u8>(), off_base, c->d_out.as<u8>() };
         NUTSB_LAUNCH_SMEM(sz.items, NUTSB_FAN_THREADS, NUTSB_FAN_SMEM, st, k_fanout, fa); CKL();
         c->tm.launches++; c->tm.fanout_launches = 1;
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], st));
-
-    // -- I. direct ops
-    if (sz.n_events > 0) {
-        DirectArgs da{ ops, pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_op.as<u32>(),
-                       c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), (i64)sz.n_events, counters,
-                       c->d_status.as<u32>() };
-        const u32 grid = cdiv(sz.n_events, NUTSB_DIRECT_THREADS);
-        NUTSB_LAUNCH(grid, NUTSB_DIRECT_THREADS, st, k_direct, da); CKL();
-        c->tm.launches++;
-    }
-    if (c->profiling) CK(cudaEventRecord(c->ev[3], st));
+    if (par) CK(cudaStreamWaitEvent(st, c->dep[3], 0));
+    if (c->profiling) CK(cudaEventRecord(c->ev[11], st));
 
     CK(cudaMemcpyAsync(h64 + 8, counters, 24, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
@@ -754,11 +797,14 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     TRY(status_to_error(c, h32[4]));
     c->last_total = sz.total_bytes; c->have_streams = true;
     if (c->profiling) {
-        CK(cudaEventElapsedTime(&c->tm.plan_ms, c->ev[0], c->ev[1]));
-        CK(cudaEventElapsedTime(&c->tm.render_ms, c->ev[1], c->ev[5]));
-        CK(cudaEventElapsedTime(&c->tm.fanout_ms, c->ev[5], c->ev[2]));
-        CK(cudaEventElapsedTime(&c->tm.direct_ms, c->ev[2], c->ev[3]));
-        CK(cudaEventElapsedTime(&c->tm.total_ms, c->ev[0], c->ev[3]));
+        // with the side stream on, render_ms / direct_ms are the side kernels' own spans and overlap plan_ms / fanout_ms
+        CK(cudaEventSynchronize(c->ev[3]));
+        CK(cudaEventElapsedTime(&c->tm.plan_ms, c->ev[0], c->ev[10]));
+        CK(cudaEventElapsedTime(&c->tm.render_ms, c->ev[1], c->ev[8]));
+        CK(cudaEventElapsedTime(&c->tm.fanout_ms, c->ev[10], c->ev[2]));
+        CK(cudaEventElapsedTime(&c->tm.direct_ms, c->ev[9], c->ev[3]));
+        CK(cudaEventElapsedTime(&c->tm.total_ms, c->ev[0], c->ev[11]));
+        if (!par) c->tm.plan_ms -= c->tm.render_ms + c->tm.direct_ms;
     }
     c->tm.fanout_bytes_out = sz.total_bytes - h64[9];
     c->tm.fanout_bytes_in = c->tm.slab_bytes;          // each rendering of a tile is read once per work item

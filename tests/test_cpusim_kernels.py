@@ -59,3 +59,51 @@ def test_ban_verdicts(sim_lib, port):
         assert (ctx.site_banned_batch(st, so) == port.ban_batch(0, sf, st, so)).all()
         assert (ctx.user_banned_batch(nt, no) == port.ban_batch(1, uf, nt, no)).all()
     ctx.close()
+
+
+def test_long_strings_cross_the_render_windows(sim_lib, port):
+    """Strings of up to 2000 bytes dense in newlines / commands: renderings of up to 12 KB, so a warp's
+    shared-memory windows are flushed in the middle of a string (k_render, k_direct) and a tile's
+    renderings exceed the fan-out's windows (slab -> stream copy)."""
+    rng = np.random.default_rng(7)
+    alphabet = np.frombuffer(b"~/\n" + b"FRSOLKBGTWYMUIV" + b"xy z", np.uint8)
+    texts = []
+    for i in range(90):
+        n = int(rng.integers(0, 2001)) if i % 3 else int(rng.integers(0, 40))
+        w = np.ones(len(alphabet)); w[:3] = (8, 2, 6) if i % 2 else (1, 1, 1)
+        texts.append(rng.choice(alphabet, size=n, p=w / w.sum()).tobytes())
+    texts[5] = b"\n" * 2000
+    texts[11] = b"~FR" * 666
+    text, off = O.pack(texts)
+    n_users, n = 7, len(texts)
+    kind = rng.integers(0, 2, n).astype(np.uint8)
+    target = np.where(kind == 0, rng.integers(0, n_users, n), rng.integers(-1, 2, n)).astype(np.int32)
+    ops = dict(text=text, off=off, kind=kind, target=target,
+               except_user=rng.integers(-1, n_users, n).astype(np.int32), flags=np.zeros(n, np.uint8))
+    users = dict(room=np.array([0, 0, 0, 1, 1, 0, 1], np.int32), flags=np.array([1, 0, 1, 0, 1, 5, 0], np.uint8),
+                 level=np.ones(n_users, np.uint8))
+    ctx = _ctx(sim_lib)
+    ctx.set_users(users["room"], users["flags"], users["level"], 2)
+    st = ctx.write_batch(ops)
+    eoff, data, nd = port.write_batch(ops, users)
+    assert (st.off == eoff).all() and (st.data == data).all() and st.n_deliveries == int(nd.sum())
+    ctx.close()
+
+
+def test_many_tiles_per_room_seams(sim_lib, port):
+    """say() traffic long enough for several fan-out tiles per room: runs are cut at tile boundaries and at
+    every speaker's exclusion / "You say" line, and k_direct's seam pass writes the sectors around the cuts."""
+    ctx = _ctx(sim_lib)
+    words = synth.swear_words(8)
+    for n_users, per_room, n_msgs, stress in ((24, 12, 700, False), (9, 3, 500, True)):
+        us, n_rooms = synth.users(n_users, per_room, stress=stress)
+        bt, bo = synth.bodies(n_msgs, words)
+        v = port.contains_swearing_batch(bt, bo, words)
+        sops, _, _ = synth.say_ops(n_msgs, n_users, per_room, bt, bo, gated=True)
+        ctx.set_users(us["room"], us["flags"], us["level"], n_rooms)
+        st = ctx.write_batch(dict(sops, verdict=v))
+        off, data, nd = port.write_batch(sops, us, verdict=v)
+        assert (st.off == off).all() and st.n_deliveries == int(nd.sum())
+        bad = np.nonzero(st.data != data)[0]
+        assert bad.size == 0, (n_users, bad[:8], int(np.searchsorted(off, bad[0], side="right")) - 1)
+    ctx.close()
