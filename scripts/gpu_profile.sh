@@ -1,9 +1,10 @@
-# launch list + full captures of the main kernels (each ncu run only after the plain command exited 0)
+# launch list + full captures of the main kernels (each ncu run only after the plain command exited 0).
+# Serial schedule (NUTSB_OVERLAP=0) so that the per-kernel figures are each kernel's own.
 set -x
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
-$CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
-$CMD > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"k_fanout|k_render|k_direct|k_measure|k_ac_match|k_plan" -c 14 -o gpurun_out/prof_main $CMD > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out
+NUTSB_OVERLAP=0 $CMD > gpurun_out/plain.log 2>&1 &&
+NUTSB_OVERLAP=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+NUTSB_OVERLAP=0 $CMD > gpurun_out/plain2.log 2>&1 &&
+NUTSB_OVERLAP=0 ncu --set full --clock-control none --import-source on -k regex:"k_fanout|k_render|k_direct|k_measure|k_ac_match|k_plan" -c 14 -f -o gpurun_out/prof_main $CMD > gpurun_out/ncu_full.log 2>&1
+ls -la gpurun_out | head -40

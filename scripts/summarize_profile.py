@@ -20,9 +20,10 @@ rows = list(csv.DictReader(lines))
 names = [r["Kernel Name"] for r in rows]
 durs = [float(r["Metric Value"].replace(",", "")) for r in rows]
 idx = [i for i, n in enumerate(names) if n.startswith("k_measure")]
-start = idx[-1] - 3                      # the three verdict kernels precede the write batch
+start = (idx[1] if len(idx) > 1 else idx[0]) - 3   # second step (after the warm-up); the three verdict kernels precede the write batch
+end = (idx[2] - 3) if len(idx) > 2 else len(names)
 agg = collections.OrderedDict()
-for n, d in zip(names[start:], durs[start:]):
+for n, d in zip(names[start:end], durs[start:end]):
     k = re.sub(r"\(.*", "", n)
     agg.setdefault(k, [0, 0.0]); agg[k][0] += 1; agg[k][1] += d
 tot = sum(v[1] for v in agg.values())
@@ -30,7 +31,7 @@ with open(out / f"{tag}_launches_one_step.csv", "w") as f:
     f.write("kernel,launches,total_us,share_pct\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"\"{k}\",{v[0]},{v[1] / 1e3:.1f},{100 * v[1] / tot:.1f}\n")
-    f.write(f"\"TOTAL\",{len(names) - start},{tot / 1e3:.1f},100.0\n")
+    f.write(f"\"TOTAL\",{end - start},{tot / 1e3:.1f},100.0\n")
 (out / f"{tag}_launches_raw.csv").write_text("".join(lines))
 
 # 2. key metrics of the full captures
