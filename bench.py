@@ -43,6 +43,7 @@ N_USERS = 10_000
 USERS_PER_ROOM = 100
 N_SWEAR = 64
 KERNEL_TIMING_STEPS = 3
+IN_FLIGHT = 1
 N_BAN_QUERIES = 100_000
 N_BAN_ENTRIES = 10_000
 SEED = 0x333
@@ -285,22 +286,51 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     state = dict(deliv=0, bytes=0, launches=0, fan_ms=0.0, fan_in=0, fan_out=0, plan_ms=0.0, direct_ms=0.0, render_ms=0.0, ksteps=0)
+    state_lock = threading.Lock()
 
-    def step_device():
-        with torch.cuda.stream(stream):
-            ctx.verdicts_dev("contains_swearing", N_MSGS, d["bt"].data_ptr(), d["bo"].data_ptr(), d["verdict"].data_ptr())
-            ctx.verdicts_dev("site_banned", N_BAN_QUERIES, d["st"].data_ptr(), d["so"].data_ptr(), d["vs"].data_ptr())
-            ctx.verdicts_dev("user_banned", N_BAN_QUERIES, d["nt"].data_ptr(), d["no"].data_ptr(), d["vu"].data_ptr())
-            s = ctx.write_batch_dev(n_ops, d["text"].data_ptr(), d["off"].data_ptr(), d["kind"].data_ptr(),
-                                    d["target"].data_ptr(), d["exc"].data_ptr(), d["flags"].data_ptr(),
-                                    d["gate"].data_ptr(), d["verdict"].data_ptr())
-        t = ctx.timing()
-        state["deliv"] += int(s.n_deliveries); state["bytes"] += int(s.total_bytes)
-        state["launches"] += int(t.launches) + 3
-        state["fan_ms"] += float(t.fanout_ms); state["fan_in"] += int(t.fanout_bytes_in); state["fan_out"] += int(t.fanout_bytes_out)
-        state["plan_ms"] += float(t.plan_ms); state["direct_ms"] += float(t.direct_ms); state["render_ms"] += float(t.render_ms)
-        state["ksteps"] += 1
+    # Batches in flight on this GPU: every lane is a context of its own (own stream, own scratch and stream
+    # buffers) fed by its own host thread; the inputs in HBM are shared, the verdict outputs are per lane.
+    # With two lanes one batch's planning / rendering (issue-bound) runs beside the other's fan-out (HBM-bound).
+    lanes = [dict(ctx=ctx, stream=stream, verdict=d["verdict"], vs=d["vs"], vu=d["vu"])]
+    for _ in range(1, max(1, args.in_flight)):
+        c2 = api.Context(local)
+        s2 = torch.cuda.Stream(device=dev)
+        c2.set_stream(s2.cuda_stream); c2.set_profiling(True)
+        c2.set_swear_words(inp["words"]); c2.set_ban_files(inp["sfile"], inp["ufile"])
+        c2.set_users(users["room"], users["flags"], users["level"], inp["n_rooms"])
+        lanes.append(dict(ctx=c2, stream=s2, verdict=torch.zeros_like(d["verdict"]), vs=torch.zeros_like(d["vs"]),
+                          vu=torch.zeros_like(d["vu"])))
+
+    def step_device(L=None):
+        L = L or lanes[0]
+        c = L["ctx"]
+        c.verdicts_dev("contains_swearing", N_MSGS, d["bt"].data_ptr(), d["bo"].data_ptr(), L["verdict"].data_ptr())
+        c.verdicts_dev("site_banned", N_BAN_QUERIES, d["st"].data_ptr(), d["so"].data_ptr(), L["vs"].data_ptr())
+        c.verdicts_dev("user_banned", N_BAN_QUERIES, d["nt"].data_ptr(), d["no"].data_ptr(), L["vu"].data_ptr())
+        s = c.write_batch_dev(n_ops, d["text"].data_ptr(), d["off"].data_ptr(), d["kind"].data_ptr(),
+                              d["target"].data_ptr(), d["exc"].data_ptr(), d["flags"].data_ptr(),
+                              d["gate"].data_ptr(), L["verdict"].data_ptr())
+        t = c.timing()
+        with state_lock:
+            state["deliv"] += int(s.n_deliveries); state["bytes"] += int(s.total_bytes)
+            state["launches"] += int(t.launches) + 3
+            state["fan_ms"] += float(t.fanout_ms); state["fan_in"] += int(t.fanout_bytes_in); state["fan_out"] += int(t.fanout_bytes_out)
+            state["plan_ms"] += float(t.plan_ms); state["direct_ms"] += float(t.direct_ms); state["render_ms"] += float(t.render_ms)
+            state["ksteps"] += 1
         return s
+
+    def run_steps(k):
+        """exactly k steps, dealt to the lanes"""
+        if len(lanes) == 1:
+            for _ in range(k):
+                step_device()
+            return
+        share = [k // len(lanes) + (1 if i < k % len(lanes) else 0) for i in range(len(lanes))]
+        th = [threading.Thread(target=lambda L=L, m=m: [step_device(L) for _ in range(m)]) for L, m in zip(lanes, share)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
 
     def barrier():
         if world > 1:
@@ -309,17 +339,18 @@ def run_ours(args):
 
     clocks = ClockSampler(local)
     clocks.start()                      # nvidia-smi needs ~0.1 s to start: launched before the warm-up
-    for _ in range(args.warmup):
-        step_device()
+    run_steps(args.warmup * len(lanes))
     for k in state:
         state[k] = 0 if not isinstance(state[k], float) else 0.0
     barrier()
+    marker = torch.cuda.Stream(device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
+    e0.record(marker)                   # the device is idle here (barrier above): the lanes' first kernels come after
+    run_steps(args.steps)
+    for L in lanes:
+        marker.wait_stream(L["stream"])
+    e1.record(marker)
     barrier()
     tw1 = time.perf_counter()
     clocks.window(tw0, tw1)
@@ -406,6 +437,7 @@ def run_ours(args):
                     config=dict(workload=workload_name(), sharding="rooms per rank, no collective",
                                 l2="inputs (%.0f MB) and outputs (%.1f GB) per step exceed the 126 MB L2; no flush needed"
                                    % (input_bytes / 1e6, dev_state["bytes"] / max(1, args.steps) / 1e9),
+                                batches_in_flight=len(lanes),
                                 source_msgs_per_s=world * N_MSGS * args.steps / (ms_max * 1e-3),
                                 ban_queries_per_step=2 * N_BAN_QUERIES,
                                 kernel_ms_alone=dict(plan=kstate["plan_ms"] / ks, render=kstate["render_ms"] / ks, fanout=fan_ms,
@@ -433,7 +465,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
+    for L in lanes:
+        L["ctx"].close()
     return 0
 
 
@@ -443,6 +476,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--in-flight", type=int, default=IN_FLIGHT, help="batches in flight per GPU (one context + host thread each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     args = ap.parse_args()

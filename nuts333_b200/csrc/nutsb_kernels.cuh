@@ -473,10 +473,9 @@ k_user_len(UserLenIn in, i64 n, u64 *len)
 // recipient is the excluded speaker (c:1415), where a direct write_user op's
 // bytes interleave, or -- for recipients behind a filter (login / ignall /
 // ignshout, write_level) -- where an op is not delivered to the recipient's
-// class.  The plan is made in two passes over the cells (count, exclusive scan,
-// fill) and leaves a flat run list in (room, tile, recipient) order plus one
-// descriptor per fan-out work item, so that the kernel that moves the bytes
-// (k_fanout) has nothing to decide.
+// class.  k_plan leaves a flat run list (each work item's runs contiguous, in
+// recipient order) plus one descriptor per fan-out work item, so that the kernel
+// that moves the bytes (k_fanout) has nothing to decide.
 struct Geometry {
     const u32 *room_b_off;       // [Rt+1] slab rank of room r's first op
     const u32 *room_tile_off;    // [Rt+1] tiles before room r
@@ -508,130 +507,157 @@ struct PlanArgs {
     const u32 *bl_meta;          // per slab op: kind | flags << 8 | clamped target << 16
     u64 n_cells, off_base;       // off_base: where the colour-off renderings start in the slab buffer
     u32 has_level;
-    u32 *cell_nruns;             // count pass: out
-    const u64 *run_off;          // fill pass: exclusive scan of cell_nruns, [n_cells+1]
+    u32 *run_cursor;             // runs reserved so far
     uint4 *runs; ItemDesc *items;
     u64 *counters;               // [0] deliveries
     u32 *status;
 };
 
+// The walk of one cell (tile t of the room, recipient ls of the room): counts its runs (FILL = false) or
+// writes them from A.runs[r_out] on (FILL = true).
 template <bool FILL>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ u32 nutsb_plan_cell(const PlanArgs &A, u32 room, u32 t, u32 ls, u64 r_out, u32 &deliv)
+{
+    const u32 slot0 = (u32)A.pop.room_slot_off[room];
+    const u32 s = slot0 + ls;
+    const u32 b0 = A.geo.room_b_off[room], nb_room = A.geo.room_b_off[room + 1] - b0;
+    const u32 a0 = t * NUTSB_TILE_OPS;                   // room-local slab rank of the tile's first op
+    const u32 nb = nb_room - a0 < NUTSB_TILE_OPS ? nb_room - a0 : NUTSB_TILE_OPS;
+    const u32 g0 = b0 + a0;
+    const u32 e0 = A.ev_off[s], e1 = A.ev_off[s + 1];
+    // the recipient's events inside the tile: keys in [4*a0+1, 4*(a0+nb)] (a direct op before the tile's first
+    // slab op belongs to the tile before)
+    u32 l = e0, h = e1;
+    { const u32 thr = 4 * a0 + 1; while (l < h) { const u32 mid = (l + h) >> 1; if (A.sv_ukey[mid] < thr) l = mid + 1; else h = mid; } }
+    u32 l_end = l; h = e1;
+    { const u32 thr = 4 * (a0 + nb) + 1; while (l_end < h) { const u32 mid = (l_end + h) >> 1; if (A.sv_ukey[mid] < thr) l_end = mid + 1; else h = mid; } }
+    const i32 u = A.pop.slot_user[s];
+    const i32 k = A.pop.user_cls[u];
+    const u32 cf = A.pop.slot_cf[s], clv = A.pop.slot_lv[s];
+    const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
+    const bool full = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
+    const u64 *vp = (colour ? A.cpx.vp_on : A.cpx.vp_off) + g0;      // tile-local prefix of rendered lengths
+    const u64 sb = colour ? 0 : A.off_base;
+    // stream position of the tile's first op: class prefix + the recipient's own events before the tile
+    const u64 so_u = A.stream_off[u], cp_b0 = A.cpx.at(k, room, b0);
+    u64 p = so_u + (A.cpx.at(k, room, g0) - cp_b0) + (A.sv_pre[l] - A.sv_pre[e0]);
+    // Plain listeners: a run covers only whole 32-byte sectors of the stream.  The pieces of a sector
+    // that holds a discontinuity (an event of this recipient) are written together by k_direct's seam
+    // pass: two partial writes of one sector far apart in time cost a read-modify-write in DRAM.
+    // a_start = where the contiguous stretch of slab bytes this run belongs to begins in the stream.
+    u64 a_start = so_u; bool first_seg = true;
+    if (full && l > e0) {                                 // ... after the last event before the tile
+        const u32 uk = A.sv_ukey[l - 1];
+        a_start = so_u + (A.cpx.at(k, room, b0 + (uk >> 2) + ((uk & 3u) != NUTSB_EV_DIRECT)) - cp_b0) + (A.sv_pre[l] - A.sv_pre[e0]);
+        first_seg = false;
+    }
+    const bool last_tile = a0 + nb == nb_room;
+    u32 nruns = 0;
+    u32 cur = 0;
+    for (u32 e = l; ; ++e) {
+        u32 j = nb, ek = NUTSB_EV_SKIP; i32 dlt = 0;
+        if (e < l_end) { const u32 uk = A.sv_ukey[e]; j = (uk >> 2) - a0; ek = uk & 3u; if (ek != NUTSB_EV_SKIP) dlt = A.sv_delta[e]; }
+        if (full) {
+            if (cur < j) {
+                const u64 v0 = vp[cur], v1 = vp[j];
+                deliv += j - cur;                                  // zero-length renderings are deliveries too
+                if (v1 > v0) {
+                    const u64 x0 = p, x1 = p + (v1 - v0), f0 = x0 & ~(u64)31;
+                    const u64 xs = a_start <= f0 ? f0 : (first_seg ? x0 : (x0 + 31) & ~(u64)31);
+                    const u64 xe = (e >= l_end && last_tile) ? x1 : x1 & ~(u64)31;      // the stream's end is kept exact
+                    if (xs < xe) {
+                        if (FILL) A.runs[r_out + nruns] = nutsb_run_pack(xs, sb + v0 + xs - x0, (u32)(xe - xs));
+                        ++nruns;
+                    }
+                    p = x1;
+                }
+            }
+        } else {
+            // behind a filter: op by op, maximal stretches of delivered ops make a run
+            u64 run_dst = 0, run_src = 0; u32 run_len = 0;
+            for (u32 i = cur; i < j; ++i) {
+                const u32 m = A.bl_meta[g0 + i];
+                const bool del = nutsb_class_delivers(cf, clv, m & 0xffu, (m >> 8) & 0xffu, (i32)(int16_t)(m >> 16));
+                if (del) {
+                    const u64 v0 = vp[i]; const u32 len = (u32)(vp[i + 1] - v0);
+                    ++deliv;
+                    if (!run_len) { run_dst = p; run_src = sb + v0; }
+                    run_len += len; p += len;
+                }
+                if ((!del || i + 1 == j) && run_len) {
+                    if (FILL) A.runs[r_out + nruns] = nutsb_run_pack(run_dst, run_src, run_len);
+                    ++nruns; run_len = 0;
+                }
+            }
+        }
+        if (e >= l_end) break;
+        // a direct op's bytes go here (k_direct writes them); excluded from op j: nothing emitted for it
+        if (ek == NUTSB_EV_DIRECT) { p += (u64)(i64)dlt; cur = j; }
+        else {
+            if (ek == NUTSB_EV_REPLACE) p += (u64)(i64)dlt + (A.cpx.at(k, room, g0 + j + 1) - A.cpx.at(k, room, g0 + j));
+            cur = j + 1;
+        }
+        a_start = p; first_seg = false;
+    }
+    return nruns;
+}
+
+// One block per fan-out work item (room, tile, chunk of recipients), one thread per recipient: count the
+// cell's runs, reserve the item's piece of the run list (one atomic per item: the order of the items in the
+// list does not matter, each item's runs are contiguous), walk again and write them, write the descriptor.
+// FILL = false only adds up the number of runs (sizes the list when recipients sit behind filters).
+template <bool FILL>
+__global__ void __launch_bounds__(NUTSB_UCHUNK)
 k_plan(PlanArgs A)
 {
-    __shared__ u32 s_deliv;
-    if (FILL) { if (threadIdx.x == 0) s_deliv = 0; __syncthreads(); }
-    const u64 cell = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ u32 s_room, s_base, s_deliv;
+    __shared__ u32 s_w[NUTSB_UCHUNK / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        const u32 item = blockIdx.x;
+        u32 lo = 0, hi = (u32)A.pop.n_rooms_tot;            // last room with room_item_off[r] <= item
+        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (A.geo.room_item_off[mid] <= item) lo = mid; else hi = mid; }
+        s_room = lo; s_deliv = 0;
+    }
+    __syncthreads();
+    const u32 room = s_room;
+    const u32 users_r = (u32)(A.pop.room_slot_off[room + 1] - A.pop.room_slot_off[room]);
+    const u32 chunks = (users_r + NUTSB_UCHUNK - 1) / NUTSB_UCHUNK;
+    const u32 local = blockIdx.x - A.geo.room_item_off[room];
+    const u32 t = local / chunks, ls = (local % chunks) * NUTSB_UCHUNK + (u32)tid;
+    const bool valid = ls < users_r;
     u32 deliv = 0;
-    if (cell < A.n_cells) {
-        u32 lo = 0, hi = (u32)A.pop.n_rooms_tot;            // last room with room_cell_off[r] <= cell
-        while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (A.geo.room_cell_off[mid] <= cell) lo = mid; else hi = mid; }
-        const u32 room = lo;
-        const u32 slot0 = (u32)A.pop.room_slot_off[room];
-        const u32 users_r = (u32)A.pop.room_slot_off[room + 1] - slot0;
-        const u64 local = cell - A.geo.room_cell_off[room];
-        const u32 t = (u32)(local / users_r), ls = (u32)(local % users_r);
-        const u32 s = slot0 + ls;
+    const u32 n = valid ? nutsb_plan_cell<false>(A, room, t, ls, 0, deliv) : 0u;
+    u32 inc = n;
+    for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(NUTSB_FULL, inc, d); if (lane >= d) inc += x; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    u32 before = 0, total = 0;
+    for (int w = 0; w < NUTSB_UCHUNK / 32; ++w) { if (w < warp) before += s_w[w]; total += s_w[w]; }
+    if (tid == 0) s_base = total ? atomicAdd(A.run_cursor, total) : 0u;
+    if (!FILL) return;
+    __syncthreads();
+    const u32 base = s_base;
+    deliv = 0;
+    if (valid && n) (void)nutsb_plan_cell<true>(A, room, t, ls, (u64)base + before + inc - n, deliv);
+    else if (valid) (void)nutsb_plan_cell<false>(A, room, t, ls, 0, deliv);      // deliveries of zero-length renderings
+    if (tid == 0) {
         const u32 b0 = A.geo.room_b_off[room], nb_room = A.geo.room_b_off[room + 1] - b0;
-        const u32 a0 = t * NUTSB_TILE_OPS;                   // room-local slab rank of the tile's first op
+        const u32 a0 = t * NUTSB_TILE_OPS;
         const u32 nb = nb_room - a0 < NUTSB_TILE_OPS ? nb_room - a0 : NUTSB_TILE_OPS;
         const u32 g0 = b0 + a0;
-        const u32 e0 = A.ev_off[s], e1 = A.ev_off[s + 1];
-        // the recipient's events inside the tile: keys in [4*a0+1, 4*(a0+nb)] (a direct op before the tile's first
-        // slab op belongs to the tile before)
-        u32 l = e0, h = e1;
-        { const u32 thr = 4 * a0 + 1; while (l < h) { const u32 mid = (l + h) >> 1; if (A.sv_ukey[mid] < thr) l = mid + 1; else h = mid; } }
-        u32 l_end = l; h = e1;
-        { const u32 thr = 4 * (a0 + nb) + 1; while (l_end < h) { const u32 mid = (l_end + h) >> 1; if (A.sv_ukey[mid] < thr) l_end = mid + 1; else h = mid; } }
-        const i32 u = A.pop.slot_user[s];
-        const i32 k = A.pop.user_cls[u];
-        const u32 cf = A.pop.slot_cf[s], clv = A.pop.slot_lv[s];
-        const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
-        const bool full = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
-        const u64 *vp = (colour ? A.cpx.vp_on : A.cpx.vp_off) + g0;      // tile-local prefix of rendered lengths
-        const u64 sb = colour ? 0 : A.off_base;
-        // stream position of the tile's first op: class prefix + the recipient's own events before the tile
-        const u64 so_u = A.stream_off[u], cp_b0 = A.cpx.at(k, room, b0);
-        u64 p = so_u + (A.cpx.at(k, room, g0) - cp_b0) + (A.sv_pre[l] - A.sv_pre[e0]);
-        // Plain listeners: a run covers only whole 32-byte sectors of the stream.  The pieces of a sector
-        // that holds a discontinuity (an event of this recipient) are written together by k_direct's seam
-        // pass: two partial writes of one sector far apart in time cost a read-modify-write in DRAM.
-        // a_start = where the contiguous stretch of slab bytes this run belongs to begins in the stream.
-        u64 a_start = so_u; bool first_seg = true;
-        if (full && l > e0) {                                 // ... after the last event before the tile
-            const u32 uk = A.sv_ukey[l - 1];
-            a_start = so_u + (A.cpx.at(k, room, b0 + (uk >> 2) + ((uk & 3u) != NUTSB_EV_DIRECT)) - cp_b0) + (A.sv_pre[l] - A.sv_pre[e0]);
-            first_seg = false;
-        }
-        const bool last_tile = a0 + nb == nb_room;
-        u64 r_out = FILL ? A.run_off[cell] : 0;
-        u32 nruns = 0;
-        u32 cur = 0;
-        for (u32 e = l; ; ++e) {
-            u32 j = nb, ek = NUTSB_EV_SKIP; i32 dlt = 0;
-            if (e < l_end) { const u32 uk = A.sv_ukey[e]; j = (uk >> 2) - a0; ek = uk & 3u; if (ek != NUTSB_EV_SKIP) dlt = A.sv_delta[e]; }
-            if (full) {
-                if (cur < j) {
-                    const u64 v0 = vp[cur], v1 = vp[j];
-                    deliv += j - cur;                                  // zero-length renderings are deliveries too
-                    if (v1 > v0) {
-                        const u64 x0 = p, x1 = p + (v1 - v0), f0 = x0 & ~(u64)31;
-                        const u64 xs = a_start <= f0 ? f0 : (first_seg ? x0 : (x0 + 31) & ~(u64)31);
-                        const u64 xe = (e >= l_end && last_tile) ? x1 : x1 & ~(u64)31;      // the stream's end is kept exact
-                        if (xs < xe) {
-                            if (FILL) A.runs[r_out + nruns] = nutsb_run_pack(xs, sb + v0 + xs - x0, (u32)(xe - xs));
-                            ++nruns;
-                        }
-                        p = x1;
-                    }
-                }
-            } else {
-                // behind a filter: op by op, maximal stretches of delivered ops make a run
-                u64 run_dst = 0, run_src = 0; u32 run_len = 0;
-                for (u32 i = cur; i < j; ++i) {
-                    const u32 m = A.bl_meta[g0 + i];
-                    const bool del = nutsb_class_delivers(cf, clv, m & 0xffu, (m >> 8) & 0xffu, (i32)(int16_t)(m >> 16));
-                    if (del) {
-                        const u64 v0 = vp[i]; const u32 len = (u32)(vp[i + 1] - v0);
-                        ++deliv;
-                        if (!run_len) { run_dst = p; run_src = sb + v0; }
-                        run_len += len; p += len;
-                    }
-                    if ((!del || i + 1 == j) && run_len) {
-                        if (FILL) A.runs[r_out + nruns] = nutsb_run_pack(run_dst, run_src, run_len);
-                        ++nruns; run_len = 0;
-                    }
-                }
-            }
-            if (e >= l_end) break;
-            // a direct op's bytes go here (k_direct writes them); excluded from op j: nothing emitted for it
-            if (ek == NUTSB_EV_DIRECT) { p += (u64)(i64)dlt; cur = j; }
-            else {
-                if (ek == NUTSB_EV_REPLACE) p += (u64)(i64)dlt + (A.cpx.at(k, room, g0 + j + 1) - A.cpx.at(k, room, g0 + j));
-                cur = j + 1;
-            }
-            a_start = p; first_seg = false;
-        }
-        if (!FILL) A.cell_nruns[cell] = nruns;
-        else if (ls % NUTSB_UCHUNK == 0) {
-            const u32 chunks = (users_r + NUTSB_UCHUNK - 1) / NUTSB_UCHUNK;
-            const u32 ls_end = ls + NUTSB_UCHUNK < users_r ? ls + NUTSB_UCHUNK : users_r;
-            const u64 r_end = A.run_off[cell + (ls_end - ls)];
-            ItemDesc d;                                       // a run may reach up to 31 bytes back into the previous tile
-            const u64 n0 = A.cpx.vp_on[g0], o0 = A.cpx.vp_off[g0];
-            const u32 xn = n0 < 32 ? (u32)n0 : 32u, xo = o0 < 32 ? (u32)o0 : 32u;
-            d.on_src = n0 - xn; d.on_len = (u32)(A.cpx.vp_on[g0 + nb] - n0) + xn;
-            d.off_src = A.off_base + o0 - xo; d.off_len = (u32)(A.cpx.vp_off[g0 + nb] - o0) + xo;
-            d.run_begin = (u32)r_out; d.run_cnt = (u32)(r_end - r_out);
-            A.items[A.geo.room_item_off[room] + t * chunks + ls / NUTSB_UCHUNK] = d;
-        }
+        ItemDesc d;                                           // a run may reach up to 31 bytes back into the previous tile
+        const u64 n0 = A.cpx.vp_on[g0], o0 = A.cpx.vp_off[g0];
+        const u32 xn = n0 < 32 ? (u32)n0 : 32u, xo = o0 < 32 ? (u32)o0 : 32u;
+        d.on_src = n0 - xn; d.on_len = (u32)(A.cpx.vp_on[g0 + nb] - n0) + xn;
+        d.off_src = A.off_base + o0 - xo; d.off_len = (u32)(A.cpx.vp_off[g0 + nb] - o0) + xo;
+        d.run_begin = base; d.run_cnt = total;
+        A.items[blockIdx.x] = d;
     }
-    if (FILL) {
-        for (int d = 16; d; d >>= 1) deliv += __shfl_xor_sync(NUTSB_FULL, deliv, d);
-        if ((threadIdx.x & 31) == 0 && deliv) atomicAdd(&s_deliv, deliv);
-        __syncthreads();
-        if (threadIdx.x == 0 && s_deliv) nutsb_add64(A.counters, (u64)s_deliv);
-    }
+    for (int d = 16; d; d >>= 1) deliv += __shfl_xor_sync(NUTSB_FULL, deliv, d);
+    if (lane == 0 && deliv) atomicAdd(&s_deliv, deliv);
+    __syncthreads();
+    if (tid == 0 && s_deliv) nutsb_add64(A.counters, (u64)s_deliv);
 }
 
 // Bytes of colcode[k] (nuts333.h:237-246), little-endian in one register pair.
@@ -1033,7 +1059,7 @@ k_direct(DirectArgs A)
     for (int i = tid; i < NUTSB_CODETAB_BYTES; i += NUTSB_DIRECT_THREADS) s_tab[i] = A.pop.codetab[i];
     __syncthreads();
 
-    u64 c_cnt = 0, c_bytes = 0;
+    u64 c_cnt = 0, c_bytes = 0; u32 seam_bytes = 0;
     for (i64 ebase = ((i64)blockIdx.x * (NUTSB_DIRECT_THREADS / 32) + warp) * 32; ebase < A.n_ev;
          ebase += (i64)gridDim.x * NUTSB_DIRECT_THREADS) {
         const i64 e = ebase + lane;
@@ -1093,6 +1119,7 @@ k_direct(DirectArgs A)
             u64 t0 = p & ~(u64)31; if (t0 < a_start) t0 = a_start;
             u64 h1 = (q + 31) & ~(u64)31; if (h1 > b_end) h1 = b_end;
             const u32 tlen = seam ? (u32)(p - t0) : 0u, hlen = seam && h1 > q ? (u32)(h1 - q) : 0u;
+            seam_bytes += tlen + hlen;
             // every piece (< 32 bytes) is copied by the whole warp at once: one store request per piece
             u32 m = __ballot_sync(NUTSB_FULL, tlen != 0);
             while (m) {
@@ -1137,7 +1164,8 @@ k_direct(DirectArgs A)
         if (lane == 0 && sink.done != total) atomicOr(A.status, NUTSB_ST_RENDER_MISMATCH);
         c_cnt += cnt; c_bytes += total;
     }
-    if (lane == 0 && c_cnt) { nutsb_add64(A.n_deliveries, c_cnt); nutsb_add64(A.n_deliveries + 1, c_bytes); }
+    for (int d = 16; d; d >>= 1) seam_bytes += __shfl_xor_sync(NUTSB_FULL, seam_bytes, d);
+    if (lane == 0 && (c_cnt | seam_bytes)) { nutsb_add64(A.n_deliveries, c_cnt); nutsb_add64(A.n_deliveries + 1, c_bytes + seam_bytes); }
 }
 
 // ---- stream digests ------------------------------------------------------------------------

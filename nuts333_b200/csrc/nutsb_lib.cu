@@ -76,7 +76,7 @@ struct nutsb_ctx {
     DBuf d_sv_ukey, d_sv_delta, d_sv_op, d_sv_pre, d_ev_off;
     DBuf d_vp_on, d_vp_off, d_cp;
     DBuf d_room_tile_off, d_room_cell_off, d_room_item_off, d_sizes, d_counters;
-    DBuf d_cell_nruns, d_run_off, d_runs, d_items, d_slab, d_bl_meta;
+    DBuf d_runs, d_items, d_slab, d_bl_meta;
     DBuf d_off, d_out, d_digest, d_ulen;
     HBuf h_small, h_off, h_out;
     u64 last_total = 0; bool have_streams = false;
@@ -344,7 +344,7 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
         &c->d_evk[1], &c->d_evv[0], &c->d_evv[1], &c->d_ev_ukey, &c->d_ev_delta, &c->d_ev_op, &c->d_sv_ukey,
         &c->d_sv_delta, &c->d_sv_op, &c->d_sv_pre, &c->d_ev_off, &c->d_vp_on, &c->d_vp_off, &c->d_cp,
         &c->d_room_tile_off, &c->d_room_cell_off, &c->d_room_item_off, &c->d_sizes, &c->d_counters,
-        &c->d_cell_nruns, &c->d_run_off, &c->d_runs, &c->d_items, &c->d_slab, &c->d_bl_meta, &c->d_off, &c->d_out, &c->d_digest, &c->d_ulen,
+        &c->d_runs, &c->d_items, &c->d_slab, &c->d_bl_meta, &c->d_off, &c->d_out, &c->d_digest, &c->d_ulen,
         &c->s_text, &c->s_toff, &c->s_kind, &c->s_target, &c->s_except, &c->s_flags, &c->s_gate, &c->s_verdict, &c->s_v8,
         &c->d_names, &c->d_name_off, &c->d_sflags, &c->d_lit, &c->d_lit_off, &c->d_sp_len, &c->d_sp_off, &c->d_sp_text,
         &c->d_sp_kind, &c->d_sp_target, &c->d_sp_except, &c->d_sp_flags, &c->d_sp_gate, &c->d_sp_verdict,
@@ -755,28 +755,30 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     if (c->profiling) CK(cudaEventRecord(c->ev[3], sd));
     if (par) CK(cudaEventRecord(c->dep[3], sd));
 
-    // -- F. copy plan: runs per cell (count, scan, fill) and the work-item descriptors
+    // -- F. copy plan: the run list and the work-item descriptors
     const bool fan = sz.cells > 0 && sz.items > 0;
     if (fan) {
-        TRY(ensure(c, c->d_cell_nruns, (sz.cells + 1) * 4)); TRY(ensure(c, c->d_run_off, (sz.cells + 2) * 8));
         TRY(ensure(c, c->d_items, (size_t)sz.items * sizeof(ItemDesc)));
+        u32 *cursor = counts + 4;
+        CK(cudaMemsetAsync(cursor, 0, 4, st));
         PlanArgs pa{ pop, geo, cpx, c->d_off.as<u64>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_delta.as<i32>(),
                      c->d_sv_pre.as<u64>(), c->d_bl_meta.as<u32>(), (u64)sz.cells, off_base, has_level ? 1u : 0u,
-                     c->d_cell_nruns.as<u32>(), c->d_run_off.as<u64>(), nullptr, c->d_items.as<ItemDesc>(), counters, c->d_status.as<u32>() };
-        NUTSB_LAUNCH(cdiv(sz.cells, 256), 256, st, k_plan<false>, pa); CKL();
-        TRY(run_scan(c, InU32{c->d_cell_nruns.as<u32>()}, OutU64{c->d_run_off.as<u64>()}, (i64)sz.cells, nullptr));
-        // plain listeners: at most one run per cell plus one per event; behind a filter the count is read back
+                     cursor, nullptr, c->d_items.as<ItemDesc>(), counters, c->d_status.as<u32>() };
+        // plain listeners: at most one run per cell plus one per event; behind a filter the count is taken first
         u64 n_runs = sz.cells + sz.n_events;
         if (!alias) {
-            CK(cudaMemcpyAsync(h64 + 2, c->d_run_off.as<u64>() + sz.cells, 8, cudaMemcpyDeviceToHost, st));
+            NUTSB_LAUNCH(sz.items, NUTSB_UCHUNK, st, k_plan<false>, pa); CKL();
+            CK(cudaMemcpyAsync(h32 + 6, cursor, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemsetAsync(cursor, 0, 4, st));
             CK(cudaStreamSynchronize(st));
-            n_runs = h64[2];
+            n_runs = h32[6];
+            c->tm.launches++;
         }
         if (n_runs >= 0xfffffff0ull) return fail(c, NUTSB_E_RANGE, "more than 2^32 copy runs in one batch%s");
         TRY(ensure(c, c->d_runs, (n_runs + 1) * sizeof(uint4)));
         pa.runs = c->d_runs.as<uint4>();
-        NUTSB_LAUNCH(cdiv(sz.cells, 256), 256, st, k_plan<true>, pa); CKL();
-        c->tm.launches += 2;
+        NUTSB_LAUNCH(sz.items, NUTSB_UCHUNK, st, k_plan<true>, pa); CKL();
+        c->tm.launches++;
     }
 
     // -- H. fan-out: after the slab is rendered
