@@ -58,6 +58,8 @@ enum {
 #define NUTSB_MAX_TEXT 2000
 /* line[82] in site_banned/user_banned (c:334,353): longer tokens overflow there. */
 #define NUTSB_MAX_BAN_TOKEN 81
+#define NUTSB_REVIEW_LINES 15    /* nuts333.h:37 */
+#define NUTSB_REVIEW_LEN   200   /* nuts333.h:39 */
 
 /* recipient flags (nuts333.h:67-85 fields actually read on the path) */
 #define NUTSB_UF_COLOUR   0x01u  /* user->colour != 0            */
@@ -214,6 +216,19 @@ int nutsb_speech_batch_dev(nutsb_ctx *ctx, int64_t n, const uint8_t *verb, const
 /* queue tier: one call of the reference's say()/shout()/... ; composed on the host, the swear
  * verdicts of the queued lines are taken in one device batch at nutsb_flush */
 int nutsb_q_speech(nutsb_ctx *ctx, int verb, int32_t user, const char *inpstr);
+
+/* ---- review buffers (queue tier; record c:2062, review c:5192, clear_revbuff c:2626) ------
+ * nutsb_q_speech records what say / emote / echo send to the room (c:4099, c:4209, c:4304), as
+ * the reference does: the first REVIEW_LEN bytes of the line ('\n' appended when it was cut).
+ * nutsb_q_record is record() for any other caller.  nutsb_q_review queues what review() writes
+ * to `user` for `room` (the room is the caller's to resolve: get_room / has_room_access):
+ * header, the buffered lines oldest first through write_user again, footer -- or "Review
+ * buffer is empty.".  Lines refused for swearing are never recorded: a review (like a flush)
+ * first takes the swear verdicts of the lines queued so far.  Buffers are cleared by
+ * nutsb_set_users (create_room, c:2799) and nutsb_q_review_clear. */
+int nutsb_q_record(nutsb_ctx *ctx, int32_t room, const char *str);
+int nutsb_q_review(nutsb_ctx *ctx, int32_t user, int32_t room, const char *room_name);
+int nutsb_q_review_clear(nutsb_ctx *ctx, int32_t room);
 
 /* ---- colour_com_count / colour_com_strip (nuts333.c:2563-2610), host buffers ------------- */
 /* count[i] = colour_com_count(string i), including its double count ("~FBK" is 2). */

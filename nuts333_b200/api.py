@@ -71,6 +71,7 @@ EXPORTS = [
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
     "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_q_speech",
+    "nutsb_q_record", "nutsb_q_review", "nutsb_q_review_clear",
     "nutsb_colour_com_count_batch", "nutsb_colour_com_strip_batch", "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
     "nutsb_q_write_level", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_contains_swearing",
     "nutsb_site_banned", "nutsb_user_banned",
@@ -110,6 +111,9 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_speech_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
     lib.nutsb_speech_batch_dev.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
     lib.nutsb_q_speech.argtypes = [vp, C.c_int, C.c_int32, C.c_char_p]
+    lib.nutsb_q_record.argtypes = [vp, C.c_int32, C.c_char_p]
+    lib.nutsb_q_review.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
+    lib.nutsb_q_review_clear.argtypes = [vp, C.c_int32]
     lib.nutsb_colour_com_count_batch.argtypes = [vp, C.c_int64, vp, vp, vp]
     lib.nutsb_colour_com_strip_batch.argtypes = [vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp)]
     lib.nutsb_stream_digests.argtypes = [vp, u64p]
@@ -377,6 +381,18 @@ class Talker:
     def _speech(self, verb, user, inpstr):
         c = self.ctx
         c._ck(c.lib.nutsb_q_speech(c._h, verb, user, self._s(inpstr)))
+
+    def record(self, rm, s):                                         # c:2062
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_record(c._h, rm, self._s(s)))
+
+    def review(self, user, rm, room_name=None):                      # c:5192 (rm resolved by the caller)
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_review(c._h, user, rm, self._s(room_name if room_name is not None else "room%d" % rm)))
+
+    def clear_revbuff(self, rm):                                     # c:2626
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_review_clear(c._h, rm))
 
     def say(self, user, inpstr):                                     # c:4062
         self._speech(SPEECH_SAY, user, inpstr)

@@ -96,6 +96,13 @@ struct nutsb_ctx {
     std::vector<u8> q_text; std::vector<u64> q_off{0}; std::vector<u8> q_kind, q_flags;
     std::vector<i32> q_target, q_except, q_gate;
     std::vector<u8> q_sw_text; std::vector<u64> q_sw_off{0};     // bodies whose swear verdict gates queued ops
+    std::vector<u8> q_sw_verdict;                                // ... their verdicts, once taken (flush / review)
+
+    // review buffers (nuts333.h:95, REVIEW_LINES x REVIEW_LEN+2 per room), host state of the queue tier
+    struct RevBuf { char buf[NUTSB_REVIEW_LINES][NUTSB_REVIEW_LEN + 2]; int line; };
+    struct PendingRec { i32 room, gate; std::string text; };
+    std::vector<RevBuf> rev;
+    std::vector<PendingRec> q_rec;                               // record() calls whose line may still be refused (swearing)
 };
 
 static int fail(nutsb_ctx *c, int code, const char *fmt, const char *a = "")
@@ -500,6 +507,8 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     }
     c->have_users = false; c->have_streams = false;
     c->U = n_users; c->R = n_rooms; c->Rt = n_rooms + 1;
+    c->rev.assign((size_t)n_rooms, nutsb_ctx::RevBuf{});        // create_room() clears them, c:2799
+    c->q_rec.clear();
     c->user_room.resize(n_users);
     for (i32 u = 0; u < n_users; ++u) c->user_room[u] = room[u] < 0 ? n_rooms : room[u];
     // slot order: (room, flags, level, index) -- compatible with both class granularities
@@ -1065,6 +1074,73 @@ NUTSB_API int nutsb_q_more(nutsb_ctx *c, int32_t user, int32_t sock_user, const 
 
 NUTSB_API int64_t nutsb_q_pending(const nutsb_ctx *c) { return c ? (int64_t)c->q_kind.size() : 0; }
 
+// record(), nuts333.c:2062-2071: strncpy pads with NULs, byte REVIEW_LEN becomes '\n', the next one NUL.
+static void do_record(nutsb_ctx *c, i32 room, const char *str)
+{
+    if (room < 0 || room >= (i32)c->rev.size()) return;
+    nutsb_ctx::RevBuf &rb = c->rev[(size_t)room];
+    strncpy(rb.buf[rb.line], str, NUTSB_REVIEW_LEN);
+    rb.buf[rb.line][NUTSB_REVIEW_LEN] = '\n';
+    rb.buf[rb.line][NUTSB_REVIEW_LEN + 1] = '\0';
+    rb.line = (rb.line + 1) % NUTSB_REVIEW_LINES;
+}
+
+// The swear verdicts of the queued lines (one device batch) and the record() calls that waited for them.
+static int resolve_records(nutsb_ctx *c)
+{
+    const i64 n_sw = (i64)c->q_sw_off.size() - 1;
+    if ((i64)c->q_sw_verdict.size() < n_sw) {
+        static const u8 zero = 0;
+        c->q_sw_verdict.assign((size_t)n_sw, 0);
+        TRY(nutsb_contains_swearing_batch(c, n_sw, c->q_sw_text.empty() ? &zero : c->q_sw_text.data(), c->q_sw_off.data(),
+                                          c->q_sw_verdict.data()));
+    }
+    for (const auto &r : c->q_rec)
+        if (r.gate < 0 || !c->q_sw_verdict[(size_t)r.gate]) do_record(c, r.room, r.text.c_str());
+    c->q_rec.clear();
+    return NUTSB_OK;
+}
+
+NUTSB_API int nutsb_q_record(nutsb_ctx *c, int32_t room, const char *str)
+{
+    if (!c || !str) return NUTSB_E_INVAL;
+    if (room < 0 || room >= c->R) return fail(c, NUTSB_E_RANGE, "room index out of range%s");
+    c->q_rec.push_back({ room, -1, std::string(str) });      // after the records still waiting for a verdict
+    return NUTSB_OK;
+}
+
+NUTSB_API int nutsb_q_review_clear(nutsb_ctx *c, int32_t room)     // clear_revbuff(), c:2626
+{
+    if (!c) return NUTSB_E_INVAL;
+    if (room < 0 || room >= c->R) return fail(c, NUTSB_E_RANGE, "room index out of range%s");
+    TRY(resolve_records(c));
+    for (auto &l : c->rev[(size_t)room].buf) l[0] = '\0';
+    return NUTSB_OK;
+}
+
+// review(), nuts333.c:5192-5222, for a room the caller has resolved (get_room / has_room_access are the
+// talker's): the buffered lines go through write_user again, oldest first.
+NUTSB_API int nutsb_q_review(nutsb_ctx *c, int32_t user, int32_t room, const char *room_name)
+{
+    if (!c || !room_name) return NUTSB_E_INVAL;
+    if (room < 0 || room >= c->R) return fail(c, NUTSB_E_RANGE, "room index out of range%s");
+    TRY(resolve_records(c));
+    const nutsb_ctx::RevBuf &rb = c->rev[(size_t)room];
+    int cnt = 0;
+    for (int i = 0; i < NUTSB_REVIEW_LINES; ++i) {
+        const int line = (rb.line + i) % NUTSB_REVIEW_LINES;
+        if (rb.buf[line][0]) {
+            if (++cnt == 1) {
+                const std::string head = std::string("\n~BB~FG*** Review buffer for the ") + room_name + " ***\n\n";
+                TRY(nutsb_q_write_user(c, user, head.c_str()));
+            }
+            TRY(nutsb_q_write_user(c, user, rb.buf[line]));
+        }
+    }
+    if (!cnt) return nutsb_q_write_user(c, user, "Review buffer is empty.\n");
+    return nutsb_q_write_user(c, user, "\n~BB~FG*** End ***\n\n");
+}
+
 NUTSB_API int nutsb_flush(nutsb_ctx *c, nutsb_streams *out)
 {
     if (!c || !out) return NUTSB_E_INVAL;
@@ -1073,17 +1149,13 @@ NUTSB_API int nutsb_flush(nutsb_ctx *c, nutsb_streams *out)
     static const u8 zero = 0;
     o.text = c->q_text.empty() ? &zero : c->q_text.data(); o.text_off = c->q_off.data();
     o.kind = c->q_kind.data(); o.target = c->q_target.data(); o.except_user = c->q_except.data(); o.flags = c->q_flags.data();
-    std::vector<u8> verdict;
-    int rc = NUTSB_OK;
+    // the swear verdicts the queued say/shout/emote lines branch on: one device batch (unless a review took them)
+    int rc = resolve_records(c);
     const i64 n_sw = (i64)c->q_sw_off.size() - 1;
-    if (n_sw > 0) {        // the swear verdicts the queued say/shout/emote lines branch on: one device batch
-        verdict.assign((size_t)n_sw, 0);
-        rc = nutsb_contains_swearing_batch(c, n_sw, c->q_sw_text.empty() ? &zero : c->q_sw_text.data(), c->q_sw_off.data(), verdict.data());
-        o.gate = c->q_gate.data(); o.verdict = verdict.data();
-    }
+    if (rc == NUTSB_OK && n_sw > 0) { o.gate = c->q_gate.data(); o.verdict = c->q_sw_verdict.data(); }
     if (rc == NUTSB_OK) rc = nutsb_write_batch(c, &o, out);
     c->q_text.clear(); c->q_off.assign(1, 0); c->q_kind.clear(); c->q_target.clear(); c->q_except.clear(); c->q_flags.clear();
-    c->q_gate.clear(); c->q_sw_text.clear(); c->q_sw_off.assign(1, 0);
+    c->q_gate.clear(); c->q_sw_text.clear(); c->q_sw_off.assign(1, 0); c->q_sw_verdict.clear(); c->q_rec.clear();
     return rc;
 }
 
@@ -1148,6 +1220,10 @@ NUTSB_API int nutsb_q_speech(nutsb_ctx *c, int verb, int32_t user, const char *i
             }
             c->q_gate.back() = gate;
         }
+        // say, emote and echo record the line to the room in its review buffer (c:4099, c:4209, c:4304) --
+        // once it is known not to be refused
+        if (sidx == 2 && room >= 0 && (verb == NUTSB_SPEECH_SAY || verb == NUTSB_SPEECH_EMOTE || verb == NUTSB_SPEECH_ECHO))
+            c->q_rec.push_back({ room, sl.gated ? gate : -1, text });
     }
     return NUTSB_OK;
 }

@@ -421,6 +421,45 @@ static const char orc_noswearing[] = "Swearing is not allowed here.\n";      /* 
 static const char orc_invisname[] = "A presence";                            /* h:150 */
 
 /* verbs: 0 say c:4062, 1 shout c:4105, 2 emote c:4188, 3 semote c:4213, 4 echo c:4289, 5 bcast c:4772 */
+/* Review buffers, c:2062-2071 (record) and c:5192-5222 (review): 15 lines of 200 bytes per room, a ring.
+ * strncpy pads with NULs, then byte 200 is set to '\n' and byte 201 to NUL: a line of 200 bytes or more is
+ * kept as its first 200 bytes plus a newline, a shorter one as it is (the '\n' sits behind the terminator). */
+#define ORC_REVIEW_LINES 15
+#define ORC_REVIEW_LEN   200
+typedef struct { char buf[ORC_REVIEW_LINES][ORC_REVIEW_LEN + 2]; int line; } orc_revbuf;
+static orc_revbuf *orc_rev = NULL; static int32_t orc_rev_rooms = 0;
+
+static void orc_record(int32_t room, const char *str)
+{
+    if (!orc_rev || room < 0 || room >= orc_rev_rooms) return;
+    orc_revbuf *rb = &orc_rev[room];
+    strncpy(rb->buf[rb->line], str, ORC_REVIEW_LEN);
+    rb->buf[rb->line][ORC_REVIEW_LEN] = '\n';
+    rb->buf[rb->line][ORC_REVIEW_LEN + 1] = '\0';
+    rb->line = (rb->line + 1) % ORC_REVIEW_LINES;
+}
+
+static void orc_emit(orc_oplist *L, uint8_t kind, int32_t target, int32_t exc, uint8_t flags, const char *str, size_t n);
+/* review() with no argument: the user's own room (c:5200) */
+static void orc_review(orc_oplist *L, int32_t user, int32_t room)
+{
+    char text[512]; int cnt = 0;
+    if (!orc_rev || room < 0 || room >= orc_rev_rooms) return;
+    const orc_revbuf *rb = &orc_rev[room];
+    for (int i = 0; i < ORC_REVIEW_LINES; ++i) {
+        const int line = (rb->line + i) % ORC_REVIEW_LINES;
+        if (rb->buf[line][0]) {
+            if (++cnt == 1) {
+                const int len = snprintf(text, sizeof text, "\n~BB~FG*** Review buffer for the room%d ***\n\n", room);
+                orc_emit(L, 0, user, -1, 0, text, (size_t)len);
+            }
+            orc_emit(L, 0, user, -1, 0, rb->buf[line], strlen(rb->buf[line]));
+        }
+    }
+    if (!cnt) { const char *m = "Review buffer is empty.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); }
+    else { const char *m = "\n~BB~FG*** End ***\n\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); }
+}
+
 static void orc_speech_one(orc_oplist *L, int verb, int32_t user, const char *uname, int vis, int muzzled, int32_t room,
                            int ban_swearing, const char *const *words, const uint8_t *in, size_t n)
 {
@@ -438,6 +477,7 @@ static void orc_speech_one(orc_oplist *L, int verb, int32_t user, const char *un
         orc_emit(L, 0, user, -1, 0, text, (size_t)len);                              /* c:4095 */
         len = snprintf(text, sizeof text, "%s %ss: %.*s\n", name, type, (int)n, (const char *)in);
         orc_emit(L, 1, room, user, 0, text, (size_t)len);                            /* c:4098 */
+        orc_record(room, text);                                                      /* c:4099 */
         return; }
     case 1:
         if (muzzled) { const char *m = "You are muzzled, you cannot shout.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
@@ -454,6 +494,7 @@ static void orc_speech_one(orc_oplist *L, int verb, int32_t user, const char *un
         if (n && in[0] == ';') len = snprintf(text, sizeof text, "%s%.*s\n", name, (int)(n - 1), (const char *)in + 1);
         else len = snprintf(text, sizeof text, "%s %.*s\n", name, (int)n, (const char *)in);
         orc_emit(L, 1, room, -1, 0, text, (size_t)len);                              /* c:4208 write_room(user->room) */
+        orc_record(room, text);                                                      /* c:4209 */
         return;
     case 3:
         if (muzzled) { const char *m = "You are muzzled, you cannot emote.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
@@ -468,6 +509,10 @@ static void orc_speech_one(orc_oplist *L, int verb, int32_t user, const char *un
         orc_emit(L, 2, 2 /* WIZ */, -1, ORC_OF_ABOVE, text, (size_t)len);            /* c:4301 write_level(WIZ,1,text,NULL) */
         len = snprintf(text, sizeof text, "- %.*s\n", (int)n, (const char *)in);
         orc_emit(L, 1, room, -1, 0, text, (size_t)len);                              /* c:4303 */
+        orc_record(room, text);                                                      /* c:4304 */
+        return;
+    case 6:                                                     /* review, c:5192: the speaker looks at his own room */
+        orc_review(L, user, room);
         return;
     case 5:
         if (muzzled) { const char *m = "You are muzzled, you cannot broadcast anything.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
@@ -489,6 +534,12 @@ int64_t orc_speech_ops(int64_t n, const uint8_t *verb, const int32_t *speaker, c
 {
     orc_oplist L = { text, 0, text_cap, off, kind, target, except_user, flags, 0, cap };
     off[0] = 0;
+    /* review buffers start empty (c:2799) and live for the n lines of this call */
+    int32_t max_room = -1, n_users = 0;
+    for (int64_t m = 0; m < n; ++m) if (speaker[m] >= n_users) n_users = speaker[m] + 1;
+    for (int32_t u = 0; u < n_users; ++u) if (room[u] > max_room) max_room = room[u];
+    orc_rev_rooms = max_room + 1;
+    orc_rev = orc_rev_rooms ? (orc_revbuf *)calloc((size_t)orc_rev_rooms, sizeof(orc_revbuf)) : NULL;
     for (int64_t m = 0; m < n; ++m) {
         const int32_t u = speaker[m];
         char uname[64]; size_t nl = (size_t)(name_off[u + 1] - name_off[u]);
@@ -496,7 +547,8 @@ int64_t orc_speech_ops(int64_t n, const uint8_t *verb, const int32_t *speaker, c
         memcpy(uname, names + name_off[u], nl); uname[nl] = 0;
         orc_speech_one(&L, verb[m], u, uname, !(sflags[u] & 1), (sflags[u] & 2) != 0, room[u], ban_swearing, words,
                        bodies + body_off[m], (size_t)(body_off[m + 1] - body_off[m]));
-        if (L.n > L.cap) return -1;
+        if (L.n > L.cap) { free(orc_rev); orc_rev = NULL; return -1; }
     }
+    free(orc_rev); orc_rev = NULL;
     return L.n;
 }

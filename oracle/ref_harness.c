@@ -215,6 +215,7 @@ void ref_speech(int verb, int u, const char *inpstr)
     case 3: com_num = SEMOTE; semote(g_users[u], line); break;
     case 4: com_num = ECHO;   echo(g_users[u], line); break;
     case 5: com_num = BCAST;  bcast(g_users[u], line); break;
+    case 6: com_num = REVIEW; word_count = 1; review(g_users[u]); break;   /* c:5192, no argument: the user's own room */
     }
     force_listen = 0;
 }

@@ -189,8 +189,9 @@ class Port:
     def speech_ops(self, verb, speaker, bodies, body_off, names, name_off, sflags, room, ban_swearing, words):
         """input lines -> ops dict (the callers restated)"""
         n = len(verb)
-        cap = 3 * n + 1
-        tcap = int(body_off[-1]) * 2 + 256 * n + 64
+        n_rev = int((np.asarray(verb) == 6).sum())              # a review replays up to 15 lines + header + footer
+        cap = 3 * n + 17 * n_rev + 1
+        tcap = int(body_off[-1]) * 2 + 256 * n + 17 * 256 * n_rev + 64
         text = np.zeros(tcap, np.uint8); off = np.zeros(cap + 1, np.uint64); kind = np.zeros(cap, np.uint8)
         target = np.zeros(cap, np.int32); exc = np.zeros(cap, np.int32); flags = np.zeros(cap, np.uint8)
         q = self.lib.orc_speech_ops(n, _ptr(np.ascontiguousarray(verb, np.uint8), u8p), _ptr(np.ascontiguousarray(speaker, np.int32), i32p),
