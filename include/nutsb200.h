@@ -158,6 +158,15 @@ int nutsb_set_swear_words(nutsb_ctx *ctx, const char *const *words);
  * followed by whitespace is never tested).  NULL = file missing (verdict 0). */
 int nutsb_set_ban_files(nutsb_ctx *ctx, const void *siteban, size_t siteban_len,
                         const void *userban, size_t userban_len);
+/* Ban-list maintenance (nuts333.c:6216-6429) on the lists held by the context: which 0 = siteban,
+ * 1 = userban (first byte upper-cased, c:6269); add 1 = ban_site / ban_user: append "token\n" unless a
+ * TESTED token equals it (strcmp); add 0 = unban_*: the list rewritten without it, every tested token as
+ * "token\n" -- a last token that ran into EOF is dropped (the reference's feof() loop), an emptied list is
+ * removed.  The matchers in HBM follow at once.  *result: 0 done, 1 nothing to do ("already banned" /
+ * "not currently banned").  The command's own checks (own host, levels, user files) are the talker's.
+ * nutsb_get_ban_file: the list as it stands, to be written back to datafiles/ (*present 0: no file). */
+int nutsb_ban_edit(nutsb_ctx *ctx, int which, int add, const char *token, int *result);
+int nutsb_get_ban_file(nutsb_ctx *ctx, int which, const void **bytes, size_t *len, int *present);
 
 /* Population, index = position in the reference's user list (creation order,
  * c:2683-2691).  room[u] in [0,n_rooms) or -1 (user->room==NULL). */

@@ -67,7 +67,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "nutsb_version", "nutsb_strerror", "nutsb_last_error", "nutsb_create", "nutsb_destroy",
     "nutsb_set_profiling", "nutsb_get_timing", "nutsb_set_overlap", "nutsb_set_stream", "nutsb_set_swear_words",
-    "nutsb_set_ban_files", "nutsb_set_users", "nutsb_write_batch", "nutsb_write_batch_dev",
+    "nutsb_set_ban_files", "nutsb_ban_edit", "nutsb_get_ban_file", "nutsb_set_users", "nutsb_write_batch", "nutsb_write_batch_dev",
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
     "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_q_speech",
@@ -111,6 +111,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_speech_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
     lib.nutsb_speech_batch_dev.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
     lib.nutsb_q_speech.argtypes = [vp, C.c_int, C.c_int32, C.c_char_p]
+    lib.nutsb_ban_edit.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int)]
+    lib.nutsb_get_ban_file.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
     lib.nutsb_q_record.argtypes = [vp, C.c_int32, C.c_char_p]
     lib.nutsb_q_review.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
     lib.nutsb_q_review_clear.argtypes = [vp, C.c_int32]
@@ -241,6 +243,20 @@ class Context:
         self._ck(self.lib.nutsb_speech_batch(self._h, len(verb), _addr(verb), _addr(speaker),
                                              _addr(bodies) if bodies.size else None, _addr(body_off), C.byref(st)))
         return self._host_streams(st)
+
+    def ban_edit(self, which: int, add: bool, token) -> int:
+        """ban_site/ban_user (add) or unban_site/unban_user on the context's lists -> 0 done, 1 nothing to do"""
+        r = C.c_int(0)
+        self._ck(self.lib.nutsb_ban_edit(self._h, which, 1 if add else 0, token if isinstance(token, bytes) else token.encode("latin-1"), C.byref(r)))
+        return r.value
+
+    def ban_file(self, which: int):
+        """the list as it stands -> bytes, or None when there is no file"""
+        p, n, pr = C.c_void_p(), C.c_size_t(0), C.c_int(0)
+        self._ck(self.lib.nutsb_get_ban_file(self._h, which, C.byref(p), C.byref(n), C.byref(pr)))
+        if not pr.value:
+            return None
+        return C.string_at(p, n.value) if n.value else b""
 
     def set_profiling(self, on=True):
         self._ck(self.lib.nutsb_set_profiling(self._h, 1 if on else 0))

@@ -59,6 +59,7 @@ struct nutsb_ctx {
     DBuf d_codetab;
     AcDev swear, site; SetDev userban;
     bool site_file = false, user_file = false;
+    std::vector<u8> ban_bytes[2];   // the two lists as they stand on disk (nutsb_ban_edit edits them)
 
     // population
     bool have_users = false, all_simple = true;
@@ -441,14 +442,16 @@ NUTSB_API int nutsb_set_swear_words(nutsb_ctx *c, const char *const *words)
     return set_swear_impl(c, words);
 }
 
-NUTSB_API int nutsb_set_ban_files(nutsb_ctx *c, const void *siteban, size_t sn, const void *userban, size_t un)
+static int set_ban_files_impl(nutsb_ctx *c, const void *siteban, size_t sn, const void *userban, size_t un)
 {
-    if (!c) return NUTSB_E_INVAL;
     CK(cudaSetDevice(c->device));
     std::vector<std::string> st, ut;
     if (siteban) TRY(ban_tokens(c, (const u8 *)siteban, sn, st));
     if (userban) TRY(ban_tokens(c, (const u8 *)userban, un, ut));
     c->site_file = siteban != nullptr; c->user_file = userban != nullptr;
+    // (the vectors may be the very buffers passed in: nutsb_ban_edit)
+    if ((const void *)c->ban_bytes[0].data() != siteban || !siteban) c->ban_bytes[0].assign((const u8 *)siteban, (const u8 *)siteban + (siteban ? sn : 0));
+    if ((const void *)c->ban_bytes[1].data() != userban || !userban) c->ban_bytes[1].assign((const u8 *)userban, (const u8 *)userban + (userban ? un : 0));
     { AcHost h; build_ac(st, false, h); TRY(upload_ac(c, h, c->site)); }
     // exact-match set
     u32 nslots = 1; while (nslots < 2 * ut.size() + 1) nslots <<= 1;
@@ -468,6 +471,66 @@ NUTSB_API int nutsb_set_ban_files(nutsb_ctx *c, const void *siteban, size_t sn, 
     c->userban.view.pool = c->userban.pool.as<u8>(); c->userban.view.mask = nslots - 1;
     c->userban.view.count = (u32)ut.size(); c->userban.present = true;
     CK(cudaStreamSynchronize(c->stream));
+    return NUTSB_OK;
+}
+
+NUTSB_API int nutsb_set_ban_files(nutsb_ctx *c, const void *siteban, size_t sn, const void *userban, size_t un)
+{
+    if (!c) return NUTSB_E_INVAL;
+    return set_ban_files_impl(c, siteban, sn, userban, un);
+}
+
+// Ban-list maintenance, nuts333.c:6216-6429, on the lists the context holds: ban_site / ban_user
+// (add = 1) append "token\n" unless a TESTED token equals it; unban_site / unban_user (add = 0)
+// rewrite the list without it -- every tested token as "token\n", the last token dropped when it ran
+// into EOF (the same feof() loop as site_banned), an emptied list removed.  The matchers in HBM are
+// rebuilt at once.  *result: 0 done, 1 nothing to do ("already banned" / "not currently banned").
+NUTSB_API int nutsb_ban_edit(nutsb_ctx *c, int which, int add, const char *token, int *result)
+{
+    if (!c || !token || !result || which < 0 || which > 1) return NUTSB_E_INVAL;
+    std::string tok(token);
+    if (tok.empty() || tok.size() > (which ? 12u : 79u)) return fail(c, NUTSB_E_RANGE, "ban token length (site < 80, user <= 12: the reference's buffers)%s");
+    for (unsigned char b : tok) if (b == ' ' || (b >= 9 && b <= 13)) return fail(c, NUTSB_E_INVAL, "ban token holds white space%s");
+    if (which && tok[0] >= 'a' && tok[0] <= 'z') tok[0] = (char)(tok[0] - 32);      // c:6269, c:6402
+    const bool present = which ? c->user_file : c->site_file;
+    const std::vector<u8> &f = c->ban_bytes[which];
+    *result = 1;
+    if (!present && !add) return NUTSB_OK;                          // c:6349
+    std::vector<std::string> tested;
+    if (present) TRY(ban_tokens(c, f.data(), f.size(), tested));
+    std::vector<u8> nf; bool npresent = true;
+    if (add) {
+        for (auto &t : tested) if (t == tok) return NUTSB_OK;       // c:6234: "already banned"
+        nf = present ? f : std::vector<u8>();
+        nf.insert(nf.end(), tok.begin(), tok.end()); nf.push_back('\n');              // c:6250, fopen("a")
+    } else {
+        bool found = false;
+        for (auto &t : tested) {
+            if (t == tok) { found = true; continue; }
+            nf.insert(nf.end(), t.begin(), t.end()); nf.push_back('\n');               // c:6361
+        }
+        if (!found) return NUTSB_OK;                                // c:6369
+        npresent = !nf.empty();                                     // c:6375: an emptied list is unlinked
+    }
+    *result = 0;
+    std::vector<u8> other = c->ban_bytes[which ^ 1];
+    const bool opresent = which ? c->site_file : c->user_file;
+    const void *sp = which ? (opresent ? (const void *)other.data() : nullptr) : (npresent ? (const void *)nf.data() : nullptr);
+    const void *up = which ? (npresent ? (const void *)nf.data() : nullptr) : (opresent ? (const void *)other.data() : nullptr);
+    static const u8 none = 0;                                       // an existing but empty file is not NULL
+    if (!which && npresent && nf.empty()) sp = &none;
+    if (which && npresent && nf.empty()) up = &none;
+    if (!which && opresent && other.empty()) up = &none;
+    if (which && opresent && other.empty()) sp = &none;
+    return set_ban_files_impl(c, sp, which ? other.size() : nf.size(), up, which ? nf.size() : other.size());
+}
+
+// The list as it stands (what the talker writes back to datafiles/siteban | userban).  *present = 0: no file.
+NUTSB_API int nutsb_get_ban_file(nutsb_ctx *c, int which, const void **bytes, size_t *len, int *present)
+{
+    if (!c || !bytes || !len || !present || which < 0 || which > 1) return NUTSB_E_INVAL;
+    *present = (which ? c->user_file : c->site_file) ? 1 : 0;
+    *bytes = c->ban_bytes[which].data(); *len = *present ? c->ban_bytes[which].size() : 0;
     return NUTSB_OK;
 }
 

@@ -421,6 +421,50 @@ static const char orc_noswearing[] = "Swearing is not allowed here.\n";      /* 
 static const char orc_invisname[] = "A presence";                            /* h:150 */
 
 /* verbs: 0 say c:4062, 1 shout c:4105, 2 emote c:4188, 3 semote c:4213, 4 echo c:4289, 5 bcast c:4772 */
+/* ---- ban-list maintenance ------------------------------------------------------------------
+ * Both commands read the list with the same fscanf("%s") / while(!feof) loop as site_banned
+ * (c:6232-6240, c:6359-6367): a last token that runs into EOF is never looked at -- so it can be
+ * banned twice, and unban silently DROPS it from the rewritten file.  ban appends "token\n" with
+ * fopen("a") (c:6250): after a file without a final newline the new token is glued to the last one.
+ * unban rewrites every other tested token as "token\n"; an emptied list is unlinked (c:6376).
+ * user tokens: first byte upper-cased (c:6269, c:6402).  Comparison is strcmp, both lists. */
+int orc_ban_edit(const uint8_t *file, size_t n, int present, int is_user, int add, const char *token,
+                 uint8_t *out, size_t *out_n, int *out_present)
+{
+    char tok[128]; size_t tl = strlen(token);
+    if (tl > 80) tl = 80;
+    memcpy(tok, token, tl); tok[tl] = 0;
+    if (is_user && tok[0] >= 'a' && tok[0] <= 'z') tok[0] = (char)(tok[0] - 32);
+    size_t p = 0, o = 0; int found = 0, cnt = 0;
+    *out_present = present; *out_n = present ? n : 0;
+    if (present) memcpy(out, file, n);
+    if (!present && !add) return 1;                              /* c:6349: cannot open -> "not currently banned" */
+    if (present) {
+        for (;;) {
+            while (p < n && (file[p] == ' ' || (file[p] >= 9 && file[p] <= 13))) ++p;
+            if (p >= n) break;
+            const size_t b = p;
+            while (p < n && !(file[p] == ' ' || (file[p] >= 9 && file[p] <= 13))) ++p;
+            if (p >= n) break;                                   /* ran into EOF: feof() is set, the loop ends */
+            size_t m = 0; while (m < p - b && file[b + m]) ++m;  /* a C string: cut at NUL */
+            const int same = m == tl && memcmp(file + b, tok, m) == 0;
+            if (add) { if (same) return 1; }                     /* "already banned" */
+            else if (same) found = 1;
+            else { memcpy(out + o, file + b, m); o += m; out[o++] = '\n'; ++cnt; }
+        }
+    }
+    if (add) {
+        const size_t base = present ? n : 0;
+        memcpy(out + base, tok, tl); out[base + tl] = '\n';
+        *out_n = base + tl + 1; *out_present = 1;
+        return 0;
+    }
+    if (!found) { memcpy(out, file, n); *out_n = n; return 1; }   /* tempfile unlinked, list untouched */
+    *out_n = o; *out_present = cnt ? 1 : 0;
+    if (!cnt) *out_n = 0;
+    return 0;
+}
+
 /* Review buffers, c:2062-2071 (record) and c:5192-5222 (review): 15 lines of 200 bytes per room, a ring.
  * strncpy pads with NULs, then byte 200 is set to '\n' and byte 201 to NUL: a line of 200 bytes or more is
  * kept as its first 200 bytes plus a newline, a shorter one as it is (the '\n' sits behind the terminator). */

@@ -114,6 +114,13 @@ void orc_site_banned_batch(const uint8_t *file, size_t fn, int present, int64_t 
 void orc_user_banned_batch(const uint8_t *file, size_t fn, int present, int64_t n,
                            const uint8_t *text, const uint64_t *off, uint8_t *verdict);
 
+/* Ban-list maintenance on file bytes (see nuts_oracle.c): ban_site c:6216 / ban_user c:6262 (add = 1),
+ * unban_site c:6341 / unban_user c:6385 (add = 0).  out receives the file as it stands afterwards
+ * (cap >= n + strlen(token) + 2), *out_present whether it exists.  Returns 0 done, 1 nothing to do
+ * ("already banned" / "not currently banned"). */
+int orc_ban_edit(const uint8_t *file, size_t n, int present, int is_user, int add, const char *token,
+                 uint8_t *out, size_t *out_n, int *out_present);
+
 /* The callers say/shout/emote/semote/echo/bcast restated (see nuts_oracle.c): input lines -> ops. */
 int64_t orc_speech_ops(int64_t n, const uint8_t *verb, const int32_t *speaker, const uint8_t *bodies, const uint64_t *body_off,
                        const uint8_t *names, const uint64_t *name_off, const uint8_t *sflags, const int32_t *room,

@@ -189,6 +189,37 @@ int ref_set_ban_file(const char *dir, int which, const void *data, size_t n)
     fclose(fp);
     return 0;
 }
+/* The reference's own ban / unban commands (c:6216-6429) run by user `by` in the CWD (a scratch dir
+ * with datafiles/): which 0 site, 1 user; add 1 ban, 0 unban.  An offline user is banned only if his
+ * userfile says a lower level (c:6287-6297): the harness puts a level-0 userfile in place first. */
+int ref_ban_command(const char *dir, int by, int which, int add, const char *token)
+{
+    char path[600];
+    if (by < 0 || by >= g_nusers || chdir(dir) != 0) return -1;
+    mkdir(DATAFILES, 0777); mkdir(USERFILES, 0777);
+    strncpy(word[2], token, WORD_LEN); word[2][WORD_LEN] = 0;
+    word_count = 3;
+    if (which && add) {
+        char nm[WORD_LEN + 2]; strcpy(nm, word[2]); nm[0] = (char)toupper((unsigned char)nm[0]);
+        snprintf(path, sizeof path, "%s/%s.D", USERFILES, nm);
+        FILE *fp = fopen(path, "w");
+        if (fp) { fputs("x\n0 0 0 0 0\n", fp); fclose(fp); }
+    }
+    if (!which) { if (add) ban_site(g_users[by]); else unban_site(g_users[by]); }
+    else        { if (add) ban_user(g_users[by]); else unban_user(g_users[by]); }
+    return 0;
+}
+/* the ban file as it now stands on disk: returns its length, -1 if it does not exist */
+long ref_get_ban_file(const char *dir, int which, void *out, size_t cap)
+{
+    char path[600];
+    snprintf(path, sizeof path, "%s/%s/%s", dir, DATAFILES, which ? USERBAN : SITEBAN);
+    FILE *fp = fopen(path, "rb");
+    if (!fp) return -1;
+    const size_t n = fread(out, 1, cap, fp);
+    fclose(fp);
+    return (long)n;
+}
 int ref_site_banned(const char *site) { return site_banned((char *)site); }
 int ref_user_banned(const char *name) { return user_banned((char *)name); }
 

@@ -102,6 +102,9 @@ class Port:
         L.orc_more.restype = C.c_int
         L.orc_more.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.c_char_p,
                                C.POINTER(C.c_size_t)]
+        L.orc_ban_edit.restype = C.c_int
+        L.orc_ban_edit.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p,
+                                   C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
         L.orc_fnv1a.restype = C.c_uint64
         L.orc_fnv1a.argtypes = [C.c_char_p, C.c_size_t]
 
@@ -186,6 +189,14 @@ class Port:
         fn(file or b"", len(file or b""), int(file is not None), n, _ptr(text, u8p), _ptr(off, u64p), _ptr(v, u8p))
         return v[:n]
 
+    def ban_edit(self, file, is_user: bool, add: bool, token: bytes):
+        """ban / unban restated on file bytes (None = no file) -> (result, file afterwards or None)"""
+        data = file or b""
+        out = C.create_string_buffer(len(data) + len(token) + 8)
+        on, op = C.c_size_t(0), C.c_int(0)
+        r = self.lib.orc_ban_edit(data, len(data), int(file is not None), int(is_user), int(add), token, out, C.byref(on), C.byref(op))
+        return r, (out.raw[:on.value] if op.value else None)
+
     def speech_ops(self, verb, speaker, bodies, body_off, names, name_off, sflags, room, ban_swearing, words):
         """input lines -> ops dict (the callers restated)"""
         n = len(verb)
@@ -246,6 +257,9 @@ class Ref:
         L.ref_speech.argtypes = [C.c_int, C.c_int, C.c_char_p]
         L.ref_more.argtypes = [C.c_int, C.c_int, C.c_char_p]
         L.ref_get_filepos.restype = C.c_long
+        L.ref_ban_command.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
+        L.ref_get_ban_file.restype = C.c_long
+        L.ref_get_ban_file.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
         L.ref_write_batch.restype = C.c_int64
         L.ref_write_batch.argtypes = [C.c_int64, u8p, u64p, u8p, i32p, i32p, u8p, i32p, u8p]
         L.ref_contains_swearing_batch.argtypes = [C.c_int64, u8p, u64p, u8p]
@@ -311,6 +325,18 @@ class Ref:
             return fn(*a)
         finally:
             os.chdir(cwd)
+
+    def ban_command(self, by: int, which: int, add: bool, token: bytes):
+        """the reference's own ban_site / ban_user / unban_site / unban_user -> the list on disk afterwards"""
+        cwd = os.getcwd()
+        try:
+            rc = self.lib.ref_ban_command(self._tmp.encode(), by, which, int(add), token)
+        finally:
+            os.chdir(cwd)
+        assert rc == 0
+        buf = C.create_string_buffer(1 << 20)
+        n = self.lib.ref_get_ban_file(self._tmp.encode(), which, buf, len(buf))
+        return None if n < 0 else buf.raw[:n]
 
     def site_banned(self, site: bytes) -> int:
         return self._in_tmp(self.lib.ref_site_banned, site)
