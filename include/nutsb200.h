@@ -66,7 +66,7 @@ enum {
 #define NUTSB_UF_LOGIN    0x02u  /* user->login  != 0            */
 #define NUTSB_UF_IGNALL   0x04u  /* user->ignall                 */
 #define NUTSB_UF_IGNSHOUT 0x08u  /* user->ignshout               */
-#define NUTSB_UF_CLONE    0x10u  /* type==CLONE_TYPE  (rejected) */
+#define NUTSB_UF_CLONE    0x10u  /* type==CLONE_TYPE: receives nothing itself; nutsb_set_clones */
 #define NUTSB_UF_REMOTE   0x20u  /* type==REMOTE_TYPE (rejected) */
 
 /* op kinds: one op == one call of the reference's write surface */
@@ -146,6 +146,16 @@ int  nutsb_get_timing(const nutsb_ctx *ctx, nutsb_timing *out);
 int  nutsb_set_overlap(nutsb_ctx *ctx, int on);
 /* Use the caller's CUDA stream (a cudaStream_t) instead of the context's own. */
 int  nutsb_set_stream(nutsb_ctx *ctx, void *cuda_stream);
+
+/* Clones (nuts333.c:1416-1426): owner[u] = index of the owner of clone u, -1 for everybody else (clones are the
+ * users flagged NUTSB_UF_CLONE); hear[u] = clone_hear (0 nothing, 1 swears, 2 all).  Call after
+ * nutsb_set_users.  The queue tier then makes the relays: a room op naming a clone's room also queues
+ * write_user(owner, "~FT[ <room> ]:~RS <str>") at the clone's place in the user list, unless the clone is
+ * filtered like any recipient, hears nothing, its owner ignores everything, or (hear 1) the string does not
+ * swear.  The batch tier takes ops as given: clones receive nothing there.  Room names: rm->name, default
+ * "room<index>". */
+int nutsb_set_clones(nutsb_ctx *ctx, int32_t n_users, const int32_t *owner, const uint8_t *hear);
+int nutsb_set_room_names(nutsb_ctx *ctx, int32_t n_rooms, const uint8_t *names, const uint64_t *off);
 
 /* ---- tables ------------------------------------------------------------- */
 

@@ -67,7 +67,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "nutsb_version", "nutsb_strerror", "nutsb_last_error", "nutsb_create", "nutsb_destroy",
     "nutsb_set_profiling", "nutsb_get_timing", "nutsb_set_overlap", "nutsb_set_stream", "nutsb_set_swear_words",
-    "nutsb_set_ban_files", "nutsb_ban_edit", "nutsb_get_ban_file", "nutsb_set_users", "nutsb_write_batch", "nutsb_write_batch_dev",
+    "nutsb_set_ban_files", "nutsb_ban_edit", "nutsb_get_ban_file", "nutsb_set_users", "nutsb_set_clones", "nutsb_set_room_names", "nutsb_write_batch", "nutsb_write_batch_dev",
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
     "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_q_speech",
@@ -111,6 +111,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_speech_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
     lib.nutsb_speech_batch_dev.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
     lib.nutsb_q_speech.argtypes = [vp, C.c_int, C.c_int32, C.c_char_p]
+    lib.nutsb_set_clones.argtypes = [vp, C.c_int32, vp, vp]
+    lib.nutsb_set_room_names.argtypes = [vp, C.c_int32, vp, vp]
     lib.nutsb_ban_edit.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int)]
     lib.nutsb_get_ban_file.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
     lib.nutsb_q_record.argtypes = [vp, C.c_int32, C.c_char_p]
@@ -243,6 +245,16 @@ class Context:
         self._ck(self.lib.nutsb_speech_batch(self._h, len(verb), _addr(verb), _addr(speaker),
                                              _addr(bodies) if bodies.size else None, _addr(body_off), C.byref(st)))
         return self._host_streams(st)
+
+    def set_clones(self, owner, hear):
+        owner, hear = _np(owner, np.int32), _np(hear, np.uint8)
+        self._ck(self.lib.nutsb_set_clones(self._h, len(owner), _addr(owner), _addr(hear)))
+
+    def set_room_names(self, names):
+        data = np.frombuffer(b"".join(names) or b"\0", np.uint8)
+        off = np.zeros(len(names) + 1, np.uint64)
+        off[1:] = np.cumsum([len(n) for n in names])
+        self._ck(self.lib.nutsb_set_room_names(self._h, len(names), _addr(data), _addr(off)))
 
     def ban_edit(self, which: int, add: bool, token) -> int:
         """ban_site/ban_user (add) or unban_site/unban_user on the context's lists -> 0 done, 1 nothing to do"""

@@ -190,7 +190,8 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
         kind = ops.kind[i];
         const i32 tgt = ops.target[i], exc = ops.except_user[i];
         if (kind == NUTSB_OP_USER) {
-            if (tgt >= pop.n_users) st |= NUTSB_ST_BAD_INDEX; else if (tgt >= 0) rep = 1;
+            if (tgt >= pop.n_users) st |= NUTSB_ST_BAD_INDEX;
+            else if (tgt >= 0) rep = (pop.cls_flags[pop.user_cls[tgt]] & NUTSB_UF_CLONE) ? 0u : 1u;   // a clone has no socket
         } else if (kind == NUTSB_OP_ROOM) {
             if (tgt >= pop.n_rooms || tgt < -1) st |= NUTSB_ST_BAD_INDEX;
             else rep = tgt >= 0 ? 1u : (u32)pop.n_rooms;
@@ -535,7 +536,7 @@ __device__ __forceinline__ u32 nutsb_plan_cell(const PlanArgs &A, u32 room, u32 
     const i32 k = A.pop.user_cls[u];
     const u32 cf = A.pop.slot_cf[s], clv = A.pop.slot_lv[s];
     const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
-    const bool full = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
+    const bool full = !A.has_level && !(cf & NUTSB_UF_FILTERED);
     const u64 *vp = (colour ? A.cpx.vp_on : A.cpx.vp_off) + g0;      // tile-local prefix of rendered lengths
     const u64 sb = colour ? 0 : A.off_base;
     // stream position of the tile's first op: class prefix + the recipient's own events before the tile
@@ -1094,7 +1095,7 @@ k_direct(DirectArgs A)
             // -- seam: the event is a discontinuity in a plain listener's stream.  k_fanout's runs cover whole
             //    32-byte sectors only; the slab bytes that share a sector with the discontinuity -- the end of the
             //    stretch before it and the start of the stretch after it -- are written here, together.
-            seam = !A.has_level && !(cf & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT));
+            seam = !A.has_level && !(cf & NUTSB_UF_FILTERED);
             if (seam) {
                 const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
                 const u64 *vp = colour ? A.cpx.vp_on : A.cpx.vp_off;

@@ -65,6 +65,10 @@ struct nutsb_ctx {
     bool have_users = false, all_simple = true;
     i32 U = 0, R = 0, Rt = 1;
     std::vector<i32> user_room, user_slot, slot_user, room_slot_off;
+    std::vector<u8> uflags;
+    std::vector<i32> clone_owner; std::vector<u8> clone_hear;   // per user; owner -1 = not a clone
+    std::vector<std::vector<i32>> room_clones;                  // clones of every room, in user-list order
+    std::vector<std::string> room_names;                        // default "room<index>"
     DBuf d_user_room, d_user_slot, d_slot_user, d_room_slot_off, d_slot_cf, d_slot_lv;
     ClassSet cls[2];                 // [0] keyed without level, [1] with level
 
@@ -565,7 +569,7 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     if (!c || n_users < 0 || n_rooms < 0 || (n_users && (!room || !flags || !level))) return fail(c, NUTSB_E_INVAL, "nutsb_set_users: bad argument%s");
     CK(cudaSetDevice(c->device));
     for (i32 u = 0; u < n_users; ++u) {
-        if (flags[u] & (NUTSB_UF_CLONE | NUTSB_UF_REMOTE)) return fail(c, NUTSB_E_UNSUPPORTED, "clone/remote recipients are not implemented%s");
+        if (flags[u] & NUTSB_UF_REMOTE) return fail(c, NUTSB_E_UNSUPPORTED, "remote (netlink) recipients are not implemented%s");
         if (room[u] >= n_rooms || room[u] < -1) return fail(c, NUTSB_E_RANGE, "user room out of range%s");
     }
     c->have_users = false; c->have_streams = false;
@@ -586,7 +590,9 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     for (i32 s = 0; s < n_users; ++s) { c->user_slot[order[s]] = s; c->room_slot_off[c->user_room[order[s]] + 1]++; }
     for (i32 r = 0; r < c->Rt; ++r) c->room_slot_off[r + 1] += c->room_slot_off[r];
     c->all_simple = true;
-    for (i32 u = 0; u < n_users; ++u) if (flags[u] & (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT)) c->all_simple = false;
+    for (i32 u = 0; u < n_users; ++u) if (flags[u] & NUTSB_UF_FILTERED) c->all_simple = false;
+    c->uflags.assign(flags, flags + n_users);
+    c->clone_owner.clear(); c->clone_hear.clear(); c->room_clones.clear();       // nutsb_set_clones follows the population
     TRY(upload(c, c->d_user_room, c->user_room.data(), (size_t)n_users * 4));
     TRY(upload(c, c->d_user_slot, c->user_slot.data(), (size_t)n_users * 4));
     TRY(upload(c, c->d_slot_user, c->slot_user.data(), (size_t)n_users * 4));
@@ -1074,17 +1080,89 @@ NUTSB_API int nutsb_user_banned(nutsb_ctx *c, const char *s) { return verdict_on
 // ---------------------------------------------------------------------------------------
 // queue tier
 // ---------------------------------------------------------------------------------------
-static int q_push(nutsb_ctx *c, u8 kind, i32 target, const char *str, i32 except_user, u8 flags)
+static int q_push_one(nutsb_ctx *c, u8 kind, i32 target, const char *str, size_t n, i32 except_user, u8 flags, i32 gate)
 {
-    if (!c || !str) return NUTSB_E_INVAL;
-    const size_t n = strlen(str);
     if (n > NUTSB_MAX_TEXT) return fail(c, NUTSB_E_RANGE, "string longer than NUTSB_MAX_TEXT (2000) bytes%s");
     c->q_text.insert(c->q_text.end(), (const u8 *)str, (const u8 *)str + n);   // copied: callers reuse text[] at once
     c->q_off.push_back((u64)c->q_text.size());
     c->q_kind.push_back(kind); c->q_target.push_back(target); c->q_except.push_back(except_user); c->q_flags.push_back(flags);
-    c->q_gate.push_back(-1);
+    c->q_gate.push_back(gate);
     return NUTSB_OK;
 }
+
+// One call of the reference's write surface.  A room op that names a room with clones in it also makes
+// the relays of nuts333.c:1416-1426: write_user(clone->owner, "~FT[ <room> ]:~RS <str>") for every clone
+// that would have been a recipient, at the clone's place in the user list (before the op itself when the
+// clone precedes its owner there, after it otherwise), under the op's own gate.
+static int q_push(nutsb_ctx *c, u8 kind, i32 target, const char *str, i32 except_user, u8 flags, i32 gate = -1)
+{
+    if (!c || !str) return NUTSB_E_INVAL;
+    const size_t n = strlen(str);
+    std::vector<i32> before, after;
+    if (kind == NUTSB_OP_ROOM && target >= 0 && (size_t)target < c->room_clones.size() && !c->room_clones[(size_t)target].empty()) {
+        int swears = -1;
+        for (i32 cl : c->room_clones[(size_t)target]) {
+            const u32 uf = c->uflags[(size_t)cl];
+            if (uf & NUTSB_UF_LOGIN) continue;                                              // c:1410
+            if ((uf & NUTSB_UF_IGNALL) && !(flags & NUTSB_OF_FORCE_LISTEN)) continue;       // c:1413
+            if ((uf & NUTSB_UF_IGNSHOUT) && (flags & NUTSB_OF_SHOUT)) continue;             // c:1414
+            if (cl == except_user) continue;                                                // c:1415
+            const i32 owner = c->clone_owner[(size_t)cl];
+            const u8 hear = c->clone_hear[(size_t)cl];
+            if (hear == 0 || (c->uflags[(size_t)owner] & NUTSB_UF_IGNALL)) continue;        // c:1417
+            if (hear == 1) {                                                                // c:1421: CLONE_HEAR_SWEARS
+                if (swears < 0) { swears = nutsb_contains_swearing(c, str); if (swears < 0) return swears; }
+                if (!swears) continue;
+            }
+            (cl < owner ? before : after).push_back(owner);
+        }
+    }
+    std::string relay;
+    if (!before.empty() || !after.empty()) {
+        const std::string nm = (size_t)target < c->room_names.size() ? c->room_names[(size_t)target] : "room" + std::to_string(target);
+        relay = "~FT[ " + nm + " ]:~RS " + std::string(str, n);                               // c:1424
+    }
+    const u8 rflags = (u8)(flags & NUTSB_OF_GATE_IF_SET);
+    for (i32 o : before) TRY(q_push_one(c, NUTSB_OP_USER, o, relay.data(), relay.size(), -1, rflags, gate));
+    TRY(q_push_one(c, kind, target, str, n, except_user, flags, gate));
+    for (i32 o : after) TRY(q_push_one(c, NUTSB_OP_USER, o, relay.data(), relay.size(), -1, rflags, gate));
+    return NUTSB_OK;
+}
+
+// Clones (nuts333.h:58-62, 79): owner[u] = index of the clone's owner, -1 for everybody else (a clone is a
+// user flagged NUTSB_UF_CLONE in nutsb_set_users); hear[u] = clone_hear (0 nothing, 1 swears, 2 all).
+// Call after nutsb_set_users.  The relay is made by the queue tier; the batch tier takes ops as they are
+// given (clones simply receive nothing there).
+NUTSB_API int nutsb_set_clones(nutsb_ctx *c, int32_t n_users, const int32_t *owner, const uint8_t *hear)
+{
+    if (!c || (n_users && (!owner || !hear))) return NUTSB_E_INVAL;
+    if (!c->have_users || n_users != c->U) return fail(c, NUTSB_E_STATE, "nutsb_set_clones does not match the population%s");
+    for (i32 u = 0; u < n_users; ++u) {
+        const bool is_clone = (c->uflags[(size_t)u] & NUTSB_UF_CLONE) != 0;
+        if (is_clone != (owner[u] >= 0)) return fail(c, NUTSB_E_INVAL, "owner[] and the NUTSB_UF_CLONE flags disagree%s");
+        if (owner[u] >= n_users || (owner[u] >= 0 && (c->uflags[(size_t)owner[u]] & NUTSB_UF_CLONE)))
+            return fail(c, NUTSB_E_RANGE, "clone owner out of range (or a clone itself)%s");
+        if (hear[u] > 2) return fail(c, NUTSB_E_RANGE, "clone_hear is 0, 1 or 2%s");
+    }
+    c->clone_owner.assign(owner, owner + n_users); c->clone_hear.assign(hear, hear + n_users);
+    c->room_clones.assign((size_t)c->R, std::vector<i32>());
+    for (i32 u = 0; u < n_users; ++u)
+        if (owner[u] >= 0 && c->user_room[(size_t)u] < c->R) c->room_clones[(size_t)c->user_room[(size_t)u]].push_back(u);
+    return NUTSB_OK;
+}
+
+// rm->name of every room (the relay's prefix, review's header); rooms never named are "room<index>"
+NUTSB_API int nutsb_set_room_names(nutsb_ctx *c, int32_t n_rooms, const uint8_t *names, const uint64_t *off)
+{
+    if (!c || n_rooms < 0 || (n_rooms && (!names || !off))) return NUTSB_E_INVAL;
+    c->room_names.clear();
+    for (i32 r = 0; r < n_rooms; ++r) {
+        if (off[r + 1] < off[r] || off[r + 1] - off[r] > 20) return fail(c, NUTSB_E_RANGE, "room name longer than ROOM_NAME_LEN (20)%s");
+        c->room_names.emplace_back((const char *)names + off[r], (size_t)(off[r + 1] - off[r]));
+    }
+    return NUTSB_OK;
+}
+
 NUTSB_API int nutsb_q_write_user(nutsb_ctx *c, int32_t user, const char *str) { return q_push(c, NUTSB_OP_USER, user, str, -1, 0); }
 NUTSB_API int nutsb_q_write_room_except(nutsb_ctx *c, int32_t room, const char *str, int32_t except_user, int force_listen, int shout)
 { return q_push(c, NUTSB_OP_ROOM, room, str, except_user, (u8)((force_listen ? NUTSB_OF_FORCE_LISTEN : 0) | (shout ? NUTSB_OF_SHOUT : 0))); }
@@ -1274,15 +1352,12 @@ NUTSB_API int nutsb_q_speech(nutsb_ctx *c, int verb, int32_t user, const char *i
         text += c->lits[sl.b];
         if (sl.body == 1) text.append(inpstr, blen); else if (sl.body == 2 && blen) text.append(inpstr + 1, blen - 1);
         text += c->lits[sl.c];
-        TRY(q_push(c, sl.kind, sl.target, text.c_str(), sl.except_user, sl.flags));
-        if (sl.gated) {
-            if (gate < 0) {            // the line's body joins the swear batch run at flush
-                gate = (i32)c->q_sw_off.size() - 1;
-                c->q_sw_text.insert(c->q_sw_text.end(), (const u8 *)inpstr, (const u8 *)inpstr + blen);
-                c->q_sw_off.push_back((u64)c->q_sw_text.size());
-            }
-            c->q_gate.back() = gate;
+        if (sl.gated && gate < 0) {    // the line's body joins the swear batch run at flush
+            gate = (i32)c->q_sw_off.size() - 1;
+            c->q_sw_text.insert(c->q_sw_text.end(), (const u8 *)inpstr, (const u8 *)inpstr + blen);
+            c->q_sw_off.push_back((u64)c->q_sw_text.size());
         }
+        TRY(q_push(c, sl.kind, sl.target, text.c_str(), sl.except_user, sl.flags, sl.gated ? gate : -1));
         // say, emote and echo record the line to the room in its review buffer (c:4099, c:4209, c:4304) --
         // once it is known not to be refused
         if (sidx == 2 && room >= 0 && (verb == NUTSB_SPEECH_SAY || verb == NUTSB_SPEECH_EMOTE || verb == NUTSB_SPEECH_ECHO))

@@ -11,6 +11,7 @@
  * c: = /root/reference/nuts333.c, h: = /root/reference/nuts333.h
  */
 #include "nuts_oracle.h"
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -216,6 +217,18 @@ int orc_delivers(uint8_t kind, int32_t target, int32_t except_user, uint8_t of,
     return 0;
 }
 
+/* Clones, c:1416-1426: a CLONE_TYPE user never receives anything itself; what write_room_except would
+ * have sent it is relayed to its owner as "~FT[ <room name> ]:~RS <str>" -- only for calls that name
+ * the clone's own room (rm==NULL reaches the owner anyway), not when clone_hear is NOTHING or the
+ * owner ignores everything, and with clone_hear SWEARS only when the string swears.  Rooms are named
+ * "room<index>" as in the harness.  State set by orc_set_clones (NULL clears it). */
+static const int32_t *orc_clone_owner = NULL; static const uint8_t *orc_clone_hear = NULL;
+static const char *const *orc_clone_words = NULL;
+void orc_set_clones(const int32_t *owner, const uint8_t *hear, const char *const *words)
+{
+    orc_clone_owner = owner; orc_clone_hear = hear; orc_clone_words = words;
+}
+
 static int orc_live(int64_t i, const uint8_t *of, const int32_t *gate, const uint8_t *verdict)
 {
     if (!gate || gate[i] < 0) return 1;
@@ -260,6 +273,7 @@ int orc_write_batch(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
         if (n > maxn) maxn = n;
     }
     uint8_t *ron = malloc(6 * maxn + 8), *roff = malloc(2 * maxn + 8);
+    char *relay = malloc(maxn + 64); uint8_t *rrel = malloc(6 * (maxn + 64) + 8);
     out->n_users = n_users;
     out->off = calloc((size_t)n_users + 1, sizeof(uint64_t));
     out->n_deliveries = calloc((size_t)n_users + 1, sizeof(uint64_t));
@@ -284,6 +298,22 @@ int orc_write_batch(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
                 if (want && !want[u]) continue;
                 if (!orc_delivers(kind[i], target[i], except_user[i], of[i], u, room[u], uf[u], ul[u]))
                     continue;
+                if (kind[i] == ORC_OP_ROOM && (uf[u] & ORC_UF_CLONE)) {                 /* c:1416-1426 */
+                    if (!orc_clone_owner || !relay || !rrel) continue;
+                    const int32_t o = orc_clone_owner[u];
+                    if (o < 0 || o >= n_users) continue;
+                    if (orc_clone_hear[u] == 0 || (uf[o] & ORC_UF_IGNALL)) continue;      /* c:1417 */
+                    if (target[i] != room[u]) continue;                                   /* c:1420: rm!=u->room */
+                    if (orc_clone_hear[u] == 1 && !orc_contains_swearing(s, n, orc_clone_words)) continue;
+                    if (want && !want[o]) continue;
+                    const int pl = sprintf(relay, "~FT[ room%d ]:~RS ", (int)room[u]);    /* c:1424 */
+                    memcpy(relay + pl, s, n);
+                    const size_t rl = orc_render_ex((const uint8_t *)relay, (size_t)pl + n, (uf[o] & ORC_UF_COLOUR) != 0, 0, rrel);
+                    if (pass == 0) { out->off[o + 1] += rl; out->n_deliveries[o] += 1; }
+                    else { memcpy(out->bytes + cur[o], rrel, rl); cur[o] += rl; }
+                    continue;
+                }
+                if (kind[i] == ORC_OP_USER && (uf[u] & ORC_UF_CLONE)) continue;       /* a clone has no socket of its own */
                 int c = (uf[u] & ORC_UF_COLOUR) != 0;
                 if (c && !have_on)  { lon  = orc_render_ex(s, n, 1, of[i], ron);  have_on = 1; }
                 if (!c && !have_off){ loff = orc_render_ex(s, n, 0, of[i], roff); have_off = 1; }
@@ -299,7 +329,7 @@ int orc_write_batch(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
             if (!out->bytes) { free(ron); free(roff); free(cur); free(want); orc_streams_free(out); return -1; }
         }
     }
-    free(ron); free(roff); free(cur); free(want);
+    free(ron); free(roff); free(cur); free(want); free(relay); free(rrel);
     return 0;
 }
 

@@ -75,6 +75,10 @@ int orc_user_banned(const uint8_t *file, size_t n, int file_present,
 int orc_delivers(uint8_t kind, int32_t target, int32_t except_user, uint8_t oflags,
                  int32_t u, int32_t u_room, uint8_t u_flags, uint8_t u_level);
 
+/* Clone relay (c:1416-1426) inside orc_write_batch: owner[u] (-1 unless u is a clone), hear[u] =
+ * clone_hear (0 nothing, 1 swears, 2 all), the swear list for hear == 1.  NULL, NULL, NULL: no clones. */
+void orc_set_clones(const int32_t *owner, const uint8_t *hear, const char *const *words);
+
 typedef struct {
     int64_t   n_users;
     uint64_t *off;     /* n_users+1 stream offsets            */

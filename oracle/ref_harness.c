@@ -122,6 +122,13 @@ int ref_add_users(int n, const int32_t *room, const uint8_t *flags, const uint8_
     return g_nusers;
 }
 
+/* user u becomes a clone of `owner` (c:7022-7036: type, owner, clone_hear; a clone has no socket) */
+void ref_set_clone(int u, int owner, int hear)
+{
+    if (u < 0 || u >= g_nusers || owner < 0 || owner >= g_nusers) return;
+    g_users[u]->type = CLONE_TYPE; g_users[u]->owner = g_users[owner]; g_users[u]->clone_hear = hear;
+}
+
 /* ---- the reference's own entry points, one call each --------------------- */
 
 static void ref_ambient(uint8_t oflags)
