@@ -23,9 +23,10 @@
  *      in host memory, results in library-owned pinned host memory.
  *   3. batch tier, device buffers (*_dev): the same on buffers already in HBM.
  *
- * Semantics are bit-exact with nuts333.c for USER_TYPE recipients; the clone
- * relay (c:1416-1426) and netlink framing (c:1299-1307) are not implemented and
- * users flagged so are rejected with NUTSB_E_UNSUPPORTED.
+ * Semantics are bit-exact with nuts333.c for USER_TYPE recipients and for clones
+ * (the relay of c:1416-1426 is made by the queue tier, nutsb_set_clones); netlink
+ * framing (c:1299-1307) is not implemented and users flagged NUTSB_UF_REMOTE are
+ * rejected with NUTSB_E_UNSUPPORTED.
  *
  * Errors: every entry point returns 0 or a negative NUTSB_E_* code and never
  * aborts the host; on error outputs are left untouched.  One context per host
@@ -49,7 +50,7 @@ enum {
     NUTSB_E_INVAL       = -1,  /* bad argument (NULL, negative count, offsets not monotone) */
     NUTSB_E_NOMEM       = -2,  /* host or device allocation failed                          */
     NUTSB_E_CUDA        = -3,  /* CUDA runtime error, see nutsb_last_error()                */
-    NUTSB_E_UNSUPPORTED = -4,  /* clone / remote recipients              */
+    NUTSB_E_UNSUPPORTED = -4,  /* remote (netlink) recipients              */
     NUTSB_E_RANGE       = -5,  /* string longer than NUTSB_MAX_TEXT, index out of range     */
     NUTSB_E_STATE       = -6   /* call order (e.g. write batch before nutsb_set_users)      */
 };

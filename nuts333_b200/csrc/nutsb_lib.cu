@@ -332,7 +332,7 @@ NUTSB_API const char *nutsb_strerror(int code)
     case NUTSB_E_INVAL: return "invalid argument";
     case NUTSB_E_NOMEM: return "out of memory";
     case NUTSB_E_CUDA: return "CUDA error";
-    case NUTSB_E_UNSUPPORTED: return "unsupported recipient type (clone/remote)";
+    case NUTSB_E_UNSUPPORTED: return "unsupported recipient type (remote)";
     case NUTSB_E_RANGE: return "value out of range";
     case NUTSB_E_STATE: return "call order";
     }

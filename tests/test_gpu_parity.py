@@ -119,7 +119,7 @@ def test_errors_leave_the_host_alive(gpu_ctx):
         gpu_ctx.write_batch(one(kind=np.array([9], np.uint8)))
     assert e.value.code == api.E_INVAL
     with pytest.raises(api.NutsbError) as e:
-        gpu_ctx.set_users(np.zeros(1, np.int32), np.array([api.UF_CLONE], np.uint8), np.ones(1, np.uint8), 1)
+        gpu_ctx.set_users(np.zeros(1, np.int32), np.array([api.UF_REMOTE], np.uint8), np.ones(1, np.uint8), 1)
     assert e.value.code == api.E_UNSUPPORTED
     # and the context still works
     gpu_ctx.set_users(np.zeros(2, np.int32), np.zeros(2, np.uint8), np.ones(2, np.uint8), 1)
