@@ -34,6 +34,7 @@ struct PopView {                 // the population, built by nutsb_set_users
     const u8  *cls_flags;        // [K]
     const u8  *cls_level;        // [K]
     const u8  *codetab;          // [676]
+    u32 has_clones;              // some user is flagged NUTSB_UF_CLONE
 };
 
 #ifndef NUTSB_TILE_OPS
@@ -191,7 +192,7 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
         const i32 tgt = ops.target[i], exc = ops.except_user[i];
         if (kind == NUTSB_OP_USER) {
             if (tgt >= pop.n_users) st |= NUTSB_ST_BAD_INDEX;
-            else if (tgt >= 0) rep = (pop.cls_flags[pop.user_cls[tgt]] & NUTSB_UF_CLONE) ? 0u : 1u;   // a clone has no socket
+            else if (tgt >= 0) rep = (pop.has_clones && (pop.cls_flags[pop.user_cls[tgt]] & NUTSB_UF_CLONE)) ? 0u : 1u;   // a clone has no socket
         } else if (kind == NUTSB_OP_ROOM) {
             if (tgt >= pop.n_rooms || tgt < -1) st |= NUTSB_ST_BAD_INDEX;
             else rep = tgt >= 0 ? 1u : (u32)pop.n_rooms;

@@ -62,7 +62,7 @@ struct nutsb_ctx {
     std::vector<u8> ban_bytes[2];   // the two lists as they stand on disk (nutsb_ban_edit edits them)
 
     // population
-    bool have_users = false, all_simple = true;
+    bool have_users = false, all_simple = true, has_clones = false;
     i32 U = 0, R = 0, Rt = 1;
     std::vector<i32> user_room, user_slot, slot_user, room_slot_off;
     std::vector<u8> uflags;
@@ -592,6 +592,8 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     c->all_simple = true;
     for (i32 u = 0; u < n_users; ++u) if (flags[u] & NUTSB_UF_FILTERED) c->all_simple = false;
     c->uflags.assign(flags, flags + n_users);
+    c->has_clones = false;
+    for (i32 u = 0; u < n_users; ++u) if (flags[u] & NUTSB_UF_CLONE) c->has_clones = true;
     c->clone_owner.clear(); c->clone_hear.clear(); c->room_clones.clear();       // nutsb_set_clones follows the population
     TRY(upload(c, c->d_user_room, c->user_room.data(), (size_t)n_users * 4));
     TRY(upload(c, c->d_user_slot, c->user_slot.data(), (size_t)n_users * 4));
@@ -622,6 +624,7 @@ static PopView pop_view(const nutsb_ctx *c, int with_level)
     p.room_slot_off = c->d_room_slot_off.as<i32>(); p.room_cls_off = cs.d_room_cls_off.as<i32>();
     p.cls_flags = cs.d_cls_flags.as<u8>(); p.cls_level = cs.d_cls_level.as<u8>();
     p.codetab = c->d_codetab.as<u8>();
+    p.has_clones = c->has_clones ? 1u : 0u;
     return p;
 }
 
