@@ -61,6 +61,7 @@ enum {
 #define NUTSB_MAX_BAN_TOKEN 81
 #define NUTSB_REVIEW_LINES 15    /* nuts333.h:37 */
 #define NUTSB_REVIEW_LEN   200   /* nuts333.h:39 */
+#define NUTSB_REVTELL_LINES 5    /* nuts333.h:38 */
 
 /* recipient flags (nuts333.h:67-85 fields actually read on the path) */
 #define NUTSB_UF_COLOUR   0x01u  /* user->colour != 0            */
@@ -247,6 +248,16 @@ int nutsb_q_speech(nutsb_ctx *ctx, int verb, int32_t user, const char *inpstr);
  * first takes the swear verdicts of the lines queued so far.  Buffers are cleared by
  * nutsb_set_users (create_room, c:2799) and nutsb_q_review_clear. */
 int nutsb_q_record(nutsb_ctx *ctx, int32_t room, const char *str);
+/* tell c:4128 / pemote c:4234 after their argument checks (`target` = what get_user found: not the speaker, not
+ * afk / ignoring / offsite -- the talker's state): the muzzle refusal, or the two lines ("~OLYou tell X:~RS ..." /
+ * "~OLX tells you:~RS ...", ask for a trailing '?'; "~OL(To X)~RS ..." / "~OL>>~RS ...") and record_tell c:2074.
+ * wizshout c:6527: muzzle refusal, ban_swearing branch, then the speaker's line and write_level(lev or WIZ, 1,
+ * line, user); lev < 0 = no level word, else level_name[lev] and inpstr without it.  revtell c:7699 replays the
+ * user's five-line buffer through write_user.  Need nutsb_set_user_names. */
+int nutsb_q_tell(nutsb_ctx *ctx, int32_t user, int32_t target, const char *inpstr);
+int nutsb_q_pemote(nutsb_ctx *ctx, int32_t user, int32_t target, const char *inpstr);
+int nutsb_q_wizshout(nutsb_ctx *ctx, int32_t user, int lev, const char *level_name, const char *inpstr);
+int nutsb_q_revtell(nutsb_ctx *ctx, int32_t user);
 int nutsb_q_review(nutsb_ctx *ctx, int32_t user, int32_t room, const char *room_name);
 int nutsb_q_review_clear(nutsb_ctx *ctx, int32_t room);
 

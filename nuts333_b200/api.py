@@ -72,6 +72,7 @@ EXPORTS = [
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
     "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_q_speech",
     "nutsb_q_record", "nutsb_q_review", "nutsb_q_review_clear",
+    "nutsb_q_tell", "nutsb_q_pemote", "nutsb_q_wizshout", "nutsb_q_revtell",
     "nutsb_colour_com_count_batch", "nutsb_colour_com_strip_batch", "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
     "nutsb_q_write_level", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_contains_swearing",
     "nutsb_site_banned", "nutsb_user_banned",
@@ -118,6 +119,10 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_q_record.argtypes = [vp, C.c_int32, C.c_char_p]
     lib.nutsb_q_review.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
     lib.nutsb_q_review_clear.argtypes = [vp, C.c_int32]
+    lib.nutsb_q_tell.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
+    lib.nutsb_q_pemote.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p]
+    lib.nutsb_q_wizshout.argtypes = [vp, C.c_int32, C.c_int, C.c_char_p, C.c_char_p]
+    lib.nutsb_q_revtell.argtypes = [vp, C.c_int32]
     lib.nutsb_colour_com_count_batch.argtypes = [vp, C.c_int64, vp, vp, vp]
     lib.nutsb_colour_com_strip_batch.argtypes = [vp, C.c_int64, vp, vp, C.POINTER(vp), C.POINTER(vp)]
     lib.nutsb_stream_digests.argtypes = [vp, u64p]
@@ -421,6 +426,22 @@ class Talker:
     def clear_revbuff(self, rm):                                     # c:2626
         c = self.ctx
         c._ck(c.lib.nutsb_q_review_clear(c._h, rm))
+
+    def tell(self, user, target, inpstr):                            # c:4128 (target resolved by the caller)
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_tell(c._h, user, target, self._s(inpstr)))
+
+    def pemote(self, user, target, inpstr):                          # c:4234
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_pemote(c._h, user, target, self._s(inpstr)))
+
+    def wizshout(self, user, inpstr, lev=-1, level_name=None):       # c:6527
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_wizshout(c._h, user, lev, None if level_name is None else self._s(level_name), self._s(inpstr)))
+
+    def revtell(self, user):                                         # c:7699
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_revtell(c._h, user))
 
     def say(self, user, inpstr):                                     # c:4062
         self._speech(SPEECH_SAY, user, inpstr)

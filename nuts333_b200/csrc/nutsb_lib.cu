@@ -106,6 +106,8 @@ struct nutsb_ctx {
     // review buffers (nuts333.h:95, REVIEW_LINES x REVIEW_LEN+2 per room), host state of the queue tier
     struct RevBuf { char buf[NUTSB_REVIEW_LINES][NUTSB_REVIEW_LEN + 2]; int line; };
     struct PendingRec { i32 room, gate; std::string text; };
+    struct TellBuf { char buf[NUTSB_REVTELL_LINES][NUTSB_REVIEW_LEN + 2]; int line; };
+    std::vector<TellBuf> revtell;                                // per user (nuts333.h:73)
     std::vector<RevBuf> rev;
     std::vector<PendingRec> q_rec;                               // record() calls whose line may still be refused (swearing)
 };
@@ -575,6 +577,7 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     c->have_users = false; c->have_streams = false;
     c->U = n_users; c->R = n_rooms; c->Rt = n_rooms + 1;
     c->rev.assign((size_t)n_rooms, nutsb_ctx::RevBuf{});        // create_room() clears them, c:2799
+    c->revtell.assign((size_t)n_users, nutsb_ctx::TellBuf{});   // create_user(), c:2747
     c->q_rec.clear();
     c->user_room.resize(n_users);
     for (i32 u = 0; u < n_users; ++u) c->user_room[u] = room[u] < 0 ? n_rooms : room[u];
@@ -1367,6 +1370,87 @@ NUTSB_API int nutsb_q_speech(nutsb_ctx *c, int verb, int32_t user, const char *i
             c->q_rec.push_back({ room, sl.gated ? gate : -1, text });
     }
     return NUTSB_OK;
+}
+
+// tell() c:4128, pemote() c:4234 after their argument checks (the target resolved by get_user, not the
+// speaker, not afk / ignoring / offsite: the talker's state), wizshout() c:6527, revtell() c:7699.
+static std::string user_name(const nutsb_ctx *c, i32 u)
+{ return std::string((const char *)c->names.data() + c->name_off[(size_t)u], (size_t)(c->name_off[(size_t)u + 1] - c->name_off[(size_t)u])); }
+
+static void do_record_tell(nutsb_ctx *c, i32 u, const char *str)     // record_tell(), c:2074
+{
+    nutsb_ctx::TellBuf &rb = c->revtell[(size_t)u];
+    strncpy(rb.buf[rb.line], str, NUTSB_REVIEW_LEN);
+    rb.buf[rb.line][NUTSB_REVIEW_LEN] = '\n';
+    rb.buf[rb.line][NUTSB_REVIEW_LEN + 1] = '\0';
+    rb.line = (rb.line + 1) % NUTSB_REVTELL_LINES;
+}
+
+static int q_private(nutsb_ctx *c, int pemote, i32 user, i32 target, const char *inpstr)
+{
+    if (!c || !inpstr) return NUTSB_E_INVAL;
+    TRY(speech_ready(c));
+    if (user < 0 || user >= c->U || target < 0 || target >= c->U) return fail(c, NUTSB_E_RANGE, "user index out of range%s");
+    if (c->sflags[(size_t)user] & NUTSB_SF_MUZZLED)
+        return nutsb_q_write_user(c, user, pemote ? "You are muzzled, you cannot emote.\n" : "You are muzzled, you cannot tell anyone anything.\n");
+    const size_t n = strlen(inpstr);
+    const std::string name = (c->sflags[(size_t)user] & NUTSB_SF_INVIS) ? c->lits[NUTSB_LIT_INVISNAME] : user_name(c, user);
+    const std::string tname = user_name(c, target), msg(inpstr, n);
+    std::string a, b;
+    if (pemote) {
+        a = "~OL(To " + tname + ")~RS " + name + " " + msg + "\n";                    // c:4281
+        b = "~OL>>~RS " + name + " " + msg + "\n";                                     // c:4283
+    } else {
+        const char *type = (n && inpstr[n - 1] == '?') ? "ask" : "tell";              // c:4175
+        a = std::string("~OLYou ") + type + " " + tname + ":~RS " + msg + "\n";        // c:4177
+        b = "~OL" + name + " " + type + "s you:~RS " + msg + "\n";                     // c:4180
+    }
+    TRY(nutsb_q_write_user(c, user, a.c_str()));
+    TRY(nutsb_q_write_user(c, target, b.c_str()));
+    do_record_tell(c, target, b.c_str());
+    return NUTSB_OK;
+}
+NUTSB_API int nutsb_q_tell(nutsb_ctx *c, int32_t user, int32_t target, const char *inpstr) { return q_private(c, 0, user, target, inpstr); }
+NUTSB_API int nutsb_q_pemote(nutsb_ctx *c, int32_t user, int32_t target, const char *inpstr) { return q_private(c, 1, user, target, inpstr); }
+
+// lev < 0: no level word, everybody from WIZ up (c:6560-6564); else the form "to level <level_name>" (c:6552-6557,
+// inpstr without the level word; lev >= WIZ and <= the speaker's level are the caller's checks)
+NUTSB_API int nutsb_q_wizshout(nutsb_ctx *c, int32_t user, int lev, const char *level_name, const char *inpstr)
+{
+    if (!c || !inpstr || (lev >= 0 && !level_name)) return NUTSB_E_INVAL;
+    TRY(speech_ready(c));
+    if (user < 0 || user >= c->U) return fail(c, NUTSB_E_RANGE, "user index out of range%s");
+    if (c->sflags[(size_t)user] & NUTSB_SF_MUZZLED) return nutsb_q_write_user(c, user, "You are muzzled, you cannot wizshout.\n");
+    const size_t n = strlen(inpstr);
+    i32 gate = -1;
+    if (c->ban_swearing) {                                           // c:6541, asked of the whole line
+        gate = (i32)c->q_sw_off.size() - 1;
+        c->q_sw_text.insert(c->q_sw_text.end(), (const u8 *)inpstr, (const u8 *)inpstr + n);
+        c->q_sw_off.push_back((u64)c->q_sw_text.size());
+        TRY(q_push(c, NUTSB_OP_USER, user, c->lits[6].c_str(), -1, NUTSB_OF_GATE_IF_SET, gate));
+    }
+    const std::string msg(inpstr, n), to = lev >= 0 ? std::string(" to level ") + level_name : std::string();
+    const std::string a = "~OLYou wizshout" + to + ":~RS " + msg + "\n";
+    const std::string b = "~OL" + user_name(c, user) + " wizshouts" + to + ":~RS " + msg + "\n";
+    TRY(q_push(c, NUTSB_OP_USER, user, a.c_str(), -1, 0, gate));
+    return q_push(c, NUTSB_OP_LEVEL, lev >= 0 ? lev : 2 /* WIZ */, b.c_str(), user, NUTSB_OF_ABOVE, gate);
+}
+
+NUTSB_API int nutsb_q_revtell(nutsb_ctx *c, int32_t user)
+{
+    if (!c) return NUTSB_E_INVAL;
+    if (user < 0 || user >= c->U || (size_t)user >= c->revtell.size()) return fail(c, NUTSB_E_RANGE, "user index out of range%s");
+    const nutsb_ctx::TellBuf &rb = c->revtell[(size_t)user];
+    int cnt = 0;
+    for (int i = 0; i < NUTSB_REVTELL_LINES; ++i) {
+        const int line = (rb.line + i) % NUTSB_REVTELL_LINES;
+        if (rb.buf[line][0]) {
+            if (++cnt == 1) TRY(nutsb_q_write_user(c, user, "\n~BB~FG*** Your revtell buffer ***\n\n"));
+            TRY(nutsb_q_write_user(c, user, rb.buf[line]));
+        }
+    }
+    if (!cnt) return nutsb_q_write_user(c, user, "Revtell buffer is empty.\n");
+    return nutsb_q_write_user(c, user, "\n~BB~FG*** End ***\n\n");
 }
 
 static int run_speech(nutsb_ctx *c, i64 n, const u8 *verb, const i32 *speaker, const u8 *bodies, const u64 *body_off, nutsb_streams *out)

@@ -534,6 +534,79 @@ static void orc_review(orc_oplist *L, int32_t user, int32_t room)
     else { const char *m = "\n~BB~FG*** End ***\n\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); }
 }
 
+/* tell c:4128 / pemote c:4234 / wizshout c:6527 / revtell c:7699: targets of tell and pemote as the caller
+ * resolved them (get_user), the target's name, the per-user revtell buffers (5 lines, record_tell c:2074). */
+#define ORC_REVTELL_LINES 5
+typedef struct { char buf[ORC_REVTELL_LINES][ORC_REVIEW_LEN + 2]; int line; } orc_tellbuf;
+static orc_tellbuf *orc_tell = NULL; static int32_t orc_tell_users = 0;
+static const int32_t *orc_speech_target = NULL;          /* per input line */
+static const uint8_t *orc_names = NULL; static const uint64_t *orc_name_off = NULL;
+void orc_set_speech_targets(const int32_t *target) { orc_speech_target = target; }
+
+static void orc_record_tell(int32_t u, const char *str)
+{
+    if (!orc_tell || u < 0 || u >= orc_tell_users) return;
+    orc_tellbuf *rb = &orc_tell[u];
+    strncpy(rb->buf[rb->line], str, ORC_REVIEW_LEN);
+    rb->buf[rb->line][ORC_REVIEW_LEN] = '\n';
+    rb->buf[rb->line][ORC_REVIEW_LEN + 1] = '\0';
+    rb->line = (rb->line + 1) % ORC_REVTELL_LINES;
+}
+
+static void orc_speech_private(orc_oplist *L, int verb, int32_t user, const char *uname, int vis, int muzzled,
+                               int ban_swearing, const char *const *words, const uint8_t *in, size_t n, int64_t line)
+{
+    char text[4400], tname[64]; int len;
+    const char *name = vis ? uname : orc_invisname;
+    const int32_t t = orc_speech_target ? orc_speech_target[line] : -1;
+    tname[0] = 0;
+    if (t >= 0 && orc_names) {
+        size_t nl = (size_t)(orc_name_off[t + 1] - orc_name_off[t]); if (nl > 63) nl = 63;
+        memcpy(tname, orc_names + orc_name_off[t], nl); tname[nl] = 0;
+    }
+    switch (verb) {
+    case 7: {                                                   /* tell, c:4128 */
+        if (muzzled) { const char *m = "You are muzzled, you cannot tell anyone anything.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
+        const char *type = (n && in[n - 1] == '?') ? "ask" : "tell";                  /* c:4175 */
+        len = snprintf(text, sizeof text, "~OLYou %s %s:~RS %.*s\n", type, tname, (int)n, (const char *)in);
+        orc_emit(L, 0, user, -1, 0, text, (size_t)len);
+        len = snprintf(text, sizeof text, "~OL%s %ss you:~RS %.*s\n", name, type, (int)n, (const char *)in);
+        orc_emit(L, 0, t, -1, 0, text, (size_t)len);
+        orc_record_tell(t, text);
+        return; }
+    case 8:                                                     /* pemote, c:4234 */
+        if (muzzled) { const char *m = "You are muzzled, you cannot emote.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
+        len = snprintf(text, sizeof text, "~OL(To %s)~RS %s %.*s\n", tname, name, (int)n, (const char *)in);
+        orc_emit(L, 0, user, -1, 0, text, (size_t)len);
+        len = snprintf(text, sizeof text, "~OL>>~RS %s %.*s\n", name, (int)n, (const char *)in);
+        orc_emit(L, 0, t, -1, 0, text, (size_t)len);
+        orc_record_tell(t, text);
+        return;
+    case 9:                                                     /* wizshout without a level word, c:6527 */
+        if (muzzled) { const char *m = "You are muzzled, you cannot wizshout.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); return; }
+        if (ban_swearing && orc_contains_swearing(in, n, words)) { orc_emit(L, 0, user, -1, 0, orc_noswearing, sizeof orc_noswearing - 1); return; }
+        len = snprintf(text, sizeof text, "~OLYou wizshout:~RS %.*s\n", (int)n, (const char *)in);
+        orc_emit(L, 0, user, -1, 0, text, (size_t)len);
+        len = snprintf(text, sizeof text, "~OL%s wizshouts:~RS %.*s\n", uname, (int)n, (const char *)in);
+        orc_emit(L, 2, 2 /* WIZ */, user, ORC_OF_ABOVE, text, (size_t)len);          /* c:6564 write_level(WIZ,1,text,user) */
+        return;
+    case 10: {                                                  /* revtell, c:7699 */
+        int cnt = 0;
+        if (!orc_tell || user < 0 || user >= orc_tell_users) return;
+        const orc_tellbuf *rb = &orc_tell[user];
+        for (int i = 0; i < ORC_REVTELL_LINES; ++i) {
+            const int ln = (rb->line + i) % ORC_REVTELL_LINES;
+            if (rb->buf[ln][0]) {
+                if (++cnt == 1) { const char *m = "\n~BB~FG*** Your revtell buffer ***\n\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); }
+                orc_emit(L, 0, user, -1, 0, rb->buf[ln], strlen(rb->buf[ln]));
+            }
+        }
+        if (!cnt) { const char *m = "Revtell buffer is empty.\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); }
+        else { const char *m = "\n~BB~FG*** End ***\n\n"; orc_emit(L, 0, user, -1, 0, m, strlen(m)); }
+        return; }
+    }
+}
+
 static void orc_speech_one(orc_oplist *L, int verb, int32_t user, const char *uname, int vis, int muzzled, int32_t room,
                            int ban_swearing, const char *const *words, const uint8_t *in, size_t n)
 {
@@ -614,15 +687,22 @@ int64_t orc_speech_ops(int64_t n, const uint8_t *verb, const int32_t *speaker, c
     for (int32_t u = 0; u < n_users; ++u) if (room[u] > max_room) max_room = room[u];
     orc_rev_rooms = max_room + 1;
     orc_rev = orc_rev_rooms ? (orc_revbuf *)calloc((size_t)orc_rev_rooms, sizeof(orc_revbuf)) : NULL;
+    if (orc_speech_target) for (int64_t m = 0; m < n; ++m) if (orc_speech_target[m] >= n_users) n_users = orc_speech_target[m] + 1;
+    orc_tell_users = n_users;
+    orc_tell = n_users ? (orc_tellbuf *)calloc((size_t)n_users, sizeof(orc_tellbuf)) : NULL;
+    orc_names = names; orc_name_off = name_off;
     for (int64_t m = 0; m < n; ++m) {
         const int32_t u = speaker[m];
         char uname[64]; size_t nl = (size_t)(name_off[u + 1] - name_off[u]);
         if (nl > 63) nl = 63;
         memcpy(uname, names + name_off[u], nl); uname[nl] = 0;
+        if (verb[m] >= 7) orc_speech_private(&L, verb[m], u, uname, !(sflags[u] & 1), (sflags[u] & 2) != 0, ban_swearing, words,
+                                             bodies + body_off[m], (size_t)(body_off[m + 1] - body_off[m]), m);
+        else
         orc_speech_one(&L, verb[m], u, uname, !(sflags[u] & 1), (sflags[u] & 2) != 0, room[u], ban_swearing, words,
                        bodies + body_off[m], (size_t)(body_off[m + 1] - body_off[m]));
-        if (L.n > L.cap) { free(orc_rev); orc_rev = NULL; return -1; }
+        if (L.n > L.cap) { free(orc_rev); orc_rev = NULL; free(orc_tell); orc_tell = NULL; return -1; }
     }
-    free(orc_rev); orc_rev = NULL;
+    free(orc_rev); orc_rev = NULL; free(orc_tell); orc_tell = NULL;
     return L.n;
 }

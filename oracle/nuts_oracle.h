@@ -126,6 +126,9 @@ int orc_ban_edit(const uint8_t *file, size_t n, int present, int is_user, int ad
                  uint8_t *out, size_t *out_n, int *out_present);
 
 /* The callers say/shout/emote/semote/echo/bcast restated (see nuts_oracle.c): input lines -> ops. */
+/* verbs: 0 say 1 shout 2 emote 3 semote 4 echo 5 bcast 6 review (own room) 7 tell 8 pemote 9 wizshout
+ * 10 revtell; for 7 and 8 the target user of input line m is target[m] (orc_set_speech_targets). */
+void orc_set_speech_targets(const int32_t *target);
 int64_t orc_speech_ops(int64_t n, const uint8_t *verb, const int32_t *speaker, const uint8_t *bodies, const uint64_t *body_off,
                        const uint8_t *names, const uint64_t *name_off, const uint8_t *sflags, const int32_t *room,
                        int ban_swearing, const char *const *words,

@@ -254,8 +254,24 @@ void ref_speech(int verb, int u, const char *inpstr)
     case 4: com_num = ECHO;   echo(g_users[u], line); break;
     case 5: com_num = BCAST;  bcast(g_users[u], line); break;
     case 6: com_num = REVIEW; word_count = 1; review(g_users[u]); break;   /* c:5192, no argument: the user's own room */
+    case 9: com_num = WIZSHOUT; { char *sp; strncpy(word[1], line, WORD_LEN); word[1][WORD_LEN] = 0;
+                                  if ((sp = strchr(word[1], ' '))) *sp = 0; }   /* word[1] = first word (exec_com's split) */
+            wizshout(g_users[u], line); break;
+    case 10: com_num = REVTELL; revtell(g_users[u]); break;
     }
     force_listen = 0;
+}
+
+/* tell() c:4128 / pemote() c:4234 to user t: the input line is "<name> <message>", word[1] the name */
+void ref_speech_to(int verb, int u, int t, const char *msg)
+{
+    static char line[ARR_SIZE * 2];
+    if (u < 0 || u >= g_nusers || t < 0 || t >= g_nusers) return;
+    snprintf(line, sizeof line, "%s %s", g_users[t]->name, msg);
+    strcpy(word[1], g_users[t]->name);
+    word_count = 3; force_listen = 0;
+    if (verb == 7) { com_num = TELL; tell(g_users[u], line); }
+    else { com_num = PEMOTE; pemote(g_users[u], line); }
 }
 
 /* more(), c:2205: the reference's own pager on a file on disk, socket = the user's index */

@@ -197,10 +197,12 @@ class Port:
         r = self.lib.orc_ban_edit(data, len(data), int(file is not None), int(is_user), int(add), token, out, C.byref(on), C.byref(op))
         return r, (out.raw[:on.value] if op.value else None)
 
-    def speech_ops(self, verb, speaker, bodies, body_off, names, name_off, sflags, room, ban_swearing, words):
-        """input lines -> ops dict (the callers restated)"""
+    def speech_ops(self, verb, speaker, bodies, body_off, names, name_off, sflags, room, ban_swearing, words, target=None):
+        """input lines -> ops dict (the callers restated); target[m] = the user tell / pemote line m is for"""
         n = len(verb)
-        n_rev = int((np.asarray(verb) == 6).sum())              # a review replays up to 15 lines + header + footer
+        tgt = None if target is None else np.ascontiguousarray(target, np.int32)
+        self.lib.orc_set_speech_targets(None if tgt is None else tgt.ctypes.data_as(C.c_void_p))
+        n_rev = int(((np.asarray(verb) == 6) | (np.asarray(verb) == 10)).sum())   # a review replays up to 15 lines + header + footer
         cap = 3 * n + 17 * n_rev + 1
         tcap = int(body_off[-1]) * 2 + 256 * n + 17 * 256 * n_rev + 64
         text = np.zeros(tcap, np.uint8); off = np.zeros(cap + 1, np.uint64); kind = np.zeros(cap, np.uint8)
@@ -210,6 +212,7 @@ class Port:
                                     _ptr(np.ascontiguousarray(sflags, np.uint8), u8p), _ptr(np.ascontiguousarray(room, np.int32), i32p),
                                     int(ban_swearing), self._words(words), _ptr(text, u8p), tcap, _ptr(off, u64p), _ptr(kind, u8p),
                                     _ptr(target, i32p), _ptr(exc, i32p), _ptr(flags, u8p), cap)
+        self.lib.orc_set_speech_targets(None)
         assert q >= 0
         return dict(text=text[:int(off[q])].copy(), off=off[:q + 1].copy(), kind=kind[:q].copy(), target=target[:q].copy(),
                     except_user=exc[:q].copy(), flags=flags[:q].copy())
@@ -255,6 +258,7 @@ class Ref:
         L.ref_total_write_bytes.restype = C.c_uint64
         L.ref_set_user_speech.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_int]
         L.ref_speech.argtypes = [C.c_int, C.c_int, C.c_char_p]
+        L.ref_speech_to.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p]
         L.ref_more.argtypes = [C.c_int, C.c_int, C.c_char_p]
         L.ref_get_filepos.restype = C.c_long
         L.ref_ban_command.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
