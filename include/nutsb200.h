@@ -23,10 +23,10 @@
  *      in host memory, results in library-owned pinned host memory.
  *   3. batch tier, device buffers (*_dev): the same on buffers already in HBM.
  *
- * Semantics are bit-exact with nuts333.c for USER_TYPE recipients and for clones
- * (the relay of c:1416-1426 is made by the queue tier, nutsb_set_clones); netlink
- * framing (c:1299-1307) is not implemented and users flagged NUTSB_UF_REMOTE are
- * rejected with NUTSB_E_UNSUPPORTED.
+ * Semantics are bit-exact with nuts333.c for USER_TYPE recipients, for clones (the
+ * relay of c:1416-1426) and for remote users (the MSG/EMSG framing of c:1299-1307):
+ * both are made by the queue tier (nutsb_set_clones, nutsb_set_remotes); the batch
+ * tiers take ops as given, clones and remote users receive nothing there.
  *
  * Errors: every entry point returns 0 or a negative NUTSB_E_* code and never
  * aborts the host; on error outputs are left untouched.  One context per host
@@ -69,7 +69,7 @@ enum {
 #define NUTSB_UF_IGNALL   0x04u  /* user->ignall                 */
 #define NUTSB_UF_IGNSHOUT 0x08u  /* user->ignshout               */
 #define NUTSB_UF_CLONE    0x10u  /* type==CLONE_TYPE: receives nothing itself; nutsb_set_clones */
-#define NUTSB_UF_REMOTE   0x20u  /* type==REMOTE_TYPE (rejected) */
+#define NUTSB_UF_REMOTE   0x20u  /* type==REMOTE_TYPE: reached through its netlink; nutsb_set_remotes */
 
 /* op kinds: one op == one call of the reference's write surface */
 #define NUTSB_OP_USER  0  /* write_user(target, str)                                   */
@@ -86,6 +86,8 @@ enum {
 #define NUTSB_OF_PAGER        0x10u  /* render as the pager more() renders a file line
                                         (nuts333.c:2254-2300): the same byte machine, but
                                         no terminal reset after the string (c:1365 absent) */
+#define NUTSB_OF_RAW          0x40u  /* the bytes as they are, no byte machine: what write_user hands to
+                                        write_sock for a remote user (nuts333.c:1303-1305)             */
 #define NUTSB_OF_PLAIN        0x20u  /* the recipient's colour setting is ignored and taken
                                         as off: more(NULL,sock,file) at login (c:2259,2279) */
 
@@ -157,6 +159,14 @@ int  nutsb_set_stream(nutsb_ctx *ctx, void *cuda_stream);
  * swear.  The batch tier takes ops as given: clones receive nothing there.  Room names: rm->name, default
  * "room<index>". */
 int nutsb_set_clones(nutsb_ctx *ctx, int32_t n_users, const int32_t *owner, const uint8_t *hear);
+/* Remote users (nuts333.c:1299-1307): link[u] = index of the pseudo-user whose stream stands for the netlink
+ * socket remote user u is reached through (a user in no room, flagged neither clone nor remote; several
+ * remote users may share one), -1 for everybody else; old_peer[u] != 0: the peer is older than 3.2 and gets
+ * its colour commands stripped (colour_com_strip, c:2588).  Call after nutsb_set_users and
+ * nutsb_set_user_names.  The queue tier then frames what write_user would hand to write_sock:
+ * "MSG <name>\n<str>[\n]EMSG\n", unrendered (NUTSB_OF_RAW), into the link's stream, for write_user to a remote
+ * user and for every remote recipient of a room / level op, in user-list order. */
+int nutsb_set_remotes(nutsb_ctx *ctx, int32_t n_users, const int32_t *link, const uint8_t *old_peer);
 int nutsb_set_room_names(nutsb_ctx *ctx, int32_t n_rooms, const uint8_t *names, const uint64_t *off);
 
 /* ---- tables ------------------------------------------------------------- */

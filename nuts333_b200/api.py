@@ -20,7 +20,7 @@ from pathlib import Path
 import numpy as np
 
 OP_USER, OP_ROOM, OP_LEVEL = 0, 1, 2
-OF_FORCE_LISTEN, OF_SHOUT, OF_ABOVE, OF_GATE_IF_SET, OF_PAGER, OF_PLAIN = 1, 2, 4, 8, 16, 32
+OF_FORCE_LISTEN, OF_SHOUT, OF_ABOVE, OF_GATE_IF_SET, OF_PAGER, OF_PLAIN, OF_RAW = 1, 2, 4, 8, 16, 32, 64
 UF_COLOUR, UF_LOGIN, UF_IGNALL, UF_IGNSHOUT, UF_CLONE, UF_REMOTE = 1, 2, 4, 8, 16, 32
 MAX_TEXT = 2000
 
@@ -67,7 +67,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "nutsb_version", "nutsb_strerror", "nutsb_last_error", "nutsb_create", "nutsb_destroy",
     "nutsb_set_profiling", "nutsb_get_timing", "nutsb_set_overlap", "nutsb_set_stream", "nutsb_set_swear_words",
-    "nutsb_set_ban_files", "nutsb_ban_edit", "nutsb_get_ban_file", "nutsb_set_users", "nutsb_set_clones", "nutsb_set_room_names", "nutsb_write_batch", "nutsb_write_batch_dev",
+    "nutsb_set_ban_files", "nutsb_ban_edit", "nutsb_get_ban_file", "nutsb_set_users", "nutsb_set_clones", "nutsb_set_remotes", "nutsb_set_room_names", "nutsb_write_batch", "nutsb_write_batch_dev",
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
     "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_q_speech",
@@ -114,6 +114,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_q_speech.argtypes = [vp, C.c_int, C.c_int32, C.c_char_p]
     lib.nutsb_set_clones.argtypes = [vp, C.c_int32, vp, vp]
     lib.nutsb_set_room_names.argtypes = [vp, C.c_int32, vp, vp]
+    lib.nutsb_set_remotes.argtypes = [vp, C.c_int32, vp, vp]
     lib.nutsb_ban_edit.argtypes = [vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int)]
     lib.nutsb_get_ban_file.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
     lib.nutsb_q_record.argtypes = [vp, C.c_int32, C.c_char_p]
@@ -254,6 +255,10 @@ class Context:
     def set_clones(self, owner, hear):
         owner, hear = _np(owner, np.int32), _np(hear, np.uint8)
         self._ck(self.lib.nutsb_set_clones(self._h, len(owner), _addr(owner), _addr(hear)))
+
+    def set_remotes(self, link, old_peer):
+        link, old_peer = _np(link, np.int32), _np(old_peer, np.uint8)
+        self._ck(self.lib.nutsb_set_remotes(self._h, len(link), _addr(link), _addr(old_peer)))
 
     def set_room_names(self, names):
         data = np.frombuffer(b"".join(names) or b"\0", np.uint8)

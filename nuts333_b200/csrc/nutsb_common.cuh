@@ -69,7 +69,7 @@ template <int N> __device__ __forceinline__ void nutsb_cp_async_wait() { asm vol
 __device__ __forceinline__ void nutsb_add64(u64 *p, u64 v) { atomicAdd((unsigned long long *)p, (unsigned long long)v); }
 
 // recipients that do not simply take every op of their room: they go through nutsb_class_delivers
-#define NUTSB_UF_FILTERED (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT | NUTSB_UF_CLONE)
+#define NUTSB_UF_FILTERED (NUTSB_UF_LOGIN | NUTSB_UF_IGNALL | NUTSB_UF_IGNSHOUT | NUTSB_UF_CLONE | NUTSB_UF_REMOTE)
 
 // Status bits raised by kernels (ctx->d_status), decoded on the host.
 #define NUTSB_ST_TEXT_TOO_LONG 0x01u
@@ -99,7 +99,7 @@ __device__ __forceinline__ u32 nutsb_code_len(int k) { return k < 5 ? 4u : 5u; }
 //   ROOM : nuts333.c:1410-1415      LEVEL: nuts333.c:1379-1383
 __device__ __forceinline__ bool nutsb_class_delivers(u32 cflags, u32 clevel, u32 kind, u32 oflags, i32 target)
 {
-    if (cflags & NUTSB_UF_LOGIN) return false;
+    if (cflags & (NUTSB_UF_LOGIN | NUTSB_UF_REMOTE)) return false;   // remote: framed for its netlink instead (nutsb_q_*)
     if (kind == NUTSB_OP_ROOM) {
         if (cflags & NUTSB_UF_CLONE) return false;              // c:1416: relayed to the owner instead (nutsb_q_*)
         if ((cflags & NUTSB_UF_IGNALL) && !(oflags & NUTSB_OF_FORCE_LISTEN)) return false;

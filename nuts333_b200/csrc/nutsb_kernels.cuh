@@ -183,7 +183,8 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
     else if (have) {
         loff = n - drops - 3 * (m4 + m5) + nl;
         const u32 of = ops.flags[i];
-        lon = (of & NUTSB_OF_PLAIN) ? loff                                    // colour setting ignored
+        if (of & NUTSB_OF_RAW) loff = n;                                       // no byte machine: c:1303
+        lon = (of & (NUTSB_OF_PLAIN | NUTSB_OF_RAW)) ? loff                                    // colour setting ignored
             : loff + 4 * nl + 4 * m4 + 5 * m5 + ((of & NUTSB_OF_PAGER) ? 0u : 4u);   // pager lines carry no final reset
         len_off[i] = loff; len_on[i] = lon;
 
@@ -192,7 +193,7 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
         const i32 tgt = ops.target[i], exc = ops.except_user[i];
         if (kind == NUTSB_OP_USER) {
             if (tgt >= pop.n_users) st |= NUTSB_ST_BAD_INDEX;
-            else if (tgt >= 0) rep = (pop.has_clones && (pop.cls_flags[pop.user_cls[tgt]] & NUTSB_UF_CLONE)) ? 0u : 1u;   // a clone has no socket
+            else if (tgt >= 0) rep = (pop.has_clones && (pop.cls_flags[pop.user_cls[tgt]] & (NUTSB_UF_CLONE | NUTSB_UF_REMOTE))) ? 0u : 1u;   // no socket of its own
         } else if (kind == NUTSB_OP_ROOM) {
             if (tgt >= pop.n_rooms || tgt < -1) st |= NUTSB_ST_BAD_INDEX;
             else rep = tgt >= 0 ? 1u : (u32)pop.n_rooms;
@@ -799,11 +800,13 @@ __device__ __forceinline__ void nutsb_flat_render(u32 cnt, u32 meta, u64 gw, u32
         if (lane == 31) nx = (act && wi + 1 < nwq) ? __ldg(gwq + wi + 1) & (left < 8 ? (1u << (8 * (left - 4))) - 1u : 0xffffffffu) : 0u;
         if (wi == 0) pv = 0;
         if (wi + 1 >= nwq) nx = 0;
-        const bool colour = (flq & NUTSB_FL_COLOUR) && !(flq & NUTSB_OF_PLAIN);     // more(NULL,...): c:2259
+        const bool colour = (flq & NUTSB_FL_COLOUR) && !(flq & (NUTSB_OF_PLAIN | NUTSB_OF_RAW));   // more(NULL,...): c:2259
         const bool tail = act && wi == nwq - 1 && colour && !(flq & NUTSB_OF_PAGER);   // c:1365; the pager has no such reset
 
         // -- special bytes of the word: 0x80 per byte
-        const u32 tl = nutsb_zero_bytes(x ^ 0x7e7e7e7eu), sl = nutsb_zero_bytes(x ^ 0x2f2f2f2fu), nl = nutsb_zero_bytes(x ^ 0x0a0a0a0au);
+        const u32 cook = (flq & NUTSB_OF_RAW) ? 0u : 0xffffffffu;               // raw strings have no special bytes
+        const u32 tl = nutsb_zero_bytes(x ^ 0x7e7e7e7eu) & cook, sl = nutsb_zero_bytes(x ^ 0x2f2f2f2fu) & cook,
+                  nl = nutsb_zero_bytes(x ^ 0x0a0a0a0au) & cook;
         const u32 t_next = (tl >> 8) | ((nx & 0xffu) == '~' ? 0x80000000u : 0u);      // byte k+1 is '~'
         const u32 s_prev = (sl << 8) | ((pv >> 24) == '/' ? 0x80u : 0u);             // byte k-1 is '/'
         const u32 slash_drop = sl & t_next;                                          // c:1330

@@ -65,7 +65,9 @@ struct nutsb_ctx {
     bool have_users = false, all_simple = true, has_clones = false;
     i32 U = 0, R = 0, Rt = 1;
     std::vector<i32> user_room, user_slot, slot_user, room_slot_off;
-    std::vector<u8> uflags;
+    std::vector<u8> uflags, ulevel;
+    std::vector<i32> remote_link; std::vector<u8> remote_old;   // per user; link -1 = not a remote user
+    std::vector<i32> remotes;                                   // the remote users, in user-list order
     std::vector<i32> clone_owner; std::vector<u8> clone_hear;   // per user; owner -1 = not a clone
     std::vector<std::vector<i32>> room_clones;                  // clones of every room, in user-list order
     std::vector<std::string> room_names;                        // default "room<index>"
@@ -549,9 +551,9 @@ static int build_classes(nutsb_ctx *c, ClassSet &cs, bool with_level, const std:
     std::vector<i32> per_room(Rt, 0);
     for (i32 s = 0; s < U; ++s) {
         const i32 u = order[s], r = c->user_room[u];
-        const u32 key = (u32)(flags[u] & 0x1f) | (with_level ? (u32)level[u] << 8 : 0u);
+        const u32 key = (u32)(flags[u] & 0x3f) | (with_level ? (u32)level[u] << 8 : 0u);
         if (r != prev_room || key != prev_key) {
-            ++k; cs.cls_flags.push_back((u8)(flags[u] & 0x1f)); cs.cls_level.push_back(with_level ? level[u] : 0);
+            ++k; cs.cls_flags.push_back((u8)(flags[u] & 0x3f)); cs.cls_level.push_back(with_level ? level[u] : 0);
             per_room[r]++; prev_room = r; prev_key = key;
         }
         cs.user_cls[u] = k;
@@ -571,7 +573,6 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     if (!c || n_users < 0 || n_rooms < 0 || (n_users && (!room || !flags || !level))) return fail(c, NUTSB_E_INVAL, "nutsb_set_users: bad argument%s");
     CK(cudaSetDevice(c->device));
     for (i32 u = 0; u < n_users; ++u) {
-        if (flags[u] & NUTSB_UF_REMOTE) return fail(c, NUTSB_E_UNSUPPORTED, "remote (netlink) recipients are not implemented%s");
         if (room[u] >= n_rooms || room[u] < -1) return fail(c, NUTSB_E_RANGE, "user room out of range%s");
     }
     c->have_users = false; c->have_streams = false;
@@ -585,7 +586,7 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     std::vector<i32> order(n_users); std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](i32 a, i32 b) {
         if (c->user_room[a] != c->user_room[b]) return c->user_room[a] < c->user_room[b];
-        const u32 ka = (u32)(flags[a] & 0x1f), kb = (u32)(flags[b] & 0x1f);
+        const u32 ka = (u32)(flags[a] & 0x3f), kb = (u32)(flags[b] & 0x3f);
         if (ka != kb) return ka < kb;
         return level[a] < level[b];
     });
@@ -596,7 +597,9 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     for (i32 u = 0; u < n_users; ++u) if (flags[u] & NUTSB_UF_FILTERED) c->all_simple = false;
     c->uflags.assign(flags, flags + n_users);
     c->has_clones = false;
-    for (i32 u = 0; u < n_users; ++u) if (flags[u] & NUTSB_UF_CLONE) c->has_clones = true;
+    for (i32 u = 0; u < n_users; ++u) if (flags[u] & (NUTSB_UF_CLONE | NUTSB_UF_REMOTE)) c->has_clones = true;
+    c->ulevel.assign(level, level + n_users);
+    c->remote_link.clear(); c->remote_old.clear(); c->remotes.clear();
     c->clone_owner.clear(); c->clone_hear.clear(); c->room_clones.clear();       // nutsb_set_clones follows the population
     TRY(upload(c, c->d_user_room, c->user_room.data(), (size_t)n_users * 4));
     TRY(upload(c, c->d_user_slot, c->user_slot.data(), (size_t)n_users * 4));
@@ -604,7 +607,7 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     TRY(upload(c, c->d_room_slot_off, c->room_slot_off.data(), (size_t)(c->Rt + 1) * 4));
     {
         std::vector<u8> cf(n_users), lv(n_users);
-        for (i32 s = 0; s < n_users; ++s) { cf[s] = (u8)(flags[order[s]] & 0x1f); lv[s] = level[order[s]]; }
+        for (i32 s = 0; s < n_users; ++s) { cf[s] = (u8)(flags[order[s]] & 0x3f); lv[s] = level[order[s]]; }
         TRY(upload(c, c->d_slot_cf, cf.data(), (size_t)n_users));
         TRY(upload(c, c->d_slot_lv, lv.data(), (size_t)n_users));
         CK(cudaStreamSynchronize(c->stream));          // cf/lv go out of scope
@@ -1096,15 +1099,49 @@ static int q_push_one(nutsb_ctx *c, u8 kind, i32 target, const char *str, size_t
     return NUTSB_OK;
 }
 
-// One call of the reference's write surface.  A room op that names a room with clones in it also makes
-// the relays of nuts333.c:1416-1426: write_user(clone->owner, "~FT[ <room> ]:~RS <str>") for every clone
-// that would have been a recipient, at the clone's place in the user list (before the op itself when the
-// clone precedes its owner there, after it otherwise), under the op's own gate.
+// colour_com_strip(), nuts333.c:2588-2610, on the host (what a peer older than 3.2 is sent, c:1300)
+static std::string host_colour_com_strip(const char *s, size_t n)
+{
+    static u8 tab[NUTSB_CODETAB_BYTES]; static bool have = false;
+    if (!have) { build_codetab(tab); have = true; }
+    std::string o; o.reserve(n);
+    for (size_t p = 0; p < n; ) {
+        if (s[p] == '~' && p + 2 < n) {
+            const u32 a = (u32)(u8)s[p + 1] - 'A', b = (u32)(u8)s[p + 2] - 'A';
+            if (a < 26u && b < 26u && tab[a * 26u + b]) { p += 3; continue; }
+        }
+        o.push_back(s[p++]);
+    }
+    return o;
+}
+
+// write_user(u, str) as the queue sees it: a remote user's string is framed for its netlink
+// (nuts333.c:1299-1306: "MSG <name>\n<str>[\n]EMSG\n", handed to write_sock unrendered), everybody else's is queued as it is.
+static int q_push_user(nutsb_ctx *c, i32 u, const char *str, size_t n, u8 flags, i32 gate)
+{
+    if (u >= 0 && (size_t)u < c->remote_link.size() && c->remote_link[(size_t)u] >= 0) {
+        std::string f = "MSG " + std::string((const char *)c->names.data() + c->name_off[(size_t)u], (size_t)(c->name_off[(size_t)u + 1] - c->name_off[(size_t)u])) + "\n";
+        f += c->remote_old[(size_t)u] ? host_colour_com_strip(str, n) : std::string(str, n);
+        if (f.back() != '\n' || f.size() == 5 + (size_t)(c->name_off[(size_t)u + 1] - c->name_off[(size_t)u])) f += "\n";
+        f += "EMSG\n";
+        return q_push_one(c, NUTSB_OP_USER, c->remote_link[(size_t)u], f.data(), f.size(), -1, (u8)((flags & NUTSB_OF_GATE_IF_SET) | NUTSB_OF_RAW), gate);
+    }
+    return q_push_one(c, NUTSB_OP_USER, u, str, n, -1, flags, gate);
+}
+
+// One call of the reference's write surface.  Besides the op itself:
+//  * a room op that names a room with clones in it makes the relays of nuts333.c:1416-1426:
+//    write_user(clone->owner, "~FT[ <room> ]:~RS <str>") for every clone that would have been a recipient;
+//  * every remote user that would have been a recipient of a room / level op gets its frame (q_push_user).
+// All of them at their place in the user list: before the op itself when a clone precedes its (local) owner
+// there, after it otherwise, in list order -- and under the op's own gate.
 static int q_push(nutsb_ctx *c, u8 kind, i32 target, const char *str, i32 except_user, u8 flags, i32 gate = -1)
 {
     if (!c || !str) return NUTSB_E_INVAL;
     const size_t n = strlen(str);
-    std::vector<i32> before, after;
+    if (kind == NUTSB_OP_USER) return q_push_user(c, target, str, n, flags, gate);
+    struct Extra { i32 pos, user; bool relay; };
+    std::vector<Extra> before, after;
     if (kind == NUTSB_OP_ROOM && target >= 0 && (size_t)target < c->room_clones.size() && !c->room_clones[(size_t)target].empty()) {
         int swears = -1;
         for (i32 cl : c->room_clones[(size_t)target]) {
@@ -1120,18 +1157,38 @@ static int q_push(nutsb_ctx *c, u8 kind, i32 target, const char *str, i32 except
                 if (swears < 0) { swears = nutsb_contains_swearing(c, str); if (swears < 0) return swears; }
                 if (!swears) continue;
             }
-            (cl < owner ? before : after).push_back(owner);
+            const bool local = !(c->uflags[(size_t)owner] & NUTSB_UF_REMOTE);
+            (cl < owner && local ? before : after).push_back({ cl, owner, true });
         }
     }
+    for (i32 u : c->remotes) {
+        const u32 uf = c->uflags[(size_t)u];
+        if (uf & NUTSB_UF_LOGIN) continue;
+        if (kind == NUTSB_OP_ROOM) {                                                        // c:1410-1415
+            const i32 ru = c->user_room[(size_t)u];
+            if (ru >= c->R || (target >= 0 && ru != target)) continue;
+            if ((uf & NUTSB_UF_IGNALL) && !(flags & NUTSB_OF_FORCE_LISTEN)) continue;
+            if ((uf & NUTSB_UF_IGNSHOUT) && (flags & NUTSB_OF_SHOUT)) continue;
+            if (u == except_user) continue;
+        } else {                                                                            // c:1379-1383
+            if (u == except_user) continue;
+            if ((flags & NUTSB_OF_ABOVE) ? (i32)c->ulevel[(size_t)u] < target : (i32)c->ulevel[(size_t)u] > target) continue;
+        }
+        after.push_back({ u, u, false });
+    }
+    std::stable_sort(after.begin(), after.end(), [](const Extra &a, const Extra &b) { return a.pos < b.pos; });
     std::string relay;
-    if (!before.empty() || !after.empty()) {
+    if (kind == NUTSB_OP_ROOM && target >= 0 && (!before.empty() || !after.empty())) {
         const std::string nm = (size_t)target < c->room_names.size() ? c->room_names[(size_t)target] : "room" + std::to_string(target);
         relay = "~FT[ " + nm + " ]:~RS " + std::string(str, n);                               // c:1424
     }
     const u8 rflags = (u8)(flags & NUTSB_OF_GATE_IF_SET);
-    for (i32 o : before) TRY(q_push_one(c, NUTSB_OP_USER, o, relay.data(), relay.size(), -1, rflags, gate));
+    for (const Extra &e : before) TRY(q_push_user(c, e.user, relay.data(), relay.size(), rflags, gate));
     TRY(q_push_one(c, kind, target, str, n, except_user, flags, gate));
-    for (i32 o : after) TRY(q_push_one(c, NUTSB_OP_USER, o, relay.data(), relay.size(), -1, rflags, gate));
+    for (const Extra &e : after) {
+        if (e.relay) TRY(q_push_user(c, e.user, relay.data(), relay.size(), rflags, gate));
+        else TRY(q_push_user(c, e.user, str, n, rflags, gate));
+    }
     return NUTSB_OK;
 }
 
@@ -1154,6 +1211,25 @@ NUTSB_API int nutsb_set_clones(nutsb_ctx *c, int32_t n_users, const int32_t *own
     c->room_clones.assign((size_t)c->R, std::vector<i32>());
     for (i32 u = 0; u < n_users; ++u)
         if (owner[u] >= 0 && c->user_room[(size_t)u] < c->R) c->room_clones[(size_t)c->user_room[(size_t)u]].push_back(u);
+    return NUTSB_OK;
+}
+
+// Remote users: see include/nutsb200.h
+NUTSB_API int nutsb_set_remotes(nutsb_ctx *c, int32_t n_users, const int32_t *link, const uint8_t *old_peer)
+{
+    if (!c || (n_users && (!link || !old_peer))) return NUTSB_E_INVAL;
+    if (!c->have_users || n_users != c->U) return fail(c, NUTSB_E_STATE, "nutsb_set_remotes does not match the population%s");
+    if (!c->have_names || (i32)c->sflags.size() != c->U) return fail(c, NUTSB_E_STATE, "nutsb_set_remotes needs nutsb_set_user_names%s");
+    for (i32 u = 0; u < n_users; ++u) {
+        const bool is_remote = (c->uflags[(size_t)u] & NUTSB_UF_REMOTE) != 0;
+        if (is_remote != (link[u] >= 0)) return fail(c, NUTSB_E_INVAL, "link[] and the NUTSB_UF_REMOTE flags disagree%s");
+        if (link[u] >= n_users) return fail(c, NUTSB_E_RANGE, "link pseudo-user out of range%s");
+        if (link[u] >= 0 && ((c->uflags[(size_t)link[u]] & (NUTSB_UF_CLONE | NUTSB_UF_REMOTE)) || c->user_room[(size_t)link[u]] < c->R))
+            return fail(c, NUTSB_E_INVAL, "a link pseudo-user is a plain user in no room%s");
+    }
+    c->remote_link.assign(link, link + n_users); c->remote_old.assign(old_peer, old_peer + n_users);
+    c->remotes.clear();
+    for (i32 u = 0; u < n_users; ++u) if (link[u] >= 0) c->remotes.push_back(u);
     return NUTSB_OK;
 }
 

@@ -59,6 +59,7 @@ size_t orc_render(const uint8_t *s, size_t n, int colour, uint8_t *out)
 size_t orc_render_ex(const uint8_t *s, size_t n, int colour, unsigned oflags, uint8_t *out)
 {
     size_t i = 0, o = 0;
+    if (oflags & ORC_OF_RAW) { memcpy(out, s, n); return n; }      /* write_sock, c:1281: no byte machine */
     if (oflags & ORC_OF_PLAIN) colour = 0;
     while (i < n) {
         uint8_t c = s[i];
@@ -222,6 +223,29 @@ int orc_delivers(uint8_t kind, int32_t target, int32_t except_user, uint8_t of,
  * the clone's own room (rm==NULL reaches the owner anyway), not when clone_hear is NOTHING or the
  * owner ignores everything, and with clone_hear SWEARS only when the string swears.  Rooms are named
  * "room<index>" as in the harness.  State set by orc_set_clones (NULL clears it). */
+static const int32_t *orc_remote_link = NULL; static const uint8_t *orc_remote_old = NULL;
+static const uint8_t *orc_remote_names = NULL; static const uint64_t *orc_remote_name_off = NULL;
+void orc_set_remotes(const int32_t *link, const uint8_t *old, const uint8_t *names, const uint64_t *name_off)
+{
+    orc_remote_link = link; orc_remote_old = old; orc_remote_names = names; orc_remote_name_off = name_off;
+}
+/* c:1299-1306: "MSG <name>\n<str>[\n]EMSG\n", str stripped of colour commands for a peer < 3.2 */
+static size_t orc_remote_frame(int32_t u, const uint8_t *s, size_t n, uint8_t *out)
+{
+    size_t o = 0;
+    const size_t nl = (size_t)(orc_remote_name_off[u + 1] - orc_remote_name_off[u]);
+    memcpy(out, "MSG ", 4); o = 4;
+    memcpy(out + o, orc_remote_names + orc_remote_name_off[u], nl); o += nl;
+    out[o++] = '\n';
+    size_t bl;
+    if (orc_remote_old[u]) bl = orc_colour_com_strip(s, n, out + o);
+    else { memcpy(out + o, s, n); bl = n; }
+    o += bl;
+    if (!bl || out[o - 1] != '\n') out[o++] = '\n';
+    memcpy(out + o, "EMSG\n", 5); o += 5;
+    return o;
+}
+
 static const int32_t *orc_clone_owner = NULL; static const uint8_t *orc_clone_hear = NULL;
 static const char *const *orc_clone_words = NULL;
 void orc_set_clones(const int32_t *owner, const uint8_t *hear, const char *const *words)
@@ -308,12 +332,27 @@ int orc_write_batch(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
                     if (want && !want[o]) continue;
                     const int pl = sprintf(relay, "~FT[ room%d ]:~RS ", (int)room[u]);    /* c:1424 */
                     memcpy(relay + pl, s, n);
-                    const size_t rl = orc_render_ex((const uint8_t *)relay, (size_t)pl + n, (uf[o] & ORC_UF_COLOUR) != 0, 0, rrel);
-                    if (pass == 0) { out->off[o + 1] += rl; out->n_deliveries[o] += 1; }
-                    else { memcpy(out->bytes + cur[o], rrel, rl); cur[o] += rl; }
+                    size_t rl; int32_t dst = o;
+                    if (uf[o] & ORC_UF_REMOTE) {                                          /* write_user(owner): c:1299 */
+                        if (!orc_remote_link || orc_remote_link[o] < 0) continue;
+                        dst = orc_remote_link[o];
+                        if (want && !want[dst]) continue;
+                        rl = orc_remote_frame(o, (const uint8_t *)relay, (size_t)pl + n, rrel);
+                    } else rl = orc_render_ex((const uint8_t *)relay, (size_t)pl + n, (uf[o] & ORC_UF_COLOUR) != 0, 0, rrel);
+                    if (pass == 0) { out->off[dst + 1] += rl; out->n_deliveries[dst] += 1; }
+                    else { memcpy(out->bytes + cur[dst], rrel, rl); cur[dst] += rl; }
                     continue;
                 }
                 if (kind[i] == ORC_OP_USER && (uf[u] & ORC_UF_CLONE)) continue;       /* a clone has no socket of its own */
+                if (uf[u] & ORC_UF_REMOTE) {                                            /* c:1299-1307 */
+                    if (!orc_remote_link || !rrel) continue;
+                    const int32_t l = orc_remote_link[u];
+                    if (l < 0 || l >= n_users || (want && !want[l])) continue;
+                    const size_t rl = orc_remote_frame(u, s, n, rrel);
+                    if (pass == 0) { out->off[l + 1] += rl; out->n_deliveries[l] += 1; }
+                    else { memcpy(out->bytes + cur[l], rrel, rl); cur[l] += rl; }
+                    continue;
+                }
                 int c = (uf[u] & ORC_UF_COLOUR) != 0;
                 if (c && !have_on)  { lon  = orc_render_ex(s, n, 1, of[i], ron);  have_on = 1; }
                 if (!c && !have_off){ loff = orc_render_ex(s, n, 0, of[i], roff); have_off = 1; }

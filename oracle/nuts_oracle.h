@@ -41,6 +41,7 @@ extern "C" {
 #define ORC_OF_ABOVE        0x04u /* write_level 'above' argument    c:1381 */
 #define ORC_OF_GATE_IF_SET  0x08u /* op is live iff gate verdict==1 (else ==0) */
 #define ORC_OF_PAGER        0x10u /* pager line: no reset after the string   c:2254-2300 */
+#define ORC_OF_RAW          0x40u  /* bytes as they are: what goes to a netlink socket (c:1303) */
 #define ORC_OF_PLAIN        0x20u /* colour taken as off: more(NULL,...)      c:2259      */
 
 /* ---- single-string primitives ------------------------------------------ */
@@ -74,6 +75,11 @@ int orc_user_banned(const uint8_t *file, size_t n, int file_present,
  * room[u] < 0 means user->room==NULL. */
 int orc_delivers(uint8_t kind, int32_t target, int32_t except_user, uint8_t oflags,
                  int32_t u, int32_t u_room, uint8_t u_flags, uint8_t u_level);
+
+/* Remote users (REMOTE_TYPE, c:1299-1307) inside orc_write_batch: link[u] = the pseudo-user whose stream
+ * stands for the netlink socket of remote user u (-1 for everybody else), old[u] != 0 for a peer older than
+ * 3.2 (colour commands stripped), names of the users (packed) for the "MSG <name>" line.  NULLs: none. */
+void orc_set_remotes(const int32_t *link, const uint8_t *old, const uint8_t *names, const uint64_t *name_off);
 
 /* Clone relay (c:1416-1426) inside orc_write_batch: owner[u] (-1 unless u is a clone), hear[u] =
  * clone_hear (0 nothing, 1 swears, 2 all), the swear list for hear == 1.  NULL, NULL, NULL: no clones. */

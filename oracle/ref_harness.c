@@ -60,6 +60,7 @@ static ssize_t nutsref_write(int fd, const void *buf, size_t n)
 
 /* ---- population ---------------------------------------------------------- */
 
+static NL_OBJECT g_links[4096];           /* netlink objects of the link pseudo-users (ref_set_remote) */
 static UR_OBJECT *g_users = NULL;
 static RM_OBJECT *g_rooms = NULL;
 static int g_nusers = 0, g_nrooms = 0;
@@ -73,6 +74,7 @@ void ref_reset(void)
     g_users = NULL; g_rooms = NULL; g_sink = NULL;
     g_nusers = g_nrooms = g_nsink = 0;
     g_write_calls = g_write_bytes = 0;
+    memset(g_links, 0, sizeof g_links);
     init_globals();                    /* c:1032 */
     system_logging = 0;                /* keep write_syslog() away from the CWD */
     force_listen = 0;
@@ -127,6 +129,19 @@ void ref_set_clone(int u, int owner, int hear)
 {
     if (u < 0 || u >= g_nusers || owner < 0 || owner >= g_nusers) return;
     g_users[u]->type = CLONE_TYPE; g_users[u]->owner = g_users[owner]; g_users[u]->clone_hear = hear;
+}
+
+/* user u becomes a REMOTE_TYPE user on a netlink whose socket is the sink of pseudo-user `link`
+ * (one netlink object per link user, created on first use); old != 0: a peer of version 3.1 */
+void ref_set_remote(int u, int link, int old)
+{
+    if (u < 0 || u >= g_nusers || link < 0 || link >= g_nusers || link >= 4096) return;
+    if (!g_links[link]) {
+        g_links[link] = create_netlink();
+        g_links[link]->socket = link;
+    }
+    g_links[link]->ver_major = 3; g_links[link]->ver_minor = old ? 1 : 3;
+    g_users[u]->type = REMOTE_TYPE; g_users[u]->netlink = g_links[link];
 }
 
 /* ---- the reference's own entry points, one call each --------------------- */
