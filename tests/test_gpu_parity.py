@@ -118,9 +118,13 @@ def test_errors_leave_the_host_alive(gpu_ctx):
     with pytest.raises(api.NutsbError) as e:
         gpu_ctx.write_batch(one(kind=np.array([9], np.uint8)))
     assert e.value.code == api.E_INVAL
+    # clones / remote users without their owner / link tables: nothing reaches them, nothing breaks
+    gpu_ctx.set_users(np.zeros(3, np.int32), np.array([api.UF_REMOTE, api.UF_CLONE, 0], np.uint8), np.ones(3, np.uint8), 1)
+    st = gpu_ctx.write_batch(one())
+    assert len(st.user(0)) == 0 and len(st.user(1)) == 0 and len(st.user(2)) == 2
     with pytest.raises(api.NutsbError) as e:
-        gpu_ctx.set_users(np.zeros(1, np.int32), np.array([api.UF_REMOTE], np.uint8), np.ones(1, np.uint8), 1)
-    assert e.value.code == api.E_UNSUPPORTED
+        gpu_ctx.set_clones(np.array([-1, -1, -1], np.int32), np.zeros(3, np.uint8))     # disagrees with the CLONE flag
+    assert e.value.code == api.E_INVAL
     # and the context still works
     gpu_ctx.set_users(np.zeros(2, np.int32), np.zeros(2, np.uint8), np.ones(2, np.uint8), 1)
     assert gpu_ctx.write_batch(one()).total_bytes == 2
