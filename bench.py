@@ -444,6 +444,10 @@ def run_ours(args):
                                                      direct=kstate["direct_ms"] / ks, steps=ks,
                                                      how="extra steps after the timed region with nutsb_set_overlap(0): "
                                                          "every kernel on one stream, CUDA events around each"),
+                                timed_region_ms=dict(plan_until_fanout=dev_state["plan_ms"] / max(1, dev_state["ksteps"]),
+                                                     render_span=dev_state["render_ms"] / max(1, dev_state["ksteps"]),
+                                                     fanout_and_direct=dev_state["fan_ms"] / max(1, dev_state["ksteps"]),
+                                                     how="CUDA events of the timed steps themselves (side stream on)"),
                                 plan_ms=kstate["plan_ms"] / ks, render_ms=kstate["render_ms"] / ks, fanout_ms=fan_ms,
                                 direct_ms=kstate["direct_ms"] / ks),
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,

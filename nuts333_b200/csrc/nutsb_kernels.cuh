@@ -745,6 +745,8 @@ __device__ __forceinline__ void nutsb_warp_copy(u8 *dst, const u8 *src, u32 n, i
 #define NUTSB_REN_OFF_WIN   1536                   // per-warp window, colour off (a round emits <= 32*8 bytes)
 #define NUTSB_REN_ON_ROUND  (32 * 28)
 #define NUTSB_REN_OFF_ROUND (32 * 8)
+#define NUTSB_PRAGMA_(x)     _Pragma(#x)
+#define NUTSB_UNROLL(n)      NUTSB_PRAGMA_(unroll n)
 #define NUTSB_FL_COLOUR     0x100u                 // internal: the rendering wanted is the colour-on one
 
 // 0xff in byte k of the result iff lo <= wb + k < hi (window byte coordinates)
@@ -775,6 +777,9 @@ __device__ __forceinline__ void nutsb_flat_render(u32 cnt, u32 meta, u64 gw, u32
     u32 fill_on = 0, fill_off = 0, qcount = 0;
     u32 carry_x = 0, carry_m = 0;                              // lane 31's word and command mask of the previous round
 
+#ifdef NUTSB_REN_UNROLL
+    NUTSB_UNROLL(NUTSB_REN_UNROLL)
+#endif
     for (u32 F = 0; F < W; F += 32) {
         // -- which string does flat word F + lane belong to
         const bool starts = (u32)lane < cnt && P >= F && P < F + 32;
@@ -971,15 +976,14 @@ struct FanoutArgs {
     u8 *out;
 };
 
-__global__ void __launch_bounds__(NUTSB_FAN_THREADS, NUTSB_FAN_MINBLOCKS)
-k_fanout(FanoutArgs A)
+// the work of one block: work item `item`, s_dyn = NUTSB_FAN_SMEM bytes of shared memory
+__device__ __forceinline__ void nutsb_fanout_block(const FanoutArgs &A, u32 item, u8 *s_dyn)
 {
-    NUTSB_DYN_SMEM(s_dyn);
     u8 *const s_on = s_dyn;
     u8 *const s_off = s_dyn + NUTSB_FAN_ON_CAP + 80;
     uint4 *const s_run = (uint4 *)(s_dyn + NUTSB_FAN_ON_CAP + 80 + NUTSB_FAN_OFF_CAP + 80);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const ItemDesc d = A.items[blockIdx.x];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const ItemDesc d = A.items[item];
     const bool staged = d.on_len <= NUTSB_FAN_ON_CAP && d.off_len <= NUTSB_FAN_OFF_CAP;
     const u32 a_on = (u32)(d.on_src & 15), a_off = (u32)(d.off_src & 15);
     if (staged) {
@@ -1005,6 +1009,13 @@ k_fanout(FanoutArgs A)
             nutsb_group_copy<32 * NUTSB_FAN_GROUP>(dst, src, len, tid % (32 * NUTSB_FAN_GROUP));
         }
     }
+}
+
+__global__ void __launch_bounds__(NUTSB_FAN_THREADS, NUTSB_FAN_MINBLOCKS)
+k_fanout(FanoutArgs A)
+{
+    NUTSB_DYN_SMEM(s_dyn);
+    nutsb_fanout_block(A, blockIdx.x, s_dyn);
 }
 
 // ---- I. direct ops (write_user) -----------------------------------------------------------
@@ -1053,20 +1064,27 @@ struct DirectSink {                 // string q's rendering is bytes [O, O + osz
     __device__ __forceinline__ void off(const u8 *, u32, int) {}
 };
 
-__global__ void __launch_bounds__(NUTSB_DIRECT_THREADS)
-k_direct(DirectArgs A)
+// shared memory of one k_direct block, carved from the dynamic window: per-warp render windows, per-warp
+// compaction tables, the command table
+#define NUTSB_DIR_WARPS (NUTSB_DIRECT_THREADS / 32)
+#define NUTSB_DIR_SMEM  (NUTSB_DIR_WARPS * (NUTSB_REN_ON_WIN + 64) + NUTSB_DIR_WARPS * 32 * (8 + 8 + 8) + ((NUTSB_CODETAB_BYTES + 15) & ~15))
+
+// the work of block `blk` of `nblk` (grid-strided over the events), smem = NUTSB_DIR_SMEM bytes
+__device__ __forceinline__ void nutsb_direct_block(const DirectArgs &A, u32 blk, u32 nblk, u8 *smem)
 {
-    __shared__ __align__(16) u8 s_on[NUTSB_DIRECT_THREADS / 32][NUTSB_REN_ON_WIN + 64];
-    __shared__ u64 s_gw[NUTSB_DIRECT_THREADS / 32][32], s_p[NUTSB_DIRECT_THREADS / 32][32];
-    __shared__ u32 s_par[NUTSB_DIRECT_THREADS / 32][32][2];
-    __shared__ u8 s_tab[NUTSB_CODETAB_BYTES];
+    typedef u8 OnWin[NUTSB_REN_ON_WIN + 64];
+    OnWin *const s_on = (OnWin *)smem;
+    u64 (*const s_gw)[32] = (u64 (*)[32])(smem + NUTSB_DIR_WARPS * (NUTSB_REN_ON_WIN + 64));
+    u64 (*const s_p)[32] = s_gw + NUTSB_DIR_WARPS;
+    u32 (*const s_par)[32][2] = (u32 (*)[32][2])(s_p + NUTSB_DIR_WARPS);
+    u8 *const s_tab = (u8 *)(s_par + NUTSB_DIR_WARPS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < NUTSB_CODETAB_BYTES; i += NUTSB_DIRECT_THREADS) s_tab[i] = A.pop.codetab[i];
     __syncthreads();
 
     u64 c_cnt = 0, c_bytes = 0; u32 seam_bytes = 0;
-    for (i64 ebase = ((i64)blockIdx.x * (NUTSB_DIRECT_THREADS / 32) + warp) * 32; ebase < A.n_ev;
-         ebase += (i64)gridDim.x * NUTSB_DIRECT_THREADS) {
+    for (i64 ebase = ((i64)blk * (NUTSB_DIRECT_THREADS / 32) + warp) * 32; ebase < A.n_ev;
+         ebase += (i64)nblk * NUTSB_DIRECT_THREADS) {
         const i64 e = ebase + lane;
         bool isw = false, seam = false, first_ev = false, last_ev = false;
         u64 p = 0, q = 0, gw = 0; u32 n = 0, al = 0, osz = 0, fl = 0;
@@ -1171,6 +1189,37 @@ k_direct(DirectArgs A)
     }
     for (int d = 16; d; d >>= 1) seam_bytes += __shfl_xor_sync(NUTSB_FULL, seam_bytes, d);
     if (lane == 0 && (c_cnt | seam_bytes)) { nutsb_add64(A.n_deliveries, c_cnt); nutsb_add64(A.n_deliveries + 1, c_bytes + seam_bytes); }
+}
+
+#ifndef NUTSB_DIR_MINBLOCKS
+#define NUTSB_DIR_MINBLOCKS 5       // <= 51 registers: 0.43 ms against 0.47 at 4 blocks per SM (the kernel is latency-bound)
+#endif
+__global__ void __launch_bounds__(NUTSB_DIRECT_THREADS, NUTSB_DIR_MINBLOCKS)
+k_direct(DirectArgs A)
+{
+    NUTSB_DYN_SMEM(s_dyn);
+    nutsb_direct_block(A, blockIdx.x, gridDim.x, s_dyn);
+}
+
+// ---- H+I in one launch ---------------------------------------------------------------------
+// k_fanout keeps the store queues full and issues little (about a fifth of the issue slots); k_direct is
+// bound by instruction issue and writes little.  Launched one after the other each has the machine to
+// itself; launched as two kernels on two streams the first one's blocks fill every SM and the second
+// waits.  So: ONE grid whose blocks are dealt between the two kinds by block index (a direct block every
+// `stride` blocks until they are used up), which puts both kinds on every SM for as long as both last.
+#define NUTSB_FD_SMEM (NUTSB_FAN_SMEM > NUTSB_DIR_SMEM ? NUTSB_FAN_SMEM : NUTSB_DIR_SMEM)
+static_assert(NUTSB_FAN_THREADS == NUTSB_DIRECT_THREADS, "k_fanout_direct runs both bodies with one block size");
+#ifndef NUTSB_FD_MINBLOCKS
+#define NUTSB_FD_MINBLOCKS 5
+#endif
+__global__ void __launch_bounds__(NUTSB_FAN_THREADS, NUTSB_FD_MINBLOCKS)
+k_fanout_direct(FanoutArgs F, DirectArgs D, u32 n_dir, u32 stride)
+{
+    NUTSB_DYN_SMEM(s_dyn);
+    const u32 b = blockIdx.x;
+    if (b % stride == 0 && b / stride < n_dir) { nutsb_direct_block(D, b / stride, n_dir, s_dyn); return; }
+    const u32 before = (b + stride - 1) / stride;          // direct blocks with a smaller index
+    nutsb_fanout_block(F, b - (before < n_dir ? before : n_dir), s_dyn);
 }
 
 // ---- stream digests ------------------------------------------------------------------------

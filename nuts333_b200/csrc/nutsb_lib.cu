@@ -49,6 +49,7 @@ struct nutsb_ctx {
     cudaStream_t stream = nullptr; bool own_stream = true;
     cudaStream_t side = nullptr; bool overlap = true;     // k_render / k_direct run beside the plan / the fan-out ...
     int side_render = 8, side_direct = 8;                 // ... with this many blocks per SM
+    int fd_dir_per_sm = 0;                                // k_fanout_direct: direct blocks per SM (0: one per 256 events)
     cudaEvent_t dep[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
     std::string err;
@@ -399,9 +400,12 @@ NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
         if (const char *e = getenv("NUTSB_SIDE_RENDER")) c->side_render = std::max(1, atoi(e));     // tuning aids
         if (const char *e = getenv("NUTSB_SIDE_DIRECT")) c->side_direct = std::max(1, atoi(e));
         if (const char *e = getenv("NUTSB_OVERLAP")) c->overlap = atoi(e) != 0;
+        if (const char *e = getenv("NUTSB_FD_DIR_PER_SM")) c->fd_dir_per_sm = std::max(0, atoi(e));
         for (auto &e : c->ev) CK(cudaEventCreate(&e));
         for (auto &e : c->dep) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_FAN_SMEM));
+        CK(cudaFuncSetAttribute(k_fanout_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_FD_SMEM));
+        CK(cudaFuncSetAttribute(k_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_DIR_SMEM));
         u8 tab[NUTSB_CODETAB_BYTES]; build_codetab(tab);
         TRY(upload(c, c->d_codetab, tab, sizeof tab));
         TRY(ensure(c, c->d_status, 64)); TRY(ensure(c, c->d_counts, 64)); TRY(ensure(c, c->d_sizes, sizeof(Sizes)));
@@ -826,24 +830,26 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     Geometry geo{ c->d_room_b_off.as<u32>(), c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>() };
     c->tm.fanout_launches = 0;
 
-    // -- I. direct ops: independent of the copy plan and of the fan-out (disjoint bytes of the streams), so
-    //    they go to the side stream as well
+    // -- I. direct ops + seams.  With the overlap on they share ONE launch with the fan-out (k_fanout_direct,
+    //    below): blocks of both kinds on every SM.  Otherwise (or when there is nothing to fan out) k_direct
+    //    runs by itself, here.
+    const bool fan = sz.cells > 0 && sz.items > 0;
+    const bool fused = par && fan && sz.n_events > 0;
+    DirectArgs da{ ops, pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_op.as<u32>(),
+                   c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), (i64)sz.n_events, counters,
+                   c->d_status.as<u32>(), c->d_slab.as<u8>(), off_base, has_level ? 1u : 0u };
+    u32 n_dir = cdiv(sz.n_events, NUTSB_DIRECT_THREADS);
+    if (fused && c->fd_dir_per_sm > 0) n_dir = std::min(n_dir, (u32)(c->sm_count * c->fd_dir_per_sm));   // grid-strided direct blocks
     if (c->profiling) CK(cudaEventRecord(c->ev[9], sd));
-    if (sz.n_events > 0) {
+    if (sz.n_events > 0 && !fused) {
         if (par) { CK(cudaEventRecord(c->dep[2], st)); CK(cudaStreamWaitEvent(sd, c->dep[2], 0)); }
-        DirectArgs da{ ops, pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_op.as<u32>(),
-                       c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), (i64)sz.n_events, counters,
-                       c->d_status.as<u32>(), c->d_slab.as<u8>(), off_base, has_level ? 1u : 0u };
-        u32 grid = cdiv(sz.n_events, NUTSB_DIRECT_THREADS);
-        if (par) grid = std::min(grid, (u32)(c->sm_count * c->side_direct));
-        NUTSB_LAUNCH(grid, NUTSB_DIRECT_THREADS, sd, k_direct, da); CKL();
+        NUTSB_LAUNCH_SMEM(n_dir, NUTSB_DIRECT_THREADS, NUTSB_DIR_SMEM, sd, k_direct, da); CKL();
         c->tm.launches++;
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[3], sd));
     if (par) CK(cudaEventRecord(c->dep[3], sd));
 
     // -- F. copy plan: the run list and the work-item descriptors
-    const bool fan = sz.cells > 0 && sz.items > 0;
     if (fan) {
         TRY(ensure(c, c->d_items, (size_t)sz.items * sizeof(ItemDesc)));
         u32 *cursor = counts + 4;
@@ -873,7 +879,13 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     if (c->profiling) CK(cudaEventRecord(c->ev[10], st));
     if (fan) {
         FanoutArgs fa{ c->d_items.as<ItemDesc>(), c->d_runs.as<uint4>(), c->d_slab.as<u8>(), off_base, c->d_out.as<u8>() };
-        NUTSB_LAUNCH_SMEM(sz.items, NUTSB_FAN_THREADS, NUTSB_FAN_SMEM, st, k_fanout, fa); CKL();
+        if (fused) {
+            const u32 total = sz.items + n_dir;
+            const u32 stride = std::max(1u, total / n_dir);        // a direct block every `stride` blocks
+            NUTSB_LAUNCH_SMEM(total, NUTSB_FAN_THREADS, NUTSB_FD_SMEM, st, k_fanout_direct, fa, da, n_dir, stride); CKL();
+        } else {
+            NUTSB_LAUNCH_SMEM(sz.items, NUTSB_FAN_THREADS, NUTSB_FAN_SMEM, st, k_fanout, fa); CKL();
+        }
         c->tm.launches++; c->tm.fanout_launches = 1;
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[2], st));
