@@ -107,3 +107,21 @@ def test_many_tiles_per_room_seams(sim_lib, port):
         bad = np.nonzero(st.data != data)[0]
         assert bad.size == 0, (n_users, bad[:8], int(np.searchsorted(off, bad[0], side="right")) - 1)
     ctx.close()
+
+
+def test_serial_and_overlapped_schedules_agree(sim_lib, port):
+    """nutsb_set_overlap(0): k_render, k_direct and k_fanout one after the other on one stream (the schedule
+    bench.py times kernels in); default: k_render on the side stream, k_fanout_direct in one launch."""
+    ctx = _ctx(sim_lib)
+    words = synth.swear_words(8)
+    us, n_rooms = synth.users(40, 10, stress=True)
+    bt, bo = synth.bodies(400, words)
+    v = port.contains_swearing_batch(bt, bo, words)
+    sops, _, _ = synth.say_ops(400, 40, 10, bt, bo, gated=True)
+    off, data, nd = port.write_batch(sops, us, verdict=v)
+    ctx.set_users(us["room"], us["flags"], us["level"], n_rooms)
+    for overlap in (False, True):
+        ctx.set_overlap(overlap)
+        st = ctx.write_batch(dict(sops, verdict=v))
+        assert (st.off == off).all() and (st.data == data).all() and st.n_deliveries == int(nd.sum()), overlap
+    ctx.close()

@@ -377,3 +377,27 @@ def test_config3_full_size(gpu_ctx, port):
     clean = int((v == 0).sum())
     _full_size_properties(gpu_ctx, port, ops, us, n_rooms, v, clean * 100 + (1000000 - clean))
     gpu_ctx.set_swear_words(["fuck", "shit", "cunt", "*"])
+
+
+def test_serial_and_overlapped_schedules_agree(gpu_ctx, port):
+    """every kernel on one stream (what bench.py times kernels in) against the default schedule
+    (k_render on the side stream, fan-out and direct blocks dealt over one grid)"""
+    words = synth.swear_words(64)
+    us, n_rooms = synth.users(3000, 100, stress=True)
+    bt, bo = synth.bodies(60000, words)
+    gpu_ctx.set_swear_words(words)
+    v = gpu_ctx.contains_swearing_batch(bt, bo)
+    sops, _, _ = synth.say_ops(60000, 3000, 100, bt, bo, gated=True)
+    gpu_ctx.set_users(us["room"], us["flags"], us["level"], n_rooms)
+    res = []
+    for overlap in (False, True, False):
+        gpu_ctx.set_overlap(overlap)
+        st = gpu_ctx.write_batch(dict(sops, verdict=v))
+        res.append((st.off.copy(), hashlib.sha256(st.data.tobytes()).hexdigest(), st.n_deliveries))
+    gpu_ctx.set_overlap(True)
+    assert (res[0][0] == res[1][0]).all() and res[0][1] == res[1][1] == res[2][1] and res[0][2] == res[1][2]
+    only = np.arange(0, 3000, 97, dtype=np.int32)
+    off, data, nd = port.write_batch(sops, us, verdict=v, only_users=only)
+    st = gpu_ctx.write_batch(dict(sops, verdict=v))
+    for u in only:
+        assert st.user(int(u)) == data[int(off[u]):int(off[u + 1])].tobytes()
