@@ -503,6 +503,42 @@ __device__ __forceinline__ uint4 nutsb_run_pack(u64 dst, u64 src, u32 len)
 }
 #define NUTSB_RUN_MAX_LEN 0xffffffu
 
+// What k_plan and k_direct need to know about a recipient, gathered once per batch (one 48-byte record
+// instead of a chain of dependent loads through five arrays in every cell and every event).
+struct SlotInfo {
+    u64 so_u;                    // the recipient's stream starts here
+    u64 end;                     // ... and ends here
+    u64 base;                    // stream position of slab rank g after e events = base + cpx.at(k, room, g) + sv_pre[e]
+    u32 b0, nb_room;             // the room's first slab rank, its slab ops
+    u32 e0, e1;                  // the recipient's events
+    u32 room; i32 k;             // room, class
+    u32 cf_lv;                   // recipient flags | level << 8
+    u32 pad_;
+};
+
+struct SlotInfoArgs {
+    PopView pop; ClassPrefix cpx;
+    const u32 *room_b_off, *ev_off; const u64 *sv_pre, *stream_off;
+    SlotInfo *out;
+};
+
+__global__ void __launch_bounds__(128)
+k_slot_info(SlotInfoArgs A)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= (u32)A.pop.n_users) return;
+    const i32 u = A.pop.slot_user[s];
+    SlotInfo si;
+    si.room = (u32)A.pop.user_room[u]; si.k = A.pop.user_cls[u];
+    si.b0 = A.room_b_off[si.room]; si.nb_room = A.room_b_off[si.room + 1] - si.b0;
+    si.e0 = A.ev_off[s]; si.e1 = A.ev_off[s + 1];
+    si.so_u = A.stream_off[u]; si.end = A.stream_off[u + 1];
+    si.base = si.so_u - A.cpx.at(si.k, si.room, si.b0) - A.sv_pre[si.e0];
+    si.cf_lv = (u32)A.pop.slot_cf[s] | ((u32)A.pop.slot_lv[s] << 8);
+    si.pad_ = 0;
+    A.out[s] = si;
+}
+
 struct PlanArgs {
     PopView pop; Geometry geo; ClassPrefix cpx;
     const u64 *stream_off;
@@ -510,6 +546,7 @@ struct PlanArgs {
     const u32 *bl_meta;          // per slab op: kind | flags << 8 | clamped target << 16
     u64 n_cells, off_base;       // off_base: where the colour-off renderings start in the slab buffer
     u32 has_level;
+    const SlotInfo *slots;
     u32 *run_cursor;             // runs reserved so far
     uint4 *runs; ItemDesc *items;
     u64 *counters;               // [0] deliveries
@@ -521,29 +558,27 @@ struct PlanArgs {
 template <bool FILL>
 __device__ __forceinline__ u32 nutsb_plan_cell(const PlanArgs &A, u32 room, u32 t, u32 ls, u64 r_out, u32 &deliv)
 {
-    const u32 slot0 = (u32)A.pop.room_slot_off[room];
-    const u32 s = slot0 + ls;
-    const u32 b0 = A.geo.room_b_off[room], nb_room = A.geo.room_b_off[room + 1] - b0;
+    const SlotInfo si = A.slots[(u32)A.pop.room_slot_off[room] + ls];
+    const u32 b0 = si.b0, nb_room = si.nb_room;
     const u32 a0 = t * NUTSB_TILE_OPS;                   // room-local slab rank of the tile's first op
     const u32 nb = nb_room - a0 < NUTSB_TILE_OPS ? nb_room - a0 : NUTSB_TILE_OPS;
     const u32 g0 = b0 + a0;
-    const u32 e0 = A.ev_off[s], e1 = A.ev_off[s + 1];
+    const u32 e0 = si.e0, e1 = si.e1;
     // the recipient's events inside the tile: keys in [4*a0+1, 4*(a0+nb)] (a direct op before the tile's first
     // slab op belongs to the tile before)
     u32 l = e0, h = e1;
     { const u32 thr = 4 * a0 + 1; while (l < h) { const u32 mid = (l + h) >> 1; if (A.sv_ukey[mid] < thr) l = mid + 1; else h = mid; } }
     u32 l_end = l; h = e1;
     { const u32 thr = 4 * (a0 + nb) + 1; while (l_end < h) { const u32 mid = (l_end + h) >> 1; if (A.sv_ukey[mid] < thr) l_end = mid + 1; else h = mid; } }
-    const i32 u = A.pop.slot_user[s];
-    const i32 k = A.pop.user_cls[u];
-    const u32 cf = A.pop.slot_cf[s], clv = A.pop.slot_lv[s];
+    const i32 k = si.k;
+    const u32 cf = si.cf_lv & 0xffu, clv = si.cf_lv >> 8;
     const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
     const bool full = !A.has_level && !(cf & NUTSB_UF_FILTERED);
     const u64 *vp = (colour ? A.cpx.vp_on : A.cpx.vp_off) + g0;      // tile-local prefix of rendered lengths
     const u64 sb = colour ? 0 : A.off_base;
     // stream position of the tile's first op: class prefix + the recipient's own events before the tile
-    const u64 so_u = A.stream_off[u], cp_b0 = A.cpx.at(k, room, b0);
-    u64 p = so_u + (A.cpx.at(k, room, g0) - cp_b0) + (A.sv_pre[l] - A.sv_pre[e0]);
+    const u64 so_u = si.so_u;
+    u64 p = si.base + A.cpx.at(k, room, g0) + A.sv_pre[l];
     // Plain listeners: a run covers only whole 32-byte sectors of the stream.  The pieces of a sector
     // that holds a discontinuity (an event of this recipient) are written together by k_direct's seam
     // pass: two partial writes of one sector far apart in time cost a read-modify-write in DRAM.
@@ -551,7 +586,7 @@ __device__ __forceinline__ u32 nutsb_plan_cell(const PlanArgs &A, u32 room, u32 
     u64 a_start = so_u; bool first_seg = true;
     if (full && l > e0) {                                 // ... after the last event before the tile
         const u32 uk = A.sv_ukey[l - 1];
-        a_start = so_u + (A.cpx.at(k, room, b0 + (uk >> 2) + ((uk & 3u) != NUTSB_EV_DIRECT)) - cp_b0) + (A.sv_pre[l] - A.sv_pre[e0]);
+        a_start = si.base + A.cpx.at(k, room, b0 + (uk >> 2) + ((uk & 3u) != NUTSB_EV_DIRECT)) + A.sv_pre[l];
         first_seg = false;
     }
     const bool last_tile = a0 + nb == nb_room;
@@ -1035,6 +1070,7 @@ struct DirectArgs {
     u32 *status;
     const u8 *slab; u64 off_base;   // the rendered slab (k_render): source of the seam bytes
     u32 has_level;
+    const SlotInfo *slots;
 };
 
 #define NUTSB_DIRECT_THREADS 256
@@ -1091,16 +1127,12 @@ __device__ __forceinline__ void nutsb_direct_block(const DirectArgs &A, u32 blk,
         u64 a_start = 0, b_end = 0; const u8 *sa = nullptr, *sb = nullptr;
         if (e < A.n_ev) {
             const u32 uk = A.sv_ukey[e];
-            const u32 s = A.ev_slot_sorted[e];
-            const i32 u = A.pop.slot_user[s];
-            const u32 room = (u32)A.pop.user_room[u];
-            const i32 k = A.pop.user_cls[u];
-            const u32 b0 = A.room_b_off[room];
-            const u32 cf = A.pop.slot_cf[s];
-            const u32 e0 = A.ev_off[s], e1 = A.ev_off[s + 1];
-            const u64 so_u = A.stream_off[u], cp_b0 = A.cpx.at(k, room, b0), pre0 = A.sv_pre[e0];
+            const SlotInfo si = A.slots[A.ev_slot_sorted[e]];
+            const u32 room = si.room; const i32 k = si.k;
+            const u32 b0 = si.b0, cf = si.cf_lv & 0xffu;
+            const u32 e0 = si.e0, e1 = si.e1;
+            const u64 so_u = si.so_u, base = si.base;
             const u32 j = uk >> 2, ek = uk & 3u, skip = ek != NUTSB_EV_DIRECT;
-            const u64 base = so_u - cp_b0 - pre0;
             p = base + A.cpx.at(k, room, b0 + j) + A.sv_pre[e];
             q = base + A.cpx.at(k, room, b0 + j + skip) + A.sv_pre[e + 1];     // where the stream goes on after the event
             if (ek != NUTSB_EV_SKIP) {                         // a direct op: its rendering fills [p, q)
@@ -1123,7 +1155,7 @@ __device__ __forceinline__ void nutsb_direct_block(const DirectArgs &A, u32 blk,
                 const u64 *vp = colour ? A.cpx.vp_on : A.cpx.vp_off;
                 const u8 *R = A.slab + (colour ? 0 : A.off_base);
                 first_ev = (u32)e == e0; last_ev = (u32)e + 1 == e1;
-                a_start = so_u; b_end = A.stream_off[u + 1];
+                a_start = so_u; b_end = si.end;
                 if (!first_ev && lane == 0) {                  // the other lanes take it from their neighbour
                     const u32 ukp = A.sv_ukey[e - 1];
                     a_start = base + A.cpx.at(k, room, b0 + (ukp >> 2) + ((ukp & 3u) != NUTSB_EV_DIRECT)) + A.sv_pre[e];

@@ -84,7 +84,7 @@ struct nutsb_ctx {
     DBuf d_sv_ukey, d_sv_delta, d_sv_op, d_sv_pre, d_ev_off;
     DBuf d_vp_on, d_vp_off, d_cp;
     DBuf d_room_tile_off, d_room_cell_off, d_room_item_off, d_sizes, d_counters;
-    DBuf d_runs, d_items, d_slab, d_bl_meta;
+    DBuf d_runs, d_items, d_slab, d_bl_meta, d_slots;
     DBuf d_off, d_out, d_digest, d_ulen;
     HBuf h_small, h_off, h_out;
     u64 last_total = 0; bool have_streams = false;
@@ -361,7 +361,7 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
         &c->d_evk[1], &c->d_evv[0], &c->d_evv[1], &c->d_ev_ukey, &c->d_ev_delta, &c->d_ev_op, &c->d_sv_ukey,
         &c->d_sv_delta, &c->d_sv_op, &c->d_sv_pre, &c->d_ev_off, &c->d_vp_on, &c->d_vp_off, &c->d_cp,
         &c->d_room_tile_off, &c->d_room_cell_off, &c->d_room_item_off, &c->d_sizes, &c->d_counters,
-        &c->d_runs, &c->d_items, &c->d_slab, &c->d_bl_meta, &c->d_off, &c->d_out, &c->d_digest, &c->d_ulen,
+        &c->d_runs, &c->d_slots, &c->d_items, &c->d_slab, &c->d_bl_meta, &c->d_off, &c->d_out, &c->d_digest, &c->d_ulen,
         &c->s_text, &c->s_toff, &c->s_kind, &c->s_target, &c->s_except, &c->s_flags, &c->s_gate, &c->s_verdict, &c->s_v8,
         &c->d_names, &c->d_name_off, &c->d_sflags, &c->d_lit, &c->d_lit_off, &c->d_sp_len, &c->d_sp_off, &c->d_sp_text,
         &c->d_sp_kind, &c->d_sp_target, &c->d_sp_except, &c->d_sp_flags, &c->d_sp_gate, &c->d_sp_verdict,
@@ -820,6 +820,13 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
                  c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>(), c->d_sizes.as<Sizes>()); CKL();
     c->tm.launches++;
 
+    TRY(ensure(c, c->d_slots, ((size_t)U + 1) * sizeof(SlotInfo)));
+    if (U > 0) {
+        SlotInfoArgs sa{ pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), c->d_slots.as<SlotInfo>() };
+        NUTSB_LAUNCH(cdiv((u64)U, 128), 128, st, k_slot_info, sa); CKL();
+        c->tm.launches++;
+    }
+
     // -- read-back #2: sizes
     Sizes *hs = (Sizes *)(c->h_small.as<u8>() + 256);
     CK(cudaMemcpyAsync(hs, c->d_sizes.p, sizeof(Sizes), cudaMemcpyDeviceToHost, st));
@@ -837,7 +844,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     const bool fused = par && fan && sz.n_events > 0;
     DirectArgs da{ ops, pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_op.as<u32>(),
                    c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), (i64)sz.n_events, counters,
-                   c->d_status.as<u32>(), c->d_slab.as<u8>(), off_base, has_level ? 1u : 0u };
+                   c->d_status.as<u32>(), c->d_slab.as<u8>(), off_base, has_level ? 1u : 0u, c->d_slots.as<SlotInfo>() };
     u32 n_dir = cdiv(sz.n_events, NUTSB_DIRECT_THREADS);
     if (fused && c->fd_dir_per_sm > 0) n_dir = std::min(n_dir, (u32)(c->sm_count * c->fd_dir_per_sm));   // grid-strided direct blocks
     if (c->profiling) CK(cudaEventRecord(c->ev[9], sd));
@@ -856,7 +863,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
         CK(cudaMemsetAsync(cursor, 0, 4, st));
         PlanArgs pa{ pop, geo, cpx, c->d_off.as<u64>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_delta.as<i32>(),
                      c->d_sv_pre.as<u64>(), c->d_bl_meta.as<u32>(), (u64)sz.cells, off_base, has_level ? 1u : 0u,
-                     cursor, nullptr, c->d_items.as<ItemDesc>(), counters, c->d_status.as<u32>() };
+                     c->d_slots.as<SlotInfo>(), cursor, nullptr, c->d_items.as<ItemDesc>(), counters, c->d_status.as<u32>() };
         // plain listeners: at most one run per cell plus one per event; behind a filter the count is taken first
         u64 n_runs = sz.cells + sz.n_events;
         if (!alias) {
