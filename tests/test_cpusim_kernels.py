@@ -125,3 +125,11 @@ def test_serial_and_overlapped_schedules_agree(sim_lib, port):
         st = ctx.write_batch(dict(sops, verdict=v))
         assert (st.off == off).all() and (st.data == data).all() and st.n_deliveries == int(nd.sum()), overlap
     ctx.close()
+
+
+def test_config5_pipeline_on_emulator(sim_lib, port):
+    """admission by the ban verdicts, swear verdicts, say() fan-out: BASELINE config 5 in miniature"""
+    from test_gpu_parity import _config5_pipeline
+    ctx = _ctx(sim_lib)
+    _config5_pipeline(ctx, port, 90, 300, 10, 12, 20)
+    ctx.close()

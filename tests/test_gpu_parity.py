@@ -401,3 +401,45 @@ def test_serial_and_overlapped_schedules_agree(gpu_ctx, port):
     st = gpu_ctx.write_batch(dict(sops, verdict=v))
     for u in only:
         assert st.user(int(u)) == data[int(off[u]):int(off[u + 1])].tobytes()
+
+
+def _config5_pipeline(ctx, port, n_users, n_msgs, per_room, n_ban, sample):
+    """BASELINE config 5, one rank's share: stage A admission (site_banned or user_banned -> never a user of the
+    talker), stage B swear verdicts, stage C say() composed lines rendered and fanned out in rooms of `per_room`."""
+    words = synth.swear_words(64)
+    ctx.set_swear_words(words)
+    sf, uf = synth.ban_file(0, n_ban, n_users, n_users, True), synth.ban_file(1, n_ban, n_users, n_users, False)
+    ctx.set_ban_files(sf, uf)
+    st_, so_ = synth.sites(n_users)
+    nt_, no_ = synth.names(n_users)
+    vs, vu = ctx.site_banned_batch(st_, so_), ctx.user_banned_batch(nt_, no_)
+    assert (vs == port.ban_batch(0, sf, st_, so_)).all() and (vu == port.ban_batch(1, uf, nt_, no_)).all()
+    admitted = np.nonzero((vs | vu) == 0)[0]
+    assert 0 < len(admitted) < n_users                       # some connections are refused (c:279, c:1496)
+    U = len(admitted) - len(admitted) % per_room              # whole rooms of admitted users
+    us, n_rooms = synth.users(U, per_room)
+    bt, bo = synth.bodies(n_msgs, words)
+    v = ctx.contains_swearing_batch(bt, bo)
+    assert (v == port.contains_swearing_batch(bt, bo, words)).all()
+    ops, spk, rm = synth.say_ops(n_msgs, U, per_room, bt, bo, gated=True)
+    ctx.set_users(us["room"], us["flags"], us["level"], n_rooms)
+    st = ctx.write_batch(dict(ops, verdict=v))
+    clean = int((v == 0).sum())
+    assert st.n_deliveries == clean * per_room + (n_msgs - clean)
+    pick = sorted(np.random.RandomState(5).choice(U, sample, replace=False).tolist())
+    o, d, nd = port.write_batch(ops, us, verdict=v, only_users=pick)
+    for u in pick:
+        assert st.user(u) == d[int(o[u]):int(o[u + 1])].tobytes(), u
+    ctx.set_swear_words(["fuck", "shit", "cunt", "*"])
+    return st
+
+
+def test_config5_pipeline_scaled(gpu_ctx, port):
+    _config5_pipeline(gpu_ctx, port, 6000, 60000, 100, 600, 40)
+
+
+def test_config5_pipeline_one_rank_full_size(gpu_ctx, port):
+    """10M messages x 100k users over 8 ranks = 1.25M messages x 12.5k connecting users per rank"""
+    st = _config5_pipeline(gpu_ctx, port, 12500, 1250000, 100, 1250, 16)
+    dg = gpu_ctx.stream_digests()
+    assert len(set(dg.tolist())) == len(dg)                   # every user's stream is its own
