@@ -28,44 +28,6 @@ typedef uint8_t            u8;
 
 #define NUTSB_FULL 0xffffffffu
 
-// ---- TMA bulk copy shared -> global (cp.async.bulk, SASS: UBLKCP) -------------------------
-// 16-byte aligned source, destination and size.  Bulk-group completion: commit, then
-// wait_read before the shared source is overwritten, wait_all before the block exits.
-#ifdef NUTSB_CPUSIM
-static inline void nutsb_bulk_s2g(void *gdst, const void *ssrc, u32 bytes) { memcpy(gdst, ssrc, bytes); }
-static inline void nutsb_bulk_commit() {}
-static inline void nutsb_bulk_wait_read() {}
-static inline void nutsb_bulk_wait_read1() {}
-static inline void nutsb_bulk_wait_all() {}
-static inline void nutsb_fence_async_smem() {}
-#else
-__device__ __forceinline__ void nutsb_bulk_s2g(void *gdst, const void *ssrc, u32 bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 :: "l"(gdst), "r"((u32)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void nutsb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void nutsb_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void nutsb_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void nutsb_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-// make generic-proxy writes to shared memory visible to the async proxy (TMA)
-__device__ __forceinline__ void nutsb_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-#endif
-
-// ---- cp.async (LDGSTS): 16 bytes global -> shared without a register round trip ----------------
-#ifdef NUTSB_CPUSIM
-static inline void nutsb_cp_async16(void *sdst, const void *gsrc) { memcpy(sdst, gsrc, 16); }
-static inline void nutsb_cp_async_commit() {}
-template <int N> static inline void nutsb_cp_async_wait() {}
-#else
-__device__ __forceinline__ void nutsb_cp_async16(void *sdst, const void *gsrc)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((u32)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void nutsb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void nutsb_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-#endif
-
 __device__ __forceinline__ void nutsb_add64(u64 *p, u64 v) { atomicAdd((unsigned long long *)p, (unsigned long long)v); }
 
 // recipients that do not simply take every op of their room: they go through nutsb_class_delivers

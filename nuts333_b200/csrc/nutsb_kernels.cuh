@@ -780,8 +780,6 @@ __device__ __forceinline__ void nutsb_warp_copy(u8 *dst, const u8 *src, u32 n, i
 #define NUTSB_REN_OFF_WIN   1536                   // per-warp window, colour off (a round emits <= 32*8 bytes)
 #define NUTSB_REN_ON_ROUND  (32 * 28)
 #define NUTSB_REN_OFF_ROUND (32 * 8)
-#define NUTSB_PRAGMA_(x)     _Pragma(#x)
-#define NUTSB_UNROLL(n)      NUTSB_PRAGMA_(unroll n)
 #define NUTSB_FL_COLOUR     0x100u                 // internal: the rendering wanted is the colour-on one
 
 // 0xff in byte k of the result iff lo <= wb + k < hi (window byte coordinates)
@@ -812,9 +810,6 @@ __device__ __forceinline__ void nutsb_flat_render(u32 cnt, u32 meta, u64 gw, u32
     u32 fill_on = 0, fill_off = 0, qcount = 0;
     u32 carry_x = 0, carry_m = 0;                              // lane 31's word and command mask of the previous round
 
-#ifdef NUTSB_REN_UNROLL
-    NUTSB_UNROLL(NUTSB_REN_UNROLL)
-#endif
     for (u32 F = 0; F < W; F += 32) {
         // -- which string does flat word F + lane belong to
         const bool starts = (u32)lane < cnt && P >= F && P < F + 32;

@@ -48,7 +48,7 @@ struct nutsb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr; bool own_stream = true;
     cudaStream_t side = nullptr; bool overlap = true;     // k_render / k_direct run beside the plan / the fan-out ...
-    int side_render = 8, side_direct = 8;                 // ... with this many blocks per SM
+    int side_render = 8;                                  // ... with this many k_render blocks per SM
     int fd_dir_per_sm = 0;                                // k_fanout_direct: direct blocks per SM (0: one per 256 events)
     cudaEvent_t dep[4] = {nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
@@ -398,7 +398,6 @@ NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
         CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
         CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
         if (const char *e = getenv("NUTSB_SIDE_RENDER")) c->side_render = std::max(1, atoi(e));     // tuning aids
-        if (const char *e = getenv("NUTSB_SIDE_DIRECT")) c->side_direct = std::max(1, atoi(e));
         if (const char *e = getenv("NUTSB_OVERLAP")) c->overlap = atoi(e) != 0;
         if (const char *e = getenv("NUTSB_FD_DIR_PER_SM")) c->fd_dir_per_sm = std::max(0, atoi(e));
         for (auto &e : c->ev) CK(cudaEventCreate(&e));
