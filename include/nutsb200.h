@@ -200,7 +200,9 @@ int nutsb_set_users(nutsb_ctx *ctx, int32_t n_users, int32_t n_rooms, const int3
 /* write_user / write_room[_except] / write_level, batched.  Host variant:
  * ops in host memory, streams returned in pinned host memory. */
 int nutsb_write_batch(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_streams *out);
-/* Device variant: every pointer in ops is a device pointer; streams stay in HBM. */
+/* Device variant: every pointer in ops is a device pointer; streams stay in HBM.  The packed text is read
+ * in aligned 16-byte vectors: it must be readable from the 16-byte boundary at or before its first byte to the
+ * one at or after its last (true of any buffer that starts a cudaMalloc allocation, whatever its length). */
 int nutsb_write_batch_dev(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_streams *out);
 
 /* contains_swearing / site_banned / user_banned over n packed strings

@@ -1,0 +1,42 @@
+"""Run by tests/test_asan.py in a python started under AddressSanitizer: the product's kernels compiled against the
+SIMT emulator with -fsanitize=address, on batches that cross every window (tiles, render windows, seams)."""
+import sys, ctypes
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / 'tests'))
+import numpy as np
+from cpusim.build_sim import build_sim
+from nuts333_b200 import api, synth
+import oracle_lib as O
+lib = api.bind(ctypes.CDLL(str(build_sim(sanitize="address"))))
+port = O.port()
+ctx = api.Context(0, lib)
+words = synth.swear_words(8)
+ctx.set_swear_words(words)
+for n_users, per_room, n_msgs, stress in ((24, 12, 500, False), (9, 3, 300, True)):
+    us, n_rooms = synth.users(n_users, per_room, stress=stress)
+    bt, bo = synth.bodies(n_msgs, words)
+    v = ctx.contains_swearing_batch(bt, bo)
+    sops, _, _ = synth.say_ops(n_msgs, n_users, per_room, bt, bo, gated=True)
+    ctx.set_users(us["room"], us["flags"], us["level"], n_rooms)
+    for ov in (True, False):
+        ctx.set_overlap(ov)
+        st = ctx.write_batch(dict(sops, verdict=v))
+        off, data, nd = port.write_batch(sops, us, verdict=v)
+        assert (st.off == off).all() and (st.data == data).all()
+# long strings
+rng = np.random.default_rng(7)
+alphabet = np.frombuffer(b"~/\n" + b"FRSOLKBGTWYMUIV" + b"xy z", np.uint8)
+texts = [rng.choice(alphabet, size=int(rng.integers(0, 2001))).tobytes() for _ in range(60)]
+text, toff = O.pack(texts)
+n = len(texts)
+kind = rng.integers(0, 2, n).astype(np.uint8)
+ops = dict(text=text, off=toff, kind=kind, target=np.where(kind == 0, rng.integers(0, 7, n), rng.integers(-1, 2, n)).astype(np.int32),
+           except_user=rng.integers(-1, 7, n).astype(np.int32), flags=np.zeros(n, np.uint8))
+users = dict(room=np.array([0, 0, 0, 1, 1, 0, 1], np.int32), flags=np.array([1, 0, 1, 0, 1, 5, 0], np.uint8), level=np.ones(7, np.uint8))
+ctx.set_users(users["room"], users["flags"], users["level"], 2)
+st = ctx.write_batch(ops)
+eoff, data, nd = port.write_batch(ops, users)
+assert (st.off == eoff).all() and (st.data == data).all()
+ctx.close()
+print("asan run ok")
