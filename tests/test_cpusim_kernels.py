@@ -133,3 +133,34 @@ def test_config5_pipeline_on_emulator(sim_lib, port):
     ctx = _ctx(sim_lib)
     _config5_pipeline(ctx, port, 90, 300, 10, 12, 20)
     ctx.close()
+
+
+def test_flat_renderer_fuzz_vs_oracle(sim_lib, port):
+    """The position-parallel renderer against the byte machine's restatement on strings dense in everything the
+    machine looks at -- '~', '/', newlines, command letters, every other byte value 1..255 -- of lengths that put
+    commands across word, lane and round boundaries, as write_user ops (k_direct) and room ops (k_render)."""
+    rng = np.random.default_rng(2024)
+    hot = np.frombuffer(b"~/\n" + b"FRSOLKBGTWYMUIV" + b"x ", np.uint8)
+    texts = []
+    for i in range(700):
+        n = int(rng.integers(0, 40)) if i % 4 else int(rng.integers(100, 420))
+        s = rng.choice(hot, size=n)
+        noise = rng.random(n) < 0.12
+        s = np.where(noise, rng.integers(1, 256, n).astype(np.uint8), s).astype(np.uint8)
+        texts.append(s.tobytes())
+    texts += [b"", b"~", b"~F", b"~FR", b"/~FR", b"//~FR", b"~/~", b"\n", b"~OL\n", b"x/~", b"~FBK", b"\xff~RS\x80", b"~FX~RS", b"tail~"]
+    text, off = O.pack(texts)
+    n = len(texts)
+    kind = (np.arange(n) % 2).astype(np.uint8)                       # alternately write_user and write_room
+    target = np.where(kind == 0, np.arange(n) % 4, 0).astype(np.int32)
+    ops = dict(text=text, off=off, kind=kind, target=target, except_user=np.full(n, -1, np.int32),
+               flags=np.where(np.arange(n) % 7 == 0, api.OF_PAGER, 0).astype(np.uint8))
+    users = dict(room=np.zeros(4, np.int32), flags=np.array([1, 0, 1, 0], np.uint8), level=np.ones(4, np.uint8))
+    ctx = _ctx(sim_lib)
+    ctx.set_users(users["room"], users["flags"], users["level"], 1)
+    st = ctx.write_batch(ops)
+    eoff, data, nd = port.write_batch(ops, users)
+    assert (st.off == eoff).all()
+    bad = np.nonzero(st.data != data)[0]
+    assert bad.size == 0, bad[:8]
+    ctx.close()
