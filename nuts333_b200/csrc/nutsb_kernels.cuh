@@ -1170,22 +1170,31 @@ __device__ __forceinline__ void nutsb_direct_block(const DirectArgs &A, u32 blk,
             u64 h1 = (q + 31) & ~(u64)31; if (h1 > b_end) h1 = b_end;
             const u32 tlen = seam ? (u32)(p - t0) : 0u, hlen = seam && h1 > q ? (u32)(h1 - q) : 0u;
             seam_bytes += tlen + hlen;
-            // every piece (< 32 bytes) is copied by the whole warp at once: one store request per piece
-            u32 m = __ballot_sync(NUTSB_FULL, tlen != 0);
-            while (m) {
-                const int i = __ffs((int)m) - 1; m &= m - 1;
-                const u32 len = __shfl_sync(NUTSB_FULL, tlen, i);
-                const u64 dpos = __shfl_sync(NUTSB_FULL, t0, i);
-                const u8 *src = (const u8 *)(size_t)__shfl_sync(NUTSB_FULL, (u64)(size_t)sa, i) - len;
-                if ((u32)lane < len) A.out[dpos + lane] = src[lane];
-            }
-            m = __ballot_sync(NUTSB_FULL, hlen != 0);
-            while (m) {
-                const int i = __ffs((int)m) - 1; m &= m - 1;
-                const u32 len = __shfl_sync(NUTSB_FULL, hlen, i);
-                const u64 dpos = __shfl_sync(NUTSB_FULL, q, i);
-                const u8 *src = (const u8 *)(size_t)__shfl_sync(NUTSB_FULL, (u64)(size_t)sb, i);
-                if ((u32)lane < len) A.out[dpos + lane] = src[lane];
+            // Every piece (< 32 bytes) is copied by the whole warp at once: one store request per piece.  All the
+            // loads first (into the render window, free until the renderer starts), then all the stores: a load
+            // and its store in one loop iteration would make every iteration wait a full trip to L2 / HBM.
+            u8 *const stage = s_on[warp];                      // event i: tail piece at [64 i, +32), head piece at [64 i + 32, +32)
+            const u32 lens = tlen | (hlen << 8);
+            if (__any_sync(NUTSB_FULL, lens != 0)) {
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
+                    const u32 l = __shfl_sync(NUTSB_FULL, lens, i);
+                    const u8 *pa = (const u8 *)(size_t)__shfl_sync(NUTSB_FULL, (u64)(size_t)sa, i) - (l & 0xffu);
+                    const u8 *pb = (const u8 *)(size_t)__shfl_sync(NUTSB_FULL, (u64)(size_t)sb, i);
+                    u8 va = 0, vb = 0;
+                    if ((u32)lane < (l & 0xffu)) va = pa[lane];
+                    if ((u32)lane < (l >> 8)) vb = pb[lane];
+                    stage[64 * i + lane] = va; stage[64 * i + 32 + lane] = vb;
+                }
+                __syncwarp();
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {
+                    const u32 l = __shfl_sync(NUTSB_FULL, lens, i);
+                    const u64 da = __shfl_sync(NUTSB_FULL, t0, i), db = __shfl_sync(NUTSB_FULL, q, i);
+                    if ((u32)lane < (l & 0xffu)) A.out[da + lane] = stage[64 * i + lane];
+                    if ((u32)lane < (l >> 8)) A.out[db + lane] = stage[64 * i + 32 + lane];
+                }
+                __syncwarp();
             }
         }
         // -- compact the warp's direct ops to lanes 0..cnt-1
