@@ -28,6 +28,17 @@ typedef uint8_t            u8;
 
 #define NUTSB_FULL 0xffffffffu
 
+// bring the 128-byte lines that hold [p, p+n) towards the SM ahead of their use (n <= 2048 + 3)
+#ifdef NUTSB_CPUSIM
+static inline void nutsb_prefetch(const void *, u32) {}
+#else
+__device__ __forceinline__ void nutsb_prefetch(const void *p, u32 n)
+{
+    const char *a = (const char *)((size_t)p & ~(size_t)127), *e = (const char *)p + n;
+    for (; a < e; a += 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+}
+#endif
+
 __device__ __forceinline__ void nutsb_add64(u64 *p, u64 v) { atomicAdd((unsigned long long *)p, (unsigned long long)v); }
 
 // recipients that do not simply take every op of their room: they go through nutsb_class_delivers

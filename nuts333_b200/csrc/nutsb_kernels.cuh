@@ -968,6 +968,7 @@ k_render(RenderArgs A)
             const u32 al = (u32)((size_t)src & 3);
             gw = (u64)(size_t)(src - al);
             nw = (al + n + 3) >> 2; if (!nw) nw = 1;            // an empty string still ends in a reset (c:1365)
+            nutsb_prefetch(src, n);                             // all 32 strings on their way before the first round
             meta = NUTSB_FLAT_META(al, n, A.ops.flags[op] | NUTSB_FL_COLOUR);
         }
         SlabSink sink{ A.slab + A.vp_on[gbase], A.slab + A.off_base + A.vp_off[gbase] };
@@ -1137,6 +1138,7 @@ __device__ __forceinline__ void nutsb_direct_block(const DirectArgs &A, u32 blk,
                 n = (u32)(A.ops.toff[op + 1] - t0);
                 al = (u32)((size_t)src & 3);
                 gw = (u64)(size_t)(src - al);
+                nutsb_prefetch(src, n);                         // on its way while the seams are done
                 fl = A.ops.flags[op] | ((cf & NUTSB_UF_COLOUR) ? NUTSB_FL_COLOUR : 0u);
                 osz = (u32)(q - p);
                 isw = true;
