@@ -555,8 +555,10 @@ struct PlanArgs {
 
 // The walk of one cell (tile t of the room, recipient ls of the room): counts its runs (FILL = false) or
 // writes them from A.runs[r_out] on (FILL = true).
+// `first`: index of the recipient's first event inside the tile -- found by binary search in the count pass
+// (FILL = false) and handed back to the fill pass.
 template <bool FILL>
-__device__ __forceinline__ u32 nutsb_plan_cell(const PlanArgs &A, u32 room, u32 t, u32 ls, u64 r_out, u32 &deliv)
+__device__ __forceinline__ u32 nutsb_plan_cell(const PlanArgs &A, u32 room, u32 t, u32 ls, u64 r_out, u32 &deliv, u32 &first)
 {
     const SlotInfo si = A.slots[(u32)A.pop.room_slot_off[room] + ls];
     const u32 b0 = si.b0, nb_room = si.nb_room;
@@ -565,11 +567,15 @@ __device__ __forceinline__ u32 nutsb_plan_cell(const PlanArgs &A, u32 room, u32 
     const u32 g0 = b0 + a0;
     const u32 e0 = si.e0, e1 = si.e1;
     // the recipient's events inside the tile: keys in [4*a0+1, 4*(a0+nb)] (a direct op before the tile's first
-    // slab op belongs to the tile before)
-    u32 l = e0, h = e1;
-    { const u32 thr = 4 * a0 + 1; while (l < h) { const u32 mid = (l + h) >> 1; if (A.sv_ukey[mid] < thr) l = mid + 1; else h = mid; } }
-    u32 l_end = l; h = e1;
-    { const u32 thr = 4 * (a0 + nb) + 1; while (l_end < h) { const u32 mid = (l_end + h) >> 1; if (A.sv_ukey[mid] < thr) l_end = mid + 1; else h = mid; } }
+    // slab op belongs to the tile before); the walk below stops at the first key beyond
+    u32 l = first;
+    if (!FILL) {
+        u32 h = e1; l = e0;
+        const u32 thr = 4 * a0 + 1;
+        while (l < h) { const u32 mid = (l + h) >> 1; if (A.sv_ukey[mid] < thr) l = mid + 1; else h = mid; }
+        first = l;
+    }
+    const u32 thr_end = 4 * (a0 + nb) + 1;
     const i32 k = si.k;
     const u32 cf = si.cf_lv & 0xffu, clv = si.cf_lv >> 8;
     const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
@@ -594,7 +600,11 @@ __device__ __forceinline__ u32 nutsb_plan_cell(const PlanArgs &A, u32 room, u32 
     u32 cur = 0;
     for (u32 e = l; ; ++e) {
         u32 j = nb, ek = NUTSB_EV_SKIP; i32 dlt = 0;
-        if (e < l_end) { const u32 uk = A.sv_ukey[e]; j = (uk >> 2) - a0; ek = uk & 3u; if (ek != NUTSB_EV_SKIP) dlt = A.sv_delta[e]; }
+        bool in_tile = false;                                 // event e lies in this tile
+        if (e < e1) {
+            const u32 uk = A.sv_ukey[e];
+            if (uk < thr_end) { in_tile = true; j = (uk >> 2) - a0; ek = uk & 3u; if (ek != NUTSB_EV_SKIP) dlt = A.sv_delta[e]; }
+        }
         if (full) {
             if (cur < j) {
                 const u64 v0 = vp[cur], v1 = vp[j];
@@ -602,7 +612,7 @@ __device__ __forceinline__ u32 nutsb_plan_cell(const PlanArgs &A, u32 room, u32 
                 if (v1 > v0) {
                     const u64 x0 = p, x1 = p + (v1 - v0), f0 = x0 & ~(u64)31;
                     const u64 xs = a_start <= f0 ? f0 : (first_seg ? x0 : (x0 + 31) & ~(u64)31);
-                    const u64 xe = (e >= l_end && last_tile) ? x1 : x1 & ~(u64)31;      // the stream's end is kept exact
+                    const u64 xe = (!in_tile && last_tile) ? x1 : x1 & ~(u64)31;        // the stream's end is kept exact
                     if (xs < xe) {
                         if (FILL) A.runs[r_out + nruns] = nutsb_run_pack(xs, sb + v0 + xs - x0, (u32)(xe - xs));
                         ++nruns;
@@ -628,7 +638,7 @@ __device__ __forceinline__ u32 nutsb_plan_cell(const PlanArgs &A, u32 room, u32 
                 }
             }
         }
-        if (e >= l_end) break;
+        if (!in_tile) break;
         // a direct op's bytes go here (k_direct writes them); excluded from op j: nothing emitted for it
         if (ek == NUTSB_EV_DIRECT) { p += (u64)(i64)dlt; cur = j; }
         else {
@@ -665,7 +675,8 @@ k_plan(PlanArgs A)
     const u32 t = local / chunks, ls = (local % chunks) * NUTSB_UCHUNK + (u32)tid;
     const bool valid = ls < users_r;
     u32 deliv = 0;
-    const u32 n = valid ? nutsb_plan_cell<false>(A, room, t, ls, 0, deliv) : 0u;
+    u32 first = 0;
+    const u32 n = valid ? nutsb_plan_cell<false>(A, room, t, ls, 0, deliv, first) : 0u;
     u32 inc = n;
     for (int d = 1; d < 32; d <<= 1) { const u32 x = __shfl_up_sync(NUTSB_FULL, inc, d); if (lane >= d) inc += x; }
     if (lane == 31) s_w[warp] = inc;
@@ -677,8 +688,8 @@ k_plan(PlanArgs A)
     __syncthreads();
     const u32 base = s_base;
     deliv = 0;
-    if (valid && n) (void)nutsb_plan_cell<true>(A, room, t, ls, (u64)base + before + inc - n, deliv);
-    else if (valid) (void)nutsb_plan_cell<false>(A, room, t, ls, 0, deliv);      // deliveries of zero-length renderings
+    if (valid && n) (void)nutsb_plan_cell<true>(A, room, t, ls, (u64)base + before + inc - n, deliv, first);
+    else if (valid) (void)nutsb_plan_cell<false>(A, room, t, ls, 0, deliv, first);      // deliveries of zero-length renderings
     if (tid == 0) {
         const u32 b0 = A.geo.room_b_off[room], nb_room = A.geo.room_b_off[room + 1] - b0;
         const u32 a0 = t * NUTSB_TILE_OPS;
