@@ -381,37 +381,58 @@ def run_ours(args):
 
     bt, bo, st_, so_, nt_, no_ = (pin(a) for a in (bt, bo, st_, so_, nt_, no_))
     hops = {k: (pin(v) if isinstance(v, np.ndarray) else v) for k, v in ops.items()}
-    e2e_h2d_ms, e2e_d2h_ms = 0.0, 0.0
-    e2e_ms, e2e_deliv, h2d, d2h = 0.0, 0, 0, 0
+    def e2e_leg(iov):
+        """One leg through the host-buffer entry points: verdict batches, then nutsb_write_batch (streams in
+        pinned host memory) or nutsb_write_batch_iov (gather lists into the pool of renderings)."""
+        r = dict(h2d_ms=0.0, d2h_ms=0.0, ms=0.0, deliv=0, h2d=0, d2h=0, extra={})
+        for i in range(1 + e2e_steps):                     # first pass allocates the pinned result buffers
+            barrier()
+            t0 = time.perf_counter()
+            v = ctx.contains_swearing_batch(bt, bo)
+            vs = ctx.site_banned_batch(st_, so_)
+            vu = ctx.user_banned_batch(nt_, no_)
+            keep = []
+            o = ctx._ops_struct(dict(hops, verdict=v), keep)
+            if iov:
+                s = api._IovStreams()
+                ctx._ck(ctx.lib.nutsb_write_batch_iov(ctx._h, o, s))
+                touch = int(np.ctypeslib.as_array(api.C.cast(s.pool, api.u8p), shape=(16,))[0])      # touch the result
+                touch += int(np.ctypeslib.as_array(api.C.cast(s.iov, api.u64p), shape=(2,))[1])
+                out_bytes = int(s.pool_bytes) + 16 * int(s.n_iov) + 12 * N_USERS
+            else:
+                s = api._Streams()
+                ctx._ck(ctx.lib.nutsb_write_batch(ctx._h, o, s))
+                touch = int(np.ctypeslib.as_array(api.C.cast(s.bytes, api.u8p), shape=(16,))[0])
+                out_bytes = int(s.total_bytes)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if i == 0 and iov:
+                # outside the timed passes: the lists describe every byte of every stream
+                lens = np.ctypeslib.as_array(api.C.cast(s.iov, api.u64p), shape=(int(s.n_iov), 2))[:, 1]
+                assert int(lens.sum()) == int(s.total_bytes), "gather lists do not add up to the streams"
+                r["extra"] = dict(pool_bytes=int(s.pool_bytes), n_iov=int(s.n_iov), stream_bytes=int(s.total_bytes))
+            if i > 0:
+                tt = ctx.timing()
+                r["h2d_ms"] += float(tt.h2d_ms); r["d2h_ms"] += float(tt.d2h_ms)
+                r["ms"] += dt * 1e3; r["deliv"] += int(s.n_deliveries)
+                r["h2d"] = int(bt.nbytes + bo.nbytes + st_.nbytes + so_.nbytes + nt_.nbytes + no_.nbytes + ops["text"].nbytes
+                               + ops["off"].nbytes + 2 * n_ops + 12 * n_ops + v.nbytes)
+                r["d2h"] = out_bytes + 8 * (N_USERS + 1) + v.nbytes + vs.nbytes + vu.nbytes
+        return r
+
     e2e_steps = max(1, min(args.steps, 3))
-    for i in range(0 if args.no_e2e else 1 + e2e_steps):   # first pass allocates the pinned result buffers
-        barrier()
-        t0 = time.perf_counter()
-        v = ctx.contains_swearing_batch(bt, bo)
-        vs = ctx.site_banned_batch(st_, so_)
-        vu = ctx.user_banned_batch(nt_, no_)
-        keep = []
-        o = ctx._ops_struct(dict(hops, verdict=v), keep)
-        s = api._Streams()
-        ctx._ck(ctx.lib.nutsb_write_batch(ctx._h, o, s))
-        first = int(np.ctypeslib.as_array(api.C.cast(s.bytes, api.u8p), shape=(16,))[0])     # touch the result
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if i > 0:
-            tt = ctx.timing()
-            e2e_h2d_ms += float(tt.h2d_ms); e2e_d2h_ms += float(tt.d2h_ms)
-            e2e_ms += dt * 1e3; e2e_deliv += int(s.n_deliveries)
-            h2d = int(bt.nbytes + bo.nbytes + st_.nbytes + so_.nbytes + nt_.nbytes + no_.nbytes + ops["text"].nbytes
-                      + ops["off"].nbytes + 2 * n_ops + 12 * n_ops + v.nbytes)
-            d2h = int(s.total_bytes) + 8 * (N_USERS + 1) + v.nbytes + vs.nbytes + vu.nbytes
+    zero = dict(h2d_ms=0.0, d2h_ms=0.0, ms=0.0, deliv=0, h2d=0, d2h=0, extra={})
+    leg_s = zero if args.no_e2e else e2e_leg(False)
+    leg_v = zero if args.no_e2e else e2e_leg(True)
+    e2e_h2d_ms, e2e_d2h_ms, e2e_ms, e2e_deliv, h2d, d2h = (leg_s[k] for k in ("h2d_ms", "d2h_ms", "ms", "deliv", "h2d", "d2h"))
     # ---- reduce over ranks
-    vals = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
-    sums = torch.tensor([dev_state["deliv"], e2e_deliv, dev_state["launches"]], dtype=torch.float64, device=dev)
+    vals = torch.tensor([ms, e2e_ms, leg_v["ms"]], dtype=torch.float64, device=dev)
+    sums = torch.tensor([dev_state["deliv"], e2e_deliv, dev_state["launches"], leg_v["deliv"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max = float(vals[0]), float(vals[1])
-    total_deliv, total_e2e_deliv, total_launch = float(sums[0]), float(sums[1]), int(sums[2])
+    ms_max, e2e_ms_max, iov_ms_max = float(vals[0]), float(vals[1]), float(vals[2])
+    total_deliv, total_e2e_deliv, total_launch, total_iov_deliv = float(sums[0]), float(sums[1]), int(sums[2]), float(sums[3])
 
     if rank == 0:
         peaks = {}
@@ -459,6 +480,15 @@ def run_ours(args):
                               write_batch_h2d_ms=e2e_h2d_ms / e2e_steps, write_batch_d2h_ms=e2e_d2h_ms / e2e_steps,
                               host_memory="pinned (inputs: caller's pinned buffers; streams: the library's pinned buffer)")),
                     gpu_launches=total_launch, clocks=clk)
+        if not args.no_e2e:
+            # the same step with gather lists as the result (nutsb_write_batch_iov): what a host that writev()s needs.
+            # Reported beside `e2e`, which stays the full per-recipient streams.
+            line["e2e_iov"] = dict(value=total_iov_deliv / (iov_ms_max * 1e-3), unit=UNIT, h2d_bytes_per_step=leg_v["h2d"],
+                                   d2h_bytes_per_step=leg_v["d2h"], steps=e2e_steps, ms_per_step=iov_ms_max / e2e_steps,
+                                   write_batch_h2d_ms=leg_v["h2d_ms"] / e2e_steps, write_batch_d2h_ms=leg_v["d2h_ms"] / e2e_steps,
+                                   result="per-user struct iovec lists into one pinned pool: every room op rendered once per "
+                                          "colour setting + every write_user op rendered once; byte-identical to `e2e`'s streams "
+                                          "when gathered (tests/test_iov.py)", **leg_v["extra"])
         if world == 1 and not args.no_cpu_baseline:
             procs = 1
             dcpu, nbytes, busy, wall, kind = reference_step(0, 40_000, 4_000, procs)

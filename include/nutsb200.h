@@ -205,6 +205,33 @@ int nutsb_write_batch(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_streams *out);
  * one at or after its last (true of any buffer that starts a cudaMalloc allocation, whatever its length). */
 int nutsb_write_batch_dev(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_streams *out);
 
+/* The same streams as gather lists, for a host that hands them to writev(2).  The reference writes the
+ * same rendered bytes to every listener of a room (write_room_except's loop, c:1409-1428, calls write_user
+ * per recipient); here they cross PCIe once per colour setting instead of once per recipient.  User u's
+ * stream is the concatenation of iov[first[u]] .. iov[first[u] + count[u] - 1] (zero-length pieces
+ * occur); every piece points into `pool`, pinned host memory owned by the context:
+ *     writev(user->socket, (const struct iovec *)(s.iov + s.first[u]), s.count[u]);   (in chunks of IOV_MAX)
+ * nutsb_iovec has the layout of struct iovec on LP64.  Concatenated, the pieces are byte for byte the
+ * stream nutsb_write_batch returns for u (off[] is the same array).  pool = every room / level op
+ * rendered once per colour setting + every write_user op rendered once for its recipient.  With
+ * recipients behind a filter (login / ignall / ignshout users, write_level ops in the batch) the pool is
+ * the full streams and every user has one piece: same result, no saving.  Valid until the next write
+ * batch / flush / destroy on the context. */
+typedef struct nutsb_iovec { const void *base; size_t len; } nutsb_iovec;
+typedef struct nutsb_iov_streams {
+    int64_t            n_users;
+    uint64_t           total_bytes;    /* sum of all streams                                 */
+    uint64_t           n_deliveries;
+    const uint64_t    *off;            /* n_users + 1: off[u+1] - off[u] = length of u's stream */
+    const uint64_t    *first;          /* n_users                                            */
+    const uint32_t    *count;          /* n_users                                            */
+    const nutsb_iovec *iov;
+    uint64_t           n_iov;
+    const uint8_t     *pool;
+    uint64_t           pool_bytes;     /* bytes brought back from the device                 */
+} nutsb_iov_streams;
+int nutsb_write_batch_iov(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_iov_streams *out);
+
 /* contains_swearing / site_banned / user_banned over n packed strings
  * (bytes + off[n+1]); verdict[n] gets 0/1.  *_dev: device pointers. */
 int nutsb_contains_swearing_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes,

@@ -56,6 +56,12 @@ class _Streams(C.Structure):
                 ("off", C.c_void_p), ("bytes", C.c_void_p), ("on_device", C.c_int32)]
 
 
+class _IovStreams(C.Structure):
+    _fields_ = [("n_users", C.c_int64), ("total_bytes", C.c_uint64), ("n_deliveries", C.c_uint64),
+                ("off", C.c_void_p), ("first", C.c_void_p), ("count", C.c_void_p), ("iov", C.c_void_p),
+                ("n_iov", C.c_uint64), ("pool", C.c_void_p), ("pool_bytes", C.c_uint64)]
+
+
 class Timing(C.Structure):
     _fields_ = [("plan_ms", C.c_float), ("render_ms", C.c_float), ("fanout_ms", C.c_float), ("direct_ms", C.c_float),
                 ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
@@ -67,7 +73,7 @@ class Timing(C.Structure):
 EXPORTS = [
     "nutsb_version", "nutsb_strerror", "nutsb_last_error", "nutsb_create", "nutsb_destroy",
     "nutsb_set_profiling", "nutsb_get_timing", "nutsb_set_overlap", "nutsb_set_stream", "nutsb_set_swear_words",
-    "nutsb_set_ban_files", "nutsb_ban_edit", "nutsb_get_ban_file", "nutsb_set_users", "nutsb_set_clones", "nutsb_set_remotes", "nutsb_set_room_names", "nutsb_write_batch", "nutsb_write_batch_dev",
+    "nutsb_set_ban_files", "nutsb_ban_edit", "nutsb_get_ban_file", "nutsb_set_users", "nutsb_set_clones", "nutsb_set_remotes", "nutsb_set_room_names", "nutsb_write_batch", "nutsb_write_batch_dev", "nutsb_write_batch_iov",
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
     "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_q_speech",
@@ -103,6 +109,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_set_users.argtypes = [vp, C.c_int32, C.c_int32, i32p, u8p, u8p]
     lib.nutsb_write_batch.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_Streams)]
     lib.nutsb_write_batch_dev.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_Streams)]
+    lib.nutsb_write_batch_iov.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_IovStreams)]
     for name in ("contains_swearing", "site_banned", "user_banned"):
         getattr(lib, f"nutsb_{name}_batch").argtypes = [vp, C.c_int64, vp, vp, vp]
         getattr(lib, f"nutsb_{name}_batch_dev").argtypes = [vp, C.c_int64, vp, vp, vp]
@@ -187,6 +194,42 @@ class Streams:
 
     def user(self, u) -> bytes:
         return self.data[int(self.off[u]):int(self.off[u + 1])].tobytes()
+
+
+class IovStreams:
+    """Per-user gather lists returned by nutsb_write_batch_iov: what a host hands to writev(2).  The pieces
+    point into the context's pinned pool, so this object is valid until the next batch on the context;
+    user(u) / streams() gather the bytes a socket would receive."""
+
+    def __init__(self, off, first, count, iov, pool_addr, pool_bytes, n_deliveries, raw=None):
+        self.off, self.first, self.count, self.iov = off, first, count, iov      # iov: u64[n_iov, 2] = (address, length)
+        self.pool_addr, self.pool_bytes, self.n_deliveries = int(pool_addr), int(pool_bytes), int(n_deliveries)
+        self.raw = raw
+
+    @property
+    def n_users(self):
+        return len(self.first)
+
+    @property
+    def n_iov(self):
+        return len(self.iov)
+
+    @property
+    def total_bytes(self):
+        return int(self.off[-1]) if len(self.off) else 0
+
+    def pieces(self, u):
+        f, c = int(self.first[u]), int(self.count[u])
+        return self.iov[f:f + c]
+
+    def user(self, u) -> bytes:
+        return b"".join(C.string_at(int(a), int(n)) for a, n in self.pieces(u) if n)
+
+    def streams(self) -> "Streams":
+        """The same result as nutsb_write_batch would return (gathered on the host)."""
+        parts = [self.user(u) for u in range(self.n_users)]
+        data = np.frombuffer(b"".join(parts), np.uint8)
+        return Streams(self.off.copy(), data, self.n_deliveries)
 
 
 class Context:
@@ -319,6 +362,19 @@ class Context:
         st = _Streams()
         self._ck(self.lib.nutsb_write_batch(self._h, C.byref(o), C.byref(st)))
         return self._host_streams(st)
+
+    def write_batch_iov(self, ops) -> IovStreams:
+        """write_batch with gather lists as the result (nutsb_write_batch_iov)."""
+        keep = []
+        o = self._ops_struct(ops, keep)
+        st = _IovStreams()
+        self._ck(self.lib.nutsb_write_batch_iov(self._h, C.byref(o), C.byref(st)))
+        U, n = int(st.n_users), int(st.n_iov)
+        off = np.ctypeslib.as_array(C.cast(st.off, u64p), shape=(U + 1,)).copy()
+        first = np.ctypeslib.as_array(C.cast(st.first, u64p), shape=(max(U, 1),))[:U].copy()
+        count = np.ctypeslib.as_array(C.cast(st.count, C.POINTER(C.c_uint32)), shape=(max(U, 1),))[:U].copy()
+        iov = (np.ctypeslib.as_array(C.cast(st.iov, u64p), shape=(n, 2)).copy() if n else np.zeros((0, 2), np.uint64))
+        return IovStreams(off, first, count, iov, st.pool or 0, st.pool_bytes, st.n_deliveries, raw=st)
 
     def _host_streams(self, st) -> Streams:
         U = int(st.n_users)

@@ -1078,6 +1078,7 @@ struct DirectArgs {
     const u8 *slab; u64 off_base;   // the rendered slab (k_render): source of the seam bytes
     u32 has_level;
     const SlotInfo *slots;
+    const u64 *dpre;                // gather-list mode (k_direct_compact): event e's rendering goes to out + dpre[e]
 };
 
 #define NUTSB_DIRECT_THREADS 256
@@ -1112,7 +1113,10 @@ struct DirectSink {                 // string q's rendering is bytes [O, O + osz
 #define NUTSB_DIR_WARPS (NUTSB_DIRECT_THREADS / 32)
 #define NUTSB_DIR_SMEM  (NUTSB_DIR_WARPS * (NUTSB_REN_ON_WIN + 64) + NUTSB_DIR_WARPS * 32 * (8 + 8 + 8) + ((NUTSB_CODETAB_BYTES + 15) & ~15))
 
-// the work of block `blk` of `nblk` (grid-strided over the events), smem = NUTSB_DIR_SMEM bytes
+// the work of block `blk` of `nblk` (grid-strided over the events), smem = NUTSB_DIR_SMEM bytes.
+// COMPACT (gather-list mode, nutsb_write_batch_iov): the renderings are packed one after the other in event
+// order (out + dpre[e]) instead of going to their places in the streams, and there are no seams to write.
+template <bool COMPACT>
 __device__ __forceinline__ void nutsb_direct_block(const DirectArgs &A, u32 blk, u32 nblk, u8 *smem)
 {
     typedef u8 OnWin[NUTSB_REN_ON_WIN + 64];
@@ -1157,7 +1161,8 @@ __device__ __forceinline__ void nutsb_direct_block(const DirectArgs &A, u32 blk,
             // -- seam: the event is a discontinuity in a plain listener's stream.  k_fanout's runs cover whole
             //    32-byte sectors only; the slab bytes that share a sector with the discontinuity -- the end of the
             //    stretch before it and the start of the stretch after it -- are written here, together.
-            seam = !A.has_level && !(cf & NUTSB_UF_FILTERED);
+            seam = !COMPACT && !A.has_level && !(cf & NUTSB_UF_FILTERED);
+            if (COMPACT && isw) p = A.dpre[e];                  // (q - p was taken above)
             if (seam) {
                 const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
                 const u64 *vp = colour ? A.cpx.vp_on : A.cpx.vp_off;
@@ -1174,7 +1179,7 @@ __device__ __forceinline__ void nutsb_direct_block(const DirectArgs &A, u32 blk,
                 sb = R + vp[b0 + j + skip];                    // after an exclusion the stream goes on with op j+1
             }
         }
-        {
+        if (!COMPACT) {
             // the neighbouring events of the same recipient sit in the neighbouring lanes
             const u64 q_prev = __shfl_up_sync(NUTSB_FULL, q, 1), p_next = __shfl_down_sync(NUTSB_FULL, p, 1);
             if (seam && !first_ev && lane > 0) a_start = q_prev;
@@ -1247,7 +1252,14 @@ __global__ void __launch_bounds__(NUTSB_DIRECT_THREADS, NUTSB_DIR_MINBLOCKS)
 k_direct(DirectArgs A)
 {
     NUTSB_DYN_SMEM(s_dyn);
-    nutsb_direct_block(A, blockIdx.x, gridDim.x, s_dyn);
+    nutsb_direct_block<false>(A, blockIdx.x, gridDim.x, s_dyn);
+}
+
+__global__ void __launch_bounds__(NUTSB_DIRECT_THREADS, NUTSB_DIR_MINBLOCKS)
+k_direct_compact(DirectArgs A)
+{
+    NUTSB_DYN_SMEM(s_dyn);
+    nutsb_direct_block<true>(A, blockIdx.x, gridDim.x, s_dyn);
 }
 
 // ---- H+I in one launch ---------------------------------------------------------------------
@@ -1266,7 +1278,7 @@ k_fanout_direct(FanoutArgs F, DirectArgs D, u32 n_dir, u32 stride)
 {
     NUTSB_DYN_SMEM(s_dyn);
     const u32 b = blockIdx.x;
-    if (b % stride == 0 && b / stride < n_dir) { nutsb_direct_block(D, b / stride, n_dir, s_dyn); return; }
+    if (b % stride == 0 && b / stride < n_dir) { nutsb_direct_block<false>(D, b / stride, n_dir, s_dyn); return; }
     const u32 before = (b + stride - 1) / stride;          // direct blocks with a smaller index
     nutsb_fanout_block(F, b - (before < n_dir ? before : n_dir), s_dyn);
 }
@@ -1313,13 +1325,14 @@ struct Sizes {                   // read back by the host before the fan-out is 
     u64 cells;
     u64 slab_on, slab_off;       // bytes of the slab's two renderings
     u32 n_slab, n_events, items, tiles;
+    u64 direct_bytes;            // gather-list mode: bytes of the direct ops' renderings
 };
 
 // Per room: tiles, (tile, recipient) cells and fan-out work items; exclusive
 // prefixes over rooms.  One block.
 __global__ void __launch_bounds__(NUTSB_SCAN_THREADS)
 k_geometry(PopView pop, const u32 *room_b_off, const u64 *stream_off, const u32 *counts, const u64 *vp_on, const u64 *vp_off,
-           u32 *room_tile_off, u64 *room_cell_off, u32 *room_item_off, Sizes *sz)
+           u32 *room_tile_off, u64 *room_cell_off, u32 *room_item_off, Sizes *sz, const u64 *dpre)
 {
     u64 c_tiles = 0, c_cells = 0, c_items = 0;
     const i32 rt = pop.n_rooms_tot;
@@ -1350,5 +1363,83 @@ k_geometry(PopView pop, const u32 *room_b_off, const u64 *stream_off, const u32 
         sz->cells = c_cells; sz->n_slab = counts[0]; sz->n_events = counts[1];
         sz->items = (u32)c_items; sz->tiles = (u32)c_tiles;
         sz->slab_on = vp_on[counts[0]]; sz->slab_off = vp_off[counts[0]];
+        sz->direct_bytes = dpre ? dpre[counts[1]] : 0;
     }
+}
+
+// ---- gather lists (nutsb_write_batch_iov) ---------------------------------------------------
+// A plain listener's stream is its room's slab in its colour setting, cut at its own events.  Instead of
+// copying those bytes once per recipient (k_fanout), hand the host the slab itself (two renderings), the
+// direct ops' renderings packed in event order (k_direct_compact) and, per recipient, the list of pieces:
+// for every event the slab stretch before it and the direct op's rendering, then the stretch after the
+// last event -- 2 * events + 1 entries, zero-length ones included so that every index is known up front
+// (slot s, event e: entries 2e + s and 2e + 1 + s; the tail: 2 * e1 + s).  Entries are {address, length}
+// in the HOST's copy of the pool: struct iovec as writev(2) takes it.
+struct InDirectLen {                // bytes of sorted event e's direct rendering (0 for a pure exclusion)
+    const u32 *sv_ukey, *sv_slot; const i32 *sv_delta; const SlotInfo *slots; const u64 *vp_on, *vp_off;
+    __device__ u64 operator()(i64 e) const
+    {
+        const u32 uk = sv_ukey[e], ek = uk & 3u;
+        if (ek == NUTSB_EV_SKIP) return 0;
+        i64 d = sv_delta[e];                                // direct length minus the excluded op's
+        if (ek == NUTSB_EV_REPLACE) {
+            const SlotInfo *si = slots + sv_slot[e];
+            const u64 *vp = (si->cf_lv & NUTSB_UF_COLOUR) ? vp_on : vp_off;
+            const u32 g = si->b0 + (uk >> 2);
+            d += (i64)(vp[g + 1] - vp[g]);
+        }
+        return (u64)d;
+    }
+};
+
+struct __align__(16) IovEnt { u64 base, len; };    // struct iovec (LP64)
+__device__ __forceinline__ IovEnt nutsb_iov_ent(u64 base, u64 len) { IovEnt x; x.base = base; x.len = len; return x; }
+
+struct IovArgs {
+    PopView pop; const SlotInfo *slots;
+    const u64 *vp_on, *vp_off;
+    const u32 *sv_ukey, *sv_slot; const u64 *dpre;
+    u32 n_ev;
+    u64 host_pool;                  // address of the pool in host memory
+    u64 off_base, dir_base;         // pool offsets of the colour-off slab and of the direct renderings
+    IovEnt *iov; u64 *first; u32 *count;
+    u64 *deliveries;
+};
+
+__global__ void __launch_bounds__(256)
+k_iov(IovArgs A)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    i64 deliv = 0;
+    if (t < A.n_ev) {
+        const u32 e = t, s = A.sv_slot[e];
+        const SlotInfo si = A.slots[s];
+        const bool colour = (si.cf_lv & NUTSB_UF_COLOUR) != 0;
+        const u64 *vp = (colour ? A.vp_on : A.vp_off) + si.b0;
+        const u64 R = A.host_pool + (colour ? 0 : A.off_base);
+        const u32 uk = A.sv_ukey[e], j = uk >> 2, skip = (uk & 3u) != NUTSB_EV_DIRECT;
+        u32 jp = 0;                                         // slab rank the stretch before the event starts at
+        if (e != si.e0) { const u32 ukp = A.sv_ukey[e - 1]; jp = (ukp >> 2) + ((ukp & 3u) != NUTSB_EV_DIRECT); }
+        const u64 v0 = vp[jp], v1 = vp[j];
+        const u64 d0 = A.dpre[e], d1 = A.dpre[e + 1];
+        const u64 i0 = 2ull * e + s;
+        A.iov[i0] = nutsb_iov_ent(R + v0, v1 - v0);
+        A.iov[i0 + 1] = nutsb_iov_ent(A.host_pool + A.dir_base + d0, d1 - d0);
+        if (e + 1 == si.e1) { const u64 w0 = vp[j + skip]; A.iov[i0 + 2] = nutsb_iov_ent(R + w0, vp[si.nb_room] - w0); }
+        deliv -= (i64)skip;
+    }
+    if (t < (u32)A.pop.n_users) {
+        const u32 s = t;
+        const SlotInfo si = A.slots[s];
+        const i32 u = A.pop.slot_user[s];
+        A.first[u] = 2ull * si.e0 + s; A.count[u] = 2u * (si.e1 - si.e0) + 1u;
+        if (si.e0 == si.e1) {
+            const bool colour = (si.cf_lv & NUTSB_UF_COLOUR) != 0;
+            const u64 *vp = (colour ? A.vp_on : A.vp_off) + si.b0;
+            A.iov[2ull * si.e0 + s] = nutsb_iov_ent(A.host_pool + (colour ? 0 : A.off_base) + vp[0], vp[si.nb_room] - vp[0]);
+        }
+        deliv += (i64)si.nb_room;                           // every slab op of the room but the ones it is excluded from
+    }
+    for (int d = 16; d; d >>= 1) deliv += __shfl_xor_sync(NUTSB_FULL, deliv, d);
+    if ((threadIdx.x & 31) == 0 && deliv) nutsb_add64(A.deliveries, (u64)deliv);
 }

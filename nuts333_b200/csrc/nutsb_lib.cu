@@ -86,7 +86,8 @@ struct nutsb_ctx {
     DBuf d_room_tile_off, d_room_cell_off, d_room_item_off, d_sizes, d_counters;
     DBuf d_runs, d_items, d_slab, d_bl_meta, d_slots;
     DBuf d_off, d_out, d_digest, d_ulen;
-    HBuf h_small, h_off, h_out;
+    DBuf d_dpre, d_dir, d_iov, d_iov_first, d_iov_cnt;           // gather-list mode (nutsb_write_batch_iov)
+    HBuf h_small, h_off, h_out, h_iov, h_iov_first, h_iov_cnt;
     u64 last_total = 0; bool have_streams = false;
 
     // staging for the host-buffer entry points
@@ -362,12 +363,14 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
         &c->d_sv_delta, &c->d_sv_op, &c->d_sv_pre, &c->d_ev_off, &c->d_vp_on, &c->d_vp_off, &c->d_cp,
         &c->d_room_tile_off, &c->d_room_cell_off, &c->d_room_item_off, &c->d_sizes, &c->d_counters,
         &c->d_runs, &c->d_slots, &c->d_items, &c->d_slab, &c->d_bl_meta, &c->d_off, &c->d_out, &c->d_digest, &c->d_ulen,
+        &c->d_dpre, &c->d_dir, &c->d_iov, &c->d_iov_first, &c->d_iov_cnt,
         &c->s_text, &c->s_toff, &c->s_kind, &c->s_target, &c->s_except, &c->s_flags, &c->s_gate, &c->s_verdict, &c->s_v8,
         &c->d_names, &c->d_name_off, &c->d_sflags, &c->d_lit, &c->d_lit_off, &c->d_sp_len, &c->d_sp_off, &c->d_sp_text,
         &c->d_sp_kind, &c->d_sp_target, &c->d_sp_except, &c->d_sp_flags, &c->d_sp_gate, &c->d_sp_verdict,
         &c->s_verb, &c->s_speaker, &c->s_body, &c->s_boff };
     for (DBuf *b : all) release(*b);
     release(c->h_small); release(c->h_off); release(c->h_out);
+    release(c->h_iov); release(c->h_iov_first); release(c->h_iov_cnt);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->dep) if (e) cudaEventDestroy(e);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
@@ -650,7 +653,15 @@ static int status_to_error(nutsb_ctx *c, u32 st)
     return NUTSB_OK;
 }
 
-static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
+// Gather-list request (nutsb_write_batch_iov): when every recipient is a plain listener the fan-out is
+// skipped altogether: `compact` comes back true and the pool (slab + direct renderings) and the lists are
+// left in HBM for the caller to bring over; otherwise the streams are made as usual (compact = false).
+struct IovReq {
+    bool compact = false;
+    u64 slab_span = 0, dir_base = 0, direct_bytes = 0, n_iov = 0;    // pool = [slab | direct renderings]
+};
+
+static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovReq *iv = nullptr)
 {
     if (!c->have_users) return fail(c, NUTSB_E_STATE, "nutsb_set_users has not been called%s");
     const i64 n = o->n_ops;
@@ -812,19 +823,25 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     TRY(ensure(c, c->d_ulen, ((size_t)U + 1) * 8));
     if (U > 0) { NUTSB_LAUNCH(cdiv((u64)U, 128), 128, st, k_user_len, uli, (i64)U, c->d_ulen.as<u64>()); CKL(); c->tm.launches++; }
     TRY(run_scan(c, InU64{c->d_ulen.as<u64>()}, OutU64{c->d_off.as<u64>()}, (i64)U, nullptr));
-    TRY(ensure(c, c->d_room_tile_off, ((size_t)Rt + 2) * 4)); TRY(ensure(c, c->d_room_cell_off, ((size_t)Rt + 2) * 8));
-    TRY(ensure(c, c->d_room_item_off, ((size_t)Rt + 2) * 4));
-    NUTSB_LAUNCH(1, NUTSB_SCAN_THREADS, st, k_geometry, pop, c->d_room_b_off.as<u32>(), c->d_off.as<u64>(), counts,
-                 c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(),
-                 c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>(), c->d_sizes.as<Sizes>()); CKL();
-    c->tm.launches++;
-
     TRY(ensure(c, c->d_slots, ((size_t)U + 1) * sizeof(SlotInfo)));
     if (U > 0) {
         SlotInfoArgs sa{ pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), c->d_slots.as<SlotInfo>() };
         NUTSB_LAUNCH(cdiv((u64)U, 128), 128, st, k_slot_info, sa); CKL();
         c->tm.launches++;
     }
+    const bool compact = iv && alias && U > 0;                 // gather lists: plain listeners only
+    if (compact) {                                             // where each direct rendering goes in the pool
+        TRY(ensure(c, c->d_dpre, (E + 2) * 8));
+        TRY(run_scan(c, InDirectLen{ c->d_sv_ukey.as<u32>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_slots.as<SlotInfo>(),
+                                     c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>() }, OutU64{c->d_dpre.as<u64>()}, (i64)E, counts + 1));
+    }
+    TRY(ensure(c, c->d_room_tile_off, ((size_t)Rt + 2) * 4)); TRY(ensure(c, c->d_room_cell_off, ((size_t)Rt + 2) * 8));
+    TRY(ensure(c, c->d_room_item_off, ((size_t)Rt + 2) * 4));
+    NUTSB_LAUNCH(1, NUTSB_SCAN_THREADS, st, k_geometry, pop, c->d_room_b_off.as<u32>(), c->d_off.as<u64>(), counts,
+                 c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(),
+                 c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>(), c->d_sizes.as<Sizes>(),
+                 compact ? c->d_dpre.as<u64>() : (const u64 *)nullptr); CKL();
+    c->tm.launches++;
 
     // -- read-back #2: sizes
     Sizes *hs = (Sizes *)(c->h_small.as<u8>() + 256);
@@ -832,6 +849,52 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     CK(cudaStreamSynchronize(st));
     const Sizes sz = *hs;
     if (sz.slab_on != slab_on || sz.slab_off != slab_off) return fail(c, NUTSB_E_CUDA, "internal: slab size mismatch%s");
+    if (compact) {
+        // -- gather lists instead of streams: direct ops rendered one after the other (k_direct_compact), one
+        //    list entry per stretch of slab bytes and per direct rendering (k_iov); no copy plan, no fan-out
+        iv->compact = true;
+        iv->slab_span = off_base + slab_off;
+        iv->dir_base = (iv->slab_span + 15) & ~(u64)15;
+        iv->direct_bytes = sz.direct_bytes;
+        iv->n_iov = 2ull * sz.n_events + (u64)U;
+        TRY(ensure(c, c->d_dir, sz.direct_bytes + 64));
+        TRY(ensure(c, c->d_iov, (size_t)iv->n_iov * sizeof(IovEnt)));
+        TRY(ensure(c, c->d_iov_first, (size_t)U * 8)); TRY(ensure(c, c->d_iov_cnt, (size_t)U * 4));
+        TRY(ensure_host(c, c->h_out, (size_t)(iv->dir_base + sz.direct_bytes) + 64));      // its address goes into the entries
+        if (c->profiling) { CK(cudaEventRecord(c->ev[9], st)); }
+        if (sz.n_events > 0) {
+            DirectArgs da{ ops, pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_op.as<u32>(),
+                           c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_dir.as<u8>(), (i64)sz.n_events, counters,
+                           c->d_status.as<u32>(), c->d_slab.as<u8>(), off_base, 0u, c->d_slots.as<SlotInfo>(), c->d_dpre.as<u64>() };
+            NUTSB_LAUNCH_SMEM(cdiv(sz.n_events, NUTSB_DIRECT_THREADS), NUTSB_DIRECT_THREADS, NUTSB_DIR_SMEM, st, k_direct_compact, da); CKL();
+            c->tm.launches++;
+        }
+        if (c->profiling) { CK(cudaEventRecord(c->ev[3], st)); CK(cudaEventRecord(c->ev[10], st)); }
+        IovArgs ia{ pop, c->d_slots.as<SlotInfo>(), c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(), c->d_sv_ukey.as<u32>(), sv_slot,
+                    c->d_dpre.as<u64>(), sz.n_events, (u64)(size_t)c->h_out.p, off_base, iv->dir_base,
+                    c->d_iov.as<IovEnt>(), c->d_iov_first.as<u64>(), c->d_iov_cnt.as<u32>(), counters };
+        NUTSB_LAUNCH(cdiv(std::max<u64>(sz.n_events, (u64)U), 256), 256, st, k_iov, ia); CKL();
+        c->tm.launches++;
+        if (c->profiling) CK(cudaEventRecord(c->ev[2], st));
+        if (par) CK(cudaStreamWaitEvent(st, c->dep[1], 0));    // the slab is rendered
+        if (c->profiling) CK(cudaEventRecord(c->ev[11], st));
+        CK(cudaMemcpyAsync(h64 + 8, counters, 24, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        TRY(status_to_error(c, h32[4]));
+        c->last_total = sz.total_bytes; c->have_streams = false;     // no streams in HBM (nutsb_stream_digests needs them)
+        if (c->profiling) {
+            CK(cudaEventElapsedTime(&c->tm.plan_ms, c->ev[0], c->ev[9]));
+            CK(cudaEventElapsedTime(&c->tm.render_ms, c->ev[1], c->ev[8]));
+            CK(cudaEventElapsedTime(&c->tm.fanout_ms, c->ev[10], c->ev[2]));
+            CK(cudaEventElapsedTime(&c->tm.direct_ms, c->ev[9], c->ev[3]));
+            CK(cudaEventElapsedTime(&c->tm.total_ms, c->ev[0], c->ev[11]));
+        }
+        c->tm.fanout_bytes_out = 0; c->tm.fanout_bytes_in = 0; c->tm.render_bytes_in = h64[10];
+        out->n_users = U; out->total_bytes = sz.total_bytes; out->n_deliveries = h64[8];
+        out->off = c->d_off.as<u64>(); out->bytes = nullptr; out->on_device = 1;
+        return NUTSB_OK;
+    }
     TRY(ensure(c, c->d_out, sz.total_bytes + 64));
     Geometry geo{ c->d_room_b_off.as<u32>(), c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>() };
     c->tm.fanout_launches = 0;
@@ -843,7 +906,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     const bool fused = par && fan && sz.n_events > 0;
     DirectArgs da{ ops, pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_op.as<u32>(),
                    c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_out.as<u8>(), (i64)sz.n_events, counters,
-                   c->d_status.as<u32>(), c->d_slab.as<u8>(), off_base, has_level ? 1u : 0u, c->d_slots.as<SlotInfo>() };
+                   c->d_status.as<u32>(), c->d_slab.as<u8>(), off_base, has_level ? 1u : 0u, c->d_slots.as<SlotInfo>(), nullptr };
     u32 n_dir = cdiv(sz.n_events, NUTSB_DIRECT_THREADS);
     if (fused && c->fd_dir_per_sm > 0) n_dir = std::min(n_dir, (u32)(c->sm_count * c->fd_dir_per_sm));   // grid-strided direct blocks
     if (c->profiling) CK(cudaEventRecord(c->ev[9], sd));
@@ -937,36 +1000,44 @@ NUTSB_API int nutsb_write_batch_dev(nutsb_ctx *c, const nutsb_ops *o, nutsb_stre
     return run_write(c, o, out);
 }
 
+// ops in host memory -> the context's staging buffers in HBM (*d = the same batch with device pointers)
+static int upload_ops(nutsb_ctx *c, const nutsb_ops *o, nutsb_ops *d)
+{
+    const i64 n = o->n_ops;
+    cudaStream_t st = c->stream;
+    *d = *o;
+    if (n <= 0) return NUTSB_OK;
+    const u64 t0 = o->text_off[0], t1 = o->text_off[n];
+    if (t1 < t0) return fail(c, NUTSB_E_INVAL, "text_off is not monotone%s");
+    if (t1 > t0 && !o->text) return fail(c, NUTSB_E_INVAL, "text is NULL%s");
+    // text is uploaded from t0 on; offsets are used as they are (base pointer shifted back)
+    TRY(ensure(c, c->s_text, (size_t)(t1 - t0) + 64));
+    if (t1 > t0) CK(cudaMemcpyAsync(c->s_text.p, o->text + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, st));
+    TRY(upload(c, c->s_toff, o->text_off, ((size_t)n + 1) * 8));
+    TRY(upload(c, c->s_kind, o->kind, (size_t)n));
+    TRY(upload(c, c->s_target, o->target, (size_t)n * 4));
+    TRY(upload(c, c->s_except, o->except_user, (size_t)n * 4));
+    TRY(upload(c, c->s_flags, o->flags, (size_t)n));
+    d->text = c->s_text.as<u8>() - t0; d->text_off = c->s_toff.as<u64>(); d->kind = c->s_kind.as<u8>();
+    d->target = c->s_target.as<i32>(); d->except_user = c->s_except.as<i32>(); d->flags = c->s_flags.as<u8>();
+    d->gate = nullptr; d->verdict = nullptr;
+    if (o->gate && o->verdict) {
+        i32 mx = -1; for (i64 i = 0; i < n; ++i) mx = std::max(mx, o->gate[i]);
+        TRY(upload(c, c->s_gate, o->gate, (size_t)n * 4));
+        TRY(upload(c, c->s_verdict, o->verdict, (size_t)(mx + 1)));
+        d->gate = c->s_gate.as<i32>(); d->verdict = c->s_verdict.as<u8>();
+    }
+    return NUTSB_OK;
+}
+
 NUTSB_API int nutsb_write_batch(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
 {
     TRY(check_ops(c, o, out));
     CK(cudaSetDevice(c->device));
-    const i64 n = o->n_ops;
     cudaStream_t st = c->stream;
     if (c->profiling) CK(cudaEventRecord(c->ev[4], st));
-    nutsb_ops d = *o;
-    if (n > 0) {
-        const u64 t0 = o->text_off[0], t1 = o->text_off[n];
-        if (t1 < t0) return fail(c, NUTSB_E_INVAL, "text_off is not monotone%s");
-        if (t1 > t0 && !o->text) return fail(c, NUTSB_E_INVAL, "text is NULL%s");
-        // text is uploaded from t0 on; offsets are used as they are (base pointer shifted back)
-        TRY(ensure(c, c->s_text, (size_t)(t1 - t0) + 64));
-        if (t1 > t0) CK(cudaMemcpyAsync(c->s_text.p, o->text + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, st));
-        TRY(upload(c, c->s_toff, o->text_off, ((size_t)n + 1) * 8));
-        TRY(upload(c, c->s_kind, o->kind, (size_t)n));
-        TRY(upload(c, c->s_target, o->target, (size_t)n * 4));
-        TRY(upload(c, c->s_except, o->except_user, (size_t)n * 4));
-        TRY(upload(c, c->s_flags, o->flags, (size_t)n));
-        d.text = c->s_text.as<u8>() - t0; d.text_off = c->s_toff.as<u64>(); d.kind = c->s_kind.as<u8>();
-        d.target = c->s_target.as<i32>(); d.except_user = c->s_except.as<i32>(); d.flags = c->s_flags.as<u8>();
-        d.gate = nullptr; d.verdict = nullptr;
-        if (o->gate && o->verdict) {
-            i32 mx = -1; for (i64 i = 0; i < n; ++i) mx = std::max(mx, o->gate[i]);
-            TRY(upload(c, c->s_gate, o->gate, (size_t)n * 4));
-            TRY(upload(c, c->s_verdict, o->verdict, (size_t)(mx + 1)));
-            d.gate = c->s_gate.as<i32>(); d.verdict = c->s_verdict.as<u8>();
-        }
-    }
+    nutsb_ops d;
+    TRY(upload_ops(c, o, &d));
     if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
     nutsb_streams ds{};
     TRY(run_write(c, &d, &ds));
@@ -980,6 +1051,61 @@ NUTSB_API int nutsb_write_batch(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams 
     if (c->profiling) CK(cudaEventElapsedTime(&c->tm.d2h_ms, c->ev[4], c->ev[5]));
     *out = ds;
     out->off = c->h_off.as<u64>(); out->bytes = c->h_out.as<u8>(); out->on_device = 0;
+    return NUTSB_OK;
+}
+
+// Gather lists (include/nutsb200.h): with plain listeners only, what crosses PCIe is the slab's two
+// renderings, the direct ops' renderings and 16 bytes per piece -- not one copy of the bytes per recipient.
+NUTSB_API int nutsb_write_batch_iov(nutsb_ctx *c, const nutsb_ops *o, nutsb_iov_streams *out)
+{
+    if (!out) return fail(c, NUTSB_E_INVAL, "null argument%s");
+    nutsb_streams probe{};
+    TRY(check_ops(c, o, &probe));
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t U = (size_t)c->U;
+    if (c->profiling) CK(cudaEventRecord(c->ev[4], st));
+    nutsb_ops d;
+    TRY(upload_ops(c, o, &d));
+    if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
+    nutsb_streams ds{}; IovReq iv;
+    TRY(run_write(c, &d, &ds, &iv));
+    if (c->profiling) { CK(cudaEventElapsedTime(&c->tm.h2d_ms, c->ev[4], c->ev[5])); CK(cudaEventRecord(c->ev[4], st)); }
+    TRY(ensure_host(c, c->h_off, (U + 1) * 8));
+    TRY(ensure_host(c, c->h_iov_first, (U + 1) * 8)); TRY(ensure_host(c, c->h_iov_cnt, (U + 1) * 4));
+    CK(cudaMemcpyAsync(c->h_off.p, ds.off, (U + 1) * 8, cudaMemcpyDeviceToHost, st));
+    u64 n_iov = 0, pool_bytes = 0;
+    if (iv.compact) {
+        // h_out was sized by run_write (the entries hold addresses inside it)
+        n_iov = iv.n_iov; pool_bytes = iv.dir_base + iv.direct_bytes;
+        TRY(ensure_host(c, c->h_iov, (size_t)n_iov * sizeof(nutsb_iovec)));
+        if (iv.slab_span) CK(cudaMemcpyAsync(c->h_out.p, c->d_slab.p, (size_t)iv.slab_span, cudaMemcpyDeviceToHost, st));
+        if (iv.direct_bytes) CK(cudaMemcpyAsync(c->h_out.as<u8>() + iv.dir_base, c->d_dir.p, (size_t)iv.direct_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_iov.p, c->d_iov.p, (size_t)n_iov * sizeof(nutsb_iovec), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_iov_first.p, c->d_iov_first.p, U * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_iov_cnt.p, c->d_iov_cnt.p, U * 4, cudaMemcpyDeviceToHost, st));
+        if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
+        CK(cudaStreamSynchronize(st));
+    } else {
+        // recipients behind filters (or nothing to send): the streams themselves, one piece per user
+        n_iov = U; pool_bytes = ds.total_bytes;
+        TRY(ensure_host(c, c->h_out, (size_t)ds.total_bytes + 16));
+        TRY(ensure_host(c, c->h_iov, (U + 1) * sizeof(nutsb_iovec)));
+        if (ds.total_bytes) CK(cudaMemcpyAsync(c->h_out.p, ds.bytes, (size_t)ds.total_bytes, cudaMemcpyDeviceToHost, st));
+        if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
+        CK(cudaStreamSynchronize(st));
+        const u64 *off = c->h_off.as<u64>();
+        nutsb_iovec *v = c->h_iov.as<nutsb_iovec>();
+        for (size_t u = 0; u < U; ++u) {
+            v[u].base = c->h_out.as<u8>() + off[u]; v[u].len = (size_t)(off[u + 1] - off[u]);
+            c->h_iov_first.as<u64>()[u] = u; c->h_iov_cnt.as<u32>()[u] = 1;
+        }
+    }
+    if (c->profiling) CK(cudaEventElapsedTime(&c->tm.d2h_ms, c->ev[4], c->ev[5]));
+    out->n_users = (int64_t)U; out->total_bytes = ds.total_bytes; out->n_deliveries = ds.n_deliveries;
+    out->off = c->h_off.as<u64>(); out->first = c->h_iov_first.as<u64>(); out->count = c->h_iov_cnt.as<u32>();
+    out->iov = c->h_iov.as<nutsb_iovec>(); out->n_iov = n_iov;
+    out->pool = c->h_out.as<u8>(); out->pool_bytes = pool_bytes;
     return NUTSB_OK;
 }
 

@@ -1,0 +1,134 @@
+"""Gather lists (nutsb_write_batch_iov): user u's pieces, concatenated, are byte for byte the stream the
+oracle gives for u (= what write_user / write_room_except, nuts333.c:1291-1429, would have written to
+u's socket), and the same as nutsb_write_batch returns.  The bodies run on the SIMT emulator (CPU tier)
+and on the device (-m gpu)."""
+import random
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from nuts333_b200 import api, synth
+
+ALPHA = [bytes([c]) for c in b"abcdefghijklmnopqrstuvwxyzRSOLFBKGTWYMUIV ~~~~//\n\n"]
+
+
+def _random_batch(rng, U, NR, N, maxlen, simple):
+    room = np.array([rng.randint(0 if rng.random() < 0.5 else -1, NR - 1) for _ in range(U)], np.int32)
+    flags = np.array([rng.choice([0, 1] if simple else [0, 1, 1, 0, 2, 4, 8, 5, 9]) for _ in range(U)], np.uint8)
+    level = np.array([rng.randint(0, 4) for _ in range(U)], np.uint8)
+    texts, kind, target, exc, fl = [], [], [], [], []
+    for i in range(N):
+        k = rng.choice([0, 0, 1, 1, 1] if simple else [0, 1, 1, 1, 1, 2])
+        n = rng.randint(0, maxlen) if rng.random() < 0.9 else 0
+        texts.append(b"".join(rng.choice(ALPHA + [b"~FR", b"~RS", b"~OL", b"word ", b"/~", b"\xfe"]) for _ in range(n))[:2000])
+        kind.append(k)
+        f = rng.choice([0, 0, 0, api.OF_PAGER, api.OF_PLAIN])
+        if k == 0:
+            target.append(rng.randint(-1, U - 1)); exc.append(-1); fl.append(f)
+        elif k == 1:
+            target.append(rng.randint(-1, NR - 1)); exc.append(rng.randint(-1, U - 1)); fl.append(f | rng.choice([0, 0, 1, 2]))
+        else:
+            target.append(rng.randint(0, 4)); exc.append(rng.randint(-1, U - 1)); fl.append(f | rng.choice([0, 4]))
+    text, off = O.pack(texts)
+    ops = dict(text=text, off=off, kind=np.array(kind, np.uint8), target=np.array(target, np.int32),
+               except_user=np.array(exc, np.int32), flags=np.array(fl, np.uint8))
+    return ops, dict(room=room, flags=flags, level=level)
+
+
+def _check(ctx, port, ops, users, n_rooms, verdict=None, expect_compact=None):
+    ctx.set_users(users["room"], users["flags"], users["level"], n_rooms)
+    full = dict(ops, verdict=verdict) if verdict is not None else ops
+    iv = ctx.write_batch_iov(full)
+    o, d, nd = port.write_batch(ops, users, verdict=verdict)
+    U = len(users["room"])
+    assert iv.n_users == U and (iv.off == o).all() and iv.n_deliveries == int(nd.sum())
+    lo, hi = iv.pool_addr, iv.pool_addr + iv.pool_bytes
+    for u in range(U):
+        p = iv.pieces(u)
+        assert int(p[:, 1].sum()) == int(o[u + 1] - o[u]), u
+        for a, n in p:                                  # every piece lies inside the pool
+            assert n == 0 or (lo <= int(a) and int(a) + int(n) <= hi), u
+        assert iv.user(u) == d[int(o[u]):int(o[u + 1])].tobytes(), u
+    if expect_compact is False:                         # recipients behind filters: the streams, one piece per user
+        assert iv.n_iov == U and (iv.count == 1).all()
+    if expect_compact and U and int(o[-1]):
+        assert (iv.count % 2 == 1).all() and iv.n_iov == int(iv.count.sum())
+    # ... and the streams call still gives the same bytes afterwards (shared scratch is not left dirty)
+    st = ctx.write_batch(full)
+    assert (st.off == o).all() and (st.data == d).all() and st.n_deliveries == int(nd.sum())
+    return iv
+
+
+def _body_say_pipeline(ctx, port, n_users, per_room, n_msgs):
+    words = synth.swear_words(64)
+    ctx.set_swear_words(words)
+    us, n_rooms = synth.users(n_users, per_room)
+    bt, bo = synth.bodies(n_msgs, words)
+    v = ctx.contains_swearing_batch(bt, bo)
+    ops, spk, rm = synth.say_ops(n_msgs, n_users, per_room, bt, bo, gated=True)
+    iv = _check(ctx, port, ops, us, n_rooms, verdict=v, expect_compact=True)
+    # plain listeners: the pool is far smaller than the streams it describes
+    assert iv.pool_bytes < iv.total_bytes / 4
+    ctx.set_swear_words(["fuck", "shit", "cunt", "*"])
+
+
+def _body_random(ctx, port, seeds, sizes):
+    for seed in seeds:
+        rng = random.Random(seed)
+        U, NR, N, maxlen = rng.choice(sizes)
+        simple = seed % 3 != 0
+        ops, users = _random_batch(rng, U, NR, N, maxlen, simple)
+        plain = not (users["flags"] & 0x3e).any() and not (ops["kind"] == 2).any()      # every recipient a plain listener
+        assert plain or not simple
+        _check(ctx, port, ops, users, NR, expect_compact=plain)
+
+
+def _body_edges(ctx, port):
+    users = dict(room=np.array([0, 0, -1, 1], np.int32), flags=np.array([1, 0, 1, 0], np.uint8), level=np.ones(4, np.uint8))
+    e = dict(text=np.zeros(0, np.uint8), off=np.zeros(1, np.uint64), kind=np.zeros(0, np.uint8), target=np.zeros(0, np.int32),
+             except_user=np.zeros(0, np.int32), flags=np.zeros(0, np.uint8))
+    iv = _check(ctx, port, e, users, 2)                          # empty batch
+    assert iv.total_bytes == 0 and all(iv.user(u) == b"" for u in range(4))
+    # direct ops only (a user in no room among them), then room ops only, then two direct ops before one room op
+    for texts, kind, target, exc in (
+            ([b"~FRhello\n", b"", b"x"], [0, 0, 0], [2, 0, 1], [-1, -1, -1]),
+            ([b"~OLroom line\n", b"all\n"], [1, 1], [0, -1], [1, 3]),
+            ([b"a\n", b"b\n", b"~FGc\n", b"d"], [0, 0, 1, 0], [0, 0, 0, 0], [-1, -1, 0, -1])):
+        text, off = O.pack(texts)
+        ops = dict(text=text, off=off, kind=np.array(kind, np.uint8), target=np.array(target, np.int32),
+                   except_user=np.array(exc, np.int32), flags=np.zeros(len(kind), np.uint8))
+        _check(ctx, port, ops, users, 2, expect_compact=True)
+    # no users at all
+    ctx.set_users(np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.uint8), 2)
+    iv = ctx.write_batch_iov(dict(ops, kind=np.ones(4, np.uint8), target=np.array([0, 1, -1, 0], np.int32),
+                                  except_user=np.full(4, -1, np.int32)))
+    assert iv.n_users == 0 and iv.total_bytes == 0 and iv.n_iov == 0
+
+
+# ---- CPU tier: the product's sources on the SIMT emulator ------------------------------------
+def test_iov_say_pipeline_sim(sim_lib, port):
+    ctx = api.Context(0, sim_lib)
+    _body_say_pipeline(ctx, port, 60, 20, 150)
+    ctx.close()
+
+
+def test_iov_random_and_edges_sim(sim_lib, port):
+    ctx = api.Context(0, sim_lib)
+    _body_edges(ctx, port)
+    _body_random(ctx, port, range(4), [(5, 1, 40, 30), (40, 3, 150, 40), (33, 2, 200, 12)])
+    ctx.close()
+
+
+# ---- device tier --------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_iov_say_pipeline_gpu(gpu_ctx, port):
+    _body_say_pipeline(gpu_ctx, port, 2000, 100, 20000)
+
+
+@pytest.mark.gpu
+def test_iov_random_and_edges_gpu(gpu_ctx, port):
+    _body_edges(gpu_ctx, port)
+    _body_random(gpu_ctx, port, range(200, 230),
+                 [(1, 1, 5, 20), (40, 3, 400, 40), (300, 2, 900, 30), (1000, 1, 300, 60), (64, 70, 5000, 25),
+                  (7, 1, 2000, 1990), (129, 5, 257, 400)])
