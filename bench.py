@@ -67,7 +67,7 @@ def make_inputs(rank: int, n_msgs: int):
     sfile = synth.ban_file(0, N_BAN_ENTRIES, N_BAN_QUERIES, N_BAN_QUERIES, True, seed=seed)
     ufile = synth.ban_file(1, N_BAN_ENTRIES, N_BAN_QUERIES, N_BAN_QUERIES, True, seed=seed)
     return dict(words=words, users=sh["users"], n_rooms=sh["n_rooms"], bodies=sh["bodies"], ops=sh["ops"],
-                sites=(st, so), names=(nt, no), sfile=sfile, ufile=ufile)
+                speaker=sh["speaker"], sites=(st, so), names=(nt, no), sfile=sfile, ufile=ufile)
 
 
 # ---------------------------------------------------------------------------------------
@@ -381,21 +381,38 @@ def run_ours(args):
 
     bt, bo, st_, so_, nt_, no_ = (pin(a) for a in (bt, bo, st_, so_, nt_, no_))
     hops = {k: (pin(v) if isinstance(v, np.ndarray) else v) for k, v in ops.items()}
-    def e2e_leg(iov):
-        """One leg through the host-buffer entry points: verdict batches, then nutsb_write_batch (streams in
-        pinned host memory) or nutsb_write_batch_iov (gather lists into the pool of renderings)."""
+    # the speech tier takes the input lines themselves (verb, speaker, body): say() composed on the device
+    from nuts333_b200 import synth
+    un, uo = synth.names(N_USERS)
+    ctx.set_user_names([un[int(uo[u]):int(uo[u + 1])].tobytes() for u in range(N_USERS)], np.zeros(N_USERS, np.uint8))
+    ctx.set_ban_swearing(True)
+    sp_verb, sp_spk = pin(np.zeros(N_MSGS, np.uint8)), pin(inp["speaker"].astype(np.int32))
+
+    def e2e_leg(mode):
+        """One leg through the host-buffer entry points: verdict batches, then nutsb_write_batch (mode "streams":
+        streams in pinned host memory), nutsb_write_batch_iov ("iov": gather lists into the pool of renderings) or
+        nutsb_speech_batch_iov ("speech_iov": the 1M input lines of say() in -- swear verdicts, composition and
+        rendering on the device -- gather lists out)."""
+        iov = mode != "streams"
         r = dict(h2d_ms=0.0, d2h_ms=0.0, ms=0.0, deliv=0, h2d=0, d2h=0, extra={})
         for i in range(1 + e2e_steps):                     # first pass allocates the pinned result buffers
             barrier()
             t0 = time.perf_counter()
-            v = ctx.contains_swearing_batch(bt, bo)
             vs = ctx.site_banned_batch(st_, so_)
             vu = ctx.user_banned_batch(nt_, no_)
             keep = []
-            o = ctx._ops_struct(dict(hops, verdict=v), keep)
-            if iov:
+            if mode == "speech_iov":
+                v = np.zeros(0, np.uint8)                  # the verdicts stay on the device
+                s = api._IovStreams()
+                ctx._ck(ctx.lib.nutsb_speech_batch_iov(ctx._h, N_MSGS, api._addr(sp_verb), api._addr(sp_spk), api._addr(bt),
+                                                       api._addr(bo), s))
+            else:
+                v = ctx.contains_swearing_batch(bt, bo)
+                o = ctx._ops_struct(dict(hops, verdict=v), keep)
+            if mode == "iov":
                 s = api._IovStreams()
                 ctx._ck(ctx.lib.nutsb_write_batch_iov(ctx._h, o, s))
+            if iov:
                 touch = int(np.ctypeslib.as_array(api.C.cast(s.pool, api.u8p), shape=(16,))[0])      # touch the result
                 touch += int(np.ctypeslib.as_array(api.C.cast(s.iov, api.u64p), shape=(2,))[1])
                 out_bytes = int(s.pool_bytes) + 16 * int(s.n_iov) + 12 * N_USERS
@@ -415,23 +432,28 @@ def run_ours(args):
                 tt = ctx.timing()
                 r["h2d_ms"] += float(tt.h2d_ms); r["d2h_ms"] += float(tt.d2h_ms)
                 r["ms"] += dt * 1e3; r["deliv"] += int(s.n_deliveries)
-                r["h2d"] = int(bt.nbytes + bo.nbytes + st_.nbytes + so_.nbytes + nt_.nbytes + no_.nbytes + ops["text"].nbytes
-                               + ops["off"].nbytes + 2 * n_ops + 12 * n_ops + v.nbytes)
+                r["h2d"] = int(bt.nbytes + bo.nbytes + st_.nbytes + so_.nbytes + nt_.nbytes + no_.nbytes)
+                r["h2d"] += (5 * N_MSGS if mode == "speech_iov" else
+                             int(ops["text"].nbytes + ops["off"].nbytes + 2 * n_ops + 12 * n_ops + v.nbytes))
                 r["d2h"] = out_bytes + 8 * (N_USERS + 1) + v.nbytes + vs.nbytes + vu.nbytes
         return r
 
     e2e_steps = max(1, min(args.steps, 3))
     zero = dict(h2d_ms=0.0, d2h_ms=0.0, ms=0.0, deliv=0, h2d=0, d2h=0, extra={})
-    leg_s = zero if args.no_e2e else e2e_leg(False)
-    leg_v = zero if args.no_e2e else e2e_leg(True)
+    leg_s = zero if args.no_e2e else e2e_leg("streams")
+    leg_v = zero if args.no_e2e else e2e_leg("iov")
+    leg_p = zero if args.no_e2e else e2e_leg("speech_iov")
+    if not args.no_e2e:                                    # the three legs deliver the same streams
+        assert leg_v["deliv"] == leg_s["deliv"] == leg_p["deliv"], (leg_s["deliv"], leg_v["deliv"], leg_p["deliv"])
+        assert leg_v["extra"]["stream_bytes"] == leg_p["extra"]["stream_bytes"]
     e2e_h2d_ms, e2e_d2h_ms, e2e_ms, e2e_deliv, h2d, d2h = (leg_s[k] for k in ("h2d_ms", "d2h_ms", "ms", "deliv", "h2d", "d2h"))
     # ---- reduce over ranks
-    vals = torch.tensor([ms, e2e_ms, leg_v["ms"]], dtype=torch.float64, device=dev)
+    vals = torch.tensor([ms, e2e_ms, leg_v["ms"], leg_p["ms"]], dtype=torch.float64, device=dev)
     sums = torch.tensor([dev_state["deliv"], e2e_deliv, dev_state["launches"], leg_v["deliv"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max, iov_ms_max = float(vals[0]), float(vals[1]), float(vals[2])
+    ms_max, e2e_ms_max, iov_ms_max, sp_ms_max = float(vals[0]), float(vals[1]), float(vals[2]), float(vals[3])
     total_deliv, total_e2e_deliv, total_launch, total_iov_deliv = float(sums[0]), float(sums[1]), int(sums[2]), float(sums[3])
 
     if rank == 0:
@@ -489,6 +511,11 @@ def run_ours(args):
                                    result="per-user struct iovec lists into one pinned pool: every room op rendered once per "
                                           "colour setting + every write_user op rendered once; byte-identical to `e2e`'s streams "
                                           "when gathered (tests/test_iov.py)", **leg_v["extra"])
+            # ... and from the input lines themselves: say(user, inpstr) x 1M through nutsb_speech_batch_iov
+            line["e2e_speech_iov"] = dict(value=total_iov_deliv / (sp_ms_max * 1e-3), unit=UNIT, h2d_bytes_per_step=leg_p["h2d"],
+                                          d2h_bytes_per_step=leg_p["d2h"], steps=e2e_steps, ms_per_step=sp_ms_max / e2e_steps,
+                                          input="verb, speaker and body of every line (nutsb_speech_batch_iov): swear verdicts, "
+                                                "say()'s composition and the rendering all on the device", **leg_p["extra"])
         if world == 1 and not args.no_cpu_baseline:
             procs = 1
             dcpu, nbytes, busy, wall, kind = reference_step(0, 40_000, 4_000, procs)

@@ -273,6 +273,9 @@ int nutsb_speech_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *verb, const int
                        const uint8_t *bodies, const uint64_t *body_off, nutsb_streams *out);
 int nutsb_speech_batch_dev(nutsb_ctx *ctx, int64_t n, const uint8_t *verb, const int32_t *speaker,
                            const uint8_t *bodies, const uint64_t *body_off, nutsb_streams *out);
+/* Host buffers in, gather lists out (see nutsb_write_batch_iov). */
+int nutsb_speech_batch_iov(nutsb_ctx *ctx, int64_t n, const uint8_t *verb, const int32_t *speaker,
+                           const uint8_t *bodies, const uint64_t *body_off, nutsb_iov_streams *out);
 /* queue tier: one call of the reference's say()/shout()/... ; composed on the host, the swear
  * verdicts of the queued lines are taken in one device batch at nutsb_flush */
 int nutsb_q_speech(nutsb_ctx *ctx, int verb, int32_t user, const char *inpstr);
@@ -337,6 +340,8 @@ int64_t nutsb_q_pending(const nutsb_ctx *ctx);
 /* Runs everything queued since the last flush; the host then write()s each
  * user's stream to its socket. */
 int nutsb_flush(nutsb_ctx *ctx, nutsb_streams *out);
+/* The same with gather lists as the result (nutsb_write_batch_iov): the host writev()s each user's list. */
+int nutsb_flush_iov(nutsb_ctx *ctx, nutsb_iov_streams *out);
 
 /* Synchronous single-item verdicts (the callers branch on them immediately,
  * c:4091, c:279, c:1496): one tiny launch each, latency-bound by design. */

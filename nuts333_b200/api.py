@@ -76,11 +76,11 @@ EXPORTS = [
     "nutsb_set_ban_files", "nutsb_ban_edit", "nutsb_get_ban_file", "nutsb_set_users", "nutsb_set_clones", "nutsb_set_remotes", "nutsb_set_room_names", "nutsb_write_batch", "nutsb_write_batch_dev", "nutsb_write_batch_iov",
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
-    "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_q_speech",
+    "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_speech_batch_iov", "nutsb_q_speech",
     "nutsb_q_record", "nutsb_q_review", "nutsb_q_review_clear",
     "nutsb_q_tell", "nutsb_q_pemote", "nutsb_q_wizshout", "nutsb_q_revtell",
     "nutsb_colour_com_count_batch", "nutsb_colour_com_strip_batch", "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
-    "nutsb_q_write_level", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_contains_swearing",
+    "nutsb_q_write_level", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_flush_iov", "nutsb_contains_swearing",
     "nutsb_site_banned", "nutsb_user_banned",
 ]
 
@@ -118,6 +118,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_set_ban_swearing.argtypes = [vp, C.c_int]
     lib.nutsb_speech_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
     lib.nutsb_speech_batch_dev.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_Streams)]
+    lib.nutsb_speech_batch_iov.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.POINTER(_IovStreams)]
     lib.nutsb_q_speech.argtypes = [vp, C.c_int, C.c_int32, C.c_char_p]
     lib.nutsb_set_clones.argtypes = [vp, C.c_int32, vp, vp]
     lib.nutsb_set_room_names.argtypes = [vp, C.c_int32, vp, vp]
@@ -143,6 +144,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_q_pending.restype = C.c_int64
     lib.nutsb_q_pending.argtypes = [vp]
     lib.nutsb_flush.argtypes = [vp, C.POINTER(_Streams)]
+    lib.nutsb_flush_iov.argtypes = [vp, C.POINTER(_IovStreams)]
     return lib
 
 
@@ -295,6 +297,15 @@ class Context:
                                              _addr(bodies) if bodies.size else None, _addr(body_off), C.byref(st)))
         return self._host_streams(st)
 
+    def speech_batch_iov(self, verb, speaker, bodies, body_off) -> "IovStreams":
+        """speech_batch with gather lists as the result (nutsb_speech_batch_iov)."""
+        verb, speaker = _np(verb, np.uint8), _np(speaker, np.int32)
+        bodies, body_off = _np(bodies, np.uint8), _np(body_off, np.uint64)
+        st = _IovStreams()
+        self._ck(self.lib.nutsb_speech_batch_iov(self._h, len(verb), _addr(verb), _addr(speaker),
+                                                 _addr(bodies) if bodies.size else None, _addr(body_off), C.byref(st)))
+        return self._host_iov(st)
+
     def set_clones(self, owner, hear):
         owner, hear = _np(owner, np.int32), _np(hear, np.uint8)
         self._ck(self.lib.nutsb_set_clones(self._h, len(owner), _addr(owner), _addr(hear)))
@@ -369,6 +380,9 @@ class Context:
         o = self._ops_struct(ops, keep)
         st = _IovStreams()
         self._ck(self.lib.nutsb_write_batch_iov(self._h, C.byref(o), C.byref(st)))
+        return self._host_iov(st)
+
+    def _host_iov(self, st) -> IovStreams:
         U, n = int(st.n_users), int(st.n_iov)
         off = np.ctypeslib.as_array(C.cast(st.off, u64p), shape=(U + 1,)).copy()
         first = np.ctypeslib.as_array(C.cast(st.first, u64p), shape=(max(U, 1),))[:U].copy()
@@ -549,6 +563,13 @@ class Talker:
         st = _Streams()
         c._ck(c.lib.nutsb_flush(c._h, C.byref(st)))
         return c._host_streams(st)
+
+    def flush_iov(self) -> IovStreams:
+        """Runs everything queued; the host then writev()s each user's gather list."""
+        c = self.ctx
+        st = _IovStreams()
+        c._ck(c.lib.nutsb_flush_iov(c._h, C.byref(st)))
+        return c._host_iov(st)
 
     def contains_swearing(self, s) -> int:                            # c:2540
         return self.ctx._ck(self.ctx.lib.nutsb_contains_swearing(self.ctx._h, self._s(s)))

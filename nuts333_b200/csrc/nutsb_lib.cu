@@ -1054,23 +1054,11 @@ NUTSB_API int nutsb_write_batch(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams 
     return NUTSB_OK;
 }
 
-// Gather lists (include/nutsb200.h): with plain listeners only, what crosses PCIe is the slab's two
-// renderings, the direct ops' renderings and 16 bytes per piece -- not one copy of the bytes per recipient.
-NUTSB_API int nutsb_write_batch_iov(nutsb_ctx *c, const nutsb_ops *o, nutsb_iov_streams *out)
+// Brings a gather-list result to the host (pool, lists) after run_write(..., &iv); ev[4] was recorded before.
+static int fetch_iov(nutsb_ctx *c, const nutsb_streams &ds, const IovReq &iv, nutsb_iov_streams *out)
 {
-    if (!out) return fail(c, NUTSB_E_INVAL, "null argument%s");
-    nutsb_streams probe{};
-    TRY(check_ops(c, o, &probe));
-    CK(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const size_t U = (size_t)c->U;
-    if (c->profiling) CK(cudaEventRecord(c->ev[4], st));
-    nutsb_ops d;
-    TRY(upload_ops(c, o, &d));
-    if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
-    nutsb_streams ds{}; IovReq iv;
-    TRY(run_write(c, &d, &ds, &iv));
-    if (c->profiling) { CK(cudaEventElapsedTime(&c->tm.h2d_ms, c->ev[4], c->ev[5])); CK(cudaEventRecord(c->ev[4], st)); }
     TRY(ensure_host(c, c->h_off, (U + 1) * 8));
     TRY(ensure_host(c, c->h_iov_first, (U + 1) * 8)); TRY(ensure_host(c, c->h_iov_cnt, (U + 1) * 4));
     CK(cudaMemcpyAsync(c->h_off.p, ds.off, (U + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -1107,6 +1095,25 @@ NUTSB_API int nutsb_write_batch_iov(nutsb_ctx *c, const nutsb_ops *o, nutsb_iov_
     out->iov = c->h_iov.as<nutsb_iovec>(); out->n_iov = n_iov;
     out->pool = c->h_out.as<u8>(); out->pool_bytes = pool_bytes;
     return NUTSB_OK;
+}
+
+// Gather lists (include/nutsb200.h): with plain listeners only, what crosses PCIe is the slab's two
+// renderings, the direct ops' renderings and 16 bytes per piece -- not one copy of the bytes per recipient.
+NUTSB_API int nutsb_write_batch_iov(nutsb_ctx *c, const nutsb_ops *o, nutsb_iov_streams *out)
+{
+    if (!out) return fail(c, NUTSB_E_INVAL, "null argument%s");
+    nutsb_streams probe{};
+    TRY(check_ops(c, o, &probe));
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    if (c->profiling) CK(cudaEventRecord(c->ev[4], st));
+    nutsb_ops d;
+    TRY(upload_ops(c, o, &d));
+    if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
+    nutsb_streams ds{}; IovReq iv;
+    TRY(run_write(c, &d, &ds, &iv));
+    if (c->profiling) { CK(cudaEventElapsedTime(&c->tm.h2d_ms, c->ev[4], c->ev[5])); CK(cudaEventRecord(c->ev[4], st)); }
+    return fetch_iov(c, ds, iv, out);
 }
 
 NUTSB_API int nutsb_stream_digests(nutsb_ctx *c, uint64_t *digest)
@@ -1508,9 +1515,9 @@ NUTSB_API int nutsb_q_review(nutsb_ctx *c, int32_t user, int32_t room, const cha
     return nutsb_q_write_user(c, user, "\n~BB~FG*** End ***\n\n");
 }
 
-NUTSB_API int nutsb_flush(nutsb_ctx *c, nutsb_streams *out)
+static int flush_impl(nutsb_ctx *c, nutsb_streams *out, nutsb_iov_streams *out_iov)
 {
-    if (!c || !out) return NUTSB_E_INVAL;
+    if (!c || (!out && !out_iov)) return NUTSB_E_INVAL;
     nutsb_ops o{};
     o.n_ops = (i64)c->q_kind.size();
     static const u8 zero = 0;
@@ -1520,11 +1527,13 @@ NUTSB_API int nutsb_flush(nutsb_ctx *c, nutsb_streams *out)
     int rc = resolve_records(c);
     const i64 n_sw = (i64)c->q_sw_off.size() - 1;
     if (rc == NUTSB_OK && n_sw > 0) { o.gate = c->q_gate.data(); o.verdict = c->q_sw_verdict.data(); }
-    if (rc == NUTSB_OK) rc = nutsb_write_batch(c, &o, out);
+    if (rc == NUTSB_OK) rc = out ? nutsb_write_batch(c, &o, out) : nutsb_write_batch_iov(c, &o, out_iov);
     c->q_text.clear(); c->q_off.assign(1, 0); c->q_kind.clear(); c->q_target.clear(); c->q_except.clear(); c->q_flags.clear();
     c->q_gate.clear(); c->q_sw_text.clear(); c->q_sw_off.assign(1, 0); c->q_sw_verdict.clear(); c->q_rec.clear();
     return rc;
 }
+NUTSB_API int nutsb_flush(nutsb_ctx *c, nutsb_streams *out) { return flush_impl(c, out, nullptr); }
+NUTSB_API int nutsb_flush_iov(nutsb_ctx *c, nutsb_iov_streams *out) { return flush_impl(c, nullptr, out); }
 
 // ---------------------------------------------------------------------------------------
 // the callers' composition
@@ -1673,11 +1682,12 @@ NUTSB_API int nutsb_q_revtell(nutsb_ctx *c, int32_t user)
     return nutsb_q_write_user(c, user, "\n~BB~FG*** End ***\n\n");
 }
 
-static int run_speech(nutsb_ctx *c, i64 n, const u8 *verb, const i32 *speaker, const u8 *bodies, const u64 *body_off, nutsb_streams *out)
+static int run_speech(nutsb_ctx *c, i64 n, const u8 *verb, const i32 *speaker, const u8 *bodies, const u64 *body_off, nutsb_streams *out,
+                      IovReq *iv = nullptr)
 {
     TRY(speech_ready(c));
     cudaStream_t st = c->stream;
-    if (n == 0) { nutsb_ops o{}; return run_write(c, &o, out); }
+    if (n == 0) { nutsb_ops o{}; return run_write(c, &o, out, iv); }
     SpeechView v{ n, verb, speaker, bodies, body_off, c->d_names.as<u8>(), c->d_name_off.as<u64>(), c->d_sflags.as<u8>(),
                   c->d_user_room.as<i32>(), c->d_lit.as<u8>(), c->d_lit_off.as<u32>(), c->U, c->R, c->ban_swearing ? 1u : 0u };
     const size_t n3 = (size_t)n * 3;
@@ -1700,7 +1710,7 @@ static int run_speech(nutsb_ctx *c, i64 n, const u8 *verb, const i32 *speaker, c
     TRY(verdict_dev(c, V_SWEAR, n, bodies, body_off, c->d_sp_verdict.as<u8>()));
     nutsb_ops o{ (i64)n3, c->d_sp_text.as<u8>(), c->d_sp_off.as<u64>(), c->d_sp_kind.as<u8>(), c->d_sp_target.as<i32>(),
                  c->d_sp_except.as<i32>(), c->d_sp_flags.as<u8>(), c->d_sp_gate.as<i32>(), c->d_sp_verdict.as<u8>() };
-    return run_write(c, &o, out);
+    return run_write(c, &o, out, iv);
 }
 
 NUTSB_API int nutsb_speech_batch_dev(nutsb_ctx *c, int64_t n, const uint8_t *verb, const int32_t *speaker,
@@ -1711,23 +1721,33 @@ NUTSB_API int nutsb_speech_batch_dev(nutsb_ctx *c, int64_t n, const uint8_t *ver
     return run_speech(c, n, verb, speaker, bodies, body_off, out);
 }
 
+// the n input lines of a speech batch, host memory -> staging buffers in HBM
+static int upload_speech(nutsb_ctx *c, i64 n, const u8 *verb, const i32 *speaker, const u8 *bodies, const u64 *body_off,
+                         const u8 **dv, const i32 **ds, const u8 **db, const u64 **dbo)
+{
+    *dv = nullptr; *ds = nullptr; *db = nullptr; *dbo = nullptr;
+    if (n <= 0) return NUTSB_OK;
+    const u64 t0 = body_off[0], t1 = body_off[n];
+    if (t1 < t0 || (t1 > t0 && !bodies)) return fail(c, NUTSB_E_INVAL, "bad body offsets%s");
+    u64 bad = 0;                                               // branch-free: the loop vectorises
+    for (i64 i = 0; i < n; ++i) bad |= (u64)(body_off[i + 1] < body_off[i]);
+    if (bad) return fail(c, NUTSB_E_INVAL, "body offsets are not monotone%s");
+    TRY(ensure(c, c->s_body, (size_t)(t1 - t0) + 64));
+    if (t1 > t0) CK(cudaMemcpyAsync(c->s_body.p, bodies + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, c->stream));
+    TRY(upload(c, c->s_boff, body_off, ((size_t)n + 1) * 8));
+    TRY(upload(c, c->s_verb, verb, (size_t)n));
+    TRY(upload(c, c->s_speaker, speaker, (size_t)n * 4));
+    *dv = c->s_verb.as<u8>(); *ds = c->s_speaker.as<i32>(); *db = c->s_body.as<u8>() - t0; *dbo = c->s_boff.as<u64>();
+    return NUTSB_OK;
+}
+
 NUTSB_API int nutsb_speech_batch(nutsb_ctx *c, int64_t n, const uint8_t *verb, const int32_t *speaker,
                                  const uint8_t *bodies, const uint64_t *body_off, nutsb_streams *out)
 {
     if (!c || !out || n < 0 || (n && (!verb || !speaker || !body_off))) return fail(c, NUTSB_E_INVAL, "bad argument%s");
     CK(cudaSetDevice(c->device));
-    const u8 *dv = nullptr; const i32 *ds = nullptr; const u8 *db = nullptr; const u64 *dbo = nullptr;
-    if (n > 0) {
-        const u64 t0 = body_off[0], t1 = body_off[n];
-        if (t1 < t0 || (t1 > t0 && !bodies)) return fail(c, NUTSB_E_INVAL, "bad body offsets%s");
-        for (i64 i = 0; i < n; ++i) if (body_off[i + 1] < body_off[i]) return fail(c, NUTSB_E_INVAL, "body offsets are not monotone%s");
-        TRY(ensure(c, c->s_body, (size_t)(t1 - t0) + 64));
-        if (t1 > t0) CK(cudaMemcpyAsync(c->s_body.p, bodies + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, c->stream));
-        TRY(upload(c, c->s_boff, body_off, ((size_t)n + 1) * 8));
-        TRY(upload(c, c->s_verb, verb, (size_t)n));
-        TRY(upload(c, c->s_speaker, speaker, (size_t)n * 4));
-        dv = c->s_verb.as<u8>(); ds = c->s_speaker.as<i32>(); db = c->s_body.as<u8>() - t0; dbo = c->s_boff.as<u64>();
-    }
+    const u8 *dv; const i32 *ds; const u8 *db; const u64 *dbo;
+    TRY(upload_speech(c, n, verb, speaker, bodies, body_off, &dv, &ds, &db, &dbo));
     nutsb_streams ds_{};
     TRY(run_speech(c, n, dv, ds, db, dbo, &ds_));
     TRY(ensure_host(c, c->h_off, ((size_t)c->U + 1) * 8));
@@ -1738,4 +1758,21 @@ NUTSB_API int nutsb_speech_batch(nutsb_ctx *c, int64_t n, const uint8_t *verb, c
     *out = ds_;
     out->off = c->h_off.as<u64>(); out->bytes = c->h_out.as<u8>(); out->on_device = 0;
     return NUTSB_OK;
+}
+
+// input lines in, gather lists out: the smallest host <-> device traffic the path has (bodies + 5 bytes per
+// line one way; each rendering once per colour setting + 16 bytes per piece the other)
+NUTSB_API int nutsb_speech_batch_iov(nutsb_ctx *c, int64_t n, const uint8_t *verb, const int32_t *speaker,
+                                     const uint8_t *bodies, const uint64_t *body_off, nutsb_iov_streams *out)
+{
+    if (!c || !out || n < 0 || (n && (!verb || !speaker || !body_off))) return fail(c, NUTSB_E_INVAL, "bad argument%s");
+    CK(cudaSetDevice(c->device));
+    if (c->profiling) CK(cudaEventRecord(c->ev[4], c->stream));
+    const u8 *dv; const i32 *ds; const u8 *db; const u64 *dbo;
+    TRY(upload_speech(c, n, verb, speaker, bodies, body_off, &dv, &ds, &db, &dbo));
+    if (c->profiling) CK(cudaEventRecord(c->ev[5], c->stream));
+    nutsb_streams ds_{}; IovReq iv;
+    TRY(run_speech(c, n, dv, ds, db, dbo, &ds_, &iv));
+    if (c->profiling) { CK(cudaEventElapsedTime(&c->tm.h2d_ms, c->ev[4], c->ev[5])); CK(cudaEventRecord(c->ev[4], c->stream)); }
+    return fetch_iov(c, ds_, iv, out);
 }

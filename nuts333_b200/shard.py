@@ -17,7 +17,7 @@ def shard_inputs(rank: int, n_msgs: int, n_users: int, users_per_room: int, word
     users, n_rooms = synth.users(n_users, users_per_room, seed=seed)
     bt, bo = synth.bodies(n_msgs, words if gated else None, seed=seed)
     ops, spk, rm = synth.say_ops(n_msgs, n_users, users_per_room, bt, bo, gated=gated, seed=seed)
-    return dict(users=users, n_rooms=n_rooms, bodies=(bt, bo), ops=ops)
+    return dict(users=users, n_rooms=n_rooms, bodies=(bt, bo), ops=ops, speaker=spk)
 
 
 def to_global(shards):

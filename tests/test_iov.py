@@ -2,12 +2,14 @@
 oracle gives for u (= what write_user / write_room_except, nuts333.c:1291-1429, would have written to
 u's socket), and the same as nutsb_write_batch returns.  The bodies run on the SIMT emulator (CPU tier)
 and on the device (-m gpu)."""
+import hashlib
 import random
 
 import numpy as np
 import pytest
 
 import oracle_lib as O
+from golden_util import golden
 from nuts333_b200 import api, synth
 
 ALPHA = [bytes([c]) for c in b"abcdefghijklmnopqrstuvwxyzRSOLFBKGTWYMUIV ~~~~//\n\n"]
@@ -106,6 +108,37 @@ def _body_edges(ctx, port):
     assert iv.n_users == 0 and iv.total_bytes == 0 and iv.n_iov == 0
 
 
+def _body_c1_through_the_queue_tier(ctx, n):
+    """BASELINE config 1 through the reference's call surface (write_room per line), flushed into gather
+    lists; the SHA-256 of the gathered stream is the one minted from the unmodified reference."""
+    for colour in (0, 1):
+        ctx.set_users(np.zeros(1, np.int32), np.array([colour], np.uint8), np.array([api.GOD], np.uint8), 1)
+        t = api.Talker(ctx)
+        for i in range(n):
+            t.write_room(0, b"Fred says: ~OLline %04d ~FRred~RS done\n" % i)
+        iv = t.flush_iov()
+        assert t.pending() == 0 and iv.n_deliveries == n
+        if n == 1000:
+            g = golden()["c1"][str(colour)]
+            assert iv.total_bytes == g["n"] and hashlib.sha256(iv.user(0)).hexdigest() == g["sha256"]
+        else:
+            assert iv.total_bytes == n * (52 if colour else 31)
+        # speech through the queue tier: say() = write_user + write_room_except (c:4094-4098)
+    ctx.set_users(np.zeros(3, np.int32), np.array([1, 0, 1], np.uint8), np.full(3, api.GOD, np.uint8), 1)
+    ctx.set_user_names([b"Fred", b"Wilma", b"Barney"], np.zeros(3, np.uint8))
+    t = api.Talker(ctx)
+    for i in range(5):
+        t.say(i % 3, b"hello ~FRthere~RS %d" % i)
+    a = t.flush_iov()
+    got = [a.user(u) for u in range(3)]                  # the pieces point into the context's pool: gather before the next batch
+    for i in range(5):
+        t.say(i % 3, b"hello ~FRthere~RS %d" % i)
+    b = t.flush()
+    assert (a.off == b.off).all() and a.n_deliveries == b.n_deliveries
+    for u in range(3):
+        assert got[u] == b.user(u) and len(got[u]) > 0
+
+
 # ---- CPU tier: the product's sources on the SIMT emulator ------------------------------------
 def test_iov_say_pipeline_sim(sim_lib, port):
     ctx = api.Context(0, sim_lib)
@@ -117,6 +150,12 @@ def test_iov_random_and_edges_sim(sim_lib, port):
     ctx = api.Context(0, sim_lib)
     _body_edges(ctx, port)
     _body_random(ctx, port, range(4), [(5, 1, 40, 30), (40, 3, 150, 40), (33, 2, 200, 12)])
+    ctx.close()
+
+
+def test_iov_c1_queue_tier_sim(sim_lib):
+    ctx = api.Context(0, sim_lib)
+    _body_c1_through_the_queue_tier(ctx, 40)
     ctx.close()
 
 
@@ -132,3 +171,8 @@ def test_iov_random_and_edges_gpu(gpu_ctx, port):
     _body_random(gpu_ctx, port, range(200, 230),
                  [(1, 1, 5, 20), (40, 3, 400, 40), (300, 2, 900, 30), (1000, 1, 300, 60), (64, 70, 5000, 25),
                   (7, 1, 2000, 1990), (129, 5, 257, 400)])
+
+
+@pytest.mark.gpu
+def test_iov_c1_queue_tier_gpu(gpu_ctx):
+    _body_c1_through_the_queue_tier(gpu_ctx, 1000)
