@@ -415,7 +415,7 @@ def run_ours(args):
             if iov:
                 touch = int(np.ctypeslib.as_array(api.C.cast(s.pool, api.u8p), shape=(16,))[0])      # touch the result
                 touch += int(np.ctypeslib.as_array(api.C.cast(s.iov, api.u64p), shape=(2,))[1])
-                out_bytes = int(s.pool_bytes) + 16 * int(s.n_iov) + 12 * N_USERS
+                out_bytes = int(s.pool_bytes) + int(s.pool2_bytes) + 16 * int(s.n_iov) + 12 * N_USERS
             else:
                 s = api._Streams()
                 ctx._ck(ctx.lib.nutsb_write_batch(ctx._h, o, s))
@@ -427,7 +427,7 @@ def run_ours(args):
                 # outside the timed passes: the lists describe every byte of every stream
                 lens = np.ctypeslib.as_array(api.C.cast(s.iov, api.u64p), shape=(int(s.n_iov), 2))[:, 1]
                 assert int(lens.sum()) == int(s.total_bytes), "gather lists do not add up to the streams"
-                r["extra"] = dict(pool_bytes=int(s.pool_bytes), n_iov=int(s.n_iov), stream_bytes=int(s.total_bytes))
+                r["extra"] = dict(pool_bytes=int(s.pool_bytes) + int(s.pool2_bytes), n_iov=int(s.n_iov), stream_bytes=int(s.total_bytes))
             if i > 0:
                 tt = ctx.timing()
                 r["h2d_ms"] += float(tt.h2d_ms); r["d2h_ms"] += float(tt.d2h_ms)

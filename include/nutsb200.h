@@ -209,11 +209,12 @@ int nutsb_write_batch_dev(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_streams *o
  * same rendered bytes to every listener of a room (write_room_except's loop, c:1409-1428, calls write_user
  * per recipient); here they cross PCIe once per colour setting instead of once per recipient.  User u's
  * stream is the concatenation of iov[first[u]] .. iov[first[u] + count[u] - 1] (zero-length pieces
- * occur); every piece points into `pool`, pinned host memory owned by the context:
+ * occur); every piece points into `pool` or `pool2`, pinned host memory owned by the context:
  *     writev(user->socket, (const struct iovec *)(s.iov + s.first[u]), s.count[u]);   (in chunks of IOV_MAX)
  * nutsb_iovec has the layout of struct iovec on LP64.  Concatenated, the pieces are byte for byte the
  * stream nutsb_write_batch returns for u (off[] is the same array).  pool = every room / level op
- * rendered once per colour setting + every write_user op rendered once for its recipient.  With
+ * rendered once per colour setting (copied to the host while the device is still planning), pool2 = every
+ * write_user op rendered once for its recipient.  With
  * recipients behind a filter (login / ignall / ignshout users, write_level ops in the batch) the pool is
  * the full streams and every user has one piece: same result, no saving.  Valid until the next write
  * batch / flush / destroy on the context. */
@@ -227,8 +228,10 @@ typedef struct nutsb_iov_streams {
     const uint32_t    *count;          /* n_users                                            */
     const nutsb_iovec *iov;
     uint64_t           n_iov;
-    const uint8_t     *pool;
-    uint64_t           pool_bytes;     /* bytes brought back from the device                 */
+    const uint8_t     *pool;           /* room / level ops, once per colour setting (or the full streams) */
+    uint64_t           pool_bytes;
+    const uint8_t     *pool2;          /* write_user ops, once each (NULL when the pool is the streams)    */
+    uint64_t           pool2_bytes;
 } nutsb_iov_streams;
 int nutsb_write_batch_iov(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_iov_streams *out);
 

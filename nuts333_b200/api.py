@@ -59,7 +59,8 @@ class _Streams(C.Structure):
 class _IovStreams(C.Structure):
     _fields_ = [("n_users", C.c_int64), ("total_bytes", C.c_uint64), ("n_deliveries", C.c_uint64),
                 ("off", C.c_void_p), ("first", C.c_void_p), ("count", C.c_void_p), ("iov", C.c_void_p),
-                ("n_iov", C.c_uint64), ("pool", C.c_void_p), ("pool_bytes", C.c_uint64)]
+                ("n_iov", C.c_uint64), ("pool", C.c_void_p), ("pool_bytes", C.c_uint64),
+                ("pool2", C.c_void_p), ("pool2_bytes", C.c_uint64)]
 
 
 class Timing(C.Structure):
@@ -203,10 +204,15 @@ class IovStreams:
     point into the context's pinned pool, so this object is valid until the next batch on the context;
     user(u) / streams() gather the bytes a socket would receive."""
 
-    def __init__(self, off, first, count, iov, pool_addr, pool_bytes, n_deliveries, raw=None):
+    def __init__(self, off, first, count, iov, pools, n_deliveries, raw=None):
         self.off, self.first, self.count, self.iov = off, first, count, iov      # iov: u64[n_iov, 2] = (address, length)
-        self.pool_addr, self.pool_bytes, self.n_deliveries = int(pool_addr), int(pool_bytes), int(n_deliveries)
+        self.pools = [(int(a), int(n)) for a, n in pools]                       # (address, bytes) of the host pools
+        self.n_deliveries = int(n_deliveries)
         self.raw = raw
+
+    @property
+    def pool_bytes(self):
+        return sum(n for _, n in self.pools)
 
     @property
     def n_users(self):
@@ -388,7 +394,8 @@ class Context:
         first = np.ctypeslib.as_array(C.cast(st.first, u64p), shape=(max(U, 1),))[:U].copy()
         count = np.ctypeslib.as_array(C.cast(st.count, C.POINTER(C.c_uint32)), shape=(max(U, 1),))[:U].copy()
         iov = (np.ctypeslib.as_array(C.cast(st.iov, u64p), shape=(n, 2)).copy() if n else np.zeros((0, 2), np.uint64))
-        return IovStreams(off, first, count, iov, st.pool or 0, st.pool_bytes, st.n_deliveries, raw=st)
+        return IovStreams(off, first, count, iov, [(st.pool or 0, st.pool_bytes), (st.pool2 or 0, st.pool2_bytes)],
+                          st.n_deliveries, raw=st)
 
     def _host_streams(self, st) -> Streams:
         U = int(st.n_users)

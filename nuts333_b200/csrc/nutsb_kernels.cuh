@@ -1400,8 +1400,8 @@ struct IovArgs {
     const u64 *vp_on, *vp_off;
     const u32 *sv_ukey, *sv_slot; const u64 *dpre;
     u32 n_ev;
-    u64 host_pool;                  // address of the pool in host memory
-    u64 off_base, dir_base;         // pool offsets of the colour-off slab and of the direct renderings
+    u64 host_pool, host_dir;        // host addresses the slab's two renderings and the direct renderings are copied to
+    u64 off_base;                   // where the colour-off renderings start in the slab
     IovEnt *iov; u64 *first; u32 *count;
     u64 *deliveries;
 };
@@ -1424,7 +1424,7 @@ k_iov(IovArgs A)
         const u64 d0 = A.dpre[e], d1 = A.dpre[e + 1];
         const u64 i0 = 2ull * e + s;
         A.iov[i0] = nutsb_iov_ent(R + v0, v1 - v0);
-        A.iov[i0 + 1] = nutsb_iov_ent(A.host_pool + A.dir_base + d0, d1 - d0);
+        A.iov[i0 + 1] = nutsb_iov_ent(A.host_dir + d0, d1 - d0);
         if (e + 1 == si.e1) { const u64 w0 = vp[j + skip]; A.iov[i0 + 2] = nutsb_iov_ent(R + w0, vp[si.nb_room] - w0); }
         deliv -= (i64)skip;
     }

@@ -87,7 +87,7 @@ struct nutsb_ctx {
     DBuf d_runs, d_items, d_slab, d_bl_meta, d_slots;
     DBuf d_off, d_out, d_digest, d_ulen;
     DBuf d_dpre, d_dir, d_iov, d_iov_first, d_iov_cnt;           // gather-list mode (nutsb_write_batch_iov)
-    HBuf h_small, h_off, h_out, h_iov, h_iov_first, h_iov_cnt;
+    HBuf h_small, h_off, h_out, h_dir, h_iov, h_iov_first, h_iov_cnt;
     u64 last_total = 0; bool have_streams = false;
 
     // staging for the host-buffer entry points
@@ -370,7 +370,7 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
         &c->s_verb, &c->s_speaker, &c->s_body, &c->s_boff };
     for (DBuf *b : all) release(*b);
     release(c->h_small); release(c->h_off); release(c->h_out);
-    release(c->h_iov); release(c->h_iov_first); release(c->h_iov_cnt);
+    release(c->h_dir); release(c->h_iov); release(c->h_iov_first); release(c->h_iov_cnt);
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     for (auto &e : c->dep) if (e) cudaEventDestroy(e);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
@@ -658,7 +658,7 @@ static int status_to_error(nutsb_ctx *c, u32 st)
 // left in HBM for the caller to bring over; otherwise the streams are made as usual (compact = false).
 struct IovReq {
     bool compact = false;
-    u64 slab_span = 0, dir_base = 0, direct_bytes = 0, n_iov = 0;    // pool = [slab | direct renderings]
+    u64 slab_span = 0, direct_bytes = 0, n_iov = 0;      // h_out = the slab's two renderings, h_dir = the direct renderings
 };
 
 static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovReq *iv = nullptr)
@@ -717,6 +717,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
     if (E >= 0xfffffff0ull) return fail(c, NUTSB_E_RANGE, "more than 2^32 (room, op) entries in one batch%s");
     const bool has_level = (status & NUTSB_ST_HAS_LEVEL) != 0;
     const bool alias = c->all_simple && !has_level;
+    const bool compact = iv && alias && U > 0;                 // gather lists: plain listeners only
     const PopView pop = pop_view(c, has_level ? 1 : 0);
     const ClassSet &cs = c->cls[has_level ? 1 : 0];
 
@@ -792,6 +793,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
     u64 *counters = c->d_counters.as<u64>();
     if (off_base + slab_off >= (1ull << 40)) return fail(c, NUTSB_E_RANGE, "more than 2^40 bytes of rendered slab in one batch%s");
     TRY(ensure(c, c->d_slab, off_base + slab_off + 256));
+    if (compact) TRY(ensure_host(c, c->h_out, (size_t)(off_base + slab_off) + 64));      // before anything is queued on the side stream
     c->tm.slab_bytes = slab_on + slab_off;
     if (par) { CK(cudaEventRecord(c->dep[0], st)); CK(cudaStreamWaitEvent(sd, c->dep[0], 0)); }
     if (c->profiling) CK(cudaEventRecord(c->ev[1], sd));
@@ -805,6 +807,8 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
         c->tm.launches++;
     }
     if (c->profiling) CK(cudaEventRecord(c->ev[8], sd));
+    // gather lists: the slab is part of the result as it stands -- on its way to the host while the planning goes on
+    if (compact && off_base + slab_off) CK(cudaMemcpyAsync(c->h_out.p, c->d_slab.p, (size_t)(off_base + slab_off), cudaMemcpyDeviceToHost, sd));
     if (par) CK(cudaEventRecord(c->dep[1], sd));
 
     // -- D. events: sort by recipient slot, prefix of byte deltas
@@ -829,23 +833,22 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
         NUTSB_LAUNCH(cdiv((u64)U, 128), 128, st, k_slot_info, sa); CKL();
         c->tm.launches++;
     }
-    const bool compact = iv && alias && U > 0;                 // gather lists: plain listeners only
-    if (compact) {                                             // where each direct rendering goes in the pool
+    if (compact) {                                             // where each direct rendering goes in its pool
         TRY(ensure(c, c->d_dpre, (E + 2) * 8));
         TRY(run_scan(c, InDirectLen{ c->d_sv_ukey.as<u32>(), sv_slot, c->d_sv_delta.as<i32>(), c->d_slots.as<SlotInfo>(),
                                      c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>() }, OutU64{c->d_dpre.as<u64>()}, (i64)E, counts + 1));
     }
     TRY(ensure(c, c->d_room_tile_off, ((size_t)Rt + 2) * 4)); TRY(ensure(c, c->d_room_cell_off, ((size_t)Rt + 2) * 8));
     TRY(ensure(c, c->d_room_item_off, ((size_t)Rt + 2) * 4));
+    // read-back #2 (sizes): k_geometry writes them straight into pinned host memory (zero-copy: the context's
+    // h_small is device-accessible under unified addressing), so that nothing waits in a copy queue -- in
+    // gather-list mode the slab's copy to the host is in flight on the side stream by now
+    Sizes *hs = (Sizes *)(c->h_small.as<u8>() + 256);
     NUTSB_LAUNCH(1, NUTSB_SCAN_THREADS, st, k_geometry, pop, c->d_room_b_off.as<u32>(), c->d_off.as<u64>(), counts,
                  c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(),
-                 c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>(), c->d_sizes.as<Sizes>(),
+                 c->d_room_tile_off.as<u32>(), c->d_room_cell_off.as<u64>(), c->d_room_item_off.as<u32>(), hs,
                  compact ? c->d_dpre.as<u64>() : (const u64 *)nullptr); CKL();
     c->tm.launches++;
-
-    // -- read-back #2: sizes
-    Sizes *hs = (Sizes *)(c->h_small.as<u8>() + 256);
-    CK(cudaMemcpyAsync(hs, c->d_sizes.p, sizeof(Sizes), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const Sizes sz = *hs;
     if (sz.slab_on != slab_on || sz.slab_off != slab_off) return fail(c, NUTSB_E_CUDA, "internal: slab size mismatch%s");
@@ -854,13 +857,15 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
         //    list entry per stretch of slab bytes and per direct rendering (k_iov); no copy plan, no fan-out
         iv->compact = true;
         iv->slab_span = off_base + slab_off;
-        iv->dir_base = (iv->slab_span + 15) & ~(u64)15;
         iv->direct_bytes = sz.direct_bytes;
         iv->n_iov = 2ull * sz.n_events + (u64)U;
         TRY(ensure(c, c->d_dir, sz.direct_bytes + 64));
         TRY(ensure(c, c->d_iov, (size_t)iv->n_iov * sizeof(IovEnt)));
         TRY(ensure(c, c->d_iov_first, (size_t)U * 8)); TRY(ensure(c, c->d_iov_cnt, (size_t)U * 4));
-        TRY(ensure_host(c, c->h_out, (size_t)(iv->dir_base + sz.direct_bytes) + 64));      // its address goes into the entries
+        TRY(ensure_host(c, c->h_dir, (size_t)sz.direct_bytes + 64));                        // the entries hold host addresses
+        TRY(ensure_host(c, c->h_iov, (size_t)iv->n_iov * sizeof(IovEnt)));
+        TRY(ensure_host(c, c->h_iov_first, ((size_t)U + 1) * 8)); TRY(ensure_host(c, c->h_iov_cnt, ((size_t)U + 1) * 4));
+        TRY(ensure_host(c, c->h_off, ((size_t)U + 1) * 8));
         if (c->profiling) { CK(cudaEventRecord(c->ev[9], st)); }
         if (sz.n_events > 0) {
             DirectArgs da{ ops, pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_op.as<u32>(),
@@ -871,15 +876,21 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
         }
         if (c->profiling) { CK(cudaEventRecord(c->ev[3], st)); CK(cudaEventRecord(c->ev[10], st)); }
         IovArgs ia{ pop, c->d_slots.as<SlotInfo>(), c->d_vp_on.as<u64>(), c->d_vp_off.as<u64>(), c->d_sv_ukey.as<u32>(), sv_slot,
-                    c->d_dpre.as<u64>(), sz.n_events, (u64)(size_t)c->h_out.p, off_base, iv->dir_base,
+                    c->d_dpre.as<u64>(), sz.n_events, (u64)(size_t)c->h_out.p, (u64)(size_t)c->h_dir.p, off_base,
                     c->d_iov.as<IovEnt>(), c->d_iov_first.as<u64>(), c->d_iov_cnt.as<u32>(), counters };
         NUTSB_LAUNCH(cdiv(std::max<u64>(sz.n_events, (u64)U), 256), 256, st, k_iov, ia); CKL();
         c->tm.launches++;
-        if (c->profiling) CK(cudaEventRecord(c->ev[2], st));
-        if (par) CK(cudaStreamWaitEvent(st, c->dep[1], 0));    // the slab is rendered
-        if (c->profiling) CK(cudaEventRecord(c->ev[11], st));
+        if (c->profiling) { CK(cudaEventRecord(c->ev[2], st)); CK(cudaEventRecord(c->ev[11], st)); }
+        // the rest of the result, beside the slab's copy on the side stream
+        if (sz.direct_bytes) CK(cudaMemcpyAsync(c->h_dir.p, c->d_dir.p, (size_t)sz.direct_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_iov.p, c->d_iov.p, (size_t)iv->n_iov * sizeof(IovEnt), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_iov_first.p, c->d_iov_first.p, (size_t)U * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_iov_cnt.p, c->d_iov_cnt.p, (size_t)U * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(c->h_off.p, c->d_off.p, ((size_t)U + 1) * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h64 + 8, counters, 24, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
+        if (par) CK(cudaStreamWaitEvent(st, c->dep[1], 0));    // the slab is rendered and on the host
+        if (c->profiling) CK(cudaEventRecord(c->ev[6], st));
         CK(cudaStreamSynchronize(st));
         TRY(status_to_error(c, h32[4]));
         c->last_total = sz.total_bytes; c->have_streams = false;     // no streams in HBM (nutsb_stream_digests needs them)
@@ -889,6 +900,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
             CK(cudaEventElapsedTime(&c->tm.fanout_ms, c->ev[10], c->ev[2]));
             CK(cudaEventElapsedTime(&c->tm.direct_ms, c->ev[9], c->ev[3]));
             CK(cudaEventElapsedTime(&c->tm.total_ms, c->ev[0], c->ev[11]));
+            CK(cudaEventElapsedTime(&c->tm.d2h_ms, c->ev[11], c->ev[6]));      // what of the copies is left after the last kernel
         }
         c->tm.fanout_bytes_out = 0; c->tm.fanout_bytes_in = 0; c->tm.render_bytes_in = h64[10];
         out->n_users = U; out->total_bytes = sz.total_bytes; out->n_deliveries = h64[8];
@@ -1059,29 +1071,25 @@ static int fetch_iov(nutsb_ctx *c, const nutsb_streams &ds, const IovReq &iv, nu
 {
     cudaStream_t st = c->stream;
     const size_t U = (size_t)c->U;
-    TRY(ensure_host(c, c->h_off, (U + 1) * 8));
-    TRY(ensure_host(c, c->h_iov_first, (U + 1) * 8)); TRY(ensure_host(c, c->h_iov_cnt, (U + 1) * 4));
-    CK(cudaMemcpyAsync(c->h_off.p, ds.off, (U + 1) * 8, cudaMemcpyDeviceToHost, st));
-    u64 n_iov = 0, pool_bytes = 0;
+    u64 n_iov = 0;
+    out->pool2 = nullptr; out->pool2_bytes = 0;
     if (iv.compact) {
-        // h_out was sized by run_write (the entries hold addresses inside it)
-        n_iov = iv.n_iov; pool_bytes = iv.dir_base + iv.direct_bytes;
-        TRY(ensure_host(c, c->h_iov, (size_t)n_iov * sizeof(nutsb_iovec)));
-        if (iv.slab_span) CK(cudaMemcpyAsync(c->h_out.p, c->d_slab.p, (size_t)iv.slab_span, cudaMemcpyDeviceToHost, st));
-        if (iv.direct_bytes) CK(cudaMemcpyAsync(c->h_out.as<u8>() + iv.dir_base, c->d_dir.p, (size_t)iv.direct_bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(c->h_iov.p, c->d_iov.p, (size_t)n_iov * sizeof(nutsb_iovec), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(c->h_iov_first.p, c->d_iov_first.p, U * 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(c->h_iov_cnt.p, c->d_iov_cnt.p, U * 4, cudaMemcpyDeviceToHost, st));
-        if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
-        CK(cudaStreamSynchronize(st));
+        // run_write has brought everything over already (the slab while the planning went on)
+        n_iov = iv.n_iov;
+        out->pool_bytes = iv.slab_span;
+        out->pool2 = c->h_dir.as<u8>(); out->pool2_bytes = iv.direct_bytes;
     } else {
         // recipients behind filters (or nothing to send): the streams themselves, one piece per user
-        n_iov = U; pool_bytes = ds.total_bytes;
+        n_iov = U; out->pool_bytes = ds.total_bytes;
+        TRY(ensure_host(c, c->h_off, (U + 1) * 8));
+        TRY(ensure_host(c, c->h_iov_first, (U + 1) * 8)); TRY(ensure_host(c, c->h_iov_cnt, (U + 1) * 4));
         TRY(ensure_host(c, c->h_out, (size_t)ds.total_bytes + 16));
         TRY(ensure_host(c, c->h_iov, (U + 1) * sizeof(nutsb_iovec)));
+        CK(cudaMemcpyAsync(c->h_off.p, ds.off, (U + 1) * 8, cudaMemcpyDeviceToHost, st));
         if (ds.total_bytes) CK(cudaMemcpyAsync(c->h_out.p, ds.bytes, (size_t)ds.total_bytes, cudaMemcpyDeviceToHost, st));
         if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
         CK(cudaStreamSynchronize(st));
+        if (c->profiling) CK(cudaEventElapsedTime(&c->tm.d2h_ms, c->ev[4], c->ev[5]));
         const u64 *off = c->h_off.as<u64>();
         nutsb_iovec *v = c->h_iov.as<nutsb_iovec>();
         for (size_t u = 0; u < U; ++u) {
@@ -1089,11 +1097,10 @@ static int fetch_iov(nutsb_ctx *c, const nutsb_streams &ds, const IovReq &iv, nu
             c->h_iov_first.as<u64>()[u] = u; c->h_iov_cnt.as<u32>()[u] = 1;
         }
     }
-    if (c->profiling) CK(cudaEventElapsedTime(&c->tm.d2h_ms, c->ev[4], c->ev[5]));
     out->n_users = (int64_t)U; out->total_bytes = ds.total_bytes; out->n_deliveries = ds.n_deliveries;
     out->off = c->h_off.as<u64>(); out->first = c->h_iov_first.as<u64>(); out->count = c->h_iov_cnt.as<u32>();
     out->iov = c->h_iov.as<nutsb_iovec>(); out->n_iov = n_iov;
-    out->pool = c->h_out.as<u8>(); out->pool_bytes = pool_bytes;
+    out->pool = c->h_out.as<u8>();
     return NUTSB_OK;
 }
 
@@ -1729,9 +1736,7 @@ static int upload_speech(nutsb_ctx *c, i64 n, const u8 *verb, const i32 *speaker
     if (n <= 0) return NUTSB_OK;
     const u64 t0 = body_off[0], t1 = body_off[n];
     if (t1 < t0 || (t1 > t0 && !bodies)) return fail(c, NUTSB_E_INVAL, "bad body offsets%s");
-    u64 bad = 0;                                               // branch-free: the loop vectorises
-    for (i64 i = 0; i < n; ++i) bad |= (u64)(body_off[i + 1] < body_off[i]);
-    if (bad) return fail(c, NUTSB_E_INVAL, "body offsets are not monotone%s");
+    // (offsets that are not monotone inside [t0, t1] are caught on the device: k_speech_measure)
     TRY(ensure(c, c->s_body, (size_t)(t1 - t0) + 64));
     if (t1 > t0) CK(cudaMemcpyAsync(c->s_body.p, bodies + t0, (size_t)(t1 - t0), cudaMemcpyHostToDevice, c->stream));
     TRY(upload(c, c->s_boff, body_off, ((size_t)n + 1) * 8));

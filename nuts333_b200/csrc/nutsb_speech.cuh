@@ -162,6 +162,11 @@ k_speech_measure(SpeechView v, u32 *slot_len, u32 *status)
         return;
     }
     const u64 b0 = v.body_off[m], b1 = v.body_off[m + 1];
+    if (b1 < b0 || b0 < v.body_off[0] || b1 > v.body_off[v.n]) {       // not monotone: nothing is read through these offsets
+        atomicOr(status, NUTSB_ST_BAD_OFFSETS);
+        slot_len[3 * m] = slot_len[3 * m + 1] = slot_len[3 * m + 2] = 0;
+        return;
+    }
     const u32 blen = (u32)(b1 - b0);
     const u8 first = blen ? v.body[b0] : 0, last = blen ? v.body[b1 - 1] : 0;
     const i32 room = v.user_room[spk] < v.n_rooms ? v.user_room[spk] : -1;

@@ -349,6 +349,18 @@ def _full_size_properties(gpu_ctx, port, ops, us, n_rooms, verdict, expect_deliv
     # idempotence: the same batch again gives the same bytes
     st2 = gpu_ctx.write_batch(dict(ops, verdict=verdict) if verdict is not None else ops)
     assert (st2.off == st.off).all() and (gpu_ctx.stream_digests() == dg).all()
+    # the same batch as gather lists (nutsb_write_batch_iov): every user's pieces add up to its stream's
+    # length, the sampled users' gathered bytes are the oracle's, and the pool is a fraction of the streams
+    iv = gpu_ctx.write_batch_iov(dict(ops, verdict=verdict) if verdict is not None else ops)
+    assert (iv.off == st.off).all() and iv.n_deliveries == expect_deliveries
+    piece_user = np.repeat(np.arange(U), iv.count.astype(np.int64))
+    order = (np.repeat(iv.first.astype(np.int64), iv.count.astype(np.int64))
+             + np.arange(len(piece_user)) - np.repeat(np.cumsum(iv.count.astype(np.int64)) - iv.count.astype(np.int64), iv.count.astype(np.int64)))
+    per_user = np.bincount(piece_user, weights=iv.iov[order, 1].astype(np.float64), minlength=U).astype(np.int64)
+    assert (per_user == lens).all()
+    for u in sample:
+        assert iv.user(u) == d[int(o[u]):int(o[u + 1])].tobytes(), u
+    assert iv.pool_bytes * 8 < st.total_bytes
     return st
 
 

@@ -45,12 +45,11 @@ def _check(ctx, port, ops, users, n_rooms, verdict=None, expect_compact=None):
     o, d, nd = port.write_batch(ops, users, verdict=verdict)
     U = len(users["room"])
     assert iv.n_users == U and (iv.off == o).all() and iv.n_deliveries == int(nd.sum())
-    lo, hi = iv.pool_addr, iv.pool_addr + iv.pool_bytes
     for u in range(U):
         p = iv.pieces(u)
         assert int(p[:, 1].sum()) == int(o[u + 1] - o[u]), u
-        for a, n in p:                                  # every piece lies inside the pool
-            assert n == 0 or (lo <= int(a) and int(a) + int(n) <= hi), u
+        for a, n in p:                                  # every piece lies inside one of the pools
+            assert n == 0 or any(lo <= int(a) and int(a) + int(n) <= lo + sz for lo, sz in iv.pools), u
         assert iv.user(u) == d[int(o[u]):int(o[u + 1])].tobytes(), u
     if expect_compact is False:                         # recipients behind filters: the streams, one piece per user
         assert iv.n_iov == U and (iv.count == 1).all()

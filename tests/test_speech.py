@@ -92,6 +92,31 @@ def _check_composer(ctx, port, seed, U, NR, N):
     ctx.set_ban_swearing(False)
 
 
+def _check_bad_body_offsets(ctx):
+    """offsets that are not monotone are refused (caught on the device), for both result forms"""
+    ctx.set_users(np.zeros(2, np.int32), np.zeros(2, np.uint8), np.ones(2, np.uint8), 1)
+    ctx.set_user_names([b"Ua", b"Ub"], np.zeros(2, np.uint8))
+    bt = np.frombuffer(b"hello there, world", np.uint8).copy()
+    verb, spk = np.zeros(3, np.uint8), np.zeros(3, np.int32)
+    for bo in ([0, 12, 5, 18], [0, 40, 12, 18], [4, 2, 12, 18]):
+        for call in (ctx.speech_batch, ctx.speech_batch_iov):
+            with pytest.raises(api.NutsbError) as e:
+                call(verb, spk, bt, np.array(bo, np.uint64))
+            assert e.value.code == api.E_INVAL
+    assert ctx.speech_batch(verb, spk, bt, np.array([0, 5, 12, 18], np.uint64)).total_bytes > 0
+
+
+def test_composer_bad_offsets_on_emulator(sim_lib):
+    ctx = api.Context(0, sim_lib)
+    _check_bad_body_offsets(ctx)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_composer_bad_offsets_on_gpu(gpu_ctx):
+    _check_bad_body_offsets(gpu_ctx)
+
+
 def test_composer_on_emulator(sim_lib, port):
     ctx = api.Context(0, sim_lib)
     _check_composer(ctx, port, 4, 30, 3, 120)
