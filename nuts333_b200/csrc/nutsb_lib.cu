@@ -1712,7 +1712,7 @@ static int run_speech(nutsb_ctx *c, i64 n, const u8 *verb, const i32 *speaker, c
     TRY(status_to_error(c, h32[4]));
     const u64 text_bytes = h64[0];
     TRY(ensure(c, c->d_sp_text, text_bytes + 64));
-    NUTSB_LAUNCH(cdiv((u64)n * 32, 256), 256, st, k_speech_compose, v, c->d_sp_off.as<u64>(), c->d_sp_text.as<u8>(),
+    NUTSB_LAUNCH(cdiv((u64)n * NUTSB_SPEECH_GROUP, 256), 256, st, k_speech_compose, v, c->d_sp_off.as<u64>(), c->d_sp_text.as<u8>(),
                  c->d_sp_kind.as<u8>(), c->d_sp_target.as<i32>(), c->d_sp_except.as<i32>(), c->d_sp_flags.as<u8>(), c->d_sp_gate.as<i32>()); CKL();
     TRY(verdict_dev(c, V_SWEAR, n, bodies, body_off, c->d_sp_verdict.as<u8>()));
     nutsb_ops o{ (i64)n3, c->d_sp_text.as<u8>(), c->d_sp_off.as<u64>(), c->d_sp_kind.as<u8>(), c->d_sp_target.as<i32>(),
