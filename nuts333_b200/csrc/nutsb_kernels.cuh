@@ -1283,6 +1283,13 @@ k_fanout_direct(FanoutArgs F, DirectArgs D, u32 n_dir, u32 stride)
     nutsb_fanout_block(F, b - (before < n_dir ? before : n_dir), s_dyn);
 }
 
+// the counters and the status at the end of a write batch, zero-copy as k_readback1
+__global__ void k_readback_end(const u64 *counters, const u32 *status, u64 *h_counters, u32 *h_status)
+{
+    if (threadIdx.x < 3) h_counters[threadIdx.x] = counters[threadIdx.x];
+    if (threadIdx.x == 0) *h_status = *status;
+}
+
 // ---- stream digests ------------------------------------------------------------------------
 // h = fold(h * P + byte), h0 = FNV offset basis.  A block per user: each thread
 // folds a contiguous slice as an affine map (mult, add), the block composes them
@@ -1314,6 +1321,16 @@ k_digest(const u8 *bytes, const u64 *off, i32 n_users, u64 *digest)
 }
 
 // ---- small bookkeeping kernels -----------------------------------------------------------
+// read-back #1, written straight into pinned host memory (zero-copy): the number of (room, op) entries, the
+// validation status and the slab totals -- one launch instead of three small copies in the copy queue
+__global__ void __launch_bounds__(64)
+k_readback1(const u64 *eoff_end, const u32 *status, const u64 *slab_tot, u64 *h_entries, u32 *h_status, u64 *h_slab_tot)
+{
+    const u32 t = threadIdx.x;
+    if (t == 0) { *h_entries = *eoff_end; *h_status = *status; }
+    if (t < 2 * NUTSB_SLAB_TOT_WAYS) h_slab_tot[t] = slab_tot[t];
+}
+
 // counts[0] = slab ops, counts[1] = events (from the packed entry scan's total)
 __global__ void k_counts(const u64 *e_scan, i64 n_ent, u32 *counts)
 {

@@ -704,9 +704,10 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
     TRY(run_scan(c, InU32{nrep}, OutU64{c->d_eoff.as<u64>()}, n, nullptr));
 
     // -- read-back #1: number of (room, op) entries, validation status
-    CK(cudaMemcpyAsync(h64, c->d_eoff.as<u64>() + n, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h64 + 64, c->d_counters.as<u64>() + 8, 16 * NUTSB_SLAB_TOT_WAYS, cudaMemcpyDeviceToHost, st));
+    static_assert(2 * NUTSB_SLAB_TOT_WAYS <= 64, "k_readback1 copies the slab totals with one block of 64 threads");
+    NUTSB_LAUNCH(1, 64, st, k_readback1, c->d_eoff.as<u64>() + n, c->d_status.as<u32>(), c->d_counters.as<u64>() + 8,
+                 h64, h32 + 4, h64 + 64); CKL();
+    c->tm.launches++;
     CK(cudaStreamSynchronize(st));
     const u64 E = h64[0]; const u32 status = h32[4];
     u64 slab_on = 0, slab_off = 0;
@@ -973,8 +974,8 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
     if (par) CK(cudaStreamWaitEvent(st, c->dep[3], 0));
     if (c->profiling) CK(cudaEventRecord(c->ev[11], st));
 
-    CK(cudaMemcpyAsync(h64 + 8, counters, 24, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h32 + 4, c->d_status.p, 4, cudaMemcpyDeviceToHost, st));
+    NUTSB_LAUNCH(1, 32, st, k_readback_end, counters, c->d_status.as<u32>(), h64 + 8, h32 + 4); CKL();
+    c->tm.launches++;
     CK(cudaStreamSynchronize(st));
     TRY(status_to_error(c, h32[4]));
     c->last_total = sz.total_bytes; c->have_streams = true;
