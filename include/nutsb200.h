@@ -316,7 +316,8 @@ int nutsb_colour_com_strip_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes
 
 /* Position-weighted 64-bit digest of every user's stream, computed on the
  * device from the last write batch: h = fold(h*0x100000001b3 + byte) over the
- * stream, h0 = 0xcbf29ce484222325.  digest[n_users] is a HOST array. */
+ * stream, h0 = 0xcbf29ce484222325.  digest[n_users] is a HOST array.  NUTSB_E_STATE after a
+ * gather-list batch that never built the streams (plain listeners: nothing to digest in HBM). */
 int nutsb_stream_digests(nutsb_ctx *ctx, uint64_t *digest);
 
 /* ---- queue tier: the reference's call surface, one call each ------------ */

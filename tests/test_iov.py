@@ -101,6 +101,14 @@ def _body_edges(ctx, port):
         ops = dict(text=text, off=off, kind=np.array(kind, np.uint8), target=np.array(target, np.int32),
                    except_user=np.array(exc, np.int32), flags=np.zeros(len(kind), np.uint8))
         _check(ctx, port, ops, users, 2, expect_compact=True)
+    # the streams were never built in HBM: nothing to digest (the streams call builds them again)
+    ctx.set_users(users["room"], users["flags"], users["level"], 2)
+    ctx.write_batch_iov(ops)
+    with pytest.raises(api.NutsbError) as e:
+        ctx.stream_digests()
+    assert e.value.code == api.E_STATE
+    ctx.write_batch(ops)
+    assert len(ctx.stream_digests()) == 4
     # no users at all
     ctx.set_users(np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.uint8), 2)
     iv = ctx.write_batch_iov(dict(ops, kind=np.ones(4, np.uint8), target=np.array([0, 1, -1, 0], np.int32),
