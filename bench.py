@@ -495,7 +495,11 @@ def run_ours(args):
                                 direct_ms=kstate["direct_ms"] / ks),
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                                   traffic=traffic, kernel="k_fanout", peak_source=peak_src,
-                                  algorithmic_bytes_per_launch=fan_bytes),
+                                  algorithmic_bytes_per_launch=fan_bytes,
+                                  frac_of_spec_8000=achieved / 8000.0,          # both percentages
+                                  whole_step=dict(achieved=(dev_state["bytes"] / max(1, args.steps) + input_bytes) / (ms_max / max(1, args.steps) * 1e-3) / 1e9,
+                                                  unit="GB/s", note="stream bytes written + input bytes read per step / ms_per_step (rank 0): "
+                                                                    "what the planning, rendering and verdict kernels cost on top of the fan-out")),
                     e2e=(None if args.no_e2e else
                          dict(value=total_e2e_deliv / (e2e_ms_max * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d,
                               d2h_bytes_per_step=d2h, steps=e2e_steps, ms_per_step=e2e_ms_max / e2e_steps,
