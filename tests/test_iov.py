@@ -86,6 +86,29 @@ def _body_random(ctx, port, seeds, sizes, again=True):
         _check(ctx, port, ops, users, NR, expect_compact=plain, again=again)
 
 
+def _body_long_strings(ctx, port, n_texts):
+    """strings of up to 2000 bytes dense in newlines / commands: renderings of up to 12 KB cross the
+    renderer's shared-memory windows in k_direct_compact and k_render; plain listeners, so the lists are compact"""
+    rng = np.random.default_rng(11)
+    alphabet = np.frombuffer(b"~/\n" + b"FRSOLKBGTWYMUIV" + b"xy z", np.uint8)
+    texts = []
+    for i in range(n_texts):
+        n = int(rng.integers(0, 2001)) if i % 3 else int(rng.integers(0, 40))
+        w = np.ones(len(alphabet)); w[:3] = (8, 2, 6) if i % 2 else (1, 1, 1)
+        texts.append(rng.choice(alphabet, size=n, p=w / w.sum()).tobytes())
+    texts[1] = b"\n" * 2000
+    texts[2] = b"~FR" * 666
+    text, off = O.pack(texts)
+    n = len(texts)
+    kind = rng.integers(0, 2, n).astype(np.uint8)
+    ops = dict(text=text, off=off, kind=kind,
+               target=np.where(kind == 0, rng.integers(0, 7, n), rng.integers(-1, 2, n)).astype(np.int32),
+               except_user=rng.integers(-1, 7, n).astype(np.int32), flags=np.zeros(n, np.uint8))
+    users = dict(room=np.array([0, 0, 0, 1, 1, 0, -1], np.int32), flags=np.array([1, 0, 1, 0, 1, 1, 0], np.uint8),
+                 level=np.ones(7, np.uint8))
+    _check(ctx, port, ops, users, 2, expect_compact=True, again=False)
+
+
 def _body_edges(ctx, port):
     users = dict(room=np.array([0, 0, -1, 1], np.int32), flags=np.array([1, 0, 1, 0], np.uint8), level=np.ones(4, np.uint8))
     e = dict(text=np.zeros(0, np.uint8), off=np.zeros(1, np.uint64), kind=np.zeros(0, np.uint8), target=np.zeros(0, np.int32),
@@ -161,6 +184,12 @@ def test_iov_random_and_edges_sim(sim_lib, port):
     ctx.close()
 
 
+def test_iov_long_strings_sim(sim_lib, port):
+    ctx = api.Context(0, sim_lib)
+    _body_long_strings(ctx, port, 24)
+    ctx.close()
+
+
 def test_iov_c1_queue_tier_sim(sim_lib):
     ctx = api.Context(0, sim_lib)
     _body_c1_through_the_queue_tier(ctx, 40)
@@ -179,6 +208,11 @@ def test_iov_random_and_edges_gpu(gpu_ctx, port):
     _body_random(gpu_ctx, port, range(200, 230),
                  [(1, 1, 5, 20), (40, 3, 400, 40), (300, 2, 900, 30), (1000, 1, 300, 60), (64, 70, 5000, 25),
                   (7, 1, 2000, 1990), (129, 5, 257, 400)])
+
+
+@pytest.mark.gpu
+def test_iov_long_strings_gpu(gpu_ctx, port):
+    _body_long_strings(gpu_ctx, port, 300)
 
 
 @pytest.mark.gpu
