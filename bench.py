@@ -469,13 +469,45 @@ def run_ours(args):
         assert leg_v["deliv"] == leg_s["deliv"] == leg_p["deliv"], (leg_s["deliv"], leg_v["deliv"], leg_p["deliv"])
         assert leg_v["extra"]["stream_bytes"] == leg_p["extra"]["stream_bytes"]
     e2e_h2d_ms, e2e_d2h_ms, e2e_ms, e2e_deliv, h2d, d2h = (leg_s[k] for k in ("h2d_ms", "d2h_ms", "ms", "deliv", "h2d", "d2h"))
+
+    # ---- the last leg again with two calls in flight (two contexts, two host threads): one call's H2D and
+    #      kernels run under the other's D2H (PCIe is full duplex: scripts/probes/pcie_probe.py)
+    pipe_ms, pipe_deliv = 0.0, 0
+    if not args.no_e2e:
+        c2 = api.Context(local)
+        c2.set_swear_words(inp["words"]); c2.set_ban_files(inp["sfile"], inp["ufile"])
+        c2.set_users(users["room"], users["flags"], users["level"], inp["n_rooms"])
+        c2.set_user_names([un[int(uo[u]):int(uo[u + 1])].tobytes() for u in range(N_USERS)], np.zeros(N_USERS, np.uint8))
+        c2.set_ban_swearing(True)
+        got = [0, 0]
+
+        def pipe_worker(k, cx, reps):
+            for _ in range(reps):
+                cx.site_banned_batch(st_, so_); cx.user_banned_batch(nt_, no_)
+                s = api._IovStreams()
+                cx._ck(cx.lib.nutsb_speech_batch_iov(cx._h, N_MSGS, api._addr(sp_verb), api._addr(sp_spk), api._addr(bt), api._addr(bo), s))
+                got[k] += int(s.n_deliveries)
+
+        for reps in (1, e2e_steps):                        # first round allocates the second context's buffers
+            got[0] = got[1] = 0
+            barrier()
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=pipe_worker, args=(k, cx, reps)) for k, cx in enumerate((ctx, c2))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            torch.cuda.synchronize()
+            pipe_ms = (time.perf_counter() - t0) * 1e3
+        pipe_deliv = got[0] + got[1]
+        c2.close()
     # ---- reduce over ranks
-    vals = torch.tensor([ms, e2e_ms, leg_v["ms"], leg_p["ms"], two_ms], dtype=torch.float64, device=dev)
-    sums = torch.tensor([dev_state["deliv"], e2e_deliv, dev_state["launches"], leg_v["deliv"]], dtype=torch.float64, device=dev)
+    vals = torch.tensor([ms, e2e_ms, leg_v["ms"], leg_p["ms"], two_ms, pipe_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([dev_state["deliv"], e2e_deliv, dev_state["launches"], leg_v["deliv"], pipe_deliv], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max, iov_ms_max, sp_ms_max, two_ms_max = (float(vals[i]) for i in range(5))
+    ms_max, e2e_ms_max, iov_ms_max, sp_ms_max, two_ms_max, pipe_ms_max = (float(vals[i]) for i in range(6))
     total_deliv, total_e2e_deliv, total_launch, total_iov_deliv = float(sums[0]), float(sums[1]), int(sums[2]), float(sums[3])
 
     if rank == 0:
@@ -546,6 +578,9 @@ def run_ours(args):
                                           d2h_bytes_per_step=leg_p["d2h"], steps=e2e_steps, ms_per_step=sp_ms_max / e2e_steps,
                                           input="verb, speaker and body of every line (nutsb_speech_batch_iov): swear verdicts, "
                                                 "say()'s composition and the rendering all on the device", **leg_p["extra"])
+            line["e2e_speech_iov"]["two_calls_in_flight"] = dict(
+                value=float(sums[4]) / (pipe_ms_max * 1e-3), ms_per_step=pipe_ms_max / (2 * e2e_steps),
+                note="two contexts / host threads per GPU, %d calls each: one call's H2D and kernels under the other's D2H" % e2e_steps)
         if world == 1 and not args.no_cpu_baseline:
             procs = 1
             dcpu, nbytes, busy, wall, kind = reference_step(0, 40_000, 4_000, procs)
