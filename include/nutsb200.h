@@ -25,8 +25,9 @@
  *
  * Semantics are bit-exact with nuts333.c for USER_TYPE recipients, for clones (the
  * relay of c:1416-1426) and for remote users (the MSG/EMSG framing of c:1299-1307):
- * both are made by the queue tier (nutsb_set_clones, nutsb_set_remotes); the batch
- * tiers take ops as given, clones and remote users receive nothing there.
+ * both are made on the host by the queue tier and by the host-buffer batch calls
+ * (nutsb_set_clones, nutsb_set_remotes); the device-buffer calls refuse such a
+ * population (NUTSB_E_UNSUPPORTED).
  *
  * Errors: every entry point returns 0 or a negative NUTSB_E_* code and never
  * aborts the host; on error outputs are left untouched.  One context per host
@@ -50,7 +51,7 @@ enum {
     NUTSB_E_INVAL       = -1,  /* bad argument (NULL, negative count, offsets not monotone) */
     NUTSB_E_NOMEM       = -2,  /* host or device allocation failed                          */
     NUTSB_E_CUDA        = -3,  /* CUDA runtime error, see nutsb_last_error()                */
-    NUTSB_E_UNSUPPORTED = -4,  /* remote (netlink) recipients              */
+    NUTSB_E_UNSUPPORTED = -4,  /* device-buffer batch over a population with clones / remote users */
     NUTSB_E_RANGE       = -5,  /* string longer than NUTSB_MAX_TEXT, index out of range     */
     NUTSB_E_STATE       = -6   /* call order (e.g. write batch before nutsb_set_users)      */
 };
@@ -194,11 +195,24 @@ int nutsb_get_ban_file(nutsb_ctx *ctx, int which, const void **bytes, size_t *le
  * c:2683-2691).  room[u] in [0,n_rooms) or -1 (user->room==NULL). */
 int nutsb_set_users(nutsb_ctx *ctx, int32_t n_users, int32_t n_rooms, const int32_t *room,
                     const uint8_t *flags, const uint8_t *level);
+/* The same when users joined or left (the list positions shift): prev_index[u] = the index user u had in
+ * the population before, -1 for a new user (create_user() starts with empty buffers, c:2747); NULL = nobody
+ * moved.  Queued ops name users by index, so both calls return NUTSB_E_STATE while anything is queued
+ * (nutsb_q_pending() > 0): flush first, then bring the new population in.  The review buffers of the rooms and
+ * the revtell buffers of the users live on across the call (the reference clears them only in create_room,
+ * create_user and clear_revbuff). */
+int nutsb_set_users_remap(nutsb_ctx *ctx, int32_t n_users, int32_t n_rooms, const int32_t *room,
+                          const uint8_t *flags, const uint8_t *level, const int32_t *prev_index);
 
 /* ---- batch tier --------------------------------------------------------- */
 
 /* write_user / write_room[_except] / write_level, batched.  Host variant:
- * ops in host memory, streams returned in pinned host memory. */
+ * ops in host memory, streams returned in pinned host memory.  With clones or remote users in the
+ * population (NUTSB_UF_CLONE / NUTSB_UF_REMOTE) the host-buffer calls (nutsb_write_batch, nutsb_write_batch_iov)
+ * expand every op on the host exactly as the queue tier does -- the relays of nuts333.c:1416-1426 and the
+ * MSG/EMSG frames of c:1299-1307, each under the op's own gate -- before the batch runs (needs an empty queue,
+ * nutsb_set_clones / nutsb_set_remotes); the device-buffer calls (*_dev, nutsb_speech_batch*) take ops as they
+ * are and return NUTSB_E_UNSUPPORTED for such a population rather than deliver different bytes. */
 int nutsb_write_batch(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_streams *out);
 /* Device variant: every pointer in ops is a device pointer; streams stay in HBM.  The packed text is read
  * in aligned 16-byte vectors: it must be readable from the 16-byte boundary at or before its first byte to the
@@ -296,8 +310,9 @@ int nutsb_q_record(nutsb_ctx *ctx, int32_t room, const char *str);
 /* tell c:4128 / pemote c:4234 after their argument checks (`target` = what get_user found: not the speaker, not
  * afk / ignoring / offsite -- the talker's state): the muzzle refusal, or the two lines ("~OLYou tell X:~RS ..." /
  * "~OLX tells you:~RS ...", ask for a trailing '?'; "~OL(To X)~RS ..." / "~OL>>~RS ...") and record_tell c:2074.
- * wizshout c:6527: muzzle refusal, ban_swearing branch, then the speaker's line and write_level(lev or WIZ, 1,
- * line, user); lev < 0 = no level word, else level_name[lev] and inpstr without it.  revtell c:7699 replays the
+ * wizshout c:6527: muzzle refusal, ban_swearing branch (asked of the whole line, c:6541), then the speaker's line
+ * and write_level(lev or WIZ, 1, line, user); inpstr = the whole line; lev < 0 = no level word, else the level
+ * word is taken off inside (remove_first, c:6553) and level_name = level_name[lev].  revtell c:7699 replays the
  * user's five-line buffer through write_user.  Need nutsb_set_user_names. */
 int nutsb_q_tell(nutsb_ctx *ctx, int32_t user, int32_t target, const char *inpstr);
 int nutsb_q_pemote(nutsb_ctx *ctx, int32_t user, int32_t target, const char *inpstr);
@@ -329,6 +344,10 @@ int nutsb_q_write_room_except(nutsb_ctx *ctx, int32_t room, const char *str, int
                               int force_listen, int shout);                       /* c:1401 */
 int nutsb_q_write_level(nutsb_ctx *ctx, int level, int above, const char *str,
                         int32_t except_user);                                     /* c:1372 */
+/* write_sock(sock, str) (c:1281-1286) to the socket of user `sock_user` (or of a netlink's pseudo-user): the
+ * bytes as they are (NUTSB_OF_RAW), in order with everything else queued for that socket.  A socket that is
+ * nobody's (accept_connection's refusal, c:280) is the host's own write(2) -- after a flush. */
+int nutsb_q_write_sock(nutsb_ctx *ctx, int32_t sock_user, const char *str);
 /* One fgets() chunk of a paged file as more() writes it (c:2254-2300): the byte machine of
  * write_user without the closing reset; plain != 0 when more() was called with user==NULL. */
 int nutsb_q_page_line(nutsb_ctx *ctx, int32_t sock_user, const char *str, int plain);
@@ -342,7 +361,11 @@ int nutsb_q_more(nutsb_ctx *ctx, int32_t user, int32_t sock_user, const void *fi
                  int64_t *filepos, int *retval);
 int64_t nutsb_q_pending(const nutsb_ctx *ctx);
 /* Runs everything queued since the last flush; the host then write()s each
- * user's stream to its socket. */
+ * user's stream to its socket.  The queue is emptied when the batch has run and when it can never run
+ * (a validation error); after NUTSB_E_NOMEM / NUTSB_E_CUDA it is kept -- ops, swear bodies, pending
+ * record() calls -- so that the flush can be tried again, and the review buffers take the queued lines
+ * only once the batch that delivers them has succeeded.  A queue call that fails (NUTSB_E_RANGE: a relay
+ * or frame over NUTSB_MAX_TEXT) queues nothing. */
 int nutsb_flush(nutsb_ctx *ctx, nutsb_streams *out);
 /* The same with gather lists as the result (nutsb_write_batch_iov): the host writev()s each user's list. */
 int nutsb_flush_iov(nutsb_ctx *ctx, nutsb_iov_streams *out);

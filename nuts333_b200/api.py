@@ -74,14 +74,14 @@ class Timing(C.Structure):
 EXPORTS = [
     "nutsb_version", "nutsb_strerror", "nutsb_last_error", "nutsb_create", "nutsb_destroy",
     "nutsb_set_profiling", "nutsb_get_timing", "nutsb_set_overlap", "nutsb_set_stream", "nutsb_set_swear_words",
-    "nutsb_set_ban_files", "nutsb_ban_edit", "nutsb_get_ban_file", "nutsb_set_users", "nutsb_set_clones", "nutsb_set_remotes", "nutsb_set_room_names", "nutsb_write_batch", "nutsb_write_batch_dev", "nutsb_write_batch_iov",
+    "nutsb_set_ban_files", "nutsb_ban_edit", "nutsb_get_ban_file", "nutsb_set_users", "nutsb_set_users_remap", "nutsb_set_clones", "nutsb_set_remotes", "nutsb_set_room_names", "nutsb_write_batch", "nutsb_write_batch_dev", "nutsb_write_batch_iov",
     "nutsb_contains_swearing_batch", "nutsb_contains_swearing_batch_dev", "nutsb_site_banned_batch",
     "nutsb_site_banned_batch_dev", "nutsb_user_banned_batch", "nutsb_user_banned_batch_dev",
     "nutsb_set_user_names", "nutsb_set_ban_swearing", "nutsb_speech_batch", "nutsb_speech_batch_dev", "nutsb_speech_batch_iov", "nutsb_q_speech",
     "nutsb_q_record", "nutsb_q_review", "nutsb_q_review_clear",
     "nutsb_q_tell", "nutsb_q_pemote", "nutsb_q_wizshout", "nutsb_q_revtell",
     "nutsb_colour_com_count_batch", "nutsb_colour_com_strip_batch", "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
-    "nutsb_q_write_level", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_flush_iov", "nutsb_contains_swearing",
+    "nutsb_q_write_level", "nutsb_q_write_sock", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_flush_iov", "nutsb_contains_swearing",
     "nutsb_site_banned", "nutsb_user_banned",
 ]
 
@@ -108,6 +108,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_set_swear_words.argtypes = [vp, C.POINTER(C.c_char_p)]
     lib.nutsb_set_ban_files.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
     lib.nutsb_set_users.argtypes = [vp, C.c_int32, C.c_int32, i32p, u8p, u8p]
+    lib.nutsb_set_users_remap.argtypes = [vp, C.c_int32, C.c_int32, i32p, u8p, u8p, i32p]
+    lib.nutsb_q_write_sock.argtypes = [vp, C.c_int32, C.c_char_p]
     lib.nutsb_write_batch.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_Streams)]
     lib.nutsb_write_batch_dev.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_Streams)]
     lib.nutsb_write_batch_iov.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_IovStreams)]
@@ -279,10 +281,16 @@ class Context:
         """Raw bytes of datafiles/siteban and datafiles/userban; None = file missing."""
         self._ck(self.lib.nutsb_set_ban_files(self._h, siteban, len(siteban or b""), userban, len(userban or b"")))
 
-    def set_users(self, room, flags, level, n_rooms: int):
+    def set_users(self, room, flags, level, n_rooms: int, prev_index=None):
+        """prev_index[u]: the index user u had in the population before (-1: new), when users joined or left"""
         room, flags, level = _np(room, np.int32), _np(flags, np.uint8), _np(level, np.uint8)
-        self._ck(self.lib.nutsb_set_users(self._h, len(room), n_rooms, room.ctypes.data_as(i32p),
-                                          flags.ctypes.data_as(u8p), level.ctypes.data_as(u8p)))
+        if prev_index is None:
+            self._ck(self.lib.nutsb_set_users(self._h, len(room), n_rooms, room.ctypes.data_as(i32p),
+                                              flags.ctypes.data_as(u8p), level.ctypes.data_as(u8p)))
+        else:
+            prev = _np(prev_index, np.int32)
+            self._ck(self.lib.nutsb_set_users_remap(self._h, len(room), n_rooms, room.ctypes.data_as(i32p),
+                                                    flags.ctypes.data_as(u8p), level.ctypes.data_as(u8p), prev.ctypes.data_as(i32p)))
         self.n_users = len(room)
 
     def set_user_names(self, names, speech_flags):
@@ -492,6 +500,10 @@ class Talker:
     def write_level(self, level, above, s, user):                    # c:1372
         c = self.ctx
         c._ck(c.lib.nutsb_q_write_level(c._h, level, 1 if above else 0, self._s(s), -1 if user is None else user))
+
+    def write_sock(self, sock_user, s):                              # c:1281, a user's own socket
+        c = self.ctx
+        c._ck(c.lib.nutsb_q_write_sock(c._h, sock_user, self._s(s)))
 
     def _speech(self, verb, user, inpstr):
         c = self.ctx

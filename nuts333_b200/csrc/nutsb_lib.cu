@@ -63,7 +63,8 @@ struct nutsb_ctx {
     std::vector<u8> ban_bytes[2];   // the two lists as they stand on disk (nutsb_ban_edit edits them)
 
     // population
-    bool have_users = false, all_simple = true, has_clones = false;
+    bool have_users = false, all_simple = true, has_clones = false;   // has_clones: some user is a clone or a remote user
+    i32 n_clone_flag = 0, n_remote_flag = 0;
     i32 U = 0, R = 0, Rt = 1;
     std::vector<i32> user_room, user_slot, slot_user, room_slot_off;
     std::vector<u8> uflags, ulevel;
@@ -573,19 +574,34 @@ static int build_classes(nutsb_ctx *c, ClassSet &cs, bool with_level, const std:
     return NUTSB_OK;
 }
 
-NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, const int32_t *room,
-                               const uint8_t *flags, const uint8_t *level)
+static int set_users_impl(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, const int32_t *room,
+                          const uint8_t *flags, const uint8_t *level, const int32_t *prev_index)
 {
     if (!c || n_users < 0 || n_rooms < 0 || (n_users && (!room || !flags || !level))) return fail(c, NUTSB_E_INVAL, "nutsb_set_users: bad argument%s");
     CK(cudaSetDevice(c->device));
     for (i32 u = 0; u < n_users; ++u) {
         if (room[u] >= n_rooms || room[u] < -1) return fail(c, NUTSB_E_RANGE, "user room out of range%s");
     }
+    // queued ops name users and rooms by their index in the population they were queued under: a new
+    // population may only come in between two flushes
+    if (!c->q_kind.empty() || !c->q_rec.empty())
+        return fail(c, NUTSB_E_STATE, "nutsb_set_users with ops still queued: flush first%s");
     c->have_users = false; c->have_streams = false;
+    // review buffers live as long as their room / user does (the reference clears them in create_room c:2799,
+    // create_user c:2747 and clear_revbuff c:2626 only): room r keeps buffer r; user u keeps the buffer of
+    // prev_index[u] (nutsb_set_users_remap), index u itself without a map; new rooms / users start empty
+    {
+        std::vector<nutsb_ctx::RevBuf> rev((size_t)n_rooms, nutsb_ctx::RevBuf{});
+        for (size_t r = 0; r < rev.size() && r < c->rev.size(); ++r) rev[r] = c->rev[r];
+        c->rev.swap(rev);
+        std::vector<nutsb_ctx::TellBuf> rt((size_t)n_users, nutsb_ctx::TellBuf{});
+        for (i32 u = 0; u < n_users; ++u) {
+            const i32 p = prev_index ? prev_index[u] : u;
+            if (p >= 0 && (size_t)p < c->revtell.size()) rt[(size_t)u] = c->revtell[(size_t)p];
+        }
+        c->revtell.swap(rt);
+    }
     c->U = n_users; c->R = n_rooms; c->Rt = n_rooms + 1;
-    c->rev.assign((size_t)n_rooms, nutsb_ctx::RevBuf{});        // create_room() clears them, c:2799
-    c->revtell.assign((size_t)n_users, nutsb_ctx::TellBuf{});   // create_user(), c:2747
-    c->q_rec.clear();
     c->user_room.resize(n_users);
     for (i32 u = 0; u < n_users; ++u) c->user_room[u] = room[u] < 0 ? n_rooms : room[u];
     // slot order: (room, flags, level, index) -- compatible with both class granularities
@@ -602,9 +618,11 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     c->all_simple = true;
     for (i32 u = 0; u < n_users; ++u) if (flags[u] & NUTSB_UF_FILTERED) c->all_simple = false;
     c->uflags.assign(flags, flags + n_users);
-    c->has_clones = false;
-    for (i32 u = 0; u < n_users; ++u) if (flags[u] & (NUTSB_UF_CLONE | NUTSB_UF_REMOTE)) c->has_clones = true;
+    c->n_clone_flag = c->n_remote_flag = 0;
+    for (i32 u = 0; u < n_users; ++u) { c->n_clone_flag += (flags[u] & NUTSB_UF_CLONE) != 0; c->n_remote_flag += (flags[u] & NUTSB_UF_REMOTE) != 0; }
+    c->has_clones = c->n_clone_flag + c->n_remote_flag > 0;
     c->ulevel.assign(level, level + n_users);
+    if ((i32)c->sflags.size() != n_users) c->have_names = false;             // nutsb_set_user_names follows the population
     c->remote_link.clear(); c->remote_old.clear(); c->remotes.clear();
     c->clone_owner.clear(); c->clone_hear.clear(); c->room_clones.clear();       // nutsb_set_clones follows the population
     TRY(upload(c, c->d_user_room, c->user_room.data(), (size_t)n_users * 4));
@@ -624,6 +642,14 @@ NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, co
     c->have_users = true;
     return NUTSB_OK;
 }
+
+NUTSB_API int nutsb_set_users(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, const int32_t *room,
+                               const uint8_t *flags, const uint8_t *level)
+{ return set_users_impl(c, n_users, n_rooms, room, flags, level, nullptr); }
+
+NUTSB_API int nutsb_set_users_remap(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, const int32_t *room,
+                                     const uint8_t *flags, const uint8_t *level, const int32_t *prev_index)
+{ return set_users_impl(c, n_users, n_rooms, room, flags, level, prev_index); }
 
 static PopView pop_view(const nutsb_ctx *c, int with_level)
 {
@@ -1006,9 +1032,20 @@ static int check_ops(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
     return NUTSB_OK;
 }
 
+// Clones and remote users (nuts333.c:1416-1426, 1299-1307) are reached through relays / frames that are
+// extra write_user calls, made on the host (q_push).  The device tiers take ops as they are, so with such
+// users in the population they refuse rather than deliver something else than the reference would.
+static int no_relays_on_device(nutsb_ctx *c)
+{
+    if (c && c->has_clones)
+        return fail(c, NUTSB_E_UNSUPPORTED, "population holds clones / remote users: use the host-buffer or the queue tier%s");
+    return NUTSB_OK;
+}
+
 NUTSB_API int nutsb_write_batch_dev(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
 {
     TRY(check_ops(c, o, out));
+    TRY(no_relays_on_device(c));
     CK(cudaSetDevice(c->device));
     return run_write(c, o, out);
 }
@@ -1043,7 +1080,8 @@ static int upload_ops(nutsb_ctx *c, const nutsb_ops *o, nutsb_ops *d)
     return NUTSB_OK;
 }
 
-NUTSB_API int nutsb_write_batch(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
+// ops in host memory, streams back in pinned host memory; the ops are taken as they are
+static int write_batch_host(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
 {
     TRY(check_ops(c, o, out));
     CK(cudaSetDevice(c->device));
@@ -1107,7 +1145,7 @@ static int fetch_iov(nutsb_ctx *c, const nutsb_streams &ds, const IovReq &iv, nu
 
 // Gather lists (include/nutsb200.h): with plain listeners only, what crosses PCIe is the slab's two
 // renderings, the direct ops' renderings and 16 bytes per piece -- not one copy of the bytes per recipient.
-NUTSB_API int nutsb_write_batch_iov(nutsb_ctx *c, const nutsb_ops *o, nutsb_iov_streams *out)
+static int write_batch_iov_host(nutsb_ctx *c, const nutsb_ops *o, nutsb_iov_streams *out)
 {
     if (!out) return fail(c, NUTSB_E_INVAL, "null argument%s");
     nutsb_streams probe{};
@@ -1261,8 +1299,9 @@ static int q_push_one(nutsb_ctx *c, u8 kind, i32 target, const char *str, size_t
 // colour_com_strip(), nuts333.c:2588-2610, on the host (what a peer older than 3.2 is sent, c:1300)
 static std::string host_colour_com_strip(const char *s, size_t n)
 {
-    static u8 tab[NUTSB_CODETAB_BYTES]; static bool have = false;
-    if (!have) { build_codetab(tab); have = true; }
+    struct Tab { u8 t[NUTSB_CODETAB_BYTES]; Tab() { build_codetab(t); } };
+    static const Tab T;                                  // C++11: initialised once, whatever the number of threads / contexts
+    const u8 *tab = T.t;
     std::string o; o.reserve(n);
     for (size_t p = 0; p < n; ) {
         if (s[p] == '~' && p + 2 < n) {
@@ -1279,6 +1318,7 @@ static std::string host_colour_com_strip(const char *s, size_t n)
 static int q_push_user(nutsb_ctx *c, i32 u, const char *str, size_t n, u8 flags, i32 gate)
 {
     if (u >= 0 && (size_t)u < c->remote_link.size() && c->remote_link[(size_t)u] >= 0) {
+        if ((size_t)u + 1 >= c->name_off.size()) return fail(c, NUTSB_E_STATE, "nutsb_set_user_names does not match the population%s");
         std::string f = "MSG " + std::string((const char *)c->names.data() + c->name_off[(size_t)u], (size_t)(c->name_off[(size_t)u + 1] - c->name_off[(size_t)u])) + "\n";
         f += c->remote_old[(size_t)u] ? host_colour_com_strip(str, n) : std::string(str, n);
         if (f.back() != '\n' || f.size() == 5 + (size_t)(c->name_off[(size_t)u + 1] - c->name_off[(size_t)u])) f += "\n";
@@ -1294,10 +1334,44 @@ static int q_push_user(nutsb_ctx *c, i32 u, const char *str, size_t n, u8 flags,
 //  * every remote user that would have been a recipient of a room / level op gets its frame (q_push_user).
 // All of them at their place in the user list: before the op itself when a clone precedes its (local) owner
 // there, after it otherwise, in list order -- and under the op's own gate.
+struct QMark { size_t text, off, kind, target, except, flags, gate; };
+static QMark q_mark(const nutsb_ctx *c)
+{ return { c->q_text.size(), c->q_off.size(), c->q_kind.size(), c->q_target.size(), c->q_except.size(), c->q_flags.size(), c->q_gate.size() }; }
+static void q_rollback(nutsb_ctx *c, const QMark &m)
+{
+    c->q_text.resize(m.text); c->q_off.resize(m.off); c->q_kind.resize(m.kind); c->q_target.resize(m.target);
+    c->q_except.resize(m.except); c->q_flags.resize(m.flags); c->q_gate.resize(m.gate);
+}
+
+// users flagged as clones / remote users need nutsb_set_clones / nutsb_set_remotes before anything is queued:
+// without them their relays and frames would silently be missing
+static int relays_ready(nutsb_ctx *c)
+{
+    if (c->n_clone_flag && (i32)c->clone_owner.size() != c->U) return fail(c, NUTSB_E_STATE, "users flagged NUTSB_UF_CLONE: nutsb_set_clones has not been called%s");
+    if (c->n_remote_flag && (i32)c->remote_link.size() != c->U) return fail(c, NUTSB_E_STATE, "users flagged NUTSB_UF_REMOTE: nutsb_set_remotes has not been called%s");
+    return NUTSB_OK;
+}
+
+static int q_push_impl(nutsb_ctx *c, u8 kind, i32 target, const char *str, size_t n, i32 except_user, u8 flags, i32 gate);
+
+// all or nothing: a call that fails half-way (a relay or a frame longer than NUTSB_MAX_TEXT) leaves the queue as it was
+static int q_push_n(nutsb_ctx *c, u8 kind, i32 target, const char *str, size_t n, i32 except_user, u8 flags, i32 gate = -1)
+{
+    if (!c || !str) return NUTSB_E_INVAL;
+    if (c->has_clones) TRY(relays_ready(c));
+    const QMark m = q_mark(c);
+    const int rc = q_push_impl(c, kind, target, str, n, except_user, flags, gate);
+    if (rc != NUTSB_OK) q_rollback(c, m);
+    return rc;
+}
 static int q_push(nutsb_ctx *c, u8 kind, i32 target, const char *str, i32 except_user, u8 flags, i32 gate = -1)
 {
     if (!c || !str) return NUTSB_E_INVAL;
-    const size_t n = strlen(str);
+    return q_push_n(c, kind, target, str, strlen(str), except_user, flags, gate);
+}
+
+static int q_push_impl(nutsb_ctx *c, u8 kind, i32 target, const char *str, size_t n, i32 except_user, u8 flags, i32 gate)
+{
     if (kind == NUTSB_OP_USER) return q_push_user(c, target, str, n, flags, gate);
     struct Extra { i32 pos, user; bool relay; };
     std::vector<Extra> before, after;
@@ -1313,7 +1387,11 @@ static int q_push(nutsb_ctx *c, u8 kind, i32 target, const char *str, i32 except
             const u8 hear = c->clone_hear[(size_t)cl];
             if (hear == 0 || (c->uflags[(size_t)owner] & NUTSB_UF_IGNALL)) continue;        // c:1417
             if (hear == 1) {                                                                // c:1421: CLONE_HEAR_SWEARS
-                if (swears < 0) { swears = nutsb_contains_swearing(c, str); if (swears < 0) return swears; }
+                if (swears < 0) {
+                    const u64 so[2] = { 0, (u64)n }; u8 v = 0; static const u8 zero = 0;
+                    TRY(nutsb_contains_swearing_batch(c, 1, n ? (const u8 *)str : &zero, so, &v));
+                    swears = v;
+                }
                 if (!swears) continue;
             }
             const bool local = !(c->uflags[(size_t)owner] & NUTSB_UF_REMOTE);
@@ -1411,6 +1489,16 @@ NUTSB_API int nutsb_q_write_room(nutsb_ctx *c, int32_t room, const char *str, in
 { return nutsb_q_write_room_except(c, room, str, -1, force_listen, shout); }
 NUTSB_API int nutsb_q_write_level(nutsb_ctx *c, int level, int above, const char *str, int32_t except_user)
 { return q_push(c, NUTSB_OP_LEVEL, level, str, except_user, above ? NUTSB_OF_ABOVE : 0); }
+// write_sock(sock, str), nuts333.c:1281-1286, for a socket that is a user's (or a netlink's pseudo-user's): the
+// bytes as they are, in order with everything else queued for that socket
+NUTSB_API int nutsb_q_write_sock(nutsb_ctx *c, int32_t sock_user, const char *str)
+{
+    if (!c || !str) return NUTSB_E_INVAL;
+    const QMark m = q_mark(c);
+    const int rc = q_push_one(c, NUTSB_OP_USER, sock_user, str, strlen(str), -1, NUTSB_OF_RAW, -1);
+    if (rc != NUTSB_OK) q_rollback(c, m);
+    return rc;
+}
 NUTSB_API int nutsb_q_page_line(nutsb_ctx *c, int32_t sock_user, const char *str, int plain)
 { return q_push(c, NUTSB_OP_USER, sock_user, str, -1, (u8)(NUTSB_OF_PAGER | (plain ? NUTSB_OF_PLAIN : 0))); }
 
@@ -1467,16 +1555,23 @@ static void do_record(nutsb_ctx *c, i32 room, const char *str)
     rb.line = (rb.line + 1) % NUTSB_REVIEW_LINES;
 }
 
-// The swear verdicts of the queued lines (one device batch) and the record() calls that waited for them.
-static int resolve_records(nutsb_ctx *c)
+// The swear verdicts of the queued lines, taken in one device batch.
+static int resolve_verdicts(nutsb_ctx *c)
 {
     const i64 n_sw = (i64)c->q_sw_off.size() - 1;
     if ((i64)c->q_sw_verdict.size() < n_sw) {
         static const u8 zero = 0;
-        c->q_sw_verdict.assign((size_t)n_sw, 0);
-        TRY(nutsb_contains_swearing_batch(c, n_sw, c->q_sw_text.empty() ? &zero : c->q_sw_text.data(), c->q_sw_off.data(),
-                                          c->q_sw_verdict.data()));
+        std::vector<u8> v((size_t)n_sw, 0);
+        TRY(nutsb_contains_swearing_batch(c, n_sw, c->q_sw_text.empty() ? &zero : c->q_sw_text.data(), c->q_sw_off.data(), v.data()));
+        c->q_sw_verdict.swap(v);
     }
+    return NUTSB_OK;
+}
+
+// ... and the record() calls that waited for them (a line refused for swearing is never recorded)
+static int resolve_records(nutsb_ctx *c)
+{
+    TRY(resolve_verdicts(c));
     for (const auto &r : c->q_rec)
         if (r.gate < 0 || !c->q_sw_verdict[(size_t)r.gate]) do_record(c, r.room, r.text.c_str());
     c->q_rec.clear();
@@ -1523,6 +1618,16 @@ NUTSB_API int nutsb_q_review(nutsb_ctx *c, int32_t user, int32_t room, const cha
     return nutsb_q_write_user(c, user, "\n~BB~FG*** End ***\n\n");
 }
 
+static void q_clear(nutsb_ctx *c)
+{
+    c->q_text.clear(); c->q_off.assign(1, 0); c->q_kind.clear(); c->q_target.clear(); c->q_except.clear(); c->q_flags.clear();
+    c->q_gate.clear(); c->q_sw_text.clear(); c->q_sw_off.assign(1, 0); c->q_sw_verdict.clear(); c->q_rec.clear();
+}
+
+// Policy (include/nutsb200.h): the queue is emptied when the batch has run, or when it can never run (a
+// validation error: the same ops would fail again).  After NUTSB_E_NOMEM / NUTSB_E_CUDA the queue -- ops,
+// swear bodies, pending record() calls -- is kept as it was, so that the flush can be tried again; the review
+// buffers take the pending lines only once the batch that delivers them has succeeded.
 static int flush_impl(nutsb_ctx *c, nutsb_streams *out, nutsb_iov_streams *out_iov)
 {
     if (!c || (!out && !out_iov)) return NUTSB_E_INVAL;
@@ -1532,15 +1637,54 @@ static int flush_impl(nutsb_ctx *c, nutsb_streams *out, nutsb_iov_streams *out_i
     o.text = c->q_text.empty() ? &zero : c->q_text.data(); o.text_off = c->q_off.data();
     o.kind = c->q_kind.data(); o.target = c->q_target.data(); o.except_user = c->q_except.data(); o.flags = c->q_flags.data();
     // the swear verdicts the queued say/shout/emote lines branch on: one device batch (unless a review took them)
-    int rc = resolve_records(c);
+    int rc = resolve_verdicts(c);
     const i64 n_sw = (i64)c->q_sw_off.size() - 1;
     if (rc == NUTSB_OK && n_sw > 0) { o.gate = c->q_gate.data(); o.verdict = c->q_sw_verdict.data(); }
-    if (rc == NUTSB_OK) rc = out ? nutsb_write_batch(c, &o, out) : nutsb_write_batch_iov(c, &o, out_iov);
-    c->q_text.clear(); c->q_off.assign(1, 0); c->q_kind.clear(); c->q_target.clear(); c->q_except.clear(); c->q_flags.clear();
-    c->q_gate.clear(); c->q_sw_text.clear(); c->q_sw_off.assign(1, 0); c->q_sw_verdict.clear(); c->q_rec.clear();
+    if (rc == NUTSB_OK) rc = out ? write_batch_host(c, &o, out) : write_batch_iov_host(c, &o, out_iov);
+    if (rc == NUTSB_OK) rc = resolve_records(c);
+    if (rc != NUTSB_E_NOMEM && rc != NUTSB_E_CUDA) q_clear(c);
     return rc;
 }
 NUTSB_API int nutsb_flush(nutsb_ctx *c, nutsb_streams *out) { return flush_impl(c, out, nullptr); }
+
+// The host-buffer batch tier.  With clones / remote users in the population every op goes through the
+// queue tier's expansion (the relays of c:1416-1426, the frames of c:1299-1307, each under the op's own gate)
+// before the batch runs, so that the streams are the reference's here too.
+static int write_batch_public(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, nutsb_iov_streams *out_iov)
+{
+    if (!c || !c->has_clones) return out ? write_batch_host(c, o, out) : write_batch_iov_host(c, o, out_iov);
+    nutsb_streams probe{};
+    TRY(check_ops(c, o, &probe));
+    if (!c->have_users) return fail(c, NUTSB_E_STATE, "nutsb_set_users has not been called%s");
+    if (!c->q_kind.empty() || !c->q_rec.empty()) return fail(c, NUTSB_E_STATE, "a batch over a population with clones / remote users needs an empty queue: flush first%s");
+    int rc = NUTSB_OK;
+    for (i64 i = 0; i < o->n_ops && rc == NUTSB_OK; ++i) {
+        if (o->text_off[i + 1] < o->text_off[i]) { rc = fail(c, NUTSB_E_INVAL, "text_off is not monotone%s"); break; }
+        const u8 k = o->kind[i];
+        if (k == NUTSB_OP_NONE) continue;
+        if (k > NUTSB_OP_LEVEL) { rc = fail(c, NUTSB_E_INVAL, "unknown op kind%s"); break; }
+        const i32 t = o->target[i], x = o->except_user[i];
+        if (x >= c->U || x < -1 || (k == NUTSB_OP_USER && t >= c->U) || (k == NUTSB_OP_ROOM && (t >= c->R || t < -1))) { rc = fail(c, NUTSB_E_RANGE, "user/room index out of range%s"); break; }
+        static const char none = 0;
+        const size_t n = (size_t)(o->text_off[i + 1] - o->text_off[i]);
+        rc = q_push_n(c, k, t, n ? (const char *)o->text + o->text_off[i] : &none, n, x, o->flags[i], o->gate && o->verdict ? o->gate[i] : -1);
+    }
+    if (rc == NUTSB_OK) {
+        nutsb_ops e{};
+        e.n_ops = (i64)c->q_kind.size();
+        static const u8 zero = 0;
+        e.text = c->q_text.empty() ? &zero : c->q_text.data(); e.text_off = c->q_off.data();
+        e.kind = c->q_kind.data(); e.target = c->q_target.data(); e.except_user = c->q_except.data(); e.flags = c->q_flags.data();
+        if (o->gate && o->verdict) { e.gate = c->q_gate.data(); e.verdict = o->verdict; }
+        rc = out ? write_batch_host(c, &e, out) : write_batch_iov_host(c, &e, out_iov);
+    }
+    q_clear(c);
+    return rc;
+}
+NUTSB_API int nutsb_write_batch(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
+{ if (!out) return fail(c, NUTSB_E_INVAL, "null argument%s"); return write_batch_public(c, o, out, nullptr); }
+NUTSB_API int nutsb_write_batch_iov(nutsb_ctx *c, const nutsb_ops *o, nutsb_iov_streams *out)
+{ if (!out) return fail(c, NUTSB_E_INVAL, "null argument%s"); return write_batch_public(c, o, nullptr, out); }
 NUTSB_API int nutsb_flush_iov(nutsb_ctx *c, nutsb_iov_streams *out) { return flush_impl(c, nullptr, out); }
 
 // ---------------------------------------------------------------------------------------
@@ -1550,6 +1694,7 @@ NUTSB_API int nutsb_set_user_names(nutsb_ctx *c, int32_t n_users, const uint8_t 
 {
     if (!c || n_users < 0 || (n_users && (!off || !sflags))) return fail(c, NUTSB_E_INVAL, "nutsb_set_user_names: bad argument%s");
     CK(cudaSetDevice(c->device));
+    if (c->have_users && n_users != c->U) return fail(c, NUTSB_E_STATE, "nutsb_set_user_names does not match the population%s");
     for (i32 u = 0; u < n_users; ++u) if (off[u + 1] < off[u]) return fail(c, NUTSB_E_INVAL, "name offsets are not monotone%s");
     const u64 t0 = n_users ? off[0] : 0, t1 = n_users ? off[n_users] : 0;
     if (t1 > t0 && !names) return fail(c, NUTSB_E_INVAL, "names is NULL%s");
@@ -1650,27 +1795,40 @@ static int q_private(nutsb_ctx *c, int pemote, i32 user, i32 target, const char 
 NUTSB_API int nutsb_q_tell(nutsb_ctx *c, int32_t user, int32_t target, const char *inpstr) { return q_private(c, 0, user, target, inpstr); }
 NUTSB_API int nutsb_q_pemote(nutsb_ctx *c, int32_t user, int32_t target, const char *inpstr) { return q_private(c, 1, user, target, inpstr); }
 
-// lev < 0: no level word, everybody from WIZ up (c:6560-6564); else the form "to level <level_name>" (c:6552-6557,
-// inpstr without the level word; lev >= WIZ and <= the speaker's level are the caller's checks)
+// inpstr = the whole line as wizshout() receives it.  lev < 0: no level word, everybody from WIZ up (c:6560-6564);
+// else the form "to level <level_name>" (c:6552-6557; lev >= WIZ and <= the speaker's level are the caller's checks):
+// the level word is taken off here (remove_first, c:2350) -- after the ban_swearing check, which the reference asks
+// of the whole line (c:6541), level word included
 NUTSB_API int nutsb_q_wizshout(nutsb_ctx *c, int32_t user, int lev, const char *level_name, const char *inpstr)
 {
     if (!c || !inpstr || (lev >= 0 && !level_name)) return NUTSB_E_INVAL;
     TRY(speech_ready(c));
     if (user < 0 || user >= c->U) return fail(c, NUTSB_E_RANGE, "user index out of range%s");
     if (c->sflags[(size_t)user] & NUTSB_SF_MUZZLED) return nutsb_q_write_user(c, user, "You are muzzled, you cannot wizshout.\n");
-    const size_t n = strlen(inpstr);
+    const size_t n_all = strlen(inpstr);
+    const QMark m = q_mark(c);
+    const size_t sw_text = c->q_sw_text.size(), sw_off = c->q_sw_off.size();
     i32 gate = -1;
+    int rc = NUTSB_OK;
     if (c->ban_swearing) {                                           // c:6541, asked of the whole line
         gate = (i32)c->q_sw_off.size() - 1;
-        c->q_sw_text.insert(c->q_sw_text.end(), (const u8 *)inpstr, (const u8 *)inpstr + n);
+        c->q_sw_text.insert(c->q_sw_text.end(), (const u8 *)inpstr, (const u8 *)inpstr + n_all);
         c->q_sw_off.push_back((u64)c->q_sw_text.size());
-        TRY(q_push(c, NUTSB_OP_USER, user, c->lits[6].c_str(), -1, NUTSB_OF_GATE_IF_SET, gate));
+        rc = q_push(c, NUTSB_OP_USER, user, c->lits[6].c_str(), -1, NUTSB_OF_GATE_IF_SET, gate);
     }
-    const std::string msg(inpstr, n), to = lev >= 0 ? std::string(" to level ") + level_name : std::string();
+    const char *body = inpstr;
+    if (lev >= 0) {                                                  // remove_first(), c:2350-2358 (char is signed there)
+        while ((signed char)*body < 33 && *body) ++body;
+        while ((signed char)*body > 32) ++body;
+        while ((signed char)*body < 33 && *body) ++body;
+    }
+    const std::string msg(body), to = lev >= 0 ? std::string(" to level ") + level_name : std::string();
     const std::string a = "~OLYou wizshout" + to + ":~RS " + msg + "\n";
     const std::string b = "~OL" + user_name(c, user) + " wizshouts" + to + ":~RS " + msg + "\n";
-    TRY(q_push(c, NUTSB_OP_USER, user, a.c_str(), -1, 0, gate));
-    return q_push(c, NUTSB_OP_LEVEL, lev >= 0 ? lev : 2 /* WIZ */, b.c_str(), user, NUTSB_OF_ABOVE, gate);
+    if (rc == NUTSB_OK) rc = q_push(c, NUTSB_OP_USER, user, a.c_str(), -1, 0, gate);
+    if (rc == NUTSB_OK) rc = q_push(c, NUTSB_OP_LEVEL, lev >= 0 ? lev : 2 /* WIZ */, b.c_str(), user, NUTSB_OF_ABOVE, gate);
+    if (rc != NUTSB_OK) { q_rollback(c, m); c->q_sw_text.resize(sw_text); c->q_sw_off.resize(sw_off); }
+    return rc;
 }
 
 NUTSB_API int nutsb_q_revtell(nutsb_ctx *c, int32_t user)

@@ -270,7 +270,8 @@ void ref_speech(int verb, int u, const char *inpstr)
     case 5: com_num = BCAST;  bcast(g_users[u], line); break;
     case 6: com_num = REVIEW; word_count = 1; review(g_users[u]); break;   /* c:5192, no argument: the user's own room */
     case 9: com_num = WIZSHOUT; { char *sp; strncpy(word[1], line, WORD_LEN); word[1][WORD_LEN] = 0;
-                                  if ((sp = strchr(word[1], ' '))) *sp = 0; }   /* word[1] = first word (exec_com's split) */
+                                  if ((sp = strchr(word[1], ' '))) *sp = 0;     /* word[1] = first word (exec_com's split) */
+                                  if (sp && *remove_first(line)) word_count = 3; }   /* ".wizshout <level> <message>" */
             wizshout(g_users[u], line); break;
     case 10: com_num = REVTELL; revtell(g_users[u]); break;
     }

@@ -91,11 +91,35 @@ def _check_queue_tier(ctx, port, seed, U, NR, N):
             t.write_level(tg, bool(f & 4), s, None if ex < 0 else ex)
     st = t.flush()
     assert (st.off == off).all() and (st.data == data).all()
+    # the host-buffer batch tier makes the same relays (it expands every op as the queue tier does) ...
+    st = ctx.write_batch(o)
+    assert (st.off == off).all() and (st.data == data).all()
+    iv = ctx.write_batch_iov(o)
+    assert (iv.off == off).all() and all(iv.user(u) == st.user(u) for u in range(U))
+    # ... flagged clones without their owner table are refused, not silently skipped
+    ctx.set_users(c["users"]["room"], c["users"]["flags"], c["users"]["level"], c["n_rooms"])
+    with pytest.raises(api.NutsbError) as e:
+        ctx.write_batch(o)
+    assert e.value.code == api.E_STATE
+    with pytest.raises(api.NutsbError) as e:
+        t.write_room_except(0, b"x\n", None)
+    assert e.value.code == api.E_STATE and t.pending() == 0
+    ctx.set_clones(c["owner"], c["hear"])
 
 
 def test_clone_relay_on_emulator(sim_lib, port):
     ctx = api.Context(0, sim_lib)
     _check_queue_tier(ctx, port, 34, 16, 3, 120)
+    # a call whose relay would not fit text[] queues nothing at all (not the op, not the relays made before)
+    ctx.set_users(np.array([0, 0, 0], np.int32), np.array([0x10, 0, 0x10], np.uint8), np.ones(3, np.uint8), 1)
+    ctx.set_clones(np.array([1, -1, 1], np.int32), np.array([2, 0, 2], np.uint8))
+    t = api.Talker(ctx)
+    t.write_room_except(0, b"ok\n", None)
+    n0 = t.pending()
+    with pytest.raises(api.NutsbError) as e:
+        t.write_room_except(0, b"y" * 1995, None)
+    assert e.value.code == api.E_RANGE and t.pending() == n0
+    assert t.flush().user(1).count(b"ok") == 3
     with pytest.raises(api.NutsbError):
         ctx.set_clones(np.full(16, -1, np.int32), np.zeros(16, np.uint8))      # disagrees with the CLONE flags
     ctx.close()

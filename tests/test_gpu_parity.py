@@ -118,10 +118,15 @@ def test_errors_leave_the_host_alive(gpu_ctx):
     with pytest.raises(api.NutsbError) as e:
         gpu_ctx.write_batch(one(kind=np.array([9], np.uint8)))
     assert e.value.code == api.E_INVAL
-    # clones / remote users without their owner / link tables: nothing reaches them, nothing breaks
+    # clones / remote users without their owner / link tables: refused (their relays and frames would be missing),
+    # and the device tier refuses such a population altogether
     gpu_ctx.set_users(np.zeros(3, np.int32), np.array([api.UF_REMOTE, api.UF_CLONE, 0], np.uint8), np.ones(3, np.uint8), 1)
-    st = gpu_ctx.write_batch(one())
-    assert len(st.user(0)) == 0 and len(st.user(1)) == 0 and st.user(2) == b"x"
+    with pytest.raises(api.NutsbError) as e:
+        gpu_ctx.write_batch(one())
+    assert e.value.code == api.E_STATE
+    with pytest.raises(api.NutsbError) as e:
+        gpu_ctx.write_batch_dev(0, 0, 0, 0, 0, 0, 0)
+    assert e.value.code == api.E_UNSUPPORTED
     with pytest.raises(api.NutsbError) as e:
         gpu_ctx.set_clones(np.array([-1, -1, -1], np.int32), np.zeros(3, np.uint8))     # disagrees with the CLONE flag
     assert e.value.code == api.E_INVAL

@@ -68,7 +68,8 @@ def _check_queue_tier(ctx, port, seed, U, N):
         c = make_script(seed, U, N)
         off, data, nd = port_streams(port, c, ban)
         ctx.set_swear_words(STOCK)
-        ctx.set_users(c["users"]["room"], c["users"]["flags"], c["users"]["level"], c["n_rooms"])
+        # a fresh set of users (create_user() starts with empty revtell buffers, c:2747)
+        ctx.set_users(c["users"]["room"], c["users"]["flags"], c["users"]["level"], c["n_rooms"], prev_index=np.full(U, -1, np.int32))
         ctx.set_user_names(c["names"], c["sflags"])
         ctx.set_ban_swearing(ban)
         t = api.Talker(ctx)
@@ -91,7 +92,7 @@ def test_wizshout_to_a_level(sim_lib, port):
     ctx.set_users(users["room"], users["flags"], users["level"], 1)
     ctx.set_user_names([b"God", b"Arch", b"Wiz", b"User"], np.zeros(4, np.uint8))
     t = api.Talker(ctx)
-    t.wizshout(0, b"meeting ~FRnow", lev=3, level_name=b"ARCH")
+    t.wizshout(0, b"ARCH  meeting ~FRnow", lev=3, level_name=b"ARCH")     # the whole line: the level word is taken off inside
     st = t.flush()
     assert st.user(0) == port.render(b"~OLYou wizshout to level ARCH:~RS meeting ~FRnow\n", 1)
     assert st.user(1) == port.render(b"~OLGod wizshouts to level ARCH:~RS meeting ~FRnow\n", 0)
@@ -108,3 +109,33 @@ def test_private_on_emulator(sim_lib, port):
 @pytest.mark.gpu
 def test_private_on_gpu(gpu_ctx, port):
     _check_queue_tier(gpu_ctx, port, 44, 40, 700)
+
+
+def test_wizshout_swear_check_sees_the_level_word(sim_lib, ref):
+    """c:6541 asks contains_swearing of the WHOLE line, before remove_first (c:6553) takes the level word off: a list
+    word that matches the level word, or straddles it and the message, refuses the line."""
+    words = ["arch", "h mee", "*"]
+    ctx = api.Context(0, sim_lib)
+    ctx.set_swear_words(words)
+    users = dict(room=np.zeros(3, np.int32), flags=np.array([1, 0, 0], np.uint8), level=np.array([4, 3, 2], np.uint8))
+    names = [b"God", b"Arch", b"Wiz"]
+    ctx.set_users(users["room"], users["flags"], users["level"], 1)
+    ctx.set_user_names(names, np.zeros(3, np.uint8))
+    ctx.set_ban_swearing(True)
+    lines = [(b"GOD hello all", 4, b"GOD"), (b"ARCH hello", 3, b"ARCH"), (b"WIZ meeting", 2, b"WIZ"), (b"GOD h meet", 4, b"GOD"),
+             (b"plain words", -1, None), (b"search party", -1, None)]
+    ref.reset(1, users)
+    ref.set_swear_words(words[:-1])
+    ref.lib.ref_set_ban_swearing(1)
+    for u, nm in enumerate(names):
+        ref.lib.ref_set_user_speech(u, nm, 1, 0)
+    t = api.Talker(ctx)
+    for line, lev, lname in lines:
+        t.wizshout(0, line, lev=lev, level_name=lname)
+        ref.lib.ref_speech(WIZSHOUT, 0, line)
+    st = t.flush()
+    for u in range(3):
+        assert st.user(u) == ref.stream(u), u
+    assert b"Swearing is not allowed" in st.user(0) and b"wizshout to level GOD" in st.user(0)
+    ref.lib.ref_set_ban_swearing(0)
+    ctx.close()

@@ -115,6 +115,14 @@ def _check_queue_tier(ctx, port, seed, U, NR, N):
             t.write_level(tg, bool(f & 4), s, None if ex < 0 else ex)
     st = t.flush()
     assert (st.off == off).all() and (st.data == data).all()
+    # the host-buffer batch tier frames and relays like the queue tier; the device tier refuses the population
+    st = ctx.write_batch(o)
+    assert (st.off == off).all() and (st.data == data).all()
+    iv = ctx.write_batch_iov(o)
+    assert (iv.off == off).all() and all(iv.user(u) == st.user(u) for u in range(U))
+    with pytest.raises(api.NutsbError) as e:
+        ctx.write_batch_dev(0, 0, 0, 0, 0, 0, 0)
+    assert e.value.code == api.E_UNSUPPORTED
 
 
 def test_remote_on_emulator(sim_lib, port):

@@ -87,6 +87,8 @@ def _check_queue_tier(ctx, port, seed, U, NR, N):
         ctx.set_user_names(c["names"], c["sflags"])
         ctx.set_ban_swearing(ban)
         t = api.Talker(ctx)
+        for r in range(c["n_rooms"]):          # the rooms' buffers outlive nutsb_set_users (only create_room / clear_revbuff empty them)
+            t.clear_revbuff(r)
         fn = [t.say, t.shout, t.emote, t.semote, t.echo, t.bcast]
         for v, s, b in zip(c["verb"], c["speaker"], c["bodies"]):
             if int(v) == REVIEW:
@@ -107,3 +109,33 @@ def test_review_on_emulator(sim_lib, port):
 @pytest.mark.gpu
 def test_review_on_gpu(gpu_ctx, port):
     _check_queue_tier(gpu_ctx, port, 14, 40, 3, 600)
+
+
+def test_population_updates_keep_the_buffers_and_wait_for_the_flush(sim_lib, port):
+    """nutsb_set_users between two flushes only (queued ops name users by index: NUTSB_E_STATE otherwise), and it
+    leaves the review / revtell buffers alone: a logout shifts the list, prev_index carries the revtell buffers over."""
+    ctx = api.Context(0, sim_lib)
+    room, flags, level = np.zeros(3, np.int32), np.array([0, 1, 0], np.uint8), np.ones(3, np.uint8)
+    ctx.set_users(room, flags, level, 1)
+    ctx.set_user_names([b"Ann", b"Bob", b"Cy"], np.zeros(3, np.uint8))
+    t = api.Talker(ctx)
+    t.say(0, b"first line")
+    t.tell(0, 2, b"psst")
+    with pytest.raises(api.NutsbError) as e:
+        ctx.set_users(room[:2], flags[:2], level[:2], 1)
+    assert e.value.code == api.E_STATE and t.pending() > 0
+    st = t.flush()
+    assert st.user(2) == port.render(b"Ann says: first line\n", 0) + port.render(b"~OLAnn tells you:~RS psst\n", 0)
+    # Bob logs out: Cy moves from index 2 to 1 and keeps his revtell buffer; the room keeps its review buffer
+    ctx.set_users(room[:2], flags[[0, 2]], level[:2], 1, prev_index=np.array([0, 2], np.int32))
+    ctx.set_user_names([b"Ann", b"Cy"], np.zeros(2, np.uint8))
+    t.revtell(1)
+    t.review(0, 0)
+    st = t.flush()
+    assert b"Ann tells you:" in st.user(1) and b"Review buffer is empty" not in st.user(0) and b"Ann says: first line" in st.user(0)
+    # a new user at index 1 instead: empty revtell buffer
+    ctx.set_users(room[:2], flags[:2], level[:2], 1, prev_index=np.array([0, -1], np.int32))
+    ctx.set_user_names([b"Ann", b"Dee"], np.zeros(2, np.uint8))
+    t.revtell(1)
+    assert t.flush().user(1) == port.render(b"Revtell buffer is empty.\n", 1)
+    ctx.close()
