@@ -83,6 +83,7 @@ static int dropin_close(int fd) { (void)fd; return 0; }
 /* ---- session set-up -------------------------------------------------------------------------- */
 #define MAX_H 4096
 static UR_OBJECT g_users[MAX_H]; static int g_nusers = 0;
+static int g_user_fd[MAX_H];       /* the socket a handle was given: never reused, so it tells a user from a later one at the same address */
 static RM_OBJECT g_rooms[256];   static int g_nrooms = 0;
 static NL_OBJECT g_links[64];    static int g_nlinks = 0;
 static int g_next_fd = FD_BASE;
@@ -207,7 +208,7 @@ int dropin_add_user(const char *name, int room, int level, int colour, int login
     u->level = level; u->colour = colour; u->login = login; u->prompt = prompt_on; u->command_mode = command_mode;
     u->last_login = g_now - 3600; u->last_input = g_now;
     if (!login) num_of_users++; else num_of_logins++;
-    g_users[g_nusers] = u;
+    g_users[g_nusers] = u; g_user_fd[g_nusers] = u->socket;
     return g_nusers++;
 }
 
@@ -217,7 +218,7 @@ int dropin_add_remote_user(const char *name, int room, int level, int link)
     const int h = dropin_add_user(name, room, level, 1, 0, 0, 0);
     if (h < 0 || link < 0 || link >= g_nlinks) return -1;
     --g_next_fd;
-    g_users[h]->type = REMOTE_TYPE; g_users[h]->socket = -1; g_users[h]->netlink = g_links[link];
+    g_users[h]->type = REMOTE_TYPE; g_users[h]->socket = -1; g_users[h]->netlink = g_links[link]; g_user_fd[h] = -1;
     return h;
 }
 
@@ -225,7 +226,7 @@ static int dropin_alive(int h)
 {
     UR_OBJECT u;
     if (h < 0 || h >= g_nusers || !g_users[h]) return 0;
-    for (u = user_first; u; u = u->next) if (u == g_users[h]) return 1;
+    for (u = user_first; u; u = u->next) if (u == g_users[h] && u->socket == g_user_fd[h] && u->type != CLONE_TYPE) return 1;
     g_users[h] = NULL;
     return 0;
 }
