@@ -34,8 +34,9 @@ struct HBuf {                        // growable pinned host buffer
 
 struct AcHost {
     std::vector<u32> trans; u8 clsmap[256]; u32 ncls = 1, nstates = 1, root_match = 0;
+    std::vector<u16> tr16; u8 cls2[256]; u32 thresh = 0x10000u, maxpat = 0;     // k_ac_warp's form (empty: does not fit)
 };
-struct AcDev { DBuf trans, clsmap; AcView view{}; bool present = false; };
+struct AcDev { DBuf trans, clsmap, tr16, cls2; AcView view{}; bool present = false; };
 struct SetDev { DBuf slot_off, slot_len, pool; SetView view{}; bool present = false; };
 
 struct ClassSet {                    // one class granularity (with / without level)
@@ -294,6 +295,20 @@ static void build_ac(const std::vector<std::string> &pats, bool fold_case, AcHos
         const u32 t = (u32)go[i];
         ac.trans[i] = t | (match[t] ? 0x80000000u : 0u);
     }
+    // k_ac_warp's form: states renumbered with the match states last (the root stays 0: it is a match state only for an
+    // empty pattern, which root_match covers), entries = byte offset of the target's row, classes pre-doubled
+    ac.tr16.clear(); ac.maxpat = 0; ac.thresh = 0x10000u;
+    for (auto &p : pats) ac.maxpat = std::max<u32>(ac.maxpat, (u32)p.size());
+    if ((size_t)ns * nc <= NUTSB_AC_SMEM_ENTRIES && nc <= 127 && (size_t)ns * nc * 2 <= 0xffffu) {
+        std::vector<u32> newid(ns, 0); u32 k = 0;
+        for (u32 st = 0; st < ns; ++st) if (!match[st] || st == 0) newid[st] = k++;
+        ac.thresh = k == ns ? 0x10000u : k * nc * 2;              // (no match state at all: never reached)
+        for (u32 st = 1; st < ns; ++st) if (match[st]) newid[st] = k++;
+        ac.tr16.assign((size_t)ns * nc, 0);
+        for (u32 st = 0; st < ns; ++st)
+            for (u32 cc = 0; cc < nc; ++cc) ac.tr16[(size_t)newid[st] * nc + cc] = (u16)(newid[(u32)go[(size_t)st * nc + cc]] * nc * 2);
+        for (int b = 0; b < 256; ++b) ac.cls2[b] = (u8)(2 * ac.clsmap[b]);
+    }
 }
 
 static int upload_ac(nutsb_ctx *c, const AcHost &h, AcDev &d)
@@ -302,6 +317,12 @@ static int upload_ac(nutsb_ctx *c, const AcHost &h, AcDev &d)
     TRY(upload(c, d.clsmap, h.clsmap, 256));
     d.view.trans = d.trans.as<u32>(); d.view.clsmap = d.clsmap.as<u8>();
     d.view.ncls = h.ncls; d.view.nstates = h.nstates; d.view.root_match = h.root_match;
+    d.view.tr16 = nullptr; d.view.cls2 = nullptr; d.view.thresh = h.thresh; d.view.maxpat = h.maxpat;
+    if (!h.tr16.empty()) {
+        TRY(upload(c, d.tr16, h.tr16.data(), h.tr16.size() * sizeof(u16)));
+        TRY(upload(c, d.cls2, h.cls2, 256));
+        d.view.tr16 = d.tr16.as<u16>(); d.view.cls2 = d.cls2.as<u8>();
+    }
     d.present = true;
     CK(cudaStreamSynchronize(c->stream));
     return NUTSB_OK;
@@ -352,7 +373,7 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DBuf *all[] = { &c->d_codetab, &c->swear.trans, &c->swear.clsmap, &c->site.trans, &c->site.clsmap,
+    DBuf *all[] = { &c->d_codetab, &c->swear.trans, &c->swear.clsmap, &c->swear.tr16, &c->swear.cls2, &c->site.trans, &c->site.clsmap, &c->site.tr16, &c->site.cls2,
         &c->userban.slot_off, &c->userban.slot_len, &c->userban.pool,
         &c->d_user_room, &c->d_user_slot, &c->d_slot_user, &c->d_room_slot_off, &c->d_slot_cf, &c->d_slot_lv,
         &c->cls[0].d_user_cls, &c->cls[0].d_room_cls_off, &c->cls[0].d_cls_flags, &c->cls[0].d_cls_level,
@@ -409,6 +430,7 @@ NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
         CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_FAN_SMEM));
         CK(cudaFuncSetAttribute(k_fanout_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_FD_SMEM));
         CK(cudaFuncSetAttribute(k_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_DIR_SMEM));
+        CK(cudaFuncSetAttribute(k_ac_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_ACW_SMEM(2 * NUTSB_AC_SMEM_ENTRIES)));
         u8 tab[NUTSB_CODETAB_BYTES]; build_codetab(tab);
         TRY(upload(c, c->d_codetab, tab, sizeof tab));
         TRY(ensure(c, c->d_status, 64)); TRY(ensure(c, c->d_counts, 64)); TRY(ensure(c, c->d_sizes, sizeof(Sizes)));
@@ -1182,6 +1204,14 @@ NUTSB_API int nutsb_stream_digests(nutsb_ctx *c, uint64_t *digest)
 static int run_ac(nutsb_ctx *c, const AcDev &ac, i64 n, const u8 *bytes, const u64 *off, u8 *verdict)
 {
     if (n == 0) return NUTSB_OK;
+    if (ac.view.tr16 && ac.view.maxpat <= 256) {                   // the warp-cooperative form: 4 blocks of ~50 KB per SM
+        const u32 tr_bytes = (ac.view.nstates * ac.view.ncls * 2u + 15u) & ~15u;
+        const u32 smem = NUTSB_ACW_SMEM(tr_bytes);
+        const u32 per_sm = std::max(1u, std::min(8u, (227u * 1024u) / (smem + 1024u)));     // resident blocks per SM
+        const u32 g = std::min<u32>(cdiv(n, NUTSB_ACW_THREADS), (u32)c->sm_count * per_sm);
+        NUTSB_LAUNCH_SMEM(g, NUTSB_ACW_THREADS, smem, c->stream, k_ac_warp, bytes, off, n, ac.view, tr_bytes, verdict); CKL();
+        return NUTSB_OK;
+    }
     const u32 grid = std::min<u32>(cdiv(n, NUTSB_AC_THREADS), (u32)c->sm_count * 8u);
     const bool smem = ac.view.nstates <= 32768u && (u64)ac.view.nstates * ac.view.ncls <= NUTSB_AC_SMEM_ENTRIES;
     if (smem) { NUTSB_LAUNCH(grid, NUTSB_AC_THREADS, c->stream, k_ac_match<true>, bytes, off, n, ac.view, verdict); }

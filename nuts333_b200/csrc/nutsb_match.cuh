@@ -18,6 +18,11 @@ struct AcView {
     const u8  *clsmap;       // [256] byte -> class (0 = byte absent from every pattern)
     u32 ncls, nstates;
     u32 root_match;          // an empty pattern: every string matches (strstr(s,"") != NULL)
+    // the compact form k_ac_warp walks (null when the automaton does not fit: then k_ac_match runs)
+    const u16 *tr16;         // [nstates][ncls]: BYTE offset of the target state's row; match states have the highest rows
+    const u8  *cls2;         // [256] 2 * class
+    u32 thresh;              // a row offset >= thresh is a match state's
+    u32 maxpat;              // longest pattern, bytes
 };
 
 #define NUTSB_AC_THREADS     256
@@ -83,6 +88,157 @@ k_ac_match(const u8 *text, const u64 *off, i64 n, AcView ac, u8 *verdict)
             while (j < len && !hit) { hit = nutsb_ac_step<SMEM_DFA>(st, s_cls[__ldg(s + j)], s_tr, ac); ++j; }
         }
         verdict[i] = hit ? 1 : 0;
+    }
+}
+
+// ---- the warp-cooperative form --------------------------------------------------------------
+// One thread per string leaves half the lanes idle (the longest string of a warp sets the pace) and reads
+// the text with per-thread 4-byte loads.  Here a warp takes 32 consecutive strings -- one contiguous piece
+// of the packed text -- stages it into shared memory with coalesced 16-byte loads and splits it into 32
+// equal pieces BY BYTES, whatever the string lengths.  A lane starts its walk (maxpat - 1) bytes before its
+// piece, in the root state: any match that ends inside the piece lies wholly in what the lane has walked,
+// so every match is found by the lane whose piece it ends in (and a match found in the overlap is a true
+// one as well).  The state falls back to the root at every string start; a hit is credited to the string
+// the walk is in.  The automaton is stored for a five-instruction step: u16 entries that hold the BYTE
+// offset of the next state's row (no multiply), the class table pre-doubled, match states numbered last so
+// that "hit" is a running maximum compared once per string piece.
+#define NUTSB_ACW_THREADS 256
+#define NUTSB_ACW_WIN     2560                     // text bytes staged per warp (32 strings of 80 bytes), and as many mask bytes
+// dynamic shared memory: the table (tr_bytes, a multiple of 16), the class table, the warps' windows and string starts
+#define NUTSB_ACW_HITW    ((NUTSB_ACW_WIN + 48) / 32 + 1)                  // words of the per-warp hit bitmap
+#define NUTSB_ACW_SMEM(tr_bytes) ((tr_bytes) + 256 + (NUTSB_ACW_THREADS / 32) * (2 * (NUTSB_ACW_WIN + 48) + 34 * 4 + 4 * NUTSB_ACW_HITW))
+
+__device__ __forceinline__ u32 nutsb_acw_walk(const u8 *p, const u8 *e, const u8 *s_trb, const u8 *s_cls2, u32 &st)
+{
+    u32 acc = 0;
+    for (; p < e; ++p) {
+        st = *(const u16 *)(s_trb + st + s_cls2[*p]);
+        acc = acc > st ? acc : st;
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(NUTSB_ACW_THREADS)
+k_ac_warp(const u8 *text, const u64 *off, i64 n, AcView ac, u32 tr_bytes, u8 *verdict)
+{
+    NUTSB_DYN_SMEM(smem);
+    u8 *const s_trb = smem;                                              // the transition table, bytes
+    u8 *const s_cls2 = smem + tr_bytes;
+    u8 *const s_stage_all = s_cls2 + 256;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u8 *const stage = s_stage_all + warp * 2 * (NUTSB_ACW_WIN + 48);
+    u8 *const pm = stage + NUTSB_ACW_WIN + 48;
+    u32 *const s_p0 = (u32 *)(s_stage_all + (NUTSB_ACW_THREADS / 32) * 2 * (NUTSB_ACW_WIN + 48)) + warp * (34 + NUTSB_ACW_HITW);
+    u32 *const hits = s_p0 + 34;
+    {
+        const u32 cnt = ac.nstates * ac.ncls;
+        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) ((u16 *)s_trb)[i] = ac.tr16[i];
+        for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_cls2[i] = ac.cls2[i];
+    }
+    __syncthreads();
+    const u32 ov = ac.maxpat ? ac.maxpat - 1 : 0;
+    const i64 ntask = (n + 31) >> 5;
+    for (i64 task = (i64)blockIdx.x * (NUTSB_ACW_THREADS / 32) + warp; task < ntask; task += (i64)gridDim.x * (NUTSB_ACW_THREADS / 32)) {
+        const i64 wbase = task << 5;
+        const u32 nops = (u32)(n - wbase < 32 ? n - wbase : 32);
+        u64 o0 = 0, o1 = 0;
+        if ((u32)lane < nops) { o0 = off[wbase + lane]; o1 = off[wbase + lane + 1]; }
+        const bool bad = __any_sync(NUTSB_FULL, o1 < o0);
+        u32 mask = 0;
+        if (ac.root_match) mask = 0xffffffffu;                           // strstr(s, "") != NULL
+        else if (bad) {                                                  // offsets out of order: each string by itself
+            u32 st = 0;
+            if ((u32)lane < nops && o1 > o0 && nutsb_acw_walk(text + o0, text + o1, s_trb, s_cls2, st) >= ac.thresh) mask = 1u << lane;
+        } else {
+            // the warp's strings in one window, or -- when they add up to more than the window -- in several
+            for (u32 qa = 0; qa < nops; ) {
+                const u64 b0 = __shfl_sync(NUTSB_FULL, o0, (int)qa);
+                const u8 *pa = (const u8 *)((size_t)(text + b0) & ~(size_t)15);
+                const bool fit = (u32)lane >= qa && (u32)lane < nops && (u64)((text + o1) - pa) <= NUTSB_ACW_WIN;
+                const u32 fm = __ballot_sync(NUTSB_FULL, fit) >> qa;
+                const u32 cnt = fm == 0xffffffffu ? 32u : (u32)__ffs((int)~fm) - 1;   // strings qa .. qa+cnt-1 fit together (fit is monotone)
+                if (cnt == 0) {                                          // one string longer than the window: its lane walks it
+                    u32 st = 0;
+                    if ((u32)lane == qa && nutsb_acw_walk(text + o0, text + o1, s_trb, s_cls2, st) >= ac.thresh) mask |= 1u << lane;
+                    ++qa;
+                    continue;
+                }
+                const u32 qb = qa + cnt;
+                const u64 b1 = __shfl_sync(NUTSB_FULL, o1, (int)qb - 1);
+                const u32 span = (u32)((text + b1) - pa);
+                const u32 nvec = (span + 15) >> 4;
+                for (u32 v = lane; v < nvec; v += 32) {
+                    *(uint4 *)(stage + 16 * v) = __ldg((const uint4 *)pa + v);
+                    *(uint4 *)(pm + 16 * v) = make_uint4(~0u, ~0u, ~0u, ~0u);
+                }
+                for (u32 v = lane; v < (NUTSB_ACW_WIN + 48) / 32; v += 32) hits[v] = 0;
+                const u32 r0 = (u32)((text + b0) - pa), r1 = span;
+                // s_p0[i] = start of string qa + i in the window, i = 0 .. cnt (the end)
+                if ((u32)lane >= qa && (u32)lane < qb) s_p0[lane - qa] = (u32)((text + o0) - pa);
+                if (lane == 0) s_p0[cnt] = r1;
+                __syncwarp();
+                // string starts as DATA: pm[j] = 0 where a string begins (the state falls back to the root there), 0xff
+                // elsewhere -- a lane meets a string start once in ~64 bytes, but some lane of the warp meets one every
+                // other step, so a branch for it would run all the time
+                if ((u32)lane < cnt) pm[s_p0[lane]] = 0;
+                __syncwarp();
+                // a lane's piece is an ODD number of words: the lanes walk in step, byte i of every piece at once, and
+                // with an odd word stride those 32 bytes sit in 32 different banks (64-byte pieces would share two)
+                const u32 total = r1 - r0;
+                const u32 chunk = 4u * ((((total + 31) >> 5) + 3) >> 2 | 1u);
+                const u32 c0 = r0 + (u32)lane * chunk;
+                u32 c1 = c0 + chunk; if (c1 > r1) c1 = r1;
+                if (c0 < r1) {
+                    // four bytes per round: the text word and the mask word with one load each, the four class lookups
+                    // together, then the four dependent transitions; hits are looked for once per round (a running
+                    // maximum) and, when there is one, the round is walked again byte by byte to credit the right string.
+                    // The walk starts on a word boundary at or before its first byte and ends on one at or after its last:
+                    // the extra bytes only lengthen the overlap (hits outside [r0, r1) are dropped).
+                    const u32 js = (c0 >= r0 + ov ? c0 - ov : r0) & ~3u, je = (c1 + 3) & ~3u;
+                    u32 st = 0;
+                    // (the next round's words and classes are fetched before this round's transitions are walked: they do
+                    // not depend on the state, and the kernel is bound by the latency of the four dependent lookups)
+                    u32 m = *(const u32 *)(pm + js);
+                    u32 k0, k1, k2, k3;
+                    { const u32 w = *(const u32 *)(stage + js);
+                      k0 = s_cls2[w & 0xffu]; k1 = s_cls2[(w >> 8) & 0xffu]; k2 = s_cls2[(w >> 16) & 0xffu]; k3 = s_cls2[w >> 24]; }
+                    for (u32 j = js; j < je; j += 4) {                    // the same trip count in every lane (+-1)
+                        const u32 jn = j + 4 < je ? j + 4 : j;
+                        const u32 wn = *(const u32 *)(stage + jn), mn = *(const u32 *)(pm + jn);
+                        const u32 n0 = s_cls2[wn & 0xffu], n1 = s_cls2[(wn >> 8) & 0xffu], n2 = s_cls2[(wn >> 16) & 0xffu], n3 = s_cls2[wn >> 24];
+                        const u32 s1 = *(const u16 *)(s_trb + (st & __byte_perm(m, 0, 0x4400)) + k0);
+                        const u32 s2 = *(const u16 *)(s_trb + (s1 & __byte_perm(m, 0, 0x4511)) + k1);
+                        const u32 s3 = *(const u16 *)(s_trb + (s2 & __byte_perm(m, 0, 0x4622)) + k2);
+                        st = *(const u16 *)(s_trb + (s3 & __byte_perm(m, 0, 0x4733)) + k3);
+                        m = mn; k0 = n0; k1 = n1; k2 = n2; k3 = n3;
+                        u32 acc = s1 > s2 ? s1 : s2; acc = acc > s3 ? acc : s3; acc = acc > st ? acc : st;
+                        if (acc >= ac.thresh) {
+                            // a hit: only its POSITION is noted here (one bit per text byte, one shared-memory atomic per
+                            // round) -- whose string it is gets settled after the walk, by the string's own lane
+                            const u32 T = ac.thresh;
+                            const u32 hb = (s1 >= T ? 1u : 0u) | (s2 >= T ? 2u : 0u) | (s3 >= T ? 4u : 0u) | (st >= T ? 8u : 0u);
+                            atomicOr(&hits[j >> 5], hb << (j & 31u));     // (j is a multiple of 4: the four bits stay in one word)
+                        }
+                    }
+                }
+                __syncwarp();
+                if ((u32)lane < cnt) {                                    // lane i: any hit inside string qa + i ?
+                    const u32 a0 = s_p0[lane], a1 = s_p0[lane + 1];
+                    u32 any = 0;
+                    for (u32 wd = a0 >> 5; a1 > a0 && wd <= (a1 - 1) >> 5; ++wd) {
+                        u32 bits = hits[wd];
+                        if (wd == a0 >> 5) bits &= 0xffffffffu << (a0 & 31u);
+                        if (wd == (a1 - 1) >> 5) bits &= 0xffffffffu >> (31u - ((a1 - 1) & 31u));
+                        any |= bits;
+                    }
+                    if (any) mask |= 1u << (qa + (u32)lane);
+                }
+                __syncwarp();
+                qa = qb;
+            }
+        }
+        mask = __reduce_or_sync(NUTSB_FULL, mask);
+        if ((u32)lane < nops) verdict[wbase + lane] = (u8)((mask >> lane) & 1u);
     }
 }
 
