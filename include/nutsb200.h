@@ -335,6 +335,52 @@ int nutsb_colour_com_strip_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes
  * gather-list batch that never built the streams (plain listeners: nothing to digest in HBM). */
 int nutsb_stream_digests(nutsb_ctx *ctx, uint64_t *digest);
 
+/* Streams left in HBM: ops in host memory, nutsb_streams with device pointers (on_device 1) -- for a caller
+ * that only wants digests (nutsb_stream_digests) or copies what it needs later. */
+int nutsb_write_batch_keep(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_streams *out);
+/* nutsb_stream_digests continuing from the values in digest[]: the fold over what a user received in earlier
+ * batches goes on over this batch's stream (a job run in message-ordered chunks). */
+int nutsb_stream_digests_continue(nutsb_ctx *ctx, uint64_t *digest);
+
+/* ---- several GPUs: one population, one batch ------------------------------------
+ * The path shards by room with no exchange step.  nutsb_multi holds one context per shard; rooms are dealt to
+ * the shards heaviest first onto the least loaded one (weight: the room's population, or room_weight[]), a room's
+ * users go with it.  A batch is routed on the host: write_user -> the user's shard, write_room[_except](rm) -> rm's
+ * shard, the all-room forms (rm == NULL, nuts333.c:1399-1400: shout c:4119-4123, bcast c:4783-4787) and write_level
+ * (c:1372-1385) are replicated to every shard, each rendering for its own users.  Shards run concurrently, one host
+ * thread and one device each, no collective; results come back in GLOBAL user order.  Clones / remote users are
+ * refused (NUTSB_E_UNSUPPORTED): their relays cross rooms.
+ * nutsb_multi_create_rank: one process per GPU (torchrun) -- this process runs shard `shard` only; every process
+ * gives the same population and batches, plans and routes identically, and reports its own users' streams. */
+typedef struct nutsb_multi nutsb_multi;
+typedef struct nutsb_mstreams {
+    int64_t         n_users;
+    uint64_t        total_bytes;    /* over the shards this process runs                   */
+    uint64_t        n_deliveries;
+    const uint64_t *len;            /* n_users: length of user u's stream (NULL when kept in HBM) */
+    const uint8_t *const *ptr;      /* n_users: its bytes, in the owning shard's pinned buffer     */
+    int32_t         on_device;      /* 1: the streams were left in HBM (keep != 0)          */
+} nutsb_mstreams;
+int  nutsb_multi_create(nutsb_multi **out, const int *device_ids, int n_devices);
+int  nutsb_multi_create_rank(nutsb_multi **out, int n_shards, int shard, int device);
+void nutsb_multi_destroy(nutsb_multi *m);
+const char *nutsb_multi_last_error(const nutsb_multi *m);
+int  nutsb_multi_n_shards(const nutsb_multi *m);
+nutsb_ctx *nutsb_multi_ctx(nutsb_multi *m, int shard);          /* NULL for a shard this process does not run */
+int  nutsb_multi_set_swear_words(nutsb_multi *m, const char *const *words);
+int  nutsb_multi_set_ban_files(nutsb_multi *m, const void *siteban, size_t siteban_len, const void *userban, size_t userban_len);
+int  nutsb_multi_set_profiling(nutsb_multi *m, int on);
+int  nutsb_multi_set_users(nutsb_multi *m, int32_t n_users, int32_t n_rooms, const int32_t *room,
+                           const uint8_t *flags, const uint8_t *level, const uint64_t *room_weight);
+int  nutsb_multi_plan(const nutsb_multi *m, int32_t *room_shard, int32_t *user_shard, int32_t *user_local);
+int  nutsb_multi_route(nutsb_multi *m, const nutsb_ops *ops, int shard, nutsb_ops *out);
+int  nutsb_multi_write_batch(nutsb_multi *m, const nutsb_ops *ops, nutsb_mstreams *out, int keep);
+int  nutsb_multi_stream_digests(nutsb_multi *m, uint64_t *digest, int cont);
+int  nutsb_multi_contains_swearing_batch(nutsb_multi *m, int64_t n, const uint8_t *bytes, const uint64_t *off, uint8_t *verdict);
+int  nutsb_multi_site_banned_batch(nutsb_multi *m, int64_t n, const uint8_t *bytes, const uint64_t *off, uint8_t *verdict);
+int  nutsb_multi_user_banned_batch(nutsb_multi *m, int64_t n, const uint8_t *bytes, const uint64_t *off, uint8_t *verdict);
+int  nutsb_multi_get_timing(const nutsb_multi *m, int shard, nutsb_timing *out);
+
 /* ---- queue tier: the reference's call surface, one call each ------------ */
 
 int nutsb_q_write_user(nutsb_ctx *ctx, int32_t user, const char *str);            /* c:1291 */

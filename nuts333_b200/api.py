@@ -63,6 +63,11 @@ class _IovStreams(C.Structure):
                 ("pool2", C.c_void_p), ("pool2_bytes", C.c_uint64)]
 
 
+class _MStreams(C.Structure):
+    _fields_ = [("n_users", C.c_int64), ("total_bytes", C.c_uint64), ("n_deliveries", C.c_uint64),
+                ("len", C.c_void_p), ("ptr", C.c_void_p), ("on_device", C.c_int32)]
+
+
 class Timing(C.Structure):
     _fields_ = [("plan_ms", C.c_float), ("render_ms", C.c_float), ("fanout_ms", C.c_float), ("direct_ms", C.c_float),
                 ("total_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
@@ -83,6 +88,11 @@ EXPORTS = [
     "nutsb_colour_com_count_batch", "nutsb_colour_com_strip_batch", "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
     "nutsb_q_write_level", "nutsb_q_write_sock", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_flush_iov", "nutsb_contains_swearing",
     "nutsb_site_banned", "nutsb_user_banned",
+    "nutsb_write_batch_keep", "nutsb_stream_digests_continue",
+    "nutsb_multi_create", "nutsb_multi_create_rank", "nutsb_multi_destroy", "nutsb_multi_last_error", "nutsb_multi_n_shards", "nutsb_multi_ctx",
+    "nutsb_multi_set_swear_words", "nutsb_multi_set_ban_files", "nutsb_multi_set_profiling", "nutsb_multi_set_users", "nutsb_multi_plan",
+    "nutsb_multi_route", "nutsb_multi_write_batch", "nutsb_multi_stream_digests", "nutsb_multi_contains_swearing_batch",
+    "nutsb_multi_site_banned_batch", "nutsb_multi_user_banned_batch", "nutsb_multi_get_timing",
 ]
 
 
@@ -148,6 +158,28 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_q_pending.argtypes = [vp]
     lib.nutsb_flush.argtypes = [vp, C.POINTER(_Streams)]
     lib.nutsb_flush_iov.argtypes = [vp, C.POINTER(_IovStreams)]
+    lib.nutsb_write_batch_keep.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_Streams)]
+    lib.nutsb_stream_digests_continue.argtypes = [vp, u64p]
+    lib.nutsb_multi_create.argtypes = [C.POINTER(vp), i32p, C.c_int]
+    lib.nutsb_multi_create_rank.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int]
+    lib.nutsb_multi_destroy.argtypes = [vp]
+    lib.nutsb_multi_destroy.restype = None
+    lib.nutsb_multi_last_error.argtypes = [vp]
+    lib.nutsb_multi_last_error.restype = C.c_char_p
+    lib.nutsb_multi_n_shards.argtypes = [vp]
+    lib.nutsb_multi_ctx.argtypes = [vp, C.c_int]
+    lib.nutsb_multi_ctx.restype = vp
+    lib.nutsb_multi_set_swear_words.argtypes = [vp, C.POINTER(C.c_char_p)]
+    lib.nutsb_multi_set_ban_files.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    lib.nutsb_multi_set_profiling.argtypes = [vp, C.c_int]
+    lib.nutsb_multi_set_users.argtypes = [vp, C.c_int32, C.c_int32, i32p, u8p, u8p, u64p]
+    lib.nutsb_multi_plan.argtypes = [vp, i32p, i32p, i32p]
+    lib.nutsb_multi_route.argtypes = [vp, C.POINTER(_Ops), C.c_int, C.POINTER(_Ops)]
+    lib.nutsb_multi_write_batch.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_MStreams), C.c_int]
+    lib.nutsb_multi_stream_digests.argtypes = [vp, u64p, C.c_int]
+    for name in ("contains_swearing", "site_banned", "user_banned"):
+        getattr(lib, f"nutsb_multi_{name}_batch").argtypes = [vp, C.c_int64, vp, vp, vp]
+    lib.nutsb_multi_get_timing.argtypes = [vp, C.c_int, C.POINTER(Timing)]
     return lib
 
 
@@ -598,3 +630,131 @@ class Talker:
 
     def user_banned(self, name) -> int:                               # c:349
         return self.ctx._ck(self.ctx.lib.nutsb_user_banned(self.ctx._h, self._s(name)))
+
+
+class MultiContext:
+    """nutsb_multi: one population and one batch over several GPUs (include/nutsb200.h).  `devices`: one context per
+    entry (the same device may be named twice); or rank=(n_shards, shard, device) for one process per GPU."""
+
+    def __init__(self, devices=None, lib=None, rank=None):
+        self.lib = lib or load_library()
+        self._h = C.c_void_p()
+        if rank is not None:
+            rc = self.lib.nutsb_multi_create_rank(C.byref(self._h), int(rank[0]), int(rank[1]), int(rank[2]))
+        else:
+            d = _np(devices, np.int32)
+            rc = self.lib.nutsb_multi_create(C.byref(self._h), d.ctypes.data_as(i32p), len(d))
+        if rc != 0:
+            raise NutsbError(rc, "nutsb_multi_create failed: there is no CPU fallback")
+        self.n_users = 0
+        self._ctxs = {}
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise NutsbError(rc, (self.lib.nutsb_multi_last_error(self._h) or b"").decode(errors="replace"))
+
+    def close(self):
+        if self._h:
+            self.lib.nutsb_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    @property
+    def n_shards(self):
+        return int(self.lib.nutsb_multi_n_shards(self._h))
+
+    def ctx(self, shard) -> "Context":
+        """The shard's own context (None when this process does not run it); owned by the MultiContext."""
+        if shard not in self._ctxs:
+            h = self.lib.nutsb_multi_ctx(self._h, shard)
+            if not h:
+                return None
+            c = Context.__new__(Context)
+            c.lib, c._h, c.n_users = self.lib, C.c_void_p(h), 0
+            c.close = lambda: None
+            self._ctxs[shard] = c
+        return self._ctxs[shard]
+
+    def set_swear_words(self, words):
+        ws = [w if isinstance(w, bytes) else w.encode() for w in words]
+        arr = (C.c_char_p * (len(ws) + 1))(*ws, None)
+        self._ck(self.lib.nutsb_multi_set_swear_words(self._h, arr))
+
+    def set_ban_files(self, siteban, userban):
+        self._ck(self.lib.nutsb_multi_set_ban_files(self._h, siteban, 0 if siteban is None else len(siteban),
+                                                    userban, 0 if userban is None else len(userban)))
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.nutsb_multi_set_profiling(self._h, 1 if on else 0))
+
+    def set_users(self, room, flags, level, n_rooms, room_weight=None):
+        room, flags, level = _np(room, np.int32), _np(flags, np.uint8), _np(level, np.uint8)
+        w = None if room_weight is None else _np(room_weight, np.uint64)
+        self._ck(self.lib.nutsb_multi_set_users(self._h, len(room), n_rooms, room.ctypes.data_as(i32p), flags.ctypes.data_as(u8p),
+                                                level.ctypes.data_as(u8p), None if w is None else w.ctypes.data_as(u64p)))
+        self.n_users, self.n_rooms = len(room), n_rooms
+
+    def plan(self):
+        """-> room_shard[n_rooms], user_shard[n_users], user_local[n_users]"""
+        rs, us, ul = np.zeros(max(self.n_rooms, 1), np.int32), np.zeros(max(self.n_users, 1), np.int32), np.zeros(max(self.n_users, 1), np.int32)
+        self._ck(self.lib.nutsb_multi_plan(self._h, rs.ctypes.data_as(i32p), us.ctypes.data_as(i32p), ul.ctypes.data_as(i32p)))
+        return rs[:self.n_rooms], us[:self.n_users], ul[:self.n_users]
+
+    def _ops(self, ops, keep):
+        return Context._ops_struct(ops, keep)
+
+    def route(self, ops, shard):
+        """The shard's routed ops as numpy copies (dict like `ops`, local indices)."""
+        keep = []
+        o = self._ops(ops, keep)
+        r = _Ops()
+        self._ck(self.lib.nutsb_multi_route(self._h, C.byref(o), shard, C.byref(r)))
+        n = int(r.n_ops)
+        arr = lambda p, t, k: (np.ctypeslib.as_array(C.cast(p, C.POINTER(t)), shape=(k,)).copy() if k else np.zeros(0, t))
+        off = arr(r.text_off, C.c_uint64, n + 1)
+        out = dict(text=arr(r.text, C.c_uint8, int(off[-1])), off=off, kind=arr(r.kind, C.c_uint8, n), target=arr(r.target, C.c_int32, n),
+                   except_user=arr(r.except_user, C.c_int32, n), flags=arr(r.flags, C.c_uint8, n))
+        if r.gate:
+            out["gate"] = arr(r.gate, C.c_int32, n)
+            out["verdict"] = np.ascontiguousarray(ops["verdict"], np.uint8)
+        return out
+
+    def write_batch(self, ops, keep=False):
+        """-> list[bytes] per user in GLOBAL order (None per user when keep), total_bytes, n_deliveries"""
+        k = []
+        o = self._ops(ops, k)
+        st = _MStreams()
+        self._ck(self.lib.nutsb_multi_write_batch(self._h, C.byref(o), C.byref(st), 1 if keep else 0))
+        if keep:
+            return None, int(st.total_bytes), int(st.n_deliveries)
+        U = int(st.n_users)
+        ln = np.ctypeslib.as_array(C.cast(st.len, u64p), shape=(max(U, 1),))[:U]
+        pt = np.ctypeslib.as_array(C.cast(st.ptr, u64p), shape=(max(U, 1),))[:U]
+        return [C.string_at(int(pt[u]), int(ln[u])) if ln[u] else b"" for u in range(U)], int(st.total_bytes), int(st.n_deliveries)
+
+    def stream_digests(self, digest=None):
+        """Per-user digests in global order; digest given: the fold continues from it (chunked jobs)."""
+        cont = digest is not None
+        d = np.zeros(max(self.n_users, 1), np.uint64) if digest is None else np.ascontiguousarray(digest, np.uint64)
+        self._ck(self.lib.nutsb_multi_stream_digests(self._h, d.ctypes.data_as(u64p), 1 if cont else 0))
+        return d[:self.n_users]
+
+    def _verdicts(self, fn, data, off):
+        data, off = _np(data, np.uint8), _np(off, np.uint64)
+        n = len(off) - 1
+        v = np.zeros(max(n, 1), np.uint8)
+        self._ck(fn(self._h, n, _addr(data) if data.size else None, _addr(off), _addr(v)))
+        return v[:n]
+
+    def contains_swearing_batch(self, data, off):
+        return self._verdicts(self.lib.nutsb_multi_contains_swearing_batch, data, off)
+
+    def site_banned_batch(self, data, off):
+        return self._verdicts(self.lib.nutsb_multi_site_banned_batch, data, off)
+
+    def user_banned_batch(self, data, off):
+        return self._verdicts(self.lib.nutsb_multi_user_banned_batch, data, off)
+
+    def timing(self, shard) -> Timing:
+        t = Timing()
+        self._ck(self.lib.nutsb_multi_get_timing(self._h, shard, C.byref(t)))
+        return t

@@ -1297,8 +1297,9 @@ __global__ void k_readback_end(const u64 *counters, const u32 *status, u64 *h_co
 #define NUTSB_DIGEST_P  0x100000001b3ull
 #define NUTSB_DIGEST_H0 0xcbf29ce484222325ull
 
+// init != null: the fold goes on from init[u] (the digest of what user u received in earlier batches)
 __global__ void __launch_bounds__(256)
-k_digest(const u8 *bytes, const u64 *off, i32 n_users, u64 *digest)
+k_digest(const u8 *bytes, const u64 *off, i32 n_users, const u64 *init, u64 *digest)
 {
     __shared__ u64 s_m[256], s_a[256];
     for (i32 u = blockIdx.x; u < n_users; u += gridDim.x) {
@@ -1312,7 +1313,7 @@ k_digest(const u8 *bytes, const u64 *off, i32 n_users, u64 *digest)
         s_m[threadIdx.x] = m; s_a[threadIdx.x] = a;
         __syncthreads();
         if (threadIdx.x == 0) {
-            u64 h = NUTSB_DIGEST_H0;
+            u64 h = init ? init[u] : NUTSB_DIGEST_H0;
             for (int q = 0; q < 256; ++q) h = h * s_m[q] + s_a[q];
             digest[u] = h;
         }

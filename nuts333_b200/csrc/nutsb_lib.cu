@@ -1184,17 +1184,37 @@ static int write_batch_iov_host(nutsb_ctx *c, const nutsb_ops *o, nutsb_iov_stre
     return fetch_iov(c, ds, iv, out);
 }
 
-NUTSB_API int nutsb_stream_digests(nutsb_ctx *c, uint64_t *digest)
+static int stream_digests(nutsb_ctx *c, uint64_t *digest, bool cont)
 {
     if (!c || !digest) return NUTSB_E_INVAL;
     if (!c->have_streams) return fail(c, NUTSB_E_STATE, "no write batch has run%s");
     CK(cudaSetDevice(c->device));
     if (c->U == 0) return NUTSB_OK;
-    TRY(ensure(c, c->d_digest, (size_t)c->U * 8));
+    TRY(ensure(c, c->d_digest, (size_t)c->U * 16));
+    u64 *d_out = c->d_digest.as<u64>(), *d_init = d_out + c->U;
+    if (cont) CK(cudaMemcpyAsync(d_init, digest, (size_t)c->U * 8, cudaMemcpyHostToDevice, c->stream));
     const u32 grid = std::min<u32>((u32)c->U, (u32)c->sm_count * 16u);
-    NUTSB_LAUNCH(grid, 256, c->stream, k_digest, c->d_out.as<u8>(), c->d_off.as<u64>(), c->U, c->d_digest.as<u64>()); CKL();
-    CK(cudaMemcpyAsync(digest, c->d_digest.p, (size_t)c->U * 8, cudaMemcpyDeviceToHost, c->stream));
+    NUTSB_LAUNCH(grid, 256, c->stream, k_digest, c->d_out.as<u8>(), c->d_off.as<u64>(), c->U, cont ? (const u64 *)d_init : (const u64 *)nullptr, d_out); CKL();
+    CK(cudaMemcpyAsync(digest, d_out, (size_t)c->U * 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    return NUTSB_OK;
+}
+NUTSB_API int nutsb_stream_digests(nutsb_ctx *c, uint64_t *digest) { return stream_digests(c, digest, false); }
+NUTSB_API int nutsb_stream_digests_continue(nutsb_ctx *c, uint64_t *digest) { return stream_digests(c, digest, true); }
+
+// ops in host memory, streams left in HBM (digests, or a later copy, are the caller's business)
+NUTSB_API int nutsb_write_batch_keep(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)
+{
+    TRY(check_ops(c, o, out));
+    TRY(no_relays_on_device(c));
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    if (c->profiling) CK(cudaEventRecord(c->ev[4], st));
+    nutsb_ops d;
+    TRY(upload_ops(c, o, &d));
+    if (c->profiling) CK(cudaEventRecord(c->ev[5], st));
+    TRY(run_write(c, &d, out));
+    if (c->profiling) { CK(cudaEventElapsedTime(&c->tm.h2d_ms, c->ev[4], c->ev[5])); c->tm.d2h_ms = 0; }
     return NUTSB_OK;
 }
 
@@ -1970,3 +1990,5 @@ NUTSB_API int nutsb_speech_batch_iov(nutsb_ctx *c, int64_t n, const uint8_t *ver
     if (c->profiling) { CK(cudaEventElapsedTime(&c->tm.h2d_ms, c->ev[4], c->ev[5])); CK(cudaEventRecord(c->ev[4], c->stream)); }
     return fetch_iov(c, ds_, iv, out);
 }
+
+#include "nutsb_multi.cuh"

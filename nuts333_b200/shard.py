@@ -1,7 +1,10 @@
-"""Room sharding for multi-GPU runs: rank g owns a contiguous block of
-rooms together with those rooms' users and messages.  The path has no exchange step, so a
-rank's per-user streams depend on its own shard only; all-room broadcasts would be
-replicated as input to every rank.  Host-side bookkeeping only."""
+"""Synthetic per-rank inputs for the weak-scaling benchmark and the sharding checks.
+
+The sharder itself is in the library: nutsb_multi (include/nutsb200.h, csrc/nutsb_multi.cuh) takes one global
+population and one batch, deals the rooms to the shards, routes the ops (all-room and level ops replicated) and
+returns the streams in global user order; api.MultiContext binds it.  This module only *generates* inputs: rank g's
+own rooms, users and messages (bench.py's weak scaling: per-GPU work fixed), and `to_global`, which puts such shards
+together into the one population / one batch that a single context -- or nutsb_multi -- renders as a whole."""
 from __future__ import annotations
 
 import numpy as np
