@@ -135,7 +135,13 @@ class ClockSampler:
 def _ref_worker(args):
     """One process = one single-threaded reference instance (its state is global) on one
     room-shard of the sample.  Returns (deliveries, bytes, seconds, kind)."""
-    rank, shard, n_shards, n_msgs, n_ban = args
+    rank, shard, n_shards, n_msgs, n_ban = args[:5]
+    both_sinks = len(args) > 5 and args[5]
+    if len(args) > 6 and args[6] is not None:             # the one-core leg: pinned (BASELINE.md section 3: taskset)
+        try:
+            os.sched_setaffinity(0, {args[6]})
+        except OSError:
+            pass
     import tempfile
     import oracle_lib as O
     inp = make_inputs(rank, n_msgs)
@@ -169,40 +175,71 @@ def _ref_worker(args):
     qn = [nt[int(no[i]):int(no[i + 1])].tobytes() for i in range(shard, n_ban, n_shards)]
     qst, qso = O.pack(qs)
     qnt, qno = O.pack(qn)
+    comp = dict(n_msgs=len(msg_idx), n_ban=len(qs) + len(qn))
     t0 = time.perf_counter()
     if R is not None:
         R.set_swear_words(words[:-1])
         R.set_ban_file(0, inp["sfile"]); R.set_ban_file(1, inp["ufile"])
+        ta = time.perf_counter()
         v = R.contains_swearing_batch(b2, bo2)
+        tb = time.perf_counter()
         R.ban_batch(0, qst, qso); R.ban_batch(1, qnt, qno)
+        tc = time.perf_counter()
         R.write_batch(sub, inp["n_rooms"], users, verdict=v, sink_mode=1)
+        td = time.perf_counter()
         deliveries = None
         nbytes = int(R.lib.ref_total_write_bytes())
-        dt = time.perf_counter() - t0
+        dt = td - t0
+        comp.update(swear_s=tb - ta, bans_s=tc - tb, write_s=td - tc)
         deliveries, _ = P.write_batch_count(sub, users, verdict=v)      # counted outside the timed region
+        if both_sinks:                                                  # the faithful sink: write(2) to /dev/null (c:1318 ...)
+            te = time.perf_counter()
+            R.write_batch(sub, inp["n_rooms"], users, verdict=v, sink_mode=2)
+            comp.update(write_devnull_s=time.perf_counter() - te, write_calls=int(R.lib.ref_total_write_calls()))
     else:
+        ta = time.perf_counter()
         v = P.contains_swearing_batch(b2, bo2, words)
+        tb = time.perf_counter()
         P.ban_batch(0, inp["sfile"], qst, qso); P.ban_batch(1, inp["ufile"], qnt, qno)
+        tc = time.perf_counter()
         deliveries, nbytes = P.write_batch_count(sub, users, verdict=v)
-        dt = time.perf_counter() - t0
-    return deliveries, nbytes, dt, kind
+        td = time.perf_counter()
+        dt = td - t0
+        comp.update(swear_s=tb - ta, bans_s=tc - tb, write_s=td - tc)
+    comp["deliveries"] = int(deliveries)
+    return deliveries, nbytes, dt, kind, comp
 
 
-def reference_step(rank: int, n_msgs: int, n_ban: int, procs: int):
-    """Runs the reference's CPU path over a bounded sample with `procs` host processes."""
+def reference_step(rank: int, n_msgs: int, n_ban: int, procs: int, both_sinks: bool = False, components: dict | None = None):
+    """Runs the reference's CPU path over a bounded sample with `procs` host processes (one process: pinned to one
+    core, in a child so that the caller's affinity is left alone).  components: filled with the slowest worker's
+    time per component (swear, bans, render + fan-out) and the sample's sizes."""
     import multiprocessing as mp
     import oracle_lib as O
     O.port(); O.ref()                       # build / load the checkers once, before forking
-    args = [(rank, s, procs, n_msgs, n_ban) for s in range(procs)]
-    t0 = time.perf_counter()
+    pin = None
     if procs == 1:
-        res = [_ref_worker(args[0])]
-    else:
-        with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(_ref_worker, args)
+        try:
+            pin = sorted(os.sched_getaffinity(0))[-1]
+        except (AttributeError, OSError):
+            pin = None
+    args = [(rank, s, procs, n_msgs, n_ban, both_sinks, pin) for s in range(procs)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(procs) as pool:
+        res = pool.map(_ref_worker, args)
     wall = time.perf_counter() - t0
     d = sum(r[0] for r in res)
     busy = max(r[2] for r in res)
+    if components is not None:
+        for k in ("swear_s", "bans_s", "write_s", "write_devnull_s"):
+            vals = [r[4][k] for r in res if k in r[4]]
+            if vals:
+                components[k] = max(vals)
+        for k in ("n_msgs", "n_ban", "deliveries", "write_calls"):
+            vals = [r[4][k] for r in res if k in r[4]]
+            if vals:
+                components[k] = sum(vals)
+        components["pinned_core"] = pin
     return d, sum(r[1] for r in res), busy, wall, res[0][3]
 
 
@@ -215,8 +252,9 @@ def run_reference(args):
     n_msgs = min(20_000 * max(1, procs // 4), N_MSGS)
     n_ban = max(procs, n_msgs * N_BAN_QUERIES // N_MSGS)        # the sample keeps the step's msgs : ban-queries ratio
     times, deliv = [], 0
+    comp = {}
     for i in range(args.warmup + args.steps):
-        d, nbytes, busy, wall, kind = reference_step(0, n_msgs, n_ban, procs)
+        d, nbytes, busy, wall, kind = reference_step(0, n_msgs, n_ban, procs, components=comp)
         if i >= args.warmup:
             times.append(busy); deliv += d
     total = sum(times)
@@ -227,7 +265,10 @@ def run_reference(args):
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * total / max(1, args.steps), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
-                config=dict(workload=workload_name(), note="reference CPU path on a bounded sample of the workload"),
+                config=dict(workload=workload_name(), note="reference CPU path on a bounded sample of the workload: the rate "
+                            "of a proportional %.0f %% sample (msgs and ban queries in the step's ratio), not a full step" % (100.0 * n_msgs / N_MSGS),
+                            components=dict(comp, note="slowest worker's seconds per component in the last step; the ban checks "
+                                            "(fopen + fscanf of a 10k-entry file per query, nuts333.c:330-364) dominate")),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=procs, kind=kind, sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
@@ -372,6 +413,19 @@ def run_ours(args):
         step_device()
     torch.cuda.synchronize()
     kstate = dict(state)
+    # the three verdict kernels by themselves (CUDA events on the stream they run on)
+    comp_ms = {}
+    L0 = lanes[0]
+    for nme, n_q, a, b, out in (("swear", N_MSGS, d["bt"], d["bo"], L0["verdict"]), ("site", N_BAN_QUERIES, d["st"], d["so"], L0["vs"]),
+                                ("user", N_BAN_QUERIES, d["nt"], d["no"], L0["vu"])):
+        fn = {"swear": "contains_swearing", "site": "site_banned", "user": "user_banned"}[nme]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KERNEL_TIMING_STEPS)]
+        for a0, a1 in evs:
+            a0.record(stream)
+            ctx.verdicts_dev(fn, n_q, a.data_ptr(), b.data_ptr(), out.data_ptr())
+            a1.record(stream)
+        torch.cuda.synchronize()
+        comp_ms[nme] = min(a0.elapsed_time(a1) for a0, a1 in evs)
     ctx.set_overlap(os.environ.get('NUTSB_OVERLAP', '1') != '0')
 
     # ---- beside the headline (one batch at a time): the same K steps with two batches in flight on the GPU
@@ -445,8 +499,27 @@ def run_ours(args):
                 out_bytes = int(s.total_bytes)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            if i == 0:
+                # outside the timed passes: the BYTES of sampled users' streams, so that the three legs can be told
+                # to deliver the same streams and not just the same counts
+                import hashlib
+                sample = range(0, N_USERS, max(1, N_USERS // 64))
+                offs = np.ctypeslib.as_array(api.C.cast(s.off, api.u64p), shape=(N_USERS + 1,))
+                h = hashlib.sha256()
+                if iov:
+                    first = np.ctypeslib.as_array(api.C.cast(s.first, api.u64p), shape=(N_USERS,))
+                    cnt = np.ctypeslib.as_array(api.C.cast(s.count, api.C.POINTER(api.C.c_uint32)), shape=(N_USERS,))
+                    pieces = np.ctypeslib.as_array(api.C.cast(s.iov, api.u64p), shape=(int(s.n_iov), 2))
+                    for u in sample:
+                        for k in range(int(first[u]), int(first[u]) + int(cnt[u])):
+                            if pieces[k, 1]:
+                                h.update(api.C.string_at(int(pieces[k, 0]), int(pieces[k, 1])))
+                else:
+                    for u in sample:
+                        h.update(api.C.string_at(s.bytes + int(offs[u]), int(offs[u + 1] - offs[u])))
+                r["sample_sha"] = h.hexdigest()
             if i == 0 and iov:
-                # outside the timed passes: the lists describe every byte of every stream
+                # the lists describe every byte of every stream
                 lens = np.ctypeslib.as_array(api.C.cast(s.iov, api.u64p), shape=(int(s.n_iov), 2))[:, 1]
                 assert int(lens.sum()) == int(s.total_bytes), "gather lists do not add up to the streams"
                 r["extra"] = dict(pool_bytes=int(s.pool_bytes) + int(s.pool2_bytes), n_iov=int(s.n_iov), stream_bytes=int(s.total_bytes))
@@ -461,13 +534,14 @@ def run_ours(args):
         return r
 
     e2e_steps = max(1, min(args.steps, 3))
-    zero = dict(h2d_ms=0.0, d2h_ms=0.0, ms=0.0, deliv=0, h2d=0, d2h=0, extra={})
+    zero = dict(h2d_ms=0.0, d2h_ms=0.0, ms=0.0, deliv=0, h2d=0, d2h=0, extra={}, sample_sha="")
     leg_s = zero if args.no_e2e else e2e_leg("streams")
     leg_v = zero if args.no_e2e else e2e_leg("iov")
     leg_p = zero if args.no_e2e else e2e_leg("speech_iov")
     if not args.no_e2e:                                    # the three legs deliver the same streams
         assert leg_v["deliv"] == leg_s["deliv"] == leg_p["deliv"], (leg_s["deliv"], leg_v["deliv"], leg_p["deliv"])
         assert leg_v["extra"]["stream_bytes"] == leg_p["extra"]["stream_bytes"]
+        assert leg_s["sample_sha"] == leg_v["sample_sha"] == leg_p["sample_sha"], "the e2e legs deliver different bytes"
     e2e_h2d_ms, e2e_d2h_ms, e2e_ms, e2e_deliv, h2d, d2h = (leg_s[k] for k in ("h2d_ms", "d2h_ms", "ms", "deliv", "h2d", "d2h"))
 
     # ---- the last leg again with two calls in flight (two contexts, two host threads): one call's H2D and
@@ -521,11 +595,12 @@ def run_ours(args):
         fan_bytes = (kstate["fan_in"] + kstate["fan_out"]) / ks
         fan_ms = kstate["fan_ms"] / ks
         achieved = fan_bytes / (fan_ms * 1e-3) / 1e9 if fan_ms > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None
         tp = ROOT / "profiles" / "fanout_traffic.json"
-        if tp.exists():
+        if tp.exists():             # an ncu figure (dram__bytes_read.sum + dram__bytes_write.sum of one k_fanout launch), NOT measured by this run
             try:
-                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
+                tj = json.loads(tp.read_text())
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
             except Exception:
                 traffic = None
         line = dict(metric=METRIC, value=total_deliv / (ms_max * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
@@ -552,7 +627,7 @@ def run_ours(args):
                                 plan_ms=kstate["plan_ms"] / ks, render_ms=kstate["render_ms"] / ks, fanout_ms=fan_ms,
                                 direct_ms=kstate["direct_ms"] / ks),
                     roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                                  traffic=traffic, kernel="k_fanout", peak_source=peak_src,
+                                  traffic=traffic, traffic_source=traffic_src, kernel="k_fanout", peak_source=peak_src,
                                   algorithmic_bytes_per_launch=fan_bytes,
                                   frac_of_spec_8000=achieved / 8000.0,          # both percentages
                                   whole_step=dict(achieved=(dev_state["bytes"] / max(1, args.steps) + input_bytes) / (ms_max / max(1, args.steps) * 1e-3) / 1e9,
@@ -581,18 +656,307 @@ def run_ours(args):
             line["e2e_speech_iov"]["two_calls_in_flight"] = dict(
                 value=float(sums[4]) / (pipe_ms_max * 1e-3), ms_per_step=pipe_ms_max / (2 * e2e_steps),
                 note="two contexts / host threads per GPU, %d calls each: one call's H2D and kernels under the other's D2H" % e2e_steps)
+        line["roofline"]["whole_step"]["frac"] = line["roofline"]["whole_step"]["achieved"] / peak
+        line["config"]["verdict_kernel_ms"] = dict(comp_ms, how="each verdict kernel alone, CUDA events, best of %d" % KERNEL_TIMING_STEPS)
         if world == 1 and not args.no_cpu_baseline:
             procs = 1
-            dcpu, nbytes, busy, wall, kind = reference_step(0, 40_000, 4_000, procs)
+            comp = {}
+            dcpu, nbytes, busy, wall, kind = reference_step(0, 40_000, 4_000, procs, both_sinks=True, components=comp)
             line["cpu_baseline"] = dict(value=dcpu / busy, unit=UNIT, cores=procs, kind=kind,
                                         sample="40000 of 1000000 msgs (all 10000 users) + 4000 of 100000 ban queries per "
-                                               "list, one single-threaded reference process, write(2) hooked to a byte counter")
+                                               "list, one single-threaded reference process pinned to core %s, write(2) hooked "
+                                               "to a byte counter" % comp.get("pinned_core"))
+            # what the one number above hides: per component, the reference on one pinned core against this GPU.
+            # The reference's ban checks re-open and re-parse the 10k-entry file per query (nuts333.c:330-364): they
+            # are ~90 % of its time on this workload, so the whole-step ratio is mostly a ban-file ratio.
+            write_ms = ms_max / max(1, args.steps) - sum(comp_ms.values())
+            gpu_d = total_deliv / max(1, args.steps)
+            vc = dict(
+                render_fanout=dict(gpu=gpu_d / (write_ms * 1e-3), cpu_1core=comp["deliveries"] / comp["write_s"], unit="deliveries/s",
+                                   cpu_sink="write(2) hooked to a byte counter (no syscalls)",
+                                   gpu_note="step time minus the verdict kernels, inputs resident in HBM, streams left in HBM"),
+                swear=dict(gpu=N_MSGS / (comp_ms["swear"] * 1e-3), cpu_1core=comp["n_msgs"] / comp["swear_s"], unit="msgs/s", words=N_SWEAR),
+                bans=dict(gpu=2 * N_BAN_QUERIES / ((comp_ms["site"] + comp_ms["user"]) * 1e-3), cpu_1core=comp["n_ban"] / comp["bans_s"],
+                          unit="queries/s", entries=N_BAN_ENTRIES),
+                cpu_time_share=dict(swear=comp["swear_s"] / busy, bans=comp["bans_s"] / busy, render_fanout=comp["write_s"] / busy),
+                pinned_core=comp.get("pinned_core"))
+            if "write_devnull_s" in comp:
+                vc["render_fanout"]["cpu_1core_devnull"] = comp["deliveries"] / comp["write_devnull_s"]
+                vc["render_fanout"]["cpu_devnull_sink"] = "the faithful sink: real write(2) to /dev/null, %.2f calls per delivery" % (comp.get("write_calls", 0) / max(1, comp["deliveries"]))
+            for k in ("render_fanout", "swear", "bans"):
+                vc[k]["ratio"] = vc[k]["gpu"] / vc[k]["cpu_1core"]
+            if not args.no_e2e:
+                vc["render_fanout"]["gpu_e2e_streams"] = line["e2e"]["value"]
+                vc["render_fanout"]["gpu_e2e_gather_lists"] = line["e2e_iov"]["value"]
+            line["vs_cpu_components"] = vc
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     for L in lanes:
         L["ctx"].close()
+    return 0
+
+
+# ---------------------------------------------------------------------------------------
+# the other BASELINE configs ("reported per config and GPU count")
+# ---------------------------------------------------------------------------------------
+def run_config(args):
+    """--config c2 | c4 | c5: one JSON line each, same timing rules as the default line (CUDA events on the stream the
+    kernels run on, >= 3 warm-up steps, max over ranks).  c2 = BASELINE config 2 (100k msgs x 1k users in one room,
+    colour only), c4 = config 4 alone (100k sites + 100k names vs 10k-entry lists), c5 = config 5 (10M msgs x 100k users,
+    admission -> swear -> say, rooms sharded over the GPUs by the library's sharder: STRONG scaling, total work fixed)."""
+    import torch
+    import torch.distributed as dist
+    from nuts333_b200 import api, build, synth
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    build.build()
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    stream = torch.cuda.Stream(device=dev)
+    to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    pad16 = lambda a: np.concatenate([a, np.zeros(32, np.uint8)])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    words = synth.swear_words(N_SWEAR)
+    cfg = args.config
+    line = None
+    if cfg == "c2":
+        M, U = 100_000, 1_000
+        users, n_rooms = synth.users(U, U)                       # one room
+        bt, bo = synth.bodies(M, None)
+        ops, spk, rm = synth.say_ops(M, U, U, bt, bo, gated=False)
+        ctx = api.Context(local); ctx.set_stream(stream.cuda_stream); ctx.set_profiling(True)
+        ctx.set_users(users["room"], users["flags"], users["level"], n_rooms)
+        dd = dict(text=to_dev(pad16(ops["text"])), off=to_dev(ops["off"].view(np.int64)), kind=to_dev(ops["kind"]), target=to_dev(ops["target"]),
+                  exc=to_dev(ops["except_user"]), flags=to_dev(ops["flags"]))
+        acc = dict(deliv=0, bytes=0, fan_ms=0.0, fan_b=0, n=0, launches=0)
+
+        def step():
+            st = ctx.write_batch_dev(len(ops["kind"]), dd["text"].data_ptr(), dd["off"].data_ptr(), dd["kind"].data_ptr(), dd["target"].data_ptr(),
+                                     dd["exc"].data_ptr(), dd["flags"].data_ptr())
+            t = ctx.timing()
+            acc["deliv"] += int(st.n_deliveries); acc["bytes"] += int(st.total_bytes); acc["fan_ms"] += float(t.fanout_ms)
+            acc["fan_b"] += int(t.fanout_bytes_in) + int(t.fanout_bytes_out); acc["n"] += 1; acc["launches"] += int(t.launches)
+        for _ in range(args.warmup):
+            step()
+        for k in acc:
+            acc[k] = 0 if not isinstance(acc[k], float) else 0.0
+        tw0 = time.perf_counter()
+        ms = timed(step, args.steps, 0)
+        tw1 = time.perf_counter()
+        in_bytes = int(ops["text"].nbytes + ops["off"].nbytes + 10 * len(ops["kind"]))
+        # host buffers: streams (the full per-recipient bytes) and gather lists
+        hops = {k: v for k, v in ops.items()}
+        e2e = {}
+        for mode in ("streams", "iov"):
+            fn = ctx.write_batch if mode == "streams" else ctx.write_batch_iov
+            fn(hops); barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                r = fn(hops)
+            torch.cuda.synchronize()
+            e2e[mode] = (time.perf_counter() - t0) / 2
+        d_per = acc["deliv"] / acc["n"]
+        ach = acc["fan_b"] / acc["n"] / (acc["fan_ms"] / acc["n"] * 1e-3) / 1e9
+        line = dict(metric=METRIC, value=acc["deliv"] / (ms * 1e-3), unit=UNIT, n_gpus=1, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
+                    config=dict(workload="C2: %d say() lines x %d users in ONE room, colour expand/strip only (no swear gate), 1 B200" % (M, U),
+                                l2="outputs (%.1f GB) per step exceed the 126 MB L2" % (acc["bytes"] / acc["n"] / 1e9), source_msgs_per_s=M * args.steps / (ms * 1e-3)),
+                    roofline=dict(bound="hbm", kernel="k_fanout", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+                                  whole_step=dict(achieved=(acc["bytes"] / acc["n"] + in_bytes) / (ms / args.steps * 1e-3) / 1e9, unit="GB/s",
+                                                  frac=(acc["bytes"] / acc["n"] + in_bytes) / (ms / args.steps * 1e-3) / 1e9 / peak)),
+                    e2e=dict(value=d_per / e2e["streams"], unit=UNIT, h2d_bytes_per_step=in_bytes, d2h_bytes_per_step=int(acc["bytes"] / acc["n"]), ms_per_step=1e3 * e2e["streams"]),
+                    e2e_iov=dict(value=d_per / e2e["iov"], unit=UNIT, ms_per_step=1e3 * e2e["iov"]),
+                    gpu_launches=acc["launches"])
+        ctx.close()
+    elif cfg == "c4":
+        NQ, NE = 100_000, 10_000
+        st_, so_ = synth.sites(NQ); nt_, no_ = synth.names(NQ)
+        ctx = api.Context(local); ctx.set_stream(stream.cuda_stream)
+        dd = dict(st=to_dev(pad16(st_)), so=to_dev(so_.view(np.int64)), nt=to_dev(pad16(nt_)), no=to_dev(no_.view(np.int64)),
+                  vs=torch.zeros(NQ, dtype=torch.uint8, device=dev), vu=torch.zeros(NQ, dtype=torch.uint8, device=dev))
+        res = {}
+        for nl in (True, False):                                 # the file with and without its last newline (the feof quirk)
+            sf, uf = synth.ban_file(0, NE, NQ, NQ, nl), synth.ban_file(1, NE, NQ, NQ, nl)
+            ctx.set_ban_files(sf, uf)
+
+            def step():
+                ctx.verdicts_dev("site_banned", NQ, dd["st"].data_ptr(), dd["so"].data_ptr(), dd["vs"].data_ptr())
+                ctx.verdicts_dev("user_banned", NQ, dd["nt"].data_ptr(), dd["no"].data_ptr(), dd["vu"].data_ptr())
+            tw0 = time.perf_counter()
+            res[nl] = timed(step, args.steps, args.warmup)
+            tw1 = time.perf_counter()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ctx.site_banned_batch(st_, so_); ctx.user_banned_batch(nt_, no_)
+            res[(nl, "e2e")] = (time.perf_counter() - t0) / 3
+        ms = res[True]
+        algo = int(st_.nbytes + nt_.nbytes + 2 * NQ + len(sf) + len(uf))
+        line = dict(metric="ban verdicts/sec (site_banned + user_banned)", value=2 * NQ * args.steps / (ms * 1e-3), unit="queries/s", n_gpus=1, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
+                    config=dict(workload="C4: %d sites + %d names vs %d-entry siteban / userban files" % (NQ, NQ, NE),
+                                without_trailing_newline_ms_per_step=res[False] / args.steps,
+                                l2="queries (3 MB) and tables live in L2 / shared memory: latency-bound, not HBM-bound (SURVEY 8d)"),
+                    roofline=dict(bound="hbm", kernel="k_ac_match<0> + k_set_match", achieved=algo / (ms / args.steps * 1e-3) / 1e9, peak=peak, unit="GB/s",
+                                  frac=algo / (ms / args.steps * 1e-3) / 1e9 / peak, traffic=None, peak_source=peak_src,
+                                  note="working set in L2: the HBM floor is microseconds; reported for completeness"),
+                    e2e=dict(value=2 * NQ / res[(True, "e2e")], unit="queries/s", h2d_bytes_per_step=int(st_.nbytes + so_.nbytes + nt_.nbytes + no_.nbytes),
+                             d2h_bytes_per_step=2 * NQ, ms_per_step=1e3 * res[(True, "e2e")]),
+                    gpu_launches=2 * args.steps)
+        ctx.close()
+    else:                                                        # c5
+        UT, UPR, MT = args.c5_users, 100, args.c5_msgs
+        CH = min(1_000_000, MT)
+        n_chunks = (MT + CH - 1) // CH
+        users, n_rooms = synth.users(UT, UPR)
+        m = api.MultiContext(rank=(world, rank, local))
+        m.set_profiling(True)
+        m.set_swear_words(words)
+        sfile, ufile = synth.ban_file(0, N_BAN_ENTRIES, UT, UT, True), synth.ban_file(1, N_BAN_ENTRIES, UT, UT, True)
+        m.set_ban_files(sfile, ufile)
+        ctx = m.ctx(rank)
+        ctx.set_stream(stream.cuda_stream)
+        # stage A, admission (site_banned or user_banned => never a recipient, never a speaker): split by rank, gathered
+        st_, so_ = synth.sites(UT); nt_, no_ = synth.names(UT)
+        lo, hi = rank * UT // world, (rank + 1) * UT // world
+        dA = dict(st=to_dev(pad16(st_)), so=to_dev(so_.view(np.int64)), nt=to_dev(pad16(nt_)), no=to_dev(no_.view(np.int64)),
+                  vs=torch.zeros(UT, dtype=torch.uint8, device=dev), vu=torch.zeros(UT, dtype=torch.uint8, device=dev))
+
+        def admission():
+            ctx.verdicts_dev("site_banned", hi - lo, dA["st"].data_ptr(), dA["so"].data_ptr() + 8 * lo, dA["vs"].data_ptr() + lo)
+            ctx.verdicts_dev("user_banned", hi - lo, dA["nt"].data_ptr(), dA["no"].data_ptr() + 8 * lo, dA["vu"].data_ptr() + lo)
+        admission(); torch.cuda.synchronize()
+        banned = (dA["vs"] | dA["vu"])
+        if world > 1:
+            parts = [torch.zeros_like(banned) for _ in range(world)]
+            dist.all_gather(parts, banned)                         # (gathering outputs: the only cross-rank traffic)
+            banned = torch.zeros_like(banned)
+            for r in range(world):
+                a, b = r * UT // world, (r + 1) * UT // world
+                banned[a:b] = parts[r][a:b]
+        banned = banned.cpu().numpy().astype(bool)
+        uf2, ur2 = users["flags"].copy(), users["room"].copy()
+        uf2[banned] |= api.UF_LOGIN; ur2[banned] = -1
+        m.set_users(ur2, uf2, users["level"], n_rooms)
+        _, ush, _ = m.plan()
+        # stage B + C inputs, chunk by chunk: every rank generates the same global chunk, the library routes it, the
+        # rank's share goes to its HBM (resident before anything is timed)
+        chunks = []
+        for c in range(n_chunks):
+            m0, n = c * CH, min(CH, MT - c * CH)
+            bt, bo = synth.bodies(n, words, m0=m0)
+            ops, spk, rm = synth.say_ops(n, UT, UPR, bt, bo, gated=True, m0=m0)
+            dead = np.repeat(banned[spk], 3)
+            ops["kind"] = np.where(dead, np.uint8(3), ops["kind"]).astype(np.uint8)      # a banned speaker says nothing (NUTSB_OP_NONE)
+            r = m.route(dict(ops, verdict=np.zeros(n, np.uint8)), rank)
+            b_lo, b_hi = rank * n // world, (rank + 1) * n // world
+            chunks.append(dict(n=n, n_ops=len(r["kind"]), bt=to_dev(pad16(bt)), bo=to_dev(bo.view(np.int64)), b_lo=b_lo, b_hi=b_hi,
+                               text=to_dev(pad16(r["text"])), off=to_dev(r["off"].view(np.int64)), kind=to_dev(r["kind"]), target=to_dev(r["target"]),
+                               exc=to_dev(r["except_user"]), flags=to_dev(r["flags"]), gate=to_dev(r["gate"]),
+                               verdict=torch.zeros(n, dtype=torch.uint8, device=dev),
+                               parts=[torch.zeros(n, dtype=torch.uint8, device=dev) for _ in range(world)] if world > 1 else None))
+        acc = dict(deliv=0, bytes=0, launches=0, fan_ms=0.0, fan_b=0, n=0)
+        digests = [None]
+
+        def job(with_digests=False):
+            admission()
+            dg = None
+            for ck in chunks:
+                # swear verdicts: this rank's index range, then gathered (1 byte per message)
+                ctx.verdicts_dev("contains_swearing", ck["b_hi"] - ck["b_lo"], ck["bt"].data_ptr(), ck["bo"].data_ptr() + 8 * ck["b_lo"],
+                                 ck["verdict"].data_ptr() + ck["b_lo"])
+                if world > 1:
+                    with torch.cuda.stream(stream):
+                        dist.all_gather(ck["parts"], ck["verdict"])
+                        for r in range(world):
+                            a, b = r * ck["n"] // world, (r + 1) * ck["n"] // world
+                            ck["verdict"][a:b] = ck["parts"][r][a:b]
+                st = ctx.write_batch_dev(ck["n_ops"], ck["text"].data_ptr(), ck["off"].data_ptr(), ck["kind"].data_ptr(), ck["target"].data_ptr(),
+                                         ck["exc"].data_ptr(), ck["flags"].data_ptr(), ck["gate"].data_ptr(), ck["verdict"].data_ptr())
+                t = ctx.timing()
+                acc["deliv"] += int(st.n_deliveries); acc["bytes"] += int(st.total_bytes); acc["launches"] += int(t.launches) + 1
+                acc["fan_ms"] += float(t.fanout_ms); acc["fan_b"] += int(t.fanout_bytes_in) + int(t.fanout_bytes_out); acc["n"] += 1
+                if with_digests:
+                    dg = m.stream_digests(dg)
+            if with_digests:
+                digests[0] = dg
+        job(with_digests=True)                                   # warm-up no. 1, with the per-user digests of the whole job
+        for _ in range(max(0, args.warmup - 1)):
+            job()
+        for k in acc:
+            acc[k] = 0 if not isinstance(acc[k], float) else 0.0
+        tw0 = time.perf_counter()
+        ms = timed(job, args.steps, 0)
+        tw1 = time.perf_counter()
+        mine = ush == rank
+        # a checksum of the per-user digests: the same number whatever the GPU count means the same streams
+        chk = np.bitwise_xor.reduce(digests[0][mine]) if mine.any() else np.uint64(0)
+        sm = torch.tensor([float(acc["deliv"]), float(acc["bytes"]), float(acc["launches"])], dtype=torch.float64, device=dev)
+        cx = torch.tensor([np.int64(np.uint64(chk).astype(np.int64))], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            cxs = [torch.zeros_like(cx) for _ in range(world)]
+            dist.all_gather(cxs, cx)
+            allx = np.bitwise_xor.reduce(np.array([int(t[0]) for t in cxs], np.int64).astype(np.uint64))
+        else:
+            allx = np.uint64(chk)
+        ach = acc["fan_b"] / max(1, acc["n"]) / (acc["fan_ms"] / max(1, acc["n"]) * 1e-3) / 1e9 if acc["fan_ms"] > 0 else 0.0
+        in_bytes = sum(int(v.numel() * v.element_size()) for ck in chunks for k, v in ck.items() if isinstance(v, torch.Tensor) and k != "verdict")
+        line = dict(metric=METRIC, value=float(sm[0]) / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="u8", data="synthetic",
+                    config=dict(workload="C5: full pipeline, %d msgs x %d users (%d rooms of %d): admission (site_banned | user_banned, %d-entry lists) -> "
+                                         "contains_swearing (%d words) -> say() render + fan-out, in %d message-ordered chunks; one step = the whole job"
+                                         % (MT, UT, n_rooms, UPR, N_BAN_ENTRIES, N_SWEAR, n_chunks),
+                                sharding="rooms dealt to the GPUs by nutsb_multi (the library's sharder), streams stay in HBM; swear / ban batches split by "
+                                         "index range and their verdict bytes gathered (NCCL all_gather: the only cross-rank traffic)",
+                                l2="per chunk and GPU: inputs and outputs far beyond the 126 MB L2",
+                                banned_users=int(banned.sum()), deliveries_per_job=float(sm[0]) / args.steps, stream_bytes_per_job=float(sm[1]) / args.steps,
+                                digest_checksum="%016x" % int(allx), source_msgs_per_s=MT * args.steps / (ms * 1e-3)),
+                    roofline=dict(bound="hbm", kernel="k_fanout", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+                                  whole_step=dict(achieved=(float(sm[1]) / args.steps / world + in_bytes) / (ms / args.steps * 1e-3) / 1e9, unit="GB/s per GPU",
+                                                  frac=(float(sm[1]) / args.steps / world + in_bytes) / (ms / args.steps * 1e-3) / 1e9 / peak)),
+                    e2e=None, gpu_launches=int(sm[2]))
+        m.close()
+    clocks.window(tw0, tw1)
+    clk = clocks.stop()
+    if rank == 0:
+        line["clocks"] = clk
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
@@ -605,9 +969,15 @@ def main():
     ap.add_argument("--in-flight", type=int, default=IN_FLIGHT, help="batches in flight per GPU (one context + host thread each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--config", default="c3c4", choices=["c3c4", "c2", "c4", "c5"],
+                    help="c3c4 (default): the headline workload; c2 / c4 / c5: the other BASELINE configs, one line each")
+    ap.add_argument("--c5-msgs", type=int, default=10_000_000)
+    ap.add_argument("--c5-users", type=int, default=100_000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config != "c3c4":
+        return run_config(args)
     return run_ours(args)
 
 
