@@ -166,3 +166,63 @@ k_scan_apply(In in, Out out, i64 n_host, const u32 *n_dev, const u64 *block_sums
     u64 ex = nutsb_block_excl_scan(s, &total) + before;
     for (int k = 0; k < NUTSB_SCAN_ITEMS; ++k) { i64 i = base + k; if (i <= n) out(i, ex); ex += v[k]; }   // out(n) = total
 }
+
+// ---- the same scan in ONE kernel: decoupled look-back ------------------------------------------
+// Every block takes the next tile (a ticket, so that tiles are started in order), scans it, publishes
+// its aggregate, adds up the aggregates / inclusive prefixes of the tiles before it as they appear and
+// writes the tile's exclusive prefixes: the input is read once and there is one launch instead of two
+// or three.  The per-tile state lives in a context buffer that is never cleared: a state word carries
+// the epoch of the scan it belongs to (`epoch`, bumped by the host per scan), and the block that
+// finishes last resets the ticket.  state[t] = { flag (epoch << 2 | 1 aggregate, | 2 inclusive), aggregate, inclusive }.
+// (the aggregate and the inclusive prefix have a word each: a reader that has seen "aggregate" must still find the
+// aggregate there when the writer has moved on to "inclusive")
+struct ScanState { unsigned long long flag, aggregate, inclusive, pad_; };
+
+template <class In, class Out>
+__global__ void __launch_bounds__(NUTSB_SCAN_THREADS)
+k_scan1(In in, Out out, i64 n_host, const u32 *n_dev, ScanState *state, u32 *ticket, u32 epoch, u32 nb)
+{
+    __shared__ u32 s_tile;
+    __shared__ u64 s_before;
+    const i64 n = n_dev ? (i64)*n_dev : n_host;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const i64 base = (i64)tile * NUTSB_SCAN_TILE + (i64)threadIdx.x * NUTSB_SCAN_ITEMS;
+    u64 v[NUTSB_SCAN_ITEMS], s = 0;
+    for (int k = 0; k < NUTSB_SCAN_ITEMS; ++k) { const i64 i = base + k; v[k] = i < n ? in(i) : 0; s += v[k]; }
+    u64 total;
+    u64 ex = nutsb_block_excl_scan(s, &total);
+    if (threadIdx.x < 32) {
+        // look-back by the block's first warp, 32 tiles at a time: lane l looks at tile (hi - 1 - l); the window's sum is
+        // everything up to and including the nearest tile that already knows its inclusive prefix
+        const unsigned long long fa = ((unsigned long long)epoch << 2) | 1ull, fi = ((unsigned long long)epoch << 2) | 2ull;
+        volatile ScanState *st = state;
+        const int lane = (int)threadIdx.x;
+        u64 before = 0;
+        if (tile > 0) {
+            if (lane == 0) { st[tile].aggregate = total; __threadfence(); st[tile].flag = fa; }   // my aggregate, for the tiles after me
+            for (u32 hi = tile; hi > 0; ) {
+                const bool have = (u32)lane < hi;
+                const u32 t = have ? hi - 1 - (u32)lane : 0;
+                unsigned long long f = fi;
+                if (have) do { f = st[t].flag; } while (f != fa && f != fi);              // (tiles before me were started before me)
+                __threadfence();
+                const u32 incl = __ballot_sync(NUTSB_FULL, have && f == fi);
+                const int stop = incl ? __ffs((int)incl) - 1 : 31;                          // nearest inclusive tile in the window
+                u64 v = (have && lane <= stop) ? (f == fi ? st[t].inclusive : st[t].aggregate) : 0;
+                for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(NUTSB_FULL, v, d);
+                before += v;
+                if (incl) break;
+                hi = hi > 32 ? hi - 32 : 0;
+            }
+        }
+        if (lane == 0) { st[tile].inclusive = before + total; __threadfence(); st[tile].flag = fi; s_before = before; }
+    }
+    __syncthreads();
+    ex += s_before;
+    for (int k = 0; k < NUTSB_SCAN_ITEMS; ++k) { const i64 i = base + k; if (i <= n) out(i, ex); ex += v[k]; }   // out(n) = total
+    // the last block to get here puts the ticket back for the next scan
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); if (atomicAdd(ticket + 1, 1u) == nb - 1) { ticket[0] = 0; ticket[1] = 0; } }
+}

@@ -236,8 +236,8 @@ k_expand(OpsView ops, PopView pop, const u32 *nrep, const u64 *eoff, u32 *e_room
     }
 }
 
-// ---- stable LSD radix sort of (key,val) pairs, 11-bit digits ------------------------
-#define NUTSB_RS_BITS    11
+// ---- stable LSD radix sort of (key,val) pairs, digits of up to 8 bits ------------------------
+#define NUTSB_RS_BITS    8                         // digit width: 8 warps x 256 counters of shared memory in the scatter
 #define NUTSB_RS_DIGITS  (1 << NUTSB_RS_BITS)
 #define NUTSB_RS_THREADS 256
 #define NUTSB_RS_ROUNDS  16
@@ -263,46 +263,56 @@ k_rs_hist(const u32 *keys, i64 n_host, const u32 *n_dev, int shift, u32 bits, u3
 }
 
 // offs = exclusive scan of hist (same layout).  vals_in == nullptr means iota.
+// Stable: a warp owns a contiguous piece of the block's chunk (NUTSB_RS_ROUNDS x 32 keys) and counts digits into
+// its OWN row of shared-memory counters (match_any ranking inside a round), so the rounds need no barrier between
+// the warps; one pass over the rows then turns the counts into each warp's first output slot per digit.
 __global__ void __launch_bounds__(NUTSB_RS_THREADS)
 k_rs_scatter(const u32 *keys_in, const u32 *vals_in, i64 n_host, const u32 *n_dev, int shift, u32 bits,
              const u64 *offs, u32 nblocks, u32 *keys_out, u32 *vals_out)
 {
     const i64 n = n_dev ? (i64)*n_dev : n_host;
     const u32 digits = 1u << bits;
-    __shared__ u32 s_run[NUTSB_RS_DIGITS];
-    for (u32 d = threadIdx.x; d < digits; d += blockDim.x)
-        s_run[d] = (u32)offs[(size_t)d * nblocks + blockIdx.x];
-    __syncthreads();
+    __shared__ u32 s_cnt[NUTSB_RS_THREADS / 32][NUTSB_RS_DIGITS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const i64 base = (i64)blockIdx.x * NUTSB_RS_CHUNK;
+    for (u32 i = threadIdx.x; i < (NUTSB_RS_THREADS / 32) * NUTSB_RS_DIGITS; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const i64 base = (i64)blockIdx.x * NUTSB_RS_CHUNK + (i64)warp * (NUTSB_RS_ROUNDS * 32);
+    u32 rk[NUTSB_RS_ROUNDS];                               // rank of the key among the warp's keys of the same digit
+#pragma unroll
     for (int r = 0; r < NUTSB_RS_ROUNDS; ++r) {
-        const i64 i = base + r * NUTSB_RS_THREADS + threadIdx.x;
+        const i64 i = base + r * 32 + lane;
         const bool valid = i < n;
-        const u32 key = valid ? keys_in[i] : 0;
-        const u32 d = valid ? ((key >> shift) & (digits - 1)) : 0xffffffffu;
+        const u32 d = valid ? ((keys_in[i] >> shift) & (digits - 1)) : 0xffffffffu;
         const u32 grp = __match_any_sync(NUTSB_FULL, d);
         const int leader = __ffs((int)grp) - 1;
-        const u32 rank = (u32)__popc(grp & ((1u << lane) - 1));
-        u32 gbase = 0;
-        // warps take turns so that equal digits keep their input order
-        for (int w = 0; w < NUTSB_RS_THREADS / 32; ++w) {
-            if (warp == w && valid && lane == leader) { gbase = s_run[d]; s_run[d] = gbase + (u32)__popc(grp); }
-            __syncthreads();
-        }
-        gbase = __shfl_sync(NUTSB_FULL, gbase, leader);
-        if (valid) {
-            keys_out[gbase + rank] = key;
-            vals_out[gbase + rank] = vals_in ? vals_in[i] : (u32)i;
+        u32 first = 0;
+        if (valid && lane == leader) { first = s_cnt[warp][d]; s_cnt[warp][d] = first + (u32)__popc(grp); }
+        first = __shfl_sync(NUTSB_FULL, first, leader);
+        rk[r] = first + (u32)__popc(grp & ((1u << lane) - 1));
+        __syncwarp();
+    }
+    __syncthreads();
+    for (u32 d = threadIdx.x; d < digits; d += blockDim.x) {   // counts -> first slots: the block's base, then warp after warp
+        u32 run = (u32)offs[(size_t)d * nblocks + blockIdx.x];
+        for (int w = 0; w < NUTSB_RS_THREADS / 32; ++w) { const u32 t = s_cnt[w][d]; s_cnt[w][d] = run; run += t; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < NUTSB_RS_ROUNDS; ++r) {
+        const i64 i = base + r * 32 + lane;
+        if (i < n) {
+            const u32 key = keys_in[i];
+            const u32 dst = s_cnt[warp][(key >> shift) & (digits - 1)] + rk[r];
+            keys_out[dst] = key;
+            vals_out[dst] = vals_in ? vals_in[i] : (u32)i;
         }
     }
 }
 
-// seg_off[k] = first index i with keys[i] >= k, for k in [0, nkeys]; keys sorted.
-__global__ void __launch_bounds__(256)
-k_seg_bounds(const u32 *keys, i64 n_host, const u32 *n_dev, u32 nkeys, u32 *seg_off)
+// seg_off[k] = first index i with keys[i] >= k, for k in [0, nkeys]; keys sorted.  Thread i in [0, n] writes the
+// entries between its left neighbour's key and its own (folded into the kernels that walk the sorted keys anyway).
+__device__ __forceinline__ void nutsb_seg_bounds(const u32 *keys, i64 n, i64 i, u32 nkeys, u32 *seg_off)
 {
-    const i64 n = n_dev ? (i64)*n_dev : n_host;
-    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i > n) return;
     const i64 lo = (i == 0) ? 0 : (i64)keys[i - 1] + 1;
     const i64 hi = (i == n) ? (i64)nkeys : (i64)keys[i];
@@ -326,9 +336,10 @@ struct EntryArrays {
 };
 
 __global__ void __launch_bounds__(256)
-k_entry_info(OpsView ops, PopView pop, EntryArrays ea, i64 n_ent, const u32 *len_on, const u32 *len_off)
+k_entry_info(OpsView ops, PopView pop, EntryArrays ea, i64 n_ent, const u32 *len_on, const u32 *len_off, u32 *room_ent_off)
 {
     const i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    nutsb_seg_bounds(ea.e_room, n_ent, e, (u32)pop.n_rooms_tot, room_ent_off);     // room_ent_off[r] = first entry of room r
     if (e >= n_ent) return;
     const u32 op = ea.e_op[e], room = ea.e_room[e];
     const u32 kind = ops.kind[op];
@@ -409,11 +420,13 @@ k_entry_scatter(EntryScatter s, i64 n_ent)
     }
 }
 
-// room_b_off[r] = slab rank of room r's first entry, r in [0, Rt]
+// room_b_off[r] = slab rank of room r's first entry, r in [0, Rt]; counts[0] = slab ops, counts[1] = events (the
+// packed entry scan's total)
 __global__ void __launch_bounds__(256)
-k_room_b_off(const u32 *room_ent_off, const u64 *e_scan, u32 n_rooms_tot, u32 *room_b_off)
+k_room_b_off(const u32 *room_ent_off, const u64 *e_scan, i64 n_ent, u32 n_rooms_tot, u32 *room_b_off, u32 *counts)
 {
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) { const u64 t = e_scan[n_ent]; counts[0] = (u32)t; counts[1] = (u32)(t >> 32); }
     if (r > n_rooms_tot) return;
     room_b_off[r] = (u32)e_scan[room_ent_off[r]];
 }
@@ -421,10 +434,11 @@ k_room_b_off(const u32 *room_ent_off, const u64 *e_scan, u32 n_rooms_tot, u32 *r
 // gather the sorted event arrays through the sort permutation
 __global__ void __launch_bounds__(256)
 k_ev_gather(const u32 *perm, const u32 *n_dev, const u32 *ev_ukey, const i32 *ev_delta, const u32 *ev_op,
-            u32 *sv_ukey, i32 *sv_delta, u32 *sv_op)
+            u32 *sv_ukey, i32 *sv_delta, u32 *sv_op, const u32 *sv_slot, u32 n_users, u32 *ev_off)
 {
     const i64 n_ev = (i64)*n_dev;
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    nutsb_seg_bounds(sv_slot, n_ev, i, n_users, ev_off);                           // ev_off[s] = first event of slot s
     if (i >= n_ev) return;
     const u32 p = perm[i];
     sv_ukey[i] = ev_ukey[p]; sv_delta[i] = ev_delta[p]; sv_op[i] = ev_op[p];
@@ -462,12 +476,6 @@ struct UserLenIn {
     }
 };
 
-__global__ void __launch_bounds__(128)
-k_user_len(UserLenIn in, i64 n, u64 *len)
-{
-    const i64 u = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < n) len[u] = in(u);
-}
 
 // ---- F. copy plan ---------------------------------------------------------------------------
 // A room's slab ops are cut into tiles of NUTSB_TILE_OPS; a cell is one (tile,
@@ -1330,12 +1338,6 @@ k_readback1(const u64 *eoff_end, const u32 *status, const u64 *slab_tot, u64 *h_
     const u32 t = threadIdx.x;
     if (t == 0) { *h_entries = *eoff_end; *h_status = *status; }
     if (t < 2 * NUTSB_SLAB_TOT_WAYS) h_slab_tot[t] = slab_tot[t];
-}
-
-// counts[0] = slab ops, counts[1] = events (from the packed entry scan's total)
-__global__ void k_counts(const u64 *e_scan, i64 n_ent, u32 *counts)
-{
-    if (blockIdx.x == 0 && threadIdx.x == 0) { const u64 t = e_scan[n_ent]; counts[0] = (u32)t; counts[1] = (u32)(t >> 32); }
 }
 
 struct Sizes {                   // read back by the host before the fan-out is launched

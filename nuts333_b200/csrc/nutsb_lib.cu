@@ -78,7 +78,8 @@ struct nutsb_ctx {
     ClassSet cls[2];                 // [0] keyed without level, [1] with level
 
     // per-batch scratch
-    DBuf d_status, d_len_on, d_len_off, d_nrep, d_eoff, d_sums;
+    DBuf d_status, d_len_on, d_len_off, d_nrep, d_eoff, d_sums, d_scan_ticket;
+    void *scan_state_seen = nullptr; size_t scan_state_cap = 0; u32 scan_epoch = 0;      // k_scan1's per-tile state: flags carry the scan's epoch
     DBuf d_ek[2], d_ev_[2];          // (room, op) entries, ping-pong
     DBuf d_hist, d_hoffs;
     DBuf d_room_ent_off, d_e_info, d_e_delta, d_e_slot, d_e_scan, d_counts, d_room_b_off;
@@ -191,20 +192,21 @@ struct InClassLen {                 // bytes class column j receives from slab o
     }
 };
 
-// Exclusive scan of in(0..n) into out(0..n) (out(n) = total).  n = *n_dev when given.
+// Exclusive scan of in(0..n) into out(0..n) (out(n) = total).  n = *n_dev when given.  One launch (k_scan1).
 template <class In, class Out>
 static int run_scan(nutsb_ctx *c, In in, Out out, i64 n_upper, const u32 *n_dev)
 {
     const u32 nb = cdiv((u64)n_upper + 1, NUTSB_SCAN_TILE);
-    TRY(ensure(c, c->d_sums, ((size_t)nb + 1) * sizeof(u64)));
-    u64 *sums = c->d_sums.as<u64>();
-    auto kr = k_scan_reduce<In>;
-    auto ka = k_scan_apply<In, Out>;
-    const int fused = nb <= 1024 ? 1 : 0;
-    NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, kr, in, n_upper, n_dev, sums); CKL();
-    if (!fused) { NUTSB_LAUNCH(1, NUTSB_SCAN_THREADS, c->stream, k_scan_sums, sums, (i64)nb); CKL(); }
-    NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, ka, in, out, n_upper, n_dev, sums, fused); CKL();
-    c->tm.launches += fused ? 2 : 3;
+    TRY(ensure(c, c->d_sums, ((size_t)nb + 1) * sizeof(ScanState)));
+    if (!c->d_scan_ticket.p) { TRY(ensure(c, c->d_scan_ticket, 64)); CK(cudaMemsetAsync(c->d_scan_ticket.p, 0, 64, c->stream)); }
+    if (c->d_sums.p != c->scan_state_seen || c->d_sums.cap != c->scan_state_cap) {     // a fresh (re)allocation: whatever it holds must not look like a flag
+        CK(cudaMemsetAsync(c->d_sums.p, 0, c->d_sums.cap, c->stream));
+        c->scan_state_seen = c->d_sums.p; c->scan_state_cap = c->d_sums.cap;
+    }
+    if (++c->scan_epoch >= 0x3fffffffu) { c->scan_epoch = 1; CK(cudaMemsetAsync(c->d_sums.p, 0, c->d_sums.cap, c->stream)); }
+    auto k1 = k_scan1<In, Out>;
+    NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, k1, in, out, n_upper, n_dev, c->d_sums.as<ScanState>(), c->d_scan_ticket.as<u32>(), c->scan_epoch, nb); CKL();
+    c->tm.launches += 1;
     return NUTSB_OK;
 }
 
@@ -378,7 +380,7 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
         &c->d_user_room, &c->d_user_slot, &c->d_slot_user, &c->d_room_slot_off, &c->d_slot_cf, &c->d_slot_lv,
         &c->cls[0].d_user_cls, &c->cls[0].d_room_cls_off, &c->cls[0].d_cls_flags, &c->cls[0].d_cls_level,
         &c->cls[1].d_user_cls, &c->cls[1].d_room_cls_off, &c->cls[1].d_cls_flags, &c->cls[1].d_cls_level,
-        &c->d_status, &c->d_len_on, &c->d_len_off, &c->d_nrep, &c->d_eoff, &c->d_sums, &c->d_ek[0], &c->d_ek[1],
+        &c->d_status, &c->d_len_on, &c->d_len_off, &c->d_nrep, &c->d_eoff, &c->d_sums, &c->d_scan_ticket, &c->d_ek[0], &c->d_ek[1],
         &c->d_ev_[0], &c->d_ev_[1], &c->d_hist, &c->d_hoffs, &c->d_room_ent_off, &c->d_e_info, &c->d_e_delta,
         &c->d_e_slot, &c->d_e_scan, &c->d_counts, &c->d_room_b_off, &c->d_bl_op, &c->d_bl_room, &c->d_evk[0],
         &c->d_evk[1], &c->d_evv[0], &c->d_evv[1], &c->d_ev_ukey, &c->d_ev_delta, &c->d_ev_op, &c->d_sv_ukey,
@@ -795,18 +797,16 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
         e_room = c->d_ek[cur].as<u32>(); e_op = c->d_ev_[cur].as<u32>();
     }
     TRY(ensure(c, c->d_room_ent_off, ((size_t)Rt + 2) * 4));
-    NUTSB_LAUNCH(cdiv(E + 1, 256), 256, st, k_seg_bounds, e_room, (i64)E, (const u32 *)nullptr, (u32)Rt, c->d_room_ent_off.as<u32>()); CKL();
 
     // -- C. classify entries, scatter the slab list and the event list
     TRY(ensure(c, c->d_e_info, E)); TRY(ensure(c, c->d_e_delta, E * 4)); TRY(ensure(c, c->d_e_slot, E * 4));
     TRY(ensure(c, c->d_e_scan, (E + 1) * 8));
     EntryArrays ea{ e_room, e_op, c->d_e_info.as<u8>(), c->d_e_delta.as<i32>(), c->d_e_slot.as<u32>() };
-    NUTSB_LAUNCH(cdiv(E, 256), 256, st, k_entry_info, ops, pop, ea, (i64)E, len_on, len_off); CKL();
+    NUTSB_LAUNCH(cdiv(E + 1, 256), 256, st, k_entry_info, ops, pop, ea, (i64)E, len_on, len_off, c->d_room_ent_off.as<u32>()); CKL();
     TRY(run_scan(c, InEntryPacked{c->d_e_info.as<u8>()}, OutU64{c->d_e_scan.as<u64>()}, (i64)E, nullptr));
     u32 *counts = c->d_counts.as<u32>();
-    NUTSB_LAUNCH(1, 32, st, k_counts, c->d_e_scan.as<u64>(), (i64)E, counts); CKL();
     TRY(ensure(c, c->d_room_b_off, ((size_t)Rt + 2) * 4));
-    NUTSB_LAUNCH(cdiv((u64)Rt + 1, 256), 256, st, k_room_b_off, c->d_room_ent_off.as<u32>(), c->d_e_scan.as<u64>(), (u32)Rt, c->d_room_b_off.as<u32>()); CKL();
+    NUTSB_LAUNCH(cdiv((u64)Rt + 1, 256), 256, st, k_room_b_off, c->d_room_ent_off.as<u32>(), c->d_e_scan.as<u64>(), (i64)E, (u32)Rt, c->d_room_b_off.as<u32>(), counts); CKL();
     TRY(ensure(c, c->d_bl_op, E * 4 + 16)); TRY(ensure(c, c->d_bl_room, E * 4 + 16)); TRY(ensure(c, c->d_bl_meta, E * 4 + 16));
     for (int q = 0; q < 2; ++q) { TRY(ensure(c, c->d_evk[q], E * 4 + 16)); TRY(ensure(c, c->d_evv[q], E * 4 + 16)); }
     TRY(ensure(c, c->d_ev_ukey, E * 4)); TRY(ensure(c, c->d_ev_delta, E * 4)); TRY(ensure(c, c->d_ev_op, E * 4));
@@ -814,7 +814,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
                      c->d_room_ent_off.as<u32>(), c->d_e_scan.as<u64>(), c->d_bl_op.as<u32>(), c->d_bl_room.as<u32>(),
                      c->d_bl_meta.as<u32>(), ops, c->d_evk[0].as<u32>(), c->d_ev_ukey.as<u32>(), c->d_ev_op.as<u32>(), c->d_ev_delta.as<i32>() };
     NUTSB_LAUNCH(cdiv(E, 256), 256, st, k_entry_scatter, es, (i64)E); CKL();
-    c->tm.launches += 5;
+    c->tm.launches += 3;
 
     // -- slab prefixes (per colour) and, when classes differ in what they take, per class column
     TRY(ensure(c, c->d_vp_on, (E + 2) * 8)); TRY(ensure(c, c->d_vp_off, (E + 2) * 8));
@@ -865,17 +865,14 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
     TRY(radix_sort(c, c->d_evk, c->d_evv, (i64)E, counts + 1, bits_for((u64)std::max(U, 1)), &sv_slot, &perm));
     TRY(ensure(c, c->d_sv_ukey, E * 4 + 16)); TRY(ensure(c, c->d_sv_delta, E * 4 + 16)); TRY(ensure(c, c->d_sv_op, E * 4 + 16));
     TRY(ensure(c, c->d_sv_pre, (E + 2) * 8)); TRY(ensure(c, c->d_ev_off, ((size_t)U + 2) * 4));
-    NUTSB_LAUNCH(cdiv(E, 256), 256, st, k_ev_gather, perm, counts + 1, c->d_ev_ukey.as<u32>(), c->d_ev_delta.as<i32>(),
-                 c->d_ev_op.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_delta.as<i32>(), c->d_sv_op.as<u32>()); CKL();
+    NUTSB_LAUNCH(cdiv(E + 1, 256), 256, st, k_ev_gather, perm, counts + 1, c->d_ev_ukey.as<u32>(), c->d_ev_delta.as<i32>(),
+                 c->d_ev_op.as<u32>(), c->d_sv_ukey.as<u32>(), c->d_sv_delta.as<i32>(), c->d_sv_op.as<u32>(), sv_slot, (u32)U, c->d_ev_off.as<u32>()); CKL();
     TRY(run_scan(c, InI32{c->d_sv_delta.as<i32>()}, OutU64{c->d_sv_pre.as<u64>()}, (i64)E, counts + 1));
-    NUTSB_LAUNCH(cdiv(E + 1, 256), 256, st, k_seg_bounds, sv_slot, (i64)E, counts + 1, (u32)U, c->d_ev_off.as<u32>()); CKL();
-    c->tm.launches += 2;
+    c->tm.launches += 1;
 
-    // -- E. stream offsets, geometry
+    // -- E. stream offsets (a scan over the users' stream lengths, each computed as it is read), geometry
     UserLenIn uli{ cpx, pop, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_pre.as<u64>() };
-    TRY(ensure(c, c->d_ulen, ((size_t)U + 1) * 8));
-    if (U > 0) { NUTSB_LAUNCH(cdiv((u64)U, 128), 128, st, k_user_len, uli, (i64)U, c->d_ulen.as<u64>()); CKL(); c->tm.launches++; }
-    TRY(run_scan(c, InU64{c->d_ulen.as<u64>()}, OutU64{c->d_off.as<u64>()}, (i64)U, nullptr));
+    TRY(run_scan(c, uli, OutU64{c->d_off.as<u64>()}, (i64)U, nullptr));
     TRY(ensure(c, c->d_slots, ((size_t)U + 1) * sizeof(SlotInfo)));
     if (U > 0) {
         SlotInfoArgs sa{ pop, cpx, c->d_room_b_off.as<u32>(), c->d_ev_off.as<u32>(), c->d_sv_pre.as<u64>(), c->d_off.as<u64>(), c->d_slots.as<SlotInfo>() };
