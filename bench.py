@@ -546,7 +546,7 @@ def run_ours(args):
 
     # ---- the last leg again with two calls in flight (two contexts, two host threads): one call's H2D and
     #      kernels run under the other's D2H (PCIe is full duplex: scripts/probes/pcie_probe.py)
-    pipe_ms, pipe_deliv = 0.0, 0
+    pipe_ms, pipe_deliv, lib_pipe_ms, lib_pipe3_ms = 0.0, 0, 0.0, 0.0
     if not args.no_e2e:
         c2 = api.Context(local)
         c2.set_swear_words(inp["words"]); c2.set_ban_files(inp["sfile"], inp["ufile"])
@@ -575,13 +575,35 @@ def run_ours(args):
             pipe_ms = (time.perf_counter() - t0) * 1e3
         pipe_deliv = got[0] + got[1]
         c2.close()
+        # the same through the library's own pipe (nutsb_pipe: two contexts and their worker threads inside the
+        # library, one caller thread that submits call k+1 before it waits for call k)
+        lib_pipe = {}
+        for depth in (2, 3):
+            pp = api.Pipe(local, depth)
+            pp.set_swear_words(inp["words"]); pp.set_users(users["room"], users["flags"], users["level"], inp["n_rooms"])
+            pp.set_user_names([un[int(uo[u]):int(uo[u + 1])].tobytes() for u in range(N_USERS)], np.zeros(N_USERS, np.uint8))
+            pp.set_ban_swearing(True)
+            sub = lambda: pp.submit_speech_iov(sp_verb, sp_spk, bt, bo)
+            raw_wait = lambda t: pp.lib.nutsb_pipe_wait(pp._h, t, api.C.byref(api._IovStreams()))
+            for reps in (depth, 3 * e2e_steps):             # first round allocates the contexts' buffers
+                barrier()
+                t0 = time.perf_counter()
+                tk = [sub() for _ in range(min(depth, reps))]      # `depth` calls in flight, then one in for one out
+                for k in range(reps):
+                    assert raw_wait(tk[k]) == 0
+                    if len(tk) < reps:
+                        tk.append(sub())
+                torch.cuda.synchronize()
+                lib_pipe[depth] = (time.perf_counter() - t0) * 1e3 / reps
+            pp.close()
+        lib_pipe_ms, lib_pipe3_ms = lib_pipe[2], lib_pipe[3]
     # ---- reduce over ranks
-    vals = torch.tensor([ms, e2e_ms, leg_v["ms"], leg_p["ms"], two_ms, pipe_ms], dtype=torch.float64, device=dev)
+    vals = torch.tensor([ms, e2e_ms, leg_v["ms"], leg_p["ms"], two_ms, pipe_ms, lib_pipe_ms, lib_pipe3_ms], dtype=torch.float64, device=dev)
     sums = torch.tensor([dev_state["deliv"], e2e_deliv, dev_state["launches"], leg_v["deliv"], pipe_deliv], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max, iov_ms_max, sp_ms_max, two_ms_max, pipe_ms_max = (float(vals[i]) for i in range(6))
+    ms_max, e2e_ms_max, iov_ms_max, sp_ms_max, two_ms_max, pipe_ms_max, lib_pipe_ms_max, lib_pipe3_ms_max = (float(vals[i]) for i in range(8))
     total_deliv, total_e2e_deliv, total_launch, total_iov_deliv = float(sums[0]), float(sums[1]), int(sums[2]), float(sums[3])
 
     if rank == 0:
@@ -656,6 +678,11 @@ def run_ours(args):
             line["e2e_speech_iov"]["two_calls_in_flight"] = dict(
                 value=float(sums[4]) / (pipe_ms_max * 1e-3), ms_per_step=pipe_ms_max / (2 * e2e_steps),
                 note="two contexts / host threads per GPU, %d calls each: one call's H2D and kernels under the other's D2H" % e2e_steps)
+            line["e2e_speech_iov"]["library_pipe"] = dict(
+                value=total_iov_deliv / e2e_steps / (lib_pipe_ms_max * 1e-3), ms_per_call=lib_pipe_ms_max,
+                depth3=dict(value=total_iov_deliv / e2e_steps / (lib_pipe3_ms_max * 1e-3), ms_per_call=lib_pipe3_ms_max),
+                note="nutsb_pipe (depth 2; depth3: three contexts): ONE caller thread keeps `depth` calls in flight; the speech lines only "
+                     "(the step's two ban batches, 0.2 ms, are not part of these calls); the D2H floor of a call is 3.5 ms")
         line["roofline"]["whole_step"]["frac"] = line["roofline"]["whole_step"]["achieved"] / peak
         line["config"]["verdict_kernel_ms"] = dict(comp_ms, how="each verdict kernel alone, CUDA events, best of %d" % KERNEL_TIMING_STEPS)
         if world == 1 and not args.no_cpu_baseline:

@@ -381,6 +381,25 @@ int  nutsb_multi_site_banned_batch(nutsb_multi *m, int64_t n, const uint8_t *byt
 int  nutsb_multi_user_banned_batch(nutsb_multi *m, int64_t n, const uint8_t *bytes, const uint64_t *off, uint8_t *verdict);
 int  nutsb_multi_get_timing(const nutsb_multi *m, int shard, nutsb_timing *out);
 
+/* ---- calls in flight on one device -----------------------------------------------------------------
+ * A host-buffer call is H2D copy -> kernels -> D2H copy; PCIe is full duplex, so with two calls in flight one call's
+ * H2D and kernels run under the other's D2H.  nutsb_pipe holds `depth` contexts on one device with a worker thread
+ * each: submit returns at once, wait returns the call's result (valid until `depth` further submissions; the call's
+ * input buffers must stay valid until it has been waited for).  The setters reach every context. */
+typedef struct nutsb_pipe nutsb_pipe;
+int  nutsb_pipe_create(nutsb_pipe **out, int device, int depth);
+void nutsb_pipe_destroy(nutsb_pipe *p);
+int  nutsb_pipe_depth(const nutsb_pipe *p);
+nutsb_ctx *nutsb_pipe_ctx(nutsb_pipe *p, int lane);
+int  nutsb_pipe_set_swear_words(nutsb_pipe *p, const char *const *words);
+int  nutsb_pipe_set_users(nutsb_pipe *p, int32_t n_users, int32_t n_rooms, const int32_t *room, const uint8_t *flags, const uint8_t *level);
+int  nutsb_pipe_set_user_names(nutsb_pipe *p, int32_t n_users, const uint8_t *names, const uint64_t *off, const uint8_t *speech_flags);
+int  nutsb_pipe_set_ban_swearing(nutsb_pipe *p, int on);
+int  nutsb_pipe_submit_speech_iov(nutsb_pipe *p, int64_t n, const uint8_t *verb, const int32_t *speaker,
+                                  const uint8_t *bodies, const uint64_t *body_off, uint64_t *ticket);
+int  nutsb_pipe_submit_write_iov(nutsb_pipe *p, const nutsb_ops *ops, uint64_t *ticket);
+int  nutsb_pipe_wait(nutsb_pipe *p, uint64_t ticket, nutsb_iov_streams *out);
+
 /* ---- queue tier: the reference's call surface, one call each ------------ */
 
 int nutsb_q_write_user(nutsb_ctx *ctx, int32_t user, const char *str);            /* c:1291 */

@@ -93,6 +93,8 @@ EXPORTS = [
     "nutsb_multi_set_swear_words", "nutsb_multi_set_ban_files", "nutsb_multi_set_profiling", "nutsb_multi_set_users", "nutsb_multi_plan",
     "nutsb_multi_route", "nutsb_multi_write_batch", "nutsb_multi_stream_digests", "nutsb_multi_contains_swearing_batch",
     "nutsb_multi_site_banned_batch", "nutsb_multi_user_banned_batch", "nutsb_multi_get_timing",
+    "nutsb_pipe_create", "nutsb_pipe_destroy", "nutsb_pipe_depth", "nutsb_pipe_ctx", "nutsb_pipe_set_swear_words", "nutsb_pipe_set_users",
+    "nutsb_pipe_set_user_names", "nutsb_pipe_set_ban_swearing", "nutsb_pipe_submit_speech_iov", "nutsb_pipe_submit_write_iov", "nutsb_pipe_wait",
 ]
 
 
@@ -180,6 +182,19 @@ def bind(lib: C.CDLL) -> C.CDLL:
     for name in ("contains_swearing", "site_banned", "user_banned"):
         getattr(lib, f"nutsb_multi_{name}_batch").argtypes = [vp, C.c_int64, vp, vp, vp]
     lib.nutsb_multi_get_timing.argtypes = [vp, C.c_int, C.POINTER(Timing)]
+    lib.nutsb_pipe_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int]
+    lib.nutsb_pipe_destroy.argtypes = [vp]
+    lib.nutsb_pipe_destroy.restype = None
+    lib.nutsb_pipe_depth.argtypes = [vp]
+    lib.nutsb_pipe_ctx.argtypes = [vp, C.c_int]
+    lib.nutsb_pipe_ctx.restype = vp
+    lib.nutsb_pipe_set_swear_words.argtypes = [vp, C.POINTER(C.c_char_p)]
+    lib.nutsb_pipe_set_users.argtypes = [vp, C.c_int32, C.c_int32, i32p, u8p, u8p]
+    lib.nutsb_pipe_set_user_names.argtypes = [vp, C.c_int32, vp, vp, vp]
+    lib.nutsb_pipe_set_ban_swearing.argtypes = [vp, C.c_int]
+    lib.nutsb_pipe_submit_speech_iov.argtypes = [vp, C.c_int64, vp, vp, vp, vp, u64p]
+    lib.nutsb_pipe_submit_write_iov.argtypes = [vp, C.POINTER(_Ops), u64p]
+    lib.nutsb_pipe_wait.argtypes = [vp, C.c_uint64, C.POINTER(_IovStreams)]
     return lib
 
 
@@ -758,3 +773,67 @@ class MultiContext:
         t = Timing()
         self._ck(self.lib.nutsb_multi_get_timing(self._h, shard, C.byref(t)))
         return t
+
+
+class Pipe:
+    """nutsb_pipe: `depth` host-buffer calls in flight on one device (include/nutsb200.h)."""
+
+    def __init__(self, device=0, depth=2, lib=None):
+        self.lib = lib or load_library()
+        self._h = C.c_void_p()
+        rc = self.lib.nutsb_pipe_create(C.byref(self._h), device, depth)
+        if rc != 0:
+            raise NutsbError(rc, "nutsb_pipe_create failed: there is no CPU fallback")
+        self.depth, self._keep = depth, {}
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise NutsbError(rc, "nutsb_pipe")
+
+    def close(self):
+        if self._h:
+            self.lib.nutsb_pipe_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def ctx(self, lane) -> "Context":
+        c = Context.__new__(Context)
+        c.lib, c._h, c.n_users = self.lib, C.c_void_p(self.lib.nutsb_pipe_ctx(self._h, lane)), 0
+        c.close = lambda: None
+        return c
+
+    def set_swear_words(self, words):
+        ws = [w if isinstance(w, bytes) else w.encode() for w in words]
+        self._ck(self.lib.nutsb_pipe_set_swear_words(self._h, (C.c_char_p * (len(ws) + 1))(*ws, None)))
+
+    def set_users(self, room, flags, level, n_rooms):
+        room, flags, level = _np(room, np.int32), _np(flags, np.uint8), _np(level, np.uint8)
+        self._ck(self.lib.nutsb_pipe_set_users(self._h, len(room), n_rooms, room.ctypes.data_as(i32p), flags.ctypes.data_as(u8p), level.ctypes.data_as(u8p)))
+        self.n_users = len(room)
+
+    def set_user_names(self, names, speech_flags):
+        data, off = pack([n if isinstance(n, bytes) else n.encode() for n in names])
+        fl = _np(speech_flags, np.uint8)
+        self._ck(self.lib.nutsb_pipe_set_user_names(self._h, len(names), _addr(data) if data.size else None, _addr(off), _addr(fl)))
+
+    def set_ban_swearing(self, on):
+        self._ck(self.lib.nutsb_pipe_set_ban_swearing(self._h, 1 if on else 0))
+
+    def submit_speech_iov(self, verb, speaker, bodies, body_off) -> int:
+        a = (_np(verb, np.uint8), _np(speaker, np.int32), _np(bodies, np.uint8), _np(body_off, np.uint64))
+        t = C.c_uint64()
+        self._ck(self.lib.nutsb_pipe_submit_speech_iov(self._h, len(a[0]), _addr(a[0]), _addr(a[1]), _addr(a[2]) if a[2].size else None, _addr(a[3]), C.byref(t)))
+        self._keep[t.value % self.depth] = a               # the inputs stay alive until the lane is reused
+        return t.value
+
+    def submit_write_iov(self, ops) -> int:
+        keep = []
+        o = Context._ops_struct(ops, keep)
+        t = C.c_uint64()
+        self._ck(self.lib.nutsb_pipe_submit_write_iov(self._h, C.byref(o), C.byref(t)))
+        self._keep[t.value % self.depth] = keep
+        return t.value
+
+    def wait(self, ticket) -> "IovStreams":
+        st = _IovStreams()
+        self._ck(self.lib.nutsb_pipe_wait(self._h, ticket, C.byref(st)))
+        return Context._host_iov(None, st)

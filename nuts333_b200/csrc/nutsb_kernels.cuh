@@ -240,7 +240,7 @@ k_expand(OpsView ops, PopView pop, const u32 *nrep, const u64 *eoff, u32 *e_room
 #define NUTSB_RS_BITS    8                         // digit width: 8 warps x 256 counters of shared memory in the scatter
 #define NUTSB_RS_DIGITS  (1 << NUTSB_RS_BITS)
 #define NUTSB_RS_THREADS 256
-#define NUTSB_RS_ROUNDS  16
+#define NUTSB_RS_ROUNDS  8
 #define NUTSB_RS_CHUNK   (NUTSB_RS_THREADS * NUTSB_RS_ROUNDS)
 
 // hist[digit * nblocks + block]
@@ -277,12 +277,17 @@ k_rs_scatter(const u32 *keys_in, const u32 *vals_in, i64 n_host, const u32 *n_de
     for (u32 i = threadIdx.x; i < (NUTSB_RS_THREADS / 32) * NUTSB_RS_DIGITS; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     const i64 base = (i64)blockIdx.x * NUTSB_RS_CHUNK + (i64)warp * (NUTSB_RS_ROUNDS * 32);
-    u32 rk[NUTSB_RS_ROUNDS];                               // rank of the key among the warp's keys of the same digit
+    u32 rk[NUTSB_RS_ROUNDS], ky[NUTSB_RS_ROUNDS];          // rank of the key among the warp's keys of the same digit; the keys
+#pragma unroll
+    for (int r = 0; r < NUTSB_RS_ROUNDS; ++r) {            // every load on its way before the first rank is taken (the kernel is latency-bound)
+        const i64 i = base + r * 32 + lane;
+        ky[r] = i < n ? keys_in[i] : 0u;
+    }
 #pragma unroll
     for (int r = 0; r < NUTSB_RS_ROUNDS; ++r) {
         const i64 i = base + r * 32 + lane;
         const bool valid = i < n;
-        const u32 d = valid ? ((keys_in[i] >> shift) & (digits - 1)) : 0xffffffffu;
+        const u32 d = valid ? ((ky[r] >> shift) & (digits - 1)) : 0xffffffffu;
         const u32 grp = __match_any_sync(NUTSB_FULL, d);
         const int leader = __ffs((int)grp) - 1;
         u32 first = 0;
@@ -301,7 +306,7 @@ k_rs_scatter(const u32 *keys_in, const u32 *vals_in, i64 n_host, const u32 *n_de
     for (int r = 0; r < NUTSB_RS_ROUNDS; ++r) {
         const i64 i = base + r * 32 + lane;
         if (i < n) {
-            const u32 key = keys_in[i];
+            const u32 key = ky[r];
             const u32 dst = s_cnt[warp][(key >> shift) & (digits - 1)] + rk[r];
             keys_out[dst] = key;
             vals_out[dst] = vals_in ? vals_in[i] : (u32)i;

@@ -329,3 +329,131 @@ NUTSB_API int nutsb_multi_get_timing(const nutsb_multi *m, int shard, nutsb_timi
     *out = m->routed[(size_t)shard].tm;
     return NUTSB_OK;
 }
+
+// ---- calls in flight: nutsb_pipe ------------------------------------------------------------------
+// A host-buffer call is H2D copy -> kernels -> D2H copy, and PCIe is full duplex: with two calls in flight one
+// call's H2D and kernels run under the other's D2H (profiles/r01_pcie_probe.json: 57 GB/s either way, 99 GB/s both
+// ways at once).  nutsb_pipe keeps `depth` contexts on one device, each with its own worker thread; submit hands a
+// call to the next context and returns at once, wait returns its result.  Results are valid until `depth` further
+// submissions; a call's input buffers must stay valid until it has been waited for.  Tables and population are
+// set once for all contexts (nutsb_pipe_ctx(p, i) gives each of them for anything else).
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+
+struct nutsb_pipe {
+    struct Lane {
+        nutsb_ctx *ctx = nullptr;
+        std::thread th; std::mutex m; std::condition_variable cv;
+        std::function<int()> job; bool has_job = false, done = true, quit = false; int rc = NUTSB_OK;
+        nutsb_iov_streams out{};
+    };
+    int depth = 0;
+    std::vector<Lane *> lanes;
+    uint64_t next = 0;
+};
+
+static void pipe_worker(nutsb_pipe::Lane *L)
+{
+    for (;;) {
+        std::function<int()> job;
+        {
+            std::unique_lock<std::mutex> lk(L->m);
+            L->cv.wait(lk, [L] { return L->has_job || L->quit; });
+            if (L->quit) return;
+            job = L->job; L->has_job = false;
+        }
+        const int rc = job();
+        { std::lock_guard<std::mutex> lk(L->m); L->rc = rc; L->done = true; }
+        L->cv.notify_all();
+    }
+}
+
+NUTSB_API void nutsb_pipe_destroy(nutsb_pipe *p)
+{
+    if (!p) return;
+    for (nutsb_pipe::Lane *L : p->lanes) {
+        if (L->th.joinable()) {
+            { std::unique_lock<std::mutex> lk(L->m); L->cv.wait(lk, [L] { return L->done; }); L->quit = true; }
+            L->cv.notify_all();
+            L->th.join();
+        }
+        if (L->ctx) nutsb_destroy(L->ctx);
+        delete L;
+    }
+    delete p;
+}
+
+NUTSB_API int nutsb_pipe_create(nutsb_pipe **out, int device, int depth)
+{
+    if (!out || depth < 1 || depth > 8) return NUTSB_E_INVAL;
+    *out = nullptr;
+    nutsb_pipe *p = new (std::nothrow) nutsb_pipe;
+    if (!p) return NUTSB_E_NOMEM;
+    p->depth = depth;
+    for (int i = 0; i < depth; ++i) {
+        nutsb_pipe::Lane *L = new (std::nothrow) nutsb_pipe::Lane;
+        if (!L) { nutsb_pipe_destroy(p); return NUTSB_E_NOMEM; }
+        p->lanes.push_back(L);
+        const int rc = nutsb_create(&L->ctx, device);
+        if (rc != NUTSB_OK) { nutsb_pipe_destroy(p); return rc; }
+#ifndef NUTSB_CPUSIM
+        L->th = std::thread(pipe_worker, L);
+#endif
+    }
+    *out = p;
+    return NUTSB_OK;
+}
+NUTSB_API int nutsb_pipe_depth(const nutsb_pipe *p) { return p ? p->depth : 0; }
+NUTSB_API nutsb_ctx *nutsb_pipe_ctx(nutsb_pipe *p, int lane) { return (p && lane >= 0 && lane < p->depth) ? p->lanes[(size_t)lane]->ctx : nullptr; }
+
+#define PEACH(call) do { for (nutsb_pipe::Lane *L_ : p->lanes) { nutsb_ctx *c_ = L_->ctx; const int rc_ = (call); if (rc_ != NUTSB_OK) return rc_; } } while (0)
+NUTSB_API int nutsb_pipe_set_swear_words(nutsb_pipe *p, const char *const *words) { if (!p) return NUTSB_E_INVAL; PEACH(nutsb_set_swear_words(c_, words)); return NUTSB_OK; }
+NUTSB_API int nutsb_pipe_set_users(nutsb_pipe *p, int32_t n_users, int32_t n_rooms, const int32_t *room, const uint8_t *flags, const uint8_t *level)
+{ if (!p) return NUTSB_E_INVAL; PEACH(nutsb_set_users(c_, n_users, n_rooms, room, flags, level)); return NUTSB_OK; }
+NUTSB_API int nutsb_pipe_set_user_names(nutsb_pipe *p, int32_t n_users, const uint8_t *names, const uint64_t *off, const uint8_t *sflags)
+{ if (!p) return NUTSB_E_INVAL; PEACH(nutsb_set_user_names(c_, n_users, names, off, sflags)); return NUTSB_OK; }
+NUTSB_API int nutsb_pipe_set_ban_swearing(nutsb_pipe *p, int on) { if (!p) return NUTSB_E_INVAL; PEACH(nutsb_set_ban_swearing(c_, on)); return NUTSB_OK; }
+
+static int pipe_submit(nutsb_pipe *p, std::function<int(nutsb_pipe::Lane *)> fn, uint64_t *ticket)
+{
+    if (!p || !ticket) return NUTSB_E_INVAL;
+    nutsb_pipe::Lane *L = p->lanes[(size_t)(p->next % (uint64_t)p->depth)];
+    *ticket = p->next++;
+#ifdef NUTSB_CPUSIM                     // the emulator's launch state is process-global: the call runs here and now
+    L->rc = fn(L); L->done = true;
+#else
+    {
+        std::unique_lock<std::mutex> lk(L->m);
+        L->cv.wait(lk, [L] { return L->done; });             // the lane's previous call (its result is given up by now)
+        L->job = [fn, L] { return fn(L); }; L->has_job = true; L->done = false;
+    }
+    L->cv.notify_all();
+#endif
+    return NUTSB_OK;
+}
+
+// nutsb_speech_batch_iov / nutsb_write_batch_iov, in flight
+NUTSB_API int nutsb_pipe_submit_speech_iov(nutsb_pipe *p, int64_t n, const uint8_t *verb, const int32_t *speaker,
+                                           const uint8_t *bodies, const uint64_t *body_off, uint64_t *ticket)
+{
+    return pipe_submit(p, [=](nutsb_pipe::Lane *L) { return nutsb_speech_batch_iov(L->ctx, n, verb, speaker, bodies, body_off, &L->out); }, ticket);
+}
+NUTSB_API int nutsb_pipe_submit_write_iov(nutsb_pipe *p, const nutsb_ops *ops, uint64_t *ticket)
+{
+    if (!ops) return NUTSB_E_INVAL;
+    const nutsb_ops o = *ops;
+    return pipe_submit(p, [o](nutsb_pipe::Lane *L) { return nutsb_write_batch_iov(L->ctx, &o, &L->out); }, ticket);
+}
+// the result of call `ticket` (one of the last `depth` submitted); its return code is the call's own
+NUTSB_API int nutsb_pipe_wait(nutsb_pipe *p, uint64_t ticket, nutsb_iov_streams *out)
+{
+    if (!p || !out || ticket >= p->next || ticket + (uint64_t)p->depth < p->next) return NUTSB_E_INVAL;
+    nutsb_pipe::Lane *L = p->lanes[(size_t)(ticket % (uint64_t)p->depth)];
+    {
+        std::unique_lock<std::mutex> lk(L->m);
+        L->cv.wait(lk, [L] { return L->done; });
+    }
+    *out = L->out;
+    return L->rc;
+}
