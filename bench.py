@@ -865,7 +865,7 @@ def run_config(args):
         ctx.close()
     else:                                                        # c5
         UT, UPR, MT = args.c5_users, 100, args.c5_msgs
-        CH = min(1_000_000, MT)
+        CH = min(1_000_000 * world, MT)                          # a chunk = 1M messages per GPU: the same HBM per GPU at every N
         n_chunks = (MT + CH - 1) // CH
         users, n_rooms = synth.users(UT, UPR)
         m = api.MultiContext(rank=(world, rank, local))
@@ -964,7 +964,7 @@ def run_config(args):
         line = dict(metric=METRIC, value=float(sm[0]) / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="u8", data="synthetic",
                     config=dict(workload="C5: full pipeline, %d msgs x %d users (%d rooms of %d): admission (site_banned | user_banned, %d-entry lists) -> "
-                                         "contains_swearing (%d words) -> say() render + fan-out, in %d message-ordered chunks; one step = the whole job"
+                                         "contains_swearing (%d words) -> say() render + fan-out, in %d message-ordered chunks (1M messages per GPU each); one step = the whole job"
                                          % (MT, UT, n_rooms, UPR, N_BAN_ENTRIES, N_SWEAR, n_chunks),
                                 sharding="rooms dealt to the GPUs by nutsb_multi (the library's sharder), streams stay in HBM; swear / ban batches split by "
                                          "index range and their verdict bytes gathered (NCCL all_gather: the only cross-rank traffic)",
