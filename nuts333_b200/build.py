@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
     LIB.parent.mkdir(parents=True, exist_ok=True)
-    extra = os.environ.get("NUTSB_NVCC_EXTRA", "").split()      # e.g. -DNUTSB_TILE_OPS=256 for A/B runs (scripts/gpu_matrix.sh)
+    extra = os.environ.get("NUTSB_NVCC_EXTRA", "").split()      # e.g. -DNUTSB_TILE_OPS=256 for A/B runs
     cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", str(LIB), *map(str, SOURCES)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
