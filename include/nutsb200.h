@@ -335,6 +335,13 @@ int nutsb_colour_com_strip_batch(nutsb_ctx *ctx, int64_t n, const uint8_t *bytes
  * gather-list batch that never built the streams (plain listeners: nothing to digest in HBM). */
 int nutsb_stream_digests(nutsb_ctx *ctx, uint64_t *digest);
 
+/* The parity digests of SURVEY.md 8(d) for the last write batch whose streams are in HBM (host arrays, either may be
+ * NULL): d(m,u) = 64-bit FNV-1a (offset 0xcbf29ce484222325, prime 0x100000001b3) over the rendered bytes of one delivery;
+ * per_user[u] = the left fold over u's deliveries in call order, per_op[m] = the same fold over op m's recipients in
+ * user-list order (the loop of nuts333.c:1409):  D <- (D * 0x9E3779B97F4A7C15) ^ d ^ len, D0 = 0.  A delivery of no
+ * bytes makes no write(2) in the reference and is not folded; an op that was gated off or reached nobody has digest 0.
+ * The message-major view of the batch: what each call delivered, without materialising a byte per recipient. */
+int nutsb_delivery_digests(nutsb_ctx *ctx, uint64_t *per_user, uint64_t *per_op);
 /* Streams left in HBM: ops in host memory, nutsb_streams with device pointers (on_device 1) -- for a caller
  * that only wants digests (nutsb_stream_digests) or copies what it needs later. */
 int nutsb_write_batch_keep(nutsb_ctx *ctx, const nutsb_ops *ops, nutsb_streams *out);

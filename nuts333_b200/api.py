@@ -88,7 +88,7 @@ EXPORTS = [
     "nutsb_colour_com_count_batch", "nutsb_colour_com_strip_batch", "nutsb_stream_digests", "nutsb_q_write_user", "nutsb_q_write_room", "nutsb_q_write_room_except",
     "nutsb_q_write_level", "nutsb_q_write_sock", "nutsb_q_page_line", "nutsb_q_more", "nutsb_q_pending", "nutsb_flush", "nutsb_flush_iov", "nutsb_contains_swearing",
     "nutsb_site_banned", "nutsb_user_banned",
-    "nutsb_write_batch_keep", "nutsb_stream_digests_continue",
+    "nutsb_write_batch_keep", "nutsb_stream_digests_continue", "nutsb_delivery_digests",
     "nutsb_multi_create", "nutsb_multi_create_rank", "nutsb_multi_destroy", "nutsb_multi_last_error", "nutsb_multi_n_shards", "nutsb_multi_ctx",
     "nutsb_multi_set_swear_words", "nutsb_multi_set_ban_files", "nutsb_multi_set_profiling", "nutsb_multi_set_users", "nutsb_multi_plan",
     "nutsb_multi_route", "nutsb_multi_write_batch", "nutsb_multi_stream_digests", "nutsb_multi_contains_swearing_batch",
@@ -162,6 +162,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.nutsb_flush_iov.argtypes = [vp, C.POINTER(_IovStreams)]
     lib.nutsb_write_batch_keep.argtypes = [vp, C.POINTER(_Ops), C.POINTER(_Streams)]
     lib.nutsb_stream_digests_continue.argtypes = [vp, u64p]
+    lib.nutsb_delivery_digests.argtypes = [vp, u64p, u64p]
     lib.nutsb_multi_create.argtypes = [C.POINTER(vp), i32p, C.c_int]
     lib.nutsb_multi_create_rank.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int]
     lib.nutsb_multi_destroy.argtypes = [vp]
@@ -472,6 +473,12 @@ class Context:
         d = np.zeros(max(self.n_users, 1), np.uint64)
         self._ck(self.lib.nutsb_stream_digests(self._h, d.ctypes.data_as(u64p)))
         return d[:self.n_users]
+
+    def delivery_digests(self, n_ops):
+        """SURVEY.md 8(d) parity digests of the last write batch -> (per_user u64[U], per_op u64[n_ops])"""
+        pu, po = np.zeros(max(self.n_users, 1), np.uint64), np.zeros(max(n_ops, 1), np.uint64)
+        self._ck(self.lib.nutsb_delivery_digests(self._h, pu.ctypes.data_as(u64p), po.ctypes.data_as(u64p)))
+        return pu[:self.n_users], po[:n_ops]
 
     # -- verdict batches -----------------------------------------------------------------
     def _verdicts(self, name, text, off):

@@ -1468,3 +1468,120 @@ k_iov(IovArgs A)
     for (int d = 16; d; d >>= 1) deliv += __shfl_xor_sync(NUTSB_FULL, deliv, d);
     if ((threadIdx.x & 31) == 0 && deliv) nutsb_add64(A.deliveries, (u64)deliv);
 }
+
+// ---- parity digests ----------------------------------------------------------------
+// d(m,u) = FNV-1a over the bytes of one delivery; per user D_u = the left fold over his deliveries in call order,
+// per op D_m = the same fold over its recipients in user-list order:  D <- (D * K) ^ d ^ len,  D0 = 0; a delivery
+// of no bytes is not folded (the reference makes no write(2) for it).  Computed from what the last write batch
+// left in HBM: a room / level op has two renderings in the slab (so two d's, whoever receives it), a write_user's
+// rendering sits in its recipient's stream.  Checking tools, not part of the hot path.
+#define NUTSB_DG_K 0x9E3779B97F4A7C15ull
+
+__device__ __forceinline__ u64 nutsb_fnv1a(const u8 *p, u64 n)
+{
+    u64 h = 0xcbf29ce484222325ull;
+    for (u64 i = 0; i < n; ++i) { h ^= p[i]; h *= 0x100000001b3ull; }
+    return h;
+}
+
+struct DgArgs {
+    OpsView ops; PopView pop; ClassPrefix cpx;
+    const u32 *bl_op, *bl_meta, *ev_slot_sorted, *sv_ukey, *sv_op; const u64 *sv_pre;
+    const SlotInfo *slots; const u8 *slab, *out; u64 off_base;
+    const u32 *counts;               // [0] slab ops, [1] events
+    u32 has_level;
+    const u32 *nrep; const i32 *room_users, *room_users_off;
+    u64 *dg_on, *dg_off;             // per slab entry
+    u64 *ev_d; u32 *ev_len;          // per event (direct kinds)
+    u32 *op_g, *op_ev;               // per op: one of its slab entries / its event (~0: none)
+    u64 *per_user, *per_op;
+};
+
+__global__ void __launch_bounds__(256) k_dg_slab(DgArgs A)
+{
+    const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= A.counts[0]) return;
+    const u64 a0 = A.cpx.vp_on[g], a1 = A.cpx.vp_on[g + 1], b0 = A.cpx.vp_off[g], b1 = A.cpx.vp_off[g + 1];
+    A.dg_on[g] = nutsb_fnv1a(A.slab + a0, a1 - a0);
+    A.dg_off[g] = nutsb_fnv1a(A.slab + A.off_base + b0, b1 - b0);
+    A.op_g[A.bl_op[g]] = g;                          // (an all-room op has one entry per room, all with the same bytes)
+}
+
+__global__ void __launch_bounds__(256) k_dg_events(DgArgs A)
+{
+    const u32 e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A.counts[1]) return;
+    const u32 uk = A.sv_ukey[e], j = uk >> 2, ek = uk & 3u;
+    if (ek == NUTSB_EV_SKIP) return;
+    const SlotInfo si = A.slots[A.ev_slot_sorted[e]];
+    const u32 skip = ek != NUTSB_EV_DIRECT;
+    const u64 p = si.base + A.cpx.at(si.k, si.room, si.b0 + j) + A.sv_pre[e];
+    const u64 q = si.base + A.cpx.at(si.k, si.room, si.b0 + j + skip) + A.sv_pre[e + 1];
+    A.ev_d[e] = nutsb_fnv1a(A.out + p, q - p);
+    A.ev_len[e] = (u32)(q - p);
+    A.op_ev[A.sv_op[e]] = e;
+}
+
+__global__ void __launch_bounds__(128) k_dg_user(DgArgs A)
+{
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= (u32)A.pop.n_users) return;
+    const SlotInfo si = A.slots[s];
+    const u32 cf = si.cf_lv & 0xffu, lv = si.cf_lv >> 8;
+    const bool colour = (cf & NUTSB_UF_COLOUR) != 0;
+    const bool full = !A.has_level && !(cf & NUTSB_UF_FILTERED);
+    const u64 *vp = colour ? A.cpx.vp_on : A.cpx.vp_off;
+    const u64 *dg = colour ? A.dg_on : A.dg_off;
+    u32 e = si.e0;
+    u64 D = 0;
+    for (u32 a = 0; a <= si.nb_room; ++a) {
+        bool skip = false;
+        while (e < si.e1 && (A.sv_ukey[e] >> 2) == a) {              // the recipient's own events at this slab rank, in call order
+            const u32 ek = A.sv_ukey[e] & 3u;
+            if (ek != NUTSB_EV_SKIP) { const u64 len = A.ev_len[e]; if (len) D = (D * NUTSB_DG_K) ^ A.ev_d[e] ^ len; }
+            if (ek != NUTSB_EV_DIRECT) skip = true;                   // ... and he is the excluded user of slab op a
+            ++e;
+        }
+        if (a == si.nb_room || skip) continue;
+        const u32 g = si.b0 + a;
+        const u32 m = A.bl_meta[g];
+        if (full || nutsb_class_delivers(cf, lv, m & 0xffu, (m >> 8) & 0xffu, (i32)(int16_t)(m >> 16))) {
+            const u64 len = vp[g + 1] - vp[g];
+            if (len) D = (D * NUTSB_DG_K) ^ dg[g] ^ len;
+        }
+    }
+    A.per_user[A.pop.slot_user[s]] = D;
+}
+
+__global__ void __launch_bounds__(128) k_dg_op(DgArgs A)
+{
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.ops.n) return;
+    u64 D = 0;
+    if (A.nrep[i]) {
+        const u32 kind = A.ops.kind[i];
+        if (kind == NUTSB_OP_USER) {
+            const u32 e = A.op_ev[i];
+            if (e != 0xffffffffu && A.ev_len[e]) D = A.ev_d[e] ^ (u64)A.ev_len[e];
+        } else if (A.op_g[i] != 0xffffffffu) {
+            const u32 g = A.op_g[i];
+            const u64 l_on = A.cpx.vp_on[g + 1] - A.cpx.vp_on[g], l_off = A.cpx.vp_off[g + 1] - A.cpx.vp_off[g];
+            const u64 d_on = A.dg_on[g], d_off = A.dg_off[g];
+            const i32 tgt = A.ops.target[i], exc = A.ops.except_user[i];
+            const u32 of = A.ops.flags[i];
+            const bool one_room = kind == NUTSB_OP_ROOM && tgt >= 0;
+            const i32 n0 = one_room ? A.room_users_off[tgt] : 0, n1 = one_room ? A.room_users_off[tgt + 1] : A.pop.n_users;
+            for (i32 x = n0; x < n1; ++x) {                           // recipients in user-list order (c:1409)
+                const i32 u = one_room ? A.room_users[x] : x;
+                if (u == exc) continue;
+                if (kind == NUTSB_OP_ROOM && A.pop.user_room[u] >= A.pop.n_rooms) continue;      // u->room == NULL: c:1410
+                const i32 s = A.pop.user_slot[u];
+                const u32 cf = A.pop.slot_cf[s];
+                if (!nutsb_class_delivers(cf, A.pop.slot_lv[s], kind, of, tgt)) continue;
+                const u64 len = (cf & NUTSB_UF_COLOUR) ? l_on : l_off;
+                if (len) D = (D * NUTSB_DG_K) ^ ((cf & NUTSB_UF_COLOUR) ? d_on : d_off) ^ len;
+            }
+        }
+    }
+    A.per_op[i] = D;
+}

@@ -92,6 +92,9 @@ struct nutsb_ctx {
     DBuf d_dpre, d_dir, d_iov, d_iov_first, d_iov_cnt;           // gather-list mode (nutsb_write_batch_iov)
     HBuf h_small, h_off, h_out, h_dir, h_iov, h_iov_first, h_iov_cnt;
     u64 last_total = 0; bool have_streams = false;
+    // what nutsb_delivery_digests needs of the last write batch (its arrays stay in the scratch buffers until the next one)
+    struct LastBatch { bool valid = false; OpsView ops{}; ClassPrefix cpx{}; bool has_level = false; u64 off_base = 0; u32 *sv_slot = nullptr; } last;
+    DBuf d_room_users, d_room_users_off, d_dg;
 
     // staging for the host-buffer entry points
     DBuf s_text, s_toff, s_kind, s_target, s_except, s_flags, s_gate, s_verdict, s_v8;
@@ -387,7 +390,7 @@ NUTSB_API void nutsb_destroy(nutsb_ctx *c)
         &c->d_sv_delta, &c->d_sv_op, &c->d_sv_pre, &c->d_ev_off, &c->d_vp_on, &c->d_vp_off, &c->d_cp,
         &c->d_room_tile_off, &c->d_room_cell_off, &c->d_room_item_off, &c->d_sizes, &c->d_counters,
         &c->d_runs, &c->d_slots, &c->d_items, &c->d_slab, &c->d_bl_meta, &c->d_off, &c->d_out, &c->d_digest, &c->d_ulen,
-        &c->d_dpre, &c->d_dir, &c->d_iov, &c->d_iov_first, &c->d_iov_cnt,
+        &c->d_dpre, &c->d_dir, &c->d_iov, &c->d_iov_first, &c->d_iov_cnt, &c->d_room_users, &c->d_room_users_off, &c->d_dg,
         &c->s_text, &c->s_toff, &c->s_kind, &c->s_target, &c->s_except, &c->s_flags, &c->s_gate, &c->s_verdict, &c->s_v8,
         &c->d_names, &c->d_name_off, &c->d_sflags, &c->d_lit, &c->d_lit_off, &c->d_sp_len, &c->d_sp_off, &c->d_sp_text,
         &c->d_sp_kind, &c->d_sp_target, &c->d_sp_except, &c->d_sp_flags, &c->d_sp_gate, &c->d_sp_verdict,
@@ -660,6 +663,17 @@ static int set_users_impl(nutsb_ctx *c, int32_t n_users, int32_t n_rooms, const 
         TRY(upload(c, c->d_slot_lv, lv.data(), (size_t)n_users));
         CK(cudaStreamSynchronize(c->stream));          // cf/lv go out of scope
     }
+    {   // every room's users in user-list order (the order write_room_except reaches them, c:1409): for the per-op digests
+        std::vector<i32> ro((size_t)c->Rt + 1, 0), ru((size_t)n_users);
+        for (i32 u = 0; u < n_users; ++u) ro[(size_t)c->user_room[u] + 1]++;
+        for (i32 r = 0; r < c->Rt; ++r) ro[(size_t)r + 1] += ro[(size_t)r];
+        std::vector<i32> cur(ro.begin(), ro.end() - 1);
+        for (i32 u = 0; u < n_users; ++u) ru[(size_t)cur[(size_t)c->user_room[u]]++] = u;
+        TRY(upload(c, c->d_room_users, ru.data(), (size_t)n_users * 4));
+        TRY(upload(c, c->d_room_users_off, ro.data(), ro.size() * 4));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    c->last.valid = false;
     TRY(build_classes(c, c->cls[0], false, order, flags, level));
     TRY(build_classes(c, c->cls[1], true, order, flags, level));
     CK(cudaStreamSynchronize(c->stream));
@@ -717,7 +731,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
     const i64 n = o->n_ops;
     const i32 U = c->U, Rt = c->Rt;
     cudaStream_t st = c->stream;
-    c->have_streams = false;
+    c->have_streams = false; c->last.valid = false;
     c->tm.launches = 0; c->tm.fanout_launches = 0;
     if (c->side) CK(cudaStreamSynchronize(c->side));           // idle unless an earlier batch failed half-way
     if (c->profiling) CK(cudaEventRecord(c->ev[0], st));
@@ -1024,6 +1038,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
     CK(cudaStreamSynchronize(st));
     TRY(status_to_error(c, h32[4]));
     c->last_total = sz.total_bytes; c->have_streams = true;
+    c->last.valid = true; c->last.ops = ops; c->last.cpx = cpx; c->last.has_level = has_level; c->last.off_base = off_base; c->last.sv_slot = sv_slot;
     if (c->profiling) {
         // with the side stream on, render_ms / direct_ms are the side kernels' own spans and overlap plan_ms / fanout_ms
         CK(cudaEventSynchronize(c->ev[3]));
@@ -1198,6 +1213,45 @@ static int stream_digests(nutsb_ctx *c, uint64_t *digest, bool cont)
 }
 NUTSB_API int nutsb_stream_digests(nutsb_ctx *c, uint64_t *digest) { return stream_digests(c, digest, false); }
 NUTSB_API int nutsb_stream_digests_continue(nutsb_ctx *c, uint64_t *digest) { return stream_digests(c, digest, true); }
+
+// The parity digests of SURVEY.md 8(d) for the last write batch (its streams and scratch arrays still in HBM):
+// per_user[n_users] and per_op[n_ops], host arrays, either may be NULL.
+NUTSB_API int nutsb_delivery_digests(nutsb_ctx *c, uint64_t *per_user, uint64_t *per_op)
+{
+    if (!c) return NUTSB_E_INVAL;
+    if (!c->have_streams || !c->last.valid) return fail(c, NUTSB_E_STATE, "no write batch with streams in HBM has run (or it was empty)%s");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const i64 n = c->last.ops.n; const size_t U = (size_t)c->U;
+    // upper bounds on the slab ops and the events: the entries of the batch (the counts themselves are on the device)
+    u32 hcounts[2];
+    CK(cudaMemcpyAsync(hcounts, c->d_counts.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const size_t nS = hcounts[0], nE = hcounts[1];
+    const size_t bytes = (2 * (nS + 1) + (nE + 1) + U + 1 + (size_t)n + 1) * 8 + ((nE + 1) + 2 * ((size_t)n + 1)) * 4;
+    TRY(ensure(c, c->d_dg, bytes));
+    u64 *p64 = c->d_dg.as<u64>();
+    DgArgs A{};
+    A.ops = c->last.ops; A.pop = pop_view(c, c->last.has_level ? 1 : 0); A.cpx = c->last.cpx;
+    A.bl_op = c->d_bl_op.as<u32>(); A.bl_meta = c->d_bl_meta.as<u32>(); A.ev_slot_sorted = c->last.sv_slot;
+    A.sv_ukey = c->d_sv_ukey.as<u32>(); A.sv_op = c->d_sv_op.as<u32>(); A.sv_pre = c->d_sv_pre.as<u64>();
+    A.slots = c->d_slots.as<SlotInfo>(); A.slab = c->d_slab.as<u8>(); A.out = c->d_out.as<u8>(); A.off_base = c->last.off_base;
+    A.counts = c->d_counts.as<u32>(); A.has_level = c->last.has_level ? 1u : 0u;
+    A.nrep = c->d_nrep.as<u32>(); A.room_users = c->d_room_users.as<i32>(); A.room_users_off = c->d_room_users_off.as<i32>();
+    A.dg_on = p64; A.dg_off = A.dg_on + nS + 1; A.ev_d = A.dg_off + nS + 1; A.per_user = A.ev_d + nE + 1; A.per_op = A.per_user + U + 1;
+    u32 *p32 = (u32 *)(A.per_op + n + 1);
+    A.ev_len = p32; A.op_g = p32 + nE + 1; A.op_ev = A.op_g + n + 1;
+    CK(cudaMemsetAsync(A.ev_len, 0, (nE + 1) * 4, st));
+    CK(cudaMemsetAsync(A.op_g, 0xff, 2 * ((size_t)n + 1) * 4, st));
+    if (nS) { NUTSB_LAUNCH(cdiv(nS, 256), 256, st, k_dg_slab, A); CKL(); }
+    if (nE) { NUTSB_LAUNCH(cdiv(nE, 256), 256, st, k_dg_events, A); CKL(); }
+    if (U && per_user) { NUTSB_LAUNCH(cdiv(U, 128), 128, st, k_dg_user, A); CKL(); }
+    if (n && per_op) { NUTSB_LAUNCH(cdiv((u64)n, 128), 128, st, k_dg_op, A); CKL(); }
+    if (per_user && U) CK(cudaMemcpyAsync(per_user, A.per_user, U * 8, cudaMemcpyDeviceToHost, st));
+    if (per_op && n) CK(cudaMemcpyAsync(per_op, A.per_op, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return NUTSB_OK;
+}
 
 // ops in host memory, streams left in HBM (digests, or a later copy, are the caller's business)
 NUTSB_API int nutsb_write_batch_keep(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out)

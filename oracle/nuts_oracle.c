@@ -372,6 +372,51 @@ int orc_write_batch(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
     return 0;
 }
 
+/* Parity digests: d = FNV-1a over one delivery's rendered bytes; per user, the left fold over his
+ * deliveries in call order, per op the same fold over its recipients in user-list order (the order of the loop at
+ * nuts333.c:1409):  D <- (D * 0x9E3779B97F4A7C15) ^ d ^ len,  D0 = 0.  A delivery of no bytes (an empty string for a
+ * colour-off recipient) makes no write(2) at all in the reference and is not folded.  Populations without clones /
+ * remote users (their relays are deliveries of other strings to other sockets).  Either array may be NULL. */
+#define ORC_DG_K 0x9E3779B97F4A7C15ull
+int orc_delivery_digests(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
+                         const uint8_t *kind, const int32_t *target,
+                         const int32_t *except_user, const uint8_t *of,
+                         const int32_t *gate, const uint8_t *verdict,
+                         int32_t n_users, const int32_t *room, const uint8_t *uf, const uint8_t *ul,
+                         uint64_t *per_user, uint64_t *per_op)
+{
+    size_t maxn = 0;
+    for (int64_t i = 0; i < n_ops; ++i) { size_t n = (size_t)(toff[i + 1] - toff[i]); if (n > maxn) maxn = n; }
+    for (int32_t u = 0; u < n_users; ++u) if (uf[u] & (ORC_UF_CLONE | ORC_UF_REMOTE)) return -2;
+    uint8_t *buf = malloc(6 * maxn + 8);
+    if (!buf) return -1;
+    if (per_user) memset(per_user, 0, sizeof(uint64_t) * (size_t)n_users);
+    for (int64_t i = 0; i < n_ops; ++i) {
+        uint64_t D = 0;
+        if (per_op) per_op[i] = 0;
+        if (kind[i] > ORC_OP_LEVEL || !orc_live(i, of, gate, verdict)) continue;
+        const uint8_t *s = text + toff[i];
+        const size_t n = (size_t)(toff[i + 1] - toff[i]);
+        uint64_t dv[2] = { 0, 0 }; size_t lv[2] = { 0, 0 }; int have[2] = { 0, 0 };
+        int32_t u0 = 0, u1 = n_users;
+        if (kind[i] == ORC_OP_USER) {
+            if (target[i] < 0 || target[i] >= n_users) continue;
+            u0 = target[i]; u1 = u0 + 1;
+        }
+        for (int32_t u = u0; u < u1; ++u) {
+            if (!orc_delivers(kind[i], target[i], except_user[i], of[i], u, room[u], uf[u], ul[u])) continue;
+            const int c = (uf[u] & ORC_UF_COLOUR) != 0;
+            if (!have[c]) { lv[c] = orc_render_ex(s, n, c, of[i], buf); dv[c] = orc_fnv1a(buf, lv[c]); have[c] = 1; }
+            if (!lv[c]) continue;
+            D = (D * ORC_DG_K) ^ dv[c] ^ (uint64_t)lv[c];
+            if (per_user) per_user[u] = (per_user[u] * ORC_DG_K) ^ dv[c] ^ (uint64_t)lv[c];
+        }
+        if (per_op) per_op[i] = D;
+    }
+    free(buf);
+    return 0;
+}
+
 int64_t orc_write_batch_count(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
                     const uint8_t *kind, const int32_t *target,
                     const int32_t *except_user, const uint8_t *of,

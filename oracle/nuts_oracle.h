@@ -92,6 +92,13 @@ typedef struct {
     uint64_t *n_deliveries; /* per user                       */
 } orc_streams;
 
+/* Parity digests of SURVEY.md 8(d): per user and per op (see nuts_oracle.c).  -2: clones / remote users present. */
+int orc_delivery_digests(int64_t n_ops, const uint8_t *text, const uint64_t *text_off,
+                         const uint8_t *kind, const int32_t *target, const int32_t *except_user, const uint8_t *oflags,
+                         const int32_t *gate, const uint8_t *verdict,
+                         int32_t n_users, const int32_t *room, const uint8_t *uflags, const uint8_t *ulevel,
+                         uint64_t *per_user, uint64_t *per_op);
+
 /* Runs n_ops calls in order against the population and returns, per user, the
  * exact byte stream the reference would have written to that user's socket.
  * gate[i] >= 0 makes op i conditional on verdict[gate[i]] (say(), c:4091).

@@ -40,9 +40,21 @@ static int      g_sink_mode = 0;      /* 0 keep bytes, 1 count only, 2 real writ
 static int      g_devnull = -1;
 static uint64_t g_write_calls = 0, g_write_bytes = 0;
 
+/* parity digests taken from the reference's own write(2) calls: one delivery = the 1-3 calls
+ * write_user makes for one recipient (buffer flushes c:1318,1339,1360,1363 and the closing reset c:1365), so the
+ * running FNV-1a of a socket is carried across calls and closed when the harness moves on to the next op */
+static int       g_dg_on = 0, g_dg_ntouched = 0;
+static uint64_t *g_dg_fnv = NULL, *g_dg_len = NULL; static int *g_dg_order = NULL; static uint8_t *g_dg_touched = NULL;
+
 static ssize_t nutsref_write(int fd, const void *buf, size_t n)
 {
     ++g_write_calls; g_write_bytes += n;
+    if (g_dg_on && fd >= 0 && fd < g_nsink && n) {
+        if (!g_dg_touched[fd]) { g_dg_touched[fd] = 1; g_dg_order[g_dg_ntouched++] = fd; g_dg_fnv[fd] = 0xcbf29ce484222325ull; g_dg_len[fd] = 0; }
+        uint64_t h = g_dg_fnv[fd];
+        for (size_t k = 0; k < n; ++k) { h ^= ((const uint8_t *)buf)[k]; h *= 0x100000001b3ull; }
+        g_dg_fnv[fd] = h; g_dg_len[fd] += n;
+    }
     if (g_sink_mode == 2) return write(g_devnull, buf, n);   /* the real write(2) */
     if (g_sink_mode == 1 || fd < 0 || fd >= g_nsink) return (ssize_t)n;
     sink_t *s = &g_sink[fd];
@@ -338,6 +350,40 @@ int64_t ref_write_batch(int64_t n_ops, const uint8_t *text, const uint64_t *toff
         ++calls;
     }
     free(str);
+    return calls;
+}
+
+/* ref_write_batch with the parity digests of SURVEY.md 8(d) folded from what the reference writes: per user
+ * (sockets = user indices) in call order, per op over its recipients in the order the reference reached them */
+int64_t ref_write_batch_digests(int64_t n_ops, const uint8_t *text, const uint64_t *toff,
+                                const uint8_t *kind, const int32_t *target,
+                                const int32_t *except_user, const uint8_t *oflags,
+                                const int32_t *gate, const uint8_t *verdict, uint64_t *per_user, uint64_t *per_op)
+{
+    const uint64_t K = 0x9E3779B97F4A7C15ull;
+    g_dg_fnv = calloc((size_t)g_nsink + 1, 8); g_dg_len = calloc((size_t)g_nsink + 1, 8);
+    g_dg_order = calloc((size_t)g_nsink + 1, sizeof(int)); g_dg_touched = calloc((size_t)g_nsink + 1, 1);
+    if (!g_dg_fnv || !g_dg_len || !g_dg_order || !g_dg_touched) return -1;
+    for (int u = 0; u < g_nusers; ++u) per_user[u] = 0;
+    const int mode = g_sink_mode;
+    g_sink_mode = 1; g_dg_on = 1;
+    int64_t calls = 0;
+    for (int64_t i = 0; i < n_ops; ++i) {
+        g_dg_ntouched = 0;
+        calls += ref_write_batch(1, text, toff + i, kind + i, target + i, except_user + i, oflags + i, gate ? gate + i : NULL, verdict);
+        uint64_t D = 0;
+        for (int k = 0; k < g_dg_ntouched; ++k) {
+            const int fd = g_dg_order[k];
+            const uint64_t d = g_dg_fnv[fd], len = g_dg_len[fd];
+            D = (D * K) ^ d ^ len;
+            if (fd < g_nusers) per_user[fd] = (per_user[fd] * K) ^ d ^ len;
+            g_dg_touched[fd] = 0;
+        }
+        per_op[i] = D;
+    }
+    g_dg_on = 0; g_sink_mode = mode;
+    free(g_dg_fnv); free(g_dg_len); free(g_dg_order); free(g_dg_touched);
+    g_dg_fnv = g_dg_len = NULL; g_dg_order = NULL; g_dg_touched = NULL;
     return calls;
 }
 

@@ -93,6 +93,8 @@ class Port:
         L.orc_write_batch_count.argtypes = [C.c_int64, u8p, u64p, u8p, i32p, i32p, u8p, i32p, u8p,
                                             C.c_int32, i32p, u8p, u8p, u64p]
         L.orc_streams_free.argtypes = [C.POINTER(_Streams)]
+        L.orc_delivery_digests.argtypes = [C.c_int64, u8p, u64p, u8p, i32p, i32p, u8p, i32p, u8p,
+                                           C.c_int32, i32p, u8p, u8p, u64p, u64p]
         L.orc_contains_swearing_batch.argtypes = [C.c_int64, u8p, u64p, C.POINTER(C.c_char_p), u8p]
         L.orc_site_banned_batch.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int64, u8p, u64p, u8p]
         L.orc_user_banned_batch.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int64, u8p, u64p, u8p]
@@ -164,6 +166,16 @@ class Port:
         nd = np.ctypeslib.as_array(st.n_deliveries, shape=(U + 1,))[:U].copy()
         self.lib.orc_streams_free(C.byref(st))
         return off, data, nd
+
+    def delivery_digests(self, ops, users, verdict=None):
+        """SURVEY.md 8(d) parity digests -> (per_user u64[U], per_op u64[n_ops])"""
+        U, n = len(users["room"]), len(ops["kind"])
+        pu, po = np.zeros(max(U, 1), np.uint64), np.zeros(max(n, 1), np.uint64)
+        rc = self.lib.orc_delivery_digests(n, _ptr(ops["text"], u8p), _ptr(ops["off"], u64p), _ptr(ops["kind"], u8p), _ptr(ops["target"], i32p),
+                                           _ptr(ops["except_user"], i32p), _ptr(ops["flags"], u8p), _ptr(ops.get("gate"), i32p), _ptr(verdict, u8p),
+                                           U, _ptr(users["room"], i32p), _ptr(users["flags"], u8p), _ptr(users["level"], u8p), _ptr(pu, u64p), _ptr(po, u64p))
+        assert rc == 0, rc
+        return pu[:U], po[:n]
 
     def write_batch_count(self, ops, users, verdict=None):
         nb = C.c_uint64(0)
@@ -364,6 +376,18 @@ class Ref:
 
     def streams(self, n_users):
         return [self.stream(u) for u in range(n_users)]
+
+    def delivery_digests(self, ops, n_rooms, users, verdict=None):
+        """the same digests folded from the reference's own write(2) calls"""
+        self.reset(n_rooms, users, 1)
+        U, n = len(users["room"]), len(ops["kind"])
+        pu, po = np.zeros(max(U, 1), np.uint64), np.zeros(max(n, 1), np.uint64)
+        self.lib.ref_write_batch_digests.restype = C.c_int64
+        rc = self.lib.ref_write_batch_digests(n, _ptr(ops["text"], u8p), _ptr(ops["off"], u64p), _ptr(ops["kind"], u8p), _ptr(ops["target"], i32p),
+                                              _ptr(ops["except_user"], i32p), _ptr(ops["flags"], u8p), _ptr(ops.get("gate"), i32p), _ptr(verdict, u8p),
+                                              _ptr(pu, u64p), _ptr(po, u64p))
+        assert rc >= 0
+        return pu[:U], po[:n]
 
     def contains_swearing_batch(self, text, off):
         n = len(off) - 1
