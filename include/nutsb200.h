@@ -11,6 +11,10 @@
  *     int  contains_swearing(char *str);                                 nuts333.c:2540
  *     int  site_banned(char *site);                                      nuts333.c:330
  *     int  user_banned(char *name);                                      nuts333.c:349
+ *     void write_sock(int sock, char *str);                              nuts333.c:1281
+ *
+ * shim/nuts333_shim.c holds bodies with exactly these names over this header (the
+ * drop-in; tests/dropin/ links them over the unmodified nuts333.c).
  *
  * This header exposes that surface in three tiers, all `extern "C"`, plain
  * pointers and sizes only:
@@ -18,10 +22,12 @@
  *   1. queue tier  (nutsb_q_*, nutsb_flush): one call per reference call, user /
  *      room passed as their index in the reference's lists.  str is copied on
  *      enqueue (callers overwrite the global text[] right after, c:4094-4098).
- *      INTEGRATION.md shows the 7 one-line bodies that bind nuts333.c to it.
+ *      shim/nuts333_shim.c holds the eight bodies that bind nuts333.c to it.
  *   2. batch tier, host buffers (nutsb_write_batch, nutsb_*_batch): SoA batches
  *      in host memory, results in library-owned pinned host memory.
  *   3. batch tier, device buffers (*_dev): the same on buffers already in HBM.
+ * and, over the batch tier, nutsb_multi (one population and one batch over several
+ * GPUs, sharded by room, no collective) and nutsb_pipe (calls in flight on one GPU).
  *
  * Semantics are bit-exact with nuts333.c for USER_TYPE recipients, for clones (the
  * relay of c:1416-1426) and for remote users (the MSG/EMSG framing of c:1299-1307):
