@@ -267,8 +267,8 @@ def run_reference(args):
                 scaling="weak", vs_baseline=None, dtype="u8", data="synthetic",
                 config=dict(workload=workload_name(), note="reference CPU path on a bounded sample of the workload: the rate "
                             "of a proportional %.0f %% sample (msgs and ban queries in the step's ratio), not a full step" % (100.0 * n_msgs / N_MSGS),
-                            components=dict(comp, note="slowest worker's seconds per component in the last step; the ban checks "
-                                            "(fopen + fscanf of a 10k-entry file per query, nuts333.c:330-364) dominate")),
+                            components=dict(comp, note="slowest worker's seconds per component in the last step (the ban checks re-open "
+                                            "and re-parse the 10k-entry file per query, nuts333.c:330-364: about half of the time)")),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=procs, kind=kind, sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)

@@ -11,6 +11,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 G = ROOT / "gpurun_out"
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=ROOT).stdout.strip() or "?"
 out = ROOT / "profiles"
 out.mkdir(exist_ok=True)
 
@@ -69,7 +70,8 @@ with open(out / f"{tag}_ncu_full_summary.txt", "w") as f:
                 float(row[hdr.index("dram__bytes_write.sum")].replace(",", "")) * \
                 {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[r[1][hdr.index("dram__bytes_write.sum")]]
             (out / "fanout_traffic.json").write_text(json.dumps(
-                {"dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_ncu_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, k_fanout)"}))
+                {"dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_ncu_full_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of one k_fanout "
+                                                             f"launch, ncu --set full on the build of commit {head}; a committed figure, not measured by the run that prints it)"}))
 if (G / "bench.json").exists():
     (out / f"{tag}_bench.json").write_text((G / "bench.json").read_text())
 print("wrote", sorted(p.name for p in out.iterdir()))
