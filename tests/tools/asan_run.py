@@ -41,5 +41,43 @@ ctx.set_users(users["room"], users["flags"], users["level"], 2)
 st = ctx.write_batch(ops)
 eoff, data, nd = port.write_batch(ops, users)
 assert (st.off == eoff).all() and (st.data == data).all()
+# round 2 kernels: the warp matcher across its staging windows (pieces beyond the window, empty strings, a one-string
+# call), the digest kernels, the ban matchers, two room shards behind nutsb_multi
+from test_swear_warp import _case as swear_case, LISTS
+from test_multi import make_case
+for wl in LISTS[:4]:
+    ctx.set_swear_words(wl)
+    for n, maxlen in ((70, 60), (40, 400), (1, 50), (33, 0), (3, 999)):
+        strs = swear_case(rng, n, maxlen, wl)
+        if n > 40: strs[3] = b""; strs[35] = b""
+        t2, o2 = O.pack(strs)
+        assert (ctx.contains_swearing_batch(t2, o2) == port.contains_swearing_batch(t2, o2, wl)).all()
+c = make_case(91, 24, 3, 150)
+o, us = c["ops"], c["users"]
+pu, po = port.delivery_digests(o, us, verdict=o["verdict"])
+ctx.set_users(us["room"], us["flags"], us["level"], c["n_rooms"])
+ctx.write_batch(o)
+du, do = ctx.delivery_digests(len(o["kind"]))
+assert (du == pu).all() and (do == po).all()
+off, data, nd = port.write_batch(o, us, verdict=o["verdict"])
+def fnv(b):
+    h = 0xcbf29ce484222325
+    for x in b: h = ((h * 0x100000001b3) + x) & 0xFFFFFFFFFFFFFFFF
+    return h
+sd = np.array([fnv(data[int(off[u]):int(off[u + 1])].tobytes()) for u in range(24)], np.uint64)
+assert (ctx.stream_digests() == sd).all()
+sf, uf = synth.ban_file(0, 50, 300, 300, False), synth.ban_file(1, 50, 300, 300, True)
+ctx.set_ban_files(sf, uf)
+stx, sox = synth.sites(300)
+ntx, nox = synth.names(300)
+assert (ctx.site_banned_batch(stx, sox) == port.ban_batch(0, sf, stx, sox)).all()
+assert (ctx.user_banned_batch(ntx, nox) == port.ban_batch(1, uf, ntx, nox)).all()
 ctx.close()
+m = api.MultiContext([0, 0], lib)
+m.set_users(us["room"], us["flags"], us["level"], c["n_rooms"])
+got, total, deliv = m.write_batch(o)
+assert total == int(off[-1]) and all(got[u] == data[int(off[u]):int(off[u + 1])].tobytes() for u in range(24))
+m.write_batch(o, keep=True)
+assert (m.stream_digests() == sd).all()
+m.close()
 print("asan run ok")
