@@ -34,9 +34,10 @@ struct HBuf {                        // growable pinned host buffer
 
 struct AcHost {
     std::vector<u32> trans; u8 clsmap[256]; u32 ncls = 1, nstates = 1, root_match = 0;
-    std::vector<u16> tr16; u8 cls2[256]; u32 thresh = 0x10000u, maxpat = 0;     // k_ac_warp's form (empty: does not fit)
+    std::vector<u16> tr16; u8 cls2[256]; u32 thresh = 0x10000u, maxpat = 0;     // the one-byte compact form (empty: does not fit)
+    std::vector<u16> t2; u16 clsA[256]; u8 clsB[256]; u32 t2_rs = 0;            // k_ac_pair's form (empty: does not fit)
 };
-struct AcDev { DBuf trans, clsmap, tr16, cls2; AcView view{}; bool present = false; };
+struct AcDev { DBuf trans, clsmap, tr16, cls2, t2, clsA, clsB; AcView view{}; bool present = false; };
 struct SetDev { DBuf slot_off, slot_len, pool; SetView view{}; bool present = false; };
 
 struct ClassSet {                    // one class granularity (with / without level)
@@ -300,7 +301,7 @@ static void build_ac(const std::vector<std::string> &pats, bool fold_case, AcHos
         const u32 t = (u32)go[i];
         ac.trans[i] = t | (match[t] ? 0x80000000u : 0u);
     }
-    // k_ac_warp's form: states renumbered with the match states last (the root stays 0: it is a match state only for an
+    // the one-byte compact form: states renumbered with the match states last (the root stays 0: it is a match state only for an
     // empty pattern, which root_match covers), entries = byte offset of the target's row, classes pre-doubled
     ac.tr16.clear(); ac.maxpat = 0; ac.thresh = 0x10000u;
     for (auto &p : pats) ac.maxpat = std::max<u32>(ac.maxpat, (u32)p.size());
@@ -313,6 +314,26 @@ static void build_ac(const std::vector<std::string> &pats, bool fold_case, AcHos
         for (u32 st = 0; st < ns; ++st)
             for (u32 cc = 0; cc < nc; ++cc) ac.tr16[(size_t)newid[st] * nc + cc] = (u16)(newid[(u32)go[(size_t)st * nc + cc]] * nc * 2);
         for (int b = 0; b < 256; ++b) ac.cls2[b] = (u8)(2 * ac.clsmap[b]);
+    }
+    // k_ac_pair's form: the table squared (two bytes a step), rows padded to a power of two so that row | column is the
+    // entry's byte offset; bits 14 / 15 of an entry flag a match state after the first / the second byte.  It leans on
+    // the one-byte form for its second looks, and has to fit 16 KB (14 bits of row offset).
+    ac.t2.clear(); ac.t2_rs = 0;
+    if (!ac.tr16.empty()) {
+        u32 rs = 4; while (rs < 2 * nc * nc) rs <<= 1;
+        if ((u64)ns * rs <= 0x4000u) {
+            ac.t2_rs = rs;
+            ac.t2.assign((size_t)ns * (rs / 2), 0);
+            for (u32 st = 0; st < ns; ++st)
+                for (u32 a = 0; a < nc; ++a) {
+                    const u32 mid = (u32)go[(size_t)st * nc + a];
+                    for (u32 b = 0; b < nc; ++b) {
+                        const u32 fin = (u32)go[(size_t)mid * nc + b];
+                        ac.t2[(size_t)st * (rs / 2) + a * nc + b] = (u16)(fin * rs | (mid && match[mid] ? 0x4000u : 0u) | (fin && match[fin] ? 0x8000u : 0u));
+                    }
+                }
+            for (int b = 0; b < 256; ++b) { ac.clsA[b] = (u16)(2 * nc * ac.clsmap[b]); ac.clsB[b] = (u8)(2 * ac.clsmap[b]); }
+        }
     }
 }
 
@@ -327,6 +348,13 @@ static int upload_ac(nutsb_ctx *c, const AcHost &h, AcDev &d)
         TRY(upload(c, d.tr16, h.tr16.data(), h.tr16.size() * sizeof(u16)));
         TRY(upload(c, d.cls2, h.cls2, 256));
         d.view.tr16 = d.tr16.as<u16>(); d.view.cls2 = d.cls2.as<u8>();
+    }
+    d.view.t2 = nullptr; d.view.clsA = nullptr; d.view.clsB = nullptr; d.view.t2_rs = h.t2_rs;
+    if (!h.t2.empty()) {
+        TRY(upload(c, d.t2, h.t2.data(), h.t2.size() * sizeof(u16)));
+        TRY(upload(c, d.clsA, h.clsA, sizeof h.clsA));
+        TRY(upload(c, d.clsB, h.clsB, 256));
+        d.view.t2 = d.t2.as<u16>(); d.view.clsA = d.clsA.as<u16>(); d.view.clsB = d.clsB.as<u8>();
     }
     d.present = true;
     CK(cudaStreamSynchronize(c->stream));
@@ -435,7 +463,8 @@ NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
         CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_FAN_SMEM));
         CK(cudaFuncSetAttribute(k_fanout_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_FD_SMEM));
         CK(cudaFuncSetAttribute(k_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_DIR_SMEM));
-        CK(cudaFuncSetAttribute(k_ac_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_ACW_SMEM(2 * NUTSB_AC_SMEM_ENTRIES)));
+        CK(cudaFuncSetAttribute(k_ac_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_ACP_SMEM(0x4000)));
+        CK(cudaFuncSetAttribute(k_ac_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NUTSB_ACP_SMEM(2 * NUTSB_AC_SMEM_ENTRIES)));
         u8 tab[NUTSB_CODETAB_BYTES]; build_codetab(tab);
         TRY(upload(c, c->d_codetab, tab, sizeof tab));
         TRY(ensure(c, c->d_status, 64)); TRY(ensure(c, c->d_counts, 64)); TRY(ensure(c, c->d_sizes, sizeof(Sizes)));
@@ -1275,12 +1304,16 @@ NUTSB_API int nutsb_write_batch_keep(nutsb_ctx *c, const nutsb_ops *o, nutsb_str
 static int run_ac(nutsb_ctx *c, const AcDev &ac, i64 n, const u8 *bytes, const u64 *off, u8 *verdict)
 {
     if (n == 0) return NUTSB_OK;
-    if (ac.view.tr16 && ac.view.maxpat <= 256) {                   // the warp-cooperative form: 4 blocks of ~50 KB per SM
-        const u32 tr_bytes = (ac.view.nstates * ac.view.ncls * 2u + 15u) & ~15u;
-        const u32 smem = NUTSB_ACW_SMEM(tr_bytes);
-        const u32 per_sm = std::max(1u, std::min(8u, (227u * 1024u) / (smem + 1024u)));     // resident blocks per SM
+    if (ac.view.tr16 && ac.view.maxpat <= 256) {                   // the warp-cooperative form
+        // no string-start mask (k_ac_pair): two bytes a step when the squared table fits 16 KB, else one
+        const bool pair = ac.view.t2 != nullptr;
+        const u32 tb = ((pair ? ac.view.nstates * ac.view.t2_rs : ac.view.nstates * ac.view.ncls * 2u) + 15u) & ~15u;
+        const u32 smem = NUTSB_ACP_SMEM(tb);
+        const u32 per_sm = std::max(1u, std::min(8u, (227u * 1024u) / (smem + 1024u)));
         const u32 g = std::min<u32>(cdiv(n, NUTSB_ACW_THREADS), (u32)c->sm_count * per_sm);
-        NUTSB_LAUNCH_SMEM(g, NUTSB_ACW_THREADS, smem, c->stream, k_ac_warp, bytes, off, n, ac.view, tr_bytes, verdict); CKL();
+        if (pair) { NUTSB_LAUNCH_SMEM(g, NUTSB_ACW_THREADS, smem, c->stream, k_ac_pair<true>, bytes, off, n, ac.view, tb, verdict); }
+        else      { NUTSB_LAUNCH_SMEM(g, NUTSB_ACW_THREADS, smem, c->stream, k_ac_pair<false>, bytes, off, n, ac.view, tb, verdict); }
+        CKL();
         return NUTSB_OK;
     }
     const u32 grid = std::min<u32>(cdiv(n, NUTSB_AC_THREADS), (u32)c->sm_count * 8u);

@@ -18,11 +18,16 @@ struct AcView {
     const u8  *clsmap;       // [256] byte -> class (0 = byte absent from every pattern)
     u32 ncls, nstates;
     u32 root_match;          // an empty pattern: every string matches (strstr(s,"") != NULL)
-    // the compact form k_ac_warp walks (null when the automaton does not fit: then k_ac_match runs)
+    // the one-byte compact form k_ac_pair<false> walks (null when the automaton does not fit: then k_ac_match runs)
     const u16 *tr16;         // [nstates][ncls]: BYTE offset of the target state's row; match states have the highest rows
     const u8  *cls2;         // [256] 2 * class
     u32 thresh;              // a row offset >= thresh is a match state's
     u32 maxpat;              // longest pattern, bytes
+    // the two-bytes-a-step form k_ac_pair walks (null when it does not fit 16 KB: short lists only)
+    const u16 *t2;           // [nstates][t2_rs / 2]: entry (a, b) = row offset of delta(delta(s, a), b) | bit14: delta(s, a) is a match state | bit15: the target is
+    const u16 *clsA;         // [256] 2 * ncls * class  (the pair's first byte)
+    const u8  *clsB;         // [256] 2 * class         (its second)
+    u32 t2_rs;               // bytes per row: a power of two >= 2 * ncls * ncls
 };
 
 #define NUTSB_AC_THREADS     256
@@ -98,15 +103,13 @@ k_ac_match(const u8 *text, const u64 *off, i64 n, AcView ac, u8 *verdict)
 // equal pieces BY BYTES, whatever the string lengths.  A lane starts its walk (maxpat - 1) bytes before its
 // piece, in the root state: any match that ends inside the piece lies wholly in what the lane has walked,
 // so every match is found by the lane whose piece it ends in (and a match found in the overlap is a true
-// one as well).  The state falls back to the root at every string start; a hit is credited to the string
-// the walk is in.  The automaton is stored for a five-instruction step: u16 entries that hold the BYTE
-// offset of the next state's row (no multiply), the class table pre-doubled, match states numbered last so
-// that "hit" is a running maximum compared once per string piece.
+// one as well).  The automaton is stored for a short step: u16 entries that hold the BYTE offset of the
+// next state's row (no multiply), the class table pre-doubled, match states numbered last so that "hit" is
+// one comparison of a running maximum per round.  A hit only sets the bit of its text position (one
+// shared-memory atomic); whose string it is gets settled after the walk by the string's own lane.
 #define NUTSB_ACW_THREADS 256
-#define NUTSB_ACW_WIN     2560                     // text bytes staged per warp (32 strings of 80 bytes), and as many mask bytes
-// dynamic shared memory: the table (tr_bytes, a multiple of 16), the class table, the warps' windows and string starts
+#define NUTSB_ACW_WIN     2560                     // text bytes staged per warp (32 strings of 80 bytes)
 #define NUTSB_ACW_HITW    ((NUTSB_ACW_WIN + 48) / 32 + 1)                  // words of the per-warp hit bitmap
-#define NUTSB_ACW_SMEM(tr_bytes) ((tr_bytes) + 256 + (NUTSB_ACW_THREADS / 32) * (2 * (NUTSB_ACW_WIN + 48) + 34 * 4 + 4 * NUTSB_ACW_HITW))
 
 __device__ __forceinline__ u32 nutsb_acw_walk(const u8 *p, const u8 *e, const u8 *s_trb, const u8 *s_cls2, u32 &st)
 {
@@ -118,24 +121,59 @@ __device__ __forceinline__ u32 nutsb_acw_walk(const u8 *p, const u8 *e, const u8
     return acc;
 }
 
+// ---- no reset at string starts; two bytes a step ----------------------------------------------
+// The walk's time goes into the chain of dependent table lookups (one per byte); a mask that reset the state at
+// every string start (round 2's first form of this kernel) cost a second staged array and a third of the
+// instructions on top.  Both are cut down:
+//   * for a short word list the table is squared -- entry (s, a, b) is the state after the two bytes a b, with two
+//     flag bits for "the state in between is a match state" and "the target is": half the dependent lookups, 16 KB
+//     at most (PAIR; the 64-word list of config 3 does not fit and walks the one-byte table);
+//   * the state is NOT reset at string starts.  A match found that way is a true occurrence in the packed text; it
+//     belongs to string i iff it also STARTS at or after the string's first byte, and a pattern is at most maxpat
+//     bytes, so a hit at least maxpat - 1 bytes into the string is good as it stands.  Only a hit inside a string's
+//     first maxpat - 1 bytes can reach back into the previous string: the string's own lane settles that after the
+//     walk by walking those few bytes again from the root (rare: the packed text has to break inside a word).
+#define NUTSB_ACP_SMEM(t2_bytes) ((t2_bytes) + 512 + 256 + (NUTSB_ACW_THREADS / 32) * ((NUTSB_ACW_WIN + 48) + 34 * 4 + 4 * NUTSB_ACW_HITW))
+
+__device__ __forceinline__ u32 nutsb_bits_any(const u32 *hits, u32 a0, u32 a1)              // any bit in [a0, a1) ?
+{
+    u32 any = 0;
+    for (u32 wd = a0 >> 5; a1 > a0 && wd <= (a1 - 1) >> 5; ++wd) {
+        u32 bits = hits[wd];
+        if (wd == a0 >> 5) bits &= 0xffffffffu << (a0 & 31u);
+        if (wd == (a1 - 1) >> 5) bits &= 0xffffffffu >> (31u - ((a1 - 1) & 31u));
+        any |= bits;
+    }
+    return any;
+}
+
+// PAIR: the squared table; !PAIR: the one-byte table (tr16) walked the same way (no string-start mask, half the
+// shared memory), for lists whose squared table does not fit.
+template <bool PAIR>
 __global__ void __launch_bounds__(NUTSB_ACW_THREADS)
-k_ac_warp(const u8 *text, const u64 *off, i64 n, AcView ac, u32 tr_bytes, u8 *verdict)
+k_ac_pair(const u8 *text, const u64 *off, i64 n, AcView ac, u32 t2_bytes, u8 *verdict)
 {
     NUTSB_DYN_SMEM(smem);
-    u8 *const s_trb = smem;                                              // the transition table, bytes
-    u8 *const s_cls2 = smem + tr_bytes;
-    u8 *const s_stage_all = s_cls2 + 256;
+    u8 *const s_t2 = smem;                                               // (!PAIR: the one-byte table, t2_bytes its size)
+    u16 *const s_clsA = (u16 *)(smem + t2_bytes);
+    u8 *const s_clsB = smem + t2_bytes + 512;
+    u8 *const s_cls2 = smem + t2_bytes;                                  // (!PAIR)
+    u8 *const s_stage_all = s_clsB + 256;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u8 *const stage = s_stage_all + warp * 2 * (NUTSB_ACW_WIN + 48);
-    u8 *const pm = stage + NUTSB_ACW_WIN + 48;
-    u32 *const s_p0 = (u32 *)(s_stage_all + (NUTSB_ACW_THREADS / 32) * 2 * (NUTSB_ACW_WIN + 48)) + warp * (34 + NUTSB_ACW_HITW);
+    u8 *const stage = s_stage_all + warp * (NUTSB_ACW_WIN + 48);
+    u32 *const s_p0 = (u32 *)(s_stage_all + (NUTSB_ACW_THREADS / 32) * (NUTSB_ACW_WIN + 48)) + warp * (34 + NUTSB_ACW_HITW);
     u32 *const hits = s_p0 + 34;
-    {
+    if (PAIR) {
+        const u32 cnt = ac.nstates * (ac.t2_rs >> 1);
+        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) ((u16 *)s_t2)[i] = ac.t2[i];
+        for (u32 i = threadIdx.x; i < 256; i += blockDim.x) { s_clsA[i] = ac.clsA[i]; s_clsB[i] = ac.clsB[i]; }
+    } else {
         const u32 cnt = ac.nstates * ac.ncls;
-        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) ((u16 *)s_trb)[i] = ac.tr16[i];
+        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) ((u16 *)s_t2)[i] = ac.tr16[i];
         for (u32 i = threadIdx.x; i < 256; i += blockDim.x) s_cls2[i] = ac.cls2[i];
     }
     __syncthreads();
+    const u8 *const g_trb = (const u8 *)ac.tr16;                          // the one-byte table, for the rare second looks
     const u32 ov = ac.maxpat ? ac.maxpat - 1 : 0;
     const i64 ntask = (n + 31) >> 5;
     for (i64 task = (i64)blockIdx.x * (NUTSB_ACW_THREADS / 32) + warp; task < ntask; task += (i64)gridDim.x * (NUTSB_ACW_THREADS / 32)) {
@@ -148,18 +186,17 @@ k_ac_warp(const u8 *text, const u64 *off, i64 n, AcView ac, u32 tr_bytes, u8 *ve
         if (ac.root_match) mask = 0xffffffffu;                           // strstr(s, "") != NULL
         else if (bad) {                                                  // offsets out of order: each string by itself
             u32 st = 0;
-            if ((u32)lane < nops && o1 > o0 && nutsb_acw_walk(text + o0, text + o1, s_trb, s_cls2, st) >= ac.thresh) mask = 1u << lane;
+            if ((u32)lane < nops && o1 > o0 && nutsb_acw_walk(text + o0, text + o1, g_trb, ac.cls2, st) >= ac.thresh) mask = 1u << lane;
         } else {
-            // the warp's strings in one window, or -- when they add up to more than the window -- in several
             for (u32 qa = 0; qa < nops; ) {
                 const u64 b0 = __shfl_sync(NUTSB_FULL, o0, (int)qa);
                 const u8 *pa = (const u8 *)((size_t)(text + b0) & ~(size_t)15);
                 const bool fit = (u32)lane >= qa && (u32)lane < nops && (u64)((text + o1) - pa) <= NUTSB_ACW_WIN;
                 const u32 fm = __ballot_sync(NUTSB_FULL, fit) >> qa;
-                const u32 cnt = fm == 0xffffffffu ? 32u : (u32)__ffs((int)~fm) - 1;   // strings qa .. qa+cnt-1 fit together (fit is monotone)
+                const u32 cnt = fm == 0xffffffffu ? 32u : (u32)__ffs((int)~fm) - 1;
                 if (cnt == 0) {                                          // one string longer than the window: its lane walks it
                     u32 st = 0;
-                    if ((u32)lane == qa && nutsb_acw_walk(text + o0, text + o1, s_trb, s_cls2, st) >= ac.thresh) mask |= 1u << lane;
+                    if ((u32)lane == qa && nutsb_acw_walk(text + o0, text + o1, g_trb, ac.cls2, st) >= ac.thresh) mask |= 1u << lane;
                     ++qa;
                     continue;
                 }
@@ -167,71 +204,65 @@ k_ac_warp(const u8 *text, const u64 *off, i64 n, AcView ac, u32 tr_bytes, u8 *ve
                 const u64 b1 = __shfl_sync(NUTSB_FULL, o1, (int)qb - 1);
                 const u32 span = (u32)((text + b1) - pa);
                 const u32 nvec = (span + 15) >> 4;
-                for (u32 v = lane; v < nvec; v += 32) {
-                    *(uint4 *)(stage + 16 * v) = __ldg((const uint4 *)pa + v);
-                    *(uint4 *)(pm + 16 * v) = make_uint4(~0u, ~0u, ~0u, ~0u);
-                }
+                for (u32 v = lane; v < nvec; v += 32) *(uint4 *)(stage + 16 * v) = __ldg((const uint4 *)pa + v);
                 for (u32 v = lane; v < (NUTSB_ACW_WIN + 48) / 32; v += 32) hits[v] = 0;
                 const u32 r0 = (u32)((text + b0) - pa), r1 = span;
-                // s_p0[i] = start of string qa + i in the window, i = 0 .. cnt (the end)
                 if ((u32)lane >= qa && (u32)lane < qb) s_p0[lane - qa] = (u32)((text + o0) - pa);
                 if (lane == 0) s_p0[cnt] = r1;
                 __syncwarp();
-                // string starts as DATA: pm[j] = 0 where a string begins (the state falls back to the root there), 0xff
-                // elsewhere -- a lane meets a string start once in ~64 bytes, but some lane of the warp meets one every
-                // other step, so a branch for it would run all the time
-                if ((u32)lane < cnt) pm[s_p0[lane]] = 0;
-                __syncwarp();
-                // a lane's piece is an ODD number of words: the lanes walk in step, byte i of every piece at once, and
-                // with an odd word stride those 32 bytes sit in 32 different banks (64-byte pieces would share two)
                 const u32 total = r1 - r0;
-                const u32 chunk = 4u * ((((total + 31) >> 5) + 3) >> 2 | 1u);
+                const u32 chunk = 4u * ((((total + 31) >> 5) + 3) >> 2 | 1u);            // an odd number of words (banks)
                 const u32 c0 = r0 + (u32)lane * chunk;
                 u32 c1 = c0 + chunk; if (c1 > r1) c1 = r1;
                 if (c0 < r1) {
-                    // four bytes per round: the text word and the mask word with one load each, the four class lookups
-                    // together, then the four dependent transitions; hits are looked for once per round (a running
-                    // maximum) and, when there is one, the round is walked again byte by byte to credit the right string.
-                    // The walk starts on a word boundary at or before its first byte and ends on one at or after its last:
-                    // the extra bytes only lengthen the overlap (hits outside [r0, r1) are dropped).
+                    // a word a round: its two column offsets are ready before the round starts (they do not depend on the
+                    // state), the round itself is two dependent lookups.  Bytes walked outside [r0, r1) -- word alignment --
+                    // only set hit bits nobody looks at, or lengthen the overlap.
                     const u32 js = (c0 >= r0 + ov ? c0 - ov : r0) & ~3u, je = (c1 + 3) & ~3u;
-                    u32 st = 0;
-                    // (the next round's words and classes are fetched before this round's transitions are walked: they do
-                    // not depend on the state, and the kernel is bound by the latency of the four dependent lookups)
-                    u32 m = *(const u32 *)(pm + js);
-                    u32 k0, k1, k2, k3;
-                    { const u32 w = *(const u32 *)(stage + js);
-                      k0 = s_cls2[w & 0xffu]; k1 = s_cls2[(w >> 8) & 0xffu]; k2 = s_cls2[(w >> 16) & 0xffu]; k3 = s_cls2[w >> 24]; }
-                    for (u32 j = js; j < je; j += 4) {                    // the same trip count in every lane (+-1)
-                        const u32 jn = j + 4 < je ? j + 4 : j;
-                        const u32 wn = *(const u32 *)(stage + jn), mn = *(const u32 *)(pm + jn);
-                        const u32 n0 = s_cls2[wn & 0xffu], n1 = s_cls2[(wn >> 8) & 0xffu], n2 = s_cls2[(wn >> 16) & 0xffu], n3 = s_cls2[wn >> 24];
-                        const u32 s1 = *(const u16 *)(s_trb + (st & __byte_perm(m, 0, 0x4400)) + k0);
-                        const u32 s2 = *(const u16 *)(s_trb + (s1 & __byte_perm(m, 0, 0x4511)) + k1);
-                        const u32 s3 = *(const u16 *)(s_trb + (s2 & __byte_perm(m, 0, 0x4622)) + k2);
-                        st = *(const u16 *)(s_trb + (s3 & __byte_perm(m, 0, 0x4733)) + k3);
-                        m = mn; k0 = n0; k1 = n1; k2 = n2; k3 = n3;
-                        u32 acc = s1 > s2 ? s1 : s2; acc = acc > s3 ? acc : s3; acc = acc > st ? acc : st;
-                        if (acc >= ac.thresh) {
-                            // a hit: only its POSITION is noted here (one bit per text byte, one shared-memory atomic per
-                            // round) -- whose string it is gets settled after the walk, by the string's own lane
-                            const u32 T = ac.thresh;
-                            const u32 hb = (s1 >= T ? 1u : 0u) | (s2 >= T ? 2u : 0u) | (s3 >= T ? 4u : 0u) | (st >= T ? 8u : 0u);
-                            atomicOr(&hits[j >> 5], hb << (j & 31u));     // (j is a multiple of 4: the four bits stay in one word)
+                    u32 st = 0, k01, k23;
+                    if (!PAIR) {
+                        u32 k0, k1, k2, k3;
+                        { const u32 w = *(const u32 *)(stage + js);
+                          k0 = s_cls2[w & 0xffu]; k1 = s_cls2[(w >> 8) & 0xffu]; k2 = s_cls2[(w >> 16) & 0xffu]; k3 = s_cls2[w >> 24]; }
+                        const u32 T = ac.thresh;
+                        for (u32 j = js; j < je; j += 4) {
+                            const u32 jn = j + 4 < je ? j + 4 : j;
+                            const u32 wn = *(const u32 *)(stage + jn);
+                            const u32 n0 = s_cls2[wn & 0xffu], n1 = s_cls2[(wn >> 8) & 0xffu], n2 = s_cls2[(wn >> 16) & 0xffu], n3 = s_cls2[wn >> 24];
+                            const u32 s1 = *(const u16 *)(s_t2 + st + k0);
+                            const u32 s2 = *(const u16 *)(s_t2 + s1 + k1);
+                            const u32 s3 = *(const u16 *)(s_t2 + s2 + k2);
+                            st = *(const u16 *)(s_t2 + s3 + k3);
+                            k0 = n0; k1 = n1; k2 = n2; k3 = n3;
+                            u32 acc = s1 > s2 ? s1 : s2; acc = acc > s3 ? acc : s3; acc = acc > st ? acc : st;
+                            if (acc >= T)
+                                atomicOr(&hits[j >> 5], ((s1 >= T ? 1u : 0u) | (s2 >= T ? 2u : 0u) | (s3 >= T ? 4u : 0u) | (st >= T ? 8u : 0u)) << (j & 31u));
                         }
+                    } else {
+                    { const u32 w = *(const u32 *)(stage + js);
+                      k01 = s_clsA[w & 0xffu] + s_clsB[(w >> 8) & 0xffu]; k23 = s_clsA[(w >> 16) & 0xffu] + s_clsB[w >> 24]; }
+                    for (u32 j = js; j < je; j += 4) {
+                        const u32 jn = j + 4 < je ? j + 4 : j;
+                        const u32 wn = *(const u32 *)(stage + jn);
+                        const u32 n01 = s_clsA[wn & 0xffu] + s_clsB[(wn >> 8) & 0xffu], n23 = s_clsA[(wn >> 16) & 0xffu] + s_clsB[wn >> 24];
+                        const u32 s1 = *(const u16 *)(s_t2 + ((st & 0x3fffu) | k01));
+                        st = *(const u16 *)(s_t2 + ((s1 & 0x3fffu) | k23));
+                        k01 = n01; k23 = n23;
+                        if ((s1 | st) >= 0x4000u)                            // bits 14/15 of the two entries = hits at bytes j .. j+3
+                            atomicOr(&hits[j >> 5], ((s1 >> 14) | ((st >> 14) << 2)) << (j & 31u));
+                    }
                     }
                 }
                 __syncwarp();
-                if ((u32)lane < cnt) {                                    // lane i: any hit inside string qa + i ?
+                if ((u32)lane < cnt) {                                    // lane i: string qa + i
                     const u32 a0 = s_p0[lane], a1 = s_p0[lane + 1];
-                    u32 any = 0;
-                    for (u32 wd = a0 >> 5; a1 > a0 && wd <= (a1 - 1) >> 5; ++wd) {
-                        u32 bits = hits[wd];
-                        if (wd == a0 >> 5) bits &= 0xffffffffu << (a0 & 31u);
-                        if (wd == (a1 - 1) >> 5) bits &= 0xffffffffu >> (31u - ((a1 - 1) & 31u));
-                        any |= bits;
+                    const u32 am = a0 + ov < a1 ? a0 + ov : a1;           // hits from here on lie wholly inside the string
+                    bool hit = nutsb_bits_any(hits, am, a1) != 0;
+                    if (!hit && nutsb_bits_any(hits, a0, am)) {           // a hit in the first maxpat - 1 bytes: from inside, or from the string before?
+                        u32 st = 0;
+                        hit = nutsb_acw_walk(stage + a0, stage + am, g_trb, ac.cls2, st) >= ac.thresh;
                     }
-                    if (any) mask |= 1u << (qa + (u32)lane);
+                    if (hit) mask |= 1u << (qa + (u32)lane);
                 }
                 __syncwarp();
                 qa = qb;

@@ -9,6 +9,6 @@ CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
 NUTSB_OVERLAP=0 $CMD > gpurun_out/plain.log 2>&1 &&
 NUTSB_OVERLAP=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2_launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 NUTSB_OVERLAP=0 $CMD > gpurun_out/plain2.log 2>&1 &&
-NUTSB_OVERLAP=0 ncu --set full --clock-control none --import-source on -k regex:"k_fanout|k_render|k_direct|k_measure|k_ac_warp|k_ac_match|k_set_match|k_plan|k_rs_scatter|k_entry_info" -s 12 -c 14 -f -o gpurun_out/prof_r2_main $CMD > gpurun_out/ncu_full.log 2>&1
+NUTSB_OVERLAP=0 ncu --set full --clock-control none --import-source on -k regex:"k_fanout|k_render|k_direct|k_measure|k_ac_pair|k_ac_match|k_set_match|k_plan|k_rs_scatter|k_entry_info" -s 12 -c 14 -f -o gpurun_out/prof_r2_main $CMD > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 python scripts/show_list.py gpurun_out/r2_launches.csv | sort -rn | head -12

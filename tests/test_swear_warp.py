@@ -1,4 +1,4 @@
-"""contains_swearing's warp-cooperative matcher (k_ac_warp, nutsb_match.cuh) against the oracle restatement of
+"""contains_swearing's warp-cooperative matcher (k_ac_pair, nutsb_match.cuh) against the oracle restatement of
 nuts333.c:2540-2559: a warp's 32 strings are one piece of text cut into 32 equal pieces by bytes, so matches that
 straddle two lanes' pieces, strings that start or end inside a piece, empty strings, pieces larger than the staging
 window and pattern lists of every shape all have to come out as strstr() would have it."""
@@ -36,13 +36,30 @@ LISTS = [
 ]
 
 
+def _cut_case(rng, n, words):
+    """One long text full of list words, cut into n strings at random places: words broken across two (or, with empty
+    and one-byte strings, several) strings must not be found, words whole at a string's very start or end must be."""
+    ws = [w.encode() for w in words if w not in ("*", "")] or [b"q"]
+    parts, have = [], 0
+    fill = [b"a", b"b ", b"xh", b" ", b"h", b"ab x", b"x"]
+    pick = rng.integers(0, 1 << 30, 12 * n + 8)
+    while have < 12 * n:
+        r = int(pick[len(parts)])
+        parts.append(ws[(r >> 8) % len(ws)] if (r & 255) < 154 else fill[(r >> 8) % len(fill)])
+        have += len(parts[-1])
+    text = b"".join(parts)
+    cuts = np.sort(rng.integers(0, len(text) + 1, n - 1))
+    cuts = [0] + cuts.tolist() + [len(text)]
+    return [text[cuts[i]:cuts[i + 1]] for i in range(n)]
+
+
 def _check(ctx, port, seed, sizes):
     rng = np.random.default_rng(seed)
     for words in LISTS + [synth.swear_words(64)]:
         ctx.set_swear_words(words)
         for n, maxlen in sizes:
-            strs = _case(rng, n, maxlen, words)
-            if n > 40:
+            strs = _case(rng, n, maxlen, words) if maxlen >= 0 else _cut_case(rng, n, words)
+            if n > 40 and maxlen >= 0:
                 strs[3] = b""; strs[4] = b""; strs[35] = b""          # empty strings inside and at the edge of a warp's piece
             text, off = O.pack(strs)
             got = ctx.contains_swearing_batch(text, off)
@@ -53,12 +70,14 @@ def _check(ctx, port, seed, sizes):
 
 
 def test_warp_matcher_on_emulator(sim_lib, port):
+    # 70 strings of <= 60 bytes: staged pieces; 40 of <= 400: pieces beyond the 3 KB window (one string per lane);
+    # (n, -1): one text cut into n strings at random places.  The short lists walk the squared table (two bytes a
+    # step), the 64-word list the one-byte table.
     ctx = api.Context(0, sim_lib)
-    # 70 strings of <= 60 bytes: staged pieces; 40 of <= 400: pieces beyond the 3 KB window (one string per lane)
-    _check(ctx, port, 3, [(70, 60), (33, 5), (40, 400)])
+    _check(ctx, port, 3, [(70, 60), (33, 5), (40, 400), (90, -1), (300, -1)])
     ctx.close()
 
 
 @pytest.mark.gpu
 def test_warp_matcher_on_gpu(gpu_ctx, port):
-    _check(gpu_ctx, port, 4, [(20000, 90), (5000, 12), (3000, 999), (31, 200), (1, 50)])
+    _check(gpu_ctx, port, 4, [(20000, 90), (5000, 12), (3000, 999), (31, 200), (1, 50), (20000, -1), (777, -1)])
