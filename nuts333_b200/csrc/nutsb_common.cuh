@@ -178,7 +178,9 @@ k_scan_apply(In in, Out out, i64 n_host, const u32 *n_dev, const u64 *block_sums
 // aggregate there when the writer has moved on to "inclusive")
 struct ScanState { unsigned long long flag, aggregate, inclusive, pad_; };
 
-template <class In, class Out>
+// ITEMS elements per thread: 16 for a long input, 1 for a short one (<= 16k elements: more blocks, each thread waits
+// for one input value instead of sixteen -- the per-user stream length is a chain of five dependent loads).
+template <class In, class Out, int ITEMS>
 __global__ void __launch_bounds__(NUTSB_SCAN_THREADS)
 k_scan1(In in, Out out, i64 n_host, const u32 *n_dev, ScanState *state, u32 *ticket, u32 epoch, u32 nb)
 {
@@ -188,40 +190,79 @@ k_scan1(In in, Out out, i64 n_host, const u32 *n_dev, ScanState *state, u32 *tic
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const u32 tile = s_tile;
-    const i64 base = (i64)tile * NUTSB_SCAN_TILE + (i64)threadIdx.x * NUTSB_SCAN_ITEMS;
-    u64 v[NUTSB_SCAN_ITEMS], s = 0;
-    for (int k = 0; k < NUTSB_SCAN_ITEMS; ++k) { const i64 i = base + k; v[k] = i < n ? in(i) : 0; s += v[k]; }
+    // the tile goes through shared memory both ways: element tid + 256 k is read / written by thread tid (coalesced),
+    // elements 16 tid .. 16 tid + 15 are scanned by thread tid (one pad word per 16 keeps both patterns off each
+    // other's banks).  With each thread reading and writing its own 16 consecutive elements straight from / to global
+    // memory every load touched 32 sectors for 4 bytes each, and the 3M-element scan took 40 us.
+    __shared__ u64 s_val[ITEMS > 1 ? NUTSB_SCAN_THREADS * (ITEMS + 1) : 1];
+    const i64 tbase = (i64)tile * (NUTSB_SCAN_THREADS * ITEMS);
+    u64 v[ITEMS], s = 0;
+    if (ITEMS > 1) {
+        for (int k = 0; k < ITEMS; ++k) {                                  // (all the loads first, then the stores)
+            const i64 i = tbase + (i64)k * NUTSB_SCAN_THREADS + threadIdx.x;
+            v[k] = i < n ? in(i) : 0;
+        }
+        for (int k = 0; k < ITEMS; ++k) {
+            const u32 j = (u32)k * NUTSB_SCAN_THREADS + threadIdx.x;
+            s_val[j + j / ITEMS] = v[k];
+        }
+        __syncthreads();
+        for (int k = 0; k < ITEMS; ++k) { v[k] = s_val[threadIdx.x * (ITEMS + 1) + k]; s += v[k]; }
+    } else {
+        const i64 i = tbase + threadIdx.x;
+        v[0] = s = i < n ? in(i) : 0;
+    }
     u64 total;
     u64 ex = nutsb_block_excl_scan(s, &total);
-    if (threadIdx.x < 32) {
-        // look-back by the block's first warp, 32 tiles at a time: lane l looks at tile (hi - 1 - l); the window's sum is
-        // everything up to and including the nearest tile that already knows its inclusive prefix
+    {
+        // look-back by the whole block, 256 tiles at a time: thread i looks at tile (hi - 1 - i); the window's sum is
+        // everything up to and including the nearest tile that already knows its inclusive prefix.  (One warp and 32
+        // tiles a step was the first form: the prefix then travels 32 tiles per global-memory round trip, ~25 trips
+        // for the 733 tiles of a 3M-element scan.)
+        __shared__ u32 s_incl[NUTSB_SCAN_THREADS / 32];
+        __shared__ u64 s_part[NUTSB_SCAN_THREADS / 32];
         const unsigned long long fa = ((unsigned long long)epoch << 2) | 1ull, fi = ((unsigned long long)epoch << 2) | 2ull;
         volatile ScanState *st = state;
-        const int lane = (int)threadIdx.x;
-        u64 before = 0;
+        const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+        u64 before = 0;                                                    // (thread 0's copy is the one that counts)
         if (tile > 0) {
-            if (lane == 0) { st[tile].aggregate = total; __threadfence(); st[tile].flag = fa; }   // my aggregate, for the tiles after me
+            if (threadIdx.x == 0) { st[tile].aggregate = total; __threadfence(); st[tile].flag = fa; }   // my aggregate, for the tiles after me
             for (u32 hi = tile; hi > 0; ) {
-                const bool have = (u32)lane < hi;
-                const u32 t = have ? hi - 1 - (u32)lane : 0;
+                const bool have = threadIdx.x < hi;
+                const u32 t = have ? hi - 1 - threadIdx.x : 0;
                 unsigned long long f = fi;
                 if (have) do { f = st[t].flag; } while (f != fa && f != fi);              // (tiles before me were started before me)
                 __threadfence();
                 const u32 incl = __ballot_sync(NUTSB_FULL, have && f == fi);
-                const int stop = incl ? __ffs((int)incl) - 1 : 31;                          // nearest inclusive tile in the window
-                u64 v = (have && lane <= stop) ? (f == fi ? st[t].inclusive : st[t].aggregate) : 0;
-                for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(NUTSB_FULL, v, d);
-                before += v;
-                if (incl) break;
-                hi = hi > 32 ? hi - 32 : 0;
+                if (lane == 0) s_incl[warp] = incl;
+                __syncthreads();
+                int stop = NUTSB_SCAN_THREADS;                                            // nearest inclusive tile in the window
+                for (int w = NUTSB_SCAN_THREADS / 32 - 1; w >= 0; --w) if (s_incl[w]) stop = 32 * w + __ffs((int)s_incl[w]) - 1;
+                u64 pv = (have && (int)threadIdx.x <= stop) ? (f == fi ? st[t].inclusive : st[t].aggregate) : 0;
+                for (int d = 16; d; d >>= 1) pv += __shfl_xor_sync(NUTSB_FULL, pv, d);
+                if (lane == 0) s_part[warp] = pv;
+                __syncthreads();
+                if (threadIdx.x == 0) for (int w = 0; w < NUTSB_SCAN_THREADS / 32; ++w) before += s_part[w];
+                if (stop < NUTSB_SCAN_THREADS) break;                                     // (the same in every thread)
+                hi = hi > NUTSB_SCAN_THREADS ? hi - NUTSB_SCAN_THREADS : 0;
             }
         }
-        if (lane == 0) { st[tile].inclusive = before + total; __threadfence(); st[tile].flag = fi; s_before = before; }
+        if (threadIdx.x == 0) { st[tile].inclusive = before + total; __threadfence(); st[tile].flag = fi; s_before = before; }
     }
     __syncthreads();
     ex += s_before;
-    for (int k = 0; k < NUTSB_SCAN_ITEMS; ++k) { const i64 i = base + k; if (i <= n) out(i, ex); ex += v[k]; }   // out(n) = total
+    if (ITEMS > 1) {
+        for (int k = 0; k < ITEMS; ++k) { s_val[threadIdx.x * (ITEMS + 1) + k] = ex; ex += v[k]; }
+        __syncthreads();
+        for (int k = 0; k < ITEMS; ++k) {
+            const u32 j = (u32)k * NUTSB_SCAN_THREADS + threadIdx.x;
+            const i64 i = tbase + j;
+            if (i <= n) out(i, s_val[j + j / ITEMS]);                                     // out(n) = total
+        }
+    } else {
+        const i64 i = tbase + threadIdx.x;
+        if (i <= n) out(i, ex);
+    }
     // the last block to get here puts the ticket back for the next scan
     __syncthreads();
     if (threadIdx.x == 0) { __threadfence(); if (atomicAdd(ticket + 1, 1u) == nb - 1) { ticket[0] = 0; ticket[1] = 0; } }

@@ -200,7 +200,8 @@ struct InClassLen {                 // bytes class column j receives from slab o
 template <class In, class Out>
 static int run_scan(nutsb_ctx *c, In in, Out out, i64 n_upper, const u32 *n_dev)
 {
-    const u32 nb = cdiv((u64)n_upper + 1, NUTSB_SCAN_TILE);
+    const bool small = (u64)n_upper + 1 <= 16384u;                 // 64 tiles of 256: one look-back window
+    const u32 nb = cdiv((u64)n_upper + 1, small ? NUTSB_SCAN_THREADS : NUTSB_SCAN_TILE);
     TRY(ensure(c, c->d_sums, ((size_t)nb + 1) * sizeof(ScanState)));
     if (!c->d_scan_ticket.p) { TRY(ensure(c, c->d_scan_ticket, 64)); CK(cudaMemsetAsync(c->d_scan_ticket.p, 0, 64, c->stream)); }
     if (c->d_sums.p != c->scan_state_seen || c->d_sums.cap != c->scan_state_cap) {     // a fresh (re)allocation: whatever it holds must not look like a flag
@@ -208,8 +209,13 @@ static int run_scan(nutsb_ctx *c, In in, Out out, i64 n_upper, const u32 *n_dev)
         c->scan_state_seen = c->d_sums.p; c->scan_state_cap = c->d_sums.cap;
     }
     if (++c->scan_epoch >= 0x3fffffffu) { c->scan_epoch = 1; CK(cudaMemsetAsync(c->d_sums.p, 0, c->d_sums.cap, c->stream)); }
-    auto k1 = k_scan1<In, Out>;
-    NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, k1, in, out, n_upper, n_dev, c->d_sums.as<ScanState>(), c->d_scan_ticket.as<u32>(), c->scan_epoch, nb); CKL();
+    if (small) {
+        auto k1 = k_scan1<In, Out, 1>;
+        NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, k1, in, out, n_upper, n_dev, c->d_sums.as<ScanState>(), c->d_scan_ticket.as<u32>(), c->scan_epoch, nb); CKL();
+    } else {
+        auto k1 = k_scan1<In, Out, NUTSB_SCAN_ITEMS>;
+        NUTSB_LAUNCH(nb, NUTSB_SCAN_THREADS, c->stream, k1, in, out, n_upper, n_dev, c->d_sums.as<ScanState>(), c->d_scan_ticket.as<u32>(), c->scan_epoch, nb); CKL();
+    }
     c->tm.launches += 1;
     return NUTSB_OK;
 }
