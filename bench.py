@@ -865,7 +865,7 @@ def run_config(args):
         ctx.close()
     else:                                                        # c5
         UT, UPR, MT = args.c5_users, 100, args.c5_msgs
-        CH = min(1_000_000 * world, MT)                          # a chunk = 1M messages per GPU: the same HBM per GPU at every N
+        CH = min(args.c5_chunk * world, MT)                      # a chunk = --c5-chunk messages per GPU
         n_chunks = (MT + CH - 1) // CH
         users, n_rooms = synth.users(UT, UPR)
         m = api.MultiContext(rank=(world, rank, local))
@@ -964,8 +964,8 @@ def run_config(args):
         line = dict(metric=METRIC, value=float(sm[0]) / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="u8", data="synthetic",
                     config=dict(workload="C5: full pipeline, %d msgs x %d users (%d rooms of %d): admission (site_banned | user_banned, %d-entry lists) -> "
-                                         "contains_swearing (%d words) -> say() render + fan-out, in %d message-ordered chunks (1M messages per GPU each); one step = the whole job"
-                                         % (MT, UT, n_rooms, UPR, N_BAN_ENTRIES, N_SWEAR, n_chunks),
+                                         "contains_swearing (%d words) -> say() render + fan-out, in %d message-ordered chunks (%d messages per GPU each); one step = the whole job"
+                                         % (MT, UT, n_rooms, UPR, N_BAN_ENTRIES, N_SWEAR, n_chunks, args.c5_chunk),
                                 sharding="rooms dealt to the GPUs by nutsb_multi (the library's sharder), streams stay in HBM; swear / ban batches split by "
                                          "index range and their verdict bytes gathered (NCCL all_gather: the only cross-rank traffic)",
                                 l2="per chunk and GPU: inputs and outputs far beyond the 126 MB L2",
@@ -999,6 +999,8 @@ def main():
     ap.add_argument("--config", default="c3c4", choices=["c3c4", "c2", "c4", "c5"],
                     help="c3c4 (default): the headline workload; c2 / c4 / c5: the other BASELINE configs, one line each")
     ap.add_argument("--c5-msgs", type=int, default=10_000_000)
+    ap.add_argument("--c5-chunk", type=int, default=10_000_000,
+                    help="config 5: messages per GPU in one chunk = one write batch (default: the whole job in one; 1000000 = the same HBM per GPU at every N)")
     ap.add_argument("--c5-users", type=int, default=100_000)
     args = ap.parse_args()
     if args.impl == "reference":

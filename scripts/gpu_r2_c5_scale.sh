@@ -1,8 +1,8 @@
-# round 2: config 5 at N GPUs (strong scaling) and the default bench at N GPUs
+# round 2: config 5 at N GPUs (strong scaling, chunks of 1M messages per GPU) and the default bench at N GPUs
 N=${N:-8}
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --config c5 --gpus $N --steps 2 --warmup 3 2> gpurun_out/r2_bench_c5_${N}gpu.err | tail -n 1 > gpurun_out/r2_bench_c5_${N}gpu.json; echo "c5 rc=$?"
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --config c5 --c5-chunk 1000000 --gpus $N --steps 2 --warmup 3 2> gpurun_out/r2_bench_c5_${N}gpu.err | tail -n 1 > gpurun_out/r2_bench_c5_${N}gpu.json; echo "c5 rc=$?"
 python -c "
 import json; d=json.load(open('gpurun_out/r2_bench_c5_${N}gpu.json')); print(d['n_gpus'], d['value'], d['ms_per_step'], d['config']['digest_checksum'], d['config']['deliveries_per_job'])"
 if [ -n "$DEFAULT" ]; then
