@@ -167,20 +167,22 @@ def test_flat_renderer_fuzz_vs_oracle(sim_lib, port):
 
 
 def test_long_scan_tiles(sim_lib, port):
-    """More ops than one short-scan launch covers (16k elements): the per-op scans take the 16-items-per-thread
-    form of k_scan1 -- tiles through shared memory, several tiles of look-back."""
-    n, U = 17000, 6
-    rng = np.random.default_rng(5)
-    texts = [b"x" * int(k) for k in rng.integers(0, 3, n)]
-    texts[7] = b"~FRred\n"; texts[n - 1] = b"last/~ one\n"
-    text, off = O.pack(texts)
-    kind = np.zeros(n, np.uint8); kind[::1000] = 1
-    ops = dict(text=text, off=off, kind=kind, target=np.where(kind == 0, rng.integers(-1, U, n), rng.integers(-1, 2, n)).astype(np.int32),
-               except_user=np.full(n, -1, np.int32), flags=np.zeros(n, np.uint8))
+    """The per-op scans at the edge between the two forms of k_scan1: n + 1 = 16384 elements is the last input of the
+    one-item-per-thread form (64 full tiles), n + 1 = 16385 the first of the 16-items form (tiles through shared
+    memory, several tiles of look-back, a last tile that holds the total alone)."""
+    U = 6
     users = dict(room=np.array([0, 0, 1, 1, 0, -1], np.int32), flags=np.array([1, 0, 1, 0, 5, 1], np.uint8), level=np.ones(U, np.uint8))
     ctx = _ctx(sim_lib)
     ctx.set_users(users["room"], users["flags"], users["level"], 2)
-    st = ctx.write_batch(ops)
-    eoff, data, nd = port.write_batch(ops, users)
-    assert (st.off == eoff).all() and (st.data == data).all() and st.n_deliveries == int(nd.sum())
+    for n in (16383, 16384):
+        rng = np.random.default_rng(n)
+        texts = [b"x" * int(k) for k in rng.integers(0, 3, n)]
+        texts[7] = b"~FRred\n"; texts[n - 1] = b"last/~ one\n"
+        text, off = O.pack(texts)
+        kind = np.zeros(n, np.uint8); kind[::1000] = 1
+        ops = dict(text=text, off=off, kind=kind, target=np.where(kind == 0, rng.integers(-1, U, n), rng.integers(-1, 2, n)).astype(np.int32),
+                   except_user=np.full(n, -1, np.int32), flags=np.zeros(n, np.uint8))
+        st = ctx.write_batch(ops)
+        eoff, data, nd = port.write_batch(ops, users)
+        assert (st.off == eoff).all() and (st.data == data).all() and st.n_deliveries == int(nd.sum()), n
     ctx.close()
