@@ -83,8 +83,10 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const i64 wbase = (i64)blockIdx.x * NUTSB_MEASURE_THREADS + warp * 32;
-    if (wbase >= ops.n) return;                    // whole warp leaves together
+    // persistent blocks: a warp takes 32 ops after 32 ops (the command table is loaded once per block, and a warp that
+    // waits for its loads leaves the issue slots to the others instead of to a block still starting up)
+    u64 s_on = 0, s_off = 0;
+    for (i64 wbase = ((i64)blockIdx.x * (NUTSB_MEASURE_THREADS / 32) + warp) * 32; wbase < ops.n; wbase += (i64)gridDim.x * NUTSB_MEASURE_THREADS) {
     const i64 wend = (wbase + 32 < ops.n) ? wbase + 32 : ops.n;
     const u32 nops = (u32)(wend - wbase);
     const u64 b0 = ops.toff[wbase], b1 = ops.toff[wend];
@@ -175,7 +177,6 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
             }
         }
     }
-    // (no early return: the warp reduces the slab totals together at the end)
     u32 st = 0, lon = 0, loff = 0, rep = 0;
     u32 kind = NUTSB_OP_NONE;
     if (have && bad) { atomicOr(status, NUTSB_ST_BAD_OFFSETS); len_on[i] = len_off[i] = nrep[i] = 0; }
@@ -209,7 +210,9 @@ k_measure(OpsView ops, PopView pop, u32 *len_on, u32 *len_off, u32 *nrep, u32 *s
     // bytes of the slab's two renderings: every (room, op) entry of a room / level op is rendered once per
     // setting.  Known here already, so the slab buffer can be sized at the first read-back.
     const bool slab = rep && kind != NUTSB_OP_USER;
-    u64 s_on = slab ? (u64)lon * rep : 0, s_off = slab ? (u64)loff * rep : 0;
+    if (slab) { s_on += (u64)lon * rep; s_off += (u64)loff * rep; }
+    __syncwarp();                                              // (the staging window and the counters are reused)
+    }
     for (int d = 16; d; d >>= 1) { s_on += __shfl_xor_sync(NUTSB_FULL, s_on, d); s_off += __shfl_xor_sync(NUTSB_FULL, s_off, d); }
     if (lane == 0 && (s_on | s_off)) {                         // NUTSB_SLAB_TOT_WAYS pairs: same-address atomics serialise
         u64 *t = slab_tot + 2 * (blockIdx.x % NUTSB_SLAB_TOT_WAYS);

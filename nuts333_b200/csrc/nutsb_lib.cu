@@ -797,7 +797,7 @@ static int run_write(nutsb_ctx *c, const nutsb_ops *o, nutsb_streams *out, IovRe
     CK(cudaMemsetAsync(c->d_status.p, 0, 64, st));
     CK(cudaMemsetAsync(c->d_counters.p, 0, 1024, st));
     u32 *len_on = c->d_len_on.as<u32>(), *len_off = c->d_len_off.as<u32>(), *nrep = c->d_nrep.as<u32>();
-    NUTSB_LAUNCH(cdiv(n, NUTSB_MEASURE_THREADS), NUTSB_MEASURE_THREADS, st, k_measure, ops, pop0, len_on, len_off, nrep,
+    NUTSB_LAUNCH(std::min<u32>(cdiv(n, NUTSB_MEASURE_THREADS), (u32)c->sm_count * 5u), NUTSB_MEASURE_THREADS, st, k_measure, ops, pop0, len_on, len_off, nrep,
                  c->d_status.as<u32>(), c->d_counters.as<u64>() + 8); CKL();
     c->tm.launches++;
     TRY(run_scan(c, InU32{nrep}, OutU64{c->d_eoff.as<u64>()}, n, nullptr));
