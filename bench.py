@@ -299,7 +299,7 @@ def run_ours(args):
     inp = make_inputs(rank, N_MSGS)
     ops, users = inp["ops"], inp["users"]
     ctx = api.Context(local)
-    stream = torch.cuda.Stream(device=dev)
+    stream = torch.cuda.Stream(device=dev, priority=-1)         # (the library's side stream is created at the lowest priority)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_profiling(True)
     ctx.set_swear_words(inp["words"])
@@ -336,7 +336,7 @@ def run_ours(args):
 
     def add_lane():
         c2 = api.Context(local)
-        s2 = torch.cuda.Stream(device=dev)
+        s2 = torch.cuda.Stream(device=dev, priority=-1)
         c2.set_stream(s2.cuda_stream); c2.set_profiling(True)
         c2.set_swear_words(inp["words"]); c2.set_ban_files(inp["sfile"], inp["ufile"])
         c2.set_users(users["room"], users["flags"], users["level"], inp["n_rooms"])
@@ -749,7 +749,7 @@ def run_config(args):
     peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    stream = torch.cuda.Stream(device=dev)
+    stream = torch.cuda.Stream(device=dev, priority=-1)         # (the library's side stream is created at the lowest priority)
     to_dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     pad16 = lambda a: np.concatenate([a, np.zeros(32, np.uint8)])
 

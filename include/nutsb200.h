@@ -155,7 +155,9 @@ int  nutsb_get_timing(const nutsb_ctx *ctx, nutsb_timing *out);
 /* 1 (default): k_render and k_direct run on a second stream beside the planning kernels and the
  * fan-out.  0: every kernel on one stream, so that each kernel's own duration can be timed alone. */
 int  nutsb_set_overlap(nutsb_ctx *ctx, int on);
-/* Use the caller's CUDA stream (a cudaStream_t) instead of the context's own. */
+/* Use the caller's CUDA stream (a cudaStream_t) instead of the context's own.  The context's own stream has the
+ * device's highest priority and its side stream (the renderer, beside the planning kernels) the lowest; a caller's
+ * stream created above the lowest priority keeps that order (cudaStreamCreateWithPriority). */
 int  nutsb_set_stream(nutsb_ctx *ctx, void *cuda_stream);
 
 /* Clones (nuts333.c:1416-1426): owner[u] = index of the owner of clone u, -1 for everybody else (clones are the

@@ -458,9 +458,14 @@ NUTSB_API int nutsb_create(nutsb_ctx **out, int device)
     c->device = device;
     int rc = [&]() -> int {
         CK(cudaSetDevice(device));
-        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        // the main stream at the highest priority, the side stream at the lowest: k_render runs BESIDE the planning
+        // kernels (small grids, bound by their own latency) -- when both have blocks waiting the planner's go first,
+        // the renderer fills what is left
+        int prio_least = 0, prio_greatest = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        CK(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
         CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-        CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_least));
         if (const char *e = getenv("NUTSB_SIDE_RENDER")) c->side_render = std::max(1, atoi(e));     // tuning aids
         if (const char *e = getenv("NUTSB_OVERLAP")) c->overlap = atoi(e) != 0;
         if (const char *e = getenv("NUTSB_FD_DIR_PER_SM")) c->fd_dir_per_sm = std::max(0, atoi(e));
