@@ -217,8 +217,9 @@ k_scan1(In in, Out out, i64 n_host, const u32 *n_dev, ScanState *state, u32 *tic
     {
         // look-back by the whole block, 256 tiles at a time: thread i looks at tile (hi - 1 - i); the window's sum is
         // everything up to and including the nearest tile that already knows its inclusive prefix.  (One warp and 32
-        // tiles a step was the first form: the prefix then travels 32 tiles per global-memory round trip, ~25 trips
-        // for the 733 tiles of a 3M-element scan.)
+        // tiles a step was the first form; by itself the wider window measured no faster -- the blocks were waiting
+        // for their own uncoalesced loads and stores, see above -- it is kept because it bounds the number of trips:
+        // 3 instead of 23 for the 733 tiles of a 3M-element scan.)
         __shared__ u32 s_incl[NUTSB_SCAN_THREADS / 32];
         __shared__ u64 s_part[NUTSB_SCAN_THREADS / 32];
         const unsigned long long fa = ((unsigned long long)epoch << 2) | 1ull, fi = ((unsigned long long)epoch << 2) | 2ull;
